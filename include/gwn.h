@@ -1,0 +1,189 @@
+/*
+ * libgwn — C ABI of the B200-native (sm_100a) Graph WaveNet block.
+ *
+ * Drop-in boundary: the reference has no FFI layer; the unit being replaced is the
+ * `gwnet` nn.Module of models/graph_wavenet.py:100-256.  Each entry
+ * point below names the reference lines whose arithmetic it replaces.  The Python
+ * host (multimodal_outage_b200/ops.py) binds these with ctypes and registers them as
+ * torch.library custom ops; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless noted;
+ *  - the caller owns all memory (outputs, saved tensors, workspaces);
+ *  - `stream` is a cudaStream_t passed as void*; entry points are re-entrant (the
+ *    backward runs on an autograd worker thread);
+ *  - return 0 on success, <0 on error; gwn_last_error() returns a thread-local message;
+ *  - sm_100 only: any other device is an error, there is no fallback;
+ *  - activations inside the block are "channels-last": [N, L, V, 32] (batch, time,
+ *    node, channel), dtype GWN_F32 or GWN_BF16; parameters, statistics and gradients
+ *    of parameters are always fp32.  The channel width (residual = dilation channels)
+ *    is fixed at 32, the value every reference/BASELINE configuration uses
+ *    (graph_wavenet.py:101).
+ */
+#ifndef GWN_H
+#define GWN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GWN_C 32            /* residual_channels == dilation_channels */
+#define GWN_MAX_SUPPORTS 4  /* fixed supports + adaptive */
+#define GWN_MAX_TAPS 8      /* temporal kernel_size */
+#define GWN_MAX_LAYERS 32
+
+enum { GWN_F32 = 0, GWN_BF16 = 1 };
+
+const char* gwn_last_error(void);
+int gwn_version(void);
+/* 0 if the current device is sm_100 (B200); <0 otherwise. */
+int gwn_check_device(void);
+
+/* ---- adaptive adjacency: softmax(relu(E1 @ E2), dim=1)   graph_wavenet.py:202 ---- */
+/* e1 [V,R], e2 [R,V], adp [V,V] fp32 row-major (adp[v,w]); adp_t optional transpose copy. */
+int gwn_adp_fwd(const float* e1, const float* e2, float* adp, float* adp_t, int V, int R, void* stream);
+/* d_adp [V,V] -> d_e1 [V,R], d_e2 [R,V] (overwritten). ws: V*V floats. */
+int gwn_adp_bwd(const float* e1, const float* e2, const float* adp, const float* d_adp,
+                float* d_e1, float* d_e2, float* ws, int V, int R, void* stream);
+
+/* ---- start_conv (1x1, Cin->32) + left zero pad + NCHW -> channels-last
+ *      graph_wavenet.py:191-196 ---- */
+/* x [N,Cin,V,T] fp32 NCHW; w [32,Cin]; b [32]; u0 [N,L0,V,32] (dtype), L0 >= T. */
+int gwn_start_fwd(const float* x, const float* w, const float* b, void* u0, int dtype,
+                  int N, int Cin, int V, int T, int L0, void* stream);
+/* du0 [N,L0,V,32] -> dw [32,Cin], db [32] (overwritten), dx [N,Cin,V,T] (optional, may be NULL). */
+int gwn_start_bwd(const float* x, const float* w, const void* du0, int dtype, float* dw, float* db,
+                  float* dx, int N, int Cin, int V, int T, int L0, void* stream);
+
+/* ---- one WaveNet layer  graph_wavenet.py:206-250 ----
+ * forward:  r = bn_prev(u_prev)  (folded affine: r = u_prev*scale + shift, NULL = identity)
+ *           (f,g) = dilated conv k taps  (:222,224)      z = tanh(f)*sigmoid(g)  (:223-226)
+ *           z_last = z[:, -Lf:]  (the only part of z the skip path keeps, :231-236)
+ *           h = mlp(concat[z, zA0, zA0^2, ...]) + bm     (gcn, :85-96; nconv :65)
+ *           h = dropout(h)                               (:97)
+ *           u = h + r[:, -Lout:]                         (:247)
+ *           stats = per-channel (sum u, sum u^2)         (training BatchNorm, :250)
+ */
+typedef struct {
+  int N, V, Lin, Lout, Lf;      /* Lout = Lin - dilation*(taps-1); Lf = final time length */
+  int taps, dilation;
+  int n_supports, order;        /* n_supports = 0 with mlp_in = 32: gcn_bool=False path (:245) */
+  int dtype;                    /* GWN_F32 / GWN_BF16: storage of activations */
+  int training;                 /* save a,b for backward */
+  int has_gconv;                /* 0: stop after z/z_last (eval-mode last layer) */
+  float dropout_p;              /* 0 disables */
+  uint64_t seed, offset;        /* Philox key/offset for the fused dropout mask */
+} gwn_layer_cfg;
+
+typedef struct {
+  const void* u_prev;           /* [N,Lin,V,32] */
+  const float* scale;           /* [32] or NULL */
+  const float* shift;           /* [32] or NULL */
+  const float* w_fg;            /* packed [taps*32, 64]: row (j,c), col 2o = filter, 2o+1 = gate */
+  const float* b_fg;            /* [64] interleaved */
+  const float* w_mlp;           /* packed [mlp_in, 32] = mlp.weight[:, :, 0, 0]^T, mlp_in = 32*(1+order*n_supports) */
+  const float* b_mlp;           /* [32] */
+  const float* supports[GWN_MAX_SUPPORTS];   /* each [V,V] fp32, A[v,w] */
+  const void* drop_mask;        /* optional explicit mask [N,Lout,V,32] (dtype); overrides Philox */
+  const uint64_t* rng;          /* optional DEVICE {seed, offset}: overrides cfg.seed, added to cfg.offset
+                                   (keeps the mask fresh across CUDA-graph replays) */
+  void* a;                      /* out (training) tanh(f)   [N,Lout,V,32] */
+  void* b;                      /* out (training) sigmoid(g) */
+  void* z_last;                 /* out [N,Lf,V,32] */
+  void* u;                      /* out [N,Lout,V,32] */
+  double* stats;                /* out [2,32]: sum, sum of squares (zeroed by callee) */
+  void* ws_cat;                 /* workspace [N*Lout*V, 32*(1+order*n_supports)] (dtype) */
+} gwn_layer_fwd_args;
+
+int gwn_layer_fwd(const gwn_layer_cfg* cfg, const gwn_layer_fwd_args* args, void* stream);
+
+typedef struct {
+  /* saved from forward */
+  const void* u_prev; const float* scale; const float* shift;
+  const float* w_fg; const float* w_mlp;
+  const float* supports[GWN_MAX_SUPPORTS];
+  int support_needs_grad[GWN_MAX_SUPPORTS];
+  const void* drop_mask;
+  const uint64_t* rng;
+  const void* a; const void* b;
+  /* incoming gradients */
+  const void* du;               /* [N,Lout,V,32] (dtype) or NULL (dead gconv: last layer) */
+  const void* dz_last;          /* [N,Lf,V,32] (dtype) or NULL */
+  /* outputs */
+  float* dx_prev;               /* [N,Lin,V,32] fp32: grad wrt r = bn_prev(u_prev) */
+  double* dx_stats;             /* [2,32]: sum dx, sum dx*u_prev (zeroed by callee) */
+  float* dw_fg; float* db_fg;   /* [taps*32,64], [64] (overwritten) */
+  float* dw_mlp; float* db_mlp; /* packed [mlp_in, 32], [32] (overwritten) */
+  float* d_supports[GWN_MAX_SUPPORTS];   /* [V,V] fp32, ACCUMULATED into (caller zeroes) */
+  /* workspaces */
+  void* ws_cat;                 /* [P, mlp_in] (dtype): recomputed hops */
+  void* ws_dcat;                /* [P, mlp_in] (dtype): grads of the concat */
+  float* ws_dfg;                /* [P, 64] fp32 */
+} gwn_layer_bwd_args;
+
+int gwn_layer_bwd(const gwn_layer_cfg* cfg, const gwn_layer_bwd_args* args, void* stream);
+
+/* ---- BatchNorm2d(32) folded to an affine  graph_wavenet.py:167,250 ----
+ * training: mean/var from stats (count = N*L*V), scale = gamma*rstd, shift = beta - mean*scale,
+ *           running <- (1-m)*running + m*(mean, unbiased var); saves mean,rstd.
+ * eval:     scale/shift from the running statistics. */
+int gwn_bn_fold(const double* stats, double count, const float* gamma, const float* beta,
+                float* running_mean, float* running_var, float momentum, float eps, int training,
+                float* scale, float* shift, float* mean, float* rstd, void* stream);
+/* du = BN backward of dx (grad wrt BN output) given u, mean, rstd and dx_stats=(sum dx, sum dx*u).
+ * training=0: du = dx*scale.  dgamma,dbeta [32] overwritten.  du has dtype `dtype`. */
+int gwn_bn_bwd(const float* dx, const void* u, int dtype, const double* dx_stats, double count,
+               const float* gamma, const float* mean, const float* rstd, int training,
+               void* du, float* dgamma, float* dbeta, long long rows, void* stream);
+
+/* ---- head: relu(sum_i Ws_i z_last_i + bs) -> relu(end_conv_1) -> end_conv_2 -> NCHW
+ *      graph_wavenet.py:231-236 (skip identity), :252-254 ---- */
+typedef struct {
+  int N, V, Lf, n_layers, S, E, O;   /* skip, end, out channels; S,E multiples of 32 */
+  int dtype;
+} gwn_head_cfg;
+typedef struct {
+  const void* z_last[GWN_MAX_LAYERS];  /* each [N,Lf,V,32] */
+  const float* w_skip;    /* packed [32*n_layers, S]  (row (i,c)) */
+  const float* b_skip;    /* [S] = sum_i bs_i */
+  const float* w_end1;    /* packed [S, E] (= end_conv_1.weight^T) */
+  const float* b_end1;    /* [E] */
+  const float* w_end2;    /* packed [E, Opad] zero-padded, Opad = 32*ceil(O/32) */
+  const float* b_end2;    /* [Opad] */
+  float* s1;              /* out/saved [P,S] fp32  relu(skip) */
+  float* e1;              /* out/saved [P,E] fp32  relu(end_conv_1) */
+  float* out;             /* out [N,O,V,Lf] fp32 NCHW */
+  float* ws;              /* workspace [P,Opad] fp32 */
+} gwn_head_fwd_args;
+int gwn_head_fwd(const gwn_head_cfg* cfg, const gwn_head_fwd_args* a, void* stream);
+typedef struct {
+  const void* z_last[GWN_MAX_LAYERS];
+  const float* w_skip; const float* w_end1; const float* w_end2;
+  const float* s1; const float* e1;
+  const float* dout;      /* [N,O,V,Lf] fp32 NCHW */
+  float* dw_skip; float* db_skip; float* dw_end1; float* db_end1; float* dw_end2; float* db_end2;
+  void* dz_last[GWN_MAX_LAYERS];       /* out, each [N,Lf,V,32] (dtype) */
+  float* ws_do;           /* [P,Opad] */
+  float* ws_de1;          /* [P,E] */
+  float* ws_ds1;          /* [P,S] */
+} gwn_head_bwd_args;
+int gwn_head_bwd(const gwn_head_cfg* cfg, const gwn_head_bwd_args* a, void* stream);
+
+/* ---- nconv primitive, exposed for unit tests  graph_wavenet.py:60-66 ----
+ * y[s,w,c] = sum_v x[s,v,c] * A[v,w] (transpose_a=0) or A[w,v] (transpose_a=1);
+ * x,y: [slabs, V, pitch] slots of 32 channels at column offsets xoff/yoff. */
+int gwn_node_mix(const void* x, int x_pitch, int x_off, void* y, int y_pitch, int y_off, int accumulate,
+                 const float* A, int transpose_a, int slabs, int V, int dtype, void* stream);
+
+/* ---- data-parallel gradient all-reduce over NCCL (absent in the reference) ---- */
+int gwn_comm_unique_id(void* out128);                       /* host buffer, 128 bytes */
+int gwn_comm_init(const void* id128, int rank, int world);  /* host */
+int gwn_comm_allreduce_avg(float* buf, long long count, void* stream);
+int gwn_comm_destroy(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GWN_H */

@@ -1,0 +1,117 @@
+"""ctypes binding of libgwn.so (the C ABI declared in include/gwn.h).
+
+There is no CPU or eager fallback: if the shared library is missing or a call
+fails, an exception is raised (``GwnError``)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libgwn.so')
+
+GWN_F32, GWN_BF16 = 0, 1
+MAX_SUPPORTS, MAX_TAPS, MAX_LAYERS = 4, 8, 32
+
+vp = C.c_void_p
+
+
+class GwnError(RuntimeError):
+    pass
+
+
+class LayerCfg(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ('N', 'V', 'Lin', 'Lout', 'Lf', 'taps', 'dilation', 'n_supports', 'order',
+                                       'dtype', 'training', 'has_gconv')] + \
+               [('dropout_p', C.c_float), ('seed', C.c_uint64), ('offset', C.c_uint64)]
+
+
+class LayerFwdArgs(C.Structure):
+    _fields_ = [('u_prev', vp), ('scale', vp), ('shift', vp), ('w_fg', vp), ('b_fg', vp), ('w_mlp', vp),
+                ('b_mlp', vp), ('supports', vp * MAX_SUPPORTS), ('drop_mask', vp), ('rng', vp), ('a', vp), ('b', vp),
+                ('z_last', vp), ('u', vp), ('stats', vp), ('ws_cat', vp)]
+
+
+class LayerBwdArgs(C.Structure):
+    _fields_ = [('u_prev', vp), ('scale', vp), ('shift', vp), ('w_fg', vp), ('w_mlp', vp),
+                ('supports', vp * MAX_SUPPORTS), ('support_needs_grad', C.c_int * MAX_SUPPORTS),
+                ('drop_mask', vp), ('rng', vp), ('a', vp), ('b', vp), ('du', vp), ('dz_last', vp), ('dx_prev', vp),
+                ('dx_stats', vp), ('dw_fg', vp), ('db_fg', vp), ('dw_mlp', vp), ('db_mlp', vp),
+                ('d_supports', vp * MAX_SUPPORTS), ('ws_cat', vp), ('ws_dcat', vp), ('ws_dfg', vp)]
+
+
+class HeadCfg(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ('N', 'V', 'Lf', 'n_layers', 'S', 'E', 'O', 'dtype')]
+
+
+class HeadFwdArgs(C.Structure):
+    _fields_ = [('z_last', vp * MAX_LAYERS), ('w_skip', vp), ('b_skip', vp), ('w_end1', vp), ('b_end1', vp),
+                ('w_end2', vp), ('b_end2', vp), ('s1', vp), ('e1', vp), ('out', vp), ('ws', vp)]
+
+
+class HeadBwdArgs(C.Structure):
+    _fields_ = [('z_last', vp * MAX_LAYERS), ('w_skip', vp), ('w_end1', vp), ('w_end2', vp), ('s1', vp),
+                ('e1', vp), ('dout', vp), ('dw_skip', vp), ('db_skip', vp), ('dw_end1', vp), ('db_end1', vp),
+                ('dw_end2', vp), ('db_end2', vp), ('dz_last', vp * MAX_LAYERS), ('ws_do', vp), ('ws_de1', vp),
+                ('ws_ds1', vp)]
+
+
+# every symbol include/gwn.h declares: name -> (restype, argtypes)
+_i, _ll, _f, _d = C.c_int, C.c_longlong, C.c_float, C.c_double
+SIGNATURES = {
+    'gwn_last_error': (C.c_char_p, []),
+    'gwn_version': (_i, []),
+    'gwn_check_device': (_i, []),
+    'gwn_adp_fwd': (_i, [vp, vp, vp, vp, _i, _i, vp]),
+    'gwn_adp_bwd': (_i, [vp, vp, vp, vp, vp, vp, vp, _i, _i, vp]),
+    'gwn_start_fwd': (_i, [vp, vp, vp, vp, _i, _i, _i, _i, _i, _i, vp]),
+    'gwn_start_bwd': (_i, [vp, vp, vp, _i, vp, vp, vp, _i, _i, _i, _i, _i, vp]),
+    'gwn_layer_fwd': (_i, [C.POINTER(LayerCfg), C.POINTER(LayerFwdArgs), vp]),
+    'gwn_layer_bwd': (_i, [C.POINTER(LayerCfg), C.POINTER(LayerBwdArgs), vp]),
+    'gwn_bn_fold': (_i, [vp, _d, vp, vp, vp, vp, _f, _f, _i, vp, vp, vp, vp, vp]),
+    'gwn_bn_bwd': (_i, [vp, vp, _i, vp, _d, vp, vp, vp, _i, vp, vp, vp, _ll, vp]),
+    'gwn_head_fwd': (_i, [C.POINTER(HeadCfg), C.POINTER(HeadFwdArgs), vp]),
+    'gwn_head_bwd': (_i, [C.POINTER(HeadCfg), C.POINTER(HeadBwdArgs), vp]),
+    'gwn_node_mix': (_i, [vp, _i, _i, vp, _i, _i, _i, vp, _i, _i, _i, _i, vp]),
+    'gwn_comm_unique_id': (_i, [vp]),
+    'gwn_comm_init': (_i, [vp, _i, _i]),
+    'gwn_comm_allreduce_avg': (_i, [vp, _ll, vp]),
+    'gwn_comm_destroy': (_i, []),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libgwn.so (once).  Raises GwnError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GwnError(f'{LIB_PATH} is missing: build it with `python -m multimodal_outage_b200.build` '
+                           '(there is no fallback path)')
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)          # AttributeError if a declared symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().gwn_last_error()
+        raise GwnError(f'{what} failed ({rc}): {msg.decode() if msg else "?"}')
+
+
+_device_ok = set()
+
+
+def require_b200(device_index: int) -> None:
+    """The kernels are sm_100a-only; anything else is an error, not a fallback."""
+    if device_index in _device_ok:
+        return
+    import torch
+    with torch.cuda.device(device_index):
+        check(lib().gwn_check_device(), 'gwn_check_device')
+    _device_ok.add(device_index)

@@ -1,0 +1,66 @@
+"""Builds libgwn.so (hand-written sm_100a CUDA, plain C ABI) in-tree with nvcc.
+
+No torch C++ extension: the library has no torch types in its signatures
+(include/gwn.h), so it is compiled with plain ``nvcc -shared`` and bound via ctypes.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+LIB = os.path.join(HERE, 'libgwn.so')
+STAMP = os.path.join(HERE, 'libgwn.so.stamp')
+SOURCES = ['api.cu', 'adp.cu', 'layer.cu', 'head.cu', 'comm.cu']
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
+              '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr', '-Xptxas', '-v']
+
+
+def _fingerprint() -> str:
+    h = hashlib.sha256()
+    for root in (CSRC, os.path.join(HERE, '..', 'include')):
+        for fn in sorted(os.listdir(root)):
+            if fn.endswith(('.cu', '.cuh', '.h')):
+                h.update(fn.encode())
+                h.update(open(os.path.join(root, fn), 'rb').read())
+    h.update(' '.join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    fp = _fingerprint()
+    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read() == fp:
+        return LIB
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    objs = []
+    procs = []
+    os.makedirs(os.path.join(HERE, 'build'), exist_ok=True)
+    for src in SOURCES:
+        obj = os.path.join(HERE, 'build', src.replace('.cu', '.o'))
+        objs.append(obj)
+        cmd = [nvcc, *NVCC_FLAGS, '-c', os.path.join(CSRC, src), '-o', obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = []
+    for src, p in procs:
+        out, _ = p.communicate()
+        log.append(f'== {src}\n{out}')
+        if p.returncode != 0:
+            raise RuntimeError(f'nvcc failed on {src}:\n{out}')
+    link = [nvcc, '-shared', '-o', LIB, *objs, '-lcudart', '-ldl']
+    r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f'link failed:\n{r.stdout}')
+    with open(os.path.join(HERE, 'build', 'ptxas.log'), 'w') as f:
+        f.write('\n'.join(log))
+    with open(STAMP, 'w') as f:
+        f.write(fp)
+    if verbose:
+        print('\n'.join(log))
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

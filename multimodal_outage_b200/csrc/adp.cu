@@ -1,0 +1,145 @@
+// Adaptive adjacency  adp = softmax(relu(E1 @ E2), dim=1)   (graph_wavenet.py:202), fp32 always.
+// Warp-per-row: the rank-R product, relu, row max, exp, row sum and normalisation never leave
+// registers/shuffles.  Backward:
+//   dR = P * (dP - rowsum(dP*P)),  dM = dR * [M > 0],  dE1 = dM E2^T,  dE2 = E1^T dM.
+#include "common.cuh"
+
+namespace gwn {
+
+constexpr int ADP_MAX_R = 16;
+
+__global__ void __launch_bounds__(256) adp_fwd_kernel(const float* __restrict__ e1, const float* __restrict__ e2,
+                                                      float* __restrict__ adp, float* __restrict__ adp_t, int V,
+                                                      int R) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= V) return;
+  float a[ADP_MAX_R];
+#pragma unroll
+  for (int r = 0; r < ADP_MAX_R; ++r) a[r] = r < R ? __ldg(e1 + (long long)row * R + r) : 0.f;
+  float mx = 0.f;  // relu output is >= 0, so 0 is a valid lower bound only if a 0 exists; track true max
+  mx = -INFINITY;
+  for (int j = lane; j < V; j += 32) {
+    float m = 0.f;
+#pragma unroll
+    for (int r = 0; r < ADP_MAX_R; ++r)
+      if (r < R) m = fmaf(a[r], __ldg(e2 + (long long)r * V + j), m);
+    m = fmaxf(m, 0.f);
+    adp[(long long)row * V + j] = m;  // stash relu(M); overwritten below
+    mx = fmaxf(mx, m);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < V; j += 32) {
+    float e = expf(adp[(long long)row * V + j] - mx);
+    adp[(long long)row * V + j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  for (int j = lane; j < V; j += 32) {
+    float pv = adp[(long long)row * V + j] * inv;
+    adp[(long long)row * V + j] = pv;
+    if (adp_t) adp_t[(long long)j * V + row] = pv;
+  }
+}
+
+// one warp per row: dM row -> ws, dE1 row
+__global__ void __launch_bounds__(256) adp_bwd_rows_kernel(const float* __restrict__ e1,
+                                                           const float* __restrict__ e2,
+                                                           const float* __restrict__ adp,
+                                                           const float* __restrict__ dadp,
+                                                           float* __restrict__ de1, float* __restrict__ dm, int V,
+                                                           int R) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= V) return;
+  float a[ADP_MAX_R], acc[ADP_MAX_R];
+#pragma unroll
+  for (int r = 0; r < ADP_MAX_R; ++r) { a[r] = r < R ? __ldg(e1 + (long long)row * R + r) : 0.f; acc[r] = 0.f; }
+  float dot = 0.f;
+  for (int j = lane; j < V; j += 32) dot = fmaf(dadp[(long long)row * V + j], adp[(long long)row * V + j], dot);
+  dot = warp_sum(dot);
+  for (int j = lane; j < V; j += 32) {
+    float m = 0.f;
+#pragma unroll
+    for (int r = 0; r < ADP_MAX_R; ++r)
+      if (r < R) m = fmaf(a[r], __ldg(e2 + (long long)r * V + j), m);
+    float pv = adp[(long long)row * V + j];
+    float g = (m > 0.f) ? pv * (dadp[(long long)row * V + j] - dot) : 0.f;
+    dm[(long long)row * V + j] = g;
+#pragma unroll
+    for (int r = 0; r < ADP_MAX_R; ++r)
+      if (r < R) acc[r] = fmaf(g, __ldg(e2 + (long long)r * V + j), acc[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < ADP_MAX_R; ++r) {
+    float s = warp_sum(acc[r]);
+    if (lane == 0 && r < R) de1[(long long)row * R + r] = s;
+  }
+}
+
+// dE2[r, j] = sum_i E1[i, r] dM[i, j]; grid (col tiles of 256, row splits), atomics into zeroed dE2
+__global__ void __launch_bounds__(256) adp_bwd_cols_kernel(const float* __restrict__ e1,
+                                                           const float* __restrict__ dm,
+                                                           float* __restrict__ de2, int V, int R,
+                                                           int rows_per_split) {
+  __shared__ float es[64][ADP_MAX_R];
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  const int ib = blockIdx.y * rows_per_split, ie = min(V, ib + rows_per_split);
+  float acc[ADP_MAX_R];
+#pragma unroll
+  for (int r = 0; r < ADP_MAX_R; ++r) acc[r] = 0.f;
+  for (int i0 = ib; i0 < ie; i0 += 64) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < 64 * ADP_MAX_R; t += 256) {
+      int ii = t / ADP_MAX_R, r = t % ADP_MAX_R;
+      es[ii][r] = (i0 + ii < ie && r < R) ? e1[(long long)(i0 + ii) * R + r] : 0.f;
+    }
+    __syncthreads();
+    if (j < V) {
+      const int lim = min(64, ie - i0);
+      for (int ii = 0; ii < lim; ++ii) {
+        float g = dm[(long long)(i0 + ii) * V + j];
+#pragma unroll
+        for (int r = 0; r < ADP_MAX_R; ++r) acc[r] = fmaf(es[ii][r], g, acc[r]);
+      }
+    }
+  }
+  if (j < V) {
+#pragma unroll
+    for (int r = 0; r < ADP_MAX_R; ++r)
+      if (r < R) atomicAdd(de2 + (long long)r * V + j, acc[r]);
+  }
+}
+
+}  // namespace gwn
+
+using namespace gwn;
+
+extern "C" int gwn_adp_fwd(const float* e1, const float* e2, float* adp, float* adp_t, int V, int R, void* stream) {
+  GWN_REQUIRE(e1 && e2 && adp && V >= 1 && R >= 1 && R <= ADP_MAX_R, "adp_fwd: bad argument (R=%d, max %d)", R,
+              ADP_MAX_R);
+  adp_fwd_kernel<<<(unsigned)cdiv(V, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(e1, e2, adp, adp_t, V, R);
+  GWN_LAUNCHED();
+  return 0;
+}
+
+extern "C" int gwn_adp_bwd(const float* e1, const float* e2, const float* adp, const float* d_adp, float* d_e1,
+                           float* d_e2, float* ws, int V, int R, void* stream) {
+  GWN_REQUIRE(e1 && e2 && adp && d_adp && d_e1 && d_e2 && ws && V >= 1 && R >= 1 && R <= ADP_MAX_R,
+              "adp_bwd: bad argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  adp_bwd_rows_kernel<<<(unsigned)cdiv(V, 8), 256, 0, st>>>(e1, e2, adp, d_adp, d_e1, ws, V, R);
+  GWN_LAUNCHED();
+  GWN_CUDA(cudaMemsetAsync(d_e2, 0, sizeof(float) * (size_t)R * V, st));
+  int col_tiles = (int)cdiv(V, 256);
+  int splits = (int)cdiv(148 * 2, col_tiles);
+  int per = (int)cdiv(V, splits);
+  per = (int)cdiv(per, 64) * 64;
+  splits = (int)cdiv(V, per);
+  dim3 grid(col_tiles, splits);
+  adp_bwd_cols_kernel<<<grid, 256, 0, st>>>(e1, ws, d_e2, V, R, per);
+  GWN_LAUNCHED();
+  return 0;
+}

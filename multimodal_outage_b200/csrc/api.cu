@@ -1,0 +1,29 @@
+// Error reporting, version and device gate of libgwn.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+
+namespace gwn {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace gwn
+
+extern "C" const char* gwn_last_error(void) { return gwn::g_err; }
+extern "C" int gwn_version(void) { return 100; }
+
+extern "C" int gwn_check_device(void) {
+  int dev = 0;
+  GWN_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  GWN_CUDA(cudaGetDeviceProperties(&prop, dev));
+  GWN_REQUIRE(prop.major == 10 && prop.minor == 0,
+              "libgwn is built for sm_100a (B200) only; device %d is sm_%d%d (%s) - no fallback path exists", dev,
+              prop.major, prop.minor, prop.name);
+  return 0;
+}

@@ -1,0 +1,116 @@
+// Shared helpers for libgwn (sm_100a only).  See include/gwn.h for the ABI.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gwn.h"
+
+namespace gwn {
+
+void set_error(const char* fmt, ...);
+
+#define GWN_REQUIRE(cond, ...)        \
+  do {                                \
+    if (!(cond)) {                    \
+      ::gwn::set_error(__VA_ARGS__);  \
+      return -1;                      \
+    }                                 \
+  } while (0)
+
+#define GWN_CUDA(expr)                                                         \
+  do {                                                                         \
+    cudaError_t e__ = (expr);                                                  \
+    if (e__ != cudaSuccess) {                                                  \
+      ::gwn::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr,            \
+                       cudaGetErrorString(e__));                               \
+      return -2;                                                               \
+    }                                                                          \
+  } while (0)
+
+#define GWN_LAUNCHED() GWN_CUDA(cudaPeekAtLastError())
+
+typedef __nv_bfloat16 bf16;
+
+static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
+
+// ---- 4-wide loads/stores of 32-channel rows (16 B fp32 / 8 B bf16) ----
+__device__ __forceinline__ void load4(const float* p, float v[4]) {
+  float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void load4(const bf16* p, float v[4]) {
+  uint2 t = *reinterpret_cast<const uint2*>(p);
+  float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&t.x));
+  float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&t.y));
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void store4(float* p, const float v[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store4(bf16* p, const float v[4]) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 t;
+  t.x = *reinterpret_cast<uint32_t*>(&a);
+  t.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = t;
+}
+__device__ __forceinline__ void load2(const float* p, float v[2]) {
+  float2 t = *reinterpret_cast<const float2*>(p);
+  v[0] = t.x; v[1] = t.y;
+}
+__device__ __forceinline__ void load2(const bf16* p, float v[2]) {
+  float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+  v[0] = a.x; v[1] = a.y;
+}
+__device__ __forceinline__ void store2(float* p, float a, float b) {
+  *reinterpret_cast<float2*>(p) = make_float2(a, b);
+}
+__device__ __forceinline__ void store2(bf16* p, float a, float b) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+__device__ __forceinline__ float ld1(const float* p) { return *p; }
+__device__ __forceinline__ float ld1(const bf16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void st1(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st1(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- Philox4x32-10 (counter-based RNG for the fused dropout mask) ----
+__device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t offset, uint64_t counter) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint32_t c0 = (uint32_t)counter, c1 = (uint32_t)(counter >> 32);
+  uint32_t c2 = (uint32_t)offset, c3 = (uint32_t)(offset >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+// keep-mask scale for 4 consecutive channels of element group `idx4` (= (row*32 + col)/4)
+__device__ __forceinline__ void dropout4(uint64_t seed, uint64_t offset, uint64_t idx4, float p,
+                                         float m[4]) {
+  uint4 r = philox4x32(seed, offset, idx4);
+  const float inv = 1.0f / (1.0f - p);
+  const float s = 2.3283064365386963e-10f;  // 2^-32
+  m[0] = (r.x * s >= p) ? inv : 0.f;
+  m[1] = (r.y * s >= p) ? inv : 0.f;
+  m[2] = (r.z * s >= p) ? inv : 0.f;
+  m[3] = (r.w * s >= p) ? inv : 0.f;
+}
+
+}  // namespace gwn

@@ -1,0 +1,615 @@
+// One Graph WaveNet layer (graph_wavenet.py:206-250), forward and backward, channels-last.
+//   gate  : fused BN-affine-on-load + dilated (1,k) filter & gate convs + tanh*sigmoid  (:222-226)
+//   hops  : nconv  y[s,w,c] = sum_v x[s,v,c] A[v,w]                                     (:60-66,:87-93)
+//   mlp   : 1x1 conv over the never-materialised-in-NCHW concat + bias + dropout        (:95-97)
+//           + residual add with the cropped, BN-folded input (:247) + BN statistics     (:250)
+#include "gemm.cuh"
+
+namespace gwn {
+
+// ------------------------------------------------------------------------------------------ epilogues
+template <typename T>
+struct EpiGate {
+  static constexpr bool kStats = false;
+  double* stats;
+  const float* bias;  // [64] interleaved (f0,g0,f1,g1,...)
+  T* zcat; int zpitch;
+  T* a; T* b;
+  T* z_last; long long last_begin, last_rows;
+  __device__ __forceinline__ void apply(long long p, long long n, long long rem, int col, float v[4],
+                                        float*, float*) const {
+    const int o = col >> 1;
+    float f0 = v[0] + __ldg(bias + col), g0 = v[1] + __ldg(bias + col + 1);
+    float f1 = v[2] + __ldg(bias + col + 2), g1 = v[3] + __ldg(bias + col + 3);
+    float a0 = tanhf(f0), a1 = tanhf(f1);
+    float b0 = 1.f / (1.f + expf(-g0)), b1 = 1.f / (1.f + expf(-g1));
+    float z0 = a0 * b0, z1 = a1 * b1;
+    store2(zcat + p * zpitch + o, z0, z1);
+    if (a) { store2(a + p * 32 + o, a0, a1); store2(b + p * 32 + o, b0, b1); }
+    if (z_last && rem >= last_begin) store2(z_last + (n * last_rows + rem - last_begin) * 32 + o, z0, z1);
+  }
+};
+
+template <typename T>
+struct EpiMlp {
+  static constexpr bool kStats = true;
+  double* stats;
+  const float* bias;
+  const T* u_prev; long long prev_rows_per_n, crop; const float* scale; const float* shift;
+  const T* mask; float drop_p; uint64_t seed, offset; const uint64_t* rng;
+  T* u;
+  __device__ __forceinline__ void apply(long long p, long long n, long long rem, int col, float v[4],
+                                        float s1[4], float s2[4]) const {
+    float h[4], r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = v[j] + __ldg(bias + col + j);
+    if (mask) {
+      float m[4]; load4(mask + p * 32 + col, m);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h[j] *= m[j];
+    } else if (drop_p > 0.f) {
+      const uint64_t sd = rng ? __ldg(rng) : seed;
+      const uint64_t of = rng ? offset + __ldg(rng + 1) : offset;
+      float m[4]; dropout4(sd, of, (uint64_t)(p * 8 + (col >> 2)), drop_p, m);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h[j] *= m[j];
+    }
+    load4(u_prev + (n * prev_rows_per_n + rem + crop) * 32 + col, r);
+    if (scale) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r[j] = fmaf(r[j], __ldg(scale + col + j), __ldg(shift + col + j));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { h[j] += r[j]; s1[j] += h[j]; s2[j] += h[j] * h[j]; }
+    store4(u + p * 32 + col, h);
+  }
+};
+
+template <typename T>
+struct EpiStoreT {  // plain store into a pitched T buffer
+  static constexpr bool kStats = false;
+  double* stats;
+  T* out; int pitch;
+  __device__ __forceinline__ void apply(long long p, long long, long long, int col, float v[4], float*,
+                                        float*) const {
+    store4(out + p * pitch + col, v);
+  }
+};
+
+template <typename T>
+struct EpiGateBwdData {  // dx = acc + du(cropped rows); stats = (sum dx, sum dx*u_prev)
+  static constexpr bool kStats = true;
+  double* stats;
+  const T* du; long long du_rows_per_n, crop;
+  const T* u_prev;
+  float* dx;
+  __device__ __forceinline__ void apply(long long p, long long n, long long rem, int col, float v[4],
+                                        float s1[4], float s2[4]) const {
+    if (du && rem >= crop) {
+      float g[4]; load4(du + (n * du_rows_per_n + rem - crop) * 32 + col, g);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] += g[j];
+    }
+    float up[4]; load4(u_prev + p * 32 + col, up);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { s1[j] += v[j]; s2[j] += v[j] * up[j]; }
+    store4(dx + p * 32 + col, v);
+  }
+};
+
+// ------------------------------------------------------------------------------------------ nconv
+// Y[s, w, yoff+c] (+)= sum_v Aop(v,w) * X[s, v, xoff+c];  Aop(v,w) = TR ? A[w*V+v] : A[v*V+w].
+// Tile: (16*TM) w-rows x 64 cols (2 slabs x 32 ch), K-step 16 nodes; 256 threads, TMx4 per thread.
+template <typename T, int TM, bool TR>
+__global__ void __launch_bounds__(256) node_mix_kernel(const T* __restrict__ X, int xp, int xoff,
+                                                       T* __restrict__ Y, int yp, int yoff, int accumulate,
+                                                       const float* __restrict__ A, int slabs, int V) {
+  constexpr int BMW = 16 * TM, BK = 16;
+  __shared__ __align__(16) float As[BK][BMW + 4];
+  __shared__ __align__(16) float Xs[BK][64];
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  const int w0 = blockIdx.y * BMW;
+  const long long s0 = (long long)blockIdx.x * 2;
+  float acc[TM][4];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int xk = tid / 16, xc = (tid % 16) * 4;      // X tile loader: row kk, 4 cols
+  const long long xs = s0 + xc / 32;
+  const int xcc = xc % 32;
+  for (int v0 = 0; v0 < V; v0 += BK) {
+    for (int i = tid; i < BK * BMW; i += 256) {
+      int kk, m;
+      if (TR) { kk = i % BK; m = i / BK; } else { m = i % BMW; kk = i / BMW; }
+      int v = v0 + kk, w = w0 + m;
+      float val = 0.f;
+      if (v < V && w < V) val = TR ? __ldg(A + (long long)w * V + v) : __ldg(A + (long long)v * V + w);
+      As[kk][m] = val;
+    }
+    {
+      float xv[4] = {0.f, 0.f, 0.f, 0.f};
+      int v = v0 + xk;
+      if (v < V && xs < slabs) load4(X + (xs * V + v) * (long long)xp + xoff + xcc, xv);
+      *reinterpret_cast<float4*>(&Xs[xk][xc]) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+      float4 x = *reinterpret_cast<const float4*>(&Xs[kk][tx * 4]);
+#pragma unroll
+      for (int i = 0; i < TM; ++i) {
+        acc[i][0] = fmaf(a[i], x.x, acc[i][0]);
+        acc[i][1] = fmaf(a[i], x.y, acc[i][1]);
+        acc[i][2] = fmaf(a[i], x.z, acc[i][2]);
+        acc[i][3] = fmaf(a[i], x.w, acc[i][3]);
+      }
+    }
+    __syncthreads();
+  }
+  const long long s = s0 + (tx * 4) / 32;
+  const int c = (tx * 4) % 32;
+  if (s < slabs) {
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      int w = w0 + ty * TM + i;
+      if (w < V) {
+        T* dst = Y + (s * V + w) * (long long)yp + yoff + c;
+        if (accumulate) {
+          float o[4]; load4(dst, o);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] += o[j];
+        }
+        store4(dst, acc[i]);
+      }
+    }
+  }
+}
+
+template <typename T>
+int launch_node_mix(const T* X, int xp, int xoff, T* Y, int yp, int yoff, int accumulate, const float* A,
+                    bool transpose_a, long long slabs, int V, cudaStream_t st) {
+  if (slabs <= 0) return 0;
+  const bool small = V <= 80;
+  const int bmw = small ? 80 : 64;
+  dim3 grid((unsigned)cdiv(slabs, 2), (unsigned)cdiv(V, bmw));
+  GWN_REQUIRE(grid.y <= 65535u, "node_mix: V too large");
+#define GWN_NM(TM, TR) \
+  node_mix_kernel<T, TM, TR><<<grid, 256, 0, st>>>(X, xp, xoff, Y, yp, yoff, accumulate, A, (int)slabs, V)
+  if (small) { if (transpose_a) GWN_NM(5, true); else GWN_NM(5, false); }
+  else       { if (transpose_a) GWN_NM(4, true); else GWN_NM(4, false); }
+#undef GWN_NM
+  GWN_LAUNCHED();
+  return 0;
+}
+
+// dA[v,w] += sum_{s,c} X[s,v,xoff+c] * G[s,w,goff+c]     (nconv weight-grad, adaptive support only)
+template <typename T>
+__global__ void __launch_bounds__(256) dadj_kernel(const T* __restrict__ X, int xp, int xoff,
+                                                   const T* __restrict__ G, int gp, int goff,
+                                                   float* __restrict__ dA, int slabs, int V,
+                                                   int slabs_per_split) {
+  __shared__ __align__(16) float Xs[32][68];
+  __shared__ __align__(16) float Gs[32][68];
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  const int v0 = blockIdx.x * 64, w0 = blockIdx.y * 64;
+  int sb = blockIdx.z * slabs_per_split, se = min(slabs, sb + slabs_per_split);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int lr = tid % 64, lc = (tid / 64) * 8;
+  for (int s = sb; s < se; ++s) {
+    float xv[8], gv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { xv[i] = 0.f; gv[i] = 0.f; }
+    if (v0 + lr < V) {
+      const T* src = X + ((long long)s * V + v0 + lr) * xp + xoff + lc;
+      load4(src, xv); load4(src + 4, xv + 4);
+    }
+    if (w0 + lr < V) {
+      const T* src = G + ((long long)s * V + w0 + lr) * gp + goff + lc;
+      load4(src, gv); load4(src + 4, gv + 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { Xs[lc + i][lr] = xv[i]; Gs[lc + i][lr] = gv[i]; }
+    __syncthreads();
+#pragma unroll 8
+    for (int c = 0; c < 32; ++c) {
+      float4 x = *reinterpret_cast<const float4*>(&Xs[c][ty * 4]);
+      float4 g = *reinterpret_cast<const float4*>(&Gs[c][tx * 4]);
+      float xa[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[i][0] = fmaf(xa[i], g.x, acc[i][0]);
+        acc[i][1] = fmaf(xa[i], g.y, acc[i][1]);
+        acc[i][2] = fmaf(xa[i], g.z, acc[i][2]);
+        acc[i][3] = fmaf(xa[i], g.w, acc[i][3]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int v = v0 + ty * 4 + i;
+    if (v >= V) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int w = w0 + tx * 4 + j;
+      if (w < V) atomicAdd(dA + (long long)v * V + w, acc[i][j]);
+    }
+  }
+}
+
+template <typename T>
+int launch_dadj(const T* X, int xp, int xoff, const T* G, int gp, int goff, float* dA, long long slabs, int V,
+                cudaStream_t st) {
+  if (slabs <= 0) return 0;
+  long long tiles = cdiv(V, 64) * cdiv(V, 64);
+  long long want = cdiv(148 * 4, tiles);
+  long long splits = want > slabs ? slabs : (want < 1 ? 1 : want);
+  long long per = cdiv(slabs, splits);
+  splits = cdiv(slabs, per);
+  dim3 grid((unsigned)cdiv(V, 64), (unsigned)cdiv(V, 64), (unsigned)splits);
+  dadj_kernel<T><<<grid, 256, 0, st>>>(X, xp, xoff, G, gp, goff, dA, (int)slabs, V, (int)per);
+  GWN_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ elementwise
+// slot 0 of the concat buffer <- z = a*b  (backward recompute)
+template <typename T>
+__global__ void zfill_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ cat, int pitch,
+                             long long P) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * 8) return;
+  long long p = i >> 3; int c = (int)(i & 7) * 4;
+  float av[4], bv[4];
+  load4(a + p * 32 + c, av); load4(b + p * 32 + c, bv);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) av[j] *= bv[j];
+  store4(cat + p * pitch + c, av);
+}
+
+// dh = du * dropout mask
+template <typename T>
+__global__ void drop_bwd_kernel(const T* __restrict__ du, const T* __restrict__ mask, float p_drop,
+                                uint64_t seed, uint64_t offset, const uint64_t* __restrict__ rng,
+                                T* __restrict__ dh, long long P) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * 8) return;
+  long long p = i >> 3; int c = (int)(i & 7) * 4;
+  float g[4], m[4];
+  load4(du + p * 32 + c, g);
+  if (mask) {
+    load4(mask + p * 32 + c, m);
+  } else {
+    const uint64_t sd = rng ? __ldg(rng) : seed;
+    const uint64_t of = rng ? offset + __ldg(rng + 1) : offset;
+    dropout4(sd, of, (uint64_t)i, p_drop, m);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) g[j] *= m[j];
+  store4(dh + p * 32 + c, g);
+}
+
+// dfg[p, 2c] = dz*b*(1-a^2) ; dfg[p, 2c+1] = dz*a*b*(1-b);  dz = dcat slot0 (+ dz_last on the tail rows)
+template <typename T>
+__global__ void gate_bwd_kernel(const T* __restrict__ dz, int dz_pitch, const T* __restrict__ dz_last,
+                                long long rows_per_n, long long last_begin, long long last_rows,
+                                const T* __restrict__ a, const T* __restrict__ b, float* __restrict__ dfg,
+                                long long P) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * 8) return;
+  long long p = i >> 3; int c = (int)(i & 7) * 4;
+  float g[4] = {0.f, 0.f, 0.f, 0.f}, av[4], bv[4];
+  if (dz) load4(dz + p * dz_pitch + c, g);
+  if (dz_last) {
+    long long n = p / rows_per_n, rem = p % rows_per_n;
+    if (rem >= last_begin) {
+      float t[4]; load4(dz_last + (n * last_rows + rem - last_begin) * 32 + c, t);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) g[j] += t[j];
+    }
+  }
+  load4(a + p * 32 + c, av); load4(b + p * 32 + c, bv);
+  float o[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    o[2 * j] = g[j] * bv[j] * (1.f - av[j] * av[j]);
+    o[2 * j + 1] = g[j] * av[j] * bv[j] * (1.f - bv[j]);
+  }
+  float* dst = dfg + p * 64 + 2 * c;
+  *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+  *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+}
+
+// ------------------------------------------------------------------------------------------ BatchNorm fold
+__global__ void bn_fold_kernel(const double* stats, double count, const float* gamma, const float* beta,
+                               float* running_mean, float* running_var, float momentum, float eps,
+                               int training, float* scale, float* shift, float* mean_out, float* rstd_out) {
+  int c = threadIdx.x;
+  if (c >= 32) return;
+  float mean, var;
+  if (training) {
+    double m = stats[c] / count;
+    double v = stats[32 + c] / count - m * m;
+    if (v < 0) v = 0;
+    mean = (float)m; var = (float)v;
+    double unbiased = count > 1 ? v * (count / (count - 1.0)) : v;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  } else {
+    mean = running_mean[c]; var = running_var[c];
+  }
+  float rstd = rsqrtf(var + eps);
+  if (training) rstd = (float)(1.0 / sqrt((double)var + (double)eps));
+  else rstd = 1.f / sqrtf(var + eps);
+  float sc = gamma[c] * rstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - mean * sc;
+  if (mean_out) { mean_out[c] = mean; rstd_out[c] = rstd; }
+}
+
+template <typename T>
+__global__ void bn_bwd_kernel(const float* __restrict__ dx, const T* __restrict__ u, const double* dx_stats,
+                              double count, const float* gamma, const float* mean, const float* rstd,
+                              int training, T* __restrict__ du, float* dgamma, float* dbeta, long long rows) {
+  __shared__ float k0[32], k1[32], k2[32];  // du = k0*dx + k1*u + k2
+  if (threadIdx.x < 32) {
+    int c = threadIdx.x;
+    double sdx = dx_stats[c], sdxu = dx_stats[32 + c];
+    double mu = mean[c], rs = rstd[c], g = gamma[c];
+    double sdxh = rs * (sdxu - mu * sdx);  // sum dx * xhat
+    if (blockIdx.x == 0) { dgamma[c] = (float)sdxh; dbeta[c] = (float)sdx; }
+    if (training) {
+      double m1 = sdx / count, m2 = sdxh / count;
+      // du = g*rs*(dx - m1 - xhat*m2),  xhat = (u-mu)*rs
+      k0[c] = (float)(g * rs);
+      k1[c] = (float)(-g * rs * m2 * rs);
+      k2[c] = (float)(-g * rs * (m1 - mu * rs * m2));
+    } else {
+      k0[c] = (float)(g * rs); k1[c] = 0.f; k2[c] = 0.f;
+    }
+  }
+  __syncthreads();
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * 8) return;
+  long long p = i >> 3; int c = (int)(i & 7) * 4;
+  float g[4], uv[4];
+  load4(dx + p * 32 + c, g); load4(u + p * 32 + c, uv);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) g[j] = k0[c + j] * g[j] + k1[c + j] * uv[j] + k2[c + j];
+  store4(du + p * 32 + c, g);
+}
+
+// ------------------------------------------------------------------------------------------ orchestration
+static int check_cfg(const gwn_layer_cfg* c) {
+  GWN_REQUIRE(c != nullptr, "layer cfg is NULL");
+  GWN_REQUIRE(c->dtype == GWN_F32 || c->dtype == GWN_BF16, "bad dtype %d", c->dtype);
+  GWN_REQUIRE(c->taps >= 1 && c->taps <= GWN_MAX_TAPS, "kernel_size %d unsupported (1..%d)", c->taps, GWN_MAX_TAPS);
+  GWN_REQUIRE(c->n_supports >= 0 && c->n_supports <= GWN_MAX_SUPPORTS, "n_supports %d > %d", c->n_supports,
+              GWN_MAX_SUPPORTS);
+  GWN_REQUIRE(c->order >= 1 && 1 + c->order * c->n_supports <= GEMM_MAX_CHUNKS, "order %d unsupported", c->order);
+  GWN_REQUIRE(c->Lout == c->Lin - c->dilation * (c->taps - 1) && c->Lout >= 1, "bad Lin/Lout %d/%d", c->Lin, c->Lout);
+  GWN_REQUIRE(c->Lf >= 1 && c->Lf <= c->Lout, "bad Lf %d", c->Lf);
+  GWN_REQUIRE(c->N >= 1 && c->V >= 1, "bad N/V");
+  return 0;
+}
+
+template <typename T>
+static int hops_forward(const gwn_layer_cfg* c, T* cat, int mlp_in, const float* const* supports,
+                        cudaStream_t st) {
+  const long long slabs = (long long)c->N * c->Lout;
+  for (int s = 0; s < c->n_supports; ++s)
+    for (int k = 1; k <= c->order; ++k) {
+      int slot = 1 + s * c->order + (k - 1);
+      int src = (k == 1) ? 0 : slot - 1;
+      if (int rc = launch_node_mix<T>(cat, mlp_in, src * 32, cat, mlp_in, slot * 32, 0, supports[s], false, slabs,
+                                      c->V, st))
+        return rc;
+    }
+  return 0;
+}
+
+template <typename T>
+static int layer_fwd_t(const gwn_layer_cfg* c, const gwn_layer_fwd_args* g, cudaStream_t st) {
+  const long long RO = (long long)c->Lout * c->V, RI = (long long)c->Lin * c->V;
+  const long long P = c->N * RO;
+  const int nslots = 1 + c->order * c->n_supports, mlp_in = 32 * nslots;
+  T* cat = reinterpret_cast<T*>(g->ws_cat);
+  // gate
+  GemmA A{};
+  A.n_chunks = c->taps; A.rows_per_n_out = RO; A.P = P;
+  for (int j = 0; j < c->taps; ++j) {
+    AChunk& ch = A.ch[j];
+    ch.base = g->u_prev; ch.rows_per_n = RI; ch.row_off = (long long)j * c->dilation * c->V;
+    ch.pitch = 32; ch.col_off = 0; ch.scale = g->scale; ch.shift = g->shift; ch.relu = 0;
+  }
+  EpiGate<T> eg{};
+  eg.bias = g->b_fg; eg.zcat = cat; eg.zpitch = mlp_in;
+  eg.a = c->training ? reinterpret_cast<T*>(g->a) : nullptr;
+  eg.b = c->training ? reinterpret_cast<T*>(g->b) : nullptr;
+  eg.z_last = reinterpret_cast<T*>(g->z_last);
+  eg.last_begin = (long long)(c->Lout - c->Lf) * c->V; eg.last_rows = (long long)c->Lf * c->V;
+  if (int rc = launch_pos_gemm<T, 64>(A, g->w_fg, 64, eg, st)) return rc;
+  if (!c->has_gconv) return 0;
+  // diffusion hops into the concat slots, then mlp + dropout + residual + stats
+  if (int rc = hops_forward<T>(c, cat, mlp_in, g->supports, st)) return rc;
+  GWN_CUDA(cudaMemsetAsync(g->stats, 0, sizeof(double) * 64, st));
+  GemmA M{};
+  M.n_chunks = nslots; M.rows_per_n_out = RO; M.P = P;
+  for (int q = 0; q < nslots; ++q) {
+    AChunk& ch = M.ch[q];
+    ch.base = cat; ch.rows_per_n = RO; ch.row_off = 0; ch.pitch = mlp_in; ch.col_off = q * 32;
+  }
+  EpiMlp<T> em{};
+  em.stats = g->stats; em.bias = g->b_mlp;
+  em.u_prev = reinterpret_cast<const T*>(g->u_prev); em.prev_rows_per_n = RI;
+  em.crop = (long long)(c->Lin - c->Lout) * c->V; em.scale = g->scale; em.shift = g->shift;
+  em.mask = reinterpret_cast<const T*>(g->drop_mask);
+  em.drop_p = c->training ? c->dropout_p : 0.f; em.seed = c->seed; em.offset = c->offset; em.rng = g->rng;
+  if (!c->training) em.mask = nullptr;
+  em.u = reinterpret_cast<T*>(g->u);
+  return launch_pos_gemm<T, 32>(M, g->w_mlp, 32, em, st);
+}
+
+template <typename T>
+static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cudaStream_t st) {
+  const long long RO = (long long)c->Lout * c->V, RI = (long long)c->Lin * c->V;
+  const long long P = c->N * RO, PI = c->N * RI;
+  const long long slabs = (long long)c->N * c->Lout;
+  const int nslots = 1 + c->order * c->n_supports, mlp_in = 32 * nslots;
+  T* cat = reinterpret_cast<T*>(g->ws_cat);
+  T* dcat = reinterpret_cast<T*>(g->ws_dcat);
+  const T* a = reinterpret_cast<const T*>(g->a);
+  const T* b = reinterpret_cast<const T*>(g->b);
+  const T* du = reinterpret_cast<const T*>(g->du);
+  const unsigned eb = (unsigned)cdiv(P * 8, 256);
+  const T* dz = nullptr;
+  if (du) {
+    // recompute the concat (z and its hops)
+    zfill_kernel<T><<<eb, 256, 0, st>>>(a, b, cat, mlp_in, P);
+    GWN_LAUNCHED();
+    if (int rc = hops_forward<T>(c, cat, mlp_in, g->supports, st)) return rc;
+    // dh = du * mask
+    const T* dh = du;
+    const bool drop = c->training && (g->drop_mask != nullptr || c->dropout_p > 0.f);
+    if (drop) {
+      T* tmp = reinterpret_cast<T*>(g->ws_dfg);
+      drop_bwd_kernel<T><<<eb, 256, 0, st>>>(du, reinterpret_cast<const T*>(g->drop_mask), c->dropout_p, c->seed,
+                                             c->offset, g->rng, tmp, P);
+      GWN_LAUNCHED();
+      dh = tmp;
+    }
+    // dW_mlp [mlp_in, 32], db_mlp
+    GemmA M{};
+    M.n_chunks = nslots; M.rows_per_n_out = RO; M.P = P;
+    for (int q = 0; q < nslots; ++q) {
+      AChunk& ch = M.ch[q];
+      ch.base = cat; ch.rows_per_n = RO; ch.row_off = 0; ch.pitch = mlp_in; ch.col_off = q * 32;
+    }
+    if (int rc = launch_wgrad<T, T>(M, dh, 32, 0, g->dw_mlp, 32, g->db_mlp, st)) return rc;
+    // dcat[p, (slot,c)] = sum_o dh[p,o] * w_mlp_t[(slot,c), o]
+    GemmA D{};
+    D.n_chunks = 1; D.rows_per_n_out = RO; D.P = P;
+    D.ch[0].base = dh; D.ch[0].rows_per_n = RO; D.ch[0].row_off = 0; D.ch[0].pitch = 32; D.ch[0].col_off = 0;
+    D.ch[0].w_off = 0;
+    EpiStoreT<T> es{}; es.out = dcat; es.pitch = mlp_in;
+    if (int rc = launch_pos_gemm_wt<T, 32>(D, g->w_mlp, mlp_in, 32, es, st)) return rc;
+    // hops backward (reverse order inside each support)
+    for (int s = 0; s < c->n_supports; ++s)
+      for (int k = c->order; k >= 1; --k) {
+        int slot = 1 + s * c->order + (k - 1);
+        int src = (k == 1) ? 0 : slot - 1;
+        if (g->support_needs_grad[s] && g->d_supports[s])
+          if (int rc = launch_dadj<T>(cat, mlp_in, src * 32, dcat, mlp_in, slot * 32, g->d_supports[s], slabs, c->V, st))
+            return rc;
+        if (int rc = launch_node_mix<T>(dcat, mlp_in, slot * 32, dcat, mlp_in, src * 32, 1, g->supports[s], true,
+                                        slabs, c->V, st))
+          return rc;
+      }
+    dz = dcat;
+  } else {
+    GWN_CUDA(cudaMemsetAsync(g->dw_mlp, 0, sizeof(float) * 32 * mlp_in, st));
+    GWN_CUDA(cudaMemsetAsync(g->db_mlp, 0, sizeof(float) * 32, st));
+  }
+  // gate backward: (dz + dz_last) -> dfg
+  gate_bwd_kernel<T><<<eb, 256, 0, st>>>(dz, mlp_in, reinterpret_cast<const T*>(g->dz_last), RO,
+                                         (long long)(c->Lout - c->Lf) * c->V, (long long)c->Lf * c->V, a, b,
+                                         g->ws_dfg, P);
+  GWN_LAUNCHED();
+  // dW_fg [taps*32, 64], db_fg
+  GemmA A{};
+  A.n_chunks = c->taps; A.rows_per_n_out = RO; A.P = P;
+  for (int j = 0; j < c->taps; ++j) {
+    AChunk& ch = A.ch[j];
+    ch.base = g->u_prev; ch.rows_per_n = RI; ch.row_off = (long long)j * c->dilation * c->V;
+    ch.pitch = 32; ch.col_off = 0; ch.scale = g->scale; ch.shift = g->shift;
+  }
+  if (int rc = launch_wgrad<T, float>(A, g->ws_dfg, 64, 0, g->dw_fg, 64, g->db_fg, st)) return rc;
+  // dx_prev[p_in, c] = sum_{j,fg} dfg[p_in - j*d*V, fg] * w_fg[(j,c), fg]  (+ residual du on cropped rows)
+  GemmA X{};
+  X.n_chunks = 2 * c->taps; X.rows_per_n_out = RI; X.P = PI;
+  for (int j = 0; j < c->taps; ++j)
+    for (int h = 0; h < 2; ++h) {
+      AChunk& ch = X.ch[2 * j + h];
+      ch.base = g->ws_dfg; ch.rows_per_n = RO; ch.row_off = -(long long)j * c->dilation * c->V;
+      ch.pitch = 64; ch.col_off = h * 32; ch.w_off = (long long)j * 32 * 64 + h * 32;
+    }
+  GWN_CUDA(cudaMemsetAsync(g->dx_stats, 0, sizeof(double) * 64, st));
+  EpiGateBwdData<T> ex{};
+  ex.stats = g->dx_stats; ex.du = du; ex.du_rows_per_n = RO; ex.crop = (long long)(c->Lin - c->Lout) * c->V;
+  ex.u_prev = reinterpret_cast<const T*>(g->u_prev); ex.dx = g->dx_prev;
+  return launch_pos_gemm_wt<float, 32>(X, g->w_fg, 32, 64, ex, st);
+}
+
+}  // namespace gwn
+
+using namespace gwn;
+
+extern "C" int gwn_layer_fwd(const gwn_layer_cfg* cfg, const gwn_layer_fwd_args* args, void* stream) {
+  if (int rc = check_cfg(cfg)) return rc;
+  GWN_REQUIRE(args && args->u_prev && args->w_fg && args->b_fg && args->z_last && args->ws_cat, "layer_fwd: NULL argument");
+  GWN_REQUIRE(!cfg->has_gconv || (args->w_mlp && args->b_mlp && args->u && args->stats), "layer_fwd: NULL gconv argument");
+  GWN_REQUIRE(!cfg->training || (args->a && args->b), "layer_fwd: training needs a,b buffers");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return cfg->dtype == GWN_F32 ? layer_fwd_t<float>(cfg, args, st) : layer_fwd_t<bf16>(cfg, args, st);
+}
+
+extern "C" int gwn_layer_bwd(const gwn_layer_cfg* cfg, const gwn_layer_bwd_args* args, void* stream) {
+  if (int rc = check_cfg(cfg)) return rc;
+  GWN_REQUIRE(args && args->u_prev && args->w_fg && args->a && args->b && args->dx_prev && args->dx_stats &&
+                  args->dw_fg && args->db_fg && args->dw_mlp && args->db_mlp && args->ws_dfg,
+              "layer_bwd: NULL argument");
+  GWN_REQUIRE(args->du == nullptr || (args->ws_cat && args->ws_dcat && args->w_mlp), "layer_bwd: NULL workspace");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return cfg->dtype == GWN_F32 ? layer_bwd_t<float>(cfg, args, st) : layer_bwd_t<bf16>(cfg, args, st);
+}
+
+extern "C" int gwn_node_mix(const void* x, int x_pitch, int x_off, void* y, int y_pitch, int y_off, int accumulate,
+                            const float* A, int transpose_a, int slabs, int V, int dtype, void* stream) {
+  GWN_REQUIRE(x && y && A && slabs >= 0 && V >= 1, "node_mix: bad argument");
+  GWN_REQUIRE(x_pitch % 4 == 0 && y_pitch % 4 == 0 && x_off % 4 == 0 && y_off % 4 == 0, "node_mix: unaligned pitch");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == GWN_F32)
+    return launch_node_mix<float>((const float*)x, x_pitch, x_off, (float*)y, y_pitch, y_off, accumulate, A,
+                                  transpose_a != 0, slabs, V, st);
+  GWN_REQUIRE(dtype == GWN_BF16, "bad dtype %d", dtype);
+  return launch_node_mix<bf16>((const bf16*)x, x_pitch, x_off, (bf16*)y, y_pitch, y_off, accumulate, A,
+                               transpose_a != 0, slabs, V, st);
+}
+
+extern "C" int gwn_bn_fold(const double* stats, double count, const float* gamma, const float* beta,
+                           float* running_mean, float* running_var, float momentum, float eps, int training,
+                           float* scale, float* shift, float* mean, float* rstd, void* stream) {
+  GWN_REQUIRE(gamma && beta && running_mean && running_var && scale && shift, "bn_fold: NULL argument");
+  GWN_REQUIRE(!training || stats, "bn_fold: training needs stats");
+  bn_fold_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(stats, count, gamma, beta, running_mean,
+                                                                       running_var, momentum, eps, training, scale,
+                                                                       shift, mean, rstd);
+  GWN_LAUNCHED();
+  return 0;
+}
+
+extern "C" int gwn_bn_bwd(const float* dx, const void* u, int dtype, const double* dx_stats, double count,
+                          const float* gamma, const float* mean, const float* rstd, int training, void* du,
+                          float* dgamma, float* dbeta, long long rows, void* stream) {
+  GWN_REQUIRE(dx && u && dx_stats && gamma && mean && rstd && du && dgamma && dbeta, "bn_bwd: NULL argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  unsigned blocks = (unsigned)cdiv(rows * 8, 256);
+  if (blocks == 0) blocks = 1;
+  if (dtype == GWN_F32)
+    bn_bwd_kernel<float><<<blocks, 256, 0, st>>>(dx, (const float*)u, dx_stats, count, gamma, mean, rstd, training,
+                                                 (float*)du, dgamma, dbeta, rows);
+  else
+    bn_bwd_kernel<bf16><<<blocks, 256, 0, st>>>(dx, (const bf16*)u, dx_stats, count, gamma, mean, rstd, training,
+                                                (bf16*)du, dgamma, dbeta, rows);
+  GWN_LAUNCHED();
+  return 0;
+}

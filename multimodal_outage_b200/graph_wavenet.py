@@ -1,0 +1,322 @@
+"""Drop-in `gwnet` nn.Module: same constructor, parameter/buffer names and forward contract as
+``/root/reference/models/graph_wavenet.py:100-256``, with the whole block computed by the
+hand-written sm_100a kernels behind ``torch.ops.gwn.*`` (see ops.py, include/gwn.h).
+
+Two input conventions are accepted by ``forward``:
+  * 3-D ``[num_nodes, horizon, in_dim]`` - the reference's literal call from ``Modified_UNET``
+    (unet.py:224-226): the buffer is *reinterpreted* (not permuted) as ``[1, in_dim, V, horizon]``
+    (graph_wavenet.py:189) and the result reinterpreted back to ``[V, horizon, out_dim]`` (:255);
+  * 4-D ``[N, in_dim, V, T]`` - the general batched form used by every BASELINE config
+    (the reference with its two hard-coded ``.view`` lines removed).
+
+Activation precision: fp32 by default; bf16 storage (fp32 accumulate / statistics / gradients of
+parameters) when ``compute_dtype = torch.bfloat16`` is set or the call runs under
+``torch.autocast('cuda', dtype=torch.bfloat16)``.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .ops import CH
+
+_DEFAULT = object()
+
+
+class nconv(nn.Module):
+    """Node mixing ``einsum('ncvl,vw->ncwl')`` (graph_wavenet.py:60-66) on NCHW tensors, computed by
+    the channels-last CUDA kernel (layout conversion on both sides; the fused block never uses this)."""
+
+    def forward(self, x: torch.Tensor, A: torch.Tensor) -> torch.Tensor:
+        n, c, v, l = x.shape
+        if c % CH != 0:
+            raise ValueError(f'nconv kernel handles channel counts that are multiples of {CH}')
+        xs = x.permute(0, 3, 2, 1).reshape(n * l, v, c // CH, CH).permute(2, 0, 1, 3).contiguous()
+        ys = torch.stack([ops.node_mix(xs[i], A.contiguous().float(), False) for i in range(c // CH)])
+        return ys.permute(1, 2, 0, 3).reshape(n, l, A.shape[1], c).permute(0, 3, 2, 1).contiguous()
+
+
+class linear(nn.Module):
+    """Parameter container for the gcn 1x1 'mlp' (graph_wavenet.py:68-74)."""
+
+    def __init__(self, c_in: int, c_out: int):
+        super().__init__()
+        self.mlp = nn.Conv2d(c_in, c_out, kernel_size=(1, 1), padding=(0, 0), stride=(1, 1), bias=True)
+
+
+class gcn(nn.Module):
+    """Parameter container for the diffusion convolution (graph_wavenet.py:76-98)."""
+
+    def __init__(self, c_in: int, c_out: int, dropout: float, support_len: int = 3, order: int = 2):
+        super().__init__()
+        self.nconv = nconv()
+        self.mlp = linear((order * support_len + 1) * c_in, c_out)
+        self.dropout = dropout
+        self.order = order
+
+
+class _PackParams(torch.autograd.Function):
+    """Re-lays the reference-shaped parameters into the kernels' packed layouts (and un-packs the
+    gradients): a handful of batched copies per step instead of per-layer glue.
+
+    inputs : Wf[nl], bf[nl], Wg[nl], bg[nl], Wm[nl], bm[nl], Ws[nl], bs[nl], W1, b1, W2, b2  (flat list)
+    outputs: w_fg[nl] ([k*32, 64]), b_fg[nl] ([64]), w_mlp[nl] ([mlp_in, 32]), w_skip [32*nl, S],
+             b_skip [S], w_end1 [S, E], w_end2 [E, Opad], b_end2 [Opad]
+    """
+
+    @staticmethod
+    def forward(ctx, nl, *p):
+        Wf, bf, Wg, bg, Wm, bm, Ws, bs = (p[i * nl:(i + 1) * nl] for i in range(8))
+        W1, b1, W2, b2 = p[8 * nl:]
+        k = Wf[0].shape[3]
+        wf = torch.stack(Wf)[:, :, :, 0, :]                                    # [nl, o, c, k]
+        wg = torch.stack(Wg)[:, :, :, 0, :]
+        w_fg = torch.stack([wf, wg], dim=2).permute(0, 4, 3, 1, 2).reshape(nl, k * CH, 2 * CH).contiguous()
+        b_fg = torch.stack([torch.stack(bf), torch.stack(bg)], dim=2).reshape(nl, 2 * CH).contiguous()
+        w_mlp = torch.stack(Wm)[:, :, :, 0, 0].transpose(1, 2).contiguous()     # [nl, mlp_in, 32]
+        ws = torch.stack(Ws)[:, :, :, 0, 0]                                     # [nl, S, 32]
+        S = ws.shape[1]
+        w_skip = ws.permute(0, 2, 1).reshape(nl * CH, S).contiguous()
+        b_skip = torch.stack(bs).sum(0)
+        w_end1 = W1[:, :, 0, 0].t().contiguous()                                # [S, E]
+        O, E = W2.shape[0], W2.shape[1]
+        Opad = CH * ((O + CH - 1) // CH)
+        w_end2 = W2.new_zeros((E, Opad)); w_end2[:, :O] = W2[:, :, 0, 0].t()
+        b_end2 = b2.new_zeros((Opad,)); b_end2[:O] = b2
+        ctx.dims = (nl, k, S, E, O, Wm[0].shape[1])
+        ctx.set_materialize_grads(False)
+        return (*w_fg.unbind(0), *b_fg.unbind(0), *w_mlp.unbind(0), w_skip, b_skip, w_end1, w_end2, b_end2)
+
+    @staticmethod
+    def backward(ctx, *g):
+        nl, k, S, E, O, mlp_in = ctx.dims
+        g_wfg, g_bfg, g_wmlp = g[:nl], g[nl:2 * nl], g[2 * nl:3 * nl]
+        g_wskip, g_bskip, g_wend1, g_wend2, g_bend2 = g[3 * nl:]
+
+        def unstack(items, fn):
+            """per-layer grads (some None: parameters the block never used) -> per-layer param grads"""
+            live = [i for i, t in enumerate(items) if t is not None]
+            out = [None] * nl
+            if live:
+                res = fn(torch.stack([items[i] for i in live]))
+                for j, i in enumerate(live):
+                    out[i] = tuple(r[j] for r in res)
+            return out
+
+        fg = unstack(g_wfg, lambda t: (
+            t.reshape(-1, k, CH, CH, 2).permute(0, 3, 4, 2, 1)[:, :, 0].unsqueeze(3).contiguous(),   # Wf [o,c,1,k]
+            t.reshape(-1, k, CH, CH, 2).permute(0, 3, 4, 2, 1)[:, :, 1].unsqueeze(3).contiguous()))
+        bfg = unstack(g_bfg, lambda t: (t.reshape(-1, CH, 2)[:, :, 0].contiguous(),
+                                        t.reshape(-1, CH, 2)[:, :, 1].contiguous()))
+        wm = unstack(g_wmlp, lambda t: (t.transpose(1, 2).reshape(-1, CH, mlp_in, 1, 1).contiguous(),))
+        dWf = [x[0] if x else None for x in fg]; dWg = [x[1] if x else None for x in fg]
+        dbf = [x[0] if x else None for x in bfg]; dbg = [x[1] if x else None for x in bfg]
+        dWm = [x[0] if x else None for x in wm]
+        if g_wskip is not None:
+            t = g_wskip.reshape(nl, CH, S).permute(0, 2, 1).reshape(nl, S, CH, 1, 1).contiguous()
+            dWs = list(t.unbind(0))
+        else:
+            dWs = [None] * nl
+        dbs = [g_bskip] * nl if g_bskip is not None else [None] * nl
+        dW1 = g_wend1.t().reshape(E, S, 1, 1).contiguous() if g_wend1 is not None else None
+        dW2 = g_wend2[:, :O].t().reshape(O, E, 1, 1).contiguous() if g_wend2 is not None else None
+        db2 = g_bend2[:O].contiguous() if g_bend2 is not None else None
+        # bm, b1 are passed straight to the kernels (no packing) -> no grads through this Function
+        return (None, *dWf, *dbf, *dWg, *dbg, *dWm, *([None] * nl), *dWs, *dbs, dW1, None, dW2, db2)
+
+
+class gwnet(nn.Module):
+    def __init__(self, device, num_nodes=67, dropout=0.3, supports=_DEFAULT, gcn_bool=True, addaptadj=True,
+                 aptinit=None, in_dim=256, out_dim=255, horizon=1, residual_channels=32, dilation_channels=32,
+                 skip_channels=256, end_channels=512, kernel_size=1, blocks=4, layers=2):
+        super().__init__()
+        if residual_channels != CH or dilation_channels != CH:
+            raise NotImplementedError(
+                f'the sm_100a kernels are specialised for residual_channels == dilation_channels == {CH} '
+                '(the value every reference configuration uses)')
+        if skip_channels % CH or end_channels % CH:
+            raise NotImplementedError('skip_channels and end_channels must be multiples of 32')
+        self.dropout = dropout
+        self.blocks = blocks
+        self.layers = layers
+        self.gcn_bool = gcn_bool
+        self.addaptadj = addaptadj
+        self.horizon = horizon
+        self.num_nodes = num_nodes
+        self.in_dim = in_dim
+        self.out_dim = out_dim
+        self.kernel_size = kernel_size
+        self.compute_dtype: Optional[torch.dtype] = None    # None: follow autocast, else fp32
+        self.dropout_mode = 'fused'                         # 'fused' (in-kernel Philox) | 'torch' (F.dropout mask)
+
+        # registration order below mirrors graph_wavenet.py:110-183 so state_dict keys (and a seeded
+        # default init) line up with the reference
+        self.filter_convs = nn.ModuleList()
+        self.gate_convs = nn.ModuleList()
+        self.residual_convs = nn.ModuleList()
+        self.skip_convs = nn.ModuleList()
+        self.bn = nn.ModuleList()
+        self.gconv = nn.ModuleList()
+        self.start_conv = nn.Conv2d(in_dim, residual_channels, kernel_size=(1, 1))
+
+        if supports is _DEFAULT:
+            # what the reference's own load_adj('doubletransition') yields: one identity (graph_wavenet.py:24,51)
+            supports = [torch.eye(num_nodes, dtype=torch.float32)]
+        self.supports_len = 0 if supports is None else len(supports)
+        self.supports: List[torch.Tensor] = [] if supports is None else \
+            [torch.as_tensor(s, dtype=torch.float32).to(device) for s in supports]
+
+        if gcn_bool and addaptadj:
+            if aptinit is None:
+                self.nodevec1 = nn.Parameter(torch.randn(num_nodes, 10).to(device), requires_grad=True)
+                self.nodevec2 = nn.Parameter(torch.randn(10, num_nodes).to(device), requires_grad=True)
+            else:
+                m, p, n = torch.svd(torch.as_tensor(aptinit, dtype=torch.float32))
+                self.nodevec1 = nn.Parameter(torch.mm(m[:, :10], torch.diag(p[:10] ** 0.5)).to(device))
+                self.nodevec2 = nn.Parameter(torch.mm(torch.diag(p[:10] ** 0.5), n[:, :10].t()).to(device))
+            self.supports_len += 1
+
+        receptive_field = 1
+        self.dilations: List[int] = []
+        for _b in range(blocks):
+            additional_scope = kernel_size - 1
+            new_dilation = 1
+            for _i in range(layers):
+                self.filter_convs.append(nn.Conv2d(residual_channels, dilation_channels, (1, kernel_size),
+                                                   dilation=new_dilation))
+                self.gate_convs.append(nn.Conv2d(residual_channels, dilation_channels, (1, kernel_size),
+                                                 dilation=new_dilation))
+                self.residual_convs.append(nn.Conv2d(dilation_channels, residual_channels, (1, 1)))
+                self.skip_convs.append(nn.Conv2d(dilation_channels, skip_channels, (1, 1)))
+                self.bn.append(nn.BatchNorm2d(residual_channels))
+                self.dilations.append(new_dilation)
+                new_dilation *= 2
+                receptive_field += additional_scope
+                additional_scope *= 2
+                if gcn_bool:
+                    self.gconv.append(gcn(dilation_channels, residual_channels, dropout,
+                                          support_len=self.supports_len))
+        self.end_conv_1 = nn.Conv2d(skip_channels, end_channels, (1, 1), bias=True)
+        self.end_conv_2 = nn.Conv2d(end_channels, out_dim, (1, 1), bias=True)
+        self.receptive_field = receptive_field
+        self._rng_state: Optional[torch.Tensor] = None
+        self._calls = 0
+        self.to(device)
+
+    # supports are plain attributes in the reference (not buffers, not in the state_dict); keep that, but
+    # let .to()/.cuda() move them with the module
+    def _apply(self, fn, *args, **kwargs):
+        super()._apply(fn, *args, **kwargs)
+        self.supports = [fn(s) for s in self.supports]
+        if self._rng_state is not None:
+            self._rng_state = fn(self._rng_state)
+        return self
+
+    # ------------------------------------------------------------------ helpers
+    def _act_dtype(self) -> torch.dtype:
+        if self.compute_dtype is not None:
+            return self.compute_dtype
+        if torch.is_autocast_enabled('cuda') and torch.get_autocast_dtype('cuda') == torch.bfloat16:
+            return torch.bfloat16
+        return torch.float32
+
+    def layer_lengths(self, t_in: int) -> List[int]:
+        L = [max(t_in, self.receptive_field)]
+        for d in self.dilations:
+            L.append(L[-1] - d * (self.kernel_size - 1))
+        return L
+
+    def _packed(self):
+        nl = self.blocks * self.layers
+        mlps = [g.mlp.mlp for g in self.gconv] if self.gcn_bool else list(self.residual_convs)
+        flat = ([c.weight for c in self.filter_convs] + [c.bias for c in self.filter_convs] +
+                [c.weight for c in self.gate_convs] + [c.bias for c in self.gate_convs] +
+                [m.weight for m in mlps] + [m.bias for m in mlps] +
+                [c.weight for c in self.skip_convs] + [c.bias for c in self.skip_convs] +
+                [self.end_conv_1.weight, self.end_conv_1.bias, self.end_conv_2.weight, self.end_conv_2.bias])
+        out = _PackParams.apply(nl, *flat)
+        return dict(w_fg=out[:nl], b_fg=out[nl:2 * nl], w_mlp=out[2 * nl:3 * nl], b_mlp=[m.bias for m in mlps],
+                    w_skip=out[3 * nl], b_skip=out[3 * nl + 1], w_end1=out[3 * nl + 2], w_end2=out[3 * nl + 3],
+                    b_end2=out[3 * nl + 4])
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, input: torch.Tensor, dropout_masks: Optional[Sequence[Optional[torch.Tensor]]] = None):
+        literal = input.dim() == 3
+        if literal:                                          # graph_wavenet.py:189
+            x = input.reshape(1, self.in_dim, self.num_nodes, self.horizon)
+        else:
+            x = input
+        y = self._forward_nchw(x, dropout_masks)
+        if literal:                                          # graph_wavenet.py:255
+            return y.reshape(self.num_nodes, self.horizon, -1)
+        return y
+
+    def _forward_nchw(self, x, dropout_masks):
+        if not x.is_cuda:
+            raise ops._lib.GwnError('gwnet runs on a CUDA (B200) device only - there is no CPU fallback')
+        N, Cin, V, T = x.shape
+        if Cin != self.in_dim or V != self.num_nodes:
+            raise ValueError(f'expected input [N,{self.in_dim},{self.num_nodes},T], got {tuple(x.shape)}')
+        dt = self._act_dtype()
+        nl = self.blocks * self.layers
+        L = self.layer_lengths(T)
+        Lf = L[-1]
+        if Lf < 1:
+            raise ValueError(f'input length {T} too short for receptive field {self.receptive_field}')
+        training = self.training
+        pk = self._packed()
+
+        supports: List[torch.Tensor] = []
+        if self.gcn_bool:
+            supports = list(self.supports)
+            if self.addaptadj:                               # graph_wavenet.py:201-203
+                supports = supports + [ops.AdaptiveAdjacency.apply(self.nodevec1, self.nodevec2)]
+
+        p_drop = float(self.dropout) if (training and self.gcn_bool) else 0.0
+        rng = None
+        masks: List[Optional[torch.Tensor]] = [None] * nl
+        if p_drop > 0.0:
+            if dropout_masks is not None:                    # explicit NCHW masks (parity tests)
+                masks = [None if m is None else m.permute(0, 3, 2, 1).contiguous().to(dt) for m in dropout_masks]
+            elif self.dropout_mode == 'torch':               # the reference's own Philox draws (graph_wavenet.py:97)
+                masks = [torch.nn.functional.dropout(x.new_ones((N, CH, V, L[i + 1])), p_drop, True)
+                         .permute(0, 3, 2, 1).contiguous().to(dt) for i in range(nl)]
+            else:
+                if self._rng_state is None or self._rng_state.device != x.device:
+                    self._rng_state = torch.tensor([torch.initial_seed() & (2 ** 62 - 1), 0], dtype=torch.int64,
+                                                   device=x.device)
+                rng = self._rng_state.clone()                # this step's {seed, offset}
+                self._rng_state[1] += nl                     # graph-safe: advances on every replay
+
+        u = ops.StartConv.apply(x, self.start_conv.weight, self.start_conv.bias, L[0], dt == torch.bfloat16)
+        stats = None
+        z_last = []
+        for i in range(nl):
+            last = i == nl - 1
+            bn_prev = self.bn[i - 1] if i > 0 else None
+            has_gconv = (not last) or training               # last layer's gconv/bn only feed running stats
+            meta = dict(training=training, momentum=0.1 if bn_prev is None or bn_prev.momentum is None
+                        else bn_prev.momentum, eps=1e-5 if bn_prev is None else bn_prev.eps, Lf=Lf,
+                        taps=self.kernel_size, dilation=self.dilations[i], order=2, has_gconv=has_gconv,
+                        dropout_p=p_drop if masks[i] is None else 1.0, seed=0, offset=i)
+            if masks[i] is not None:
+                meta['dropout_p'] = p_drop
+            u, stats, zl = ops.WaveNetLayer.apply(
+                u, stats,
+                None if bn_prev is None else bn_prev.weight, None if bn_prev is None else bn_prev.bias,
+                None if bn_prev is None else bn_prev.running_mean, None if bn_prev is None else bn_prev.running_var,
+                pk['w_fg'][i], pk['b_fg'][i], pk['w_mlp'][i] if has_gconv else None,
+                pk['b_mlp'][i] if has_gconv else None, masks[i], rng, meta, *supports)
+            z_last.append(zl)
+        if training:
+            # the reference still runs bn[last] (its output is dead, :250-252) - keep its running stats in step
+            with torch.no_grad():
+                bl = self.bn[nl - 1]
+                ops.bn_fold(stats, float(N * L[nl] * V), bl.weight, bl.bias, bl.running_mean, bl.running_var,
+                            0.1 if bl.momentum is None else bl.momentum, bl.eps, True)
+                torch._foreach_add_([b.num_batches_tracked for b in self.bn], 1)
+        return ops.SkipHead.apply(pk['w_skip'], pk['b_skip'], pk['w_end1'], self.end_conv_1.bias, pk['w_end2'],
+                                  pk['b_end2'], self.out_dim, *z_last)

@@ -1,0 +1,472 @@
+"""torch.library custom ops (`torch.ops.gwn.*`) over the libgwn C ABI, plus the
+autograd Functions that chain them into the Graph WaveNet block.
+
+Every op calls hand-written sm_100a kernels through ctypes with raw device pointers
+and the current CUDA stream.  There is no CPU / eager fallback: non-CUDA tensors or a
+non-B200 device raise.
+
+Internal activation layout is channels-last ``[N, L, V, 32]`` (see include/gwn.h).
+Reference lines replaced are cited per op (``/root/reference/models/graph_wavenet.py``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import (GWN_BF16, GWN_F32, HeadBwdArgs, HeadCfg, HeadFwdArgs, LayerBwdArgs, LayerCfg, LayerFwdArgs,
+                   check, lib)
+
+CH = 32
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _code(dtype: torch.dtype) -> int:
+    if dtype == torch.float32:
+        return GWN_F32
+    if dtype == torch.bfloat16:
+        return GWN_BF16
+    raise TypeError(f'activation dtype must be float32 or bfloat16, got {dtype}')
+
+
+def _p(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: Tensor, dtype=None, name='tensor') -> Tensor:
+    if not t.is_cuda:
+        raise _lib.GwnError(f'{name}: libgwn ops run on CUDA (B200) tensors only - there is no CPU fallback')
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f'{name}: expected {dtype}, got {t.dtype}')
+    if not t.is_contiguous():
+        raise ValueError(f'{name}: must be contiguous')
+    _lib.require_b200(t.device.index)
+    return t
+
+
+# =========================================================================== adaptive adjacency (:202)
+@torch.library.custom_op('gwn::adp_fwd', mutates_args=())
+def adp_fwd(e1: Tensor, e2: Tensor) -> Tensor:
+    _req(e1, torch.float32, 'nodevec1'); _req(e2, torch.float32, 'nodevec2')
+    V, R = e1.shape
+    adp = torch.empty((V, V), device=e1.device, dtype=torch.float32)
+    with torch.cuda.device(e1.device):
+        check(lib().gwn_adp_fwd(_p(e1), _p(e2), _p(adp), None, V, R, _stream()), 'gwn_adp_fwd')
+    return adp
+
+
+@adp_fwd.register_fake
+def _(e1, e2):
+    return e1.new_empty((e1.shape[0], e1.shape[0]))
+
+
+@torch.library.custom_op('gwn::adp_bwd', mutates_args=())
+def adp_bwd(e1: Tensor, e2: Tensor, adp: Tensor, d_adp: Tensor) -> Tuple[Tensor, Tensor]:
+    _req(d_adp, torch.float32, 'd_adp')
+    V, R = e1.shape
+    de1, de2 = torch.empty_like(e1), torch.empty_like(e2)
+    ws = torch.empty((V, V), device=e1.device, dtype=torch.float32)
+    with torch.cuda.device(e1.device):
+        check(lib().gwn_adp_bwd(_p(e1), _p(e2), _p(adp), _p(d_adp), _p(de1), _p(de2), _p(ws), V, R, _stream()),
+              'gwn_adp_bwd')
+    return de1, de2
+
+
+@adp_bwd.register_fake
+def _(e1, e2, adp, d_adp):
+    return torch.empty_like(e1), torch.empty_like(e2)
+
+
+class AdaptiveAdjacency(torch.autograd.Function):
+    """softmax(relu(E1 @ E2), dim=1), warp-per-row fused forward and backward."""
+
+    @staticmethod
+    def forward(ctx, e1, e2):
+        e1c, e2c = e1.contiguous(), e2.contiguous()
+        adp = adp_fwd(e1c, e2c)
+        ctx.save_for_backward(e1c, e2c, adp)
+        return adp
+
+    @staticmethod
+    def backward(ctx, d_adp):
+        e1, e2, adp = ctx.saved_tensors
+        return adp_bwd(e1, e2, adp, d_adp.contiguous())
+
+
+# =========================================================================== start conv (:191-196)
+@torch.library.custom_op('gwn::start_fwd', mutates_args=())
+def start_fwd(x: Tensor, w: Tensor, b: Tensor, L0: int, bf16: bool) -> Tensor:
+    _req(x, torch.float32, 'input'); _req(w, torch.float32, 'start_conv.weight'); _req(b, torch.float32)
+    N, Cin, V, T = x.shape
+    dt = torch.bfloat16 if bf16 else torch.float32
+    u0 = torch.empty((N, L0, V, CH), device=x.device, dtype=dt)
+    with torch.cuda.device(x.device):
+        check(lib().gwn_start_fwd(_p(x), _p(w), _p(b), _p(u0), _code(dt), N, Cin, V, T, L0, _stream()),
+              'gwn_start_fwd')
+    return u0
+
+
+@start_fwd.register_fake
+def _(x, w, b, L0, bf16):
+    return x.new_empty((x.shape[0], L0, x.shape[2], CH), dtype=torch.bfloat16 if bf16 else torch.float32)
+
+
+@torch.library.custom_op('gwn::start_bwd', mutates_args=())
+def start_bwd(x: Tensor, w: Tensor, du0: Tensor, need_dx: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    _req(du0, None, 'du0')
+    N, Cin, V, T = x.shape
+    L0 = du0.shape[1]
+    dw = torch.empty((CH, Cin), device=x.device, dtype=torch.float32)
+    db = torch.empty((CH,), device=x.device, dtype=torch.float32)
+    dx = torch.empty_like(x) if need_dx else torch.empty((0,), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(lib().gwn_start_bwd(_p(x), _p(w), _p(du0), _code(du0.dtype), _p(dw), _p(db),
+                                  _p(dx) if need_dx else None, N, Cin, V, T, L0, _stream()), 'gwn_start_bwd')
+    return dw, db, dx
+
+
+@start_bwd.register_fake
+def _(x, w, du0, need_dx):
+    return (x.new_empty((CH, x.shape[1])), x.new_empty((CH,)),
+            torch.empty_like(x) if need_dx else x.new_empty((0,)))
+
+
+class StartConv(torch.autograd.Function):
+    """1x1 conv Cin->32 fused with the left zero-pad and the NCHW -> channels-last change."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, L0, bf16):
+        xc = x.contiguous().float()
+        w2 = w.reshape(CH, -1).contiguous()
+        u0 = start_fwd(xc, w2, b.contiguous(), L0, bf16)
+        ctx.save_for_backward(xc, w2)
+        ctx.wshape = w.shape
+        return u0
+
+    @staticmethod
+    def backward(ctx, du0):
+        xc, w2 = ctx.saved_tensors
+        need_dx = ctx.needs_input_grad[0]
+        dw, db, dx = start_bwd(xc, w2, du0.contiguous(), need_dx)
+        return (dx if need_dx else None), dw.reshape(ctx.wshape), db, None, None
+
+
+# =========================================================================== BatchNorm fold (:167,250)
+@torch.library.custom_op('gwn::bn_fold', mutates_args=('running_mean', 'running_var'))
+def bn_fold(stats: Optional[Tensor], count: float, gamma: Tensor, beta: Tensor, running_mean: Tensor,
+            running_var: Tensor, momentum: float, eps: float, training: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    _req(gamma, torch.float32, 'bn.weight')
+    scale, shift, mean, rstd = (torch.empty_like(gamma) for _ in range(4))
+    with torch.cuda.device(gamma.device):
+        check(lib().gwn_bn_fold(_p(stats), float(count), _p(gamma), _p(beta), _p(running_mean), _p(running_var),
+                                float(momentum), float(eps), int(training), _p(scale), _p(shift), _p(mean),
+                                _p(rstd), _stream()), 'gwn_bn_fold')
+    return scale, shift, mean, rstd
+
+
+@bn_fold.register_fake
+def _(stats, count, gamma, beta, running_mean, running_var, momentum, eps, training):
+    return tuple(torch.empty_like(gamma) for _ in range(4))
+
+
+@torch.library.custom_op('gwn::bn_bwd', mutates_args=())
+def bn_bwd(dx: Tensor, u: Tensor, dx_stats: Tensor, count: float, gamma: Tensor, mean: Tensor, rstd: Tensor,
+           training: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    _req(dx, torch.float32, 'dx'); _req(u, None, 'u')
+    du = torch.empty_like(u)
+    dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(gamma)
+    rows = u.numel() // CH
+    with torch.cuda.device(u.device):
+        check(lib().gwn_bn_bwd(_p(dx), _p(u), _code(u.dtype), _p(dx_stats), float(count), _p(gamma), _p(mean),
+                               _p(rstd), int(training), _p(du), _p(dgamma), _p(dbeta), rows, _stream()),
+              'gwn_bn_bwd')
+    return du, dgamma, dbeta
+
+
+@bn_bwd.register_fake
+def _(dx, u, dx_stats, count, gamma, mean, rstd, training):
+    return torch.empty_like(u), torch.empty_like(gamma), torch.empty_like(gamma)
+
+
+# =========================================================================== one layer (:206-250)
+def _layer_cfg(N, V, Lin, Lout, Lf, taps, dilation, n_sup, order, dtype, training, has_gconv, dropout_p, seed,
+               offset) -> LayerCfg:
+    return LayerCfg(N=N, V=V, Lin=Lin, Lout=Lout, Lf=Lf, taps=taps, dilation=dilation, n_supports=n_sup,
+                    order=order, dtype=_code(dtype), training=int(training), has_gconv=int(has_gconv),
+                    dropout_p=float(dropout_p), seed=int(seed) & (2**64 - 1), offset=int(offset))
+
+
+def _sup_array(supports: Sequence[Tensor]):
+    arr = (C.c_void_p * _lib.MAX_SUPPORTS)()
+    for i, s in enumerate(supports):
+        arr[i] = s.data_ptr()
+    return arr
+
+
+@torch.library.custom_op('gwn::layer_fwd', mutates_args=())
+def layer_fwd(u_prev: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], w_fg: Tensor, b_fg: Tensor,
+              w_mlp: Optional[Tensor], b_mlp: Optional[Tensor], supports: List[Tensor],
+              drop_mask: Optional[Tensor], rng: Optional[Tensor], Lf: int, taps: int, dilation: int, order: int,
+              training: bool, has_gconv: bool, dropout_p: float, seed: int, offset: int
+              ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    _req(u_prev, None, 'u_prev'); _req(w_fg, torch.float32, 'w_fg'); _req(b_fg, torch.float32, 'b_fg')
+    for s in supports:
+        _req(s, torch.float32, 'support')
+    N, Lin, V, _c = u_prev.shape
+    Lout = Lin - dilation * (taps - 1)
+    dt, dev = u_prev.dtype, u_prev.device
+    n_sup = len(supports) if has_gconv else 0
+    mlp_in = CH * (1 + order * n_sup)
+    P = N * Lout * V
+    if has_gconv:
+        _req(w_mlp, torch.float32, 'w_mlp')
+        if tuple(w_mlp.shape) != (mlp_in, CH):
+            raise ValueError(f'w_mlp must be [{mlp_in},{CH}], got {tuple(w_mlp.shape)}')
+    if tuple(w_fg.shape) != (taps * CH, 2 * CH):
+        raise ValueError(f'w_fg must be [{taps * CH},{2 * CH}], got {tuple(w_fg.shape)}')
+    z_last = torch.empty((N, Lf, V, CH), device=dev, dtype=dt)
+    a = torch.empty((N, Lout, V, CH) if training else (0,), device=dev, dtype=dt)
+    b = torch.empty((N, Lout, V, CH) if training else (0,), device=dev, dtype=dt)
+    u = torch.empty((N, Lout, V, CH) if has_gconv else (0,), device=dev, dtype=dt)
+    stats = torch.empty((2, CH), device=dev, dtype=torch.float64)
+    ws_cat = torch.empty((P, mlp_in), device=dev, dtype=dt)
+    cfg = _layer_cfg(N, V, Lin, Lout, Lf, taps, dilation, n_sup, order, dt, training, has_gconv, dropout_p, seed,
+                     offset)
+    args = LayerFwdArgs(u_prev=_p(u_prev), scale=_p(scale), shift=_p(shift), w_fg=_p(w_fg), b_fg=_p(b_fg),
+                        w_mlp=_p(w_mlp), b_mlp=_p(b_mlp), supports=_sup_array(supports if has_gconv else []),
+                        drop_mask=_p(drop_mask), rng=_p(rng), a=_p(a) if training else None,
+                        b=_p(b) if training else None, z_last=_p(z_last), u=_p(u) if has_gconv else None,
+                        stats=_p(stats), ws_cat=_p(ws_cat))
+    with torch.cuda.device(dev):
+        check(lib().gwn_layer_fwd(C.byref(cfg), C.byref(args), _stream()), 'gwn_layer_fwd')
+    return u, stats, z_last, a, b
+
+
+@layer_fwd.register_fake
+def _(u_prev, scale, shift, w_fg, b_fg, w_mlp, b_mlp, supports, drop_mask, rng, Lf, taps, dilation, order,
+      training, has_gconv, dropout_p, seed, offset):
+    N, Lin, V, _c = u_prev.shape
+    Lout = Lin - dilation * (taps - 1)
+    full = (N, Lout, V, CH)
+    return (u_prev.new_empty(full if has_gconv else (0,)), u_prev.new_empty((2, CH), dtype=torch.float64),
+            u_prev.new_empty((N, Lf, V, CH)), u_prev.new_empty(full if training else (0,)),
+            u_prev.new_empty(full if training else (0,)))
+
+
+@torch.library.custom_op('gwn::layer_bwd', mutates_args=())
+def layer_bwd(u_prev: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], w_fg: Tensor,
+              w_mlp: Optional[Tensor], supports: List[Tensor], needs_grad: List[bool],
+              drop_mask: Optional[Tensor], rng: Optional[Tensor], a: Tensor, b: Tensor, du: Optional[Tensor],
+              dz_last: Optional[Tensor], Lf: int, taps: int, dilation: int, order: int, training: bool,
+              dropout_p: float, seed: int, offset: int) -> List[Tensor]:
+    """Returns [dx_prev, dx_stats, dw_fg, db_fg, dw_mlp, db_mlp, d_support_0, ...] (d_support only for
+    supports whose needs_grad is True; others are empty tensors)."""
+    N, Lin, V, _c = u_prev.shape
+    Lout = Lin - dilation * (taps - 1)
+    dt, dev = u_prev.dtype, u_prev.device
+    has_du = du is not None
+    n_sup = len(supports)
+    mlp_in = CH * (1 + order * n_sup)
+    P = N * Lout * V
+    f32 = dict(device=dev, dtype=torch.float32)
+    dx_prev = torch.empty((N, Lin, V, CH), **f32)
+    dx_stats = torch.empty((2, CH), device=dev, dtype=torch.float64)
+    dw_fg, db_fg = torch.empty((taps * CH, 2 * CH), **f32), torch.empty((2 * CH,), **f32)
+    dw_mlp, db_mlp = torch.empty((mlp_in, CH), **f32), torch.empty((CH,), **f32)
+    d_sup = [torch.zeros((V, V), **f32) if (g and has_du) else torch.empty((0,), **f32) for g in needs_grad]
+    ws_cat = torch.empty((P, mlp_in) if has_du else (0,), device=dev, dtype=dt)
+    ws_dcat = torch.empty((P, mlp_in) if has_du else (0,), device=dev, dtype=dt)
+    ws_dfg = torch.empty((P, 2 * CH), **f32)
+    cfg = _layer_cfg(N, V, Lin, Lout, Lf, taps, dilation, n_sup, order, dt, training, True, dropout_p, seed, offset)
+    args = LayerBwdArgs(u_prev=_p(u_prev), scale=_p(scale), shift=_p(shift), w_fg=_p(w_fg), w_mlp=_p(w_mlp),
+                        supports=_sup_array(supports), drop_mask=_p(drop_mask), rng=_p(rng), a=_p(a), b=_p(b),
+                        du=_p(du), dz_last=_p(dz_last), dx_prev=_p(dx_prev), dx_stats=_p(dx_stats),
+                        dw_fg=_p(dw_fg), db_fg=_p(db_fg), dw_mlp=_p(dw_mlp), db_mlp=_p(db_mlp),
+                        ws_cat=_p(ws_cat) if has_du else None, ws_dcat=_p(ws_dcat) if has_du else None,
+                        ws_dfg=_p(ws_dfg))
+    for i, g in enumerate(needs_grad):
+        args.support_needs_grad[i] = int(bool(g) and has_du)
+        args.d_supports[i] = d_sup[i].data_ptr() if (g and has_du) else None
+    with torch.cuda.device(dev):
+        check(lib().gwn_layer_bwd(C.byref(cfg), C.byref(args), _stream()), 'gwn_layer_bwd')
+    return [dx_prev, dx_stats, dw_fg, db_fg, dw_mlp, db_mlp] + d_sup
+
+
+@layer_bwd.register_fake
+def _(u_prev, scale, shift, w_fg, w_mlp, supports, needs_grad, drop_mask, rng, a, b, du, dz_last, Lf, taps,
+      dilation, order, training, dropout_p, seed, offset):
+    N, Lin, V, _c = u_prev.shape
+    mlp_in = CH * (1 + order * len(supports))
+    f = lambda *s: u_prev.new_empty(s, dtype=torch.float32)  # noqa: E731
+    return [f(N, Lin, V, CH), u_prev.new_empty((2, CH), dtype=torch.float64), f(taps * CH, 2 * CH), f(2 * CH),
+            f(mlp_in, CH), f(CH)] + [f(V, V) if g and du is not None else f(0) for g in needs_grad]
+
+
+class WaveNetLayer(torch.autograd.Function):
+    """bn_prev-fold -> gated dilated conv -> (z_last) -> diffusion conv + dropout + residual -> (u, BN stats).
+
+    Inputs : u_prev, stats_prev|None, gamma_prev|None, beta_prev|None, rmean_prev|None, rvar_prev|None,
+             w_fg, b_fg, w_mlp|None, b_mlp|None, drop_mask|None, rng|None, meta(dict), *supports
+    Outputs: u (pre-BN, or empty if the gconv is skipped), stats (non-differentiable), z_last
+    """
+
+    @staticmethod
+    def forward(ctx, u_prev, stats_prev, gamma, beta, rmean, rvar, w_fg, b_fg, w_mlp, b_mlp, drop_mask, rng, meta,
+                *supports):
+        m = meta
+        training = m['training']
+        has_bn = gamma is not None
+        scale = shift = mean = rstd = None
+        count = float(u_prev.numel() // CH)
+        if has_bn:
+            scale, shift, mean, rstd = bn_fold(stats_prev if training else None, count, gamma, beta, rmean, rvar,
+                                               m['momentum'], m['eps'], training)
+        sup = [s.contiguous() for s in supports]
+        u, stats, z_last, a, b = layer_fwd(u_prev, scale, shift, w_fg, b_fg, w_mlp, b_mlp, sup, drop_mask, rng,
+                                           m['Lf'], m['taps'], m['dilation'], m['order'], training,
+                                           m['has_gconv'], m['dropout_p'], m['seed'], m['offset'])
+        ctx.meta = m
+        ctx.count = count
+        ctx.has_bn = has_bn
+        ctx.n_sup = len(sup)
+        ctx.sup_needs = [bool(s.requires_grad) for s in supports]
+        ctx.save_for_backward(u_prev, scale, shift, mean, rstd, gamma, w_fg, w_mlp, drop_mask, rng, a, b, *sup)
+        ctx.mark_non_differentiable(stats)
+        return u, stats, z_last
+
+    @staticmethod
+    def backward(ctx, du, _dstats, dz_last):
+        m = ctx.meta
+        (u_prev, scale, shift, mean, rstd, gamma, w_fg, w_mlp, drop_mask, rng, a, b, *sup) = ctx.saved_tensors
+        if not m['training']:
+            raise _lib.GwnError('backward through an eval-mode forward is not supported (a,b were not saved)')
+        if du is not None and du.numel() == 0:
+            du = None
+        has_du = du is not None and m['has_gconv']
+        outs = layer_bwd(u_prev, scale, shift, w_fg, w_mlp if has_du else None, sup if has_du else [],
+                         ctx.sup_needs if has_du else [], drop_mask, rng, a, b,
+                         du.contiguous() if has_du else None,
+                         dz_last.contiguous() if dz_last is not None else None,
+                         m['Lf'], m['taps'], m['dilation'], m['order'], True, m['dropout_p'], m['seed'],
+                         m['offset'])
+        dx_prev, dx_stats, dw_fg, db_fg, dw_mlp, db_mlp = outs[:6]
+        d_sup = outs[6:]
+        if ctx.has_bn:
+            du_prev, dgamma, dbeta = bn_bwd(dx_prev, u_prev, dx_stats, ctx.count, gamma, mean, rstd, True)
+        else:
+            du_prev, dgamma, dbeta = dx_prev.to(u_prev.dtype), None, None
+        g_sup = []
+        for i in range(ctx.n_sup):
+            g_sup.append(d_sup[i] if (has_du and ctx.sup_needs[i]) else None)
+        return (du_prev, None, dgamma, dbeta, None, None, dw_fg, db_fg,
+                dw_mlp if has_du else None, db_mlp if has_du else None, None, None, None, *g_sup)
+
+
+# =========================================================================== head (:231-236, :252-254)
+def _ptr_array(ts: Sequence[Tensor]):
+    arr = (C.c_void_p * _lib.MAX_LAYERS)()
+    for i, t in enumerate(ts):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+@torch.library.custom_op('gwn::head_fwd', mutates_args=())
+def head_fwd(z_last: List[Tensor], w_skip: Tensor, b_skip: Tensor, w_end1: Tensor, b_end1: Tensor, w_end2: Tensor,
+             b_end2: Tensor, out_dim: int) -> Tuple[Tensor, Tensor, Tensor]:
+    z0 = _req(z_last[0], None, 'z_last')
+    N, Lf, V, _c = z0.shape
+    S, E, Opad = w_skip.shape[1], w_end1.shape[1], w_end2.shape[1]
+    P = N * Lf * V
+    f32 = dict(device=z0.device, dtype=torch.float32)
+    s1, e1 = torch.empty((P, S), **f32), torch.empty((P, E), **f32)
+    out = torch.empty((N, out_dim, V, Lf), **f32)
+    ws = torch.empty((P, Opad), **f32)
+    cfg = HeadCfg(N=N, V=V, Lf=Lf, n_layers=len(z_last), S=S, E=E, O=out_dim, dtype=_code(z0.dtype))
+    args = HeadFwdArgs(z_last=_ptr_array(z_last), w_skip=_p(w_skip), b_skip=_p(b_skip), w_end1=_p(w_end1),
+                       b_end1=_p(b_end1), w_end2=_p(w_end2), b_end2=_p(b_end2), s1=_p(s1), e1=_p(e1),
+                       out=_p(out), ws=_p(ws))
+    with torch.cuda.device(z0.device):
+        check(lib().gwn_head_fwd(C.byref(cfg), C.byref(args), _stream()), 'gwn_head_fwd')
+    return out, s1, e1
+
+
+@head_fwd.register_fake
+def _(z_last, w_skip, b_skip, w_end1, b_end1, w_end2, b_end2, out_dim):
+    N, Lf, V, _c = z_last[0].shape
+    f = lambda *s: z_last[0].new_empty(s, dtype=torch.float32)  # noqa: E731
+    return f(N, out_dim, V, Lf), f(N * Lf * V, w_skip.shape[1]), f(N * Lf * V, w_end1.shape[1])
+
+
+@torch.library.custom_op('gwn::head_bwd', mutates_args=())
+def head_bwd(z_last: List[Tensor], w_skip: Tensor, w_end1: Tensor, w_end2: Tensor, s1: Tensor, e1: Tensor,
+             dout: Tensor) -> List[Tensor]:
+    """Returns [dw_skip, db_skip, dw_end1, db_end1, dw_end2, db_end2, dz_last_0, ...]."""
+    z0 = z_last[0]
+    N, Lf, V, _c = z0.shape
+    S, E, Opad = w_skip.shape[1], w_end1.shape[1], w_end2.shape[1]
+    O = dout.shape[1]
+    P = N * Lf * V
+    f32 = dict(device=z0.device, dtype=torch.float32)
+    dw_skip, db_skip = torch.empty_like(w_skip), torch.empty((S,), **f32)
+    dw_end1, db_end1 = torch.empty_like(w_end1), torch.empty((E,), **f32)
+    dw_end2, db_end2 = torch.empty_like(w_end2), torch.empty((Opad,), **f32)
+    dz = [torch.empty_like(z) for z in z_last]
+    ws_do, ws_de1, ws_ds1 = torch.empty((P, Opad), **f32), torch.empty((P, E), **f32), torch.empty((P, S), **f32)
+    cfg = HeadCfg(N=N, V=V, Lf=Lf, n_layers=len(z_last), S=S, E=E, O=O, dtype=_code(z0.dtype))
+    args = HeadBwdArgs(z_last=_ptr_array(z_last), w_skip=_p(w_skip), w_end1=_p(w_end1), w_end2=_p(w_end2),
+                       s1=_p(s1), e1=_p(e1), dout=_p(dout), dw_skip=_p(dw_skip), db_skip=_p(db_skip),
+                       dw_end1=_p(dw_end1), db_end1=_p(db_end1), dw_end2=_p(dw_end2), db_end2=_p(db_end2),
+                       dz_last=_ptr_array(dz), ws_do=_p(ws_do), ws_de1=_p(ws_de1), ws_ds1=_p(ws_ds1))
+    with torch.cuda.device(z0.device):
+        check(lib().gwn_head_bwd(C.byref(cfg), C.byref(args), _stream()), 'gwn_head_bwd')
+    return [dw_skip, db_skip, dw_end1, db_end1, dw_end2, db_end2] + dz
+
+
+@head_bwd.register_fake
+def _(z_last, w_skip, w_end1, w_end2, s1, e1, dout):
+    f = lambda t: torch.empty_like(t)  # noqa: E731
+    z0 = z_last[0]
+    v = lambda n: z0.new_empty((n,), dtype=torch.float32)  # noqa: E731
+    return [f(w_skip), v(w_skip.shape[1]), f(w_end1), v(w_end1.shape[1]), f(w_end2), v(w_end2.shape[1])] + \
+        [f(z) for z in z_last]
+
+
+class SkipHead(torch.autograd.Function):
+    """relu(sum_i Ws_i z_i[..., -Lf:] + sum_i bs_i) -> relu(end_conv_1) -> end_conv_2, NCHW out."""
+
+    @staticmethod
+    def forward(ctx, w_skip, b_skip, w_end1, b_end1, w_end2, b_end2, out_dim, *z_last):
+        zs = [z.contiguous() for z in z_last]
+        out, s1, e1 = head_fwd(zs, w_skip, b_skip, w_end1, b_end1, w_end2, b_end2, out_dim)
+        ctx.save_for_backward(w_skip, w_end1, w_end2, s1, e1, *zs)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        w_skip, w_end1, w_end2, s1, e1, *zs = ctx.saved_tensors
+        outs = head_bwd(list(zs), w_skip, w_end1, w_end2, s1, e1, dout.contiguous().float())
+        return (*outs[:6], None, *outs[6:])
+
+
+# =========================================================================== nconv primitive (:60-66)
+@torch.library.custom_op('gwn::node_mix', mutates_args=())
+def node_mix(x: Tensor, A: Tensor, transpose_a: bool) -> Tensor:
+    """x: [slabs, V, 32] channels-last; returns y[s,w,c] = sum_v x[s,v,c] * A[v,w] (or A[w,v])."""
+    _req(x, None, 'x'); _req(A, torch.float32, 'A')
+    S, V, _c = x.shape
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(lib().gwn_node_mix(_p(x), CH, 0, _p(y), CH, 0, 0, _p(A), int(transpose_a), S, V, _code(x.dtype),
+                                 _stream()), 'gwn_node_mix')
+    return y
+
+
+@node_mix.register_fake
+def _(x, A, transpose_a):
+    return torch.empty_like(x)
