@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""Benchmark of the Graph WaveNet training step (BASELINE.json metric: gwnet train samples/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (N=1 and per rank at N>1, weak scaling): BASELINE config 2 - Graph WaveNet on the 67-node
+county graph, forward/backward transition supports + adaptive adjacency, k=2, 4x2 layers, in_dim 2,
+T=12 -> 12-step forecast, batch 512 per GPU, bf16 activations, dropout 0.3 (reference default).
+A "step" is forward + MSELoss + backward + gradient all-reduce (N>1) + Adam(lr=1e-3) step
+(lit.py:24,29-43,59-61).  Synthetic N(0,1) inputs/targets, seed 42, default (reference-style) random init under seed 42.
+
+`--impl reference` times the reference's CPU implementation of the same path - the oracle port in
+its ATen-call form (the reference is Python-only and cannot travel to the GPU box) - on
+all host cores, on a bounded sample of the same workload.
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(name='config2: gwnet V=67 fwd/bwd+adaptive supports, k=2, 4x2 layers, in_dim=2, T=12, out=12',
+                V=67, in_dim=2, out_dim=12, T=12, kernel_size=2, blocks=4, layers=2, batch_per_gpu=512,
+                dropout=0.3)
+CPU_SAMPLE_BATCH = 64
+
+
+# ------------------------------------------------------------------------------------------ shared setup
+def fl_supports():
+    adj = np.load(os.path.join(ROOT, 'tests', 'golden', 'adj_mx_fl.npy')).astype(np.float32)
+    from multimodal_outage_b200.supports import double_transition
+    return double_transition(adj)
+
+
+def oracle_cfg():
+    from oracle.gwnet_oracle import GWNetConfig
+    w = WORKLOAD
+    return GWNetConfig(num_nodes=w['V'], in_dim=w['in_dim'], out_dim=w['out_dim'], kernel_size=w['kernel_size'],
+                       blocks=w['blocks'], layers=w['layers'], dropout=w['dropout'])
+
+
+def layer_lengths():
+    """[L0, L1, ...] of the workload: pad to the receptive field, then shrink by dilation*(k-1) per layer."""
+    w = WORKLOAD
+    dil = [2 ** i for _ in range(w['blocks']) for i in range(w['layers'])]
+    rf = 1 + sum(d * (w['kernel_size'] - 1) for d in dil)
+    L = [max(w['T'], rf)]
+    for d in dil:
+        L.append(L[-1] - d * (w['kernel_size'] - 1))
+    return L
+
+
+def algorithmic_work(n):
+    """Per-step algorithmic work of the block at batch n (SURVEY §8d formulas, true dims, no padding)."""
+    w = WORKLOAD
+    L = layer_lengths()
+    V, C, H = w['V'], 32, 6
+    hop_fwd = sum(H * 2 * n * C * l * V * V for l in L[1:])
+    mlp_fwd = sum(2 * n * V * l * (H + 1) * C * C for l in L[1:])
+    return dict(L=L, hop_fwd_flops=hop_fwd, mlp_fwd_flops=mlp_fwd)
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_steps(steps, warmup, batch):
+    """fwd + MSE + bwd + Adam on the oracle port (ATen-call form), all host threads. Returns samples/s."""
+    import oracle.gwnet_oracle as go
+    go.ATEN_PATH = True
+    cfg = oracle_cfg()
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = go.synthetic_state_dict(cfg, 42)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()
+              if v.is_floating_point() and 'running' not in k}
+    state = dict(sd); state.update(params)
+    sup = [torch.tensor(s) for s in fl_supports()]
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(batch, cfg.in_dim, cfg.num_nodes, WORKLOAD['T'], generator=g)
+    y = torch.randn(batch, cfg.out_dim, cfg.num_nodes, 1, generator=g)
+    L = go.layer_lengths(cfg, WORKLOAD['T'])
+    opt = torch.optim.Adam(list(params.values()), lr=1e-3)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        masks = [torch.nn.functional.dropout(torch.ones(batch, 32, cfg.num_nodes, L[i + 1]), cfg.dropout, True)
+                 for i in range(cfg.n_layers)]
+        opt.zero_grad(set_to_none=True)
+        out = go.gwnet_forward(state, x, sup, cfg, training=True, dropout_masks=masks)
+        loss = torch.nn.functional.mse_loss(out, y)
+        loss.backward()
+        opt.step()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return batch / sec, sec
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    sps, sec = cpu_reference_steps(args.steps, args.warmup, CPU_SAMPLE_BATCH)
+    cores = torch.get_num_threads()
+    line = {
+        'impl': 'reference', 'metric': 'gwnet train samples/sec', 'value': sps, 'unit': 'samples/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD['name'], 'batch_per_gpu': WORKLOAD['batch_per_gpu'],
+                   'note': 'reference CPU path = oracle port in ATen-call form (reference is Python-only)'},
+        'cpu_baseline': {'value': sps, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+                         'sample': f'batch {CPU_SAMPLE_BATCH} of the {WORKLOAD["batch_per_gpu"]}-sample step, '
+                                   'fwd+MSE+bwd+Adam, fp32, dropout 0.3'},
+        'e2e': {'value': sps, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+class ClockSampler:
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill(); out = ''
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in out.splitlines():
+            f = [t.strip() for t in ln.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def time_events(fn, iters, warmup=3):
+    """Average device time of fn() in ms, CUDA events on the current stream."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def kernel_rooflines(peaks, n):
+    """Live CUDA-event timing of the two kernels the north star names, on layer-0 shapes of the workload
+    (buffers > L2, so every launch streams from HBM)."""
+    import ctypes as C
+    from multimodal_outage_b200 import ops, _lib
+    w = WORKLOAD
+    work = algorithmic_work(n)
+    L1 = work['L'][1]
+    V, slabs, pitch = w['V'], n * L1, 224
+    dev = 'cuda'
+    cat = torch.randn(slabs * V, pitch, device=dev).to(torch.bfloat16)
+    A = torch.rand(V, V, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    lib = _lib.lib()
+
+    def hop():
+        _lib.check(lib.gwn_node_mix(cat.data_ptr(), pitch, 0, cat.data_ptr(), pitch, 32, 0, A.data_ptr(), 0, slabs,
+                                    V, _lib.GWN_BF16, st), 'gwn_node_mix')
+    ms_hop = time_events(hop, 20)
+    flops = 2.0 * slabs * 32 * V * V
+    tf = flops / (ms_hop * 1e-3) / 1e12
+    peak_tf = peaks.get('bf16_tflops', 1590.0)
+    roof = {'kernel': 'node_mix_kernel (one diffusion hop, layer 0)', 'bound': 'tensor', 'achieved': tf,
+            'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': tf / peak_tf, 'traffic': None,
+            'algorithmic_flops_per_launch': flops, 'ms_per_launch': ms_hop,
+            'peak_source': 'MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)'
+            if 'bf16_tflops' in peaks else 'fallback 1590 TFLOP/s'}
+
+    # gated temporal conv (layer 0): read r once, write z once
+    Lin = work['L'][0]
+    u_prev = torch.randn(n, Lin, V, 32, device=dev).to(torch.bfloat16)
+    w_fg = torch.randn(2 * 32, 64, device=dev) / 8
+    b_fg = torch.zeros(64, device=dev)
+
+    def gate():
+        ops.layer_fwd(u_prev, None, None, w_fg, b_fg, None, None, [], None, None, 1, 2, 1, 2, False, False, 0.0, 0, 0)
+    ms_gate = time_events(gate, 20)
+    bytes_alg = (n * 32 * V * Lin + n * 32 * V * L1) * 2.0
+    gbs = bytes_alg / (ms_gate * 1e-3) / 1e9
+    peak_bw = peaks.get('hbm_gbs', 6650.0)
+    gate_roof = {'kernel': 'pos_gemm_kernel<gate> (layer 0 gated conv fwd)', 'bound': 'hbm', 'achieved': gbs,
+                 'peak': peak_bw, 'unit': 'GB/s', 'frac': gbs / peak_bw, 'traffic': None,
+                 'algorithmic_bytes_per_launch': bytes_alg, 'ms_per_launch': ms_gate}
+    return roof, gate_roof
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from multimodal_outage_b200 import gwnet, _lib
+    from multimodal_outage_b200.ddp import BucketedGradAllReduce
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    dev = torch.device('cuda', local)
+    w = WORKLOAD
+    n = w['batch_per_gpu']
+    torch.manual_seed(42)
+    model = gwnet(dev, num_nodes=w['V'], dropout=w['dropout'], supports=[torch.tensor(s) for s in fl_supports()],
+                  in_dim=w['in_dim'], out_dim=w['out_dim'], kernel_size=w['kernel_size'], blocks=w['blocks'],
+                  layers=w['layers'])
+    assert model.layer_lengths(w['T']) == layer_lengths()
+    model.compute_dtype = torch.bfloat16
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True)
+    loss_fn = torch.nn.MSELoss()
+    sync = BucketedGradAllReduce(model) if world > 1 else None
+
+    # distinct batches rotated through the timed loop (inputs differ every step; working set >> L2)
+    R = 4
+    g = torch.Generator().manual_seed(42 + rank)
+    xs_host = [torch.randn(n, w['in_dim'], w['V'], w['T'], generator=g).pin_memory() for _ in range(R)]
+    ys_host = [torch.randn(n, w['out_dim'], w['V'], 1, generator=g).pin_memory() for _ in range(R)]
+    xs = [t.to(dev) for t in xs_host]
+    ys = [t.to(dev) for t in ys_host]
+    x_static, y_static = torch.empty_like(xs[0]), torch.empty_like(ys[0])
+    loss_static = torch.zeros((), device=dev)
+
+    def step_eager(x, y):
+        opt.zero_grad(set_to_none=True)
+        loss = loss_fn(model(x), y)
+        loss.backward()
+        if sync is not None:
+            sync.finish()
+        opt.step()
+        return loss
+
+    use_graph = (world == 1) and not args.no_graph
+    graph = None
+    launches_per_step = None
+    for _ in range(3):                                        # eager warm-up (allocator, rng state, Adam state)
+        step_eager(xs[0], ys[0])
+    torch.cuda.synchronize()
+    c0 = _lib.lib().gwn_launch_count()
+    step_eager(xs[0], ys[0])
+    torch.cuda.synchronize()
+    launches_per_step = _lib.lib().gwn_launch_count() - c0
+    if use_graph:
+        graph = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            x_static.copy_(xs[0]); y_static.copy_(ys[0])
+            step_eager(x_static, y_static)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(graph):
+            loss_static.copy_(step_eager(x_static, y_static).detach())
+
+    def step_resident(i):
+        if graph is not None:
+            x_static.copy_(xs[i % R]); y_static.copy_(ys[i % R])
+            graph.replay()
+            return loss_static
+        return step_eager(xs[i % R], ys[i % R])
+
+    def step_e2e(i):
+        # host (pinned) -> device copy of this step's inputs, the step, device -> host read of the loss
+        if graph is not None:
+            x_static.copy_(xs_host[i % R], non_blocking=True); y_static.copy_(ys_host[i % R], non_blocking=True)
+            graph.replay()
+            return float(loss_static.item())
+        x = xs_host[i % R].to(dev, non_blocking=True); y = ys_host[i % R].to(dev, non_blocking=True)
+        return float(step_eager(x, y).item())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, K, W):
+        for i in range(W):
+            step_fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            step_fn(W + i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(step_resident, args.steps, max(args.warmup, 3))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(step_e2e, args.steps, 3)
+    final_loss = float(step_resident(0).item())
+
+    if rank == 0:
+        peaks = {}
+        pth = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+        if os.path.exists(pth):
+            peaks = json.load(open(pth))
+        roof, gate_roof = kernel_rooflines(peaks, n)
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            sps_cpu, sec_cpu = cpu_reference_steps(3, 1, CPU_SAMPLE_BATCH)
+            cpu = {'value': sps_cpu, 'unit': 'samples/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                   'sample': f'batch {CPU_SAMPLE_BATCH} of the {n}-sample step (fwd+MSE+bwd+Adam, fp32, dropout 0.3), '
+                             f'{sec_cpu:.2f} s/step, oracle port in ATen-call form'}
+        ms_step = ms_total / args.steps
+        value = world * n / (ms_step * 1e-3)
+        e2e_value = world * n / (ms_e2e / args.steps * 1e-3)
+        h2d = xs_host[0].numel() * 4 + ys_host[0].numel() * 4
+        work = algorithmic_work(n)
+        line = {
+            'metric': 'gwnet train samples/sec', 'value': value, 'unit': 'samples/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': {'workload': w['name'], 'batch_per_gpu': n, 'global_batch': world * n, 'dropout': w['dropout'],
+                       'optimizer': 'Adam(lr=1e-3)', 'parallelism': f'dp{world}', 'cuda_graph': bool(graph),
+                       'l2': f'{R} distinct input batches rotated; per-step working set (activations+workspaces, '
+                             '>1 GB) exceeds the 126 MB L2; kernel microbenchmarks use buffers > L2'},
+            'clocks': clocks,
+            'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4},
+            'gpu_launches': int(launches_per_step * args.steps),
+            'gpu_launches_per_step': int(launches_per_step),
+            'roofline': roof, 'roofline_gate': gate_roof, 'cpu_baseline': cpu,
+            'final_loss': final_loss,
+            'algorithmic_gflop_per_step_diffusion_fwd': (work['hop_fwd_flops'] + work['mlp_fwd_flops']) / 1e9,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -38,6 +38,8 @@ enum { GWN_F32 = 0, GWN_BF16 = 1 };
 
 const char* gwn_last_error(void);
 int gwn_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches evidence) */
+long long gwn_launch_count(void);
 /* 0 if the current device is sm_100 (B200); <0 otherwise. */
 int gwn_check_device(void);
 

@@ -61,6 +61,7 @@ _i, _ll, _f, _d = C.c_int, C.c_longlong, C.c_float, C.c_double
 SIGNATURES = {
     'gwn_last_error': (C.c_char_p, []),
     'gwn_version': (_i, []),
+    'gwn_launch_count': (_ll, []),
     'gwn_check_device': (_i, []),
     'gwn_adp_fwd': (_i, [vp, vp, vp, vp, _i, _i, vp]),
     'gwn_adp_bwd': (_i, [vp, vp, vp, vp, vp, vp, vp, _i, _i, vp]),

@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace gwn {
@@ -12,8 +14,11 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 }  // namespace gwn
 
+extern "C" long long gwn_launch_count(void) { return gwn::g_launches.load(); }
 extern "C" const char* gwn_last_error(void) { return gwn::g_err; }
 extern "C" int gwn_version(void) { return 100; }
 

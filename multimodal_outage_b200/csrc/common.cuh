@@ -28,7 +28,12 @@ void set_error(const char* fmt, ...);
     }                                                                          \
   } while (0)
 
-#define GWN_LAUNCHED() GWN_CUDA(cudaPeekAtLastError())
+void count_launch();
+#define GWN_LAUNCHED()                  \
+  do {                                  \
+    ::gwn::count_launch();              \
+    GWN_CUDA(cudaPeekAtLastError());    \
+  } while (0)
 
 typedef __nv_bfloat16 bf16;
 

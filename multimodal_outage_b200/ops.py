@@ -331,6 +331,7 @@ class WaveNetLayer(torch.autograd.Function):
         u, stats, z_last, a, b = layer_fwd(u_prev, scale, shift, w_fg, b_fg, w_mlp, b_mlp, sup, drop_mask, rng,
                                            m['Lf'], m['taps'], m['dilation'], m['order'], training,
                                            m['has_gconv'], m['dropout_p'], m['seed'], m['offset'])
+        ctx.set_materialize_grads(False)      # a dead output (last layer's u) must stay "no gradient"
         ctx.meta = m
         ctx.count = count
         ctx.has_bn = has_bn

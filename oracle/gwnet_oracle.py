@@ -19,6 +19,48 @@ from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence
 
 import torch
+import torch.nn.functional as F
+
+# When True the 1x1 / dilated convolutions and BatchNorm go through the same ATen library calls the
+# reference's nn.Conv2d / nn.BatchNorm2d make (oneDNN on CPU).  Same arithmetic, and the honest form
+# to TIME as the reference's CPU path (bench.py cpu_baseline / --impl reference); the explicit
+# tap-sum form below stays the default for parity checks.  Both are pinned by the golden tests.
+ATEN_PATH = False
+
+
+# --------------------------------------------------------------------------- storage-rounding emulation
+class _StoreRound(torch.autograd.Function):
+    """Emulates a tensor that the 16-bit data path STORES in `dtype`: the forward value is rounded to
+    `dtype` (then carried on in the oracle's working precision) and so is the gradient flowing back
+    through it (gradient activations are stored in the same 16-bit type)."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.dtype = dtype
+        return x.to(dtype).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(ctx.dtype).to(g.dtype), None
+
+
+class _GateSavedRounded(torch.autograd.Function):
+    """z = tanh(f)*sigmoid(g) where the backward uses the 16-bit-rounded saved tanh/sigmoid values."""
+
+    @staticmethod
+    def forward(ctx, f, g, dtype):
+        a, b = torch.tanh(f), torch.sigmoid(g)
+        ctx.save_for_backward(a.to(dtype).to(a.dtype), b.to(dtype).to(b.dtype))
+        return a * b
+
+    @staticmethod
+    def backward(ctx, dz):
+        a, b = ctx.saved_tensors
+        return dz * b * (1 - a * a), dz * a * b * (1 - b), None
+
+
+def _sr(x, dtype):
+    return x if dtype is None else _StoreRound.apply(x, dtype)
 
 
 # --------------------------------------------------------------------------- config
@@ -96,6 +138,8 @@ def adaptive_adjacency(e1: torch.Tensor, e2: torch.Tensor) -> torch.Tensor:
 
 def node_mix(x: torch.Tensor, a: torch.Tensor) -> torch.Tensor:
     """y[n,c,w,l] = sum_v x[n,c,v,l] * A[v,w]   (nconv, graph_wavenet.py:65)."""
+    if ATEN_PATH:
+        return torch.einsum('ncvl,vw->ncwl', x, a).contiguous()
     n, c, v, l = x.shape
     xt = x.permute(0, 1, 3, 2).reshape(-1, v)          # rows (n,c,l), cols v
     return (xt @ a).reshape(n, c, l, a.shape[1]).permute(0, 1, 3, 2)
@@ -103,6 +147,8 @@ def node_mix(x: torch.Tensor, a: torch.Tensor) -> torch.Tensor:
 
 def pointwise(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor]) -> torch.Tensor:
     """1x1 Conv2d: w is [O, C, 1, 1]  (graph_wavenet.py:71,117,164,174,179)."""
+    if ATEN_PATH:
+        return F.conv2d(x, w, b)
     y = torch.einsum('oc,ncvl->novl', w[:, :, 0, 0], x)
     if b is not None:
         y = y + b.view(1, -1, 1, 1)
@@ -112,6 +158,8 @@ def pointwise(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor]) -> to
 def dilated_conv(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, d: int) -> torch.Tensor:
     """Conv2d kernel (1,k), dilation d, no padding (graph_wavenet.py:150-156):
     y[n,o,v,t] = b[o] + sum_{c,j} w[o,c,0,j] * x[n,c,v,t+j*d]."""
+    if ATEN_PATH:
+        return F.conv2d(x, w, b, dilation=d)
     k = w.shape[3]
     lout = x.shape[3] - d * (k - 1)
     y = None
@@ -122,14 +170,14 @@ def dilated_conv(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, d: int) -> t
 
 
 def diffusion_conv(z: torch.Tensor, supports: Sequence[torch.Tensor], w: torch.Tensor,
-                   b: torch.Tensor, order: int) -> torch.Tensor:
+                   b: torch.Tensor, order: int, storage=None) -> torch.Tensor:
     """gcn.forward before dropout (graph_wavenet.py:85-96): concat order is
     [z, zA0, zA0^2, zA1, zA1^2, ...]; powers are sequential re-applications."""
     pieces = [z]
     for a in supports:
         y = z
         for _ in range(order):
-            y = node_mix(y, a)
+            y = _sr(node_mix(y, a), storage)
             pieces.append(y)
     return pointwise(torch.cat(pieces, dim=1), w, b)
 
@@ -137,6 +185,11 @@ def diffusion_conv(z: torch.Tensor, supports: Sequence[torch.Tensor], w: torch.T
 def batch_norm_train(u: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float):
     """Training-mode BatchNorm2d (graph_wavenet.py:167,250): biased variance
     normalises; returns (y, batch_mean, biased_var)."""
+    if ATEN_PATH:
+        with torch.no_grad():
+            mean = u.mean(dim=(0, 2, 3))
+            var = u.var(dim=(0, 2, 3), unbiased=False)
+        return F.batch_norm(u, None, None, gamma, beta, True, 0.0, eps), mean, var
     mean = u.mean(dim=(0, 2, 3))
     var = ((u - mean.view(1, -1, 1, 1)) ** 2).mean(dim=(0, 2, 3))
     y = (u - mean.view(1, -1, 1, 1)) / torch.sqrt(var.view(1, -1, 1, 1) + eps)
@@ -165,7 +218,7 @@ def gwnet_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor,
                   fixed_supports: Sequence[torch.Tensor], cfg: GWNetConfig, *,
                   training: bool = True,
                   dropout_masks: Optional[Sequence[Optional[torch.Tensor]]] = None,
-                  trace: Optional[ForwardTrace] = None) -> torch.Tensor:
+                  trace: Optional[ForwardTrace] = None, storage=None) -> torch.Tensor:
     """General-mode ``gwnet.forward`` (graph_wavenet.py:188-256 without the two
     literal ``.view`` statements at :189 and :255).
 
@@ -175,12 +228,19 @@ def gwnet_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor,
     (0 or 1/(1-p)) applied to layer i's gcn output, ``[N, C, V, L_i]``; ``None``
     means dropout is inactive (p = 0 or eval).  Running statistics are not
     mutated; their would-be new values are returned through ``trace``.
+
+    ``storage`` (None or torch.bfloat16): emulate the 16-bit data path by rounding every tensor that
+    path STORES in 16 bits (the pre-BN stream u, the gate output z, every diffusion hop, the saved
+    tanh/sigmoid, and the gradients flowing through them), at the points the CUDA kernels store them;
+    all arithmetic between those points stays in the oracle's working precision (the kernels
+    accumulate in fp32).  Used for the bf16 parity tests: ReLU/relu-mask decisions then see the same
+    rounded activations as the kernels do ("bf16 parity").
     """
     rf = receptive_field(cfg)
     t_in = x.shape[3]
     if t_in < rf:                                            # :191-195
         x = torch.cat([x.new_zeros(x.shape[0], x.shape[1], x.shape[2], rf - t_in), x], dim=3)
-    h = pointwise(x, sd['start_conv.weight'], sd['start_conv.bias'])      # :196
+    h = _sr(pointwise(x, sd['start_conv.weight'], sd['start_conv.bias']), storage)      # :196
 
     supports = list(fixed_supports)
     if cfg.gcn_bool and cfg.adaptive:                        # :201-203
@@ -197,19 +257,29 @@ def gwnet_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor,
             trace.x_in.append(res)
         f = dilated_conv(res, sd[f'filter_convs.{i}.weight'], sd[f'filter_convs.{i}.bias'], dil[i])
         g = dilated_conv(res, sd[f'gate_convs.{i}.weight'], sd[f'gate_convs.{i}.bias'], dil[i])
-        z = torch.tanh(f) * torch.sigmoid(g)                 # :222-226
+        if storage is None:
+            z = torch.tanh(f) * torch.sigmoid(g)             # :222-226
+        else:
+            z = _sr(_GateSavedRounded.apply(f, g, storage), storage)
         s = pointwise(z, sd[f'skip_convs.{i}.weight'], sd[f'skip_convs.{i}.bias'])   # :231
         skip = s if skip is None else s + skip[:, :, :, -s.shape[3]:]                # :232-236
         if cfg.gcn_bool:
             hh = diffusion_conv(z, supports, sd[f'gconv.{i}.mlp.mlp.weight'],
-                                sd[f'gconv.{i}.mlp.mlp.bias'], cfg.order)            # :241
+                                sd[f'gconv.{i}.mlp.mlp.bias'], cfg.order, storage)   # :241
             if training and dropout_masks is not None and dropout_masks[i] is not None:
                 hh = hh * dropout_masks[i]                   # :97
         else:
             hh = pointwise(z, sd[f'residual_convs.{i}.weight'], sd[f'residual_convs.{i}.bias'])  # :245
         u = hh + res[:, :, :, -hh.shape[3]:]                 # :247
         if training:                                         # :250
-            h, mean, var = batch_norm_train(u, sd[f'bn.{i}.weight'], sd[f'bn.{i}.bias'], cfg.bn_eps)
+            if storage is None:
+                h, mean, var = batch_norm_train(u, sd[f'bn.{i}.weight'], sd[f'bn.{i}.bias'], cfg.bn_eps)
+            else:   # statistics from the fp32 epilogue values, normalisation applied to the stored (rounded) u
+                mean = u.mean(dim=(0, 2, 3))
+                var = ((u - mean.view(1, -1, 1, 1)) ** 2).mean(dim=(0, 2, 3))
+                us = _sr(u, storage)
+                h = (us - mean.view(1, -1, 1, 1)) / torch.sqrt(var.view(1, -1, 1, 1) + cfg.bn_eps)
+                h = h * sd[f'bn.{i}.weight'].view(1, -1, 1, 1) + sd[f'bn.{i}.bias'].view(1, -1, 1, 1)
             if trace is not None:
                 cnt = u.numel() // u.shape[1]
                 unbiased = var * (cnt / max(cnt - 1, 1))
@@ -219,7 +289,7 @@ def gwnet_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor,
                 trace.new_running[f'bn.{i}.running_var'] = \
                     (1 - m) * sd[f'bn.{i}.running_var'] + m * unbiased.detach()
         else:
-            h = batch_norm_eval(u, sd[f'bn.{i}.weight'], sd[f'bn.{i}.bias'],
+            h = batch_norm_eval(_sr(u, storage), sd[f'bn.{i}.weight'], sd[f'bn.{i}.bias'],
                                 sd[f'bn.{i}.running_mean'], sd[f'bn.{i}.running_var'], cfg.bn_eps)
         if trace is not None:
             trace.z.append(z)
@@ -323,3 +393,21 @@ def synthetic_state_dict(cfg: GWNetConfig, seed: int, dtype=torch.float32) -> Di
             arr = rng.standard_normal(shp) / np.sqrt(fan_in)
         sd[name] = torch.tensor(np.asarray(arr, dtype=np.float64)).to(dtype)
     return sd
+
+
+# --------------------------------------------------------------------------- one layer, for per-op parity
+def wavenet_layer(res: torch.Tensor, wf, bf, wg, bg, wm, bm, supports: Sequence[torch.Tensor], dilation: int,
+                  order: int = 2, dropout_mask: Optional[torch.Tensor] = None, storage=None):
+    """One iteration of the reference's layer loop (graph_wavenet.py:220-247) on an already
+    batch-normalised input ``res`` [N,C,V,L]: returns (u = gcn(z)+res[..., -L':], z).  ``storage``
+    rounds z and every hop (and their gradients) to the 16-bit type as the CUDA data path does."""
+    f = dilated_conv(res, wf, bf, dilation)
+    g = dilated_conv(res, wg, bg, dilation)
+    if storage is None:
+        z = torch.tanh(f) * torch.sigmoid(g)
+    else:
+        z = _sr(_GateSavedRounded.apply(f, g, storage), storage)
+    hh = diffusion_conv(z, supports, wm, bm, order, storage)
+    if dropout_mask is not None:
+        hh = hh * dropout_mask
+    return hh + res[:, :, :, -hh.shape[3]:], z

@@ -30,7 +30,7 @@ def rel(a, b):
 
 
 def oracle_run(cfg, sd, x_np, sup_np, target_np=None, literal=False, horizon=None, dtype=torch.float64,
-               dropout_masks=None, training=True):
+               dropout_masks=None, training=True, storage=None):
     """Runs the CPU oracle (fp64 by default); returns out, loss, grads dict, trace."""
     sdo = {}
     for k, v in sd.items():
@@ -43,9 +43,10 @@ def oracle_run(cfg, sd, x_np, sup_np, target_np=None, literal=False, horizon=Non
     tr = ForwardTrace()
     if literal:
         out = gwnet_forward_literal(sdo, x, sup, cfg, horizon, training=training, trace=tr,
-                                    dropout_masks=dropout_masks)
+                                    dropout_masks=dropout_masks, storage=storage)
     else:
-        out = gwnet_forward(sdo, x, sup, cfg, training=training, trace=tr, dropout_masks=dropout_masks)
+        out = gwnet_forward(sdo, x, sup, cfg, training=training, trace=tr, dropout_masks=dropout_masks,
+                            storage=storage)
     loss = None
     grads = {}
     if target_np is not None and training:

