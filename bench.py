@@ -218,7 +218,8 @@ def kernel_rooflines(peaks, n):
     b_fg = torch.zeros(64, device=dev)
 
     def gate():
-        ops.layer_fwd(u_prev, None, None, w_fg, b_fg, None, None, [], None, None, 1, 2, 1, 2, False, False, 0.0, 0, 0)
+        ops.layer_fwd(u_prev, None, None, w_fg, b_fg, None, None, [], None, None, None, 1, 2, 1, 2, False, False, 0.0,
+                      0, 0)
     ms_gate = time_events(gate, 20)
     bytes_alg = (n * 32 * V * Lin + n * 32 * V * L1) * 2.0
     gbs = bytes_alg / (ms_gate * 1e-3) / 1e9

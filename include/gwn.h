@@ -91,6 +91,7 @@ typedef struct {
   const void* drop_mask;        /* optional explicit mask [N,Lout,V,32] (dtype); overrides Philox */
   const uint64_t* rng;          /* optional DEVICE {seed, offset}: overrides cfg.seed, added to cfg.offset
                                    (keeps the mask fresh across CUDA-graph replays) */
+  const void* hop_mats;         /* optional gwn_hop_mats_prep images: bf16 hops run on tcgen05 */
   void* a;                      /* out (training) tanh(f)   [N,Lout,V,32] */
   void* b;                      /* out (training) sigmoid(g) */
   void* z_last;                 /* out [N,Lf,V,32] */
@@ -109,6 +110,7 @@ typedef struct {
   int support_needs_grad[GWN_MAX_SUPPORTS];
   const void* drop_mask;
   const uint64_t* rng;
+  const void* hop_mats;
   const void* a; const void* b;
   /* incoming gradients */
   const void* du;               /* [N,Lout,V,32] (dtype) or NULL (dead gconv: last layer) */
@@ -172,6 +174,16 @@ typedef struct {
   float* ws_ds1;          /* [P,S] */
 } gwn_head_bwd_args;
 int gwn_head_bwd(const gwn_head_cfg* cfg, const gwn_head_bwd_args* a, void* stream);
+
+/* ---- tensor-core (tcgen05) diffusion hops for on-chip-resident supports (V <= 128), bf16 ----
+ * gwn_hop_mats_prep builds, once per forward, the UMMA A-operand images of every support:
+ * image 4*s+0 = A_s^T, 4*s+1 = (A_s^2)^T (forward hops), 4*s+2 = A_s, 4*s+3 = A_s^2 (backward hops),
+ * bf16, K-major no-swizzle canonical layout, zero padded to [Kp/8][128][8], Kp = 16*ceil(V/16).
+ * `supports` is a HOST array of device pointers.  gwn_hop_tc runs one hop (tests / microbench). */
+int gwn_hop_mats_bytes(int V, int n_supports);
+int gwn_hop_mats_prep(const float* const* supports, int n_supports, int V, void* out, void* stream);
+int gwn_hop_tc(const void* mats, int n_mats, int mat, void* buf, int pitch, int slot_in, int slot_out,
+               int slabs, int V, void* stream);
 
 /* ---- nconv primitive, exposed for unit tests  graph_wavenet.py:60-66 ----
  * y[s,w,c] = sum_v x[s,v,c] * A[v,w] (transpose_a=0) or A[w,v] (transpose_a=1);

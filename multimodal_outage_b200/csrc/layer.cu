@@ -3,7 +3,10 @@
 //   hops  : nconv  y[s,w,c] = sum_v x[s,v,c] A[v,w]                                     (:60-66,:87-93)
 //   mlp   : 1x1 conv over the never-materialised-in-NCHW concat + bias + dropout        (:95-97)
 //           + residual add with the cropped, BN-folded input (:247) + BN statistics     (:250)
+#include <type_traits>
+
 #include "gemm.cuh"
+#include "tc_hops.cuh"
 
 namespace gwn {
 
@@ -402,9 +405,41 @@ static int check_cfg(const gwn_layer_cfg* c) {
   return 0;
 }
 
+// tensor-core path available for this layer?  (bf16 storage, images prepared, supports fit on chip)
+template <typename T>
+static bool use_tc_hops(const gwn_layer_cfg* c, const void* hop_mats) {
+  if constexpr (!std::is_same<T, bf16>::value) return false;
+  return hop_mats != nullptr && c->order == 2 && c->n_supports >= 1 &&
+         hops_tc_supported(c->V, 2 * c->n_supports) != 0;
+}
+
+static void hop_params_base(HopParams& p, const gwn_layer_cfg* c, bf16* buf, int pitch, const void* hop_mats) {
+  p.in[0] = p.in[1] = buf; p.out[0] = p.out[1] = buf;
+  p.in_pitch[0] = p.in_pitch[1] = p.out_pitch[0] = p.out_pitch[1] = pitch;
+  p.mats = reinterpret_cast<const bf16*>(hop_mats);
+  p.V = c->V; p.slabs = c->N * c->Lout;
+}
+
+// forward hops on tcgen05: the z tile is loaded once, all 2*S outputs (A_s and A_s^2) come from it
+static int hops_forward_tc(const gwn_layer_cfg* c, bf16* cat, int mlp_in, const void* hop_mats, cudaStream_t st) {
+  HopParams p{};
+  hop_params_base(p, c, cat, mlp_in, hop_mats);
+  const int nh = 2 * c->n_supports;
+  p.n_mats = nh; p.n_steps = nh; p.n_outs = nh;
+  for (int j = 0; j < nh; ++j) {
+    p.mat_src[j] = 4 * (j / 2) + (j % 2);                 // A_s^T, (A_s^2)^T
+    p.steps[j] = HopStep{0, 0, j, j & 1, TH_FIRST | TH_LAST | (j == 0 ? TH_LOAD : 0) | (j == nh - 1 ? TH_RELEASE : 0)};
+    p.outs[j] = HopOut{0, 1 + j, -1, 0};
+  }
+  return launch_hops_tc(p, st);
+}
+
 template <typename T>
 static int hops_forward(const gwn_layer_cfg* c, T* cat, int mlp_in, const float* const* supports,
-                        cudaStream_t st) {
+                        const void* hop_mats, cudaStream_t st) {
+  if constexpr (std::is_same<T, bf16>::value) {
+    if (use_tc_hops<T>(c, hop_mats)) return hops_forward_tc(c, cat, mlp_in, hop_mats, st);
+  }
   const long long slabs = (long long)c->N * c->Lout;
   for (int s = 0; s < c->n_supports; ++s)
     for (int k = 1; k <= c->order; ++k) {
@@ -440,7 +475,7 @@ static int layer_fwd_t(const gwn_layer_cfg* c, const gwn_layer_fwd_args* g, cuda
   if (int rc = launch_pos_gemm<T, 64>(A, g->w_fg, 64, eg, st)) return rc;
   if (!c->has_gconv) return 0;
   // diffusion hops into the concat slots, then mlp + dropout + residual + stats
-  if (int rc = hops_forward<T>(c, cat, mlp_in, g->supports, st)) return rc;
+  if (int rc = hops_forward<T>(c, cat, mlp_in, g->supports, g->hop_mats, st)) return rc;
   GWN_CUDA(cudaMemsetAsync(g->stats, 0, sizeof(double) * 64, st));
   GemmA M{};
   M.n_chunks = nslots; M.rows_per_n_out = RO; M.P = P;
@@ -476,7 +511,7 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
     // recompute the concat (z and its hops)
     zfill_kernel<T><<<eb, 256, 0, st>>>(a, b, cat, mlp_in, P);
     GWN_LAUNCHED();
-    if (int rc = hops_forward<T>(c, cat, mlp_in, g->supports, st)) return rc;
+    if (int rc = hops_forward<T>(c, cat, mlp_in, g->supports, g->hop_mats, st)) return rc;
     // dh = du * mask
     const T* dh = du;
     const bool drop = c->training && (g->drop_mask != nullptr || c->dropout_p > 0.f);
@@ -502,7 +537,48 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
     D.ch[0].w_off = 0;
     EpiStoreT<T> es{}; es.out = dcat; es.pitch = mlp_in;
     if (int rc = launch_pos_gemm_wt<T, 32>(D, g->w_mlp, mlp_in, 32, es, st)) return rc;
-    // hops backward (reverse order inside each support)
+    // hops backward
+    bool tc_done = false;
+    if constexpr (std::is_same<T, bf16>::value) {
+      if (use_tc_hops<T>(c, g->hop_mats)) {
+        // (1) supports that need dA: g1' = g1 + g2 * A^T (in place in the y1 slot), then dA from (z, g1'), (y1, g2)
+        for (int s = 0; s < c->n_supports; ++s) {
+          if (!(g->support_needs_grad[s] && g->d_supports[s])) continue;
+          HopParams p{};
+          hop_params_base(p, c, dcat, mlp_in, g->hop_mats);
+          p.n_mats = 1; p.mat_src[0] = 4 * s + 2; p.n_steps = 1; p.n_outs = 1;
+          p.steps[0] = HopStep{0, 2 * s + 2, 0, 0, TH_LOAD | TH_RELEASE | TH_FIRST | TH_LAST};
+          p.outs[0] = HopOut{0, 2 * s + 1, 0, 2 * s + 1};
+          if (int rc = launch_hops_tc(p, st)) return rc;
+          if (int rc = launch_dadj<T>(cat, mlp_in, (2 * s + 1) * 32, dcat, mlp_in, (2 * s + 2) * 32, g->d_supports[s],
+                                      slabs, c->V, st)) return rc;
+          if (int rc = launch_dadj<T>(cat, mlp_in, 0, dcat, mlp_in, (2 * s + 1) * 32, g->d_supports[s], slabs, c->V, st))
+            return rc;
+        }
+        // (2) dz = g0 + sum_s [ g1_s A_s^T + g2_s (A_s^2)^T ]  (one accumulator; g1' A^T where step (1) ran)
+        HopParams p{};
+        hop_params_base(p, c, dcat, mlp_in, g->hop_mats);
+        int n = 0;
+        for (int s = 0; s < c->n_supports; ++s) {
+          const bool folded = g->support_needs_grad[s] && g->d_supports[s];
+          p.mat_src[n] = 4 * s + 2;
+          p.steps[n] = HopStep{0, 2 * s + 1, n, 0, TH_LOAD | TH_RELEASE};
+          ++n;
+          if (!folded) {
+            p.mat_src[n] = 4 * s + 3;
+            p.steps[n] = HopStep{0, 2 * s + 2, n, 0, TH_LOAD | TH_RELEASE};
+            ++n;
+          }
+        }
+        p.steps[0].flags |= TH_FIRST;
+        p.steps[n - 1].flags |= TH_LAST;
+        p.n_mats = n; p.n_steps = n; p.n_outs = 1;
+        p.outs[0] = HopOut{0, 0, 0, 0};
+        if (int rc = launch_hops_tc(p, st)) return rc;
+        tc_done = true;
+      }
+    }
+    if (!tc_done)
     for (int s = 0; s < c->n_supports; ++s)
       for (int k = c->order; k >= 1; --k) {
         int slot = 1 + s * c->order + (k - 1);

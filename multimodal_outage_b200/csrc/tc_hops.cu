@@ -1,0 +1,291 @@
+// Diffusion hops on the 5th-gen tensor cores (tcgen05), for graphs whose supports fit on chip (V <= 128).
+//
+//   out[s, w, c] = sum_terms sum_v Mop_t[w, v] * in_t[s, v, c]   (+ add-in)      (nconv, graph_wavenet.py:60-66)
+//
+// Orientation: M = output node w (128 TMEM lanes, V of them used), N = (slab, channel) = 8 slabs x 32 = 256,
+// K = input node v (padded to a multiple of 16).
+//   A operand  : the support / its square / their transposes, bf16, RESIDENT in shared memory for the whole
+//                kernel, K-major no-swizzle canonical layout (built once per forward by hop_mats_prep_kernel).
+//   B operand  : one channels-last activation tile [8 slabs][V][32] streamed HBM -> smem with 16-byte cp.async
+//                straight into the MN-major no-swizzle canonical layout (no TMA tensor map: the tile is a
+//                gather of 64-byte rows out of a 448-byte-pitch concat buffer, with zero-filled K padding).
+//   D          : fp32 in TMEM, two 256-column accumulators so the epilogue of one output overlaps the MMAs of
+//                the next.  Epilogue: tcgen05.ld -> (+ add-in) -> bf16 -> 64-byte stores into the concat slot.
+// Roles (288 threads): warps 0-3 producers, warp 4 lane 0 MMA issuer (+TMEM alloc), warps 5-8 epilogue.
+// Persistent: grid = min(tiles, SMs); each CTA walks tiles of 8 slabs.
+#include "tc.cuh"
+#include "tc_hops.cuh"
+
+namespace gwn {
+
+__global__ void __launch_bounds__(TH_THREADS, 1) hops_tc_kernel(const __grid_constant__ HopParams p) {
+  using namespace tc;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Kp = p.Kp, V = p.V;
+  const uint32_t mat_bytes = (uint32_t)(Kp / 8) * 2048u;
+  const uint32_t stage_bytes = 32u * (uint32_t)Kp * 16u;
+  uint8_t* mats_s = smem;
+  uint8_t* stage_s = smem + (size_t)p.n_mats * mat_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_s + 2 * (size_t)stage_bytes);
+  uint64_t* full = bars;          // [2]
+  uint64_t* empty = bars + 2;     // [2]
+  uint64_t* tfull = bars + 4;     // [2]
+  uint64_t* tempty = bars + 6;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], TH_PRODUCERS);
+      mbar_init(&empty[i], 1);
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == TH_MMA_WARP) tmem_alloc(tmem_slot, 512);
+  {  // resident A operands: global image -> smem (generic proxy writes, then made visible to the async proxy)
+    const int per16 = (int)(mat_bytes / 16);
+    for (int m = 0; m < p.n_mats; ++m) {
+      const uint4* src = reinterpret_cast<const uint4*>(p.mats) + (size_t)p.mat_src[m] * per16;
+      uint4* dst = reinterpret_cast<uint4*>(mats_s + (size_t)m * mat_bytes);
+      for (int i = tid; i < per16; i += TH_THREADS) dst[i] = __ldg(src + i);
+    }
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < TH_MMA_WARP) {
+    // ===================== producers: cp.async tiles into the MN-major canonical layout =====================
+    int g = 0;
+    const int cg = tid & 3, vv = tid >> 2;  // this thread's 16-byte column group and first K row
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      const long long slab0 = (long long)tile * 8;
+      for (int si = 0; si < p.n_steps; ++si) {
+        const HopStep st = p.steps[si];
+        if (!(st.flags & TH_LOAD)) continue;
+        const int stage = g & 1, phase = (g >> 1) & 1;
+        mbar_wait(&empty[stage], (uint32_t)(phase ^ 1));
+        const bf16* base = p.in[st.in_buf] + st.in_slot * 32;
+        const int pitch = p.in_pitch[st.in_buf];
+        const uint32_t sdst = smem_u32(stage_s + (size_t)stage * stage_bytes);
+#pragma unroll 2
+        for (int s = 0; s < 8; ++s) {
+          const long long slab = slab0 + s;
+          const bool sok = slab < p.slabs;
+          const bf16* srow = base + slab * V * (long long)pitch + cg * 8;
+          const uint32_t drow = sdst + (uint32_t)((s * 4 + cg) * Kp) * 16u;
+          for (int v = vv; v < Kp; v += TH_PRODUCERS / 4) {
+            const bool ok = sok && (v < V);
+            cp_async16(drow + (uint32_t)v * 16u, ok ? srow + (long long)v * pitch : base, ok ? 16u : 0u);
+          }
+        }
+        cp_async_commit();
+        if (g > 0) {
+          cp_async_wait<1>();
+          fence_proxy_async();
+          mbar_arrive(&full[(g - 1) & 1]);
+        }
+        ++g;
+      }
+    }
+    if (g > 0) {
+      cp_async_wait<0>();
+      fence_proxy_async();
+      mbar_arrive(&full[(g - 1) & 1]);
+    }
+  } else if (warp == TH_MMA_WARP) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, 256, /*a_mn=*/false, /*b_mn=*/true);
+      const uint32_t mats_addr = smem_u32(mats_s), stage_addr = smem_u32(stage_s);
+      int g = 0, stage = 0;
+      uint32_t acc_uses[2] = {0u, 0u};
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int si = 0; si < p.n_steps; ++si) {
+          const HopStep st = p.steps[si];
+          if (st.flags & TH_LOAD) {
+            stage = g & 1;
+            mbar_wait(&full[stage], (uint32_t)((g >> 1) & 1));
+            ++g;
+          }
+          if (st.flags & TH_FIRST) mbar_wait(&tempty[st.acc], (acc_uses[st.acc] & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t a0 = mats_addr + (uint32_t)st.mat * mat_bytes;
+          const uint32_t b0 = stage_addr + (uint32_t)stage * stage_bytes;
+          const uint32_t d = tmem_base + (uint32_t)st.acc * 256u;
+          for (int ks = 0; ks < Kp / 16; ++ks) {
+            const uint64_t adesc = make_smem_desc(a0 + (uint32_t)ks * 4096u, 2048u, 128u);
+            const uint64_t bdesc = make_smem_desc(b0 + (uint32_t)ks * 256u, 128u, (uint32_t)Kp * 16u);
+            umma_bf16(d, adesc, bdesc, idesc, ((st.flags & TH_FIRST) && ks == 0) ? 0u : 1u);
+          }
+          if (st.flags & TH_RELEASE) umma_commit(&empty[stage]);
+          if (st.flags & TH_LAST) {
+            umma_commit(&tfull[st.acc]);
+            acc_uses[st.acc]++;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue: TMEM -> registers -> (+add) -> bf16 -> concat slot =====================
+    const int quad = warp & 3;
+    const int w = quad * 32 + lane;
+    uint32_t acc_uses[2] = {0u, 0u};
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      const long long slab0 = (long long)tile * 8;
+      int o = 0;
+      for (int si = 0; si < p.n_steps; ++si) {
+        const HopStep st = p.steps[si];
+        if (!(st.flags & TH_LAST)) continue;
+        const HopOut ho = p.outs[o++];
+        mbar_wait(&tfull[st.acc], acc_uses[st.acc] & 1u);
+        acc_uses[st.acc]++;
+        tc_fence_after();
+        bf16* obase = p.out[ho.buf] + ho.slot * 32;
+        const int opitch = p.out_pitch[ho.buf];
+#pragma unroll 1
+        for (int s = 0; s < 8; ++s) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)st.acc * 256u + (uint32_t)s * 32u, v);
+          const long long slab = slab0 + s;
+          if (w < V && slab < p.slabs) {
+            const long long row = slab * V + w;
+            if (ho.add_buf >= 0) {
+              const bf16* ap = p.in[ho.add_buf] + row * (long long)p.in_pitch[ho.add_buf] + ho.add_slot * 32;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float t[4];
+                load4(ap + 4 * j, t);
+                v[4 * j] += t[0]; v[4 * j + 1] += t[1]; v[4 * j + 2] += t[2]; v[4 * j + 3] += t[3];
+              }
+            }
+            bf16* dp = obase + row * (long long)opitch;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 pk;
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
+              __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+              __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+              pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+              pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(dp + 8 * j) = pk;
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty[st.acc]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TH_MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// image[m][kc][r][e] = Mop[r][kc*8+e] in bf16; Mop = X or X^T, X = A or A*A (fp32 product), zero padded.
+struct MatPrep {
+  const float* A[GWN_MAX_SUPPORTS];
+  int n, V, Kp;
+};
+__global__ void hop_mats_prep_kernel(MatPrep mp, bf16* __restrict__ out) {
+  // matrix index m = 4*s + variant; variant: 0 = A^T, 1 = (A^2)^T (forward), 2 = A, 3 = A^2 (backward)
+  const int per_mat = (mp.Kp / 8) * 128 * 8;
+  const long long total = (long long)mp.n * 4 * per_mat;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int m = (int)(i / per_mat), rem = (int)(i % per_mat);
+    int kc = rem / 1024, r = (rem / 8) % 128, e = rem % 8;
+    int k = kc * 8 + e;
+    int s = m / 4, variant = m % 4;
+    float val = 0.f;
+    if (r < mp.V && k < mp.V) {
+      const float* A = mp.A[s];
+      const bool transpose = variant < 2, square = variant & 1;
+      int row = transpose ? k : r, col = transpose ? r : k;  // X[row][col]
+      if (!square) {
+        val = A[(long long)row * mp.V + col];
+      } else {
+        float acc = 0.f;
+        for (int t = 0; t < mp.V; ++t) acc = fmaf(A[(long long)row * mp.V + t], A[(long long)t * mp.V + col], acc);
+        val = acc;
+      }
+    }
+    out[i] = __float2bfloat16_rn(val);
+  }
+}
+
+static int g_sm_count = 0;
+
+int hops_tc_supported(int V, int n_mats) {
+  if (V > 128 || n_mats > TH_MAX_MATS) return 0;
+  int Kp = ((V + 15) / 16) * 16;
+  size_t need = (size_t)n_mats * (Kp / 8) * 2048 + 2 * (size_t)32 * Kp * 16 + 128;
+  return need <= 227 * 1024 ? 1 : 0;
+}
+
+int launch_hops_tc(HopParams& p, cudaStream_t st) {
+  if (p.slabs <= 0) return 0;
+  p.Kp = ((p.V + 15) / 16) * 16;
+  p.n_tiles = (int)cdiv(p.slabs, 8);
+  GWN_REQUIRE(p.n_steps >= 1 && p.n_steps <= TH_MAX_STEPS && p.n_outs <= TH_MAX_OUTS, "hops_tc: too many steps");
+  GWN_REQUIRE(hops_tc_supported(p.V, p.n_mats), "hops_tc: V=%d with %d resident matrices does not fit in smem", p.V,
+              p.n_mats);
+  size_t smem = (size_t)p.n_mats * (p.Kp / 8) * 2048 + 2 * (size_t)32 * p.Kp * 16 + 128;
+  if (g_sm_count == 0) {
+    int dev = 0;
+    GWN_CUDA(cudaGetDevice(&dev));
+    GWN_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+    GWN_CUDA(cudaFuncSetAttribute(hops_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  }
+  int grid = p.n_tiles < g_sm_count ? p.n_tiles : g_sm_count;
+  hops_tc_kernel<<<grid, TH_THREADS, smem, st>>>(p);
+  GWN_LAUNCHED();
+  return 0;
+}
+
+}  // namespace gwn
+
+using namespace gwn;
+
+extern "C" int gwn_hop_mats_bytes(int V, int n_supports) {
+  int Kp = ((V + 15) / 16) * 16;
+  return n_supports * 4 * (Kp / 8) * 2048;
+}
+
+extern "C" int gwn_hop_mats_prep(const float* const* supports, int n_supports, int V, void* out, void* stream) {
+  GWN_REQUIRE(supports && out && n_supports >= 1 && n_supports <= GWN_MAX_SUPPORTS && V >= 1 && V <= 128,
+              "hop_mats_prep: bad argument (V=%d must be <= 128)", V);
+  MatPrep mp{};
+  for (int i = 0; i < n_supports; ++i) mp.A[i] = supports[i];
+  mp.n = n_supports; mp.V = V; mp.Kp = ((V + 15) / 16) * 16;
+  long long total = (long long)n_supports * 4 * (mp.Kp / 8) * 1024;
+  hop_mats_prep_kernel<<<(unsigned)cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      mp, reinterpret_cast<bf16*>(out));
+  GWN_LAUNCHED();
+  return 0;
+}
+
+// Test/bench entry: one tensor-core hop  y[slot_out] = Mop[mat] * x[slot_in]  over a pitched bf16 buffer.
+extern "C" int gwn_hop_tc(const void* mats, int n_mats, int mat, void* buf, int pitch, int slot_in, int slot_out,
+                          int slabs, int V, void* stream) {
+  GWN_REQUIRE(mats && buf && mat >= 0 && mat < n_mats && pitch % 8 == 0, "hop_tc: bad argument");
+  HopParams p{};
+  p.in[0] = p.in[1] = reinterpret_cast<const bf16*>(buf);
+  p.out[0] = p.out[1] = reinterpret_cast<bf16*>(buf);
+  p.in_pitch[0] = p.in_pitch[1] = p.out_pitch[0] = p.out_pitch[1] = pitch;
+  p.mats = reinterpret_cast<const bf16*>(mats);
+  p.n_mats = 1; p.mat_src[0] = mat; p.V = V; p.slabs = slabs;
+  p.n_steps = 1; p.n_outs = 1;
+  p.steps[0] = HopStep{0, slot_in, 0, 0, TH_LOAD | TH_RELEASE | TH_FIRST | TH_LAST};
+  p.outs[0] = HopOut{0, slot_out, -1, 0};
+  return launch_hops_tc(p, reinterpret_cast<cudaStream_t>(stream));
+}

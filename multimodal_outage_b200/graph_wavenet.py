@@ -150,6 +150,7 @@ class gwnet(nn.Module):
         self.out_dim = out_dim
         self.kernel_size = kernel_size
         self.compute_dtype: Optional[torch.dtype] = None    # None: follow autocast, else fp32
+        self.use_tensor_cores = True                        # bf16 hops on tcgen05 when the supports fit on chip
         self.dropout_mode = 'fused'                         # 'fused' (in-kernel Philox) | 'torch' (F.dropout mask)
 
         # registration order below mirrors graph_wavenet.py:110-183 so state_dict keys (and a seeded
@@ -291,6 +292,12 @@ class gwnet(nn.Module):
                 rng = self._rng_state.clone()                # this step's {seed, offset}
                 self._rng_state[1] += nl                     # graph-safe: advances on every replay
 
+        # bf16 + supports that fit on chip: diffusion hops run on the tcgen05 tensor cores; the UMMA operand
+        # images of (A, A^2, A^T, (A^2)^T) are built once per forward and shared by all layers
+        hop_mats = None
+        if dt == torch.bfloat16 and supports and self.use_tensor_cores and ops.hop_tc_supported(V):
+            hop_mats = ops.hop_mats([s.detach().contiguous() for s in supports])
+
         u = ops.StartConv.apply(x, self.start_conv.weight, self.start_conv.bias, L[0], dt == torch.bfloat16)
         stats = None
         z_last = []
@@ -309,7 +316,7 @@ class gwnet(nn.Module):
                 None if bn_prev is None else bn_prev.weight, None if bn_prev is None else bn_prev.bias,
                 None if bn_prev is None else bn_prev.running_mean, None if bn_prev is None else bn_prev.running_var,
                 pk['w_fg'][i], pk['b_fg'][i], pk['w_mlp'][i] if has_gconv else None,
-                pk['b_mlp'][i] if has_gconv else None, masks[i], rng, meta, *supports)
+                pk['b_mlp'][i] if has_gconv else None, masks[i], rng, hop_mats, meta, *supports)
             z_last.append(zl)
         if training:
             # the reference still runs bn[last] (its output is dead, :250-252) - keep its running stats in step

@@ -212,8 +212,8 @@ def _sup_array(supports: Sequence[Tensor]):
 @torch.library.custom_op('gwn::layer_fwd', mutates_args=())
 def layer_fwd(u_prev: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], w_fg: Tensor, b_fg: Tensor,
               w_mlp: Optional[Tensor], b_mlp: Optional[Tensor], supports: List[Tensor],
-              drop_mask: Optional[Tensor], rng: Optional[Tensor], Lf: int, taps: int, dilation: int, order: int,
-              training: bool, has_gconv: bool, dropout_p: float, seed: int, offset: int
+              drop_mask: Optional[Tensor], rng: Optional[Tensor], hop_mats: Optional[Tensor], Lf: int, taps: int,
+              dilation: int, order: int, training: bool, has_gconv: bool, dropout_p: float, seed: int, offset: int
               ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
     _req(u_prev, None, 'u_prev'); _req(w_fg, torch.float32, 'w_fg'); _req(b_fg, torch.float32, 'b_fg')
     for s in supports:
@@ -240,7 +240,7 @@ def layer_fwd(u_prev: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], 
                      offset)
     args = LayerFwdArgs(u_prev=_p(u_prev), scale=_p(scale), shift=_p(shift), w_fg=_p(w_fg), b_fg=_p(b_fg),
                         w_mlp=_p(w_mlp), b_mlp=_p(b_mlp), supports=_sup_array(supports if has_gconv else []),
-                        drop_mask=_p(drop_mask), rng=_p(rng), a=_p(a) if training else None,
+                        drop_mask=_p(drop_mask), rng=_p(rng), hop_mats=_p(hop_mats), a=_p(a) if training else None,
                         b=_p(b) if training else None, z_last=_p(z_last), u=_p(u) if has_gconv else None,
                         stats=_p(stats), ws_cat=_p(ws_cat))
     with torch.cuda.device(dev):
@@ -249,7 +249,7 @@ def layer_fwd(u_prev: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], 
 
 
 @layer_fwd.register_fake
-def _(u_prev, scale, shift, w_fg, b_fg, w_mlp, b_mlp, supports, drop_mask, rng, Lf, taps, dilation, order,
+def _(u_prev, scale, shift, w_fg, b_fg, w_mlp, b_mlp, supports, drop_mask, rng, hop_mats, Lf, taps, dilation, order,
       training, has_gconv, dropout_p, seed, offset):
     N, Lin, V, _c = u_prev.shape
     Lout = Lin - dilation * (taps - 1)
@@ -262,8 +262,8 @@ def _(u_prev, scale, shift, w_fg, b_fg, w_mlp, b_mlp, supports, drop_mask, rng, 
 @torch.library.custom_op('gwn::layer_bwd', mutates_args=())
 def layer_bwd(u_prev: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], w_fg: Tensor,
               w_mlp: Optional[Tensor], supports: List[Tensor], needs_grad: List[bool],
-              drop_mask: Optional[Tensor], rng: Optional[Tensor], a: Tensor, b: Tensor, du: Optional[Tensor],
-              dz_last: Optional[Tensor], Lf: int, taps: int, dilation: int, order: int, training: bool,
+              drop_mask: Optional[Tensor], rng: Optional[Tensor], hop_mats: Optional[Tensor], a: Tensor, b: Tensor,
+              du: Optional[Tensor], dz_last: Optional[Tensor], Lf: int, taps: int, dilation: int, order: int, training: bool,
               dropout_p: float, seed: int, offset: int) -> List[Tensor]:
     """Returns [dx_prev, dx_stats, dw_fg, db_fg, dw_mlp, db_mlp, d_support_0, ...] (d_support only for
     supports whose needs_grad is True; others are empty tensors)."""
@@ -285,7 +285,8 @@ def layer_bwd(u_prev: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], 
     ws_dfg = torch.empty((P, 2 * CH), **f32)
     cfg = _layer_cfg(N, V, Lin, Lout, Lf, taps, dilation, n_sup, order, dt, training, True, dropout_p, seed, offset)
     args = LayerBwdArgs(u_prev=_p(u_prev), scale=_p(scale), shift=_p(shift), w_fg=_p(w_fg), w_mlp=_p(w_mlp),
-                        supports=_sup_array(supports), drop_mask=_p(drop_mask), rng=_p(rng), a=_p(a), b=_p(b),
+                        supports=_sup_array(supports), drop_mask=_p(drop_mask), rng=_p(rng),
+                        hop_mats=_p(hop_mats), a=_p(a), b=_p(b),
                         du=_p(du), dz_last=_p(dz_last), dx_prev=_p(dx_prev), dx_stats=_p(dx_stats),
                         dw_fg=_p(dw_fg), db_fg=_p(db_fg), dw_mlp=_p(dw_mlp), db_mlp=_p(db_mlp),
                         ws_cat=_p(ws_cat) if has_du else None, ws_dcat=_p(ws_dcat) if has_du else None,
@@ -299,8 +300,8 @@ def layer_bwd(u_prev: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], 
 
 
 @layer_bwd.register_fake
-def _(u_prev, scale, shift, w_fg, w_mlp, supports, needs_grad, drop_mask, rng, a, b, du, dz_last, Lf, taps,
-      dilation, order, training, dropout_p, seed, offset):
+def _(u_prev, scale, shift, w_fg, w_mlp, supports, needs_grad, drop_mask, rng, hop_mats, a, b, du, dz_last, Lf,
+      taps, dilation, order, training, dropout_p, seed, offset):
     N, Lin, V, _c = u_prev.shape
     mlp_in = CH * (1 + order * len(supports))
     f = lambda *s: u_prev.new_empty(s, dtype=torch.float32)  # noqa: E731
@@ -312,13 +313,13 @@ class WaveNetLayer(torch.autograd.Function):
     """bn_prev-fold -> gated dilated conv -> (z_last) -> diffusion conv + dropout + residual -> (u, BN stats).
 
     Inputs : u_prev, stats_prev|None, gamma_prev|None, beta_prev|None, rmean_prev|None, rvar_prev|None,
-             w_fg, b_fg, w_mlp|None, b_mlp|None, drop_mask|None, rng|None, meta(dict), *supports
+             w_fg, b_fg, w_mlp|None, b_mlp|None, drop_mask|None, rng|None, hop_mats|None, meta(dict), *supports
     Outputs: u (pre-BN, or empty if the gconv is skipped), stats (non-differentiable), z_last
     """
 
     @staticmethod
-    def forward(ctx, u_prev, stats_prev, gamma, beta, rmean, rvar, w_fg, b_fg, w_mlp, b_mlp, drop_mask, rng, meta,
-                *supports):
+    def forward(ctx, u_prev, stats_prev, gamma, beta, rmean, rvar, w_fg, b_fg, w_mlp, b_mlp, drop_mask, rng, hop_mats,
+                meta, *supports):
         m = meta
         training = m['training']
         has_bn = gamma is not None
@@ -329,7 +330,7 @@ class WaveNetLayer(torch.autograd.Function):
                                                m['momentum'], m['eps'], training)
         sup = [s.contiguous() for s in supports]
         u, stats, z_last, a, b = layer_fwd(u_prev, scale, shift, w_fg, b_fg, w_mlp, b_mlp, sup, drop_mask, rng,
-                                           m['Lf'], m['taps'], m['dilation'], m['order'], training,
+                                           hop_mats, m['Lf'], m['taps'], m['dilation'], m['order'], training,
                                            m['has_gconv'], m['dropout_p'], m['seed'], m['offset'])
         ctx.set_materialize_grads(False)      # a dead output (last layer's u) must stay "no gradient"
         ctx.meta = m
@@ -337,21 +338,23 @@ class WaveNetLayer(torch.autograd.Function):
         ctx.has_bn = has_bn
         ctx.n_sup = len(sup)
         ctx.sup_needs = [bool(s.requires_grad) for s in supports]
-        ctx.save_for_backward(u_prev, scale, shift, mean, rstd, gamma, w_fg, w_mlp, drop_mask, rng, a, b, *sup)
+        ctx.save_for_backward(u_prev, scale, shift, mean, rstd, gamma, w_fg, w_mlp, drop_mask, rng, hop_mats, a, b,
+                              *sup)
         ctx.mark_non_differentiable(stats)
         return u, stats, z_last
 
     @staticmethod
     def backward(ctx, du, _dstats, dz_last):
         m = ctx.meta
-        (u_prev, scale, shift, mean, rstd, gamma, w_fg, w_mlp, drop_mask, rng, a, b, *sup) = ctx.saved_tensors
+        (u_prev, scale, shift, mean, rstd, gamma, w_fg, w_mlp, drop_mask, rng, hop_mats, a, b,
+         *sup) = ctx.saved_tensors
         if not m['training']:
             raise _lib.GwnError('backward through an eval-mode forward is not supported (a,b were not saved)')
         if du is not None and du.numel() == 0:
             du = None
         has_du = du is not None and m['has_gconv']
         outs = layer_bwd(u_prev, scale, shift, w_fg, w_mlp if has_du else None, sup if has_du else [],
-                         ctx.sup_needs if has_du else [], drop_mask, rng, a, b,
+                         ctx.sup_needs if has_du else [], drop_mask, rng, hop_mats if has_du else None, a, b,
                          du.contiguous() if has_du else None,
                          dz_last.contiguous() if dz_last is not None else None,
                          m['Lf'], m['taps'], m['dilation'], m['order'], True, m['dropout_p'], m['seed'],
@@ -366,7 +369,7 @@ class WaveNetLayer(torch.autograd.Function):
         for i in range(ctx.n_sup):
             g_sup.append(d_sup[i] if (has_du and ctx.sup_needs[i]) else None)
         return (du_prev, None, dgamma, dbeta, None, None, dw_fg, db_fg,
-                dw_mlp if has_du else None, db_mlp if has_du else None, None, None, None, *g_sup)
+                dw_mlp if has_du else None, db_mlp if has_du else None, None, None, None, None, *g_sup)
 
 
 # =========================================================================== head (:231-236, :252-254)
@@ -471,3 +474,40 @@ def node_mix(x: Tensor, A: Tensor, transpose_a: bool) -> Tensor:
 @node_mix.register_fake
 def _(x, A, transpose_a):
     return torch.empty_like(x)
+
+
+# =========================================================================== tcgen05 diffusion hops (V <= 128, bf16)
+def hop_tc_supported(V: int) -> bool:
+    """The tensor-core hop kernel keeps up to 6 support images resident in shared memory: V <= 80 today."""
+    return V <= 80
+
+
+@torch.library.custom_op('gwn::hop_mats', mutates_args=())
+def hop_mats(supports: List[Tensor]) -> Tensor:
+    """UMMA A-operand images of every support (A^T, (A^2)^T, A, A^2 per support), built once per forward."""
+    for s in supports:
+        _req(s, torch.float32, 'support')
+    V = supports[0].shape[0]
+    nbytes = lib().gwn_hop_mats_bytes(V, len(supports))
+    out = torch.empty((nbytes // 2,), device=supports[0].device, dtype=torch.bfloat16)
+    ptrs = (C.c_void_p * len(supports))(*[s.data_ptr() for s in supports])
+    with torch.cuda.device(out.device):
+        check(lib().gwn_hop_mats_prep(ptrs, len(supports), V, _p(out), _stream()), 'gwn_hop_mats_prep')
+    return out
+
+
+@hop_mats.register_fake
+def _(supports):
+    V = supports[0].shape[0]
+    Kp = 16 * ((V + 15) // 16)
+    return supports[0].new_empty((len(supports) * 4 * (Kp // 8) * 1024,), dtype=torch.bfloat16)
+
+
+@torch.library.custom_op('gwn::hop_tc', mutates_args=('buf',))
+def hop_tc(mats: Tensor, n_mats: int, mat: int, buf: Tensor, slot_in: int, slot_out: int, V: int) -> None:
+    """One tensor-core hop inside a pitched bf16 buffer [slabs*V, pitch]: slot_out <- Mop[mat] * slot_in."""
+    _req(buf, torch.bfloat16, 'buf')
+    rows, pitch = buf.shape
+    with torch.cuda.device(buf.device):
+        check(lib().gwn_hop_tc(_p(mats), n_mats, mat, _p(buf), pitch, slot_in, slot_out, rows // V, V, _stream()),
+              'gwn_hop_tc')

@@ -32,7 +32,7 @@ for storage in (None, torch.bfloat16):
         meta = dict(training=True, momentum=0.1, eps=1e-5, Lf=Lf, taps=2, dilation=m.dilations[i], order=2, has_gconv=True, dropout_p=0.0, seed=0, offset=i)
         u, stats, zl = ops.WaveNetLayer.apply(u, stats, None if bn_prev is None else bn_prev.weight, None if bn_prev is None else bn_prev.bias,
             None if bn_prev is None else bn_prev.running_mean, None if bn_prev is None else bn_prev.running_var,
-            pk['w_fg'][i], pk['b_fg'][i], pk['w_mlp'][i], pk['b_mlp'][i], None, None, meta, *supports)
+            pk['w_fg'][i], pk['b_fg'][i], pk['w_mlp'][i], pk['b_mlp'][i], None, None, None, meta, *supports)
         u_ref = tr.u[i].permute(0, 3, 2, 1)          # NCHW -> N,L,V,C
         z_ref = tr.z[i][..., -Lf:].permute(0, 3, 2, 1)
         if storage is not None:

@@ -335,7 +335,8 @@ def test_non_b200_or_cpu_input_raises():
         m(torch.randn(1, 2, 67, 12))
 
 
-def _layer_op_case(dtype, tol, V=67, N=6, Lin=9, dil=2, taps=2, n_sup=3, with_bn=True, mask=False, seed=0):
+def _layer_op_case(dtype, tol, V=67, N=6, Lin=9, dil=2, taps=2, n_sup=3, with_bn=True, mask=False, seed=0,
+                   tensor_cores=False):
     """ops.WaveNetLayer (bn-fold + gate + hops + mlp + dropout + residual, fwd AND bwd) against the
     oracle's single-layer restatement on IDENTICAL inputs (no ReLU anywhere -> bf16 error stays at
     rounding level, so the 2e-2 / 1e-4 bars apply to every gradient)."""
@@ -385,8 +386,9 @@ def _layer_op_case(dtype, tol, V=67, N=6, Lin=9, dil=2, taps=2, n_sup=3, with_bn
     sup_k[-1].requires_grad_(True)
     meta = dict(training=True, momentum=0.1, eps=1e-5, Lf=Lf, taps=taps, dilation=dil, order=2, has_gconv=True,
                 dropout_p=0.3 if mask else 0.0, seed=0, offset=0)
+    hop_mats_k = ops.hop_mats([a.detach() for a in sup_k]) if tensor_cores else None
     u_k, stats_k, zl_k = ops.WaveNetLayer.apply(k_in[0], stats, gk, bk, rm, rv, wfg_k, bfg_k, wm_k, bm_k,
-                                                cl(dm) if mask else None, None, meta, *sup_k)
+                                                cl(dm) if mask else None, None, hop_mats_k, meta, *sup_k)
     assert rel(u_k.permute(0, 3, 2, 1), u_o) < tol and rel(zl_k.permute(0, 3, 2, 1), z_o[..., -Lf:]) < tol
     cnt_o = N * V * Lout
     assert rel(stats_k[0] / cnt_o, u_o.mean(dim=(0, 2, 3))) < max(tol, 1e-5) * 10
@@ -415,11 +417,38 @@ def test_fp32_layer_op_fwd_bwd_vs_oracle(with_bn, mask):
     _layer_op_case(torch.float32, FP32_TOL, V=130, N=2, Lin=5, dil=1, taps=3, n_sup=2, with_bn=with_bn, mask=mask, seed=2)
 
 
+@pytest.mark.parametrize('tensor_cores', [False, True])
 @pytest.mark.parametrize('with_bn,mask', [(True, False), (False, True)])
-def test_bf16_layer_op_fwd_bwd_vs_oracle(with_bn, mask):
-    """bf16 storage: every output and EVERY gradient of the layer within 2e-2 of the fp64 oracle."""
-    errs = _layer_op_case(torch.bfloat16, BF16_TOL, with_bn=with_bn, mask=mask, seed=3)
-    print('bf16 layer-op errors:', {k: f'{v:.1e}' for k, v in errs.items()})
+def test_bf16_layer_op_fwd_bwd_vs_oracle(with_bn, mask, tensor_cores):
+    """bf16 storage: every output and EVERY gradient of the layer within 2e-2 of the fp64 oracle, with the
+    diffusion hops on CUDA cores and on the tcgen05 tensor cores."""
+    errs = _layer_op_case(torch.bfloat16, BF16_TOL, with_bn=with_bn, mask=mask, seed=3, tensor_cores=tensor_cores)
+    print(f'bf16 layer-op errors (tensor_cores={tensor_cores}):', {k: f'{v:.1e}' for k, v in errs.items()})
+    if tensor_cores:      # ragged tile (slabs not a multiple of 8), 2 supports, 1 support
+        _layer_op_case(torch.bfloat16, BF16_TOL, V=67, N=3, Lin=7, dil=1, taps=2, n_sup=2, with_bn=with_bn,
+                       mask=mask, seed=4, tensor_cores=True)
+        _layer_op_case(torch.bfloat16, BF16_TOL, V=40, N=5, Lin=4, dil=1, taps=2, n_sup=1, with_bn=with_bn,
+                       mask=mask, seed=5, tensor_cores=True)
+
+
+def test_tc_hop_kernel_every_image_variant():
+    """gwn_hop_tc (tcgen05) against an fp64 einsum for A^T, (A^2)^T, A, A^2 images, ragged slab counts."""
+    from multimodal_outage_b200 import ops
+    torch.manual_seed(0)
+    for V, slabs in ((67, 8), (67, 37), (80, 5), (33, 300)):
+        sups = [torch.softmax(torch.randn(V, V, device='cuda'), dim=1) for _ in range(2)]
+        mats = ops.hop_mats(sups)
+        buf = torch.randn(slabs * V, 96, device='cuda').to(torch.bfloat16)
+        x = buf[:, :32].double().reshape(slabs, V, 32).clone()
+        for s in range(2):
+            A = sups[s].double()
+            refs = [torch.einsum('vw,svc->swc', A, x), torch.einsum('vw,svc->swc', A @ A, x),
+                    torch.einsum('wv,svc->swc', A, x), torch.einsum('wv,svc->swc', A @ A, x)]
+            for variant in range(4):
+                ops.hop_tc(mats, 8, 4 * s + variant, buf, 0, 1 + variant % 2, V)
+                y = buf[:, 32 * (1 + variant % 2):32 * (2 + variant % 2)].double().reshape(slabs, V, 32)
+                assert rel(y, refs[variant]) < 1e-2, (V, slabs, s, variant)
+        assert torch.equal(buf[:, :32].double().reshape(slabs, V, 32), x)
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
