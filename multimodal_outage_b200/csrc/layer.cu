@@ -69,13 +69,13 @@ struct EpiMlp {
 };
 
 template <typename T>
-struct EpiStoreT {  // plain store into a pitched T buffer
+struct EpiSlotStore {  // column group col/32 goes to slot col/32 of a slot-major buffer
   static constexpr bool kStats = false;
   double* stats;
-  T* out; int pitch;
+  T* out; long long slot_stride;
   __device__ __forceinline__ void apply(long long p, long long, long long, int col, float v[4], float*,
                                         float*) const {
-    store4(out + p * pitch + col, v);
+    store4(out + (col >> 5) * slot_stride + p * 32 + (col & 31), v);
   }
 };
 
@@ -413,17 +413,21 @@ static bool use_tc_hops(const gwn_layer_cfg* c, const void* hop_mats) {
          hops_tc_supported(c->V, 2 * c->n_supports) != 0;
 }
 
-static void hop_params_base(HopParams& p, const gwn_layer_cfg* c, bf16* buf, int pitch, const void* hop_mats) {
+// The concat buffers are SLOT-MAJOR: slot q (32 channels of hop q) is a contiguous [P, 32] tensor at
+// buf + q*P*32, so a tile of a slot is one contiguous run of 64-byte rows (full 128-byte DRAM lines).
+static void hop_params_base(HopParams& p, const gwn_layer_cfg* c, bf16* buf, const void* hop_mats) {
+  const long long P = (long long)c->N * c->Lout * c->V;
   p.in[0] = p.in[1] = buf; p.out[0] = p.out[1] = buf;
-  p.in_pitch[0] = p.in_pitch[1] = p.out_pitch[0] = p.out_pitch[1] = pitch;
+  p.in_pitch[0] = p.in_pitch[1] = p.out_pitch[0] = p.out_pitch[1] = 32;
+  p.slot_stride[0] = p.slot_stride[1] = P * 32;
   p.mats = reinterpret_cast<const bf16*>(hop_mats);
   p.V = c->V; p.slabs = c->N * c->Lout;
 }
 
 // forward hops on tcgen05: the z tile is loaded once, all 2*S outputs (A_s and A_s^2) come from it
-static int hops_forward_tc(const gwn_layer_cfg* c, bf16* cat, int mlp_in, const void* hop_mats, cudaStream_t st) {
+static int hops_forward_tc(const gwn_layer_cfg* c, bf16* cat, const void* hop_mats, cudaStream_t st) {
   HopParams p{};
-  hop_params_base(p, c, cat, mlp_in, hop_mats);
+  hop_params_base(p, c, cat, hop_mats);
   const int nh = 2 * c->n_supports;
   p.n_mats = nh; p.n_steps = nh; p.n_outs = nh;
   for (int j = 0; j < nh; ++j) {
@@ -435,17 +439,18 @@ static int hops_forward_tc(const gwn_layer_cfg* c, bf16* cat, int mlp_in, const 
 }
 
 template <typename T>
-static int hops_forward(const gwn_layer_cfg* c, T* cat, int mlp_in, const float* const* supports,
+static int hops_forward(const gwn_layer_cfg* c, T* cat, const float* const* supports,
                         const void* hop_mats, cudaStream_t st) {
   if constexpr (std::is_same<T, bf16>::value) {
-    if (use_tc_hops<T>(c, hop_mats)) return hops_forward_tc(c, cat, mlp_in, hop_mats, st);
+    if (use_tc_hops<T>(c, hop_mats)) return hops_forward_tc(c, cat, hop_mats, st);
   }
   const long long slabs = (long long)c->N * c->Lout;
+  const long long SS = slabs * c->V * 32;   // slot stride
   for (int s = 0; s < c->n_supports; ++s)
     for (int k = 1; k <= c->order; ++k) {
       int slot = 1 + s * c->order + (k - 1);
       int src = (k == 1) ? 0 : slot - 1;
-      if (int rc = launch_node_mix<T>(cat, mlp_in, src * 32, cat, mlp_in, slot * 32, 0, supports[s], false, slabs,
+      if (int rc = launch_node_mix<T>(cat + src * SS, 32, 0, cat + slot * SS, 32, 0, 0, supports[s], false, slabs,
                                       c->V, st))
         return rc;
     }
@@ -467,7 +472,7 @@ static int layer_fwd_t(const gwn_layer_cfg* c, const gwn_layer_fwd_args* g, cuda
     ch.pitch = 32; ch.col_off = 0; ch.scale = g->scale; ch.shift = g->shift; ch.relu = 0;
   }
   EpiGate<T> eg{};
-  eg.bias = g->b_fg; eg.zcat = cat; eg.zpitch = mlp_in;
+  eg.bias = g->b_fg; eg.zcat = cat; eg.zpitch = 32;   // slot 0 of the slot-major concat buffer
   eg.a = c->training ? reinterpret_cast<T*>(g->a) : nullptr;
   eg.b = c->training ? reinterpret_cast<T*>(g->b) : nullptr;
   eg.z_last = reinterpret_cast<T*>(g->z_last);
@@ -475,13 +480,13 @@ static int layer_fwd_t(const gwn_layer_cfg* c, const gwn_layer_fwd_args* g, cuda
   if (int rc = launch_pos_gemm<T, 64>(A, g->w_fg, 64, eg, st)) return rc;
   if (!c->has_gconv) return 0;
   // diffusion hops into the concat slots, then mlp + dropout + residual + stats
-  if (int rc = hops_forward<T>(c, cat, mlp_in, g->supports, g->hop_mats, st)) return rc;
+  if (int rc = hops_forward<T>(c, cat, g->supports, g->hop_mats, st)) return rc;
   GWN_CUDA(cudaMemsetAsync(g->stats, 0, sizeof(double) * 64, st));
   GemmA M{};
   M.n_chunks = nslots; M.rows_per_n_out = RO; M.P = P;
   for (int q = 0; q < nslots; ++q) {
     AChunk& ch = M.ch[q];
-    ch.base = cat; ch.rows_per_n = RO; ch.row_off = 0; ch.pitch = mlp_in; ch.col_off = q * 32;
+    ch.base = cat + q * P * 32; ch.rows_per_n = RO; ch.row_off = 0; ch.pitch = 32; ch.col_off = 0;
   }
   EpiMlp<T> em{};
   em.stats = g->stats; em.bias = g->b_mlp;
@@ -509,9 +514,9 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
   const T* dz = nullptr;
   if (du) {
     // recompute the concat (z and its hops)
-    zfill_kernel<T><<<eb, 256, 0, st>>>(a, b, cat, mlp_in, P);
+    zfill_kernel<T><<<eb, 256, 0, st>>>(a, b, cat, 32, P);
     GWN_LAUNCHED();
-    if (int rc = hops_forward<T>(c, cat, mlp_in, g->supports, g->hop_mats, st)) return rc;
+    if (int rc = hops_forward<T>(c, cat, g->supports, g->hop_mats, st)) return rc;
     // dh = du * mask
     const T* dh = du;
     const bool drop = c->training && (g->drop_mask != nullptr || c->dropout_p > 0.f);
@@ -527,7 +532,7 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
     M.n_chunks = nslots; M.rows_per_n_out = RO; M.P = P;
     for (int q = 0; q < nslots; ++q) {
       AChunk& ch = M.ch[q];
-      ch.base = cat; ch.rows_per_n = RO; ch.row_off = 0; ch.pitch = mlp_in; ch.col_off = q * 32;
+      ch.base = cat + q * P * 32; ch.rows_per_n = RO; ch.row_off = 0; ch.pitch = 32; ch.col_off = 0;
     }
     if (int rc = launch_wgrad<T, T>(M, dh, 32, 0, g->dw_mlp, 32, g->db_mlp, st)) return rc;
     // dcat[p, (slot,c)] = sum_o dh[p,o] * w_mlp_t[(slot,c), o]
@@ -535,7 +540,7 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
     D.n_chunks = 1; D.rows_per_n_out = RO; D.P = P;
     D.ch[0].base = dh; D.ch[0].rows_per_n = RO; D.ch[0].row_off = 0; D.ch[0].pitch = 32; D.ch[0].col_off = 0;
     D.ch[0].w_off = 0;
-    EpiStoreT<T> es{}; es.out = dcat; es.pitch = mlp_in;
+    EpiSlotStore<T> es{}; es.out = dcat; es.slot_stride = P * 32;
     if (int rc = launch_pos_gemm_wt<T, 32>(D, g->w_mlp, mlp_in, 32, es, st)) return rc;
     // hops backward
     bool tc_done = false;
@@ -545,19 +550,19 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
         for (int s = 0; s < c->n_supports; ++s) {
           if (!(g->support_needs_grad[s] && g->d_supports[s])) continue;
           HopParams p{};
-          hop_params_base(p, c, dcat, mlp_in, g->hop_mats);
+          hop_params_base(p, c, dcat, g->hop_mats);
           p.n_mats = 1; p.mat_src[0] = 4 * s + 2; p.n_steps = 1; p.n_outs = 1;
           p.steps[0] = HopStep{0, 2 * s + 2, 0, 0, TH_LOAD | TH_RELEASE | TH_FIRST | TH_LAST};
           p.outs[0] = HopOut{0, 2 * s + 1, 0, 2 * s + 1};
           if (int rc = launch_hops_tc(p, st)) return rc;
-          if (int rc = launch_dadj<T>(cat, mlp_in, (2 * s + 1) * 32, dcat, mlp_in, (2 * s + 2) * 32, g->d_supports[s],
-                                      slabs, c->V, st)) return rc;
-          if (int rc = launch_dadj<T>(cat, mlp_in, 0, dcat, mlp_in, (2 * s + 1) * 32, g->d_supports[s], slabs, c->V, st))
+          if (int rc = launch_dadj<T>(cat + (2 * s + 1) * P * 32, 32, 0, dcat + (2 * s + 2) * P * 32, 32, 0,
+                                      g->d_supports[s], slabs, c->V, st)) return rc;
+          if (int rc = launch_dadj<T>(cat, 32, 0, dcat + (2 * s + 1) * P * 32, 32, 0, g->d_supports[s], slabs, c->V, st))
             return rc;
         }
         // (2) dz = g0 + sum_s [ g1_s A_s^T + g2_s (A_s^2)^T ]  (one accumulator; g1' A^T where step (1) ran)
         HopParams p{};
-        hop_params_base(p, c, dcat, mlp_in, g->hop_mats);
+        hop_params_base(p, c, dcat, g->hop_mats);
         int n = 0;
         for (int s = 0; s < c->n_supports; ++s) {
           const bool folded = g->support_needs_grad[s] && g->d_supports[s];
@@ -584,9 +589,10 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
         int slot = 1 + s * c->order + (k - 1);
         int src = (k == 1) ? 0 : slot - 1;
         if (g->support_needs_grad[s] && g->d_supports[s])
-          if (int rc = launch_dadj<T>(cat, mlp_in, src * 32, dcat, mlp_in, slot * 32, g->d_supports[s], slabs, c->V, st))
+          if (int rc = launch_dadj<T>(cat + src * P * 32, 32, 0, dcat + slot * P * 32, 32, 0, g->d_supports[s], slabs,
+                                      c->V, st))
             return rc;
-        if (int rc = launch_node_mix<T>(dcat, mlp_in, slot * 32, dcat, mlp_in, src * 32, 1, g->supports[s], true,
+        if (int rc = launch_node_mix<T>(dcat + slot * P * 32, 32, 0, dcat + src * P * 32, 32, 0, 1, g->supports[s], true,
                                         slabs, c->V, st))
           return rc;
       }
@@ -596,7 +602,7 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
     GWN_CUDA(cudaMemsetAsync(g->db_mlp, 0, sizeof(float) * 32, st));
   }
   // gate backward: (dz + dz_last) -> dfg
-  gate_bwd_kernel<T><<<eb, 256, 0, st>>>(dz, mlp_in, reinterpret_cast<const T*>(g->dz_last), RO,
+  gate_bwd_kernel<T><<<eb, 256, 0, st>>>(dz, 32, reinterpret_cast<const T*>(g->dz_last), RO,
                                          (long long)(c->Lout - c->Lf) * c->V, (long long)c->Lf * c->V, a, b,
                                          g->ws_dfg, P);
   GWN_LAUNCHED();

@@ -11,7 +11,8 @@
 //                gather of 64-byte rows out of a 448-byte-pitch concat buffer, with zero-filled K padding).
 //   D          : fp32 in TMEM, two 256-column accumulators so the epilogue of one output overlaps the MMAs of
 //                the next.  Epilogue: tcgen05.ld -> (+ add-in) -> bf16 -> 64-byte stores into the concat slot.
-// Roles (288 threads): warps 0-3 producers, warp 4 lane 0 MMA issuer (+TMEM alloc), warps 5-8 epilogue.
+// Roles (416 threads): warps 0-3 producers, warp 4 lane 0 MMA issuer (+TMEM alloc), warps 5-12 epilogue
+// (two warps per TMEM lane quadrant, each draining 4 of the 8 slabs of an accumulator, loads issued in pairs).
 // Persistent: grid = min(tiles, SMs); each CTA walks tiles of 8 slabs.
 #include "tc.cuh"
 #include "tc_hops.cuh"
@@ -39,7 +40,7 @@ __global__ void __launch_bounds__(TH_THREADS, 1) hops_tc_kernel(const __grid_con
       mbar_init(&full[i], TH_PRODUCERS);
       mbar_init(&empty[i], 1);
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 128);
+      mbar_init(&tempty[i], 32 * TH_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(TH_THREADS, 1) hops_tc_kernel(const __grid_con
         if (!(st.flags & TH_LOAD)) continue;
         const int stage = g & 1, phase = (g >> 1) & 1;
         mbar_wait(&empty[stage], (uint32_t)(phase ^ 1));
-        const bf16* base = p.in[st.in_buf] + st.in_slot * 32;
+        const bf16* base = p.in[st.in_buf] + st.in_slot * p.slot_stride[st.in_buf];
         const int pitch = p.in_pitch[st.in_buf];
         const uint32_t sdst = smem_u32(stage_s + (size_t)stage * stage_bytes);
 #pragma unroll 2
@@ -134,10 +135,11 @@ __global__ void __launch_bounds__(TH_THREADS, 1) hops_tc_kernel(const __grid_con
   } else {
     // ===================== epilogue: TMEM -> registers -> (+add) -> bf16 -> concat slot =====================
     const int quad = warp & 3;
+    const int half = (warp - (TH_MMA_WARP + 1)) >> 2;   // which 4 slabs of the accumulator this warp drains
     const int w = quad * 32 + lane;
     uint32_t acc_uses[2] = {0u, 0u};
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      const long long slab0 = (long long)tile * 8;
+      const long long slab0 = (long long)tile * 8 + half * 4;
       int o = 0;
       for (int si = 0; si < p.n_steps; ++si) {
         const HopStep st = p.steps[si];
@@ -146,35 +148,46 @@ __global__ void __launch_bounds__(TH_THREADS, 1) hops_tc_kernel(const __grid_con
         mbar_wait(&tfull[st.acc], acc_uses[st.acc] & 1u);
         acc_uses[st.acc]++;
         tc_fence_after();
-        bf16* obase = p.out[ho.buf] + ho.slot * 32;
+        bf16* obase = p.out[ho.buf] + ho.slot * p.slot_stride[ho.buf];
         const int opitch = p.out_pitch[ho.buf];
+        const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)st.acc * 256u +
+                               (uint32_t)half * 128u;
 #pragma unroll 1
-        for (int s = 0; s < 8; ++s) {
-          float v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)st.acc * 256u + (uint32_t)s * 32u, v);
-          const long long slab = slab0 + s;
-          if (w < V && slab < p.slabs) {
-            const long long row = slab * V + w;
-            if (ho.add_buf >= 0) {
-              const bf16* ap = p.in[ho.add_buf] + row * (long long)p.in_pitch[ho.add_buf] + ho.add_slot * 32;
+        for (int pr = 0; pr < 2; ++pr) {
+          uint32_t r[2][32];
+          tmem_ld32_issue(tbase + (uint32_t)(2 * pr) * 32u, r[0]);
+          tmem_ld32_issue(tbase + (uint32_t)(2 * pr + 1) * 32u, r[1]);
+          tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float t[4];
-                load4(ap + 4 * j, t);
-                v[4 * j] += t[0]; v[4 * j + 1] += t[1]; v[4 * j + 2] += t[2]; v[4 * j + 3] += t[3];
+          for (int h = 0; h < 2; ++h) {
+            const long long slab = slab0 + 2 * pr + h;
+            if (w < V && slab < p.slabs) {
+              const long long row = slab * V + w;
+              float v[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[h][j]);
+              if (ho.add_buf >= 0) {
+                const bf16* ap = p.in[ho.add_buf] + row * (long long)p.in_pitch[ho.add_buf] +
+                                 ho.add_slot * p.slot_stride[ho.add_buf];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  float t[4];
+                  load4(ap + 4 * j, t);
+                  v[4 * j] += t[0]; v[4 * j + 1] += t[1]; v[4 * j + 2] += t[2]; v[4 * j + 3] += t[3];
+                }
               }
-            }
-            bf16* dp = obase + row * (long long)opitch;
+              bf16* dp = obase + row * (long long)opitch;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 pk;
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
-              __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
-              __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
-              pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-              pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-              *reinterpret_cast<uint4*>(dp + 8 * j) = pk;
+              for (int j = 0; j < 4; ++j) {
+                uint4 pk;
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
+                __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+                __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(dp + 8 * j) = pk;
+              }
             }
           }
         }
@@ -282,6 +295,7 @@ extern "C" int gwn_hop_tc(const void* mats, int n_mats, int mat, void* buf, int 
   p.in[0] = p.in[1] = reinterpret_cast<const bf16*>(buf);
   p.out[0] = p.out[1] = reinterpret_cast<bf16*>(buf);
   p.in_pitch[0] = p.in_pitch[1] = p.out_pitch[0] = p.out_pitch[1] = pitch;
+  p.slot_stride[0] = p.slot_stride[1] = 32;   // row-major [rows, pitch] buffer: slots are column groups
   p.mats = reinterpret_cast<const bf16*>(mats);
   p.n_mats = 1; p.mat_src[0] = mat; p.V = V; p.slabs = slabs;
   p.n_steps = 1; p.n_outs = 1;
