@@ -7,6 +7,7 @@
 
 #include "gemm.cuh"
 #include "tc_hops.cuh"
+#include "tc_wgrad.cuh"
 
 namespace gwn {
 
@@ -302,10 +303,10 @@ __global__ void drop_bwd_kernel(const T* __restrict__ du, const T* __restrict__ 
 }
 
 // dfg[p, 2c] = dz*b*(1-a^2) ; dfg[p, 2c+1] = dz*a*b*(1-b);  dz = dcat slot0 (+ dz_last on the tail rows)
-template <typename T>
+template <typename T, typename TO>
 __global__ void gate_bwd_kernel(const T* __restrict__ dz, int dz_pitch, const T* __restrict__ dz_last,
                                 long long rows_per_n, long long last_begin, long long last_rows,
-                                const T* __restrict__ a, const T* __restrict__ b, float* __restrict__ dfg,
+                                const T* __restrict__ a, const T* __restrict__ b, TO* __restrict__ dfg,
                                 long long P) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P * 8) return;
@@ -327,9 +328,9 @@ __global__ void gate_bwd_kernel(const T* __restrict__ dz, int dz_pitch, const T*
     o[2 * j] = g[j] * bv[j] * (1.f - av[j] * av[j]);
     o[2 * j + 1] = g[j] * av[j] * bv[j] * (1.f - bv[j]);
   }
-  float* dst = dfg + p * 64 + 2 * c;
-  *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-  *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+  TO* dst = dfg + p * 64 + 2 * c;
+  store4(dst, o);
+  store4(dst + 4, o + 4);
 }
 
 // ------------------------------------------------------------------------------------------ BatchNorm fold
@@ -534,7 +535,21 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
       AChunk& ch = M.ch[q];
       ch.base = cat + q * P * 32; ch.rows_per_n = RO; ch.row_off = 0; ch.pitch = 32; ch.col_off = 0;
     }
-    if (int rc = launch_wgrad<T, T>(M, dh, 32, 0, g->dw_mlp, 32, g->db_mlp, st)) return rc;
+    bool wg_done = false;
+    if constexpr (std::is_same<T, bf16>::value) {
+      if (use_tc_hops<T>(c, g->hop_mats) && wgrad_tc_supported(nslots, 32)) {
+        GWN_CUDA(cudaMemsetAsync(g->dw_mlp, 0, sizeof(float) * 32 * mlp_in, st));
+        GWN_CUDA(cudaMemsetAsync(g->db_mlp, 0, sizeof(float) * 32, st));
+        WgParams w{};
+        w.n_chunks = nslots; w.rows_per_n_out = RO; w.P = P;
+        for (int q = 0; q < nslots; ++q) w.ch[q] = WgChunk{cat + q * P * 32, RO, 0, 32, 0};
+        w.G = dh; w.g_pitch = 32; w.N = 32; w.dW = g->dw_mlp; w.ldw = 32; w.db = g->db_mlp;
+        if (int rc = launch_wgrad_tc(w, st)) return rc;
+        wg_done = true;
+      }
+    }
+    if (!wg_done)
+      if (int rc = launch_wgrad<T, T>(M, dh, 32, 0, g->dw_mlp, 32, g->db_mlp, st)) return rc;
     // dcat[p, (slot,c)] = sum_o dh[p,o] * w_mlp_t[(slot,c), o]
     GemmA D{};
     D.n_chunks = 1; D.rows_per_n_out = RO; D.P = P;
@@ -555,10 +570,11 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
           p.steps[0] = HopStep{0, 2 * s + 2, 0, 0, TH_LOAD | TH_RELEASE | TH_FIRST | TH_LAST};
           p.outs[0] = HopOut{0, 2 * s + 1, 0, 2 * s + 1};
           if (int rc = launch_hops_tc(p, st)) return rc;
-          if (int rc = launch_dadj<T>(cat + (2 * s + 1) * P * 32, 32, 0, dcat + (2 * s + 2) * P * 32, 32, 0,
-                                      g->d_supports[s], slabs, c->V, st)) return rc;
-          if (int rc = launch_dadj<T>(cat, 32, 0, dcat + (2 * s + 1) * P * 32, 32, 0, g->d_supports[s], slabs, c->V, st))
-            return rc;
+          DadjParams dj{};
+          dj.n_terms = 2; dj.V = c->V; dj.slabs = (int)slabs; dj.dA = g->d_supports[s];
+          dj.t[0] = DadjTerm{cat + (2 * s + 1) * P * 32, dcat + (2 * s + 2) * P * 32};   // y1^T g2
+          dj.t[1] = DadjTerm{cat, dcat + (2 * s + 1) * P * 32};                           // z^T  g1'
+          if (int rc = launch_dadj_tc(dj, st)) return rc;
         }
         // (2) dz = g0 + sum_s [ g1_s A_s^T + g2_s (A_s^2)^T ]  (one accumulator; g1' A^T where step (1) ran)
         HopParams p{};
@@ -601,10 +617,17 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
     GWN_CUDA(cudaMemsetAsync(g->dw_mlp, 0, sizeof(float) * 32 * mlp_in, st));
     GWN_CUDA(cudaMemsetAsync(g->db_mlp, 0, sizeof(float) * 32, st));
   }
-  // gate backward: (dz + dz_last) -> dfg
-  gate_bwd_kernel<T><<<eb, 256, 0, st>>>(dz, 32, reinterpret_cast<const T*>(g->dz_last), RO,
-                                         (long long)(c->Lout - c->Lf) * c->V, (long long)c->Lf * c->V, a, b,
-                                         g->ws_dfg, P);
+  // gate backward: (dz + dz_last) -> dfg  (bf16 in tensor-core mode so it can be an MMA operand)
+  bool tc_gate = false;
+  if constexpr (std::is_same<T, bf16>::value) tc_gate = use_tc_hops<T>(c, g->hop_mats) && wgrad_tc_supported(c->taps, 64);
+  const long long last_begin = (long long)(c->Lout - c->Lf) * c->V, last_rows = (long long)c->Lf * c->V;
+  bf16* dfg16 = reinterpret_cast<bf16*>(g->ws_dfg);
+  if (tc_gate)
+    gate_bwd_kernel<T, bf16><<<eb, 256, 0, st>>>(dz, 32, reinterpret_cast<const T*>(g->dz_last), RO, last_begin,
+                                                  last_rows, a, b, dfg16, P);
+  else
+    gate_bwd_kernel<T, float><<<eb, 256, 0, st>>>(dz, 32, reinterpret_cast<const T*>(g->dz_last), RO, last_begin,
+                                                   last_rows, a, b, g->ws_dfg, P);
   GWN_LAUNCHED();
   // dW_fg [taps*32, 64], db_fg
   GemmA A{};
@@ -614,7 +637,21 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
     ch.base = g->u_prev; ch.rows_per_n = RI; ch.row_off = (long long)j * c->dilation * c->V;
     ch.pitch = 32; ch.col_off = 0; ch.scale = g->scale; ch.shift = g->shift;
   }
-  if (int rc = launch_wgrad<T, float>(A, g->ws_dfg, 64, 0, g->dw_fg, 64, g->db_fg, st)) return rc;
+  if (tc_gate) {
+    if constexpr (std::is_same<T, bf16>::value) {
+      GWN_CUDA(cudaMemsetAsync(g->dw_fg, 0, sizeof(float) * 64 * 32 * c->taps, st));
+      GWN_CUDA(cudaMemsetAsync(g->db_fg, 0, sizeof(float) * 64, st));
+      WgParams w{};
+      w.n_chunks = c->taps; w.rows_per_n_out = RO; w.P = P;
+      for (int j = 0; j < c->taps; ++j)
+        w.ch[j] = WgChunk{reinterpret_cast<const bf16*>(g->u_prev), RI, (long long)j * c->dilation * c->V, 32, 0};
+      w.G = dfg16; w.g_pitch = 64; w.N = 64; w.dW = g->dw_fg; w.ldw = 64; w.db = g->db_fg;
+      w.scale = g->scale; w.shift = g->shift;
+      if (int rc = launch_wgrad_tc(w, st)) return rc;
+    }
+  } else {
+    if (int rc = launch_wgrad<T, float>(A, g->ws_dfg, 64, 0, g->dw_fg, 64, g->db_fg, st)) return rc;
+  }
   // dx_prev[p_in, c] = sum_{j,fg} dfg[p_in - j*d*V, fg] * w_fg[(j,c), fg]  (+ residual du on cropped rows)
   GemmA X{};
   X.n_chunks = 2 * c->taps; X.rows_per_n_out = RI; X.P = PI;
@@ -628,6 +665,7 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
   EpiGateBwdData<T> ex{};
   ex.stats = g->dx_stats; ex.du = du; ex.du_rows_per_n = RO; ex.crop = (long long)(c->Lin - c->Lout) * c->V;
   ex.u_prev = reinterpret_cast<const T*>(g->u_prev); ex.dx = g->dx_prev;
+  if (tc_gate) return launch_pos_gemm_wt<bf16, 32>(X, g->w_fg, 32, 64, ex, st);
   return launch_pos_gemm_wt<float, 32>(X, g->w_fg, 32, 64, ex, st);
 }
 
