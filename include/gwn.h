@@ -92,6 +92,7 @@ typedef struct {
   const uint64_t* rng;          /* optional DEVICE {seed, offset}: overrides cfg.seed, added to cfg.offset
                                    (keeps the mask fresh across CUDA-graph replays) */
   const void* hop_mats;         /* optional gwn_hop_mats_prep images: bf16 hops run on tcgen05 */
+  void* ws_w;                   /* optional 128 KiB scratch for the bf16 weight images of the tcgen05 GEMMs */
   void* a;                      /* out (training) tanh(f)   [N,Lout,V,32] */
   void* b;                      /* out (training) sigmoid(g) */
   void* z_last;                 /* out [N,Lf,V,32] */
@@ -111,6 +112,7 @@ typedef struct {
   const void* drop_mask;
   const uint64_t* rng;
   const void* hop_mats;
+  void* ws_w;
   const void* a; const void* b;
   /* incoming gradients */
   const void* du;               /* [N,Lout,V,32] (dtype) or NULL (dead gconv: last layer) */

@@ -28,14 +28,14 @@ class LayerCfg(C.Structure):
 
 class LayerFwdArgs(C.Structure):
     _fields_ = [('u_prev', vp), ('scale', vp), ('shift', vp), ('w_fg', vp), ('b_fg', vp), ('w_mlp', vp),
-                ('b_mlp', vp), ('supports', vp * MAX_SUPPORTS), ('drop_mask', vp), ('rng', vp), ('hop_mats', vp), ('a', vp),
+                ('b_mlp', vp), ('supports', vp * MAX_SUPPORTS), ('drop_mask', vp), ('rng', vp), ('hop_mats', vp), ('ws_w', vp), ('a', vp),
                 ('b', vp), ('z_last', vp), ('u', vp), ('stats', vp), ('ws_cat', vp)]
 
 
 class LayerBwdArgs(C.Structure):
     _fields_ = [('u_prev', vp), ('scale', vp), ('shift', vp), ('w_fg', vp), ('w_mlp', vp),
                 ('supports', vp * MAX_SUPPORTS), ('support_needs_grad', C.c_int * MAX_SUPPORTS),
-                ('drop_mask', vp), ('rng', vp), ('hop_mats', vp), ('a', vp), ('b', vp), ('du', vp), ('dz_last', vp), ('dx_prev', vp),
+                ('drop_mask', vp), ('rng', vp), ('hop_mats', vp), ('ws_w', vp), ('a', vp), ('b', vp), ('du', vp), ('dz_last', vp), ('dx_prev', vp),
                 ('dx_stats', vp), ('dw_fg', vp), ('db_fg', vp), ('dw_mlp', vp), ('db_mlp', vp),
                 ('d_supports', vp * MAX_SUPPORTS), ('ws_cat', vp), ('ws_dcat', vp), ('ws_dfg', vp)]
 

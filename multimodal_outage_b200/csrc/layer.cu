@@ -8,6 +8,7 @@
 #include "gemm.cuh"
 #include "tc_hops.cuh"
 #include "tc_wgrad.cuh"
+#include "tc_gemm_impl.cuh"
 
 namespace gwn {
 
@@ -98,6 +99,142 @@ struct EpiGateBwdData {  // dx = acc + du(cropped rows); stats = (sum dx, sum dx
 #pragma unroll
     for (int j = 0; j < 4; ++j) { s1[j] += v[j]; s2[j] += v[j] * up[j]; }
     store4(dx + p * 32 + col, v);
+  }
+};
+
+// ------------------------------------------------------------------------------------------ tcgen05 epilogues
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void store_bf16x16(bf16* dst, const float v[16]) {
+  uint4 a, b;
+  __nv_bfloat162 h;
+  uint32_t w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]); w[i] = *reinterpret_cast<uint32_t*>(&h); }
+  a = make_uint4(w[0], w[1], w[2], w[3]); b = make_uint4(w[4], w[5], w[6], w[7]);
+  *reinterpret_cast<uint4*>(dst) = a;
+  *reinterpret_cast<uint4*>(dst + 8) = b;
+}
+
+struct EpiGateTC {   // N = 64 interleaved (f,g); a chunk of 32 columns = 16 channels
+  const float* bias;
+  bf16* z; bf16* a; bf16* b; bf16* z_last; long long last_begin, last_rows;
+  __device__ __forceinline__ void chunk(long long p, long long n, long long rem, bool valid, int c0, float v[32]) {
+    if (!valid) return;
+    float zz[16], aa[16], bb[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float f = v[2 * i] + __ldg(bias + c0 + 2 * i), g = v[2 * i + 1] + __ldg(bias + c0 + 2 * i + 1);
+      aa[i] = tanh_fast(f);
+      bb[i] = fmaf(0.5f, tanh_fast(0.5f * g), 0.5f);
+      zz[i] = aa[i] * bb[i];
+    }
+    const int ch0 = c0 >> 1;
+    store_bf16x16(z + p * 32 + ch0, zz);
+    if (a) { store_bf16x16(a + p * 32 + ch0, aa); store_bf16x16(b + p * 32 + ch0, bb); }
+    if (z_last && rem >= last_begin) store_bf16x16(z_last + (n * last_rows + rem - last_begin) * 32 + ch0, zz);
+  }
+  __device__ __forceinline__ void finish() {}
+};
+
+struct EpiMlpTC {    // N = 32: bias + dropout + residual(BN-folded input) -> u, per-channel (sum, sum^2)
+  const float* bias;
+  const bf16* u_prev; long long prev_rows_per_n, crop; const float* scale; const float* shift;
+  const bf16* mask; float drop_p; uint64_t seed, offset; const uint64_t* rng;
+  bf16* u; double* stats;
+  float s1, s2;
+  __device__ __forceinline__ void chunk(long long p, long long n, long long rem, bool valid, int c0, float v[32]) {
+    const int lane = threadIdx.x & 31;
+    float h[32];
+    if (valid) {
+      const bf16* rp = u_prev + (n * prev_rows_per_n + rem + crop) * 32;
+      uint64_t sd = 0, of = 0;
+      if (!mask && drop_p > 0.f) { sd = rng ? __ldg(rng) : seed; of = rng ? offset + __ldg(rng + 1) : offset; }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float m[4] = {1.f, 1.f, 1.f, 1.f}, r[4];
+        if (mask) load4(mask + p * 32 + 4 * j, m);
+        else if (drop_p > 0.f) dropout4(sd, of, (uint64_t)(p * 8 + j), drop_p, m);
+        load4(rp + 4 * j, r);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = 4 * j + i;
+          float rr = scale ? fmaf(r[i], __ldg(scale + c), __ldg(shift + c)) : r[i];
+          h[c] = (v[c] + __ldg(bias + c)) * m[i] + rr;
+        }
+      }
+      store_bf16x16(u + p * 32, h);
+      store_bf16x16(u + p * 32 + 16, h + 16);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) h[c] = 0.f;
+    }
+    float t[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) t[c] = h[c];
+    s1 += warp_column_sums(t, lane);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) t[c] = h[c] * h[c];
+    s2 += warp_column_sums(t, lane);
+  }
+  __device__ __forceinline__ void finish() {
+    const int lane = threadIdx.x & 31;
+    atomicAdd(stats + lane, (double)s1);
+    atomicAdd(stats + 32 + lane, (double)s2);
+  }
+};
+
+struct EpiSlotTC {   // 32-column chunk c0 -> slot c0/32 of a slot-major buffer
+  bf16* out; long long slot_stride;
+  __device__ __forceinline__ void chunk(long long p, long long, long long, bool valid, int c0, float v[32]) {
+    if (!valid) return;
+    bf16* dst = out + (long long)(c0 >> 5) * slot_stride + p * 32;
+    store_bf16x16(dst, v);
+    store_bf16x16(dst + 16, v + 16);
+  }
+  __device__ __forceinline__ void finish() {}
+};
+
+struct EpiGateBwdTC {   // N = 32: dx = acc + du(cropped rows); (sum dx, sum dx*u_prev)
+  const bf16* du; long long du_rows_per_n, crop;
+  const bf16* u_prev; float* dx; double* stats;
+  float s1, s2;
+  __device__ __forceinline__ void chunk(long long p, long long n, long long rem, bool valid, int c0, float v[32]) {
+    const int lane = threadIdx.x & 31;
+    float up[32];
+    if (valid) {
+      if (du && rem >= crop) {
+        const bf16* gp = du + (n * du_rows_per_n + rem - crop) * 32;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float g[4]; load4(gp + 4 * j, g);
+          v[4 * j] += g[0]; v[4 * j + 1] += g[1]; v[4 * j + 2] += g[2]; v[4 * j + 3] += g[3];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        load4(u_prev + p * 32 + 4 * j, up + 4 * j);
+        store4(dx + p * 32 + 4 * j, v + 4 * j);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) { v[c] = 0.f; up[c] = 0.f; }
+    }
+    float t[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) t[c] = v[c];
+    s1 += warp_column_sums(t, lane);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) t[c] = v[c] * up[c];
+    s2 += warp_column_sums(t, lane);
+  }
+  __device__ __forceinline__ void finish() {
+    const int lane = threadIdx.x & 31;
+    atomicAdd(stats + lane, (double)s1);
+    atomicAdd(stats + 32 + lane, (double)s2);
   }
 };
 
@@ -472,13 +609,39 @@ static int layer_fwd_t(const gwn_layer_cfg* c, const gwn_layer_fwd_args* g, cuda
     ch.base = g->u_prev; ch.rows_per_n = RI; ch.row_off = (long long)j * c->dilation * c->V;
     ch.pitch = 32; ch.col_off = 0; ch.scale = g->scale; ch.shift = g->shift; ch.relu = 0;
   }
+  bool tc = false;
+  if constexpr (std::is_same<T, bf16>::value) tc = use_tc_hops<T>(c, g->hop_mats) && g->ws_w != nullptr && c->taps <= 4;
+  uint8_t* wsw = reinterpret_cast<uint8_t*>(g->ws_w);
+  const long long last_begin = (long long)(c->Lout - c->Lf) * c->V, last_rows = (long long)c->Lf * c->V;
+  if (tc) {
+    if constexpr (std::is_same<T, bf16>::value) {
+      // fold the previous layer's BatchNorm affine into the gate weights/bias, build the bf16 UMMA image
+      WPrepParams wp{};
+      wp.W = g->w_fg; wp.ld = 64; wp.transposed = 0; wp.K = 32 * c->taps; wp.N = 64;
+      for (int j = 0; j < c->taps; ++j) wp.w_off[j] = (long long)j * 32 * 64;
+      wp.scale = g->scale; wp.shift = g->shift; wp.bias = g->b_fg;
+      wp.img = reinterpret_cast<bf16*>(wsw); wp.bias_out = reinterpret_cast<float*>(wsw + 48 * 1024);
+      if (int rc = launch_wprep(wp, st)) return rc;
+      PgParams pg{};
+      pg.n_chunks = c->taps; pg.rows_per_n_out = RO; pg.P = P; pg.N = 64; pg.w_img = wp.img;
+      for (int j = 0; j < c->taps; ++j)
+        pg.ch[j] = PgChunk{reinterpret_cast<const bf16*>(g->u_prev), RI, (long long)j * c->dilation * c->V, 32, 0};
+      EpiGateTC eg{};
+      eg.bias = wp.bias_out; eg.z = cat;
+      eg.a = c->training ? reinterpret_cast<bf16*>(g->a) : nullptr;
+      eg.b = c->training ? reinterpret_cast<bf16*>(g->b) : nullptr;
+      eg.z_last = reinterpret_cast<bf16*>(g->z_last); eg.last_begin = last_begin; eg.last_rows = last_rows;
+      if (int rc = launch_pos_gemm_tc(pg, eg, st)) return rc;
+    }
+  } else {
   EpiGate<T> eg{};
   eg.bias = g->b_fg; eg.zcat = cat; eg.zpitch = 32;   // slot 0 of the slot-major concat buffer
   eg.a = c->training ? reinterpret_cast<T*>(g->a) : nullptr;
   eg.b = c->training ? reinterpret_cast<T*>(g->b) : nullptr;
   eg.z_last = reinterpret_cast<T*>(g->z_last);
-  eg.last_begin = (long long)(c->Lout - c->Lf) * c->V; eg.last_rows = (long long)c->Lf * c->V;
+  eg.last_begin = last_begin; eg.last_rows = last_rows;
   if (int rc = launch_pos_gemm<T, 64>(A, g->w_fg, 64, eg, st)) return rc;
+  }
   if (!c->has_gconv) return 0;
   // diffusion hops into the concat slots, then mlp + dropout + residual + stats
   if (int rc = hops_forward<T>(c, cat, g->supports, g->hop_mats, st)) return rc;
@@ -488,6 +651,26 @@ static int layer_fwd_t(const gwn_layer_cfg* c, const gwn_layer_fwd_args* g, cuda
   for (int q = 0; q < nslots; ++q) {
     AChunk& ch = M.ch[q];
     ch.base = cat + q * P * 32; ch.rows_per_n = RO; ch.row_off = 0; ch.pitch = 32; ch.col_off = 0;
+  }
+  if (tc && nslots <= 7) {
+    if constexpr (std::is_same<T, bf16>::value) {
+      WPrepParams wp{};
+      wp.W = g->w_mlp; wp.ld = 32; wp.transposed = 0; wp.K = mlp_in; wp.N = 32;
+      for (int q = 0; q < nslots; ++q) wp.w_off[q] = (long long)q * 32 * 32;
+      wp.bias = g->b_mlp;
+      wp.img = reinterpret_cast<bf16*>(wsw + 64 * 1024); wp.bias_out = reinterpret_cast<float*>(wsw + 112 * 1024);
+      if (int rc = launch_wprep(wp, st)) return rc;
+      PgParams pg{};
+      pg.n_chunks = nslots; pg.rows_per_n_out = RO; pg.P = P; pg.N = 32; pg.w_img = wp.img;
+      for (int q = 0; q < nslots; ++q) pg.ch[q] = PgChunk{cat + q * P * 32, RO, 0, 32, 0};
+      EpiMlpTC em{};
+      em.bias = wp.bias_out; em.u_prev = reinterpret_cast<const bf16*>(g->u_prev); em.prev_rows_per_n = RI;
+      em.crop = (long long)(c->Lin - c->Lout) * c->V; em.scale = g->scale; em.shift = g->shift;
+      em.mask = c->training ? reinterpret_cast<const bf16*>(g->drop_mask) : nullptr;
+      em.drop_p = c->training ? c->dropout_p : 0.f; em.seed = c->seed; em.offset = c->offset; em.rng = g->rng;
+      em.u = reinterpret_cast<bf16*>(g->u); em.stats = g->stats; em.s1 = 0.f; em.s2 = 0.f;
+      return launch_pos_gemm_tc(pg, em, st);
+    }
   }
   EpiMlp<T> em{};
   em.stats = g->stats; em.bias = g->b_mlp;
@@ -555,8 +738,26 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
     D.n_chunks = 1; D.rows_per_n_out = RO; D.P = P;
     D.ch[0].base = dh; D.ch[0].rows_per_n = RO; D.ch[0].row_off = 0; D.ch[0].pitch = 32; D.ch[0].col_off = 0;
     D.ch[0].w_off = 0;
-    EpiSlotStore<T> es{}; es.out = dcat; es.slot_stride = P * 32;
-    if (int rc = launch_pos_gemm_wt<T, 32>(D, g->w_mlp, mlp_in, 32, es, st)) return rc;
+    bool dcat_done = false;
+    if constexpr (std::is_same<T, bf16>::value) {
+      if (use_tc_hops<T>(c, g->hop_mats) && g->ws_w != nullptr && mlp_in <= 256) {
+        uint8_t* wsw = reinterpret_cast<uint8_t*>(g->ws_w);
+        WPrepParams wp{};
+        wp.W = g->w_mlp; wp.ld = 32; wp.transposed = 1; wp.K = 32; wp.N = mlp_in; wp.w_off[0] = 0;
+        wp.img = reinterpret_cast<bf16*>(wsw); wp.bias_out = nullptr;
+        if (int rc = launch_wprep(wp, st)) return rc;
+        PgParams pg{};
+        pg.n_chunks = 1; pg.rows_per_n_out = RO; pg.P = P; pg.N = mlp_in; pg.w_img = wp.img;
+        pg.ch[0] = PgChunk{dh, RO, 0, 32, 0};
+        EpiSlotTC es{}; es.out = dcat; es.slot_stride = P * 32;
+        if (int rc = launch_pos_gemm_tc(pg, es, st)) return rc;
+        dcat_done = true;
+      }
+    }
+    if (!dcat_done) {
+      EpiSlotStore<T> es{}; es.out = dcat; es.slot_stride = P * 32;
+      if (int rc = launch_pos_gemm_wt<T, 32>(D, g->w_mlp, mlp_in, 32, es, st)) return rc;
+    }
     // hops backward
     bool tc_done = false;
     if constexpr (std::is_same<T, bf16>::value) {
@@ -665,6 +866,27 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
   EpiGateBwdData<T> ex{};
   ex.stats = g->dx_stats; ex.du = du; ex.du_rows_per_n = RO; ex.crop = (long long)(c->Lin - c->Lout) * c->V;
   ex.u_prev = reinterpret_cast<const T*>(g->u_prev); ex.dx = g->dx_prev;
+  if (tc_gate && g->ws_w != nullptr && 2 * c->taps <= PG_TC_MAX_CHUNKS) {
+    if constexpr (std::is_same<T, bf16>::value) {
+      uint8_t* wsw = reinterpret_cast<uint8_t*>(g->ws_w);
+      WPrepParams wp{};
+      wp.W = g->w_fg; wp.ld = 64; wp.transposed = 1; wp.K = 64 * c->taps; wp.N = 32;
+      for (int j = 0; j < c->taps; ++j)
+        for (int h = 0; h < 2; ++h) wp.w_off[2 * j + h] = (long long)j * 32 * 64 + h * 32;
+      wp.img = reinterpret_cast<bf16*>(wsw + 64 * 1024); wp.bias_out = nullptr;
+      if (int rc = launch_wprep(wp, st)) return rc;
+      PgParams pg{};
+      pg.n_chunks = 2 * c->taps; pg.rows_per_n_out = RI; pg.P = PI; pg.N = 32; pg.w_img = wp.img;
+      for (int j = 0; j < c->taps; ++j)
+        for (int h = 0; h < 2; ++h)
+          pg.ch[2 * j + h] = PgChunk{dfg16, RO, -(long long)j * c->dilation * c->V, 64, h * 32};
+      EpiGateBwdTC eb2{};
+      eb2.du = du; eb2.du_rows_per_n = RO; eb2.crop = (long long)(c->Lin - c->Lout) * c->V;
+      eb2.u_prev = reinterpret_cast<const bf16*>(g->u_prev); eb2.dx = g->dx_prev; eb2.stats = g->dx_stats;
+      eb2.s1 = 0.f; eb2.s2 = 0.f;
+      return launch_pos_gemm_tc(pg, eb2, st);
+    }
+  }
   if (tc_gate) return launch_pos_gemm_wt<bf16, 32>(X, g->w_fg, 32, 64, ex, st);
   return launch_pos_gemm_wt<float, 32>(X, g->w_fg, 32, 64, ex, st);
 }

@@ -1,0 +1,45 @@
+// tcgen05 position GEMM:  C[p, n] = epi( sum_k A[p, k] * W[k, n] ),  M = 128 positions per tile.
+//   A: gathered from 32-channel chunks of channels-last bf16 sources (taps / slots), cp.async'ed into the
+//      K-major no-swizzle canonical layout; W: bf16 image resident in shared memory for the whole kernel
+//      (weight-stationary, persistent CTAs); D: fp32 in TMEM, double buffered; epilogue functors fuse the
+//      gate non-linearity / bias+dropout+residual+BN statistics / slot scatter / residual-grad add.
+#pragma once
+#include "common.cuh"
+
+namespace gwn {
+
+constexpr int PG_TC_MAX_CHUNKS = 16;
+
+struct PgChunk {
+  const bf16* base;
+  long long rows_per_n;
+  long long row_off;
+  int pitch;
+  int col_off;
+};
+
+struct PgParams {
+  PgChunk ch[PG_TC_MAX_CHUNKS];
+  int n_chunks;                 // K = 32 * n_chunks
+  long long rows_per_n_out, P;
+  int N;                        // output columns (multiple of 16, <= 256)
+  const bf16* w_img;            // [K/8][N][8]
+  int n_tiles;
+};
+
+// builds w_img (+ folded bias) from fp32 weights; see tc_gemm.cu
+struct WPrepParams {
+  const float* W;
+  long long w_off[PG_TC_MAX_CHUNKS];   // element offset of chunk q
+  int ld;                       // stride of the non-contiguous index
+  int transposed;               // 0: (k,n) at w_off[q] + kk*ld + n ; 1: w_off[q] + n*ld + kk
+  int K, N;
+  const float* scale;           // optional [32]: W'(k,n) = scale[k%32] * W(k,n)
+  const float* shift;           // optional [32]: bias'(n) = bias(n) + sum_k shift[k%32] * W(k,n)
+  const float* bias;            // optional [N]
+  bf16* img;                    // out [K/8][N][8]
+  float* bias_out;              // out [N] (may be NULL)
+};
+int launch_wprep(const WPrepParams& w, cudaStream_t st);
+
+}  // namespace gwn

@@ -236,11 +236,13 @@ def layer_fwd(u_prev: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], 
     u = torch.empty((N, Lout, V, CH) if has_gconv else (0,), device=dev, dtype=dt)
     stats = torch.empty((2, CH), device=dev, dtype=torch.float64)
     ws_cat = torch.empty((P, mlp_in), device=dev, dtype=dt)
+    ws_w = torch.empty((128 * 1024,), device=dev, dtype=torch.uint8) if hop_mats is not None else None
     cfg = _layer_cfg(N, V, Lin, Lout, Lf, taps, dilation, n_sup, order, dt, training, has_gconv, dropout_p, seed,
                      offset)
     args = LayerFwdArgs(u_prev=_p(u_prev), scale=_p(scale), shift=_p(shift), w_fg=_p(w_fg), b_fg=_p(b_fg),
                         w_mlp=_p(w_mlp), b_mlp=_p(b_mlp), supports=_sup_array(supports if has_gconv else []),
-                        drop_mask=_p(drop_mask), rng=_p(rng), hop_mats=_p(hop_mats), a=_p(a) if training else None,
+                        drop_mask=_p(drop_mask), rng=_p(rng), hop_mats=_p(hop_mats), ws_w=_p(ws_w),
+                        a=_p(a) if training else None,
                         b=_p(b) if training else None, z_last=_p(z_last), u=_p(u) if has_gconv else None,
                         stats=_p(stats), ws_cat=_p(ws_cat))
     with torch.cuda.device(dev):
@@ -283,10 +285,11 @@ def layer_bwd(u_prev: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], 
     ws_cat = torch.empty((P, mlp_in) if has_du else (0,), device=dev, dtype=dt)
     ws_dcat = torch.empty((P, mlp_in) if has_du else (0,), device=dev, dtype=dt)
     ws_dfg = torch.empty((P, 2 * CH), **f32)
+    ws_w = torch.empty((128 * 1024,), device=dev, dtype=torch.uint8) if hop_mats is not None else None
     cfg = _layer_cfg(N, V, Lin, Lout, Lf, taps, dilation, n_sup, order, dt, training, True, dropout_p, seed, offset)
     args = LayerBwdArgs(u_prev=_p(u_prev), scale=_p(scale), shift=_p(shift), w_fg=_p(w_fg), w_mlp=_p(w_mlp),
                         supports=_sup_array(supports), drop_mask=_p(drop_mask), rng=_p(rng),
-                        hop_mats=_p(hop_mats), a=_p(a), b=_p(b),
+                        hop_mats=_p(hop_mats), ws_w=_p(ws_w), a=_p(a), b=_p(b),
                         du=_p(du), dz_last=_p(dz_last), dx_prev=_p(dx_prev), dx_stats=_p(dx_stats),
                         dw_fg=_p(dw_fg), db_fg=_p(db_fg), dw_mlp=_p(dw_mlp), db_mlp=_p(db_mlp),
                         ws_cat=_p(ws_cat) if has_du else None, ws_dcat=_p(ws_dcat) if has_du else None,
