@@ -187,6 +187,19 @@ int gwn_hop_mats_prep(const float* const* supports, int n_supports, int V, void*
 int gwn_hop_tc(const void* mats, int n_mats, int mat, void* buf, int pitch, int slot_in, int slot_out,
                int slabs, int V, void* stream);
 
+/* ---- tensor-core diffusion hops for supports that do NOT fit on chip (V > 128: the 3,100-node configs), bf16 ----
+ * TMA-tiled tcgen05 GEMM (csrc/tma_gemm.cuh).  gwn_support_images_prep builds per support the bf16 images
+ * [2][V][Vp] (Vp = 8*ceil(V/8)): image 0 = A^T (operand of the forward hop y[w] = sum_v A[v,w] x[v]),
+ * image 1 = A (operand of the backward hop).  `supports` is a HOST array of device pointers.
+ * gwn_hop_big: y = image(support, which) * x (+ add) over slot-major [slabs*V, 32] bf16 buffers.
+ * gwn_gemm_test: C[M][N] fp32 = A * B^T through every operand staging mode of the GEMM (unit tests). */
+long long gwn_support_images_bytes(int V, int n_supports);
+int gwn_support_images_prep(const float* const* supports, int n_supports, int V, void* out, void* stream);
+int gwn_hop_big(const void* images, int n_supports, int support, int which, const void* x, void* y,
+                const void* add, long long slabs, int V, void* stream);
+int gwn_gemm_test(const void* A, const void* B, float* C, int M, int N, int K, int a_mode, int b_mode,
+                  int lda, int ldb, int bn, int splits, void* stream);
+
 /* ---- nconv primitive, exposed for unit tests  graph_wavenet.py:60-66 ----
  * y[s,w,c] = sum_v x[s,v,c] * A[v,w] (transpose_a=0) or A[w,v] (transpose_a=1);
  * x,y: [slabs, V, pitch] slots of 32 channels at column offsets xoff/yoff. */

@@ -1,0 +1,231 @@
+// Host side of the TMA-fed tcgen05 GEMM (tma_gemm.cuh): tensor-map construction through the driver entry
+// point (no -lcuda link dependency), operand descriptor constants, and the diffusion hop for graphs whose
+// supports do not fit on chip (V > 128; the 3,100-node configurations):
+//
+//   Y[s, w, c] (+)= sum_v Aop[w, v] * X[s, v, c]           nconv, graph_wavenet.py:60-66
+//
+//   GEMM view: M = w (node), K = v (node), N = (slab, channel).  A operand = bf16 image of the support,
+//   [w][v] row-major (K-major, 128B swizzle; Aop = A^T for the forward hop, A for the backward hop);
+//   B operand = the channels-last activation slot itself (MN-major, 64B swizzle, 3-D TMA box of 8 slabs).
+#include <mutex>
+
+#include "tma_gemm.cuh"
+#include "tma_hops.cuh"
+
+namespace gwn {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int tg_map_2d(CUtensorMap* map, const void* base, uint64_t dim0, uint64_t dim1, uint64_t stride1_bytes, uint32_t box0,
+              uint32_t box1) {
+  EncodeTiledFn fn = encode_fn();
+  GWN_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  GWN_REQUIRE(stride1_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(base) % 16) == 0 && box0 * 2 <= 128 && box1 <= 256,
+              "tma map: unaligned tensor (stride %llu)", (unsigned long long)stride1_bytes);
+  cuuint64_t dims[2] = {dim0, dim1};
+  cuuint64_t strides[1] = {stride1_bytes};
+  cuuint32_t box[2] = {box0, box1};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GWN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(2d) failed: %d", (int)r);
+  return 0;
+}
+
+int tg_map_slabs(CUtensorMap* map, const void* base, uint64_t V, uint64_t slabs, uint32_t box_v, uint32_t box_slabs) {
+  EncodeTiledFn fn = encode_fn();
+  GWN_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  GWN_REQUIRE((reinterpret_cast<uintptr_t>(base) % 16) == 0 && box_v <= 256 && box_slabs <= 256, "tma slab map: bad box");
+  cuuint64_t dims[3] = {32, V, slabs};
+  cuuint64_t strides[2] = {64, V * 64};
+  cuuint32_t box[3] = {32, box_v, box_slabs};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GWN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3d) failed: %d", (int)r);
+  return 0;
+}
+
+void tg_operand(TgOperand& o, int mode, int rows) {
+  o.mode = mode;
+  if (mode == TG_K_SW128) {            // [rows][64 k] : row = 128 B, 8-row atoms of 1024 B
+    o.tile_bytes = (uint32_t)rows * 128u;
+    o.lbo = 16; o.sbo = 1024; o.kstep = 32; o.layout = 2;
+    o.n_boxes = 1; o.box_bytes = o.tile_bytes; o.box_mn = rows;
+  } else if (mode == TG_MN_SW128) {    // boxes of [64 k][64 mn]: 8 KB each
+    o.n_boxes = rows / 64; o.box_bytes = 64u * 128u; o.box_mn = 64;
+    o.tile_bytes = (uint32_t)o.n_boxes * o.box_bytes;
+    o.lbo = o.box_bytes; o.sbo = 1024; o.kstep = 2048; o.layout = 2;
+  } else {                             // [rows/32 slabs][64 nodes][64 B]
+    o.n_boxes = 1; o.box_mn = rows; o.tile_bytes = (uint32_t)(rows / 32) * 64u * 64u; o.box_bytes = o.tile_bytes;
+    o.lbo = 64u * 64u; o.sbo = 512; o.kstep = 1024; o.layout = 4;
+  }
+  o.tile_bytes = (o.tile_bytes + 1023u) & ~1023u;
+}
+
+int tg_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return sms;
+}
+
+// ------------------------------------------------------------------------------------------ epilogues
+struct EpiHopBig {   // accumulator row = node w, column = (slab, channel)
+  bf16* out; const bf16* add; int V; long long slabs;
+  __device__ __forceinline__ void chunk(int m, bool m_ok, int n0, float v[32]) const {
+    const long long slab = n0 >> 5;
+    if (!m_ok || slab >= slabs) return;
+    const long long off = (slab * V + m) * 32;
+    if (add) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t[4];
+        load4(add + off + 4 * j, t);
+        v[4 * j] += t[0]; v[4 * j + 1] += t[1]; v[4 * j + 2] += t[2]; v[4 * j + 3] += t[3];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 pk;
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
+      __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+      __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+      pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+      pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+      *reinterpret_cast<uint4*>(out + off + 8 * j) = pk;
+    }
+  }
+};
+
+struct EpiStoreF32 {  // C[m][n] fp32 row-major (tests); atomic when split-K
+  float* C; int ldc, N, atomic;
+  __device__ __forceinline__ void chunk(int m, bool m_ok, int n0, float v[32]) const {
+    if (!m_ok) return;
+    float* dst = C + (long long)m * ldc + n0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (n0 + j < N) {
+        if (atomic) atomicAdd(dst + j, v[j]); else dst[j] = v[j];
+      }
+  }
+};
+
+// ------------------------------------------------------------------------------------------ big-V hop
+int launch_hop_big(const bf16* img, int Vp, const bf16* X, bf16* Y, const bf16* add, long long slabs, int V,
+                   cudaStream_t st) {
+  if (slabs <= 0) return 0;
+  GWN_REQUIRE(Vp % 8 == 0 && Vp >= V, "hop_big: image pitch %d must be a multiple of 8 and >= V", Vp);
+  CUtensorMap ma, mb;
+  if (int rc = tg_map_2d(&ma, img, (uint64_t)V, (uint64_t)V, (uint64_t)Vp * 2, 64, 128)) return rc;
+  const int bn = slabs >= 8 ? 256 : (int)(32 * slabs);
+  if (int rc = tg_map_slabs(&mb, X, (uint64_t)V, (uint64_t)slabs, 64, (uint32_t)(bn / 32))) return rc;
+  TgParams p{};
+  p.M = V; p.K = V; p.N = (int)(slabs * 32); p.bn = bn; p.splits = 1;
+  GWN_REQUIRE(slabs * 32 < (1ll << 31), "hop_big: too many slabs");
+  tg_operand(p.a, TG_K_SW128, 128);
+  tg_operand(p.b, TG_MN_SW64, bn);
+  EpiHopBig e{Y, add, V, slabs};
+  return launch_tma_gemm(ma, mb, p, e, st);
+}
+
+// supports fp32 [V][V] -> bf16 images [2][V][Vp]: image 0 = A^T (forward hop operand), image 1 = A (backward)
+__global__ void support_images_kernel(const float* __restrict__ A, bf16* __restrict__ out, int V, int Vp) {
+  __shared__ float t[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;    // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int r = by + j, c = bx + tx;
+    const float v = (r < V && c < V) ? A[(long long)r * V + c] : 0.f;
+    t[j][tx] = v;
+    if (r < V && c < Vp) out[(long long)V * Vp + (long long)r * Vp + c] = __float2bfloat16_rn(v);   // image 1 = A
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int r = bx + j, c = by + tx;     // transposed: out0[r][c] = A[c][r]
+    if (r < V && c < Vp) out[(long long)r * Vp + c] = __float2bfloat16_rn(c < V ? t[tx][j] : 0.f);
+  }
+}
+
+}  // namespace gwn
+
+using namespace gwn;
+
+extern "C" long long gwn_support_images_bytes(int V, int n_supports) {
+  const long long Vp = ((V + 7) / 8) * 8;
+  return (long long)n_supports * 2 * V * Vp * 2;
+}
+
+extern "C" int gwn_support_images_prep(const float* const* supports, int n_supports, int V, void* out, void* stream) {
+  GWN_REQUIRE(supports && out && n_supports >= 1 && n_supports <= GWN_MAX_SUPPORTS && V >= 1, "support_images: bad argument");
+  const int Vp = ((V + 7) / 8) * 8;
+  dim3 grid((unsigned)cdiv(Vp, 32), (unsigned)cdiv(V, 32)), block(32, 8);
+  for (int s = 0; s < n_supports; ++s) {
+    support_images_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        supports[s], reinterpret_cast<bf16*>(out) + (long long)s * 2 * V * Vp, V, Vp);
+    GWN_LAUNCHED();
+  }
+  return 0;
+}
+
+// One hop over a slot-major activation buffer: y = Aop * x (+ add), Aop = image `which` (0: A^T, 1: A) of support s.
+extern "C" int gwn_hop_big(const void* images, int n_supports, int support, int which, const void* x, void* y,
+                           const void* add, long long slabs, int V, void* stream) {
+  GWN_REQUIRE(images && x && y && support >= 0 && support < n_supports && (which == 0 || which == 1), "hop_big: bad argument");
+  const int Vp = ((V + 7) / 8) * 8;
+  const bf16* img = reinterpret_cast<const bf16*>(images) + ((long long)support * 2 + which) * V * Vp;
+  return launch_hop_big(img, Vp, reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y),
+                        reinterpret_cast<const bf16*>(add), slabs, V, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// Test entry: C[M][N] fp32 = A (.) B in every staging mode (see tma_gemm.cuh).
+//   a_mode 0: A [M][lda] (K contiguous)      a_mode 1: A [K][lda] (M contiguous)
+//   b_mode 0: B [N][ldb] (K contiguous)      b_mode 1: B [K][ldb] (N contiguous)     b_mode 2: B [N/32][K][32]
+extern "C" int gwn_gemm_test(const void* A, const void* B, float* C, int M, int N, int K, int a_mode, int b_mode,
+                             int lda, int ldb, int bn, int splits, void* stream) {
+  GWN_REQUIRE(A && B && C, "gemm_test: NULL argument");
+  CUtensorMap ma, mb;
+  TgParams p{};
+  p.M = M; p.N = N; p.K = K; p.bn = bn; p.splits = splits;
+  if (a_mode == 0) {
+    if (int rc = tg_map_2d(&ma, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, 64, 128)) return rc;
+    tg_operand(p.a, TG_K_SW128, 128);
+  } else {
+    if (int rc = tg_map_2d(&ma, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, 64)) return rc;
+    tg_operand(p.a, TG_MN_SW128, 128);
+  }
+  if (b_mode == 0) {
+    if (int rc = tg_map_2d(&mb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, 64, (uint32_t)bn)) return rc;
+    tg_operand(p.b, TG_K_SW128, bn);
+  } else if (b_mode == 1) {
+    GWN_REQUIRE(bn % 64 == 0, "gemm_test: MN-major B needs bn %% 64 == 0");
+    if (int rc = tg_map_2d(&mb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, 64)) return rc;
+    tg_operand(p.b, TG_MN_SW128, bn);
+  } else {
+    if (int rc = tg_map_slabs(&mb, B, (uint64_t)K, (uint64_t)(N / 32), 64, (uint32_t)(bn / 32))) return rc;
+    tg_operand(p.b, TG_MN_SW64, bn);
+  }
+  EpiStoreF32 e{C, N, N, splits > 1 ? 1 : 0};
+  return launch_tma_gemm(ma, mb, p, e, reinterpret_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,9 @@
+// Diffusion hop for supports that do not fit on chip (V > 128): TMA-tiled tcgen05 GEMM, see tma_gemm.cu.
+#pragma once
+#include "common.cuh"
+
+namespace gwn {
+// y[s,w,c] = sum_v img[w][v] * x[s,v,c] (+ add[s,w,c]);  img: bf16 [V][Vp] row-major; x, y, add: slot-major [slabs*V, 32]
+int launch_hop_big(const bf16* img, int Vp, const bf16* X, bf16* Y, const bf16* add, long long slabs, int V,
+                   cudaStream_t st);
+}  // namespace gwn
