@@ -197,6 +197,8 @@ long long gwn_support_images_bytes(int V, int n_supports);
 int gwn_support_images_prep(const float* const* supports, int n_supports, int V, void* out, void* stream);
 int gwn_hop_big(const void* images, int n_supports, int support, int which, const void* x, void* y,
                 const void* add, long long slabs, int V, void* stream);
+/* dA[v,w] += sum_{s,c} x[s,v,c] * g[s,w,c]: gradient of nconv wrt the support (fp32 [V][V], accumulated). */
+int gwn_dadj_big(const void* x, const void* g, float* dA, long long slabs, int V, void* stream);
 int gwn_gemm_test(const void* A, const void* B, float* C, int M, int N, int K, int a_mode, int b_mode,
                   int lda, int ldb, int bn, int splits, void* stream);
 

@@ -79,6 +79,7 @@ SIGNATURES = {
     'gwn_support_images_bytes': (_ll, [_i, _i]),
     'gwn_support_images_prep': (_i, [vp, _i, _i, vp, vp]),
     'gwn_hop_big': (_i, [vp, _i, _i, _i, vp, vp, vp, _ll, _i, vp]),
+    'gwn_dadj_big': (_i, [vp, vp, vp, _ll, _i, vp]),
     'gwn_gemm_test': (_i, [vp, vp, vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, vp]),
     'gwn_node_mix': (_i, [vp, _i, _i, vp, _i, _i, _i, vp, _i, _i, _i, _i, vp]),
     'gwn_comm_unique_id': (_i, [vp]),

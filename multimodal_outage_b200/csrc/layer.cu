@@ -7,6 +7,7 @@
 
 #include "gemm.cuh"
 #include "tc_hops.cuh"
+#include "tma_hops.cuh"
 #include "tc_wgrad.cuh"
 #include "tc_gemm_impl.cuh"
 
@@ -551,6 +552,21 @@ static bool use_tc_hops(const gwn_layer_cfg* c, const void* hop_mats) {
          hops_tc_supported(c->V, 2 * c->n_supports) != 0;
 }
 
+// 0: CUDA-core hops; 1: supports resident on chip (tc_hops.cu); 2: TMA-tiled GEMM per hop (tma_gemm.cu, V > 80).
+// `hop_mats` holds gwn_hop_mats_prep images in mode 1 and gwn_support_images_prep images in mode 2.
+template <typename T>
+static int tc_mode(const gwn_layer_cfg* c, const void* hop_mats) {
+  if constexpr (!std::is_same<T, bf16>::value) return 0;
+  if (hop_mats == nullptr) return 0;
+  if (c->n_supports == 0) return 1;    // no hops at all: the position GEMMs still run on tensor cores
+  if (c->order == 2 && hops_tc_supported(c->V, 2 * c->n_supports)) return 1;
+  return 2;
+}
+static const bf16* big_image(const gwn_layer_cfg* c, const void* hop_mats, int s, int which) {
+  const long long Vp = ((c->V + 7) / 8) * 8;
+  return reinterpret_cast<const bf16*>(hop_mats) + ((long long)s * 2 + which) * c->V * Vp;
+}
+
 // The concat buffers are SLOT-MAJOR: slot q (32 channels of hop q) is a contiguous [P, 32] tensor at
 // buf + q*P*32, so a tile of a slot is one contiguous run of 64-byte rows (full 128-byte DRAM lines).
 static void hop_params_base(HopParams& p, const gwn_layer_cfg* c, bf16* buf, const void* hop_mats) {
@@ -579,11 +595,23 @@ static int hops_forward_tc(const gwn_layer_cfg* c, bf16* cat, const void* hop_ma
 template <typename T>
 static int hops_forward(const gwn_layer_cfg* c, T* cat, const float* const* supports,
                         const void* hop_mats, cudaStream_t st) {
-  if constexpr (std::is_same<T, bf16>::value) {
-    if (use_tc_hops<T>(c, hop_mats)) return hops_forward_tc(c, cat, hop_mats, st);
-  }
   const long long slabs = (long long)c->N * c->Lout;
   const long long SS = slabs * c->V * 32;   // slot stride
+  if constexpr (std::is_same<T, bf16>::value) {
+    const int mode = tc_mode<T>(c, hop_mats);
+    if (mode == 1 && c->n_supports > 0) return hops_forward_tc(c, cat, hop_mats, st);
+    if (mode == 2) {
+      const int Vp = ((c->V + 7) / 8) * 8;
+      for (int s = 0; s < c->n_supports; ++s)
+        for (int k = 1; k <= c->order; ++k) {
+          const int slot = 1 + s * c->order + (k - 1), src = (k == 1) ? 0 : slot - 1;
+          if (int rc = launch_hop_big(big_image(c, hop_mats, s, 0), Vp, cat + src * SS, cat + slot * SS, nullptr, slabs,
+                                      c->V, st))
+            return rc;
+        }
+      return 0;
+    }
+  }
   for (int s = 0; s < c->n_supports; ++s)
     for (int k = 1; k <= c->order; ++k) {
       int slot = 1 + s * c->order + (k - 1);
@@ -610,7 +638,7 @@ static int layer_fwd_t(const gwn_layer_cfg* c, const gwn_layer_fwd_args* g, cuda
     ch.pitch = 32; ch.col_off = 0; ch.scale = g->scale; ch.shift = g->shift; ch.relu = 0;
   }
   bool tc = false;
-  if constexpr (std::is_same<T, bf16>::value) tc = use_tc_hops<T>(c, g->hop_mats) && g->ws_w != nullptr && c->taps <= 4;
+  if constexpr (std::is_same<T, bf16>::value) tc = tc_mode<T>(c, g->hop_mats) != 0 && g->ws_w != nullptr && c->taps <= 4;
   uint8_t* wsw = reinterpret_cast<uint8_t*>(g->ws_w);
   const long long last_begin = (long long)(c->Lout - c->Lf) * c->V, last_rows = (long long)c->Lf * c->V;
   if (tc) {
@@ -720,7 +748,7 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
     }
     bool wg_done = false;
     if constexpr (std::is_same<T, bf16>::value) {
-      if (use_tc_hops<T>(c, g->hop_mats) && wgrad_tc_supported(nslots, 32)) {
+      if (tc_mode<T>(c, g->hop_mats) != 0 && wgrad_tc_supported(nslots, 32)) {
         GWN_CUDA(cudaMemsetAsync(g->dw_mlp, 0, sizeof(float) * 32 * mlp_in, st));
         GWN_CUDA(cudaMemsetAsync(g->db_mlp, 0, sizeof(float) * 32, st));
         WgParams w{};
@@ -740,7 +768,7 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
     D.ch[0].w_off = 0;
     bool dcat_done = false;
     if constexpr (std::is_same<T, bf16>::value) {
-      if (use_tc_hops<T>(c, g->hop_mats) && g->ws_w != nullptr && mlp_in <= 256) {
+      if (tc_mode<T>(c, g->hop_mats) != 0 && g->ws_w != nullptr && mlp_in <= 256) {
         uint8_t* wsw = reinterpret_cast<uint8_t*>(g->ws_w);
         WPrepParams wp{};
         wp.W = g->w_mlp; wp.ld = 32; wp.transposed = 1; wp.K = 32; wp.N = mlp_in; wp.w_off[0] = 0;
@@ -761,7 +789,21 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
     // hops backward
     bool tc_done = false;
     if constexpr (std::is_same<T, bf16>::value) {
-      if (use_tc_hops<T>(c, g->hop_mats)) {
+      if (tc_mode<T>(c, g->hop_mats) == 2) {
+        // big graphs: sequential hops, each one TMA-tiled tensor-core GEMM; dA likewise (K = slab x channel)
+        const int Vp = ((c->V + 7) / 8) * 8;
+        for (int s = 0; s < c->n_supports; ++s)
+          for (int k = c->order; k >= 1; --k) {
+            const int slot = 1 + s * c->order + (k - 1), src = (k == 1) ? 0 : slot - 1;
+            if (g->support_needs_grad[s] && g->d_supports[s])
+              if (int rc = launch_dadj_big(cat + src * P * 32, dcat + slot * P * 32, g->d_supports[s], slabs, c->V, st))
+                return rc;
+            if (int rc = launch_hop_big(big_image(c, g->hop_mats, s, 1), Vp, dcat + slot * P * 32, dcat + src * P * 32,
+                                        dcat + src * P * 32, slabs, c->V, st))
+              return rc;
+          }
+        tc_done = true;
+      } else if (use_tc_hops<T>(c, g->hop_mats)) {
         // (1) supports that need dA: g1' = g1 + g2 * A^T (in place in the y1 slot), then dA from (z, g1'), (y1, g2)
         for (int s = 0; s < c->n_supports; ++s) {
           if (!(g->support_needs_grad[s] && g->d_supports[s])) continue;
@@ -820,7 +862,7 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
   }
   // gate backward: (dz + dz_last) -> dfg  (bf16 in tensor-core mode so it can be an MMA operand)
   bool tc_gate = false;
-  if constexpr (std::is_same<T, bf16>::value) tc_gate = use_tc_hops<T>(c, g->hop_mats) && wgrad_tc_supported(c->taps, 64);
+  if constexpr (std::is_same<T, bf16>::value) tc_gate = tc_mode<T>(c, g->hop_mats) != 0 && wgrad_tc_supported(c->taps, 64);
   const long long last_begin = (long long)(c->Lout - c->Lf) * c->V, last_rows = (long long)c->Lf * c->V;
   bf16* dfg16 = reinterpret_cast<bf16*>(g->ws_dfg);
   if (tc_gate)

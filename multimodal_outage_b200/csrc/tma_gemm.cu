@@ -67,15 +67,22 @@ void tg_operand(TgOperand& o, int mode, int rows) {
   o.mode = mode;
   if (mode == TG_K_SW128) {            // [rows][64 k] : row = 128 B, 8-row atoms of 1024 B
     o.tile_bytes = (uint32_t)rows * 128u;
-    o.lbo = 16; o.sbo = 1024; o.kstep = 32; o.layout = 2;
+    o.lbo = 16; o.sbo = 1024; o.layout = 2;
+    for (int i = 0; i < 4; ++i) o.koff[i] = 32u * i;
     o.n_boxes = 1; o.box_bytes = o.tile_bytes; o.box_mn = rows;
   } else if (mode == TG_MN_SW128) {    // boxes of [64 k][64 mn]: 8 KB each
     o.n_boxes = rows / 64; o.box_bytes = 64u * 128u; o.box_mn = 64;
     o.tile_bytes = (uint32_t)o.n_boxes * o.box_bytes;
-    o.lbo = o.box_bytes; o.sbo = 1024; o.kstep = 2048; o.layout = 2;
-  } else {                             // [rows/32 slabs][64 nodes][64 B]
+    o.lbo = o.box_bytes; o.sbo = 1024; o.layout = 2;
+    for (int i = 0; i < 4; ++i) o.koff[i] = 2048u * i;
+  } else if (mode == TG_MN_SW64) {     // [rows/32 slabs][64 nodes][64 B]
     o.n_boxes = 1; o.box_mn = rows; o.tile_bytes = (uint32_t)(rows / 32) * 64u * 64u; o.box_bytes = o.tile_bytes;
-    o.lbo = 64u * 64u; o.sbo = 512; o.kstep = 1024; o.layout = 4;
+    o.lbo = 64u * 64u; o.sbo = 512; o.layout = 4;
+    for (int i = 0; i < 4; ++i) o.koff[i] = 1024u * i;
+  } else {                             // TG_K_SW64: [2 slabs][rows nodes][64 B]
+    o.n_boxes = 1; o.box_mn = rows; o.tile_bytes = 2u * (uint32_t)rows * 64u; o.box_bytes = o.tile_bytes;
+    o.lbo = 16; o.sbo = 512; o.layout = 4;
+    o.koff[0] = 0; o.koff[1] = 32; o.koff[2] = (uint32_t)rows * 64u; o.koff[3] = (uint32_t)rows * 64u + 32u;
   }
   o.tile_bytes = (o.tile_bytes + 1023u) & ~1023u;
 }
@@ -150,6 +157,33 @@ int launch_hop_big(const bf16* img, int Vp, const bf16* X, bf16* Y, const bf16* 
   return launch_tma_gemm(ma, mb, p, e, st);
 }
 
+// dA[v, w] += sum_{s,c} X[s,v,c] * G[s,w,c]   (nconv gradient wrt the support; adaptive adjacency only)
+struct EpiAccF32 {
+  float* C; int ldc, N;
+  __device__ __forceinline__ void chunk(int m, bool m_ok, int n0, float v[32]) const {
+    if (!m_ok) return;
+    float* dst = C + (long long)m * ldc + n0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (n0 + j < N) dst[j] += v[j];
+  }
+};
+
+int launch_dadj_big(const bf16* X, const bf16* G, float* dA, long long slabs, int V, cudaStream_t st) {
+  if (slabs <= 0) return 0;
+  CUtensorMap ma, mb;
+  const int bn = V >= 256 ? 256 : 32 * (int)cdiv(V, 32);
+  if (int rc = tg_map_slabs(&ma, X, (uint64_t)V, (uint64_t)slabs, 128, 2)) return rc;
+  if (int rc = tg_map_slabs(&mb, G, (uint64_t)V, (uint64_t)slabs, (uint32_t)bn, 2)) return rc;
+  TgParams p{};
+  GWN_REQUIRE(slabs * 32 < (1ll << 31), "dadj_big: too many slabs");
+  p.M = V; p.N = V; p.K = (int)(slabs * 32); p.bn = bn; p.splits = 1;
+  tg_operand(p.a, TG_K_SW64, 128);
+  tg_operand(p.b, TG_K_SW64, bn);
+  EpiAccF32 e{dA, V, V};
+  return launch_tma_gemm(ma, mb, p, e, st);
+}
+
 // supports fp32 [V][V] -> bf16 images [2][V][Vp]: image 0 = A^T (forward hop operand), image 1 = A (backward)
 __global__ void support_images_kernel(const float* __restrict__ A, bf16* __restrict__ out, int V, int Vp) {
   __shared__ float t[32][33];
@@ -197,6 +231,12 @@ extern "C" int gwn_hop_big(const void* images, int n_supports, int support, int 
   const bf16* img = reinterpret_cast<const bf16*>(images) + ((long long)support * 2 + which) * V * Vp;
   return launch_hop_big(img, Vp, reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y),
                         reinterpret_cast<const bf16*>(add), slabs, V, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gwn_dadj_big(const void* x, const void* g, float* dA, long long slabs, int V, void* stream) {
+  GWN_REQUIRE(x && g && dA && V >= 1, "dadj_big: bad argument");
+  return launch_dadj_big(reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(g), dA, slabs, V,
+                         reinterpret_cast<cudaStream_t>(stream));
 }
 
 // Test entry: C[M][N] fp32 = A (.) B in every staging mode (see tma_gemm.cuh).

@@ -12,10 +12,13 @@
 //   TG_MN_SW128   [K][MN] row-major, MN contiguous    -> MN-major, SWIZZLE_128B, boxes (64 mn, 64 k)
 //   TG_MN_SW64    channels-last activations [slab][K=node][32 ch]: MN = (slab, ch) -> MN-major, SWIZZLE_64B,
 //                 one 3-D box (32 ch, 64 nodes, bn/32 slabs); each slab is one 64-byte swizzle atom column.
+//   TG_K_SW64     the same activations with K = (slab, ch) and MN = node (support gradient dA = X^T G):
+//                 K-major, SWIZZLE_64B, one 3-D box (32 ch, rows nodes, 2 slabs) per 64-wide K block.
 // Canonical layouts (units of 16 B), from the PTX ISA / CuTe UMMA descriptor tables:
 //   K-major  SW128: ((8,m),(T,2)):((8T,SBO),(1,T))      -> SBO = 1024 B, K=16 step = +32 B
 //   MN-major SW128: ((8,n),(8,k)):((1,LBO),(8,SBO))     -> LBO = next 64-wide MN atom, SBO = next 8 k-rows (1024 B)
 //   MN-major SW64 : ((4,n),(8,k)):((1,LBO),(4,SBO))     -> LBO = next slab, SBO = 512 B
+//   K-major  SW64 : ((8,m),(T,2)):((4T,SBO),(1,T))      -> SBO = 512 B, K=16 step = +32 B, next slab = +rows*64 B
 #pragma once
 #include <cuda.h>
 
@@ -23,7 +26,7 @@
 
 namespace gwn {
 
-enum { TG_K_SW128 = 0, TG_MN_SW128 = 1, TG_MN_SW64 = 2 };
+enum { TG_K_SW128 = 0, TG_MN_SW128 = 1, TG_MN_SW64 = 2, TG_K_SW64 = 3 };
 
 constexpr int TG_BM = 128, TG_BK = 64;
 constexpr int TG_EPI_WARPS = 4;
@@ -33,7 +36,7 @@ struct TgOperand {
   int mode;
   uint32_t tile_bytes;   // per stage (multiple of 1024)
   uint32_t lbo, sbo;     // descriptor byte offsets
-  uint32_t kstep;        // start-address advance per MMA (K = 16)
+  uint32_t koff[4];      // start-address offset of each of the 4 MMAs (K = 16) of a K block
   uint32_t layout;       // descriptor swizzle code: 2 = 128B, 4 = 64B
   int n_boxes;           // TMA boxes per stage
   uint32_t box_bytes;
@@ -87,8 +90,10 @@ __device__ __forceinline__ void load_operand(const TgOperand& o, const CUtensorM
     tma_2d(dst, map, k0, mn0, bar);
   } else if (o.mode == TG_MN_SW128) {
     for (int i = 0; i < o.n_boxes; ++i) tma_2d(dst + (uint32_t)i * o.box_bytes, map, mn0 + i * o.box_mn, k0, bar);
-  } else {
+  } else if (o.mode == TG_MN_SW64) {
     tma_3d(dst, map, 0, k0, mn0 >> 5, bar);
+  } else {
+    tma_3d(dst, map, 0, mn0, k0 >> 5, bar);
   }
 }
 }  // namespace tg
@@ -152,7 +157,8 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, p.bn, p.a.mode != TG_K_SW128, p.b.mode != TG_K_SW128);
+      const uint32_t idesc = make_idesc_bf16(128, p.bn, p.a.mode == TG_MN_SW128 || p.a.mode == TG_MN_SW64,
+                                             p.b.mode == TG_MN_SW128 || p.b.mode == TG_MN_SW64);
       int it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
         const int rest = tile / p.m_tiles;
@@ -170,8 +176,8 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           const uint32_t sa = base + (uint32_t)s * stage_bytes, sb = sa + p.a.tile_bytes;
 #pragma unroll
           for (int ks = 0; ks < TG_BK / 16; ++ks) {
-            const uint64_t adesc = make_desc_sw(sa + (uint32_t)ks * p.a.kstep, p.a.lbo, p.a.sbo, p.a.layout);
-            const uint64_t bdesc = make_desc_sw(sb + (uint32_t)ks * p.b.kstep, p.b.lbo, p.b.sbo, p.b.layout);
+            const uint64_t adesc = make_desc_sw(sa + p.a.koff[ks], p.a.lbo, p.a.sbo, p.a.layout);
+            const uint64_t bdesc = make_desc_sw(sb + p.b.koff[ks], p.b.lbo, p.b.sbo, p.b.layout);
             umma_bf16(d, adesc, bdesc, idesc, (kb == kb0 && ks == 0) ? 0u : 1u);
           }
           umma_commit(&empty[s]);
@@ -226,6 +232,10 @@ void tg_operand(TgOperand& o, int mode, int rows);
 int tg_map_2d(CUtensorMap* map, const void* base, uint64_t dim0, uint64_t dim1, uint64_t stride1_bytes, uint32_t box0,
               uint32_t box1);                       // SWIZZLE_128B, bf16
 int tg_map_slabs(CUtensorMap* map, const void* base, uint64_t V, uint64_t slabs, uint32_t box_v, uint32_t box_slabs);
+// bf16 [rows][cols] row-major matrix with `pitch` elements per row, K-major box (64, box_rows)
+inline int tg_map_rows(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_rows) {
+  return tg_map_2d(map, base, cols, rows, pitch * 2, 64, box_rows);
+}
 int tg_sm_count();
 
 template <typename Epi>

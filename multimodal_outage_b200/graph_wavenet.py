@@ -295,8 +295,11 @@ class gwnet(nn.Module):
         # bf16 + supports that fit on chip: diffusion hops run on the tcgen05 tensor cores; the UMMA operand
         # images of (A, A^2, A^T, (A^2)^T) are built once per forward and shared by all layers
         hop_mats = None
-        if dt == torch.bfloat16 and supports and self.use_tensor_cores and ops.hop_tc_supported(V):
-            hop_mats = ops.hop_mats([s.detach().contiguous() for s in supports])
+        if dt == torch.bfloat16 and supports and self.use_tensor_cores:
+            sup_c = [s.detach().contiguous() for s in supports]
+            # V <= 80: every support image stays resident in shared memory; larger graphs (the 3,100-node
+            # configurations): one TMA-tiled tensor-core GEMM per hop
+            hop_mats = ops.hop_mats(sup_c) if ops.hop_tc_supported(V) else ops.support_images(sup_c)
 
         u = ops.StartConv.apply(x, self.start_conv.weight, self.start_conv.bias, L[0], dt == torch.bfloat16)
         stats = None

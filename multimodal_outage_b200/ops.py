@@ -506,6 +506,28 @@ def _(supports):
     return supports[0].new_empty((len(supports) * 4 * (Kp // 8) * 1024,), dtype=torch.bfloat16)
 
 
+@torch.library.custom_op('gwn::support_images', mutates_args=())
+def support_images(supports: List[Tensor]) -> Tensor:
+    """bf16 operand images of every support for the TMA-tiled hop GEMM (graphs too big to keep on chip):
+    [n_supports][2][V][Vp], image 0 = A^T (forward hop), image 1 = A (backward hop)."""
+    for s in supports:
+        _req(s, torch.float32, 'support')
+    V = supports[0].shape[0]
+    nbytes = lib().gwn_support_images_bytes(V, len(supports))
+    out = torch.empty((nbytes // 2,), device=supports[0].device, dtype=torch.bfloat16)
+    ptrs = (C.c_void_p * len(supports))(*[s.data_ptr() for s in supports])
+    with torch.cuda.device(out.device):
+        check(lib().gwn_support_images_prep(ptrs, len(supports), V, _p(out), _stream()), 'gwn_support_images_prep')
+    return out
+
+
+@support_images.register_fake
+def _(supports):
+    V = supports[0].shape[0]
+    Vp = 8 * ((V + 7) // 8)
+    return supports[0].new_empty((len(supports) * 2 * V * Vp,), dtype=torch.bfloat16)
+
+
 @torch.library.custom_op('gwn::hop_tc', mutates_args=('buf',))
 def hop_tc(mats: Tensor, n_mats: int, mat: int, buf: Tensor, slot_in: int, slot_out: int, V: int) -> None:
     """One tensor-core hop inside a pitched bf16 buffer [slabs*V, pitch]: slot_out <- Mop[mat] * slot_in."""

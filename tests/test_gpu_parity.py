@@ -386,7 +386,9 @@ def _layer_op_case(dtype, tol, V=67, N=6, Lin=9, dil=2, taps=2, n_sup=3, with_bn
     sup_k[-1].requires_grad_(True)
     meta = dict(training=True, momentum=0.1, eps=1e-5, Lf=Lf, taps=taps, dilation=dil, order=2, has_gconv=True,
                 dropout_p=0.3 if mask else 0.0, seed=0, offset=0)
-    hop_mats_k = ops.hop_mats([a.detach() for a in sup_k]) if tensor_cores else None
+    hop_mats_k = None
+    if tensor_cores:      # V <= 80: supports resident on chip; larger: TMA-tiled GEMM per hop
+        hop_mats_k = (ops.hop_mats if ops.hop_tc_supported(V) else ops.support_images)([a.detach() for a in sup_k])
     u_k, stats_k, zl_k = ops.WaveNetLayer.apply(k_in[0], stats, gk, bk, rm, rv, wfg_k, bfg_k, wm_k, bm_k,
                                                 cl(dm) if mask else None, None, hop_mats_k, meta, *sup_k)
     assert rel(u_k.permute(0, 3, 2, 1), u_o) < tol and rel(zl_k.permute(0, 3, 2, 1), z_o[..., -Lf:]) < tol
@@ -429,6 +431,85 @@ def test_bf16_layer_op_fwd_bwd_vs_oracle(with_bn, mask, tensor_cores):
                        mask=mask, seed=4, tensor_cores=True)
         _layer_op_case(torch.bfloat16, BF16_TOL, V=40, N=5, Lin=4, dil=1, taps=2, n_sup=1, with_bn=with_bn,
                        mask=mask, seed=5, tensor_cores=True)
+
+
+@pytest.mark.parametrize('with_bn,mask', [(True, False), (False, True)])
+def test_bf16_layer_op_big_graph_tma_gemm_hops(with_bn, mask):
+    """Graphs whose supports do not fit on chip (the 3,100-node configs' code path, at sizes the fp64
+    oracle finishes quickly): hops, their backward and dA on the TMA-tiled tcgen05 GEMM; ragged node tiles
+    (V % 128 != 0, V % 64 != 0, V % 8 != 0) and odd slab counts."""
+    errs = _layer_op_case(torch.bfloat16, BF16_TOL, V=150, N=3, Lin=5, dil=1, taps=2, n_sup=3, with_bn=with_bn,
+                          mask=mask, seed=6, tensor_cores=True)
+    print('bf16 big-graph layer-op errors V=150:', {k: f'{v:.1e}' for k, v in errs.items()})
+    errs = _layer_op_case(torch.bfloat16, BF16_TOL, V=333, N=1, Lin=4, dil=1, taps=2, n_sup=2, with_bn=with_bn,
+                          mask=mask, seed=7, tensor_cores=True)
+    print('bf16 big-graph layer-op errors V=333:', {k: f'{v:.1e}' for k, v in errs.items()})
+
+
+def test_tma_gemm_every_staging_mode():
+    """gwn_gemm_test: C = A.B^T through K-major/MN-major 128B-swizzled and slab (64B-swizzled) operands,
+    ragged M/N/K, split-K with atomic accumulation."""
+    from multimodal_outage_b200 import _lib
+    lib = _lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator(device='cuda').manual_seed(3)
+    pad8 = lambda n: (n + 7) // 8 * 8    # noqa: E731
+    for (M, N, K, bn, splits) in ((128, 256, 64, 256, 1), (300, 320, 200, 64, 1), (257, 512, 1000, 256, 3)):
+        A = torch.randn(M, K, device='cuda', generator=g).to(torch.bfloat16)
+        B = torch.randn(N, K, device='cuda', generator=g).to(torch.bfloat16)
+        ref = A.float() @ B.float().t()
+        for am in (0, 1):
+            for bm in (0, 1, 2):
+                if am == 0:
+                    lda = pad8(K); Ag = torch.zeros(M, lda, device='cuda', dtype=torch.bfloat16); Ag[:, :K] = A
+                else:
+                    lda = pad8(M); Ag = torch.zeros(K, lda, device='cuda', dtype=torch.bfloat16); Ag[:, :M] = A.t()
+                if bm == 0:
+                    ldb = pad8(K); Bg = torch.zeros(N, ldb, device='cuda', dtype=torch.bfloat16); Bg[:, :K] = B
+                elif bm == 1:
+                    ldb = pad8(N); Bg = torch.zeros(K, ldb, device='cuda', dtype=torch.bfloat16); Bg[:, :N] = B.t()
+                else:
+                    ldb = 32; Bg = B.reshape(N // 32, 32, K).permute(0, 2, 1).contiguous()
+                Cc = torch.zeros(M, N, device='cuda')
+                _lib.check(lib.gwn_gemm_test(Ag.data_ptr(), Bg.data_ptr(), Cc.data_ptr(), M, N, K, am, bm, lda, ldb, bn,
+                                             splits, st), 'gwn_gemm_test')
+                assert rel(Cc, ref) < 1e-5, (M, N, K, am, bm, rel(Cc, ref))
+
+
+def test_big_graph_hop_and_support_gradient_kernels():
+    """gwn_hop_big (both operand images, with and without add-in) and gwn_dadj_big against fp64 einsums."""
+    import ctypes as C
+    from multimodal_outage_b200 import ops, _lib
+    lib = _lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    torch.manual_seed(1)
+    for V, slabs in ((150, 5), (333, 16), (1000, 9)):
+        sups = [torch.softmax(torch.randn(V, V, device='cuda'), dim=1) for _ in range(2)]
+        img = ops.support_images(sups)
+        x = torch.randn(slabs, V, 32, device='cuda').to(torch.bfloat16)
+        add = torch.randn(slabs, V, 32, device='cuda').to(torch.bfloat16)
+        y = torch.empty_like(x)
+        for s in range(2):
+            Ab = sups[s].to(torch.bfloat16).double()
+            for which in range(2):
+                ref = torch.einsum('vw,svc->swc' if which == 0 else 'wv,svc->swc', Ab, x.double())
+                _lib.check(lib.gwn_hop_big(img.data_ptr(), 2, s, which, x.data_ptr(), y.data_ptr(), None, slabs, V, st), 'hop')
+                assert rel(y, ref) < 4e-3, (V, slabs, s, which, rel(y, ref))
+                _lib.check(lib.gwn_hop_big(img.data_ptr(), 2, s, which, x.data_ptr(), y.data_ptr(), add.data_ptr(), slabs,
+                                           V, st), 'hop')
+                assert rel(y, ref + add.double()) < 4e-3
+        dA = torch.ones(V, V, device='cuda')
+        _lib.check(lib.gwn_dadj_big(x.data_ptr(), add.data_ptr(), dA.data_ptr(), slabs, V, st), 'dadj')
+        ref = 1.0 + torch.einsum('svc,swc->vw', x.double(), add.double())
+        assert rel(dA, ref) < 1e-5, (V, slabs, rel(dA, ref))
+
+
+def test_bf16_whole_model_big_graph_310_nodes():
+    """Whole gwnet in bf16 on a 310-node kNN graph: the TMA-GEMM hop path end to end (fwd + bwd)."""
+    cfg = GWNetConfig(num_nodes=310, in_dim=2, out_dim=12, kernel_size=2, blocks=2, layers=2,
+                      skip_channels=64, end_channels=128, dropout=0.0)
+    sup = double_transition(synthetic_knn_graph(310))
+    _oracle_case(cfg, sup, n=2, t_in=12, seed=16, dtype=torch.bfloat16, tol=BF16_TOL)
 
 
 def test_tc_hop_kernel_every_image_variant():
