@@ -31,16 +31,54 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(name='config2: gwnet V=67 fwd/bwd+adaptive supports, k=2, 4x2 layers, in_dim=2, T=12, out=12',
-                V=67, in_dim=2, out_dim=12, T=12, kernel_size=2, blocks=4, layers=2, batch_per_gpu=512,
-                dropout=0.3)
+CONFIGS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on at N=1 (default)
+    'c2': dict(name='config2: gwnet V=67 fwd/bwd+adaptive supports, k=2, 4x2 layers, in_dim=2, T=12, out=12',
+               V=67, in_dim=2, out_dim=12, T=12, kernel_size=2, blocks=4, layers=2, batch_per_gpu=512,
+               dropout=0.3, cpu_sample_batch=64),
+    # configs[2]: 3,100-node graph, K=2 diffusion, 8 layers, batch 64 per GPU (weak scaling)
+    'c3': dict(name='config3: gwnet V=3100 synthetic kNN county graph, fwd/bwd+adaptive supports, k=2, 4x2 layers, '
+                    'in_dim=2, T=12, out=12', V=3100, in_dim=2, out_dim=12, T=12, kernel_size=2, blocks=4, layers=2,
+               batch_per_gpu=64, dropout=0.3, cpu_sample_batch=2),
+    # configs[3]: 67 nodes, in_dim = 256 UNet features + 64 date2vec, batch 256
+    'c4': dict(name='config4: gwnet V=67, in_dim=320 (UNet features + date2vec), k=2, 4x2 layers, T=12, out=12',
+               V=67, in_dim=320, out_dim=12, T=12, kernel_size=2, blocks=4, layers=2, batch_per_gpu=256,
+               dropout=0.3, cpu_sample_batch=32),
+    # configs[4]: long horizon, 3,100 nodes, T=48, 4x4 layers (dilations 1,2,4,8), batch 32 per GPU
+    'c5': dict(name='config5: gwnet V=3100, T=48, 4x4 layers (dilation <= 8, rf 61), k=2, in_dim=2, out=12',
+               V=3100, in_dim=2, out_dim=12, T=48, kernel_size=2, blocks=4, layers=4, batch_per_gpu=32,
+               dropout=0.3, cpu_sample_batch=1),
+}
+WORKLOAD = dict(CONFIGS['c2'])
 CPU_SAMPLE_BATCH = 64
+
+
+def select_config(key):
+    global CPU_SAMPLE_BATCH
+    WORKLOAD.clear(); WORKLOAD.update(CONFIGS[key])
+    CPU_SAMPLE_BATCH = WORKLOAD['cpu_sample_batch']
+
+
+def synthetic_knn_graph(n, k=6, seed=42):
+    """Seeded county-like graph: n uniform points, symmetrised k-nearest-neighbour, 0/1."""
+    rng = np.random.default_rng(seed)
+    pts = rng.random((n, 2))
+    adj = np.zeros((n, n), dtype=np.int64)
+    for s0 in range(0, n, 512):
+        d = ((pts[s0:s0 + 512, None, :] - pts[None, :, :]) ** 2).sum(-1)
+        d[np.arange(d.shape[0]), np.arange(s0, s0 + d.shape[0])] = np.inf
+        nn = np.argpartition(d, k, axis=1)[:, :k]
+        adj[np.repeat(np.arange(s0, s0 + d.shape[0]), k), nn.reshape(-1)] = 1
+    return np.maximum(adj, adj.T)
 
 
 # ------------------------------------------------------------------------------------------ shared setup
 def fl_supports():
-    adj = np.load(os.path.join(ROOT, 'tests', 'golden', 'adj_mx_fl.npy')).astype(np.float32)
     from multimodal_outage_b200.supports import double_transition
+    if WORKLOAD['V'] == 67:
+        adj = np.load(os.path.join(ROOT, 'tests', 'golden', 'adj_mx_fl.npy')).astype(np.float32)
+    else:
+        adj = synthetic_knn_graph(WORKLOAD['V']).astype(np.float32)
     return double_transition(adj)
 
 
@@ -252,7 +290,7 @@ def run_ours(args):
     assert model.layer_lengths(w['T']) == layer_lengths()
     model.compute_dtype = torch.bfloat16
     model.train()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True, fused=True)
     loss_fn = torch.nn.MSELoss()
     sync = BucketedGradAllReduce(model) if world > 1 else None
 
@@ -348,7 +386,7 @@ def run_ours(args):
         pth = os.path.join(ROOT, 'MEASURED_PEAKS.json')
         if os.path.exists(pth):
             peaks = json.load(open(pth))
-        roof, gate_roof = kernel_rooflines(peaks, n)
+        roof, gate_roof = (None, None) if args.no_roofline else kernel_rooflines(peaks, n)
         cpu = None
         if world == 1 and not args.no_cpu:
             sps_cpu, sec_cpu = cpu_reference_steps(3, 1, CPU_SAMPLE_BATCH)
@@ -389,7 +427,10 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))
+    ap.add_argument('--no-roofline', action='store_true')
     args = ap.parse_args()
+    select_config(args.config)
     if args.impl == 'reference':
         run_reference(args)
     else:

@@ -177,6 +177,34 @@ typedef struct {
 } gwn_head_bwd_args;
 int gwn_head_bwd(const gwn_head_cfg* cfg, const gwn_head_bwd_args* a, void* stream);
 
+/* bf16 head on tensor cores (TMA-fed tcgen05 GEMMs, csrc/head_tc.cu).  zcat = the per-layer z_last slices
+ * concatenated along channels: [P, 32*n_layers] bf16, P = N*Lf*V.  s1/e1 are saved in bf16.
+ * ws_w: gwn_head_tc_ws_bytes() bytes of scratch for the bf16 weight images. */
+typedef struct {
+  const void* zcat;
+  const float* w_skip; const float* b_skip; const float* w_end1; const float* b_end1;
+  const float* w_end2; const float* b_end2;      /* packed as in gwn_head_fwd_args */
+  void* s1;               /* out/saved [P,2S] bf16: [hi | lo] split of relu(skip) */
+  void* e1;               /* out/saved [P,E] bf16 */
+  float* out;             /* out [N,O,V,Lf] fp32 NCHW */
+  void* ws_w;
+} gwn_head_tc_fwd_args;
+typedef struct {
+  const void* zcat;
+  const float* w_skip; const float* w_end1; const float* w_end2;
+  const void* s1; const void* e1;
+  const float* dout;      /* [N,O,V,Lf] fp32 NCHW */
+  float* dw_skip; float* db_skip; float* dw_end1; float* db_end1; float* dw_end2; float* db_end2;  /* overwritten */
+  void* dz_last[GWN_MAX_LAYERS];       /* out, each [P,32] bf16 */
+  void* ws_do;            /* [P,Opad] bf16 */
+  void* ws_de1;           /* [P,E] bf16 */
+  void* ws_ds1;           /* [P,S] bf16 */
+  void* ws_w;
+} gwn_head_tc_bwd_args;
+long long gwn_head_tc_ws_bytes(int n_layers, int S, int E, int O);
+int gwn_head_fwd_tc(const gwn_head_cfg* cfg, const gwn_head_tc_fwd_args* a, void* stream);
+int gwn_head_bwd_tc(const gwn_head_cfg* cfg, const gwn_head_tc_bwd_args* a, void* stream);
+
 /* ---- tensor-core (tcgen05) diffusion hops for on-chip-resident supports (V <= 128), bf16 ----
  * gwn_hop_mats_prep builds, once per forward, the UMMA A-operand images of every support:
  * image 4*s+0 = A_s^T, 4*s+1 = (A_s^2)^T (forward hops), 4*s+2 = A_s, 4*s+3 = A_s^2 (backward hops),

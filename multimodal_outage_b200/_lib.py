@@ -56,6 +56,17 @@ class HeadBwdArgs(C.Structure):
                 ('ws_ds1', vp)]
 
 
+class HeadTcFwdArgs(C.Structure):
+    _fields_ = [(n, vp) for n in ('zcat', 'w_skip', 'b_skip', 'w_end1', 'b_end1', 'w_end2', 'b_end2', 's1', 'e1',
+                                  'out', 'ws_w')]
+
+
+class HeadTcBwdArgs(C.Structure):
+    _fields_ = [(n, vp) for n in ('zcat', 'w_skip', 'w_end1', 'w_end2', 's1', 'e1', 'dout', 'dw_skip', 'db_skip',
+                                  'dw_end1', 'db_end1', 'dw_end2', 'db_end2')] + \
+               [('dz_last', vp * MAX_LAYERS)] + [(n, vp) for n in ('ws_do', 'ws_de1', 'ws_ds1', 'ws_w')]
+
+
 # every symbol include/gwn.h declares: name -> (restype, argtypes)
 _i, _ll, _f, _d = C.c_int, C.c_longlong, C.c_float, C.c_double
 SIGNATURES = {
@@ -73,6 +84,9 @@ SIGNATURES = {
     'gwn_bn_bwd': (_i, [vp, vp, _i, vp, _d, vp, vp, vp, _i, vp, vp, vp, _ll, vp]),
     'gwn_head_fwd': (_i, [C.POINTER(HeadCfg), C.POINTER(HeadFwdArgs), vp]),
     'gwn_head_bwd': (_i, [C.POINTER(HeadCfg), C.POINTER(HeadBwdArgs), vp]),
+    'gwn_head_tc_ws_bytes': (_ll, [_i, _i, _i, _i]),
+    'gwn_head_fwd_tc': (_i, [C.POINTER(HeadCfg), C.POINTER(HeadTcFwdArgs), vp]),
+    'gwn_head_bwd_tc': (_i, [C.POINTER(HeadCfg), C.POINTER(HeadTcBwdArgs), vp]),
     'gwn_hop_mats_bytes': (_i, [_i, _i]),
     'gwn_hop_mats_prep': (_i, [vp, _i, _i, vp, vp]),
     'gwn_hop_tc': (_i, [vp, _i, _i, vp, _i, _i, _i, _i, _i, vp]),

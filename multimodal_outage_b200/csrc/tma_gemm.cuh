@@ -50,6 +50,7 @@ struct TgParams {
   int splits;            // split-K factor (epilogue must accumulate atomically when > 1)
   int kb_per_split;
   int stages;
+  int a_kwrap;           // > 0: operand A is addressed at k mod a_kwrap (split-precision GEMMs reuse A segments)
   TgOperand a, b;
 };
 
@@ -149,7 +150,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           mbar_wait(&empty[s], (uint32_t)(ph ^ 1));
           mbar_expect_tx(&full[s], stage_bytes);
           const uint32_t sa = base + (uint32_t)s * stage_bytes, sb = sa + p.a.tile_bytes;
-          load_operand(p.a, &mapA, sa, mt * TG_BM, kb * TG_BK, &full[s]);
+          load_operand(p.a, &mapA, sa, mt * TG_BM, p.a_kwrap > 0 ? (kb * TG_BK) % p.a_kwrap : kb * TG_BK, &full[s]);
           load_operand(p.b, &mapB, sb, nt * p.bn, kb * TG_BK, &full[s]);
         }
       }

@@ -17,8 +17,8 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import (GWN_BF16, GWN_F32, HeadBwdArgs, HeadCfg, HeadFwdArgs, LayerBwdArgs, LayerCfg, LayerFwdArgs,
-                   check, lib)
+from ._lib import (GWN_BF16, GWN_F32, HeadBwdArgs, HeadCfg, HeadFwdArgs, HeadTcBwdArgs, HeadTcFwdArgs, LayerBwdArgs,
+                   LayerCfg, LayerFwdArgs, check, lib)
 
 CH = 32
 
@@ -444,11 +444,90 @@ def _(z_last, w_skip, w_end1, w_end2, s1, e1, dout):
         [f(z) for z in z_last]
 
 
+@torch.library.custom_op('gwn::head_fwd_tc', mutates_args=())
+def head_fwd_tc(zcat: Tensor, w_skip: Tensor, b_skip: Tensor, w_end1: Tensor, b_end1: Tensor, w_end2: Tensor,
+                b_end2: Tensor, out_dim: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """bf16 head on the tensor cores (csrc/head_tc.cu).  zcat: [N,Lf,V,32*n_layers] bf16."""
+    _req(zcat, torch.bfloat16, 'zcat')
+    N, Lf, V, K0 = zcat.shape
+    S, E = w_skip.shape[1], w_end1.shape[1]
+    P = N * Lf * V
+    dev = zcat.device
+    s1 = torch.empty((P, 2 * S), device=dev, dtype=torch.bfloat16)      # [hi | lo] split (csrc/head_tc.cu)
+    e1 = torch.empty((P, E), device=dev, dtype=torch.bfloat16)
+    out = torch.empty((N, out_dim, V, Lf), device=dev, dtype=torch.float32)
+    ws_w = torch.empty((lib().gwn_head_tc_ws_bytes(K0 // CH, S, E, out_dim),), device=dev, dtype=torch.uint8)
+    cfg = HeadCfg(N=N, V=V, Lf=Lf, n_layers=K0 // CH, S=S, E=E, O=out_dim, dtype=GWN_BF16)
+    args = HeadTcFwdArgs(zcat=_p(zcat), w_skip=_p(w_skip), b_skip=_p(b_skip), w_end1=_p(w_end1), b_end1=_p(b_end1),
+                         w_end2=_p(w_end2), b_end2=_p(b_end2), s1=_p(s1), e1=_p(e1), out=_p(out), ws_w=_p(ws_w))
+    with torch.cuda.device(dev):
+        check(lib().gwn_head_fwd_tc(C.byref(cfg), C.byref(args), _stream()), 'gwn_head_fwd_tc')
+    return out, s1, e1
+
+
+@head_fwd_tc.register_fake
+def _(zcat, w_skip, b_skip, w_end1, b_end1, w_end2, b_end2, out_dim):
+    N, Lf, V, _k = zcat.shape
+    P = N * Lf * V
+    return (zcat.new_empty((N, out_dim, V, Lf), dtype=torch.float32), zcat.new_empty((P, 2 * w_skip.shape[1])),
+            zcat.new_empty((P, w_end1.shape[1])))
+
+
+@torch.library.custom_op('gwn::head_bwd_tc', mutates_args=())
+def head_bwd_tc(zcat: Tensor, w_skip: Tensor, w_end1: Tensor, w_end2: Tensor, s1: Tensor, e1: Tensor,
+                dout: Tensor) -> List[Tensor]:
+    """Returns [dw_skip, db_skip, dw_end1, db_end1, dw_end2, db_end2, dz_last_0, ...] (dz_last_i: [N,Lf,V,32] bf16)."""
+    N, Lf, V, K0 = zcat.shape
+    nl = K0 // CH
+    S, E, Opad = w_skip.shape[1], w_end1.shape[1], w_end2.shape[1]
+    O = dout.shape[1]
+    P = N * Lf * V
+    dev = zcat.device
+    f32 = dict(device=dev, dtype=torch.float32)
+    b16 = dict(device=dev, dtype=torch.bfloat16)
+    dw_skip, db_skip = torch.empty_like(w_skip), torch.empty((S,), **f32)
+    dw_end1, db_end1 = torch.empty_like(w_end1), torch.empty((E,), **f32)
+    dw_end2, db_end2 = torch.empty_like(w_end2), torch.empty((Opad,), **f32)
+    dz = [torch.empty((N, Lf, V, CH), **b16) for _ in range(nl)]
+    ws_do, ws_de1, ws_ds1 = torch.empty((P, Opad), **b16), torch.empty((P, E), **b16), torch.empty((P, S), **b16)
+    ws_w = torch.empty((lib().gwn_head_tc_ws_bytes(nl, S, E, O),), device=dev, dtype=torch.uint8)
+    cfg = HeadCfg(N=N, V=V, Lf=Lf, n_layers=nl, S=S, E=E, O=O, dtype=GWN_BF16)
+    args = HeadTcBwdArgs(zcat=_p(zcat), w_skip=_p(w_skip), w_end1=_p(w_end1), w_end2=_p(w_end2), s1=_p(s1), e1=_p(e1),
+                         dout=_p(dout), dw_skip=_p(dw_skip), db_skip=_p(db_skip), dw_end1=_p(dw_end1),
+                         db_end1=_p(db_end1), dw_end2=_p(dw_end2), db_end2=_p(db_end2), dz_last=_ptr_array(dz),
+                         ws_do=_p(ws_do), ws_de1=_p(ws_de1), ws_ds1=_p(ws_ds1), ws_w=_p(ws_w))
+    with torch.cuda.device(dev):
+        check(lib().gwn_head_bwd_tc(C.byref(cfg), C.byref(args), _stream()), 'gwn_head_bwd_tc')
+    return [dw_skip, db_skip, dw_end1, db_end1, dw_end2, db_end2] + dz
+
+
+@head_bwd_tc.register_fake
+def _(zcat, w_skip, w_end1, w_end2, s1, e1, dout):
+    N, Lf, V, K0 = zcat.shape
+    f = lambda t: torch.empty_like(t)  # noqa: E731
+    v = lambda n: zcat.new_empty((n,), dtype=torch.float32)  # noqa: E731
+    return [f(w_skip), v(w_skip.shape[1]), f(w_end1), v(w_end1.shape[1]), f(w_end2), v(w_end2.shape[1])] + \
+        [zcat.new_empty((N, Lf, V, CH)) for _ in range(K0 // CH)]
+
+
+def head_tc_supported(P: int, S: int, E: int) -> bool:
+    """TMA-fed tensor-core head: needs channel counts TMA can box (multiples of 64 keep every box full)."""
+    return S % 64 == 0 and E % 64 == 0 and P < 2 ** 31
+
+
 class SkipHead(torch.autograd.Function):
     """relu(sum_i Ws_i z_i[..., -Lf:] + sum_i bs_i) -> relu(end_conv_1) -> end_conv_2, NCHW out."""
 
     @staticmethod
     def forward(ctx, w_skip, b_skip, w_end1, b_end1, w_end2, b_end2, out_dim, *z_last):
+        z0 = z_last[0]
+        ctx.tc = (z0.dtype == torch.bfloat16 and
+                  head_tc_supported(z0.numel() // CH, w_skip.shape[1], w_end1.shape[1]))
+        if ctx.tc:
+            zcat = torch.cat(z_last, dim=-1)
+            out, s1, e1 = head_fwd_tc(zcat, w_skip, b_skip, w_end1, b_end1, w_end2, b_end2, out_dim)
+            ctx.save_for_backward(w_skip, w_end1, w_end2, s1, e1, zcat)
+            return out
         zs = [z.contiguous() for z in z_last]
         out, s1, e1 = head_fwd(zs, w_skip, b_skip, w_end1, b_end1, w_end2, b_end2, out_dim)
         ctx.save_for_backward(w_skip, w_end1, w_end2, s1, e1, *zs)
@@ -457,7 +536,10 @@ class SkipHead(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         w_skip, w_end1, w_end2, s1, e1, *zs = ctx.saved_tensors
-        outs = head_bwd(list(zs), w_skip, w_end1, w_end2, s1, e1, dout.contiguous().float())
+        if ctx.tc:
+            outs = head_bwd_tc(zs[0], w_skip, w_end1, w_end2, s1, e1, dout.contiguous().float())
+        else:
+            outs = head_bwd(list(zs), w_skip, w_end1, w_end2, s1, e1, dout.contiguous().float())
         return (*outs[:6], None, *outs[6:])
 
 

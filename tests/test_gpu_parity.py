@@ -568,3 +568,47 @@ def test_skip_head_op_fwd_bwd_vs_oracle(dtype):
     assert rel(b_skip.grad, bs[0].grad) < FP32_TOL
     assert rel(w_end1.grad.t(), W1.grad[:, :, 0, 0]) < FP32_TOL and rel(b_end1.grad, b1.grad) < FP32_TOL
     assert rel(w_end2.grad[:, :O].t(), W2.grad[:, :, 0, 0]) < FP32_TOL and rel(b_end2.grad[:O], b2.grad) < FP32_TOL
+
+
+@pytest.mark.parametrize('nl,S,E,Lf', [(3, 128, 256, 2), (8, 256, 512, 1)])
+def test_bf16_head_on_tensor_cores_fwd_bwd_vs_oracle(nl, S, E, Lf):
+    """bf16 head as TMA-fed tcgen05 GEMMs (csrc/head_tc.cu): bf16 operands, fp32 accumulation; every output and
+    gradient within the bf16 bar of the fp64 oracle, with arbitrary fp32 weights (the GEMMs that feed a ReLU run
+    in split hi/lo bf16 precision so relu masks do not flip)."""
+    from multimodal_outage_b200 import ops
+    from oracle.gwnet_oracle import pointwise
+    g = torch.Generator().manual_seed(9)
+    rn = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64)   # noqa: E731
+    r16 = lambda t: t.to(torch.bfloat16).double()                       # noqa: E731
+    N, V, O = 7, 67, 12
+    zs = [r16(torch.tanh(rn(N, 32, V, Lf))).requires_grad_(True) for _ in range(nl)]
+    f32r = lambda t: t.float().double()                                 # noqa: E731  (parameters are fp32)
+    Ws = [f32r(rn(S, 32, 1, 1) / 6).requires_grad_(True) for _ in range(nl)]
+    bs = [(0.1 * rn(S)).requires_grad_(True) for _ in range(nl)]
+    W1, b1 = f32r(rn(E, S, 1, 1) / S ** 0.5).requires_grad_(True), (0.1 * rn(E)).requires_grad_(True)
+    W2, b2 = f32r(rn(O, E, 1, 1) / E ** 0.5).requires_grad_(True), (0.1 * rn(O)).requires_grad_(True)
+    skip = sum(pointwise(z, w, b) for z, w, b in zip(zs, Ws, bs))
+    out_o = pointwise(torch.relu(pointwise(torch.relu(skip), W1, b1)), W2, b2)
+    dout = rn(N, O, V, Lf)
+    out_o.backward(dout)
+    f32 = lambda t: t.detach().float().cuda()   # noqa: E731
+    w_skip = f32(torch.cat([w[:, :, 0, 0].t() for w in Ws], 0)).contiguous().requires_grad_(True)
+    b_skip = f32(sum(bs)).requires_grad_(True)
+    w_end1, b_end1 = f32(W1[:, :, 0, 0].t()).contiguous().requires_grad_(True), f32(b1).requires_grad_(True)
+    w2p = torch.zeros(E, 32); w2p[:, :O] = W2.detach()[:, :, 0, 0].t().float()
+    b2p = torch.zeros(32); b2p[:O] = b2.detach().float()
+    w_end2, b_end2 = w2p.cuda().requires_grad_(True), b2p.cuda().requires_grad_(True)
+    zk = [z.detach().permute(0, 3, 2, 1).contiguous().to(torch.bfloat16).cuda().requires_grad_(True) for z in zs]
+    assert ops.head_tc_supported(N * V * Lf, S, E)
+    out_k = ops.SkipHead.apply(w_skip, b_skip, w_end1, b_end1, w_end2, b_end2, O, *zk)
+    errs = {'out': rel(out_k, out_o)}
+    out_k.backward(dout.float().cuda())
+    for i in range(nl):
+        errs[f'dz{i}'] = rel(zk[i].grad.permute(0, 3, 2, 1), zs[i].grad)
+        errs[f'dWs{i}'] = rel(w_skip.grad[32 * i:32 * i + 32].t(), Ws[i].grad[:, :, 0, 0])
+    errs['dbs'] = rel(b_skip.grad, bs[0].grad)
+    errs['dW1'] = rel(w_end1.grad.t(), W1.grad[:, :, 0, 0]); errs['db1'] = rel(b_end1.grad, b1.grad)
+    errs['dW2'] = rel(w_end2.grad[:, :O].t(), W2.grad[:, :, 0, 0]); errs['db2'] = rel(b_end2.grad[:O], b2.grad)
+    print('bf16 tensor-core head errors:', {k: f'{v:.1e}' for k, v in errs.items()})
+    bad = {k: v for k, v in errs.items() if not v < BF16_TOL}
+    assert not bad, bad
