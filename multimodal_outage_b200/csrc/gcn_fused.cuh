@@ -1,0 +1,50 @@
+// Fused diffusion graph convolution for graphs whose supports fit on chip (V <= 80), bf16, forward:
+//
+//   u = dropout( mlp( concat[z, z A_0, z A_0^2, ..., z A_adp^2] ) + b ) + bn_prev(u_prev)[crop]     (+ BN statistics)
+//   graph_wavenet.py:76-98 (gcn: nconv hops :87-93, concat :95, 1x1 mlp :96, dropout :97), :247 (residual), :250 (BN)
+//
+// in ONE kernel: the K-hop diffusion, the support concatenation and the mlp are one chained contraction on the
+// tcgen05 tensor cores, with every support image and the mlp weights resident in shared memory, the
+// intermediate in TMEM / shared memory, and nothing but z (read once) and u (written once) touching HBM.
+//
+// The 1x1 mlp commutes with node mixing (exact in fp64), so the contraction is evaluated in
+// Horner form per slab (one (n,t) pair = V nodes x 32 channels):
+//     U      = z W            [V,32] x [32, 32(1+H)]         GEMM 1 (M = node, K = channel), D in TMEM
+//     h      = U_0 + b + sum_j M_j U_j                       GEMM 2 (M = node w, K = node v), H = 2*supports
+// GEMM 1's accumulator is drained by "stage" warps that convert U_1..U_H to bf16 into the MN-major B-operand
+// layout of GEMM 2 in shared memory and plant U_0 + b directly into GEMM 2's TMEM accumulator (tcgen05.st),
+// so GEMM 2 only accumulates.  GEMM 2's accumulator is drained by the epilogue warps: Philox dropout, residual
+// with the folded BatchNorm affine of the previous layer, bf16 store of u, per-channel (sum, sum^2).
+#pragma once
+#include "common.cuh"
+
+namespace gwn {
+
+constexpr int GF_MAX_MATS = 6;
+
+struct GcnFwdParams {
+  const bf16* z;               // [slabs*V, 32]
+  const bf16* u_prev;          // [N, Lin, V, 32] (residual source)
+  long long RI, RO, crop;      // rows per sample of u_prev / of the output, first residual row
+  const float* scale;          // folded BN of the previous layer (NULL = identity)
+  const float* shift;
+  const bf16* mats;            // gwn_hop_mats_prep images
+  int mat_src[GF_MAX_MATS];    // image index of hop j+1
+  int n_mats;
+  const bf16* w_img;           // [4][32*(1+n_mats)][8] bf16: (k = c, n = (j, c')) = W_mlp[j*32 + c][c']
+  const float* bias;           // [32]
+  const bf16* mask;            // optional explicit dropout mask [slabs*V, 32]
+  float drop_p;
+  uint64_t seed, offset;
+  const uint64_t* rng;
+  bf16* u;                     // out [slabs*V, 32]
+  double* stats;               // [2][32], accumulated with atomics (caller zeroes)
+  int V, Kp, slabs;
+};
+
+int gcn_fused_supported(int V, int n_mats);
+// builds w_img from the packed fp32 mlp weight [32*(1+n_mats), 32]
+int launch_gcn_wprep(const float* w_mlp, int n_mats, bf16* w_img, cudaStream_t st);
+int launch_gcn_fwd(GcnFwdParams& p, cudaStream_t st);
+
+}  // namespace gwn

@@ -8,6 +8,8 @@
 #include "gemm.cuh"
 #include "tc_hops.cuh"
 #include "tma_hops.cuh"
+#include "gcn_fused.cuh"
+#include <cstdlib>
 #include "tc_wgrad.cuh"
 #include "tc_gemm_impl.cuh"
 
@@ -567,6 +569,12 @@ static const bf16* big_image(const gwn_layer_cfg* c, const void* hop_mats, int s
   return reinterpret_cast<const bf16*>(hop_mats) + ((long long)s * 2 + which) * c->V * Vp;
 }
 
+static bool fused_gcn_enabled() {   // GWN_NO_FUSED_GCN=1 keeps the unfused kernels (A/B measurements only)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GWN_NO_FUSED_GCN"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
+
 // The concat buffers are SLOT-MAJOR: slot q (32 channels of hop q) is a contiguous [P, 32] tensor at
 // buf + q*P*32, so a tile of a slot is one contiguous run of 64-byte rows (full 128-byte DRAM lines).
 static void hop_params_base(HopParams& p, const gwn_layer_cfg* c, bf16* buf, const void* hop_mats) {
@@ -671,9 +679,27 @@ static int layer_fwd_t(const gwn_layer_cfg* c, const gwn_layer_fwd_args* g, cuda
   if (int rc = launch_pos_gemm<T, 64>(A, g->w_fg, 64, eg, st)) return rc;
   }
   if (!c->has_gconv) return 0;
+  GWN_CUDA(cudaMemsetAsync(g->stats, 0, sizeof(double) * 64, st));
+  if constexpr (std::is_same<T, bf16>::value) {
+    // supports on chip: hops + concat + mlp + dropout + residual + statistics as ONE kernel (gcn_fused.cu)
+    if (tc && fused_gcn_enabled() && tc_mode<T>(c, g->hop_mats) == 1 && c->order == 2 && c->n_supports >= 1 &&
+        gcn_fused_supported(c->V, 2 * c->n_supports)) {
+      bf16* wimg = reinterpret_cast<bf16*>(wsw + 64 * 1024);
+      if (int rc = launch_gcn_wprep(g->w_mlp, 2 * c->n_supports, wimg, st)) return rc;
+      GcnFwdParams fp{};
+      fp.z = cat; fp.u_prev = reinterpret_cast<const bf16*>(g->u_prev); fp.RI = RI; fp.RO = RO;
+      fp.crop = (long long)(c->Lin - c->Lout) * c->V; fp.scale = g->scale; fp.shift = g->shift;
+      fp.mats = reinterpret_cast<const bf16*>(g->hop_mats); fp.n_mats = 2 * c->n_supports;
+      for (int j = 0; j < fp.n_mats; ++j) fp.mat_src[j] = 4 * (j / 2) + (j % 2);      // A_s^T, (A_s^2)^T
+      fp.w_img = wimg; fp.bias = g->b_mlp;
+      fp.mask = c->training ? reinterpret_cast<const bf16*>(g->drop_mask) : nullptr;
+      fp.drop_p = c->training ? c->dropout_p : 0.f; fp.seed = c->seed; fp.offset = c->offset; fp.rng = g->rng;
+      fp.u = reinterpret_cast<bf16*>(g->u); fp.stats = g->stats; fp.V = c->V; fp.slabs = c->N * c->Lout;
+      return launch_gcn_fwd(fp, st);
+    }
+  }
   // diffusion hops into the concat slots, then mlp + dropout + residual + stats
   if (int rc = hops_forward<T>(c, cat, g->supports, g->hop_mats, st)) return rc;
-  GWN_CUDA(cudaMemsetAsync(g->stats, 0, sizeof(double) * 64, st));
   GemmA M{};
   M.n_chunks = nslots; M.rows_per_n_out = RO; M.P = P;
   for (int q = 0; q < nslots; ++q) {
