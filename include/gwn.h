@@ -131,6 +131,15 @@ typedef struct {
 
 int gwn_layer_bwd(const gwn_layer_cfg* cfg, const gwn_layer_bwd_args* args, void* stream);
 
+/* The fused diffusion graph convolution of gwn_layer_fwd alone (bf16, supports resident on chip; csrc/gcn_fused.cu):
+ *   u = dropout(mlp(concat[z, z A_s, z A_s^2 ...]) + b) + (u_prev*scale + shift)[crop],  stats = (sum u, sum u^2).
+ * z [N,Lout,V,32], u_prev [N,Lin,V,32], u [N,Lout,V,32] bf16; hop_mats from gwn_hop_mats_prep; w_mlp packed
+ * [32*(1+2*n_supports), 32]; ws_w >= 16 KiB scratch.  graph_wavenet.py:76-98, :247, :250. */
+int gwn_gcn_fwd(const void* z, const void* u_prev, const float* scale, const float* shift,
+                const void* hop_mats, int n_supports, const float* w_mlp, const float* b_mlp, void* ws_w,
+                float drop_p, unsigned long long seed, unsigned long long offset, void* u, double* stats,
+                int N, int V, int Lin, int Lout, void* stream);
+
 /* ---- BatchNorm2d(32) folded to an affine  graph_wavenet.py:167,250 ----
  * training: mean/var from stats (count = N*L*V), scale = gamma*rstd, shift = beta - mean*scale,
  *           running <- (1-m)*running + m*(mean, unbiased var); saves mean,rstd.

@@ -106,16 +106,23 @@ __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t offset, uint
   }
   return make_uint4(c0, c1, c2, c3);
 }
-// keep-mask scale for 4 consecutive channels of element group `idx4` (= (row*32 + col)/4)
-__device__ __forceinline__ void dropout4(uint64_t seed, uint64_t offset, uint64_t idx4, float p,
-                                         float m[4]) {
-  uint4 r = philox4x32(seed, offset, idx4);
+// Dropout keep-mask (scaled by 1/(1-p)) for 8 consecutive channels: element e = row*32 + col -> group idx8 = e/8.
+// One Philox call yields eight 16-bit uniforms; an element is dropped when its uniform < round(p * 2^16).
+__device__ __forceinline__ void dropout8(uint64_t seed, uint64_t offset, uint64_t idx8, float p, float m[8]) {
+  const uint4 r = philox4x32(seed, offset, idx8);
   const float inv = 1.0f / (1.0f - p);
-  const float s = 2.3283064365386963e-10f;  // 2^-32
-  m[0] = (r.x * s >= p) ? inv : 0.f;
-  m[1] = (r.y * s >= p) ? inv : 0.f;
-  m[2] = (r.z * s >= p) ? inv : 0.f;
-  m[3] = (r.w * s >= p) ? inv : 0.f;
+  const uint32_t thr = (uint32_t)(p * 65536.0f + 0.5f);
+  m[0] = ((r.x & 0xFFFFu) >= thr) ? inv : 0.f;  m[1] = ((r.x >> 16) >= thr) ? inv : 0.f;
+  m[2] = ((r.y & 0xFFFFu) >= thr) ? inv : 0.f;  m[3] = ((r.y >> 16) >= thr) ? inv : 0.f;
+  m[4] = ((r.z & 0xFFFFu) >= thr) ? inv : 0.f;  m[5] = ((r.z >> 16) >= thr) ? inv : 0.f;
+  m[6] = ((r.w & 0xFFFFu) >= thr) ? inv : 0.f;  m[7] = ((r.w >> 16) >= thr) ? inv : 0.f;
+}
+// the 4 channels [col, col+4) of row `row` (col % 4 == 0) out of the same stream
+__device__ __forceinline__ void dropout4(uint64_t seed, uint64_t offset, uint64_t row, int col, float p, float m[4]) {
+  float t[8];
+  dropout8(seed, offset, row * 4 + (uint64_t)(col >> 3), p, t);
+  const int h = (col >> 2) & 1;
+  m[0] = h ? t[4] : t[0]; m[1] = h ? t[5] : t[1]; m[2] = h ? t[6] : t[2]; m[3] = h ? t[7] : t[3];
 }
 
 }  // namespace gwn

@@ -40,6 +40,7 @@ struct GcnFwdParams {
   bf16* u;                     // out [slabs*V, 32]
   double* stats;               // [2][32], accumulated with atomics (caller zeroes)
   int V, Kp, slabs;
+  long long* trace;            // optional debug: [64 slabs][8] clock64 timestamps of CTA 0 (NULL = off)
 };
 
 int gcn_fused_supported(int V, int n_mats);

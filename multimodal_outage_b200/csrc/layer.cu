@@ -58,7 +58,7 @@ struct EpiMlp {
     } else if (drop_p > 0.f) {
       const uint64_t sd = rng ? __ldg(rng) : seed;
       const uint64_t of = rng ? offset + __ldg(rng + 1) : offset;
-      float m[4]; dropout4(sd, of, (uint64_t)(p * 8 + (col >> 2)), drop_p, m);
+      float m[4]; dropout4(sd, of, (uint64_t)p, col, drop_p, m);
 #pragma unroll
       for (int j = 0; j < 4; ++j) h[j] *= m[j];
     }
@@ -157,14 +157,14 @@ struct EpiMlpTC {    // N = 32: bias + dropout + residual(BN-folded input) -> u,
       uint64_t sd = 0, of = 0;
       if (!mask && drop_p > 0.f) { sd = rng ? __ldg(rng) : seed; of = rng ? offset + __ldg(rng + 1) : offset; }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float m[4] = {1.f, 1.f, 1.f, 1.f}, r[4];
-        if (mask) load4(mask + p * 32 + 4 * j, m);
-        else if (drop_p > 0.f) dropout4(sd, of, (uint64_t)(p * 8 + j), drop_p, m);
-        load4(rp + 4 * j, r);
+      for (int j = 0; j < 4; ++j) {
+        float m[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f}, r[8];
+        if (mask) { load4(mask + p * 32 + 8 * j, m); load4(mask + p * 32 + 8 * j + 4, m + 4); }
+        else if (drop_p > 0.f) dropout8(sd, of, (uint64_t)(p * 4 + j), drop_p, m);
+        load4(rp + 8 * j, r); load4(rp + 8 * j + 4, r + 4);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int c = 4 * j + i;
+        for (int i = 0; i < 8; ++i) {
+          const int c = 8 * j + i;
           float rr = scale ? fmaf(r[i], __ldg(scale + c), __ldg(shift + c)) : r[i];
           h[c] = (v[c] + __ldg(bias + c)) * m[i] + rr;
         }
@@ -435,7 +435,7 @@ __global__ void drop_bwd_kernel(const T* __restrict__ du, const T* __restrict__ 
   } else {
     const uint64_t sd = rng ? __ldg(rng) : seed;
     const uint64_t of = rng ? offset + __ldg(rng + 1) : offset;
-    dropout4(sd, of, (uint64_t)i, p_drop, m);
+    dropout4(sd, of, (uint64_t)p, c, p_drop, m);
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) g[j] *= m[j];
@@ -980,6 +980,33 @@ extern "C" int gwn_layer_bwd(const gwn_layer_cfg* cfg, const gwn_layer_bwd_args*
   GWN_REQUIRE(args->du == nullptr || (args->ws_cat && args->ws_dcat && args->w_mlp), "layer_bwd: NULL workspace");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   return cfg->dtype == GWN_F32 ? layer_bwd_t<float>(cfg, args, st) : layer_bwd_t<bf16>(cfg, args, st);
+}
+
+// The fused diffusion graph convolution alone (unit tests / roofline microbenchmark): z -> u (+ stats).
+extern "C" int gwn_gcn_fwd(const void* z, const void* u_prev, const float* scale, const float* shift,
+                           const void* hop_mats, int n_supports, const float* w_mlp, const float* b_mlp, void* ws_w,
+                           float drop_p, unsigned long long seed, unsigned long long offset, void* u, double* stats,
+                           int N, int V, int Lin, int Lout, void* stream) {
+  GWN_REQUIRE(z && u_prev && hop_mats && w_mlp && b_mlp && ws_w && u && stats && n_supports >= 1 && Lout <= Lin,
+              "gcn_fwd: bad argument");
+  GWN_REQUIRE(gcn_fused_supported(V, 2 * n_supports), "gcn_fwd: V=%d with %d supports does not fit on chip", V, n_supports);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  GWN_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 64, st));
+  bf16* wimg = reinterpret_cast<bf16*>(ws_w);
+  if (int rc = launch_gcn_wprep(w_mlp, 2 * n_supports, wimg, st)) return rc;
+  GcnFwdParams fp{};
+  fp.z = reinterpret_cast<const bf16*>(z); fp.u_prev = reinterpret_cast<const bf16*>(u_prev);
+  fp.RI = (long long)Lin * V; fp.RO = (long long)Lout * V; fp.crop = (long long)(Lin - Lout) * V;
+  fp.scale = scale; fp.shift = shift;
+  fp.mats = reinterpret_cast<const bf16*>(hop_mats); fp.n_mats = 2 * n_supports;
+  for (int j = 0; j < fp.n_mats; ++j) fp.mat_src[j] = 4 * (j / 2) + (j % 2);
+  fp.w_img = wimg; fp.bias = b_mlp; fp.mask = nullptr; fp.drop_p = drop_p; fp.seed = seed; fp.offset = offset;
+  fp.rng = nullptr; fp.u = reinterpret_cast<bf16*>(u); fp.stats = stats; fp.V = V; fp.slabs = N * Lout;
+  {  // debug timeline: GWN_GCN_TRACE=<device pointer of 64*8 int64> (scripts/gpu_gcn_trace.py)
+    const char* e = getenv("GWN_GCN_TRACE");
+    fp.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
+  }
+  return launch_gcn_fwd(fp, st);
 }
 
 extern "C" int gwn_node_mix(const void* x, int x_pitch, int x_off, void* y, int y_pitch, int y_off, int accumulate,

@@ -252,6 +252,29 @@ def test_fused_dropout_is_a_valid_mask():
     assert abs((fp - fm) / (2 * eps) - g) < 5e-2 * max(1.0, abs(g))
 
 
+def test_fused_dropout_same_mask_in_every_kernel_path():
+    """The in-kernel Philox mask is a function of (seed, offset, element) only: the fp32 CUDA-core path, the
+    unfused bf16 tensor-core path and the fused bf16 gcn kernel must all draw the SAME mask, forward and
+    backward (so bf16 output/gradients stay within the bf16 bar of the fp32 run with dropout on)."""
+    cfg = GWNetConfig(num_nodes=67, in_dim=2, out_dim=12, kernel_size=2, blocks=1, layers=2, dropout=0.3)
+    m = build_model(cfg, case_supports('dir'))
+    load_synth(m, cfg, 19)
+    x = torch.randn(8, 2, 67, 12, device='cuda')
+    m.train()
+    outs, grads = [], []
+    for dt in (torch.float32, torch.bfloat16):
+        m.compute_dtype = dt
+        m._rng_state = None
+        torch.manual_seed(5)
+        m.zero_grad()
+        o = m(x)
+        o.square().mean().backward()
+        outs.append(o.detach().clone())
+        grads.append(m.gconv[0].mlp.mlp.weight.grad.detach().clone())
+    assert rel(outs[1], outs[0]) < BF16_TOL, rel(outs[1], outs[0])
+    assert rel(grads[1], grads[0]) < 0.1, rel(grads[1], grads[0])
+
+
 def test_adaptive_adjacency_op_fwd_bwd():
     from multimodal_outage_b200 import ops
     for V in (67, 310, 5):
