@@ -39,6 +39,14 @@ typedef __nv_bfloat16 bf16;
 
 static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
 
+// position -> (sample, row in sample) with 32-bit arithmetic: a 64-bit div/mod costs several hundred cycles
+// per call on the device and used to dominate the producer loops; launchers guarantee P < 2^31.
+__device__ __forceinline__ void split_pos(long long pp, long long rows_per_n, long long& n, long long& rem) {
+  const uint32_t q = (uint32_t)pp / (uint32_t)rows_per_n;
+  n = q;
+  rem = (uint32_t)pp - q * (uint32_t)rows_per_n;
+}
+
 // ---- 4-wide loads/stores of 32-channel rows (16 B fp32 / 8 B bf16) ----
 __device__ __forceinline__ void load4(const float* p, float v[4]) {
   float4 t = *reinterpret_cast<const float4*>(p);

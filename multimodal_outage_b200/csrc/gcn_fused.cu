@@ -280,7 +280,8 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gcn_fwd_kernel(const __grid_con
         const long long pp = slab * V + w;
         uint4 rr[4];
         if (valid) {
-          const long long n = pp / p.RO, rem = pp % p.RO;
+          long long n, rem;
+          split_pos(pp, p.RO, n, rem);
           const uint4* rp = reinterpret_cast<const uint4*>(p.u_prev + (n * p.RI + rem + p.crop) * 32);
 #pragma unroll
           for (int j = 0; j < 4; ++j) rr[j] = __ldg(rp + j);

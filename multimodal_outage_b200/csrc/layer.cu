@@ -454,7 +454,8 @@ __global__ void gate_bwd_kernel(const T* __restrict__ dz, int dz_pitch, const T*
   float g[4] = {0.f, 0.f, 0.f, 0.f}, av[4], bv[4];
   if (dz) load4(dz + p * dz_pitch + c, g);
   if (dz_last) {
-    long long n = p / rows_per_n, rem = p % rows_per_n;
+    long long n, rem;
+    split_pos(p, rows_per_n, n, rem);
     if (rem >= last_begin) {
       float t[4]; load4(dz_last + (n * last_rows + rem - last_begin) * 32 + c, t);
 #pragma unroll
@@ -543,6 +544,7 @@ static int check_cfg(const gwn_layer_cfg* c) {
   GWN_REQUIRE(c->Lout == c->Lin - c->dilation * (c->taps - 1) && c->Lout >= 1, "bad Lin/Lout %d/%d", c->Lin, c->Lout);
   GWN_REQUIRE(c->Lf >= 1 && c->Lf <= c->Lout, "bad Lf %d", c->Lf);
   GWN_REQUIRE(c->N >= 1 && c->V >= 1, "bad N/V");
+  GWN_REQUIRE((long long)c->N * c->Lin * c->V < (1ll << 31), "layer: N*Lin*V must be < 2^31 positions");
   return 0;
 }
 

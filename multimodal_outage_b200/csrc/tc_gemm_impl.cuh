@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
       const uint32_t sa = smem_u32(a_s + (size_t)stage * a_bytes) + (uint32_t)tid * 16u;
       const long long pp = (long long)tile * 128 + tid;
       const bool pv = pp < p.P;
-      const long long n = pv ? pp / p.rows_per_n_out : 0, rem = pv ? pp % p.rows_per_n_out : 0;
+      long long n = 0, rem = 0;
+      if (pv) split_pos(pp, p.rows_per_n_out, n, rem);
       for (int q = 0; q < p.n_chunks; ++q) {
         const PgChunk c = p.ch[q];
         const long long sr = rem + c.row_off;
@@ -131,7 +132,8 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
       tc_fence_after();
       const long long pp = (long long)tile * 128 + quad * 32 + lane;
       const bool pv = pp < p.P;
-      const long long n = pv ? pp / p.rows_per_n_out : 0, rem = pv ? pp % p.rows_per_n_out : 0;
+      long long n = 0, rem = 0;
+      if (pv) split_pos(pp, p.rows_per_n_out, n, rem);
       for (int c0 = half * 32; c0 < N; c0 += 64) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)c0, v);
@@ -154,6 +156,7 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
 template <typename Epi>
 int launch_pos_gemm_tc(PgParams& p, const Epi& epi, cudaStream_t st) {
   if (p.P <= 0) return 0;
+  GWN_REQUIRE(p.P < (1ll << 31), "pos_gemm_tc: too many positions");
   GWN_REQUIRE(p.n_chunks >= 1 && p.n_chunks <= PG_TC_MAX_CHUNKS && p.N % 16 == 0 && p.N >= 16 && p.N <= 256,
               "pos_gemm_tc: unsupported shape (chunks=%d, N=%d)", p.n_chunks, p.N);
   p.n_tiles = (int)cdiv(p.P, 128);

@@ -11,6 +11,8 @@
 //
 // dadj_tc: dA[v,w] += sum_{s,c} X[s,v,c] * G[s,w,c]                           (nconv grad wrt the support)
 //   M = v, N = w, K = channel; both operands K-major (channels contiguous): per slab 2 K-steps.
+#include <cstdlib>
+
 #include "tc.cuh"
 #include "tc_wgrad.cuh"
 
@@ -21,6 +23,8 @@ constexpr int WG_STAGES = 3;
 constexpr int WG_PRODUCERS = 128;    // warps 0-3
 constexpr int WG_MMA_WARP = 4;
 constexpr int WG_THREADS = 32 * 9;   // warps 5-8 epilogue
+
+#define WG_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && g < 48 && (tid & 31) == 0) p.trace[g * 8 + (slot)] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgParams p) {
   using namespace tc;
@@ -71,6 +75,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const int stage = g % WG_STAGES, phase = (g / WG_STAGES) & 1;
       mbar_wait(&empty[stage], (uint32_t)(phase ^ 1));
+      if (warp == 0) WG_TRACE(0);
       const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
       const uint32_t sg = sa + a_bytes;
 #pragma unroll
@@ -78,7 +83,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
         const int i = r0 + 32 * h;
         const long long pp = (long long)tile * WG_PT + i;
         const bool pv = pp < p.P;
-        const long long n = pv ? pp / p.rows_per_n_out : 0, rem = pv ? pp % p.rows_per_n_out : 0;
+        long long n = 0, rem = 0;
+        if (pv) split_pos(pp, p.rows_per_n_out, n, rem);
         for (int q = 0; q < p.n_chunks; ++q) {
           const WgChunk c = p.ch[q];
           const long long sr = rem + c.row_off;
@@ -92,11 +98,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
         }
       }
       cp_async_commit();
+      if (warp == 0) WG_TRACE(1);
       if (g >= WG_STAGES - 1) {
         cp_async_wait<WG_STAGES - 1>();
         fence_proxy_async();
         mbar_arrive(&full[(g - (WG_STAGES - 1)) % WG_STAGES]);
       }
+      if (warp == 0) WG_TRACE(2);
       ++g;
     }
     // drain: groups g-2, g-1 (for 3 stages) are still pending
@@ -110,6 +118,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const int stage = g % WG_STAGES;
         mbar_wait(&full[stage], (uint32_t)((g / WG_STAGES) & 1));
+        WG_TRACE(3);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes), sg = sa + a_bytes;
         for (int t = 0; t < mt; ++t)
@@ -120,6 +129,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
             umma_bf16(tmem_base + (uint32_t)(t * N), adesc, bdesc, idesc, (g == 0 && ks == 0) ? 0u : 1u);
           }
         umma_commit(&empty[stage]);
+        WG_TRACE(4);
         ++g;
       }
       umma_commit(tfull);
@@ -322,7 +332,12 @@ int wgrad_tc_supported(int n_chunks, int N) {
 int launch_wgrad_tc(WgParams& p, cudaStream_t st) {
   if (p.P <= 0) return 0;
   GWN_REQUIRE(wgrad_tc_supported(p.n_chunks, p.N), "wgrad_tc: unsupported shape (chunks=%d, N=%d)", p.n_chunks, p.N);
+  GWN_REQUIRE(p.P < (1ll << 31), "wgrad_tc: too many positions");
   p.n_tiles = (int)cdiv(p.P, WG_PT);
+  {
+    const char* e = getenv("GWN_WG_TRACE");
+    p.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
+  }
   int mt = (32 * p.n_chunks + 1 + 127) / 128;
   size_t stage = (size_t)mt * 16 * WG_PT * 16 + (size_t)(p.N / 8) * WG_PT * 16;
   size_t smem = WG_STAGES * stage + 512;

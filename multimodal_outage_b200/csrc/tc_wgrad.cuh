@@ -26,6 +26,7 @@ struct WgParams {
   const float* scale;       // optional per-input-channel affine of A: dW = scale*D + shift*db
   const float* shift;
   int n_tiles;
+  long long* trace;         // optional debug timeline of CTA 0 (GWN_WG_TRACE)
 };
 
 struct DadjTerm { const bf16* X; const bf16* G; };   // both [slabs, V, 32] contiguous slots
