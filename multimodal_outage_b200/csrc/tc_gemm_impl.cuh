@@ -69,23 +69,28 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
 
   if (warp < PGT_MMA_WARP) {
     // ===================== producers: one row per thread =====================
+    const uint32_t ro32 = (uint32_t)p.rows_per_n_out;
     int g = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const int stage = g % stages, phase = (g / stages) & 1;
       mbar_wait(&empty[stage], (uint32_t)(phase ^ 1));
       const uint32_t sa = smem_u32(a_s + (size_t)stage * a_bytes) + (uint32_t)tid * 16u;
-      const long long pp = (long long)tile * 128 + tid;
-      const bool pv = pp < p.P;
-      long long n = 0, rem = 0;
-      if (pv) split_pos(pp, p.rows_per_n_out, n, rem);
+      // 32-bit row arithmetic (launcher guarantees < 2^31 positions); one IMAD.WIDE per source row
+      const uint32_t pp = (uint32_t)tile * 128u + (uint32_t)tid;
+      const bool pv = pp < (uint32_t)p.P;
+      const uint32_t n = pp / ro32, rem = pp - n * ro32;
+#pragma unroll 4
       for (int q = 0; q < p.n_chunks; ++q) {
-        const PgChunk c = p.ch[q];
-        const long long sr = rem + c.row_off;
-        const bool ok = pv && sr >= 0 && sr < c.rows_per_n;
-        const bf16* src = ok ? c.base + (n * c.rows_per_n + sr) * (long long)c.pitch + c.col_off : c.base;
-#pragma unroll
-        for (int kc = 0; kc < 4; ++kc)
-          cp_async16(sa + (uint32_t)((q * 4 + kc) * 128) * 16u, src + kc * 8, ok ? 16u : 0u);
+        const int sr = (int)rem + (int)p.ch[q].row_off;
+        const bool ok = pv && sr >= 0 && sr < (int)p.ch[q].rows_per_n;
+        const uint32_t row = n * (uint32_t)p.ch[q].rows_per_n + (uint32_t)sr;
+        const bf16* src = p.ch[q].base + (ok ? (size_t)row * (uint32_t)p.ch[q].pitch + p.ch[q].col_off : 0);
+        const uint32_t d = sa + (uint32_t)(q * 4 * 128) * 16u;
+        const uint32_t nb = ok ? 16u : 0u;
+        cp_async16(d, src, nb);
+        cp_async16(d + 2048u, src + 8, nb);
+        cp_async16(d + 4096u, src + 16, nb);
+        cp_async16(d + 6144u, src + 24, nb);
       }
       cp_async_commit();
       // signal the stage whose group is now guaranteed complete (stages-1 groups may stay in flight)

@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   if (warp < WG_MMA_WARP) {
     // ===================== producers =====================
     const int cg = tid & 3, r0 = tid >> 2;   // rows r0 and r0+32 of the tile, channel group cg
+    const uint32_t ro32 = (uint32_t)p.rows_per_n_out;
     int g = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const int stage = g % WG_STAGES, phase = (g / WG_STAGES) & 1;
@@ -78,24 +79,28 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       if (warp == 0) WG_TRACE(0);
       const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
       const uint32_t sg = sa + a_bytes;
+      // 32-bit row arithmetic (launcher guarantees every source has < 2^31 rows); one IMAD.WIDE per copy
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int i = r0 + 32 * h;
-        const long long pp = (long long)tile * WG_PT + i;
-        const bool pv = pp < p.P;
-        long long n = 0, rem = 0;
-        if (pv) split_pos(pp, p.rows_per_n_out, n, rem);
-        for (int q = 0; q < p.n_chunks; ++q) {
-          const WgChunk c = p.ch[q];
-          const long long sr = rem + c.row_off;
-          const bool ok = pv && sr >= 0 && sr < c.rows_per_n;
-          const bf16* src = ok ? c.base + (n * c.rows_per_n + sr) * (long long)c.pitch + cg * 8 : c.base;
-          cp_async16(sa + (uint32_t)((q * 4 + cg) * WG_PT + i) * 16u, src, ok ? 16u : 0u);
+        const uint32_t pp = (uint32_t)tile * WG_PT + (uint32_t)i;
+        const bool pv = pp < (uint32_t)p.P;
+        const uint32_t n = pp / ro32, rem = pp - n * ro32;
+        const uint32_t sdst = sa + (uint32_t)(cg * WG_PT + i) * 16u;
+#pragma unroll
+        for (int q = 0; q < WG_MAX_CHUNKS; ++q) {
+          if (q < p.n_chunks) {
+            const int sr = (int)rem + (int)p.ch[q].row_off;
+            const bool ok = pv && sr >= 0 && sr < (int)p.ch[q].rows_per_n;
+            const uint32_t row = n * (uint32_t)p.ch[q].rows_per_n + (uint32_t)sr;
+            const bf16* src = p.ch[q].base + (ok ? (size_t)row * (uint32_t)p.ch[q].pitch + cg * 8 : 0);
+            cp_async16(sdst + (uint32_t)(q * 4 * WG_PT) * 16u, src, ok ? 16u : 0u);
+          }
         }
-        for (int n8 = cg; n8 < N / 8; n8 += 4) {
-          const bf16* src = pv ? p.G + pp * (long long)p.g_pitch + n8 * 8 : p.G;
-          cp_async16(sg + (uint32_t)(n8 * WG_PT + i) * 16u, src, pv ? 16u : 0u);
-        }
+        const bf16* gsrc = p.G + (pv ? (size_t)pp * (uint32_t)p.g_pitch + cg * 8 : 0);
+        const uint32_t gdst = sg + (uint32_t)(cg * WG_PT + i) * 16u;
+        cp_async16(gdst, gsrc, pv ? 16u : 0u);
+        if (N > 32) cp_async16(gdst + (uint32_t)(4 * WG_PT) * 16u, gsrc + 32, pv ? 16u : 0u);
       }
       cp_async_commit();
       if (warp == 0) WG_TRACE(1);
