@@ -18,6 +18,8 @@ struct PgChunk {
   int col_off;
 };
 
+constexpr int PG_TC_MAX_MAPS = 8;
+
 struct PgParams {
   PgChunk ch[PG_TC_MAX_CHUNKS];
   int n_chunks;                 // K = 32 * n_chunks
@@ -25,6 +27,12 @@ struct PgParams {
   int N;                        // output columns (multiple of 16, <= 256)
   const bf16* w_img;            // [K/8][N][8]
   int n_tiles;
+  // filled by the launcher: TMA tiling.  A tile is 128 consecutive output rows of ONE sample, so that a chunk
+  // (temporal tap / concat slot) is one 3-D box {32 ch, 128 rows, 1 sample} whose out-of-range rows TMA zero-fills.
+  int tiles_per_n, n_samples;
+  int rows_out;                 // output rows per (virtual) sample
+  int map_of[PG_TC_MAX_CHUNKS]; // chunk -> tensor map
+  int row_off[PG_TC_MAX_CHUNKS];
 };
 
 // builds w_img (+ folded bias) from fp32 weights; see tc_gemm.cu

@@ -8,10 +8,11 @@
 #pragma once
 #include "tc.cuh"
 #include "tc_gemm.cuh"
+#include "tma_gemm.cuh"
 
 namespace gwn {
 
-constexpr int PGT_PRODUCERS = 128;   // warps 0-3
+constexpr int PGT_PRODUCERS = 128;   // warps 0-3 (warp 0 lane 0 issues the TMA copies)
 constexpr int PGT_MMA_WARP = 4;
 constexpr int PGT_EPI_WARPS = 8;     // warps 5-12, two per TMEM lane quadrant (they split the 32-column chunks)
 constexpr int PGT_THREADS = 32 * (5 + PGT_EPI_WARPS);
@@ -31,18 +32,26 @@ __device__ __forceinline__ float warp_column_sums(float v[32], int lane) {
   return v[0];
 }
 
+struct PgMaps { CUtensorMap m[PG_TC_MAX_MAPS]; };
+
+// A operand: per chunk one TMA box -> [128 rows][64 B] 64B-swizzled (K-major SW64: 8-row atoms of 512 B, the two
+// K=16 halves of a chunk 32 B apart); B operand: resident no-swizzle weight image; D: two TMEM accumulators.
 template <typename Epi>
-__global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __grid_constant__ PgParams p, Epi epi,
+__global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __grid_constant__ PgMaps maps,
+                                                                      const __grid_constant__ PgParams p, Epi epi,
                                                                       int stages) {
   using namespace tc;
-  extern __shared__ __align__(1024) uint8_t smem[];
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int N = p.N, K8 = p.n_chunks * 4;                     // 16-byte K pieces per row
-  const uint32_t w_bytes = (uint32_t)K8 * (uint32_t)N * 16u;
-  const uint32_t a_bytes = (uint32_t)K8 * 128u * 16u;         // one stage
-  uint8_t* w_s = smem;
-  uint8_t* a_s = smem + ((w_bytes + 127u) & ~127u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(a_s + (size_t)stages * a_bytes);
+  const int N = p.N, K8 = p.n_chunks * 4;                     // 16-byte K pieces per weight row
+  const uint32_t a_bytes = (uint32_t)p.n_chunks * 8192u;      // one stage: n_chunks boxes of 128 x 64 B
+  const uint32_t w_bytes = ((uint32_t)K8 * (uint32_t)N * 16u + 1023u) & ~1023u;
+  uint8_t* a_s = smem;                                        // stages first (1024-aligned boxes)
+  uint8_t* w_s = smem + (size_t)stages * a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_s + w_bytes);
   uint64_t* full = bars;               // [stages] (<= 4)
   uint64_t* empty = bars + 4;
   uint64_t* tfull = bars + 8;          // [2]
@@ -50,7 +59,7 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   if (tid == 0) {
-    for (int i = 0; i < stages; ++i) { mbar_init(&full[i], PGT_PRODUCERS); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 32 * PGT_EPI_WARPS); }
     fence_barrier_init();
   }
@@ -59,7 +68,7 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.w_img);
     uint4* dst = reinterpret_cast<uint4*>(w_s);
-    for (int i = tid; i < (int)(w_bytes / 16); i += PGT_THREADS) dst[i] = __ldg(src + i);
+    for (int i = tid; i < K8 * N; i += PGT_THREADS) dst[i] = __ldg(src + i);
     fence_proxy_async();
   }
   tc_fence_before();
@@ -67,43 +76,21 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < PGT_MMA_WARP) {
-    // ===================== producers: one row per thread =====================
-    const uint32_t ro32 = (uint32_t)p.rows_per_n_out;
-    int g = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      const int stage = g % stages, phase = (g / stages) & 1;
-      mbar_wait(&empty[stage], (uint32_t)(phase ^ 1));
-      const uint32_t sa = smem_u32(a_s + (size_t)stage * a_bytes) + (uint32_t)tid * 16u;
-      // 32-bit row arithmetic (launcher guarantees < 2^31 positions); one IMAD.WIDE per source row
-      const uint32_t pp = (uint32_t)tile * 128u + (uint32_t)tid;
-      const bool pv = pp < (uint32_t)p.P;
-      const uint32_t n = pp / ro32, rem = pp - n * ro32;
-#pragma unroll 4
-      for (int q = 0; q < p.n_chunks; ++q) {
-        const int sr = (int)rem + (int)p.ch[q].row_off;
-        const bool ok = pv && sr >= 0 && sr < (int)p.ch[q].rows_per_n;
-        const uint32_t row = n * (uint32_t)p.ch[q].rows_per_n + (uint32_t)sr;
-        const bf16* src = p.ch[q].base + (ok ? (size_t)row * (uint32_t)p.ch[q].pitch + p.ch[q].col_off : 0);
-        const uint32_t d = sa + (uint32_t)(q * 4 * 128) * 16u;
-        const uint32_t nb = ok ? 16u : 0u;
-        cp_async16(d, src, nb);
-        cp_async16(d + 2048u, src + 8, nb);
-        cp_async16(d + 4096u, src + 16, nb);
-        cp_async16(d + 6144u, src + 24, nb);
+  if (warp == 0) {
+    // ===================== TMA producer (one thread) =====================
+    if (lane == 0) {
+      int g = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++g) {
+        const int stage = g % stages, phase = (g / stages) & 1;
+        const int n = tile / p.tiles_per_n, r0 = (tile - n * p.tiles_per_n) * 128;
+        mbar_wait(&empty[stage], (uint32_t)(phase ^ 1));
+        tg::mbar_expect_tx(&full[stage], a_bytes);
+        const uint32_t sa = base + (uint32_t)stage * a_bytes;
+        for (int q = 0; q < p.n_chunks; ++q)
+          tg::tma_3d(sa + (uint32_t)q * 8192u, &maps.m[p.map_of[q]], 0, r0 + p.row_off[q], n, &full[stage]);
       }
-      cp_async_commit();
-      // signal the stage whose group is now guaranteed complete (stages-1 groups may stay in flight)
-      if (g >= stages - 1) {
-        if (stages == 2) cp_async_wait<1>(); else if (stages == 3) cp_async_wait<2>(); else cp_async_wait<3>();
-        fence_proxy_async();
-        mbar_arrive(&full[(g - (stages - 1)) % stages]);
-      }
-      ++g;
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (int k = (g >= stages - 1 ? g - (stages - 1) : 0); k < g; ++k) mbar_arrive(&full[k % stages]);
+    __syncwarp();
   } else if (warp == PGT_MMA_WARP) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, N, false, false);
@@ -114,9 +101,9 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
         mbar_wait(&tempty[acc], (uint32_t)(((g >> 1) & 1) ^ 1));
         mbar_wait(&full[stage], (uint32_t)((g / stages) & 1));
         tc_fence_after();
-        const uint32_t sa = smem_u32(a_s + (size_t)stage * a_bytes);
+        const uint32_t sa = base + (uint32_t)stage * a_bytes;
         for (int ks = 0; ks < K8 / 2; ++ks) {
-          const uint64_t adesc = make_smem_desc(sa + (uint32_t)(2 * ks) * 2048u, 2048u, 128u);
+          const uint64_t adesc = tg::make_desc_sw(sa + (uint32_t)(ks >> 1) * 8192u + (uint32_t)(ks & 1) * 32u, 16u, 512u, 4u);
           const uint64_t bdesc = make_smem_desc(w_addr + (uint32_t)(2 * ks) * (uint32_t)N * 16u, (uint32_t)N * 16u, 128u);
           umma_bf16(tmem_base + (uint32_t)acc * acc_cols, adesc, bdesc, idesc, ks == 0 ? 0u : 1u);
         }
@@ -126,7 +113,7 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp > PGT_MMA_WARP) {
     // ===================== epilogue =====================
     const int quad = warp & 3;
     const int half = (warp - (PGT_MMA_WARP + 1)) >> 2;
@@ -135,10 +122,12 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
       const int acc = g & 1;
       mbar_wait(&tfull[acc], (uint32_t)((g >> 1) & 1));
       tc_fence_after();
-      const long long pp = (long long)tile * 128 + quad * 32 + lane;
-      const bool pv = pp < p.P;
-      long long n = 0, rem = 0;
-      if (pv) split_pos(pp, p.rows_per_n_out, n, rem);
+      const int ns = tile / p.tiles_per_n;
+      const int r = (tile - ns * p.tiles_per_n) * 128 + quad * 32 + lane;
+      const bool pv = r < p.rows_out;
+      // (sample, row) of the caller's view: virtual samples (position-wise GEMMs tile the flat position axis)
+      long long pp = (long long)ns * p.rows_out + r, n = ns, rem = r;
+      if (p.rows_out != (int)p.rows_per_n_out && pv) split_pos(pp, p.rows_per_n_out, n, rem);
       for (int c0 = half * 32; c0 < N; c0 += 64) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)c0, v);
@@ -164,23 +153,52 @@ int launch_pos_gemm_tc(PgParams& p, const Epi& epi, cudaStream_t st) {
   GWN_REQUIRE(p.P < (1ll << 31), "pos_gemm_tc: too many positions");
   GWN_REQUIRE(p.n_chunks >= 1 && p.n_chunks <= PG_TC_MAX_CHUNKS && p.N % 16 == 0 && p.N >= 16 && p.N <= 256,
               "pos_gemm_tc: unsupported shape (chunks=%d, N=%d)", p.n_chunks, p.N);
-  p.n_tiles = (int)cdiv(p.P, 128);
-  const size_t w_bytes = ((size_t)p.n_chunks * 4 * p.N * 16 + 127) & ~(size_t)127;
-  const size_t a_bytes = (size_t)p.n_chunks * 4 * 128 * 16;
-  int stages = (int)((220 * 1024 - w_bytes - 256) / a_bytes);
+  // position-wise GEMM (every chunk has the output's own row structure): tile the flat position axis
+  bool flat = true;
+  for (int q = 0; q < p.n_chunks; ++q)
+    if (p.ch[q].rows_per_n != p.rows_per_n_out || p.ch[q].row_off != 0) flat = false;
+  const long long n_real = p.P / p.rows_per_n_out;
+  GWN_REQUIRE(n_real * p.rows_per_n_out == p.P, "pos_gemm_tc: P is not a whole number of samples");
+  p.rows_out = flat ? (int)p.P : (int)p.rows_per_n_out;
+  p.n_samples = flat ? 1 : (int)n_real;
+  p.tiles_per_n = (int)cdiv(p.rows_out, 128);
+  p.n_tiles = p.n_samples * p.tiles_per_n;
+  PgMaps maps;
+  int n_maps = 0;
+  struct Key { const bf16* base; long long rows; int pitch, col; } keys[PG_TC_MAX_MAPS];
+  for (int q = 0; q < p.n_chunks; ++q) {
+    const PgChunk& c = p.ch[q];
+    const long long rows = flat ? p.P : c.rows_per_n;
+    int m = -1;
+    for (int i = 0; i < n_maps; ++i)
+      if (keys[i].base == c.base && keys[i].rows == rows && keys[i].pitch == c.pitch && keys[i].col == c.col_off) m = i;
+    if (m < 0) {
+      GWN_REQUIRE(n_maps < PG_TC_MAX_MAPS, "pos_gemm_tc: too many distinct sources");
+      m = n_maps++;
+      keys[m] = Key{c.base, rows, c.pitch, c.col_off};
+      if (int rc = tg_map_rows3d(&maps.m[m], c.base + c.col_off, (uint64_t)rows, (uint64_t)(flat ? 1 : n_real),
+                                 (uint64_t)c.pitch, 128))
+        return rc;
+    }
+    p.map_of[q] = m;
+    GWN_REQUIRE(c.row_off > -(1ll << 30) && c.row_off < (1ll << 30), "pos_gemm_tc: row offset out of range");
+    p.row_off[q] = (int)c.row_off;
+  }
+  for (int i = n_maps; i < PG_TC_MAX_MAPS; ++i) maps.m[i] = maps.m[0];
+  const size_t w_bytes = ((size_t)p.n_chunks * 4 * p.N * 16 + 1023) & ~(size_t)1023;
+  const size_t a_bytes = (size_t)p.n_chunks * 8192;
+  int stages = (int)((220 * 1024 - w_bytes - 1024 - 256) / a_bytes);
   if (stages > 4) stages = 4;
   GWN_REQUIRE(stages >= 2, "pos_gemm_tc: K=%d does not fit 2 stages in shared memory", 32 * p.n_chunks);
-  const size_t smem = w_bytes + stages * a_bytes + 256;
+  const size_t smem = w_bytes + stages * a_bytes + 1024 + 256;
   static bool attr_set = false;   // per (Epi) instantiation
   if (!attr_set) {
     GWN_CUDA(cudaFuncSetAttribute(pos_gemm_tc_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  int dev = 0, sms = 0;
-  GWN_CUDA(cudaGetDevice(&dev));
-  GWN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int sms = tg_sm_count();
   int grid = p.n_tiles < sms ? p.n_tiles : sms;
-  pos_gemm_tc_kernel<Epi><<<grid, PGT_THREADS, smem, st>>>(p, epi, stages);
+  pos_gemm_tc_kernel<Epi><<<grid, PGT_THREADS, smem, st>>>(maps, p, epi, stages);
   GWN_LAUNCHED();
   return 0;
 }

@@ -15,26 +15,36 @@
 
 #include "tc.cuh"
 #include "tc_wgrad.cuh"
+#include "tma_gemm.cuh"
 
 namespace gwn {
 
-constexpr int WG_PT = 64;            // positions per tile (4 MMA K-steps)
-constexpr int WG_STAGES = 3;
-constexpr int WG_PRODUCERS = 128;    // warps 0-3
+constexpr int WG_PT = 64;            // positions per K tile (4 MMA K-steps)
+constexpr int WG_STAGES = 4;
 constexpr int WG_MMA_WARP = 4;
-constexpr int WG_THREADS = 32 * 9;   // warps 5-8 epilogue
+constexpr int WG_THREADS = 32 * 9;   // warp 0 TMA producer, warp 4 MMA, warps 5-8 epilogue
+constexpr uint32_t WG_ATOM = WG_PT * 64u;     // one 32-channel operand atom: [64 positions][64 B], 64B-swizzled
+
+struct WgMaps { CUtensorMap a[WG_MAX_CHUNKS]; CUtensorMap g[2]; };
 
 #define WG_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && g < 48 && (tid & 31) == 0) p.trace[g * 8 + (slot)] = clock64(); } while (0)
 
-__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgParams p) {
+// Operands arrive by TMA: every 32-channel group of A (a temporal tap / concat slot) and of G is one box
+// {32 ch, 64 rows, 1 sample} -> [64][64 B] 64B-swizzled = one MN-major SWIZZLE_64B atom (M or N = channel,
+// K = position); rows outside the sample are zero-filled by TMA, so they add nothing to the sums.
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgMaps maps,
+                                                                 const __grid_constant__ WgParams p) {
   using namespace tc;
-  extern __shared__ __align__(1024) uint8_t smem[];
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int mrows = 32 * p.n_chunks;                 // real weight rows; row `mrows` is the ones row
   const int mt = (mrows + 1 + 127) / 128;            // M tiles
   const int N = p.N;
-  const uint32_t a_bytes = (uint32_t)mt * 16u * WG_PT * 16u;      // 16 m8-blocks per tile, [PT x 16 B] each
-  const uint32_t g_bytes = (uint32_t)(N / 8) * WG_PT * 16u;
+  const uint32_t a_bytes = (uint32_t)mt * 4u * WG_ATOM;           // 4 atoms per M tile
+  const uint32_t g_bytes = (uint32_t)(N / 32) * WG_ATOM;
   const uint32_t stage_bytes = a_bytes + g_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)WG_STAGES * stage_bytes);
   uint64_t* full = bars;                 // [STAGES]
@@ -44,22 +54,25 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   float* db_s = reinterpret_cast<float*>(bars + 2 * WG_STAGES + 2);   // [N]
 
   if (tid == 0) {
-    for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&full[i], WG_PRODUCERS); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(tfull, 1);
     fence_barrier_init();
   }
   const uint32_t tmem_cols = (mt * N <= 32) ? 32u : (mt * N <= 64) ? 64u : (mt * N <= 128) ? 128u : 256u;
   if (warp == WG_MMA_WARP) tmem_alloc(tmem_slot, tmem_cols);
-  {  // zero the A regions once (padding rows / unused chunk blocks stay zero), then plant the ones row
+  {  // atoms TMA never writes (the ones atom and the padding atoms of the last M tile): zero, then plant the ones row
     for (int s = 0; s < WG_STAGES; ++s) {
-      uint4* a = reinterpret_cast<uint4*>(smem + (size_t)s * stage_bytes);
-      for (int i = tid; i < (int)(a_bytes / 16); i += WG_THREADS) a[i] = make_uint4(0u, 0u, 0u, 0u);
+      uint4* a = reinterpret_cast<uint4*>(smem + (size_t)s * stage_bytes + (size_t)p.n_chunks * WG_ATOM);
+      const int n16 = (int)((a_bytes - (uint32_t)p.n_chunks * WG_ATOM) / 16);
+      for (int i = tid; i < n16; i += WG_THREADS) a[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
-    const int m8 = mrows / 8;   // mrows is a multiple of 32 -> the ones row is element 0 of block m8
+    // ones atom = atom index n_chunks: element (position k, channel 0) = 1.0; 64B swizzle puts logical 16-byte chunk 0
+    // of row k at physical chunk ((k >> 1) & 3)
     for (int s = 0; s < WG_STAGES; ++s) {
-      uint4* blk = reinterpret_cast<uint4*>(smem + (size_t)s * stage_bytes + (size_t)m8 * WG_PT * 16);
-      for (int i = tid; i < WG_PT; i += WG_THREADS) blk[i] = make_uint4(0x00003F80u, 0u, 0u, 0u);  // bf16 1.0
+      uint8_t* atom = smem + (size_t)s * stage_bytes + (size_t)p.n_chunks * WG_ATOM;
+      for (int k = tid; k < WG_PT; k += WG_THREADS)
+        *reinterpret_cast<uint16_t*>(atom + k * 64 + ((k >> 1) & 3) * 16) = 0x3F80u;   // bf16 1.0
     }
     fence_proxy_async();
   }
@@ -68,54 +81,25 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < WG_MMA_WARP) {
-    // ===================== producers =====================
-    const int cg = tid & 3, r0 = tid >> 2;   // rows r0 and r0+32 of the tile, channel group cg
-    const uint32_t ro32 = (uint32_t)p.rows_per_n_out;
-    int g = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      const int stage = g % WG_STAGES, phase = (g / WG_STAGES) & 1;
-      mbar_wait(&empty[stage], (uint32_t)(phase ^ 1));
-      if (warp == 0) WG_TRACE(0);
-      const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-      const uint32_t sg = sa + a_bytes;
-      // 32-bit row arithmetic (launcher guarantees every source has < 2^31 rows); one IMAD.WIDE per copy
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int i = r0 + 32 * h;
-        const uint32_t pp = (uint32_t)tile * WG_PT + (uint32_t)i;
-        const bool pv = pp < (uint32_t)p.P;
-        const uint32_t n = pp / ro32, rem = pp - n * ro32;
-        const uint32_t sdst = sa + (uint32_t)(cg * WG_PT + i) * 16u;
-#pragma unroll
-        for (int q = 0; q < WG_MAX_CHUNKS; ++q) {
-          if (q < p.n_chunks) {
-            const int sr = (int)rem + (int)p.ch[q].row_off;
-            const bool ok = pv && sr >= 0 && sr < (int)p.ch[q].rows_per_n;
-            const uint32_t row = n * (uint32_t)p.ch[q].rows_per_n + (uint32_t)sr;
-            const bf16* src = p.ch[q].base + (ok ? (size_t)row * (uint32_t)p.ch[q].pitch + cg * 8 : 0);
-            cp_async16(sdst + (uint32_t)(q * 4 * WG_PT) * 16u, src, ok ? 16u : 0u);
-          }
-        }
-        const bf16* gsrc = p.G + (pv ? (size_t)pp * (uint32_t)p.g_pitch + cg * 8 : 0);
-        const uint32_t gdst = sg + (uint32_t)(cg * WG_PT + i) * 16u;
-        cp_async16(gdst, gsrc, pv ? 16u : 0u);
-        if (N > 32) cp_async16(gdst + (uint32_t)(4 * WG_PT) * 16u, gsrc + 32, pv ? 16u : 0u);
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int g = 0;
+      const uint32_t tx = (uint32_t)p.n_chunks * WG_ATOM + g_bytes;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++g) {
+        const int stage = g % WG_STAGES, phase = (g / WG_STAGES) & 1;
+        const int n = tile / p.tiles_per_n, r0 = (tile - n * p.tiles_per_n) * WG_PT;
+        mbar_wait(&empty[stage], (uint32_t)(phase ^ 1));
+        WG_TRACE(0);
+        tg::mbar_expect_tx(&full[stage], tx);
+        const uint32_t sa = base + (uint32_t)stage * stage_bytes, sg = sa + a_bytes;
+        for (int q = 0; q < p.n_chunks; ++q)
+          tg::tma_3d(sa + (uint32_t)q * WG_ATOM, &maps.a[p.map_of[q]], 0, r0 + p.row_off[q], n, &full[stage]);
+        for (int j = 0; j < N / 32; ++j) tg::tma_3d(sg + (uint32_t)j * WG_ATOM, &maps.g[j], 0, r0, n, &full[stage]);
+        WG_TRACE(1);
       }
-      cp_async_commit();
-      if (warp == 0) WG_TRACE(1);
-      if (g >= WG_STAGES - 1) {
-        cp_async_wait<WG_STAGES - 1>();
-        fence_proxy_async();
-        mbar_arrive(&full[(g - (WG_STAGES - 1)) % WG_STAGES]);
-      }
-      if (warp == 0) WG_TRACE(2);
-      ++g;
     }
-    // drain: groups g-2, g-1 (for 3 stages) are still pending
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (int k = (g >= WG_STAGES - 1 ? g - (WG_STAGES - 1) : 0); k < g; ++k) mbar_arrive(&full[k % WG_STAGES]);
+    __syncwarp();
   } else if (warp == WG_MMA_WARP) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, N, /*a_mn=*/true, /*b_mn=*/true);
@@ -125,12 +109,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
         mbar_wait(&full[stage], (uint32_t)((g / WG_STAGES) & 1));
         WG_TRACE(3);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes), sg = sa + a_bytes;
+        const uint32_t sa = base + (uint32_t)stage * stage_bytes, sg = sa + a_bytes;
         for (int t = 0; t < mt; ++t)
+#pragma unroll
           for (int ks = 0; ks < WG_PT / 16; ++ks) {
-            const uint64_t adesc = make_smem_desc(sa + (uint32_t)t * 16u * WG_PT * 16u + (uint32_t)ks * 256u, 128u,
-                                                  WG_PT * 16u);
-            const uint64_t bdesc = make_smem_desc(sg + (uint32_t)ks * 256u, 128u, WG_PT * 16u);
+            // MN-major SW64: LBO = next 32-channel atom, SBO = next 8 positions, K=16 step = 1024 B
+            const uint64_t adesc = tg::make_desc_sw(sa + (uint32_t)t * 4u * WG_ATOM + (uint32_t)ks * 1024u, WG_ATOM, 512u, 4u);
+            const uint64_t bdesc = tg::make_desc_sw(sg + (uint32_t)ks * 1024u, WG_ATOM, 512u, 4u);
             umma_bf16(tmem_base + (uint32_t)(t * N), adesc, bdesc, idesc, (g == 0 && ks == 0) ? 0u : 1u);
           }
         umma_commit(&empty[stage]);
@@ -140,7 +125,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       umma_commit(tfull);
     }
     __syncwarp();
-  } else {
+  } else if (warp > WG_MMA_WARP) {
     // ===================== epilogue: one pass at the end =====================
     const int quad = warp & 3;
     const bool any = blockIdx.x < p.n_tiles;
@@ -188,6 +173,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------ dadj
+constexpr int WG_PRODUCERS = 128;    // dadj: warps 0-3 are cp.async producers
 constexpr int DJ_SLABS = 4;          // slabs per stage
 constexpr int DJ_STAGES = 3;
 
@@ -330,25 +316,59 @@ static int sm_count() {
 int wgrad_tc_supported(int n_chunks, int N) {
   if (n_chunks < 1 || n_chunks > WG_MAX_CHUNKS || (N != 32 && N != 64)) return 0;
   int mt = (32 * n_chunks + 1 + 127) / 128;
-  size_t stage = (size_t)mt * 16 * WG_PT * 16 + (size_t)(N / 8) * WG_PT * 16;
-  return (mt * N <= 256 && WG_STAGES * stage + 512 <= 227 * 1024) ? 1 : 0;
+  size_t stage = (size_t)mt * 4 * WG_ATOM + (size_t)(N / 32) * WG_ATOM;
+  return (mt * N <= 256 && WG_STAGES * stage + 2048 <= 227 * 1024) ? 1 : 0;
 }
 
 int launch_wgrad_tc(WgParams& p, cudaStream_t st) {
   if (p.P <= 0) return 0;
   GWN_REQUIRE(wgrad_tc_supported(p.n_chunks, p.N), "wgrad_tc: unsupported shape (chunks=%d, N=%d)", p.n_chunks, p.N);
   GWN_REQUIRE(p.P < (1ll << 31), "wgrad_tc: too many positions");
-  p.n_tiles = (int)cdiv(p.P, WG_PT);
   {
     const char* e = getenv("GWN_WG_TRACE");
     p.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
   }
+  bool flat = true;    // every chunk has the output's own row structure: tile the flat position axis
+  for (int q = 0; q < p.n_chunks; ++q)
+    if (p.ch[q].rows_per_n != p.rows_per_n_out || p.ch[q].row_off != 0) flat = false;
+  const long long n_real = p.P / p.rows_per_n_out;
+  GWN_REQUIRE(n_real * p.rows_per_n_out == p.P, "wgrad_tc: P is not a whole number of samples");
+  const long long rows_out = flat ? p.P : p.rows_per_n_out;
+  p.n_samples = flat ? 1 : (int)n_real;
+  p.tiles_per_n = (int)cdiv(rows_out, WG_PT);
+  p.n_tiles = p.n_samples * p.tiles_per_n;
+  WgMaps maps;
+  int n_maps = 0;
+  struct Key { const bf16* base; long long rows; int pitch; } keys[WG_MAX_CHUNKS];
+  for (int q = 0; q < p.n_chunks; ++q) {
+    const WgChunk& c = p.ch[q];
+    const long long rows = flat ? p.P : c.rows_per_n;
+    int m = -1;
+    for (int i = 0; i < n_maps; ++i)
+      if (keys[i].base == c.base && keys[i].rows == rows && keys[i].pitch == c.pitch) m = i;
+    if (m < 0) {
+      m = n_maps++;
+      keys[m] = Key{c.base, rows, c.pitch};
+      if (int rc = tg_map_rows3d(&maps.a[m], c.base, (uint64_t)rows, (uint64_t)(flat ? 1 : n_real), (uint64_t)c.pitch, WG_PT))
+        return rc;
+    }
+    p.map_of[q] = m;
+    GWN_REQUIRE(c.row_off > -(1ll << 30) && c.row_off < (1ll << 30), "wgrad_tc: row offset out of range");
+    p.row_off[q] = (int)c.row_off;
+  }
+  for (int i = n_maps; i < WG_MAX_CHUNKS; ++i) maps.a[i] = maps.a[0];
+  for (int j = 0; j < 2; ++j) {
+    const int jj = j < p.N / 32 ? j : 0;
+    if (int rc = tg_map_rows3d(&maps.g[j], p.G + 32 * jj, (uint64_t)rows_out, (uint64_t)(flat ? 1 : n_real),
+                               (uint64_t)p.g_pitch, WG_PT))
+      return rc;
+  }
   int mt = (32 * p.n_chunks + 1 + 127) / 128;
-  size_t stage = (size_t)mt * 16 * WG_PT * 16 + (size_t)(p.N / 8) * WG_PT * 16;
-  size_t smem = WG_STAGES * stage + 512;
+  size_t stage = (size_t)mt * 4 * WG_ATOM + (size_t)(p.N / 32) * WG_ATOM;
+  size_t smem = WG_STAGES * stage + 1024 + 1024;
   int sms = sm_count();
   int grid = p.n_tiles < sms ? p.n_tiles : sms;
-  wgrad_tc_kernel<<<grid, WG_THREADS, smem, st>>>(p);
+  wgrad_tc_kernel<<<grid, WG_THREADS, smem, st>>>(maps, p);
   GWN_LAUNCHED();
   return 0;
 }

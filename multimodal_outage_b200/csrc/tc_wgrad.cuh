@@ -27,6 +27,10 @@ struct WgParams {
   const float* shift;
   int n_tiles;
   long long* trace;         // optional debug timeline of CTA 0 (GWN_WG_TRACE)
+  // filled by the launcher (TMA tiling: a K tile is 64 consecutive rows of one sample)
+  int tiles_per_n, n_samples;
+  int map_of[WG_MAX_CHUNKS];
+  int row_off[WG_MAX_CHUNKS];
 };
 
 struct DadjTerm { const bf16* X; const bf16* G; };   // both [slabs, V, 32] contiguous slots

@@ -63,6 +63,22 @@ int tg_map_slabs(CUtensorMap* map, const void* base, uint64_t V, uint64_t slabs,
   return 0;
 }
 
+int tg_map_rows3d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t n, uint64_t pitch, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  GWN_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  GWN_REQUIRE((reinterpret_cast<uintptr_t>(base) % 16) == 0 && (pitch * 2) % 16 == 0 && box_rows <= 256,
+              "tma rows map: unaligned tensor");
+  cuuint64_t dims[3] = {32, rows, n};
+  cuuint64_t strides[2] = {pitch * 2, rows * pitch * 2};
+  cuuint32_t box[3] = {32, box_rows, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GWN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(rows3d) failed: %d", (int)r);
+  return 0;
+}
+
 void tg_operand(TgOperand& o, int mode, int rows) {
   o.mode = mode;
   if (mode == TG_K_SW128) {            // [rows][64 k] : row = 128 B, 8-row atoms of 1024 B

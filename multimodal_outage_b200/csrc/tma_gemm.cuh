@@ -237,6 +237,8 @@ int tg_map_slabs(CUtensorMap* map, const void* base, uint64_t V, uint64_t slabs,
 inline int tg_map_rows(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_rows) {
   return tg_map_2d(map, base, cols, rows, pitch * 2, 64, box_rows);
 }
+// channels-last activation [n][rows][32 of `pitch` channels] -> 3-D map {32, rows, n}, box {32, box_rows, 1}, 64B swizzle
+int tg_map_rows3d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t n, uint64_t pitch, uint32_t box_rows);
 int tg_sm_count();
 
 template <typename Epi>
