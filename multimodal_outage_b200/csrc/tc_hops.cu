@@ -6,26 +6,32 @@
 // K = input node v (padded to a multiple of 16).
 //   A operand  : the support / its square / their transposes, bf16, RESIDENT in shared memory for the whole
 //                kernel, K-major no-swizzle canonical layout (built once per forward by hop_mats_prep_kernel).
-//   B operand  : one channels-last activation tile [8 slabs][V][32] streamed HBM -> smem with 16-byte cp.async
-//                straight into the MN-major no-swizzle canonical layout (no TMA tensor map: the tile is a
-//                gather of 64-byte rows out of a 448-byte-pitch concat buffer, with zero-filled K padding).
+//   B operand  : one channels-last activation tile [8 slabs][Kp nodes][32 ch] brought in by ONE TMA box per load
+//                (3-D tensor map {32 ch, V nodes, slabs}: nodes >= V and slabs past the end are zero-filled), 64B
+//                swizzled = MN-major SWIZZLE_64B operand, one swizzle atom column per slab.
 //   D          : fp32 in TMEM, two 256-column accumulators so the epilogue of one output overlaps the MMAs of
 //                the next.  Epilogue: tcgen05.ld -> (+ add-in) -> bf16 -> 64-byte stores into the concat slot.
-// Roles (416 threads): warps 0-3 producers, warp 4 lane 0 MMA issuer (+TMEM alloc), warps 5-12 epilogue
+// Roles (416 threads): warp 0 lane 0 TMA producer, warp 4 lane 0 MMA issuer (+TMEM alloc), warps 5-12 epilogue
 // (two warps per TMEM lane quadrant, each draining 4 of the 8 slabs of an accumulator, loads issued in pairs).
 // Persistent: grid = min(tiles, SMs); each CTA walks tiles of 8 slabs.
 #include "tc.cuh"
 #include "tc_hops.cuh"
+#include "tma_gemm.cuh"
 
 namespace gwn {
 
-__global__ void __launch_bounds__(TH_THREADS, 1) hops_tc_kernel(const __grid_constant__ HopParams p) {
+struct HopMaps { CUtensorMap m[TH_MAX_STEPS]; };
+
+__global__ void __launch_bounds__(TH_THREADS, 1) hops_tc_kernel(const __grid_constant__ HopMaps maps,
+                                                                const __grid_constant__ HopParams p) {
   using namespace tc;
-  extern __shared__ __align__(1024) uint8_t smem[];
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Kp = p.Kp, V = p.V;
   const uint32_t mat_bytes = (uint32_t)(Kp / 8) * 2048u;
-  const uint32_t stage_bytes = 32u * (uint32_t)Kp * 16u;
+  const uint32_t stage_bytes = 8u * (uint32_t)Kp * 64u;      // [8 slabs][Kp nodes][64 B]
   uint8_t* mats_s = smem;
   uint8_t* stage_s = smem + (size_t)p.n_mats * mat_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage_s + 2 * (size_t)stage_bytes);
@@ -37,7 +43,7 @@ __global__ void __launch_bounds__(TH_THREADS, 1) hops_tc_kernel(const __grid_con
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&full[i], TH_PRODUCERS);
+      mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 32 * TH_EPI_WARPS);
@@ -59,45 +65,22 @@ __global__ void __launch_bounds__(TH_THREADS, 1) hops_tc_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < TH_MMA_WARP) {
-    // ===================== producers: cp.async tiles into the MN-major canonical layout =====================
-    int g = 0;
-    const int cg = tid & 3, vv = tid >> 2;  // this thread's 16-byte column group and first K row
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      const long long slab0 = (long long)tile * 8;
-      for (int si = 0; si < p.n_steps; ++si) {
-        const HopStep st = p.steps[si];
-        if (!(st.flags & TH_LOAD)) continue;
-        const int stage = g & 1, phase = (g >> 1) & 1;
-        mbar_wait(&empty[stage], (uint32_t)(phase ^ 1));
-        const bf16* base = p.in[st.in_buf] + st.in_slot * p.slot_stride[st.in_buf];
-        const int pitch = p.in_pitch[st.in_buf];
-        const uint32_t sdst = smem_u32(stage_s + (size_t)stage * stage_bytes);
-#pragma unroll 2
-        for (int s = 0; s < 8; ++s) {
-          const long long slab = slab0 + s;
-          const bool sok = slab < p.slabs;
-          const bf16* srow = base + slab * V * (long long)pitch + cg * 8;
-          const uint32_t drow = sdst + (uint32_t)((s * 4 + cg) * Kp) * 16u;
-          for (int v = vv; v < Kp; v += TH_PRODUCERS / 4) {
-            const bool ok = sok && (v < V);
-            cp_async16(drow + (uint32_t)v * 16u, ok ? srow + (long long)v * pitch : base, ok ? 16u : 0u);
-          }
+  if (warp == 0) {
+    // ===================== TMA producer (one thread) =====================
+    if (lane == 0) {
+      int g = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int si = 0; si < p.n_steps; ++si) {
+          if (!(p.steps[si].flags & TH_LOAD)) continue;
+          const int stage = g & 1, phase = (g >> 1) & 1;
+          mbar_wait(&empty[stage], (uint32_t)(phase ^ 1));
+          tg::mbar_expect_tx(&full[stage], stage_bytes);
+          tg::tma_3d(smem_u32(stage_s + (size_t)stage * stage_bytes), &maps.m[si], 0, 0, tile * 8, &full[stage]);
+          ++g;
         }
-        cp_async_commit();
-        if (g > 0) {
-          cp_async_wait<1>();
-          fence_proxy_async();
-          mbar_arrive(&full[(g - 1) & 1]);
-        }
-        ++g;
       }
     }
-    if (g > 0) {
-      cp_async_wait<0>();
-      fence_proxy_async();
-      mbar_arrive(&full[(g - 1) & 1]);
-    }
+    __syncwarp();
   } else if (warp == TH_MMA_WARP) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
@@ -120,7 +103,7 @@ __global__ void __launch_bounds__(TH_THREADS, 1) hops_tc_kernel(const __grid_con
           const uint32_t d = tmem_base + (uint32_t)st.acc * 256u;
           for (int ks = 0; ks < Kp / 16; ++ks) {
             const uint64_t adesc = make_smem_desc(a0 + (uint32_t)ks * 4096u, 2048u, 128u);
-            const uint64_t bdesc = make_smem_desc(b0 + (uint32_t)ks * 256u, 128u, (uint32_t)Kp * 16u);
+            const uint64_t bdesc = tg::make_desc_sw(b0 + (uint32_t)ks * 1024u, (uint32_t)Kp * 64u, 512u, 4u);
             umma_bf16(d, adesc, bdesc, idesc, ((st.flags & TH_FIRST) && ks == 0) ? 0u : 1u);
           }
           if (st.flags & TH_RELEASE) umma_commit(&empty[stage]);
@@ -132,7 +115,7 @@ __global__ void __launch_bounds__(TH_THREADS, 1) hops_tc_kernel(const __grid_con
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp > TH_MMA_WARP) {
     // ===================== epilogue: TMEM -> registers -> (+add) -> bf16 -> concat slot =====================
     const int quad = warp & 3;
     const int half = (warp - (TH_MMA_WARP + 1)) >> 2;   // which 4 slabs of the accumulator this warp drains
@@ -241,7 +224,7 @@ static int g_sm_count = 0;
 int hops_tc_supported(int V, int n_mats) {
   if (V > 128 || n_mats > TH_MAX_MATS) return 0;
   int Kp = ((V + 15) / 16) * 16;
-  size_t need = (size_t)n_mats * (Kp / 8) * 2048 + 2 * (size_t)32 * Kp * 16 + 128;
+  size_t need = (size_t)n_mats * (Kp / 8) * 2048 + 2 * (size_t)8 * Kp * 64 + 1024 + 128;
   return need <= 227 * 1024 ? 1 : 0;
 }
 
@@ -252,7 +235,19 @@ int launch_hops_tc(HopParams& p, cudaStream_t st) {
   GWN_REQUIRE(p.n_steps >= 1 && p.n_steps <= TH_MAX_STEPS && p.n_outs <= TH_MAX_OUTS, "hops_tc: too many steps");
   GWN_REQUIRE(hops_tc_supported(p.V, p.n_mats), "hops_tc: V=%d with %d resident matrices does not fit in smem", p.V,
               p.n_mats);
-  size_t smem = (size_t)p.n_mats * (p.Kp / 8) * 2048 + 2 * (size_t)32 * p.Kp * 16 + 128;
+  size_t smem = (size_t)p.n_mats * (p.Kp / 8) * 2048 + 2 * (size_t)8 * p.Kp * 64 + 1024 + 128;
+  HopMaps maps;
+  bool have = false;
+  for (int si = 0; si < p.n_steps; ++si) {
+    const HopStep& hs = p.steps[si];
+    if (!(hs.flags & TH_LOAD)) { if (have) maps.m[si] = maps.m[0]; continue; }
+    const bf16* base = p.in[hs.in_buf] + hs.in_slot * p.slot_stride[hs.in_buf];
+    if (int rc = tg_map_rows3d_box(&maps.m[si], base, (uint64_t)p.V, (uint64_t)p.slabs, (uint64_t)p.in_pitch[hs.in_buf],
+                                   (uint32_t)p.Kp, 8))
+      return rc;
+    if (!have) { for (int j = 0; j < si; ++j) maps.m[j] = maps.m[si]; have = true; }
+  }
+  for (int si = p.n_steps; si < TH_MAX_STEPS; ++si) maps.m[si] = maps.m[0];
   if (g_sm_count == 0) {
     int dev = 0;
     GWN_CUDA(cudaGetDevice(&dev));
@@ -260,7 +255,7 @@ int launch_hops_tc(HopParams& p, cudaStream_t st) {
     GWN_CUDA(cudaFuncSetAttribute(hops_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   }
   int grid = p.n_tiles < g_sm_count ? p.n_tiles : g_sm_count;
-  hops_tc_kernel<<<grid, TH_THREADS, smem, st>>>(p);
+  hops_tc_kernel<<<grid, TH_THREADS, smem, st>>>(maps, p);
   GWN_LAUNCHED();
   return 0;
 }

@@ -19,21 +19,21 @@
 
 namespace gwn {
 
-constexpr int WG_PT = 64;            // positions per K tile (4 MMA K-steps)
-constexpr int WG_STAGES = 4;
+constexpr int WG_PT = 128;           // positions per K tile (8 MMA K-steps): 8 KB per TMA box
+constexpr int WG_MAX_STAGES = 4;
 constexpr int WG_MMA_WARP = 4;
 constexpr int WG_THREADS = 32 * 9;   // warp 0 TMA producer, warp 4 MMA, warps 5-8 epilogue
-constexpr uint32_t WG_ATOM = WG_PT * 64u;     // one 32-channel operand atom: [64 positions][64 B], 64B-swizzled
+constexpr uint32_t WG_ATOM = WG_PT * 64u;     // one 32-channel operand atom: [128 positions][64 B], 64B-swizzled
 
 struct WgMaps { CUtensorMap a[WG_MAX_CHUNKS]; CUtensorMap g[2]; };
 
 #define WG_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && g < 48 && (tid & 31) == 0) p.trace[g * 8 + (slot)] = clock64(); } while (0)
 
 // Operands arrive by TMA: every 32-channel group of A (a temporal tap / concat slot) and of G is one box
-// {32 ch, 64 rows, 1 sample} -> [64][64 B] 64B-swizzled = one MN-major SWIZZLE_64B atom (M or N = channel,
+// {32 ch, 128 rows, 1 sample} -> [128][64 B] 64B-swizzled = one MN-major SWIZZLE_64B atom (M or N = channel,
 // K = position); rows outside the sample are zero-filled by TMA, so they add nothing to the sums.
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgMaps maps,
-                                                                 const __grid_constant__ WgParams p) {
+                                                                 const __grid_constant__ WgParams p, int WG_STAGES) {
   using namespace tc;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -47,11 +47,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   const uint32_t g_bytes = (uint32_t)(N / 32) * WG_ATOM;
   const uint32_t stage_bytes = a_bytes + g_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)WG_STAGES * stage_bytes);
-  uint64_t* full = bars;                 // [STAGES]
-  uint64_t* empty = bars + WG_STAGES;    // [STAGES]
-  uint64_t* tfull = bars + 2 * WG_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WG_STAGES + 1);
-  float* db_s = reinterpret_cast<float*>(bars + 2 * WG_STAGES + 2);   // [N]
+  uint64_t* full = bars;                     // [STAGES]
+  uint64_t* empty = bars + WG_MAX_STAGES;    // [STAGES]
+  uint64_t* tfull = bars + 2 * WG_MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WG_MAX_STAGES + 1);
+  float* db_s = reinterpret_cast<float*>(bars + 2 * WG_MAX_STAGES + 2);   // [N]
 
   if (tid == 0) {
     for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -317,7 +317,7 @@ int wgrad_tc_supported(int n_chunks, int N) {
   if (n_chunks < 1 || n_chunks > WG_MAX_CHUNKS || (N != 32 && N != 64)) return 0;
   int mt = (32 * n_chunks + 1 + 127) / 128;
   size_t stage = (size_t)mt * 4 * WG_ATOM + (size_t)(N / 32) * WG_ATOM;
-  return (mt * N <= 256 && WG_STAGES * stage + 2048 <= 227 * 1024) ? 1 : 0;
+  return (mt * N <= 256 && 2 * stage + 2048 <= 224 * 1024) ? 1 : 0;
 }
 
 int launch_wgrad_tc(WgParams& p, cudaStream_t st) {
@@ -365,10 +365,12 @@ int launch_wgrad_tc(WgParams& p, cudaStream_t st) {
   }
   int mt = (32 * p.n_chunks + 1 + 127) / 128;
   size_t stage = (size_t)mt * 4 * WG_ATOM + (size_t)(p.N / 32) * WG_ATOM;
-  size_t smem = WG_STAGES * stage + 1024 + 1024;
+  int stages = (int)((224 * 1024 - 2048) / stage);
+  if (stages > WG_MAX_STAGES) stages = WG_MAX_STAGES;
+  size_t smem = stages * stage + 1024 + 1024;
   int sms = sm_count();
   int grid = p.n_tiles < sms ? p.n_tiles : sms;
-  wgrad_tc_kernel<<<grid, WG_THREADS, smem, st>>>(maps, p);
+  wgrad_tc_kernel<<<grid, WG_THREADS, smem, st>>>(maps, p, stages);
   GWN_LAUNCHED();
   return 0;
 }

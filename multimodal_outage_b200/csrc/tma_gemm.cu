@@ -64,13 +64,18 @@ int tg_map_slabs(CUtensorMap* map, const void* base, uint64_t V, uint64_t slabs,
 }
 
 int tg_map_rows3d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t n, uint64_t pitch, uint32_t box_rows) {
+  return tg_map_rows3d_box(map, base, rows, n, pitch, box_rows, 1);
+}
+
+int tg_map_rows3d_box(CUtensorMap* map, const void* base, uint64_t rows, uint64_t n, uint64_t pitch, uint32_t box_rows,
+                      uint32_t box_n) {
   EncodeTiledFn fn = encode_fn();
   GWN_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
   GWN_REQUIRE((reinterpret_cast<uintptr_t>(base) % 16) == 0 && (pitch * 2) % 16 == 0 && box_rows <= 256,
               "tma rows map: unaligned tensor");
   cuuint64_t dims[3] = {32, rows, n};
   cuuint64_t strides[2] = {pitch * 2, rows * pitch * 2};
-  cuuint32_t box[3] = {32, box_rows, 1};
+  cuuint32_t box[3] = {32, box_rows, box_n};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

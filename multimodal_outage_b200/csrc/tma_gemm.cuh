@@ -239,6 +239,9 @@ inline int tg_map_rows(CUtensorMap* map, const void* base, uint64_t rows, uint64
 }
 // channels-last activation [n][rows][32 of `pitch` channels] -> 3-D map {32, rows, n}, box {32, box_rows, 1}, 64B swizzle
 int tg_map_rows3d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t n, uint64_t pitch, uint32_t box_rows);
+// same view, box {32, box_rows, box_n} (several samples / slabs per box)
+int tg_map_rows3d_box(CUtensorMap* map, const void* base, uint64_t rows, uint64_t n, uint64_t pitch, uint32_t box_rows,
+                      uint32_t box_n);
 int tg_sm_count();
 
 template <typename Epi>
