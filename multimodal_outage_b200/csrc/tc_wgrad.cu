@@ -173,20 +173,26 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------ dadj
-constexpr int WG_PRODUCERS = 128;    // dadj: warps 0-3 are cp.async producers
 constexpr int DJ_SLABS = 4;          // slabs per stage
 constexpr int DJ_STAGES = 3;
 
-__global__ void __launch_bounds__(WG_THREADS, 1) dadj_tc_kernel(const __grid_constant__ DadjParams p) {
+struct DjMaps { CUtensorMap x[4]; CUtensorMap g[4]; };
+
+// Both operands K-major (channels contiguous): per stage two TMA boxes {32 ch, rows, 4 slabs} -> [4][rows][64 B],
+// 64B-swizzled; nodes >= V and slabs past the end are zero-filled by TMA.
+__global__ void __launch_bounds__(WG_THREADS, 1) dadj_tc_kernel(const __grid_constant__ DjMaps maps,
+                                                                const __grid_constant__ DadjParams p) {
   using namespace tc;
-  extern __shared__ __align__(1024) uint8_t smem[];
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int V = p.V;
   const int Np = ((V + 15) / 16) * 16;                   // MMA N (w), multiple of 16
-  // per slab: X image [4 kc][128 rows][16 B] = 8 KB, G image [4 kc][Np rows][16 B]
-  const uint32_t x_bytes = 4u * 128u * 16u, g_bytes = 4u * (uint32_t)Np * 16u;
-  const uint32_t slab_bytes = x_bytes + g_bytes;
-  const uint32_t stage_bytes = DJ_SLABS * slab_bytes;
+  const uint32_t x_slab = 128u * 64u, g_slab = (uint32_t)Np * 64u;
+  const uint32_t x_bytes = DJ_SLABS * x_slab, g_bytes = (DJ_SLABS * g_slab + 1023u) & ~1023u;
+  const uint32_t stage_bytes = x_bytes + g_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)DJ_STAGES * stage_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + DJ_STAGES;
@@ -194,82 +200,57 @@ __global__ void __launch_bounds__(WG_THREADS, 1) dadj_tc_kernel(const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * DJ_STAGES + 1);
 
   if (tid == 0) {
-    for (int i = 0; i < DJ_STAGES; ++i) { mbar_init(&full[i], WG_PRODUCERS); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < DJ_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(tfull, 1);
     fence_barrier_init();
   }
   const uint32_t tmem_cols = Np <= 32 ? 32u : Np <= 64 ? 64u : 128u;
   if (warp == WG_MMA_WARP) tmem_alloc(tmem_slot, tmem_cols);
-  {  // zero everything once: rows >= V of every image must stay zero
-    uint4* a = reinterpret_cast<uint4*>(smem);
-    for (int i = tid; i < (int)(DJ_STAGES * stage_bytes / 16); i += WG_THREADS) a[i] = make_uint4(0u, 0u, 0u, 0u);
-    fence_proxy_async();
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int steps_total_per_tile = p.n_terms;   // each (tile, term) is one pipeline stage fill
 
-  if (warp < WG_MMA_WARP) {
-    const int kc = tid & 3, r0 = tid >> 2;   // 16-byte K piece kc of rows r0, r0+32, ...
-    int g = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      for (int term = 0; term < steps_total_per_tile; ++term) {
-        const int stage = g % DJ_STAGES, phase = (g / DJ_STAGES) & 1;
-        mbar_wait(&empty[stage], (uint32_t)(phase ^ 1));
-        const uint32_t sbase = smem_u32(smem + (size_t)stage * stage_bytes);
-        const bf16* X = p.t[term].X;
-        const bf16* G = p.t[term].G;
-        for (int sl = 0; sl < DJ_SLABS; ++sl) {
-          const long long slab = (long long)tile * DJ_SLABS + sl;
-          const bool sok = slab < p.slabs;
-          const uint32_t sx = sbase + (uint32_t)sl * slab_bytes, sg = sx + x_bytes;
-          for (int v = r0; v < V; v += WG_PRODUCERS / 4) {
-            const long long off = (slab * V + v) * 32 + kc * 8;
-            cp_async16(sx + (uint32_t)(kc * 128 + v) * 16u, sok ? X + off : X, sok ? 16u : 0u);
-            cp_async16(sg + (uint32_t)(kc * Np + v) * 16u, sok ? G + off : G, sok ? 16u : 0u);
-          }
+  if (warp == 0) {
+    if (lane == 0) {
+      int g = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int term = 0; term < p.n_terms; ++term, ++g) {
+          const int stage = g % DJ_STAGES, phase = (g / DJ_STAGES) & 1;
+          mbar_wait(&empty[stage], (uint32_t)(phase ^ 1));
+          tg::mbar_expect_tx(&full[stage], x_bytes + DJ_SLABS * g_slab);
+          const uint32_t sx = base + (uint32_t)stage * stage_bytes;
+          tg::tma_3d(sx, &maps.x[term], 0, 0, tile * DJ_SLABS, &full[stage]);
+          tg::tma_3d(sx + x_bytes, &maps.g[term], 0, 0, tile * DJ_SLABS, &full[stage]);
         }
-        cp_async_commit();
-        if (g >= DJ_STAGES - 1) {
-          cp_async_wait<DJ_STAGES - 1>();
-          fence_proxy_async();
-          mbar_arrive(&full[(g - (DJ_STAGES - 1)) % DJ_STAGES]);
-        }
-        ++g;
       }
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (int k = (g >= DJ_STAGES - 1 ? g - (DJ_STAGES - 1) : 0); k < g; ++k) mbar_arrive(&full[k % DJ_STAGES]);
+    __syncwarp();
   } else if (warp == WG_MMA_WARP) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, Np, /*a_mn=*/false, /*b_mn=*/false);
       int g = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        for (int term = 0; term < steps_total_per_tile; ++term) {
+        for (int term = 0; term < p.n_terms; ++term, ++g) {
           const int stage = g % DJ_STAGES;
           mbar_wait(&full[stage], (uint32_t)((g / DJ_STAGES) & 1));
           tc_fence_after();
-          const uint32_t sbase = smem_u32(smem + (size_t)stage * stage_bytes);
-          for (int sl = 0; sl < DJ_SLABS; ++sl) {
-            const uint32_t sx = sbase + (uint32_t)sl * slab_bytes, sg = sx + x_bytes;
+          const uint32_t sx = base + (uint32_t)stage * stage_bytes, sg = sx + x_bytes;
+#pragma unroll
+          for (int sl = 0; sl < DJ_SLABS; ++sl)
+#pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
-              // K-major: the two 16-byte K pieces of a K-step are LBO apart, 8-row groups SBO = 128 B apart
-              const uint64_t adesc = make_smem_desc(sx + (uint32_t)ks * 2u * 128u * 16u, 128u * 16u, 128u);
-              const uint64_t bdesc = make_smem_desc(sg + (uint32_t)ks * 2u * (uint32_t)Np * 16u, (uint32_t)Np * 16u, 128u);
+              const uint64_t adesc = tg::make_desc_sw(sx + (uint32_t)sl * x_slab + (uint32_t)ks * 32u, 16u, 512u, 4u);
+              const uint64_t bdesc = tg::make_desc_sw(sg + (uint32_t)sl * g_slab + (uint32_t)ks * 32u, 16u, 512u, 4u);
               umma_bf16(tmem_base, adesc, bdesc, idesc, (g == 0 && sl == 0 && ks == 0) ? 0u : 1u);
             }
-          }
           umma_commit(&empty[stage]);
-          ++g;
         }
       }
       umma_commit(tfull);
     }
     __syncwarp();
-  } else {
+  } else if (warp > WG_MMA_WARP) {
     const int quad = warp & 3;
     if (blockIdx.x < p.n_tiles) {
       mbar_wait(tfull, 0u);
@@ -379,13 +360,19 @@ int launch_dadj_tc(DadjParams& p, cudaStream_t st) {
   if (p.slabs <= 0) return 0;
   GWN_REQUIRE(p.V <= 128 && p.n_terms >= 1 && p.n_terms <= 4, "dadj_tc: V=%d unsupported", p.V);
   p.n_tiles = (int)cdiv(p.slabs, DJ_SLABS);
-  int Np = ((p.V + 15) / 16) * 16;
-  size_t stage = (size_t)DJ_SLABS * (4 * 128 * 16 + 4 * Np * 16);
-  size_t smem = DJ_STAGES * stage + 256;
+  const int Np = ((p.V + 15) / 16) * 16;
+  const size_t x_bytes = (size_t)DJ_SLABS * 128 * 64, g_bytes = ((size_t)DJ_SLABS * Np * 64 + 1023) & ~(size_t)1023;
+  const size_t smem = DJ_STAGES * (x_bytes + g_bytes) + 1024 + 256;
   GWN_REQUIRE(smem <= 227 * 1024, "dadj_tc: smem");
+  DjMaps maps;
+  for (int t = 0; t < 4; ++t) {
+    const int tt = t < p.n_terms ? t : 0;
+    if (int rc = tg_map_rows3d_box(&maps.x[t], p.t[tt].X, (uint64_t)p.V, (uint64_t)p.slabs, 32, 128, DJ_SLABS)) return rc;
+    if (int rc = tg_map_rows3d_box(&maps.g[t], p.t[tt].G, (uint64_t)p.V, (uint64_t)p.slabs, 32, (uint32_t)Np, DJ_SLABS)) return rc;
+  }
   int sms = sm_count();
   int grid = p.n_tiles < sms ? p.n_tiles : sms;
-  dadj_tc_kernel<<<grid, WG_THREADS, smem, st>>>(p);
+  dadj_tc_kernel<<<grid, WG_THREADS, smem, st>>>(maps, p);
   GWN_LAUNCHED();
   return 0;
 }
