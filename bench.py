@@ -362,16 +362,23 @@ def run_ours(args):
     x_static, y_static = torch.empty_like(xs[0]), torch.empty_like(ys[0])
     loss_static = torch.zeros((), device=dev)
 
-    def step_eager(x, y):
+    def fwd_bwd(x, y):
         opt.zero_grad(set_to_none=True)
         loss = loss_fn(model(x), y)
         loss.backward()
+        return loss
+
+    def step_eager(x, y):
+        loss = fwd_bwd(x, y)
         if sync is not None:
             sync.finish()
         opt.step()
         return loss
 
-    use_graph = (world == 1) and not args.no_graph
+    # CUDA graph: N=1 captures the whole step (fwd + loss + bwd + Adam).  N>1 captures fwd + loss + bwd + the
+    # device-side packing of gradients into the flat buckets; the ONE NCCL exchange and the fused Adam step are
+    # issued eagerly after each replay (a handful of launches), so no collective lives inside a captured graph.
+    use_graph = not args.no_graph
     graph = None
     launches_per_step = None
     for _ in range(3):                                        # eager warm-up (allocator, rng state, Adam state)
@@ -382,21 +389,37 @@ def run_ours(args):
     torch.cuda.synchronize()
     launches_per_step = _lib.lib().gwn_launch_count() - c0
     if use_graph:
+        if sync is not None:
+            sync.remove()                                     # hooks off: gradients are packed explicitly
+            sync.overlap = False
+
+        def captured(x, y):
+            if sync is None:
+                return step_eager(x, y)
+            loss = fwd_bwd(x, y)
+            sync.pack()
+            return loss
         graph = torch.cuda.CUDAGraph()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             x_static.copy_(xs[0]); y_static.copy_(ys[0])
-            step_eager(x_static, y_static)
+            captured(x_static, y_static)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         with torch.cuda.graph(graph):
-            loss_static.copy_(step_eager(x_static, y_static).detach())
+            loss_static.copy_(captured(x_static, y_static).detach())
+
+    def replay():
+        graph.replay()
+        if sync is not None:
+            sync.reduce()
+            opt.step()
 
     def step_resident(i):
         if graph is not None:
             x_static.copy_(xs[i % R]); y_static.copy_(ys[i % R])
-            graph.replay()
+            replay()
             return loss_static
         return step_eager(xs[i % R], ys[i % R])
 
@@ -404,7 +427,7 @@ def run_ours(args):
         # host (pinned) -> device copy of this step's inputs, the step, device -> host read of the loss
         if graph is not None:
             x_static.copy_(xs_host[i % R], non_blocking=True); y_static.copy_(ys_host[i % R], non_blocking=True)
-            graph.replay()
+            replay()
             return float(loss_static.item())
         x = xs_host[i % R].to(dev, non_blocking=True); y = ys_host[i % R].to(dev, non_blocking=True)
         return float(step_eager(x, y).item())

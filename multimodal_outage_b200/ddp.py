@@ -96,6 +96,26 @@ class BucketedGradAllReduce:
                 p.grad = v
             b['pending'] = len(b['params'])
 
+    # -- CUDA-graph friendly split: pack() is pure device copies (capturable with forward+backward), reduce() is the
+    #    one NCCL exchange per step, issued eagerly right after the graph replay.
+    def pack(self):
+        """Copy this step's gradients into the flat buckets and point .grad at the bucket views (no communication)."""
+        for b in self.buckets:
+            grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in b['params']]
+            torch._foreach_copy_(b['views'], grads)
+            for p, v in zip(b['params'], b['views']):
+                p.grad = v
+            b['pending'] = len(b['params'])
+            b['launched'] = False
+
+    def reduce(self):
+        """All-reduce (average) the packed buckets in place."""
+        if self.world > 1:
+            works = [dist.all_reduce(b['flat'], op=dist.ReduceOp.SUM, group=self.group, async_op=True) for b in self.buckets]
+            for w in works:
+                w.wait()
+            torch._foreach_div_([b['flat'] for b in self.buckets], float(self.world))
+
     def grad_bytes(self) -> int:
         return sum(b['flat'].numel() * 4 for b in self.buckets)
 
