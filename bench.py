@@ -247,6 +247,10 @@ def kernel_rooflines(peaks, n):
     peak_tf = peaks.get('bf16_tflops', 1590.0)
     peak_tf_sus = peaks.get('bf16_tflops_sustained', 1400.0)
     src = 'MEASURED_PEAKS.json' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
+    try:
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')))
+    except Exception:
+        traffic = {}
     V, C32 = 67, 32
     L = [13, 12]                                              # config-2 layer 0: Lin 13 -> Lout 12, dilation 1
     N = 512
@@ -280,7 +284,8 @@ def kernel_rooflines(peaks, n):
     roof = {'kernel': 'gcn_fwd_kernel (fused K-hop diffusion + concat + mlp + dropout + residual + BN stats, config-2 '
                       'layer 0: 6144 slabs of 67 nodes; includes its 2 us weight-image prep + stats memset)',
             'bound': 'hbm', 'achieved': byts / (ms * 1e-3) / 1e9, 'peak': peak_bw, 'unit': 'GB/s',
-            'frac': byts / (ms * 1e-3) / 1e9 / peak_bw, 'traffic': None,
+            'frac': byts / (ms * 1e-3) / 1e9 / peak_bw, 'traffic': traffic.get('gcn_fwd_kernel', {}).get('bytes'),
+            'traffic_source': traffic.get('gcn_fwd_kernel', {}).get('source'),
             'algorithmic_bytes_per_launch': byts, 'algorithmic_flops_per_launch': flops, 'ms_per_launch': ms,
             'tensor_tflops': flops / (ms * 1e-3) / 1e12, 'tensor_frac_of_burst_peak': flops / (ms * 1e-3) / 1e12 / peak_tf,
             'note': 'at V=67 the fused contraction has 209 flop/B, right at the ridge (214): HBM time 12.1 us, tensor '
@@ -322,7 +327,9 @@ def kernel_rooflines(peaks, n):
     big_roof = {'kernel': 'tma_gemm_kernel<EpiHopBig> (one diffusion hop at V=3100, 768 slabs: config-3 layer 0)',
                 'bound': 'tensor', 'achieved': tf, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': tf / peak_tf,
                 'frac_of_sustained_peak': tf / peak_tf_sus, 'algorithmic_flops_per_launch': fl, 'ms_per_launch': ms_hop,
-                'traffic': None, 'peak_source': src + ' (burst; kernel timed alone)'}
+                'traffic': traffic.get('tma_gemm_kernel_hop_v3100', {}).get('bytes'),
+                'traffic_source': traffic.get('tma_gemm_kernel_hop_v3100', {}).get('source'),
+                'peak_source': src + ' (burst; kernel timed alone)'}
     return roof, gate_roof, big_roof
 
 
