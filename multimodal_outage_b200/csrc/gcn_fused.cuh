@@ -49,3 +49,36 @@ int launch_gcn_wprep(const float* w_mlp, int n_mats, bf16* w_img, cudaStream_t s
 int launch_gcn_fwd(GcnFwdParams& p, cudaStream_t st);
 
 }  // namespace gwn
+
+// ------------------------------------------------------------------------------------------------------------------
+// Fused diffusion graph convolution, BACKWARD (V <= 80, bf16), supports without gradient (gcn_fused_bwd.cu):
+//   dh   = du . dropout-mask                                                   (graph_wavenet.py:97)
+//   dU_j = M_j^T dh  (j = 1..H),  dU_0 = dh                                    (transposed hops, :60-66)
+//   dz   = sum_j dU_j W_j^T  (+ dz_last on the tail rows)                      (mlp backward, :96)
+//   dW_j = z^T dU_j,  db = sum dh        with z = a . b recomputed on chip     (weight gradients)
+//   dfg  = gate backward of dz:  df = dz b (1 - a^2), dg = dz a b (1 - b)      (:222-226)
+// One kernel per layer replaces zfill + 3 hop launches + drop_bwd + mlp wgrad + dcat GEMM + gate_bwd.
+namespace gwn {
+struct GcnBwdParams {
+  const bf16* du;              // [slabs*V, 32]
+  const bf16* a;               // [slabs*V, 32] tanh(f)
+  const bf16* b;               // [slabs*V, 32] sigmoid(g)
+  const bf16* dz_last;         // [N, Lf, V, 32] or NULL
+  long long RO, last_begin, last_rows;
+  const bf16* mats;            // gwn_hop_mats_prep images
+  int mat_src[GF_MAX_MATS];    // image index of the TRANSPOSED hop j+1 (variants 2, 3)
+  int n_mats;
+  const bf16* wt_img;          // [4*(1+n_mats)][32][8]: (n = c, k = (j, c')) = W_mlp[j*32 + c][c']
+  const bf16* mask;
+  float drop_p;
+  uint64_t seed, offset;
+  const uint64_t* rng;
+  bf16* dfg;                   // out [slabs*V, 64], interleaved (f, g)
+  float* dw_mlp;               // [32*(1+n_mats), 32] fp32, accumulated with atomics (caller zeroes)
+  float* db_mlp;               // [32]
+  int V, Kp, slabs;
+};
+int gcn_bwd_fused_supported(int V, int n_mats);
+int launch_gcn_bwd_wprep(const float* w_mlp, int n_mats, bf16* wt_img, cudaStream_t st);
+int launch_gcn_bwd(GcnBwdParams& p, cudaStream_t st);
+}  // namespace gwn

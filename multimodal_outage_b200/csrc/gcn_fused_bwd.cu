@@ -1,0 +1,398 @@
+// Fused diffusion graph convolution, backward (math in gcn_fused.cuh).  Same machinery as the forward kernel:
+// one persistent CTA per SM walks slabs (one (n,t) pair = V nodes x 32 channels), every support image and the
+// mlp weight image resident in shared memory, intermediates in TMEM / shared memory.
+//
+// Per slab k (buffer b = k & 1):
+//   prep     : du, a, b rows -> dh = du.mask (bf16) into slot 0 of concat buffer b, z = a.b into z tile b  (+ db sums)
+//   MMA      : GEMM H  dU_j = M_j^T dh        (A = transposed support image, B = slot 0, D = 32 TMEM columns per j)
+//   stage    : TMEM(dU_j) -> bf16 -> slots 1..H of concat buffer b
+//   MMA      : GEMM Z  dz = [dh | dU] W^T      (A = concat buffer b as K-major [node][(j,c')], B = W^T image)
+//              GEMM W  dW += [dh | dU]^T z     (A = the SAME bytes as MN-major [(j,c')][node], B = z tile; the
+//                                               accumulator stays in TMEM for the CTA's whole share of slabs)
+//   epilogue : TMEM(dz) + dz_last -> gate backward with a, b -> dfg (bf16, 128 B per node)
+// TMEM columns: dU [0, 32H), dz [192, 224), dW tiles [224, 256) and [256, 288).
+// Warps (16): q0/q1: stage A (w0,w1), stage B (w4,w5), epilogue (w8,w9); q2: stage w6, epilogue w10; q3: MMA w3 and
+// the three prep warps w7, w11, w15 (prep is not tied to a TMEM lane quadrant, q3 holds no node rows for V <= 96).
+#include "gcn_fused.cuh"
+#include "tc.cuh"
+#include "tc_gemm_impl.cuh"   // warp_column_sums
+
+namespace gwn {
+
+constexpr int GB_THREADS = 32 * 16;
+constexpr int GB_MMA = 3;
+
+struct GbLayout {
+  uint32_t mat_bytes, w_off, w_bytes, cat_off, slot_bytes, cat_bytes, z_off, z_bytes, bar_off, total;
+};
+__host__ __device__ inline GbLayout gb_layout(int Kp, int n_mats) {
+  GbLayout L;
+  L.mat_bytes = (uint32_t)(Kp / 8) * (uint32_t)Kp * 16u;       // [Kp/8][Kp rows][16 B]
+  L.w_off = (uint32_t)n_mats * L.mat_bytes;
+  L.w_bytes = 4u * (uint32_t)(1 + n_mats) * 32u * 16u;         // [4(1+H)][32][16 B]
+  L.cat_off = L.w_off + L.w_bytes;
+  L.slot_bytes = 4u * (uint32_t)Kp * 16u;                      // [4 cg][Kp nodes][16 B]
+  L.cat_bytes = (uint32_t)(1 + n_mats) * L.slot_bytes;
+  L.z_off = L.cat_off + 2u * L.cat_bytes;
+  L.z_bytes = L.slot_bytes;
+  L.bar_off = (L.z_off + 2u * L.z_bytes + 4096u + 127u) & ~127u;     // slack: M=128 operand rows past Kp / past slot H
+  L.total = L.bar_off + 256u;
+  return L;
+}
+
+__device__ __forceinline__ uint32_t gb_pack(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void gb_unpack8(const uint4& q, float v[8]) {
+  v[0] = __uint_as_float(q.x << 16); v[1] = __uint_as_float(q.x & 0xFFFF0000u);
+  v[2] = __uint_as_float(q.y << 16); v[3] = __uint_as_float(q.y & 0xFFFF0000u);
+  v[4] = __uint_as_float(q.z << 16); v[5] = __uint_as_float(q.z & 0xFFFF0000u);
+  v[6] = __uint_as_float(q.w << 16); v[7] = __uint_as_float(q.w & 0xFFFF0000u);
+}
+
+template <int NM, int KSTEPS>
+__global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_constant__ GcnBwdParams p) {
+  using namespace tc;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int Kp = 16 * KSTEPS, NU = 32 * (1 + NM);
+  const int V = p.V;
+  const GbLayout L = gb_layout(Kp, NM);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+  uint64_t* buf_empty = bars;           // [2] concat buffer + z tile free (tail MMAs of slab k-2 completed)
+  uint64_t* in_full = bars + 2;         // [2] dh and z tiles written
+  uint64_t* ut_full = bars + 4;         // dU accumulators complete
+  uint64_t* ut_empty = bars + 5;        // dU accumulators drained
+  uint64_t* us_full = bars + 6;         // [2] dU staged in shared memory
+  uint64_t* dz_full = bars + 8;
+  uint64_t* dz_empty = bars + 9;
+  uint64_t* w_full = bars + 10;         // all MMAs of the CTA completed (dW accumulators final)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+  const int nq_stage = (Kp + 31) / 32;
+  const int nq_epi = (V + 31) / 32;
+  const int n_stage_warps = 2 * min(nq_stage, 2) + max(0, nq_stage - 2);
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&buf_empty[i], 1); mbar_init(&in_full[i], 96); mbar_init(&us_full[i], 32 * n_stage_warps);
+    }
+    mbar_init(ut_full, 1); mbar_init(ut_empty, 32 * n_stage_warps);
+    mbar_init(dz_full, 1); mbar_init(dz_empty, 32 * nq_epi);
+    mbar_init(w_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == GB_MMA) tmem_alloc(tmem_slot, 512);
+  {  // resident operands
+    constexpr int pieces = Kp / 8;
+    for (int m = 0; m < NM; ++m) {
+      const uint4* src = reinterpret_cast<const uint4*>(p.mats) + (size_t)p.mat_src[m] * pieces * 128;
+      uint4* dst = reinterpret_cast<uint4*>(smem + (size_t)m * L.mat_bytes);
+      for (int i = tid; i < pieces * Kp; i += GB_THREADS) {
+        const int kc = i / Kp, r = i % Kp;
+        dst[kc * Kp + r] = __ldg(src + kc * 128 + r);
+      }
+    }
+    const uint4* wsrc = reinterpret_cast<const uint4*>(p.wt_img);
+    uint4* wdst = reinterpret_cast<uint4*>(smem + L.w_off);
+    for (int i = tid; i < (int)(L.w_bytes / 16); i += GB_THREADS) wdst[i] = __ldg(wsrc + i);
+    // slack past the buffers is read (as ignored accumulator rows) by the M=128 operands: keep it finite
+    uint4* sl = reinterpret_cast<uint4*>(smem + L.z_off + 2 * L.z_bytes);
+    for (int i = tid; i < 4096 / 16; i += GB_THREADS) sl[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t sbase = smem_u32(smem);
+  const int quad = warp & 3, wq = warp >> 2;
+  constexpr uint32_t TZ = 192u, TW = 224u;      // TMEM columns of dz and dW
+
+  if (warp == GB_MMA) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idescH = make_idesc_bf16(128, 32, false, true);    // matT (K-major) x dh (MN-major)
+      const uint32_t idescZ = make_idesc_bf16(128, 32, false, false);   // cat (K-major) x W^T image (K-major)
+      const uint32_t idescW = make_idesc_bf16(128, 32, true, true);     // cat (MN-major) x z (MN-major)
+      const uint64_t adm = make_smem_desc(0, (uint32_t)Kp * 16u, 128u);           // K-major, K piece stride Kp*16
+      const uint64_t bmn = make_smem_desc(0, 128u, (uint32_t)Kp * 16u);           // MN-major [group][node][16 B]
+      const uint64_t bdw = make_smem_desc(0, 32u * 16u, 128u);                    // W^T image: K piece stride 512 B
+      auto tail = [&](int kk) {
+        const int bb = kk & 1;
+        mbar_wait(&us_full[bb], (uint32_t)((kk >> 1) & 1));
+        mbar_wait(dz_empty, (uint32_t)((kk & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t cat = sbase + L.cat_off + (uint32_t)bb * L.cat_bytes;
+        const uint32_t zt = sbase + L.z_off + (uint32_t)bb * L.z_bytes;
+        const uint64_t a0 = adm + (uint64_t)(cat >> 4), w0 = bdw + (uint64_t)((sbase + L.w_off) >> 4);
+#pragma unroll
+        for (int ks = 0; ks < 2 * (1 + NM); ++ks)
+          umma_bf16(tmem_base + TZ, a0 + (uint64_t)(((uint32_t)(2 * ks) * (uint32_t)Kp * 16u) >> 4),
+                    w0 + (uint64_t)(((uint32_t)(2 * ks) * 512u) >> 4), idescZ, ks == 0 ? 0u : 1u);
+        umma_commit(dz_full);
+        const uint64_t am = bmn + (uint64_t)(cat >> 4), bz = bmn + (uint64_t)(zt >> 4);
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+          for (int ks = 0; ks < KSTEPS; ++ks)
+            umma_bf16(tmem_base + TW + 32u * t, am + (uint64_t)(((uint32_t)(16 * t) * (uint32_t)Kp * 16u + (uint32_t)ks * 256u) >> 4),
+                      bz + (uint64_t)(((uint32_t)ks * 256u) >> 4), idescW, (kk == 0 && ks == 0) ? 0u : 1u);
+        umma_commit(&buf_empty[bb]);
+      };
+      int k = 0;
+      for (long long slab = blockIdx.x; slab < p.slabs; slab += gridDim.x, ++k) {
+        const int bb = k & 1;
+        mbar_wait(&in_full[bb], (uint32_t)((k >> 1) & 1));
+        mbar_wait(ut_empty, (uint32_t)((k & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t cat = sbase + L.cat_off + (uint32_t)bb * L.cat_bytes;
+        const uint64_t a0 = adm + (uint64_t)(sbase >> 4), b0 = bmn + (uint64_t)(cat >> 4);
+#pragma unroll
+        for (int m = 0; m < NM; ++m)
+#pragma unroll
+          for (int ks = 0; ks < KSTEPS; ++ks)
+            umma_bf16(tmem_base + 32u * m,
+                      a0 + (uint64_t)(((uint32_t)m * ((uint32_t)(Kp / 8) * (uint32_t)Kp * 16u) + (uint32_t)(2 * ks) * (uint32_t)Kp * 16u) >> 4),
+                      b0 + (uint64_t)(((uint32_t)ks * 256u) >> 4), idescH, ks == 0 ? 0u : 1u);
+        umma_commit(ut_full);
+        if (k > 0) tail(k - 1);
+      }
+      if (k > 0) tail(k - 1);
+      umma_commit(w_full);
+    }
+    __syncwarp();
+  } else if (quad == 3) {
+    // ===================== prep warps (w7, w11, w15): dh = du . mask -> slot 0, z = a . b -> z tile =====================
+    const int v = (wq - 1) * 32 + lane;          // node row
+    const bool has_row = v < Kp, real = v < V;
+    float dbs[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) dbs[c] = 0.f;
+    uint64_t sd = 0, of = 0;
+    const bool philox = (p.mask == nullptr) && p.drop_p > 0.f;
+    if (philox) { sd = p.rng ? __ldg(p.rng) : p.seed; of = p.rng ? p.offset + __ldg(p.rng + 1) : p.offset; }
+    int k = 0;
+    for (long long slab = blockIdx.x; slab < p.slabs; slab += gridDim.x, ++k) {
+      const int bb = k & 1;
+      const long long pp = slab * V + v;
+      uint4 qd[4], qa[4], qb[4];
+      if (real) {
+        const uint4* s0 = reinterpret_cast<const uint4*>(p.du + pp * 32);
+        const uint4* s1 = reinterpret_cast<const uint4*>(p.a + pp * 32);
+        const uint4* s2 = reinterpret_cast<const uint4*>(p.b + pp * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { qd[j] = __ldg(s0 + j); qa[j] = __ldg(s1 + j); qb[j] = __ldg(s2 + j); }
+      }
+      mbar_wait(&buf_empty[bb], (uint32_t)(((k >> 1) & 1) ^ 1));
+      if (has_row) {
+        uint8_t* dslot = smem + L.cat_off + (size_t)bb * L.cat_bytes + (size_t)v * 16;
+        uint8_t* zslot = smem + L.z_off + (size_t)bb * L.z_bytes + (size_t)v * 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 od = make_uint4(0u, 0u, 0u, 0u), oz = od;
+          if (real) {
+            float d[8], m[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f}, av[8], bv[8];
+            gb_unpack8(qd[j], d); gb_unpack8(qa[j], av); gb_unpack8(qb[j], bv);
+            if (p.mask) gb_unpack8(__ldg(reinterpret_cast<const uint4*>(p.mask + pp * 32) + j), m);
+            else if (philox) dropout8(sd, of, (uint64_t)(pp * 4 + j), p.drop_p, m);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { d[i] *= m[i]; dbs[8 * j + i] += d[i]; av[i] *= bv[i]; }
+            od = make_uint4(gb_pack(d[0], d[1]), gb_pack(d[2], d[3]), gb_pack(d[4], d[5]), gb_pack(d[6], d[7]));
+            oz = make_uint4(gb_pack(av[0], av[1]), gb_pack(av[2], av[3]), gb_pack(av[4], av[5]), gb_pack(av[6], av[7]));
+          }
+          *reinterpret_cast<uint4*>(dslot + (size_t)j * Kp * 16) = od;
+          *reinterpret_cast<uint4*>(zslot + (size_t)j * Kp * 16) = oz;
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(&in_full[bb]);
+    }
+    const float s = warp_column_sums(dbs, lane);
+    atomicAdd(p.db_mlp + lane, s);
+    if (wq == 2) {
+      // w11 also flushes quadrant 3 of the dW accumulators at the end
+      mbar_wait(w_full, 0u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        const int m = t * 128 + 96 + lane;
+        float vv[32];
+        tmem_ld32(tmem_base + ((uint32_t)96 << 16) + TW + 32u * t, vv);
+        if (m < NU) {
+          float* dst = p.dw_mlp + (size_t)(m >> 5) * 32 * 32 + (m & 31);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) atomicAdd(dst + c * 32, vv[c]);
+        }
+      }
+    }
+  } else if ((quad < 2 && wq < 2) || (quad == 2 && wq == 1)) {
+    // ===================== stage warps: TMEM(dU_j) -> bf16 -> slots 1..H =====================
+    if (quad < nq_stage) {
+      const int row = quad * 32 + lane;
+      const int first = (quad < 2) ? 1 + wq : 1, step = (quad < 2) ? 2 : 1;
+      const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+      int k = 0;
+      for (long long slab = blockIdx.x; slab < p.slabs; slab += gridDim.x, ++k) {
+        const int bb = k & 1;
+        mbar_wait(ut_full, (uint32_t)(k & 1));
+        mbar_wait(&buf_empty[bb], (uint32_t)(((k >> 1) & 1) ^ 1));
+        tc_fence_after();
+        uint8_t* cat = smem + L.cat_off + (size_t)bb * L.cat_bytes;
+        uint32_t r[32];
+        for (int j = first; j <= NM; j += step) {
+          tmem_ld32_issue(tmem_base + lane_off + 32u * (uint32_t)(j - 1), r);
+          tmem_ld_wait();
+          if (j + step > NM) { tc_fence_before(); mbar_arrive(ut_empty); }     // my last read of the accumulators
+          if (row < Kp) {
+            uint8_t* dst = cat + (size_t)j * L.slot_bytes + (size_t)row * 16;
+#pragma unroll
+            for (int cg = 0; cg < 4; ++cg) {
+              uint4 pk;
+              pk.x = gb_pack(__uint_as_float(r[8 * cg]), __uint_as_float(r[8 * cg + 1]));
+              pk.y = gb_pack(__uint_as_float(r[8 * cg + 2]), __uint_as_float(r[8 * cg + 3]));
+              pk.z = gb_pack(__uint_as_float(r[8 * cg + 4]), __uint_as_float(r[8 * cg + 5]));
+              pk.w = gb_pack(__uint_as_float(r[8 * cg + 6]), __uint_as_float(r[8 * cg + 7]));
+              *reinterpret_cast<uint4*>(dst + (size_t)cg * Kp * 16) = pk;
+            }
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(&us_full[bb]);
+      }
+    }
+  } else if (wq == 2 && quad < 3) {
+    // ===================== epilogue warps (w8, w9, w10): dz -> gate backward -> dfg; then the dW flush =====================
+    const int w = quad * 32 + lane;
+    if (quad < nq_epi) {
+      const bool valid = w < V;
+      int k = 0;
+      for (long long slab = blockIdx.x; slab < p.slabs; slab += gridDim.x, ++k) {
+        const long long pp = slab * V + w;
+        uint4 qa[4], qb[4], ql[4];
+        bool tailrow = false;
+        if (valid) {
+          const uint4* s1 = reinterpret_cast<const uint4*>(p.a + pp * 32);
+          const uint4* s2 = reinterpret_cast<const uint4*>(p.b + pp * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { qa[j] = __ldg(s1 + j); qb[j] = __ldg(s2 + j); }
+          if (p.dz_last) {
+            long long n, rem;
+            split_pos(pp, p.RO, n, rem);
+            if (rem >= p.last_begin) {
+              tailrow = true;
+              const uint4* s3 = reinterpret_cast<const uint4*>(p.dz_last + (n * p.last_rows + rem - p.last_begin) * 32);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) ql[j] = __ldg(s3 + j);
+            }
+          }
+        }
+        mbar_wait(dz_full, (uint32_t)(k & 1));
+        tc_fence_after();
+        float dz[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + TZ, dz);
+        tc_fence_before();
+        mbar_arrive(dz_empty);
+        if (valid) {
+          uint4* out = reinterpret_cast<uint4*>(p.dfg + pp * 64);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float av[8], bv[8], o[16];
+            gb_unpack8(qa[j], av); gb_unpack8(qb[j], bv);
+            if (tailrow) {
+              float t[8];
+              gb_unpack8(ql[j], t);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) dz[8 * j + i] += t[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float g = dz[8 * j + i];
+              o[2 * i] = g * bv[i] * (1.f - av[i] * av[i]);
+              o[2 * i + 1] = g * av[i] * bv[i] * (1.f - bv[i]);
+            }
+            out[2 * j] = make_uint4(gb_pack(o[0], o[1]), gb_pack(o[2], o[3]), gb_pack(o[4], o[5]), gb_pack(o[6], o[7]));
+            out[2 * j + 1] = make_uint4(gb_pack(o[8], o[9]), gb_pack(o[10], o[11]), gb_pack(o[12], o[13]), gb_pack(o[14], o[15]));
+          }
+        }
+      }
+    }
+    // dW flush: D_W[(j, c'), c] -> dw_mlp[(j*32 + c), c']
+    mbar_wait(w_full, 0u);
+    tc_fence_after();
+#pragma unroll 1
+    for (int t = 0; t < 2; ++t) {
+      const int m = t * 128 + quad * 32 + lane;
+      float vv[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + TW + 32u * t, vv);
+      if (m < NU) {
+        float* dst = p.dw_mlp + (size_t)(m >> 5) * 32 * 32 + (m & 31);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) atomicAdd(dst + c * 32, vv[c]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == GB_MMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// wt_img[kc = (j, c'>>3)][n = c][c' & 7] = W_mlp[j*32 + c][c']
+__global__ void gcn_bwd_wprep_kernel(const float* __restrict__ w, int n_mats, bf16* __restrict__ img) {
+  const int total = 32 * 32 * (1 + n_mats);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int j = i / 1024, c = (i / 32) % 32, co = i % 32;
+    img[((j * 4 + (co >> 3)) * 32 + c) * 8 + (co & 7)] = __float2bfloat16_rn(w[i]);
+  }
+}
+
+int gcn_bwd_fused_supported(int V, int n_mats) {
+  if (V < 1 || V > 80 || (n_mats != 2 && n_mats != 4 && n_mats != 6)) return 0;
+  const int Kp = ((V + 15) / 16) * 16;
+  return gb_layout(Kp, n_mats).total <= 227u * 1024u ? 1 : 0;
+}
+
+int launch_gcn_bwd_wprep(const float* w_mlp, int n_mats, bf16* wt_img, cudaStream_t st) {
+  gcn_bwd_wprep_kernel<<<8, 256, 0, st>>>(w_mlp, n_mats, wt_img);
+  GWN_LAUNCHED();
+  return 0;
+}
+
+int launch_gcn_bwd(GcnBwdParams& p, cudaStream_t st) {
+  if (p.slabs <= 0) return 0;
+  p.Kp = ((p.V + 15) / 16) * 16;
+  GWN_REQUIRE(gcn_bwd_fused_supported(p.V, p.n_mats), "gcn_bwd: V=%d with %d resident matrices is not supported", p.V,
+              p.n_mats);
+  GWN_REQUIRE((long long)p.slabs * p.V < (1ll << 31), "gcn_bwd: too many positions");
+  const GbLayout L = gb_layout(p.Kp, p.n_mats);
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    GWN_CUDA(cudaGetDevice(&dev));
+    GWN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int grid = p.slabs < sms ? p.slabs : sms;
+  const int ks = p.Kp / 16;
+#define GB_CASE(NM_, KS_)                                                                                         \
+  if (p.n_mats == NM_ && ks == KS_) {                                                                             \
+    static bool attr = false;                                                                                     \
+    if (!attr) {                                                                                                  \
+      GWN_CUDA(cudaFuncSetAttribute(gcn_bwd_kernel<NM_, KS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      attr = true;                                                                                                \
+    }                                                                                                             \
+    gcn_bwd_kernel<NM_, KS_><<<grid, GB_THREADS, L.total, st>>>(p);                                               \
+    GWN_LAUNCHED();                                                                                               \
+    return 0;                                                                                                     \
+  }
+  GB_CASE(6, 5) GB_CASE(4, 5) GB_CASE(2, 5) GB_CASE(6, 4) GB_CASE(4, 4) GB_CASE(2, 4) GB_CASE(6, 3) GB_CASE(4, 3)
+  GB_CASE(2, 3) GB_CASE(6, 2) GB_CASE(4, 2) GB_CASE(2, 2) GB_CASE(6, 1) GB_CASE(4, 1) GB_CASE(2, 1)
+#undef GB_CASE
+  GWN_REQUIRE(false, "gcn_bwd: no kernel instance for %d matrices, Kp=%d", p.n_mats, p.Kp);
+  return -1;
+}
+
+}  // namespace gwn

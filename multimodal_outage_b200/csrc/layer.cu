@@ -752,7 +752,37 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
   const T* du = reinterpret_cast<const T*>(g->du);
   const unsigned eb = (unsigned)cdiv(P * 8, 256);
   const T* dz = nullptr;
-  if (du) {
+  bool fused_bwd = false;
+  if constexpr (std::is_same<T, bf16>::value) {
+    // supports on chip and none of them needs a gradient: the whole diffusion backward (mask, transposed hops, mlp
+    // data + weight gradients, gate backward) is ONE kernel (gcn_fused_bwd.cu) that leaves dfg for the conv backward
+    bool any_dA = false;
+    for (int s = 0; s < c->n_supports; ++s) any_dA = any_dA || (g->support_needs_grad[s] && g->d_supports[s]);
+    if (du && !any_dA && fused_gcn_enabled() && tc_mode<T>(c, g->hop_mats) == 1 && c->order == 2 && c->n_supports >= 1 &&
+        g->ws_w != nullptr && gcn_bwd_fused_supported(c->V, 2 * c->n_supports) && wgrad_tc_supported(c->taps, 64)) {
+      uint8_t* wsw = reinterpret_cast<uint8_t*>(g->ws_w);
+      bf16* wt = reinterpret_cast<bf16*>(wsw + 96 * 1024);
+      GWN_CUDA(cudaMemsetAsync(g->dw_mlp, 0, sizeof(float) * 32 * mlp_in, st));
+      GWN_CUDA(cudaMemsetAsync(g->db_mlp, 0, sizeof(float) * 32, st));
+      if (int rc = launch_gcn_bwd_wprep(g->w_mlp, 2 * c->n_supports, wt, st)) return rc;
+      GcnBwdParams bp{};
+      bp.du = du; bp.a = a; bp.b = b; bp.dz_last = reinterpret_cast<const bf16*>(g->dz_last);
+      bp.RO = RO; bp.last_begin = (long long)(c->Lout - c->Lf) * c->V; bp.last_rows = (long long)c->Lf * c->V;
+      bp.mats = reinterpret_cast<const bf16*>(g->hop_mats); bp.n_mats = 2 * c->n_supports;
+      for (int j = 0; j < bp.n_mats; ++j) bp.mat_src[j] = 4 * (j / 2) + 2 + (j % 2);     // A_s, A_s^2 (transposed hops)
+      bp.wt_img = wt;
+      const bool drop = c->training && (g->drop_mask != nullptr || c->dropout_p > 0.f);
+      bp.mask = drop ? reinterpret_cast<const bf16*>(g->drop_mask) : nullptr;
+      bp.drop_p = drop ? c->dropout_p : 0.f; bp.seed = c->seed; bp.offset = c->offset; bp.rng = g->rng;
+      bp.dfg = reinterpret_cast<bf16*>(g->ws_dfg); bp.dw_mlp = g->dw_mlp; bp.db_mlp = g->db_mlp;
+      bp.V = c->V; bp.slabs = c->N * c->Lout;
+      if (int rc = launch_gcn_bwd(bp, st)) return rc;
+      fused_bwd = true;
+    }
+  }
+  if (fused_bwd) {
+    // dfg is ready: fall through to the conv weight / data gradients
+  } else if (du) {
     // recompute the concat (z and its hops)
     zfill_kernel<T><<<eb, 256, 0, st>>>(a, b, cat, 32, P);
     GWN_LAUNCHED();
@@ -893,7 +923,8 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
   if constexpr (std::is_same<T, bf16>::value) tc_gate = tc_mode<T>(c, g->hop_mats) != 0 && wgrad_tc_supported(c->taps, 64);
   const long long last_begin = (long long)(c->Lout - c->Lf) * c->V, last_rows = (long long)c->Lf * c->V;
   bf16* dfg16 = reinterpret_cast<bf16*>(g->ws_dfg);
-  if (tc_gate)
+  if (fused_bwd) {
+  } else if (tc_gate)
     gate_bwd_kernel<T, bf16><<<eb, 256, 0, st>>>(dz, 32, reinterpret_cast<const T*>(g->dz_last), RO, last_begin,
                                                   last_rows, a, b, dfg16, P);
   else

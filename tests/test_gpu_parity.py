@@ -359,7 +359,7 @@ def test_non_b200_or_cpu_input_raises():
 
 
 def _layer_op_case(dtype, tol, V=67, N=6, Lin=9, dil=2, taps=2, n_sup=3, with_bn=True, mask=False, seed=0,
-                   tensor_cores=False):
+                   tensor_cores=False, adp_grad=True):
     """ops.WaveNetLayer (bn-fold + gate + hops + mlp + dropout + residual, fwd AND bwd) against the
     oracle's single-layer restatement on IDENTICAL inputs (no ReLU anywhere -> bf16 error stays at
     rounding level, so the 2e-2 / 1e-4 bars apply to every gradient)."""
@@ -406,7 +406,7 @@ def _layer_op_case(dtype, tol, V=67, N=6, Lin=9, dil=2, taps=2, n_sup=3, with_bn
     wfg_k, bfg_k = f32(w_fg).contiguous().requires_grad_(True), f32(b_fg).requires_grad_(True)
     wm_k, bm_k = f32(wm[:, :, 0, 0].t()).contiguous().requires_grad_(True), f32(bm).requires_grad_(True)
     sup_k = [f32(a) for a in sups]
-    sup_k[-1].requires_grad_(True)
+    sup_k[-1].requires_grad_(adp_grad)
     meta = dict(training=True, momentum=0.1, eps=1e-5, Lf=Lf, taps=taps, dilation=dil, order=2, has_gconv=True,
                 dropout_p=0.3 if mask else 0.0, seed=0, offset=0)
     hop_mats_k = None
@@ -426,8 +426,9 @@ def _layer_op_case(dtype, tol, V=67, N=6, Lin=9, dil=2, taps=2, n_sup=3, with_bn
         'db_gate': rel(bfg_k.grad.reshape(32, 2)[:, 1], o_bg.grad),
         'dw_mlp': rel(wm_k.grad.t(), o_wm.grad[:, :, 0, 0]),
         'db_mlp': rel(bm_k.grad, o_bm.grad),
-        'd_adp': rel(sup_k[-1].grad, o_adp.grad),
     }
+    if adp_grad:
+        errs['d_adp'] = rel(sup_k[-1].grad, o_adp.grad)
     if with_bn:
         errs['dgamma'] = rel(gk.grad, o_g.grad)
         errs['dbeta'] = rel(bk.grad, o_b.grad)
@@ -467,6 +468,18 @@ def test_bf16_layer_op_big_graph_tma_gemm_hops(with_bn, mask):
     errs = _layer_op_case(torch.bfloat16, BF16_TOL, V=333, N=1, Lin=4, dil=1, taps=2, n_sup=2, with_bn=with_bn,
                           mask=mask, seed=7, tensor_cores=True)
     print('bf16 big-graph layer-op errors V=333:', {k: f'{v:.1e}' for k, v in errs.items()})
+
+
+@pytest.mark.parametrize('with_bn,mask', [(True, False), (False, True)])
+def test_bf16_layer_op_fused_diffusion_backward(with_bn, mask):
+    """Supports without gradient (fixed transition matrices only): the diffusion backward runs as ONE fused
+    kernel (gcn_fused_bwd.cu: mask, transposed hops, mlp data + weight gradients, gate backward on chip).  Every
+    output and gradient within the bf16 bar; ragged slab counts, 1-3 supports, V below and above 64."""
+    for kw in (dict(seed=21), dict(V=67, N=3, Lin=7, dil=1, n_sup=2, seed=22), dict(V=40, N=5, Lin=4, dil=1, n_sup=1, seed=23),
+               dict(V=80, N=2, Lin=6, dil=2, n_sup=3, seed=24)):
+        errs = _layer_op_case(torch.bfloat16, BF16_TOL, taps=2, with_bn=with_bn, mask=mask, tensor_cores=True,
+                              adp_grad=False, **kw)
+        print('bf16 fused-backward layer-op errors:', kw, {k: f'{v:.1e}' for k, v in errs.items()})
 
 
 def test_tma_gemm_every_staging_mode():
