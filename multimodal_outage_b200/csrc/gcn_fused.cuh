@@ -77,8 +77,15 @@ struct GcnBwdParams {
   float* dw_mlp;               // [32*(1+n_mats), 32] fp32, accumulated with atomics (caller zeroes)
   float* db_mlp;               // [32]
   int V, Kp, slabs;
+  // optional gradient wrt ONE support (the adaptive adjacency), sa = its index (-1: none):
+  //   dA[v,w] += sum_{slab,c} T1[v,c] dh[w,c] + U6[v,c] dU5[w,c],   U5 = z W_{2sa+1}, U6 = z W_{2sa+2}, T1 = U5 + A^T-hop(U6)
+  int sa;
+  int mat_fwd;                 // image index of the FORWARD hop of support sa (variant 0)
+  const bf16* w56_img;         // [4][64][8]: (n = (5|6, c'), k = c) = W_mlp[(2sa+1 | 2sa+2)*32 + c][c']
+  float* dA;                   // [V, V] fp32, accumulated with atomics
 };
 int gcn_bwd_fused_supported(int V, int n_mats);
-int launch_gcn_bwd_wprep(const float* w_mlp, int n_mats, bf16* wt_img, cudaStream_t st);
+// wt_img as above; w56_img (may be NULL) for support sa
+int launch_gcn_bwd_wprep(const float* w_mlp, int n_mats, bf16* wt_img, int sa, bf16* w56_img, cudaStream_t st);
 int launch_gcn_bwd(GcnBwdParams& p, cudaStream_t st);
 }  // namespace gwn

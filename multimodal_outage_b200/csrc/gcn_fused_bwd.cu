@@ -24,8 +24,9 @@ constexpr int GB_MMA = 3;
 
 struct GbLayout {
   uint32_t mat_bytes, w_off, w_bytes, cat_off, slot_bytes, cat_bytes, z_off, z_bytes, bar_off, total;
+  uint32_t fwd_off, w56_off, u6_off, t1_off;     // dA extras (has_da): forward image, W56 image, U6 / T1 staging x2
 };
-__host__ __device__ inline GbLayout gb_layout(int Kp, int n_mats) {
+__host__ __device__ inline GbLayout gb_layout(int Kp, int n_mats, bool has_da = false) {
   GbLayout L;
   L.mat_bytes = (uint32_t)(Kp / 8) * (uint32_t)Kp * 16u;       // [Kp/8][Kp rows][16 B]
   L.w_off = (uint32_t)n_mats * L.mat_bytes;
@@ -35,7 +36,15 @@ __host__ __device__ inline GbLayout gb_layout(int Kp, int n_mats) {
   L.cat_bytes = (uint32_t)(1 + n_mats) * L.slot_bytes;
   L.z_off = L.cat_off + 2u * L.cat_bytes;
   L.z_bytes = L.slot_bytes;
-  L.bar_off = (L.z_off + 2u * L.z_bytes + 4096u + 127u) & ~127u;     // slack: M=128 operand rows past Kp / past slot H
+  uint32_t end = L.z_off + 2u * L.z_bytes;
+  L.fwd_off = L.w56_off = L.u6_off = L.t1_off = end;
+  if (has_da) {
+    L.u6_off = end; end += 2u * L.slot_bytes;
+    L.t1_off = end; end += 2u * L.slot_bytes;
+    L.fwd_off = end; end += L.mat_bytes;
+    L.w56_off = end; end += 4u * 64u * 16u;
+  }
+  L.bar_off = (end + 4096u + 127u) & ~127u;     // slack: M=128 operand rows past Kp / past slot H
   L.total = L.bar_off + 256u;
   return L;
 }
@@ -51,14 +60,14 @@ __device__ __forceinline__ void gb_unpack8(const uint4& q, float v[8]) {
   v[6] = __uint_as_float(q.w << 16); v[7] = __uint_as_float(q.w & 0xFFFF0000u);
 }
 
-template <int NM, int KSTEPS>
+template <int NM, int KSTEPS, bool DA>
 __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_constant__ GcnBwdParams p) {
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int Kp = 16 * KSTEPS, NU = 32 * (1 + NM);
   const int V = p.V;
-  const GbLayout L = gb_layout(Kp, NM);
+  const GbLayout L = gb_layout(Kp, NM, DA);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
   uint64_t* buf_empty = bars;           // [2] concat buffer + z tile free (tail MMAs of slab k-2 completed)
   uint64_t* in_full = bars + 2;         // [2] dh and z tiles written
@@ -68,7 +77,12 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
   uint64_t* dz_full = bars + 8;
   uint64_t* dz_empty = bars + 9;
   uint64_t* w_full = bars + 10;         // all MMAs of the CTA completed (dW accumulators final)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* u56_full = bars + 11;       // dA: U5|U6 accumulators complete
+  uint64_t* u6s_full = bars + 12;       // [2] U6 staged in shared memory
+  uint64_t* t1_full = bars + 14;        // T1 = U5 + hop(U6) accumulator complete
+  uint64_t* t1_empty = bars + 15;       // T1 accumulator drained
+  uint64_t* t1s_full = bars + 16;       // [2] T1 staged in shared memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int nq_stage = (Kp + 31) / 32;
   const int nq_epi = (V + 31) / 32;
@@ -81,6 +95,8 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
     mbar_init(ut_full, 1); mbar_init(ut_empty, 32 * n_stage_warps);
     mbar_init(dz_full, 1); mbar_init(dz_empty, 32 * nq_epi);
     mbar_init(w_full, 1);
+    mbar_init(u56_full, 1); mbar_init(t1_full, 1); mbar_init(t1_empty, 32 * nq_stage);
+    for (int i = 0; i < 2; ++i) { mbar_init(&u6s_full[i], 32 * nq_stage); mbar_init(&t1s_full[i], 32 * nq_stage); }
     fence_barrier_init();
   }
   if (warp == GB_MMA) tmem_alloc(tmem_slot, 512);
@@ -97,8 +113,16 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
     const uint4* wsrc = reinterpret_cast<const uint4*>(p.wt_img);
     uint4* wdst = reinterpret_cast<uint4*>(smem + L.w_off);
     for (int i = tid; i < (int)(L.w_bytes / 16); i += GB_THREADS) wdst[i] = __ldg(wsrc + i);
+    if (DA) {
+      const uint4* src = reinterpret_cast<const uint4*>(p.mats) + (size_t)p.mat_fwd * pieces * 128;
+      uint4* dst = reinterpret_cast<uint4*>(smem + L.fwd_off);
+      for (int i = tid; i < pieces * Kp; i += GB_THREADS) dst[(i / Kp) * Kp + (i % Kp)] = __ldg(src + (i / Kp) * 128 + (i % Kp));
+      const uint4* w5 = reinterpret_cast<const uint4*>(p.w56_img);
+      uint4* d5 = reinterpret_cast<uint4*>(smem + L.w56_off);
+      for (int i = tid; i < 4 * 64; i += GB_THREADS) d5[i] = __ldg(w5 + i);
+    }
     // slack past the buffers is read (as ignored accumulator rows) by the M=128 operands: keep it finite
-    uint4* sl = reinterpret_cast<uint4*>(smem + L.z_off + 2 * L.z_bytes);
+    uint4* sl = reinterpret_cast<uint4*>(smem + L.bar_off - 4096u);
     for (int i = tid; i < 4096 / 16; i += GB_THREADS) sl[i] = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async();
   }
@@ -109,6 +133,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
   const uint32_t sbase = smem_u32(smem);
   const int quad = warp & 3, wq = warp >> 2;
   constexpr uint32_t TZ = 192u, TW = 224u;      // TMEM columns of dz and dW
+  constexpr uint32_t TU5 = 288u, TU6 = 320u, TDA = 352u;   // dA: U5 -> T1, U6, dA accumulator (Kp columns)
 
   if (warp == GB_MMA) {
     // ===================== MMA issuer =====================
@@ -119,6 +144,9 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
       const uint64_t adm = make_smem_desc(0, (uint32_t)Kp * 16u, 128u);           // K-major, K piece stride Kp*16
       const uint64_t bmn = make_smem_desc(0, 128u, (uint32_t)Kp * 16u);           // MN-major [group][node][16 B]
       const uint64_t bdw = make_smem_desc(0, 32u * 16u, 128u);                    // W^T image: K piece stride 512 B
+      const uint64_t b56 = make_smem_desc(0, 64u * 16u, 128u);                    // W56 image: K piece stride 1024 B
+      const uint32_t idescU = make_idesc_bf16(128, 64, false, false);   // z (K-major) x W56 image (K-major)
+      const uint32_t idescA = make_idesc_bf16(128, Kp, false, false);   // T1|U6 (K-major) x dh|dU5 (K-major, N = node)
       auto tail = [&](int kk) {
         const int bb = kk & 1;
         mbar_wait(&us_full[bb], (uint32_t)((kk >> 1) & 1));
@@ -139,12 +167,41 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
           for (int ks = 0; ks < KSTEPS; ++ks)
             umma_bf16(tmem_base + TW + 32u * t, am + (uint64_t)(((uint32_t)(16 * t) * (uint32_t)Kp * 16u + (uint32_t)ks * 256u) >> 4),
                       bz + (uint64_t)(((uint32_t)ks * 256u) >> 4), idescW, (kk == 0 && ks == 0) ? 0u : 1u);
+        if (DA) {
+          // dA += T1^T-style products: D[v, w] += sum_c T1[v,c] dh[w,c] + U6[v,c] dU5[w,c]   (all operands K-major)
+          mbar_wait(&t1s_full[bb], (uint32_t)((kk >> 1) & 1));
+          tc_fence_after();
+          const uint64_t at1 = adm + (uint64_t)((sbase + L.t1_off + (uint32_t)bb * L.slot_bytes) >> 4);
+          const uint64_t au6 = adm + (uint64_t)((sbase + L.u6_off + (uint32_t)bb * L.slot_bytes) >> 4);
+          const uint64_t bdh = adm + (uint64_t)(cat >> 4);
+          const uint64_t bd5 = adm + (uint64_t)((cat + (uint32_t)(2 * p.sa + 1) * L.slot_bytes) >> 4);
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks)
+            umma_bf16(tmem_base + TDA, at1 + (uint64_t)(((uint32_t)(2 * ks) * (uint32_t)Kp * 16u) >> 4),
+                      bdh + (uint64_t)(((uint32_t)(2 * ks) * (uint32_t)Kp * 16u) >> 4), idescA, (kk == 0 && ks == 0) ? 0u : 1u);
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks)
+            umma_bf16(tmem_base + TDA, au6 + (uint64_t)(((uint32_t)(2 * ks) * (uint32_t)Kp * 16u) >> 4),
+                      bd5 + (uint64_t)(((uint32_t)(2 * ks) * (uint32_t)Kp * 16u) >> 4), idescA, 1u);
+        }
         umma_commit(&buf_empty[bb]);
       };
       int k = 0;
       for (long long slab = blockIdx.x; slab < p.slabs; slab += gridDim.x, ++k) {
         const int bb = k & 1;
         mbar_wait(&in_full[bb], (uint32_t)((k >> 1) & 1));
+        if (DA) {
+          // U5 | U6 = z [W_{2sa+1} | W_{2sa+2}]  (issued first: its staging overlaps the hop MMAs below)
+          mbar_wait(t1_empty, (uint32_t)((k & 1) ^ 1));
+          tc_fence_after();
+          const uint64_t az = adm + (uint64_t)((sbase + L.z_off + (uint32_t)bb * L.z_bytes) >> 4);
+          const uint64_t bw = b56 + (uint64_t)((sbase + L.w56_off) >> 4);
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks)
+            umma_bf16(tmem_base + TU5, az + (uint64_t)(((uint32_t)(2 * ks) * (uint32_t)Kp * 16u) >> 4),
+                      bw + (uint64_t)(((uint32_t)(2 * ks) * 1024u) >> 4), idescU, ks == 0 ? 0u : 1u);
+          umma_commit(u56_full);
+        }
         mbar_wait(ut_empty, (uint32_t)((k & 1) ^ 1));
         tc_fence_after();
         const uint32_t cat = sbase + L.cat_off + (uint32_t)bb * L.cat_bytes;
@@ -157,6 +214,18 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
                       a0 + (uint64_t)(((uint32_t)m * ((uint32_t)(Kp / 8) * (uint32_t)Kp * 16u) + (uint32_t)(2 * ks) * (uint32_t)Kp * 16u) >> 4),
                       b0 + (uint64_t)(((uint32_t)ks * 256u) >> 4), idescH, ks == 0 ? 0u : 1u);
         umma_commit(ut_full);
+        if (DA) {
+          // T1 = U5 + A^T-hop(U6): accumulate the forward hop of the staged U6 onto the U5 columns
+          mbar_wait(&u6s_full[bb], (uint32_t)((k >> 1) & 1));
+          tc_fence_after();
+          const uint64_t af = adm + (uint64_t)((sbase + L.fwd_off) >> 4);
+          const uint64_t bu = bmn + (uint64_t)((sbase + L.u6_off + (uint32_t)bb * L.slot_bytes) >> 4);
+#pragma unroll
+          for (int ks = 0; ks < KSTEPS; ++ks)
+            umma_bf16(tmem_base + TU5, af + (uint64_t)(((uint32_t)(2 * ks) * (uint32_t)Kp * 16u) >> 4),
+                      bu + (uint64_t)(((uint32_t)ks * 256u) >> 4), idescH, 1u);
+          umma_commit(t1_full);
+        }
         if (k > 0) tail(k - 1);
       }
       if (k > 0) tail(k - 1);
@@ -236,11 +305,36 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
       int k = 0;
       for (long long slab = blockIdx.x; slab < p.slabs; slab += gridDim.x, ++k) {
         const int bb = k & 1;
+        uint32_t r[32];
+        auto stage_tile = [&](uint32_t tcol, uint8_t* dst0) {     // 32 TMEM columns of this row -> [4 cg][Kp][16 B]
+          tmem_ld32_issue(tmem_base + lane_off + tcol, r);
+          tmem_ld_wait();
+          if (row < Kp) {
+            uint8_t* dst = dst0 + (size_t)row * 16;
+#pragma unroll
+            for (int cg = 0; cg < 4; ++cg) {
+              uint4 pk;
+              pk.x = gb_pack(__uint_as_float(r[8 * cg]), __uint_as_float(r[8 * cg + 1]));
+              pk.y = gb_pack(__uint_as_float(r[8 * cg + 2]), __uint_as_float(r[8 * cg + 3]));
+              pk.z = gb_pack(__uint_as_float(r[8 * cg + 4]), __uint_as_float(r[8 * cg + 5]));
+              pk.w = gb_pack(__uint_as_float(r[8 * cg + 6]), __uint_as_float(r[8 * cg + 7]));
+              *reinterpret_cast<uint4*>(dst + (size_t)cg * Kp * 16) = pk;
+            }
+          }
+        };
+        const bool does_u6 = DA && (quad >= 2 || wq == 0), does_t1 = DA && (quad >= 2 || wq == 1);
+        if (does_u6) {       // U6 first: it is ready before the hops of this slab finish
+          mbar_wait(u56_full, (uint32_t)(k & 1));
+          tc_fence_after();
+          stage_tile(TU6, smem + L.u6_off + (size_t)bb * L.slot_bytes);
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive(&u6s_full[bb]);
+        }
         mbar_wait(ut_full, (uint32_t)(k & 1));
         mbar_wait(&buf_empty[bb], (uint32_t)(((k >> 1) & 1) ^ 1));
         tc_fence_after();
         uint8_t* cat = smem + L.cat_off + (size_t)bb * L.cat_bytes;
-        uint32_t r[32];
         for (int j = first; j <= NM; j += step) {
           tmem_ld32_issue(tmem_base + lane_off + 32u * (uint32_t)(j - 1), r);
           tmem_ld_wait();
@@ -260,6 +354,15 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
         }
         fence_proxy_async();
         mbar_arrive(&us_full[bb]);
+        if (does_t1) {
+          mbar_wait(t1_full, (uint32_t)(k & 1));
+          tc_fence_after();
+          stage_tile(TU5, smem + L.t1_off + (size_t)bb * L.slot_bytes);
+          tc_fence_before();
+          mbar_arrive(t1_empty);
+          fence_proxy_async();
+          mbar_arrive(&t1s_full[bb]);
+        }
       }
     }
   } else if (wq == 2 && quad < 3) {
@@ -332,6 +435,25 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
         for (int c = 0; c < 32; ++c) atomicAdd(dst + c * 32, vv[c]);
       }
     }
+    if (DA) {     // dA flush: accumulator row = node v, column = node w
+#pragma unroll 1
+      for (int c0 = 0; c0 < Kp; c0 += 16) {
+        uint32_t r[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(tmem_base + ((uint32_t)(quad * 32) << 16) + TDA + (uint32_t)c0)
+            : "memory");
+        tmem_ld_wait();
+        if (w < V) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < V) atomicAdd(p.dA + (long long)w * V + c0 + j, __uint_as_float(r[j]));
+        }
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -341,23 +463,29 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
   }
 }
 
-// wt_img[kc = (j, c'>>3)][n = c][c' & 7] = W_mlp[j*32 + c][c']
-__global__ void gcn_bwd_wprep_kernel(const float* __restrict__ w, int n_mats, bf16* __restrict__ img) {
+// wt_img[kc = (j, c'>>3)][n = c][c' & 7] = W_mlp[j*32 + c][c'];  w56[kc = c>>3][n = (h, c')][c & 7] = W_mlp[(2sa+1+h)*32 + c][c']
+__global__ void gcn_bwd_wprep_kernel(const float* __restrict__ w, int n_mats, bf16* __restrict__ img, int sa,
+                                     bf16* __restrict__ w56) {
   const int total = 32 * 32 * (1 + n_mats);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int j = i / 1024, c = (i / 32) % 32, co = i % 32;
-    img[((j * 4 + (co >> 3)) * 32 + c) * 8 + (co & 7)] = __float2bfloat16_rn(w[i]);
+    const bf16 v = __float2bfloat16_rn(w[i]);
+    img[((j * 4 + (co >> 3)) * 32 + c) * 8 + (co & 7)] = v;
+    if (w56 && sa >= 0 && (j == 2 * sa + 1 || j == 2 * sa + 2)) {
+      const int h = j - (2 * sa + 1);
+      w56[((c >> 3) * 64 + h * 32 + co) * 8 + (c & 7)] = v;
+    }
   }
 }
 
 int gcn_bwd_fused_supported(int V, int n_mats) {
   if (V < 1 || V > 80 || (n_mats != 2 && n_mats != 4 && n_mats != 6)) return 0;
   const int Kp = ((V + 15) / 16) * 16;
-  return gb_layout(Kp, n_mats).total <= 227u * 1024u ? 1 : 0;
+  return gb_layout(Kp, n_mats, true).total <= 227u * 1024u ? 1 : 0;
 }
 
-int launch_gcn_bwd_wprep(const float* w_mlp, int n_mats, bf16* wt_img, cudaStream_t st) {
-  gcn_bwd_wprep_kernel<<<8, 256, 0, st>>>(w_mlp, n_mats, wt_img);
+int launch_gcn_bwd_wprep(const float* w_mlp, int n_mats, bf16* wt_img, int sa, bf16* w56_img, cudaStream_t st) {
+  gcn_bwd_wprep_kernel<<<8, 256, 0, st>>>(w_mlp, n_mats, wt_img, sa, w56_img);
   GWN_LAUNCHED();
   return 0;
 }
@@ -368,7 +496,9 @@ int launch_gcn_bwd(GcnBwdParams& p, cudaStream_t st) {
   GWN_REQUIRE(gcn_bwd_fused_supported(p.V, p.n_mats), "gcn_bwd: V=%d with %d resident matrices is not supported", p.V,
               p.n_mats);
   GWN_REQUIRE((long long)p.slabs * p.V < (1ll << 31), "gcn_bwd: too many positions");
-  const GbLayout L = gb_layout(p.Kp, p.n_mats);
+  const bool has_da = p.sa >= 0;
+  GWN_REQUIRE(!has_da || (p.dA && p.w56_img && p.sa < p.n_mats / 2), "gcn_bwd: bad support-gradient arguments");
+  const GbLayout L = gb_layout(p.Kp, p.n_mats, has_da);
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
@@ -381,10 +511,12 @@ int launch_gcn_bwd(GcnBwdParams& p, cudaStream_t st) {
   if (p.n_mats == NM_ && ks == KS_) {                                                                             \
     static bool attr = false;                                                                                     \
     if (!attr) {                                                                                                  \
-      GWN_CUDA(cudaFuncSetAttribute(gcn_bwd_kernel<NM_, KS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      GWN_CUDA(cudaFuncSetAttribute(gcn_bwd_kernel<NM_, KS_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      GWN_CUDA(cudaFuncSetAttribute(gcn_bwd_kernel<NM_, KS_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
       attr = true;                                                                                                \
     }                                                                                                             \
-    gcn_bwd_kernel<NM_, KS_><<<grid, GB_THREADS, L.total, st>>>(p);                                               \
+    if (has_da) gcn_bwd_kernel<NM_, KS_, true><<<grid, GB_THREADS, L.total, st>>>(p);                             \
+    else gcn_bwd_kernel<NM_, KS_, false><<<grid, GB_THREADS, L.total, st>>>(p);                                   \
     GWN_LAUNCHED();                                                                                               \
     return 0;                                                                                                     \
   }

@@ -756,15 +756,17 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
   if constexpr (std::is_same<T, bf16>::value) {
     // supports on chip and none of them needs a gradient: the whole diffusion backward (mask, transposed hops, mlp
     // data + weight gradients, gate backward) is ONE kernel (gcn_fused_bwd.cu) that leaves dfg for the conv backward
-    bool any_dA = false;
-    for (int s = 0; s < c->n_supports; ++s) any_dA = any_dA || (g->support_needs_grad[s] && g->d_supports[s]);
-    if (du && !any_dA && fused_gcn_enabled() && tc_mode<T>(c, g->hop_mats) == 1 && c->order == 2 && c->n_supports >= 1 &&
+    int n_dA = 0, sa = -1;
+    for (int s = 0; s < c->n_supports; ++s)
+      if (g->support_needs_grad[s] && g->d_supports[s]) { ++n_dA; sa = s; }
+    if (du && n_dA <= 1 && fused_gcn_enabled() && tc_mode<T>(c, g->hop_mats) == 1 && c->order == 2 && c->n_supports >= 1 &&
         g->ws_w != nullptr && gcn_bwd_fused_supported(c->V, 2 * c->n_supports) && wgrad_tc_supported(c->taps, 64)) {
       uint8_t* wsw = reinterpret_cast<uint8_t*>(g->ws_w);
       bf16* wt = reinterpret_cast<bf16*>(wsw + 96 * 1024);
+      bf16* w56 = reinterpret_cast<bf16*>(wsw + 112 * 1024);
       GWN_CUDA(cudaMemsetAsync(g->dw_mlp, 0, sizeof(float) * 32 * mlp_in, st));
       GWN_CUDA(cudaMemsetAsync(g->db_mlp, 0, sizeof(float) * 32, st));
-      if (int rc = launch_gcn_bwd_wprep(g->w_mlp, 2 * c->n_supports, wt, st)) return rc;
+      if (int rc = launch_gcn_bwd_wprep(g->w_mlp, 2 * c->n_supports, wt, sa, w56, st)) return rc;
       GcnBwdParams bp{};
       bp.du = du; bp.a = a; bp.b = b; bp.dz_last = reinterpret_cast<const bf16*>(g->dz_last);
       bp.RO = RO; bp.last_begin = (long long)(c->Lout - c->Lf) * c->V; bp.last_rows = (long long)c->Lf * c->V;
@@ -776,6 +778,7 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
       bp.drop_p = drop ? c->dropout_p : 0.f; bp.seed = c->seed; bp.offset = c->offset; bp.rng = g->rng;
       bp.dfg = reinterpret_cast<bf16*>(g->ws_dfg); bp.dw_mlp = g->dw_mlp; bp.db_mlp = g->db_mlp;
       bp.V = c->V; bp.slabs = c->N * c->Lout;
+      bp.sa = sa; bp.mat_fwd = sa >= 0 ? 4 * sa : 0; bp.w56_img = w56; bp.dA = sa >= 0 ? g->d_supports[sa] : nullptr;
       if (int rc = launch_gcn_bwd(bp, st)) return rc;
       fused_bwd = true;
     }
