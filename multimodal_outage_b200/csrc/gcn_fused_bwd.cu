@@ -11,8 +11,9 @@
 //                                               accumulator stays in TMEM for the CTA's whole share of slabs)
 //   epilogue : TMEM(dz) + dz_last -> gate backward with a, b -> dfg (bf16, 128 B per node)
 // TMEM columns: dU [0, 32H), dz [192, 224), dW tiles [224, 256) and [256, 288).
-// Warps (16): q0/q1: stage A (w0,w1), stage B (w4,w5), epilogue (w8,w9); q2: stage w6, epilogue w10; q3: MMA w3 and
-// the three prep warps w7, w11, w15 (prep is not tied to a TMEM lane quadrant, q3 holds no node rows for V <= 96).
+// Warps (16): q0/q1: stage A (w0,w1), stage B (w4,w5), epilogue (w8,w9); q2: stage w6, epilogue w10; q3: MMA w3.
+// The three prep warps (w12, w13, w15) are not tied to a TMEM lane quadrant; they finish ALL their arithmetic (mask,
+// products, bf16 packing) in registers BEFORE waiting for the buffer, so a freed buffer is refilled in ~100 cycles.
 #include "gcn_fused.cuh"
 #include "tc.cuh"
 #include "tc_gemm_impl.cuh"   // warp_column_sums
@@ -232,9 +233,9 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
       umma_commit(w_full);
     }
     __syncwarp();
-  } else if (quad == 3) {
-    // ===================== prep warps (w7, w11, w15): dh = du . mask -> slot 0, z = a . b -> z tile =====================
-    const int v = (wq - 1) * 32 + lane;          // node row
+  } else if (warp == 12 || warp == 13 || warp == 15) {
+    // ===================== prep warps: dh = du . mask -> slot 0, z = a . b -> z tile =====================
+    const int v = (warp == 15 ? 2 : warp - 12) * 32 + lane;          // node row
     const bool has_row = v < Kp, real = v < V;
     float dbs[32];
 #pragma unroll
@@ -246,13 +247,27 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
     for (long long slab = blockIdx.x; slab < p.slabs; slab += gridDim.x, ++k) {
       const int bb = k & 1;
       const long long pp = slab * V + v;
-      uint4 qd[4], qa[4], qb[4];
+      uint4 od[4], oz[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { od[j] = make_uint4(0u, 0u, 0u, 0u); oz[j] = od[j]; }
       if (real) {
         const uint4* s0 = reinterpret_cast<const uint4*>(p.du + pp * 32);
         const uint4* s1 = reinterpret_cast<const uint4*>(p.a + pp * 32);
         const uint4* s2 = reinterpret_cast<const uint4*>(p.b + pp * 32);
+        uint4 qd[4], qa[4], qb[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) { qd[j] = __ldg(s0 + j); qa[j] = __ldg(s1 + j); qb[j] = __ldg(s2 + j); }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float d[8], m[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f}, av[8], bv[8];
+          gb_unpack8(qd[j], d); gb_unpack8(qa[j], av); gb_unpack8(qb[j], bv);
+          if (p.mask) gb_unpack8(__ldg(reinterpret_cast<const uint4*>(p.mask + pp * 32) + j), m);
+          else if (philox) dropout8(sd, of, (uint64_t)(pp * 4 + j), p.drop_p, m);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { d[i] *= m[i]; dbs[8 * j + i] += d[i]; av[i] *= bv[i]; }
+          od[j] = make_uint4(gb_pack(d[0], d[1]), gb_pack(d[2], d[3]), gb_pack(d[4], d[5]), gb_pack(d[6], d[7]));
+          oz[j] = make_uint4(gb_pack(av[0], av[1]), gb_pack(av[2], av[3]), gb_pack(av[4], av[5]), gb_pack(av[6], av[7]));
+        }
       }
       mbar_wait(&buf_empty[bb], (uint32_t)(((k >> 1) & 1) ^ 1));
       if (has_row) {
@@ -260,19 +275,8 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
         uint8_t* zslot = smem + L.z_off + (size_t)bb * L.z_bytes + (size_t)v * 16;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          uint4 od = make_uint4(0u, 0u, 0u, 0u), oz = od;
-          if (real) {
-            float d[8], m[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f}, av[8], bv[8];
-            gb_unpack8(qd[j], d); gb_unpack8(qa[j], av); gb_unpack8(qb[j], bv);
-            if (p.mask) gb_unpack8(__ldg(reinterpret_cast<const uint4*>(p.mask + pp * 32) + j), m);
-            else if (philox) dropout8(sd, of, (uint64_t)(pp * 4 + j), p.drop_p, m);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { d[i] *= m[i]; dbs[8 * j + i] += d[i]; av[i] *= bv[i]; }
-            od = make_uint4(gb_pack(d[0], d[1]), gb_pack(d[2], d[3]), gb_pack(d[4], d[5]), gb_pack(d[6], d[7]));
-            oz = make_uint4(gb_pack(av[0], av[1]), gb_pack(av[2], av[3]), gb_pack(av[4], av[5]), gb_pack(av[6], av[7]));
-          }
-          *reinterpret_cast<uint4*>(dslot + (size_t)j * Kp * 16) = od;
-          *reinterpret_cast<uint4*>(zslot + (size_t)j * Kp * 16) = oz;
+          *reinterpret_cast<uint4*>(dslot + (size_t)j * Kp * 16) = od[j];
+          *reinterpret_cast<uint4*>(zslot + (size_t)j * Kp * 16) = oz[j];
         }
       }
       fence_proxy_async();
@@ -280,8 +284,8 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
     }
     const float s = warp_column_sums(dbs, lane);
     atomicAdd(p.db_mlp + lane, s);
-    if (wq == 2) {
-      // w11 also flushes quadrant 3 of the dW accumulators at the end
+    if (warp == 15) {
+      // w15 also flushes quadrant 3 of the dW accumulators at the end
       mbar_wait(w_full, 0u);
       tc_fence_after();
 #pragma unroll 1
