@@ -291,6 +291,37 @@ def kernel_rooflines(peaks, n):
             'note': 'at V=67 the fused contraction has 209 flop/B, right at the ridge (214): HBM time 12.1 us, tensor '
                     'time 11.8 us; reported against HBM', 'peak_source': src}
 
+    # ---- fused diffusion backward (the dominant kernel of the step): du, a, b -> dfg, dW, db, dA
+    dus = [torch.randn(N, L[1], V, C32, device=dev).to(bf) for _ in range(R)]
+    aas = [torch.tanh(torch.randn(N, L[1], V, C32, device=dev)).to(bf) for _ in range(R)]
+    bbs = [torch.sigmoid(torch.randn(N, L[1], V, C32, device=dev)).to(bf) for _ in range(R)]
+    dfgs = [torch.empty(N, L[1], V, 64, device=dev, dtype=bf) for _ in range(R)]
+    dzl = torch.randn(N, 1, V, C32, device=dev).to(bf)
+    dw_m, db_m, dA_m = torch.zeros(224, 32, device=dev), torch.zeros(32, device=dev), torch.zeros(V, V, device=dev)
+
+    def gcnb(i):
+        def f():
+            _lib.check(lib.gwn_gcn_bwd(dus[i].data_ptr(), aas[i].data_ptr(), bbs[i].data_ptr(), dzl.data_ptr(), mats.data_ptr(),
+                                       3, w_mlp.data_ptr(), ws_w.data_ptr(), 0.3, 42, i, 2, dfgs[i].data_ptr(), dw_m.data_ptr(),
+                                       db_m.data_ptr(), dA_m.data_ptr(), N, V, L[1], 1, st()), 'gwn_gcn_bwd')
+        return f
+    ms_b = graph_time([gcnb(i) for i in range(R)])
+    flops_b = P * (6 * 2.0 * C32 * V + 2 * 2.0 * 224 * 32 + 2.0 * 32 * 64 + 2.0 * C32 * V + 2 * 2.0 * C32 * V)
+    byts_b = 5.0 * P * 64
+    roof_bwd = {'kernel': 'gcn_bwd_kernel (fused diffusion backward: dropout mask, 6 transposed hops, mlp data + weight '
+                          'gradients, adaptive-support gradient, gate backward; config-2 layer 0: 6144 slabs of 67 nodes; '
+                          'includes its weight-image prep + memsets)',
+                'bound': 'hbm', 'achieved': byts_b / (ms_b * 1e-3) / 1e9, 'peak': peak_bw, 'unit': 'GB/s',
+                'frac': byts_b / (ms_b * 1e-3) / 1e9 / peak_bw, 'traffic': traffic.get('gcn_bwd_kernel', {}).get('bytes'),
+                'traffic_source': traffic.get('gcn_bwd_kernel', {}).get('source'),
+                'algorithmic_bytes_per_launch': byts_b, 'algorithmic_flops_per_launch': flops_b, 'ms_per_launch': ms_b,
+                'tensor_tflops': flops_b / (ms_b * 1e-3) / 1e12, 'tensor_frac_of_burst_peak': flops_b / (ms_b * 1e-3) / 1e12 / peak_tf,
+                'note': 'algorithmic bytes = read du, a, b + write dfg (5 x 64 B per position); 71 kflop per position -> 222 '
+                        'flop/B, at the ridge like the forward: HBM time 20 us, tensor time 21 us.  The kernel is bound by '
+                        'the issue rate of its 65 small-N tcgen05.mma per slab (59 cycles each, smem-operand bound) and by '
+                        'TMEM->smem hand-offs (DESIGN.md section 3, scripts/gpu_gcn_bwd_trace.py)', 'peak_source': src}
+    del dus, aas, bbs, dfgs
+
     # ---- gated temporal conv (layer 0, inference form: read r once, write z once)
     w_fg = torch.randn(2 * 32, 64, device=dev) / 8
     b_fg = torch.zeros(64, device=dev)
@@ -330,7 +361,7 @@ def kernel_rooflines(peaks, n):
                 'traffic': traffic.get('tma_gemm_kernel_hop_v3100', {}).get('bytes'),
                 'traffic_source': traffic.get('tma_gemm_kernel_hop_v3100', {}).get('source'),
                 'peak_source': src + ' (burst; kernel timed alone)'}
-    return roof, gate_roof, big_roof
+    return roof_bwd, roof, gate_roof, big_roof
 
 
 def run_ours(args):
@@ -474,7 +505,7 @@ def run_ours(args):
         pth = os.path.join(ROOT, 'MEASURED_PEAKS.json')
         if os.path.exists(pth):
             peaks = json.load(open(pth))
-        roof, gate_roof, big_roof = (None, None, None) if args.no_roofline else kernel_rooflines(peaks, n)
+        roof, roof_fwd, gate_roof, big_roof = (None, None, None, None) if args.no_roofline else kernel_rooflines(peaks, n)
         cpu = None
         if world == 1 and not args.no_cpu:
             sps_cpu, sec_cpu = cpu_reference_steps(3, 1, CPU_SAMPLE_BATCH)
@@ -498,7 +529,7 @@ def run_ours(args):
             'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4},
             'gpu_launches': int(launches_per_step * args.steps),
             'gpu_launches_per_step': int(launches_per_step),
-            'roofline': roof, 'roofline_gate': gate_roof, 'roofline_diffusion_v3100': big_roof, 'cpu_baseline': cpu,
+            'roofline': roof, 'roofline_gcn_fwd': roof_fwd, 'roofline_gate': gate_roof, 'roofline_diffusion_v3100': big_roof, 'cpu_baseline': cpu,
             'final_loss': final_loss,
             'algorithmic_gflop_per_step_diffusion_fwd': (work['hop_fwd_flops'] + work['mlp_fwd_flops']) / 1e9,
         }

@@ -140,6 +140,16 @@ int gwn_gcn_fwd(const void* z, const void* u_prev, const float* scale, const flo
                 float drop_p, unsigned long long seed, unsigned long long offset, void* u, double* stats,
                 int N, int V, int Lin, int Lout, void* stream);
 
+/* The fused diffusion BACKWARD of gwn_layer_bwd alone (bf16, supports on chip; csrc/gcn_fused_bwd.cu):
+ *   dh = du.mask;  dU_j = M_j^T dh;  dz = sum_j dU_j W_j^T (+ dz_last);  dW_j = z^T dU_j (z = a.b);  db = sum dh;
+ *   dfg = gate backward of dz (df = dz b (1-a^2), dg = dz a b (1-b), interleaved, bf16 [N*Lout*V, 64]);
+ *   sa >= 0: dA[V,V] += gradient wrt support `sa` (the adaptive adjacency).  dw_mlp/db_mlp are overwritten, dA accumulated.
+ * ws_w >= 24 KiB scratch.  graph_wavenet.py:76-98 backward + :222-226 backward. */
+int gwn_gcn_bwd(const void* du, const void* a, const void* b, const void* dz_last, const void* hop_mats,
+                int n_supports, const float* w_mlp, void* ws_w, float drop_p, unsigned long long seed,
+                unsigned long long offset, int sa, void* dfg, float* dw_mlp, float* db_mlp, float* dA,
+                int N, int V, int Lout, int Lf, void* stream);
+
 /* ---- BatchNorm2d(32) folded to an affine  graph_wavenet.py:167,250 ----
  * training: mean/var from stats (count = N*L*V), scale = gamma*rstd, shift = beta - mean*scale,
  *           running <- (1-m)*running + m*(mean, unbiased var); saves mean,rstd.

@@ -83,6 +83,7 @@ struct GcnBwdParams {
   int mat_fwd;                 // image index of the FORWARD hop of support sa (variant 0)
   const bf16* w56_img;         // [4][64][8]: (n = (5|6, c'), k = c) = W_mlp[(2sa+1 | 2sa+2)*32 + c][c']
   float* dA;                   // [V, V] fp32, accumulated with atomics
+  long long* trace;            // optional debug timeline of CTA 0 (GWN_GCN_TRACE)
 };
 int gcn_bwd_fused_supported(int V, int n_mats);
 // wt_img as above; w56_img (may be NULL) for support sa

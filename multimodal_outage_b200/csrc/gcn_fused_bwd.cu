@@ -61,6 +61,8 @@ __device__ __forceinline__ void gb_unpack8(const uint4& q, float v[8]) {
   v[6] = __uint_as_float(q.w << 16); v[7] = __uint_as_float(q.w & 0xFFFF0000u);
 }
 
+#define GB_TRACE(kk, slot) do { if (p.trace && blockIdx.x == 0 && (kk) < 64 && lane == 0) p.trace[(kk) * 8 + (slot)] = clock64(); } while (0)
+
 template <int NM, int KSTEPS, bool DA>
 __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_constant__ GcnBwdParams p) {
   using namespace tc;
@@ -152,6 +154,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
         const int bb = kk & 1;
         mbar_wait(&us_full[bb], (uint32_t)((kk >> 1) & 1));
         mbar_wait(dz_empty, (uint32_t)((kk & 1) ^ 1));
+        GB_TRACE(kk + 1, 4);
         tc_fence_after();
         const uint32_t cat = sbase + L.cat_off + (uint32_t)bb * L.cat_bytes;
         const uint32_t zt = sbase + L.z_off + (uint32_t)bb * L.z_bytes;
@@ -170,6 +173,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
                       bz + (uint64_t)(((uint32_t)ks * 256u) >> 4), idescW, (kk == 0 && ks == 0) ? 0u : 1u);
         if (DA) {
           // dA += T1^T-style products: D[v, w] += sum_c T1[v,c] dh[w,c] + U6[v,c] dU5[w,c]   (all operands K-major)
+          GB_TRACE(kk + 1, 5);
           mbar_wait(&t1s_full[bb], (uint32_t)((kk >> 1) & 1));
           tc_fence_after();
           const uint64_t at1 = adm + (uint64_t)((sbase + L.t1_off + (uint32_t)bb * L.slot_bytes) >> 4);
@@ -191,6 +195,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
       for (long long slab = blockIdx.x; slab < p.slabs; slab += gridDim.x, ++k) {
         const int bb = k & 1;
         mbar_wait(&in_full[bb], (uint32_t)((k >> 1) & 1));
+        GB_TRACE(k, 0);
         if (DA) {
           // U5 | U6 = z [W_{2sa+1} | W_{2sa+2}]  (issued first: its staging overlaps the hop MMAs below)
           mbar_wait(t1_empty, (uint32_t)((k & 1) ^ 1));
@@ -204,6 +209,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
           umma_commit(u56_full);
         }
         mbar_wait(ut_empty, (uint32_t)((k & 1) ^ 1));
+        GB_TRACE(k, 1);
         tc_fence_after();
         const uint32_t cat = sbase + L.cat_off + (uint32_t)bb * L.cat_bytes;
         const uint64_t a0 = adm + (uint64_t)(sbase >> 4), b0 = bmn + (uint64_t)(cat >> 4);
@@ -215,6 +221,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
                       a0 + (uint64_t)(((uint32_t)m * ((uint32_t)(Kp / 8) * (uint32_t)Kp * 16u) + (uint32_t)(2 * ks) * (uint32_t)Kp * 16u) >> 4),
                       b0 + (uint64_t)(((uint32_t)ks * 256u) >> 4), idescH, ks == 0 ? 0u : 1u);
         umma_commit(ut_full);
+        GB_TRACE(k, 2);
         if (DA) {
           // T1 = U5 + A^T-hop(U6): accumulate the forward hop of the staged U6 onto the U5 columns
           mbar_wait(&u6s_full[bb], (uint32_t)((k >> 1) & 1));
@@ -227,7 +234,9 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
                       bu + (uint64_t)(((uint32_t)ks * 256u) >> 4), idescH, 1u);
           umma_commit(t1_full);
         }
+        GB_TRACE(k, 3);
         if (k > 0) tail(k - 1);
+        GB_TRACE(k, 6);
       }
       if (k > 0) tail(k - 1);
       umma_commit(w_full);

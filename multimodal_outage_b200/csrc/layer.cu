@@ -778,6 +778,10 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
       bp.drop_p = drop ? c->dropout_p : 0.f; bp.seed = c->seed; bp.offset = c->offset; bp.rng = g->rng;
       bp.dfg = reinterpret_cast<bf16*>(g->ws_dfg); bp.dw_mlp = g->dw_mlp; bp.db_mlp = g->db_mlp;
       bp.V = c->V; bp.slabs = c->N * c->Lout;
+      {
+        const char* e = getenv("GWN_GCN_TRACE");
+        bp.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
+      }
       bp.sa = sa; bp.mat_fwd = sa >= 0 ? 4 * sa : 0; bp.w56_img = w56; bp.dA = sa >= 0 ? g->d_supports[sa] : nullptr;
       if (int rc = launch_gcn_bwd(bp, st)) return rc;
       fused_bwd = true;
@@ -1043,6 +1047,35 @@ extern "C" int gwn_gcn_fwd(const void* z, const void* u_prev, const float* scale
     fp.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
   }
   return launch_gcn_fwd(fp, st);
+}
+
+// The fused diffusion backward alone (roofline microbenchmark): du, a, b -> dfg, dW_mlp, db_mlp, dA.
+extern "C" int gwn_gcn_bwd(const void* du, const void* a, const void* b, const void* dz_last, const void* hop_mats,
+                           int n_supports, const float* w_mlp, void* ws_w, float drop_p, unsigned long long seed,
+                           unsigned long long offset, int sa, void* dfg, float* dw_mlp, float* db_mlp, float* dA,
+                           int N, int V, int Lout, int Lf, void* stream) {
+  GWN_REQUIRE(du && a && b && hop_mats && w_mlp && ws_w && dfg && dw_mlp && db_mlp && n_supports >= 1 && Lf >= 1 && Lf <= Lout,
+              "gcn_bwd: bad argument");
+  GWN_REQUIRE(sa < n_supports && (sa < 0 || dA != nullptr), "gcn_bwd: bad support-gradient argument");
+  GWN_REQUIRE(gcn_bwd_fused_supported(V, 2 * n_supports), "gcn_bwd: V=%d with %d supports does not fit on chip", V, n_supports);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int mlp_in = 32 * (1 + 2 * n_supports);
+  GWN_CUDA(cudaMemsetAsync(dw_mlp, 0, sizeof(float) * 32 * mlp_in, st));
+  GWN_CUDA(cudaMemsetAsync(db_mlp, 0, sizeof(float) * 32, st));
+  uint8_t* wsw = reinterpret_cast<uint8_t*>(ws_w);
+  bf16* wt = reinterpret_cast<bf16*>(wsw);
+  bf16* w56 = reinterpret_cast<bf16*>(wsw + 16 * 1024);
+  if (int rc = launch_gcn_bwd_wprep(w_mlp, 2 * n_supports, wt, sa, w56, st)) return rc;
+  GcnBwdParams bp{};
+  bp.du = reinterpret_cast<const bf16*>(du); bp.a = reinterpret_cast<const bf16*>(a); bp.b = reinterpret_cast<const bf16*>(b);
+  bp.dz_last = reinterpret_cast<const bf16*>(dz_last);
+  bp.RO = (long long)Lout * V; bp.last_begin = (long long)(Lout - Lf) * V; bp.last_rows = (long long)Lf * V;
+  bp.mats = reinterpret_cast<const bf16*>(hop_mats); bp.n_mats = 2 * n_supports;
+  for (int j = 0; j < bp.n_mats; ++j) bp.mat_src[j] = 4 * (j / 2) + 2 + (j % 2);
+  bp.wt_img = wt; bp.mask = nullptr; bp.drop_p = drop_p; bp.seed = seed; bp.offset = offset; bp.rng = nullptr;
+  bp.dfg = reinterpret_cast<bf16*>(dfg); bp.dw_mlp = dw_mlp; bp.db_mlp = db_mlp; bp.V = V; bp.slabs = N * Lout;
+  bp.sa = sa; bp.mat_fwd = sa >= 0 ? 4 * sa : 0; bp.w56_img = w56; bp.dA = dA; bp.trace = nullptr;
+  return launch_gcn_bwd(bp, st);
 }
 
 extern "C" int gwn_node_mix(const void* x, int x_pitch, int x_off, void* y, int y_pitch, int y_off, int accumulate,
