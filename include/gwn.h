@@ -59,6 +59,16 @@ int gwn_start_fwd(const float* x, const float* w, const float* b, void* u0, int 
 int gwn_start_bwd(const float* x, const float* w, const void* du0, int dtype, float* dw, float* db,
                   float* dx, int N, int Cin, int V, int T, int L0, void* stream);
 
+/* start_conv on the tensor cores for wide inputs (Cin >= 64, Cin % 8 == 0: config 4's 256 UNet features + 64
+ * date2vec; csrc/start_tc.cu).  Forward also writes xcl = the input in channels-last bf16 [N,L0,V,Cin] (time
+ * left-padded), which the backward consumes.  ws_w: >= 128*Cin bytes (bf16 W and W^T), the SAME buffer in fwd and bwd.
+ * ws_dx: >= N*L0*V*Cin*2 bytes, only when dx != NULL. */
+int gwn_start_tc_supported(int Cin);
+int gwn_start_fwd_tc(const float* x, const float* w, const float* b, void* xcl, void* u0, void* ws_w, int N,
+                     int Cin, int V, int T, int L0, void* stream);
+int gwn_start_bwd_tc(const void* xcl, const void* du0, void* ws_w, float* dw, float* db, float* dx, void* ws_dx,
+                     int N, int Cin, int V, int T, int L0, void* stream);
+
 /* ---- one WaveNet layer  graph_wavenet.py:206-250 ----
  * forward:  r = bn_prev(u_prev)  (folded affine: r = u_prev*scale + shift, NULL = identity)
  *           (f,g) = dilated conv k taps  (:222,224)      z = tanh(f)*sigmoid(g)  (:223-226)

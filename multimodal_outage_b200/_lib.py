@@ -78,6 +78,9 @@ SIGNATURES = {
     'gwn_adp_bwd': (_i, [vp, vp, vp, vp, vp, vp, vp, _i, _i, vp]),
     'gwn_start_fwd': (_i, [vp, vp, vp, vp, _i, _i, _i, _i, _i, _i, vp]),
     'gwn_start_bwd': (_i, [vp, vp, vp, _i, vp, vp, vp, _i, _i, _i, _i, _i, vp]),
+    'gwn_start_tc_supported': (_i, [_i]),
+    'gwn_start_fwd_tc': (_i, [vp, vp, vp, vp, vp, vp, _i, _i, _i, _i, _i, vp]),
+    'gwn_start_bwd_tc': (_i, [vp, vp, vp, vp, vp, vp, vp, _i, _i, _i, _i, _i, vp]),
     'gwn_layer_fwd': (_i, [C.POINTER(LayerCfg), C.POINTER(LayerFwdArgs), vp]),
     'gwn_layer_bwd': (_i, [C.POINTER(LayerCfg), C.POINTER(LayerBwdArgs), vp]),
     'gwn_gcn_fwd': (_i, [vp, vp, vp, vp, vp, _i, vp, vp, vp, _f, C.c_uint64, C.c_uint64, vp, vp, _i, _i, _i, _i, vp]),

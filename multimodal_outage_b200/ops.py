@@ -137,6 +137,50 @@ def _(x, w, du0, need_dx):
             torch.empty_like(x) if need_dx else x.new_empty((0,)))
 
 
+@torch.library.custom_op('gwn::start_fwd_tc', mutates_args=())
+def start_fwd_tc(x: Tensor, w: Tensor, b: Tensor, L0: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """Wide-input start conv on tensor cores: returns (u0 bf16 [N,L0,V,32], xcl bf16 [N,L0,V,Cin], ws_w)."""
+    _req(x, torch.float32, 'input'); _req(w, torch.float32, 'start_conv.weight'); _req(b, torch.float32)
+    N, Cin, V, T = x.shape
+    dev = x.device
+    u0 = torch.empty((N, L0, V, CH), device=dev, dtype=torch.bfloat16)
+    xcl = torch.empty((N, L0, V, Cin), device=dev, dtype=torch.bfloat16)
+    ws_w = torch.empty((2 * CH * Cin,), device=dev, dtype=torch.bfloat16)
+    with torch.cuda.device(dev):
+        check(lib().gwn_start_fwd_tc(_p(x), _p(w), _p(b), _p(xcl), _p(u0), _p(ws_w), N, Cin, V, T, L0, _stream()),
+              'gwn_start_fwd_tc')
+    return u0, xcl, ws_w
+
+
+@start_fwd_tc.register_fake
+def _(x, w, b, L0):
+    N, Cin, V, T = x.shape
+    return (x.new_empty((N, L0, V, CH), dtype=torch.bfloat16), x.new_empty((N, L0, V, Cin), dtype=torch.bfloat16),
+            x.new_empty((2 * CH * Cin,), dtype=torch.bfloat16))
+
+
+@torch.library.custom_op('gwn::start_bwd_tc', mutates_args=())
+def start_bwd_tc(xcl: Tensor, ws_w: Tensor, du0: Tensor, T: int, need_dx: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    _req(du0, torch.bfloat16, 'du0')
+    N, L0, V, Cin = xcl.shape
+    dev = xcl.device
+    dw = torch.empty((CH, Cin), device=dev, dtype=torch.float32)
+    db = torch.empty((CH,), device=dev, dtype=torch.float32)
+    dx = torch.empty((N, Cin, V, T) if need_dx else (0,), device=dev, dtype=torch.float32)
+    ws_dx = torch.empty((N * L0 * V * Cin,) if need_dx else (0,), device=dev, dtype=torch.bfloat16)
+    with torch.cuda.device(dev):
+        check(lib().gwn_start_bwd_tc(_p(xcl), _p(du0), _p(ws_w), _p(dw), _p(db), _p(dx) if need_dx else None,
+                                     _p(ws_dx) if need_dx else None, N, Cin, V, T, L0, _stream()), 'gwn_start_bwd_tc')
+    return dw, db, dx
+
+
+@start_bwd_tc.register_fake
+def _(xcl, ws_w, du0, T, need_dx):
+    N, L0, V, Cin = xcl.shape
+    return (xcl.new_empty((CH, Cin), dtype=torch.float32), xcl.new_empty((CH,), dtype=torch.float32),
+            xcl.new_empty((N, Cin, V, T) if need_dx else (0,), dtype=torch.float32))
+
+
 class StartConv(torch.autograd.Function):
     """1x1 conv Cin->32 fused with the left zero-pad and the NCHW -> channels-last change."""
 
@@ -144,15 +188,25 @@ class StartConv(torch.autograd.Function):
     def forward(ctx, x, w, b, L0, bf16):
         xc = x.contiguous().float()
         w2 = w.reshape(CH, -1).contiguous()
+        ctx.wshape = w.shape
+        ctx.tc = bool(bf16) and bool(lib().gwn_start_tc_supported(xc.shape[1]))
+        if ctx.tc:      # wide inputs (config 4): transpose to channels-last bf16 once, then a tensor-core GEMM
+            u0, xcl, ws_w = start_fwd_tc(xc, w2, b.contiguous(), L0)
+            ctx.save_for_backward(xcl, ws_w)
+            ctx.T = xc.shape[3]
+            return u0
         u0 = start_fwd(xc, w2, b.contiguous(), L0, bf16)
         ctx.save_for_backward(xc, w2)
-        ctx.wshape = w.shape
         return u0
 
     @staticmethod
     def backward(ctx, du0):
-        xc, w2 = ctx.saved_tensors
         need_dx = ctx.needs_input_grad[0]
+        if ctx.tc:
+            xcl, ws_w = ctx.saved_tensors
+            dw, db, dx = start_bwd_tc(xcl, ws_w, du0.contiguous(), ctx.T, need_dx)
+            return (dx if need_dx else None), dw.reshape(ctx.wshape), db, None, None
+        xc, w2 = ctx.saved_tensors
         dw, db, dx = start_bwd(xc, w2, du0.contiguous(), need_dx)
         return (dx if need_dx else None), dw.reshape(ctx.wshape), db, None, None
 

@@ -221,6 +221,15 @@ def test_wide_input_in_dim_320_and_long_T():
     _oracle_case(cfg, case_supports('fl'), n=3, t_in=9, seed=16, dtype=torch.float32, tol=FP32_TOL)
 
 
+def test_wide_input_in_dim_320_bf16_start_conv_on_tensor_cores():
+    """Config-4 style input (256 features + 64 date2vec channels): the start conv runs as a TMA-fed tcgen05 GEMM on
+    a channels-last bf16 copy of the input; whole-model bf16 bar incl. the gradient wrt the input."""
+    cfg = GWNetConfig(num_nodes=67, in_dim=320, out_dim=256, kernel_size=2, blocks=2, layers=2,
+                      skip_channels=64, end_channels=64, dropout=0.0)
+    _oracle_case(cfg, case_supports('fl'), n=3, t_in=9, seed=16, dtype=torch.bfloat16, tol=BF16_TOL)
+    _oracle_case(cfg, case_supports('fl'), n=2, t_in=3, seed=17, dtype=torch.bfloat16, tol=BF16_TOL)    # padded time
+
+
 def test_fused_dropout_is_a_valid_mask():
     cfg = GWNetConfig(num_nodes=67, in_dim=2, out_dim=12, kernel_size=2, blocks=1, layers=2, dropout=0.3)
     m = build_model(cfg, case_supports('dir'))
