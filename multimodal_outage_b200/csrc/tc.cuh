@@ -40,6 +40,9 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
   return ok;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // not unrolled: the compiler otherwise clones the poll dozens of times per call site, and the rarely-running
+  // producer / MMA threads then pay instruction-cache misses at every hand-off
+#pragma unroll 1
   for (uint32_t i = 0; i < (1u << 24); ++i) {
     if (mbar_try_wait(bar, parity)) return;
   }

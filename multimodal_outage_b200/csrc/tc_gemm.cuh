@@ -33,6 +33,7 @@ struct PgParams {
   int rows_out;                 // output rows per (virtual) sample
   int map_of[PG_TC_MAX_CHUNKS]; // chunk -> tensor map
   int row_off[PG_TC_MAX_CHUNKS];
+  long long* trace;             // optional debug timeline of CTA 0 (GWN_PG_TRACE)
 };
 
 // builds w_img (+ folded bias) from fp32 weights; see tc_gemm.cu

@@ -6,6 +6,8 @@
 //        functor may use warp collectives (the BN-statistics reduction does).
 //   __device__ void finish();     called once per epilogue warp after its last tile (flush statistics)
 #pragma once
+#include <cstdlib>
+
 #include "tc.cuh"
 #include "tc_gemm.cuh"
 #include "tma_gemm.cuh"
@@ -33,6 +35,7 @@ __device__ __forceinline__ float warp_column_sums(float v[32], int lane) {
 }
 
 struct PgMaps { CUtensorMap m[PG_TC_MAX_MAPS]; };
+#define PG_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && g < 48 && lane == 0) p.trace[g * 8 + (slot)] = clock64(); } while (0)
 
 // A operand: per chunk one TMA box -> [128 rows][64 B] 64B-swizzled (K-major SW64: 8-row atoms of 512 B, the two
 // K=16 halves of a chunk 32 B apart); B operand: resident no-swizzle weight image; D: two TMEM accumulators.
@@ -84,10 +87,12 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
         const int stage = g % stages, phase = (g / stages) & 1;
         const int n = tile / p.tiles_per_n, r0 = (tile - n * p.tiles_per_n) * 128;
         mbar_wait(&empty[stage], (uint32_t)(phase ^ 1));
+        PG_TRACE(0);
         tg::mbar_expect_tx(&full[stage], a_bytes);
         const uint32_t sa = base + (uint32_t)stage * a_bytes;
         for (int q = 0; q < p.n_chunks; ++q)
           tg::tma_3d(sa + (uint32_t)q * 8192u, &maps.m[p.map_of[q]], 0, r0 + p.row_off[q], n, &full[stage]);
+        PG_TRACE(1);
       }
     }
     __syncwarp();
@@ -99,7 +104,9 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const int stage = g % stages, acc = g & 1;
         mbar_wait(&tempty[acc], (uint32_t)(((g >> 1) & 1) ^ 1));
+        PG_TRACE(2);
         mbar_wait(&full[stage], (uint32_t)((g / stages) & 1));
+        PG_TRACE(3);
         tc_fence_after();
         const uint32_t sa = base + (uint32_t)stage * a_bytes;
         for (int ks = 0; ks < K8 / 2; ++ks) {
@@ -109,6 +116,7 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
         }
         umma_commit(&empty[stage]);
         umma_commit(&tfull[acc]);
+        PG_TRACE(4);
         ++g;
       }
     }
@@ -121,6 +129,7 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const int acc = g & 1;
       mbar_wait(&tfull[acc], (uint32_t)((g >> 1) & 1));
+      if (warp == PGT_MMA_WARP + 1) PG_TRACE(5);
       tc_fence_after();
       const int ns = tile / p.tiles_per_n;
       const int r = (tile - ns * p.tiles_per_n) * 128 + quad * 32 + lane;
@@ -135,6 +144,7 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
       }
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
+      if (warp == PGT_MMA_WARP + 1) PG_TRACE(6);
       ++g;
     }
     epi.finish();
@@ -185,6 +195,10 @@ int launch_pos_gemm_tc(PgParams& p, const Epi& epi, cudaStream_t st) {
     p.row_off[q] = (int)c.row_off;
   }
   for (int i = n_maps; i < PG_TC_MAX_MAPS; ++i) maps.m[i] = maps.m[0];
+  {
+    const char* e = getenv("GWN_PG_TRACE");
+    p.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
+  }
   const size_t w_bytes = ((size_t)p.n_chunks * 4 * p.N * 16 + 1023) & ~(size_t)1023;
   const size_t a_bytes = (size_t)p.n_chunks * 8192;
   int stages = (int)((220 * 1024 - w_bytes - 1024 - 256) / a_bytes);
