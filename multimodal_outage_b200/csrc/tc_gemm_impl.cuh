@@ -100,6 +100,10 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, N, false, false);
       const uint32_t w_addr = smem_u32(w_s);
+      // descriptor templates: only the 14-bit start-address field changes per MMA (addresses < 256 KB: no carry)
+      const uint64_t at = tg::make_desc_sw(0, 16u, 512u, 4u);
+      const uint64_t bt = make_smem_desc(w_addr, (uint32_t)N * 16u, 128u);
+      const uint32_t bstep = ((uint32_t)N * 32u) >> 4;            // two K pieces of the weight image per K=16 step
       int g = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const int stage = g % stages, acc = g & 1;
@@ -108,11 +112,15 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
         mbar_wait(&full[stage], (uint32_t)((g / stages) & 1));
         PG_TRACE(3);
         tc_fence_after();
-        const uint32_t sa = base + (uint32_t)stage * a_bytes;
-        for (int ks = 0; ks < K8 / 2; ++ks) {
-          const uint64_t adesc = tg::make_desc_sw(sa + (uint32_t)(ks >> 1) * 8192u + (uint32_t)(ks & 1) * 32u, 16u, 512u, 4u);
-          const uint64_t bdesc = make_smem_desc(w_addr + (uint32_t)(2 * ks) * (uint32_t)N * 16u, (uint32_t)N * 16u, 128u);
-          umma_bf16(tmem_base + (uint32_t)acc * acc_cols, adesc, bdesc, idesc, ks == 0 ? 0u : 1u);
+        uint64_t ad = at + (uint64_t)((base + (uint32_t)stage * a_bytes) >> 4);
+        uint64_t bd = bt;
+        const uint32_t d = tmem_base + (uint32_t)acc * acc_cols;
+#pragma unroll 2
+        for (int q = 0; q < p.n_chunks; ++q) {
+          umma_bf16(d, ad, bd, idesc, q == 0 ? 0u : 1u);
+          umma_bf16(d, ad + 2u, bd + bstep, idesc, 1u);            // second K=16 half of the chunk: +32 B
+          ad += 8192u >> 4;
+          bd += 2u * bstep;
         }
         umma_commit(&empty[stage]);
         umma_commit(&tfull[acc]);
