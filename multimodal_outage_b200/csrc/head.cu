@@ -128,6 +128,73 @@ __global__ void __launch_bounds__(256) start_bwd_x_kernel(const float* __restric
   }
 }
 
+// ------------------------------------------------------------------------------------------ start conv, narrow input
+// Cin <= 8 (config 1-3, 5: in_dim = 2): the contraction is a handful of FMAs per output, so one warp handles one
+// position with lane = output channel; the Cin inputs of a position are uniform (broadcast) loads.
+template <typename T, int CIN>
+__global__ void __launch_bounds__(256) start_fwd_small_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                              const float* __restrict__ b, T* __restrict__ u0, int N,
+                                                              int V, int Tn, int L0) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float wr[CIN];
+#pragma unroll
+  for (int i = 0; i < CIN; ++i) wr[i] = w[lane * CIN + i];
+  const float bias = b[lane];
+  const int pad = L0 - Tn;
+  const long long P = (long long)N * L0 * V;
+  for (uint32_t p = blockIdx.x * 8u + warp; p < (uint32_t)P; p += gridDim.x * 8u) {     // launcher: P < 2^31
+    const uint32_t r = p / (uint32_t)V;
+    const int v = (int)(p - r * (uint32_t)V);
+    const long long n = r / (uint32_t)L0;
+    const int l = (int)(r - (uint32_t)n * (uint32_t)L0);
+    float acc = bias;
+    if (l >= pad) {
+      const float* xr = x + ((n * CIN) * V + v) * (long long)Tn + (l - pad);
+#pragma unroll
+      for (int i = 0; i < CIN; ++i) acc = fmaf(wr[i], __ldg(xr + (long long)i * V * Tn), acc);
+    }
+    st1(u0 + (size_t)p * 32 + lane, acc);
+  }
+}
+
+// dw[c][ci] += sum_p du[p][c] x[p][ci], db[c] += sum_p du[p][c]: lane = c, per-lane accumulators, one reduction at the end
+template <typename T, int CIN>
+__global__ void __launch_bounds__(256) start_bwd_w_small_kernel(const float* __restrict__ x, const T* __restrict__ du,
+                                                                float* __restrict__ dw, float* __restrict__ db, int N,
+                                                                int V, int Tn, int L0) {
+  __shared__ float red[8][32][CIN + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int pad = L0 - Tn;
+  const long long P = (long long)N * L0 * V;
+  float acc[CIN], bacc = 0.f;
+#pragma unroll
+  for (int i = 0; i < CIN; ++i) acc[i] = 0.f;
+  for (uint32_t p = blockIdx.x * 8u + warp; p < (uint32_t)P; p += gridDim.x * 8u) {     // launcher: P < 2^31
+    const uint32_t r = p / (uint32_t)V;
+    const int v = (int)(p - r * (uint32_t)V);
+    const long long n = r / (uint32_t)L0;
+    const int l = (int)(r - (uint32_t)n * (uint32_t)L0);
+    const float g = ld1(du + (size_t)p * 32 + lane);
+    bacc += g;
+    if (l >= pad) {
+      const float* xr = x + ((n * CIN) * V + v) * (long long)Tn + (l - pad);
+#pragma unroll
+      for (int i = 0; i < CIN; ++i) acc[i] = fmaf(g, __ldg(xr + (long long)i * V * Tn), acc[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < CIN; ++i) red[warp][lane][i] = acc[i];
+  red[warp][lane][CIN] = bacc;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * (CIN + 1); i += 256) {
+    const int c = i / (CIN + 1), k = i % (CIN + 1);
+    float s = 0.f;
+#pragma unroll
+    for (int wq = 0; wq < 8; ++wq) s += red[wq][c][k];
+    if (k < CIN) atomicAdd(dw + c * CIN + k, s); else atomicAdd(db + c, s);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ head epilogues
 struct EpiBiasAct {  // out[p, col] = act(acc + bias)
   static constexpr bool kStats = false;
@@ -281,6 +348,17 @@ extern "C" int gwn_start_fwd(const float* x, const float* w, const float* b, voi
                              int V, int T, int L0, void* stream) {
   GWN_REQUIRE(x && w && b && u0 && N >= 1 && Cin >= 1 && V >= 1 && T >= 1 && L0 >= T, "start_fwd: bad argument");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if ((Cin == 2 || Cin == 1 || Cin == 4) && (long long)N * L0 * V < (1ll << 31)) {   // narrow inputs: warp-per-position kernel (64-bit index math only, no smem)
+    const unsigned nb = 148 * 8;
+#define GWN_SF(CI)                                                                                                   \
+  if (dtype == GWN_F32) start_fwd_small_kernel<float, CI><<<nb, 256, 0, st>>>(x, w, b, (float*)u0, N, V, T, L0);      \
+  else if (dtype == GWN_BF16) start_fwd_small_kernel<bf16, CI><<<nb, 256, 0, st>>>(x, w, b, (bf16*)u0, N, V, T, L0);  \
+  else GWN_REQUIRE(false, "bad dtype %d", dtype);
+    if (Cin == 1) { GWN_SF(1) } else if (Cin == 2) { GWN_SF(2) } else { GWN_SF(4) }
+#undef GWN_SF
+    GWN_LAUNCHED();
+    return 0;
+  }
   long long items = (long long)N * V * ((L0 + 3) / 4);
   unsigned blocks = (unsigned)cdiv(items, 8);
   if (dtype == GWN_F32) start_fwd_kernel<float><<<blocks, 256, 0, st>>>(x, w, b, (float*)u0, N, Cin, V, T, L0);
@@ -298,6 +376,15 @@ extern "C" int gwn_start_bwd(const float* x, const float* w, const void* du0, in
   GWN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * 32 * (size_t)Cin, st));
   GWN_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * 32, st));
   const long long P = (long long)N * L0 * V;
+  if ((Cin == 2 || Cin == 1 || Cin == 4) && P < (1ll << 31)) {
+    const unsigned nb = 148 * 4;
+#define GWN_SB(CI)                                                                                                       \
+  if (dtype == GWN_F32) start_bwd_w_small_kernel<float, CI><<<nb, 256, 0, st>>>(x, (const float*)du0, dw, db, N, V, T, L0); \
+  else start_bwd_w_small_kernel<bf16, CI><<<nb, 256, 0, st>>>(x, (const bf16*)du0, dw, db, N, V, T, L0);
+    if (Cin == 1) { GWN_SB(1) } else if (Cin == 2) { GWN_SB(2) } else { GWN_SB(4) }
+#undef GWN_SB
+    GWN_LAUNCHED();
+  } else {
   int cchunks = (Cin + 31) / 32;
   long long want_blocks = cdiv(148 * 8, cchunks);
   long long per = cdiv(P, want_blocks);
@@ -306,6 +393,7 @@ extern "C" int gwn_start_bwd(const float* x, const float* w, const void* du0, in
   if (dtype == GWN_F32) start_bwd_w_kernel<float><<<grid, 256, 0, st>>>(x, (const float*)du0, dw, db, N, Cin, V, T, L0, per);
   else start_bwd_w_kernel<bf16><<<grid, 256, 0, st>>>(x, (const bf16*)du0, dw, db, N, Cin, V, T, L0, per);
   GWN_LAUNCHED();
+  }
   if (dx) {
     long long items = (long long)N * V * T;
     unsigned blocks = (unsigned)cdiv(items, 8);
