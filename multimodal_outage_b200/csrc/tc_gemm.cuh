@@ -30,6 +30,7 @@ struct PgParams {
   // filled by the launcher: TMA tiling.  A tile is 128 consecutive output rows of ONE sample, so that a chunk
   // (temporal tap / concat slot) is one 3-D box {32 ch, 128 rows, 1 sample} whose out-of-range rows TMA zero-fills.
   int tiles_per_n, n_samples;
+  int sub;                      // 128-row sub-tiles per pipeline step (macro tile = 128*sub rows): amortises hand-offs
   int rows_out;                 // output rows per (virtual) sample
   int map_of[PG_TC_MAX_CHUNKS]; // chunk -> tensor map
   int row_off[PG_TC_MAX_CHUNKS];

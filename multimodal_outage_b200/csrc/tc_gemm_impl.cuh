@@ -50,7 +50,8 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
   uint8_t* smem = smem_raw + (base - raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.N, K8 = p.n_chunks * 4;                     // 16-byte K pieces per weight row
-  const uint32_t a_bytes = (uint32_t)p.n_chunks * 8192u;      // one stage: n_chunks boxes of 128 x 64 B
+  const int SUB = p.sub;
+  const uint32_t a_bytes = (uint32_t)p.n_chunks * 8192u * (uint32_t)SUB;   // one stage: SUB x n_chunks boxes of 128 x 64 B
   const uint32_t w_bytes = ((uint32_t)K8 * (uint32_t)N * 16u + 1023u) & ~1023u;
   uint8_t* a_s = smem;                                        // stages first (1024-aligned boxes)
   uint8_t* w_s = smem + (size_t)stages * a_bytes;
@@ -67,7 +68,8 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
     fence_barrier_init();
   }
   const uint32_t acc_cols = N <= 32 ? 32u : N <= 64 ? 64u : N <= 128 ? 128u : 256u;
-  if (warp == PGT_MMA_WARP) tmem_alloc(tmem_slot, 2 * acc_cols);
+  const uint32_t buf_cols = acc_cols * (uint32_t)SUB;          // one accumulator buffer: SUB sub-tiles side by side
+  if (warp == PGT_MMA_WARP) tmem_alloc(tmem_slot, 2 * buf_cols);
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.w_img);
     uint4* dst = reinterpret_cast<uint4*>(w_s);
@@ -85,13 +87,19 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
       int g = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++g) {
         const int stage = g % stages, phase = (g / stages) & 1;
-        const int n = tile / p.tiles_per_n, r0 = (tile - n * p.tiles_per_n) * 128;
         mbar_wait(&empty[stage], (uint32_t)(phase ^ 1));
         PG_TRACE(0);
         tg::mbar_expect_tx(&full[stage], a_bytes);
         const uint32_t sa = base + (uint32_t)stage * a_bytes;
-        for (int q = 0; q < p.n_chunks; ++q)
-          tg::tma_3d(sa + (uint32_t)q * 8192u, &maps.m[p.map_of[q]], 0, r0 + p.row_off[q], n, &full[stage]);
+        for (int t = 0; t < SUB; ++t) {
+          // sub-tile st = 128 consecutive rows of ONE sample; past the last sub-tile the sample index is out of range
+          // and TMA zero-fills the box
+          const int st = tile * SUB + t;
+          const int n = st / p.tiles_per_n, r0 = (st - n * p.tiles_per_n) * 128;
+          for (int q = 0; q < p.n_chunks; ++q)
+            tg::tma_3d(sa + (uint32_t)(t * p.n_chunks + q) * 8192u, &maps.m[p.map_of[q]], 0, r0 + p.row_off[q], n,
+                       &full[stage]);
+        }
         PG_TRACE(1);
       }
     }
@@ -113,14 +121,16 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
         PG_TRACE(3);
         tc_fence_after();
         uint64_t ad = at + (uint64_t)((base + (uint32_t)stage * a_bytes) >> 4);
-        uint64_t bd = bt;
-        const uint32_t d = tmem_base + (uint32_t)acc * acc_cols;
+        for (int t = 0; t < SUB; ++t) {
+          uint64_t bd = bt;
+          const uint32_t d = tmem_base + (uint32_t)acc * buf_cols + (uint32_t)t * acc_cols;
 #pragma unroll 2
-        for (int q = 0; q < p.n_chunks; ++q) {
-          umma_bf16(d, ad, bd, idesc, q == 0 ? 0u : 1u);
-          umma_bf16(d, ad + 2u, bd + bstep, idesc, 1u);            // second K=16 half of the chunk: +32 B
-          ad += 8192u >> 4;
-          bd += 2u * bstep;
+          for (int q = 0; q < p.n_chunks; ++q) {
+            umma_bf16(d, ad, bd, idesc, q == 0 ? 0u : 1u);
+            umma_bf16(d, ad + 2u, bd + bstep, idesc, 1u);            // second K=16 half of the chunk: +32 B
+            ad += 8192u >> 4;
+            bd += 2u * bstep;
+          }
         }
         umma_commit(&empty[stage]);
         umma_commit(&tfull[acc]);
@@ -139,16 +149,19 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
       mbar_wait(&tfull[acc], (uint32_t)((g >> 1) & 1));
       if (warp == PGT_MMA_WARP + 1) PG_TRACE(5);
       tc_fence_after();
-      const int ns = tile / p.tiles_per_n;
-      const int r = (tile - ns * p.tiles_per_n) * 128 + quad * 32 + lane;
-      const bool pv = r < p.rows_out;
-      // (sample, row) of the caller's view: virtual samples (position-wise GEMMs tile the flat position axis)
-      long long pp = (long long)ns * p.rows_out + r, n = ns, rem = r;
-      if (p.rows_out != (int)p.rows_per_n_out && pv) split_pos(pp, p.rows_per_n_out, n, rem);
-      for (int c0 = half * 32; c0 < N; c0 += 64) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)c0, v);
-        epi.chunk(pp, n, rem, pv, c0, v);
+      for (int t = 0; t < SUB; ++t) {
+        const int st = tile * SUB + t;
+        const int ns = st / p.tiles_per_n;
+        const int r = (st - ns * p.tiles_per_n) * 128 + quad * 32 + lane;
+        const bool pv = r < p.rows_out && ns < p.n_samples;
+        // (sample, row) of the caller's view: virtual samples (position-wise GEMMs tile the flat position axis)
+        long long pp = (long long)ns * p.rows_out + r, n = ns, rem = r;
+        if (p.rows_out != (int)p.rows_per_n_out && pv) split_pos(pp, p.rows_per_n_out, n, rem);
+        for (int c0 = half * 32; c0 < N; c0 += 64) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * buf_cols + (uint32_t)t * acc_cols + (uint32_t)c0, v);
+          epi.chunk(pp, n, rem, pv, c0, v);
+        }
       }
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
@@ -161,7 +174,7 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
   __syncthreads();
   if (warp == PGT_MMA_WARP) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * acc_cols);
+    tmem_dealloc(tmem_base, 2 * buf_cols);
   }
 }
 
@@ -179,8 +192,16 @@ int launch_pos_gemm_tc(PgParams& p, const Epi& epi, cudaStream_t st) {
   GWN_REQUIRE(n_real * p.rows_per_n_out == p.P, "pos_gemm_tc: P is not a whole number of samples");
   p.rows_out = flat ? (int)p.P : (int)p.rows_per_n_out;
   p.n_samples = flat ? 1 : (int)n_real;
-  p.tiles_per_n = (int)cdiv(p.rows_out, 128);
-  p.n_tiles = p.n_samples * p.tiles_per_n;
+  // macro tiles: several 128-row sub-tiles per pipeline step when the accumulators are narrow (the producer / MMA
+  // threads pay ~0.5 us of hand-off latency per step whatever the tile holds)
+  const int acc_c = p.N <= 32 ? 32 : p.N <= 64 ? 64 : p.N <= 128 ? 128 : 256;
+  p.sub = 1;
+  p.tiles_per_n = (int)cdiv(p.rows_out, 128);                     // 128-row sub-tiles per (virtual) sample
+  const long long sub_tiles = (long long)p.n_samples * p.tiles_per_n;
+  while (p.sub < 4 && 2 * acc_c * (p.sub * 2) <= 512 && (size_t)p.n_chunks * 8192 * (p.sub * 2) * 2 <= 150 * 1024 &&
+         cdiv(sub_tiles, p.sub * 2) >= 2 * tg_sm_count())
+    p.sub *= 2;
+  p.n_tiles = (int)cdiv(sub_tiles, p.sub);
   PgMaps maps;
   int n_maps = 0;
   struct Key { const bf16* base; long long rows; int pitch, col; } keys[PG_TC_MAX_MAPS];
@@ -208,7 +229,7 @@ int launch_pos_gemm_tc(PgParams& p, const Epi& epi, cudaStream_t st) {
     p.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
   }
   const size_t w_bytes = ((size_t)p.n_chunks * 4 * p.N * 16 + 1023) & ~(size_t)1023;
-  const size_t a_bytes = (size_t)p.n_chunks * 8192;
+  const size_t a_bytes = (size_t)p.n_chunks * 8192 * p.sub;
   int stages = (int)((220 * 1024 - w_bytes - 1024 - 256) / a_bytes);
   if (stages > 4) stages = 4;
   GWN_REQUIRE(stages >= 2, "pos_gemm_tc: K=%d does not fit 2 stages in shared memory", 32 * p.n_chunks);

@@ -411,7 +411,7 @@ class WaveNetLayer(torch.autograd.Function):
             du = None
         has_du = du is not None and m['has_gconv']
         outs = layer_bwd(u_prev, scale, shift, w_fg, w_mlp if has_du else None, sup if has_du else [],
-                         ctx.sup_needs if has_du else [], drop_mask, rng, hop_mats if has_du else None, a, b,
+                         ctx.sup_needs if has_du else [], drop_mask, rng, hop_mats, a, b,
                          du.contiguous() if has_du else None,
                          dz_last.contiguous() if dz_last is not None else None,
                          m['Lf'], m['taps'], m['dilation'], m['order'], True, m['dropout_p'], m['seed'],
