@@ -16,7 +16,7 @@ namespace gwn {
 
 constexpr int PGT_PRODUCERS = 128;   // warps 0-3 (warp 0 lane 0 issues the TMA copies)
 constexpr int PGT_MMA_WARP = 4;
-constexpr int PGT_EPI_WARPS = 8;     // warps 5-12, two per TMEM lane quadrant (they split the 32-column chunks)
+constexpr int PGT_EPI_WARPS = 12;    // warps 5-16, three per TMEM lane quadrant: they share the (sub-tile, 32-column chunk) items
 constexpr int PGT_THREADS = 32 * (5 + PGT_EPI_WARPS);
 
 // lane c of the warp ends up with sum over the 32 lanes of v[c]  (31 shuffles; v is destroyed)
@@ -142,14 +142,17 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
   } else if (warp > PGT_MMA_WARP) {
     // ===================== epilogue =====================
     const int quad = warp & 3;
-    const int half = (warp - (PGT_MMA_WARP + 1)) >> 2;
+    const int rank = (warp - (PGT_MMA_WARP + 1)) >> 2;          // 0..2: which of the quadrant's three warps
+    const int n_c32 = (N + 31) / 32;                            // 32-column chunks per sub-tile
     int g = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const int acc = g & 1;
       mbar_wait(&tfull[acc], (uint32_t)((g >> 1) & 1));
       if (warp == PGT_MMA_WARP + 1) PG_TRACE(5);
       tc_fence_after();
-      for (int t = 0; t < SUB; ++t) {
+      // work items (sub-tile t, chunk c) dealt round-robin to the quadrant's warps
+      for (int item = rank; item < SUB * n_c32; item += PGT_EPI_WARPS / 4) {
+        const int t = item / n_c32, c0 = (item - t * n_c32) * 32;
         const int st = tile * SUB + t;
         const int ns = st / p.tiles_per_n;
         const int r = (st - ns * p.tiles_per_n) * 128 + quad * 32 + lane;
@@ -157,11 +160,9 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
         // (sample, row) of the caller's view: virtual samples (position-wise GEMMs tile the flat position axis)
         long long pp = (long long)ns * p.rows_out + r, n = ns, rem = r;
         if (p.rows_out != (int)p.rows_per_n_out && pv) split_pos(pp, p.rows_per_n_out, n, rem);
-        for (int c0 = half * 32; c0 < N; c0 += 64) {
-          float v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * buf_cols + (uint32_t)t * acc_cols + (uint32_t)c0, v);
-          epi.chunk(pp, n, rem, pv, c0, v);
-        }
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * buf_cols + (uint32_t)t * acc_cols + (uint32_t)c0, v);
+        epi.chunk(pp, n, rem, pv, c0, v);
       }
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
