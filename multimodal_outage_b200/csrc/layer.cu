@@ -123,14 +123,20 @@ __device__ __forceinline__ void store_bf16x16(bf16* dst, const float v[16]) {
 }
 
 struct EpiGateTC {   // N = 64 interleaved (f,g); a chunk of 32 columns = 16 channels
+  static constexpr bool kExtra = false;
   const float* bias;
   bf16* z; bf16* a; bf16* b; bf16* z_last; long long last_begin, last_rows;
   __device__ __forceinline__ void chunk(long long p, long long n, long long rem, bool valid, int c0, float v[32]) {
     if (!valid) return;
-    float zz[16], aa[16], bb[16];
+    float zz[16], aa[16], bb[16], bs[32];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {       // 8 vector loads instead of 32 scalar ones (the LSU queue was the stall)
+      const float4 t = __ldg(reinterpret_cast<const float4*>(bias + c0) + i);
+      bs[4 * i] = t.x; bs[4 * i + 1] = t.y; bs[4 * i + 2] = t.z; bs[4 * i + 3] = t.w;
+    }
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      const float f = v[2 * i] + __ldg(bias + c0 + 2 * i), g = v[2 * i + 1] + __ldg(bias + c0 + 2 * i + 1);
+      const float f = v[2 * i] + bs[2 * i], g = v[2 * i + 1] + bs[2 * i + 1];
       aa[i] = tanh_fast(f);
       bb[i] = fmaf(0.5f, tanh_fast(0.5f * g), 0.5f);
       zz[i] = aa[i] * bb[i];
@@ -144,6 +150,7 @@ struct EpiGateTC {   // N = 64 interleaved (f,g); a chunk of 32 columns = 16 cha
 };
 
 struct EpiMlpTC {    // N = 32: bias + dropout + residual(BN-folded input) -> u, per-channel (sum, sum^2)
+  static constexpr bool kExtra = false;
   const float* bias;
   const bf16* u_prev; long long prev_rows_per_n, crop; const float* scale; const float* shift;
   const bf16* mask; float drop_p; uint64_t seed, offset; const uint64_t* rng;
@@ -191,6 +198,7 @@ struct EpiMlpTC {    // N = 32: bias + dropout + residual(BN-folded input) -> u,
 };
 
 struct EpiSlotTC {   // 32-column chunk c0 -> slot c0/32 of a slot-major buffer
+  static constexpr bool kExtra = false;
   bf16* out; long long slot_stride;
   __device__ __forceinline__ void chunk(long long p, long long, long long, bool valid, int c0, float v[32]) {
     if (!valid) return;
@@ -202,26 +210,34 @@ struct EpiSlotTC {   // 32-column chunk c0 -> slot c0/32 of a slot-major buffer
 };
 
 struct EpiGateBwdTC {   // N = 32: dx = acc + du(cropped rows); (sum dx, sum dx*u_prev)
-  const bf16* du; long long du_rows_per_n, crop;
-  const bf16* u_prev; float* dx; double* stats;
+  // du and u_prev rows of the tile arrive by TMA as two extra 64B-swizzled [128 rows][64 B] tiles (the du tile is
+  // zero-filled outside the cropped range), so the epilogue never waits on a global load.
+  static constexpr bool kExtra = true;
+  float* dx; double* stats;
   float s1, s2;
-  __device__ __forceinline__ void chunk(long long p, long long n, long long rem, bool valid, int c0, float v[32]) {
+  __device__ __forceinline__ void chunk_ex(long long p, long long, long long, bool valid, int, float v[32],
+                                           const uint8_t* extra, int r) {
     const int lane = threadIdx.x & 31;
     float up[32];
     if (valid) {
-      if (du && rem >= crop) {
-        const bf16* gp = du + (n * du_rows_per_n + rem - crop) * 32;
+      const int sw = (r >> 1) & 3;                              // 64B swizzle: logical 16-byte chunk c sits at c ^ sw
+      const uint8_t* drow = extra + (size_t)r * 64;
+      const uint8_t* urow = extra + 8192 + (size_t)r * 64;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float g[4]; load4(gp + 4 * j, g);
-          v[4 * j] += g[0]; v[4 * j + 1] += g[1]; v[4 * j + 2] += g[2]; v[4 * j + 3] += g[3];
+      for (int c = 0; c < 4; ++c) {
+        const uint4 qd = *reinterpret_cast<const uint4*>(drow + ((c ^ sw) << 4));
+        const uint4 qu = *reinterpret_cast<const uint4*>(urow + ((c ^ sw) << 4));
+        const uint32_t wd[4] = {qd.x, qd.y, qd.z, qd.w}, wu[4] = {qu.x, qu.y, qu.z, qu.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          v[8 * c + 2 * i] += __uint_as_float(wd[i] << 16);
+          v[8 * c + 2 * i + 1] += __uint_as_float(wd[i] & 0xFFFF0000u);
+          up[8 * c + 2 * i] = __uint_as_float(wu[i] << 16);
+          up[8 * c + 2 * i + 1] = __uint_as_float(wu[i] & 0xFFFF0000u);
         }
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        load4(u_prev + p * 32 + 4 * j, up + 4 * j);
-        store4(dx + p * 32 + 4 * j, v + 4 * j);
-      }
+      for (int j = 0; j < 8; ++j) store4(dx + p * 32 + 4 * j, v + 4 * j);
     } else {
 #pragma unroll
       for (int c = 0; c < 32; ++c) { v[c] = 0.f; up[c] = 0.f; }
@@ -989,9 +1005,13 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
         for (int h = 0; h < 2; ++h)
           pg.ch[2 * j + h] = PgChunk{dfg16, RO, -(long long)j * c->dilation * c->V, 64, h * 32};
       EpiGateBwdTC eb2{};
-      eb2.du = du; eb2.du_rows_per_n = RO; eb2.crop = (long long)(c->Lin - c->Lout) * c->V;
-      eb2.u_prev = reinterpret_cast<const bf16*>(g->u_prev); eb2.dx = g->dx_prev; eb2.stats = g->dx_stats;
-      eb2.s1 = 0.f; eb2.s2 = 0.f;
+      eb2.dx = g->dx_prev; eb2.stats = g->dx_stats; eb2.s1 = 0.f; eb2.s2 = 0.f;
+      // extra tiles for the epilogue: du shifted by the crop (zero outside), u_prev
+      pg.n_extra = 2;
+      // (no du for the last layer: a row offset far past the sample makes TMA zero-fill the whole tile)
+      pg.ch[2 * c->taps] = du ? PgChunk{du, RO, -(long long)(c->Lin - c->Lout) * c->V, 32, 0}
+                              : PgChunk{reinterpret_cast<const bf16*>(g->u_prev), RI, (long long)1 << 28, 32, 0};
+      pg.ch[2 * c->taps + 1] = PgChunk{reinterpret_cast<const bf16*>(g->u_prev), RI, 0, 32, 0};
       return launch_pos_gemm_tc(pg, eb2, st);
     }
   }

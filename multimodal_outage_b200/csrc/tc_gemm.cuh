@@ -23,6 +23,7 @@ constexpr int PG_TC_MAX_MAPS = 8;
 struct PgParams {
   PgChunk ch[PG_TC_MAX_CHUNKS];
   int n_chunks;                 // K = 32 * n_chunks
+  int n_extra;                  // extra (non-MMA) source tiles ch[n_chunks .. n_chunks+n_extra) brought in by TMA for the epilogue
   long long rows_per_n_out, P;
   int N;                        // output columns (multiple of 16, <= 256)
   const bf16* w_img;            // [K/8][N][8]

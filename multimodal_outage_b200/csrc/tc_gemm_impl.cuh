@@ -51,7 +51,8 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.N, K8 = p.n_chunks * 4;                     // 16-byte K pieces per weight row
   const int SUB = p.sub;
-  const uint32_t a_bytes = (uint32_t)p.n_chunks * 8192u * (uint32_t)SUB;   // one stage: SUB x n_chunks boxes of 128 x 64 B
+  const int NB = p.n_chunks + p.n_extra;                       // TMA boxes per sub-tile (MMA chunks + epilogue extras)
+  const uint32_t a_bytes = (uint32_t)NB * 8192u * (uint32_t)SUB;   // one stage: SUB x NB boxes of 128 x 64 B
   const uint32_t w_bytes = ((uint32_t)K8 * (uint32_t)N * 16u + 1023u) & ~1023u;
   uint8_t* a_s = smem;                                        // stages first (1024-aligned boxes)
   uint8_t* w_s = smem + (size_t)stages * a_bytes;
@@ -63,7 +64,8 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   if (tid == 0) {
-    for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    // a stage is free when the MMAs have read it and (with extras) every epilogue thread is done with it
+    for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], p.n_extra ? 1 + 32 * PGT_EPI_WARPS : 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 32 * PGT_EPI_WARPS); }
     fence_barrier_init();
   }
@@ -96,9 +98,8 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
           // and TMA zero-fills the box
           const int st = tile * SUB + t;
           const int n = st / p.tiles_per_n, r0 = (st - n * p.tiles_per_n) * 128;
-          for (int q = 0; q < p.n_chunks; ++q)
-            tg::tma_3d(sa + (uint32_t)(t * p.n_chunks + q) * 8192u, &maps.m[p.map_of[q]], 0, r0 + p.row_off[q], n,
-                       &full[stage]);
+          for (int q = 0; q < NB; ++q)
+            tg::tma_3d(sa + (uint32_t)(t * NB + q) * 8192u, &maps.m[p.map_of[q]], 0, r0 + p.row_off[q], n, &full[stage]);
         }
         PG_TRACE(1);
       }
@@ -120,8 +121,8 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
         mbar_wait(&full[stage], (uint32_t)((g / stages) & 1));
         PG_TRACE(3);
         tc_fence_after();
-        uint64_t ad = at + (uint64_t)((base + (uint32_t)stage * a_bytes) >> 4);
         for (int t = 0; t < SUB; ++t) {
+          uint64_t ad = at + (uint64_t)((base + (uint32_t)stage * a_bytes + (uint32_t)(t * NB) * 8192u) >> 4);
           uint64_t bd = bt;
           const uint32_t d = tmem_base + (uint32_t)acc * buf_cols + (uint32_t)t * acc_cols;
 #pragma unroll 2
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
     const int n_c32 = (N + 31) / 32;                            // 32-column chunks per sub-tile
     int g = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      const int acc = g & 1;
+      const int acc = g & 1, stage = g % stages;
       mbar_wait(&tfull[acc], (uint32_t)((g >> 1) & 1));
       if (warp == PGT_MMA_WARP + 1) PG_TRACE(5);
       tc_fence_after();
@@ -162,10 +163,14 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
         if (p.rows_out != (int)p.rows_per_n_out && pv) split_pos(pp, p.rows_per_n_out, n, rem);
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * buf_cols + (uint32_t)t * acc_cols + (uint32_t)c0, v);
-        epi.chunk(pp, n, rem, pv, c0, v);
+        if constexpr (Epi::kExtra)
+          epi.chunk_ex(pp, n, rem, pv, c0, v, smem + (size_t)stage * a_bytes + (size_t)(t * NB + p.n_chunks) * 8192, quad * 32 + lane);
+        else
+          epi.chunk(pp, n, rem, pv, c0, v);
       }
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
+      if (p.n_extra) mbar_arrive(&empty[stage]);
       if (warp == PGT_MMA_WARP + 1) PG_TRACE(6);
       ++g;
     }
@@ -187,7 +192,9 @@ int launch_pos_gemm_tc(PgParams& p, const Epi& epi, cudaStream_t st) {
               "pos_gemm_tc: unsupported shape (chunks=%d, N=%d)", p.n_chunks, p.N);
   // position-wise GEMM (every chunk has the output's own row structure): tile the flat position axis
   bool flat = true;
-  for (int q = 0; q < p.n_chunks; ++q)
+  const int NB = p.n_chunks + p.n_extra;
+  GWN_REQUIRE(NB <= PG_TC_MAX_CHUNKS, "pos_gemm_tc: too many chunks");
+  for (int q = 0; q < NB; ++q)
     if (p.ch[q].rows_per_n != p.rows_per_n_out || p.ch[q].row_off != 0) flat = false;
   const long long n_real = p.P / p.rows_per_n_out;
   GWN_REQUIRE(n_real * p.rows_per_n_out == p.P, "pos_gemm_tc: P is not a whole number of samples");
@@ -199,14 +206,14 @@ int launch_pos_gemm_tc(PgParams& p, const Epi& epi, cudaStream_t st) {
   p.sub = 1;
   p.tiles_per_n = (int)cdiv(p.rows_out, 128);                     // 128-row sub-tiles per (virtual) sample
   const long long sub_tiles = (long long)p.n_samples * p.tiles_per_n;
-  while (p.sub < 4 && 2 * acc_c * (p.sub * 2) <= 512 && (size_t)p.n_chunks * 8192 * (p.sub * 2) * 2 <= 150 * 1024 &&
+  while (p.sub < 4 && 2 * acc_c * (p.sub * 2) <= 512 && (size_t)NB * 8192 * (p.sub * 2) * 2 <= 150 * 1024 &&
          cdiv(sub_tiles, p.sub * 2) >= 2 * tg_sm_count())
     p.sub *= 2;
   p.n_tiles = (int)cdiv(sub_tiles, p.sub);
   PgMaps maps;
   int n_maps = 0;
   struct Key { const bf16* base; long long rows; int pitch, col; } keys[PG_TC_MAX_MAPS];
-  for (int q = 0; q < p.n_chunks; ++q) {
+  for (int q = 0; q < NB; ++q) {
     const PgChunk& c = p.ch[q];
     const long long rows = flat ? p.P : c.rows_per_n;
     int m = -1;
@@ -230,7 +237,7 @@ int launch_pos_gemm_tc(PgParams& p, const Epi& epi, cudaStream_t st) {
     p.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
   }
   const size_t w_bytes = ((size_t)p.n_chunks * 4 * p.N * 16 + 1023) & ~(size_t)1023;
-  const size_t a_bytes = (size_t)p.n_chunks * 8192 * p.sub;
+  const size_t a_bytes = (size_t)NB * 8192 * p.sub;
   int stages = (int)((220 * 1024 - w_bytes - 1024 - 256) / a_bytes);
   if (stages > 4) stages = 4;
   GWN_REQUIRE(stages >= 2, "pos_gemm_tc: K=%d does not fit 2 stages in shared memory", 32 * p.n_chunks);
