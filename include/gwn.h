@@ -137,6 +137,7 @@ typedef struct {
   void* ws_cat;                 /* [P, mlp_in] (dtype): recomputed hops */
   void* ws_dcat;                /* [P, mlp_in] (dtype): grads of the concat */
   float* ws_dfg;                /* [P, 64] fp32 */
+  int outputs_zeroed;           /* != 0: the caller already zeroed dx_stats, dw_*, db_* (one fill instead of six memsets) */
 } gwn_layer_bwd_args;
 
 int gwn_layer_bwd(const gwn_layer_cfg* cfg, const gwn_layer_bwd_args* args, void* stream);

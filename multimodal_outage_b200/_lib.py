@@ -37,7 +37,7 @@ class LayerBwdArgs(C.Structure):
                 ('supports', vp * MAX_SUPPORTS), ('support_needs_grad', C.c_int * MAX_SUPPORTS),
                 ('drop_mask', vp), ('rng', vp), ('hop_mats', vp), ('ws_w', vp), ('a', vp), ('b', vp), ('du', vp), ('dz_last', vp), ('dx_prev', vp),
                 ('dx_stats', vp), ('dw_fg', vp), ('db_fg', vp), ('dw_mlp', vp), ('db_mlp', vp),
-                ('d_supports', vp * MAX_SUPPORTS), ('ws_cat', vp), ('ws_dcat', vp), ('ws_dfg', vp)]
+                ('d_supports', vp * MAX_SUPPORTS), ('ws_cat', vp), ('ws_dcat', vp), ('ws_dfg', vp), ('outputs_zeroed', C.c_int)]
 
 
 class HeadCfg(C.Structure):

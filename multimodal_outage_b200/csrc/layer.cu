@@ -780,8 +780,8 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
       uint8_t* wsw = reinterpret_cast<uint8_t*>(g->ws_w);
       bf16* wt = reinterpret_cast<bf16*>(wsw + 96 * 1024);
       bf16* w56 = reinterpret_cast<bf16*>(wsw + 112 * 1024);
-      GWN_CUDA(cudaMemsetAsync(g->dw_mlp, 0, sizeof(float) * 32 * mlp_in, st));
-      GWN_CUDA(cudaMemsetAsync(g->db_mlp, 0, sizeof(float) * 32, st));
+      if (!g->outputs_zeroed) GWN_CUDA(cudaMemsetAsync(g->dw_mlp, 0, sizeof(float) * 32 * mlp_in, st));
+      if (!g->outputs_zeroed) GWN_CUDA(cudaMemsetAsync(g->db_mlp, 0, sizeof(float) * 32, st));
       if (int rc = launch_gcn_bwd_wprep(g->w_mlp, 2 * c->n_supports, wt, sa, w56, st)) return rc;
       GcnBwdParams bp{};
       bp.du = du; bp.a = a; bp.b = b; bp.dz_last = reinterpret_cast<const bf16*>(g->dz_last);
@@ -830,8 +830,8 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
     bool wg_done = false;
     if constexpr (std::is_same<T, bf16>::value) {
       if (tc_mode<T>(c, g->hop_mats) != 0 && wgrad_tc_supported(nslots, 32)) {
-        GWN_CUDA(cudaMemsetAsync(g->dw_mlp, 0, sizeof(float) * 32 * mlp_in, st));
-        GWN_CUDA(cudaMemsetAsync(g->db_mlp, 0, sizeof(float) * 32, st));
+        if (!g->outputs_zeroed) GWN_CUDA(cudaMemsetAsync(g->dw_mlp, 0, sizeof(float) * 32 * mlp_in, st));
+        if (!g->outputs_zeroed) GWN_CUDA(cudaMemsetAsync(g->db_mlp, 0, sizeof(float) * 32, st));
         WgParams w{};
         w.n_chunks = nslots; w.rows_per_n_out = RO; w.P = P;
         for (int q = 0; q < nslots; ++q) w.ch[q] = WgChunk{cat + q * P * 32, RO, 0, 32, 0};
@@ -938,8 +938,8 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
       }
     dz = dcat;
   } else {
-    GWN_CUDA(cudaMemsetAsync(g->dw_mlp, 0, sizeof(float) * 32 * mlp_in, st));
-    GWN_CUDA(cudaMemsetAsync(g->db_mlp, 0, sizeof(float) * 32, st));
+    if (!g->outputs_zeroed) GWN_CUDA(cudaMemsetAsync(g->dw_mlp, 0, sizeof(float) * 32 * mlp_in, st));
+    if (!g->outputs_zeroed) GWN_CUDA(cudaMemsetAsync(g->db_mlp, 0, sizeof(float) * 32, st));
   }
   // gate backward: (dz + dz_last) -> dfg  (bf16 in tensor-core mode so it can be an MMA operand)
   bool tc_gate = false;
@@ -964,8 +964,8 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
   }
   if (tc_gate) {
     if constexpr (std::is_same<T, bf16>::value) {
-      GWN_CUDA(cudaMemsetAsync(g->dw_fg, 0, sizeof(float) * 64 * 32 * c->taps, st));
-      GWN_CUDA(cudaMemsetAsync(g->db_fg, 0, sizeof(float) * 64, st));
+      if (!g->outputs_zeroed) GWN_CUDA(cudaMemsetAsync(g->dw_fg, 0, sizeof(float) * 64 * 32 * c->taps, st));
+      if (!g->outputs_zeroed) GWN_CUDA(cudaMemsetAsync(g->db_fg, 0, sizeof(float) * 64, st));
       WgParams w{};
       w.n_chunks = c->taps; w.rows_per_n_out = RO; w.P = P;
       for (int j = 0; j < c->taps; ++j)
@@ -986,7 +986,7 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
       ch.base = g->ws_dfg; ch.rows_per_n = RO; ch.row_off = -(long long)j * c->dilation * c->V;
       ch.pitch = 64; ch.col_off = h * 32; ch.w_off = (long long)j * 32 * 64 + h * 32;
     }
-  GWN_CUDA(cudaMemsetAsync(g->dx_stats, 0, sizeof(double) * 64, st));
+  if (!g->outputs_zeroed) GWN_CUDA(cudaMemsetAsync(g->dx_stats, 0, sizeof(double) * 64, st));
   EpiGateBwdData<T> ex{};
   ex.stats = g->dx_stats; ex.du = du; ex.du_rows_per_n = RO; ex.crop = (long long)(c->Lin - c->Lout) * c->V;
   ex.u_prev = reinterpret_cast<const T*>(g->u_prev); ex.dx = g->dx_prev;

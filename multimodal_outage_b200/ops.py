@@ -321,8 +321,9 @@ def layer_bwd(u_prev: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], 
               drop_mask: Optional[Tensor], rng: Optional[Tensor], hop_mats: Optional[Tensor], a: Tensor, b: Tensor,
               du: Optional[Tensor], dz_last: Optional[Tensor], Lf: int, taps: int, dilation: int, order: int, training: bool,
               dropout_p: float, seed: int, offset: int) -> List[Tensor]:
-    """Returns [dx_prev, dx_stats, dw_fg, db_fg, dw_mlp, db_mlp, d_support_0, ...] (d_support only for
-    supports whose needs_grad is True; others are empty tensors)."""
+    """Returns [dx_prev, flat]: flat is ONE zero-initialised fp32 buffer holding, back to back, dx_stats (64 fp64),
+    dw_fg, db_fg, dw_mlp, db_mlp and d_support_i for the supports whose needs_grad is True - see
+    `_split_layer_bwd` (custom-op outputs may not alias, so the views are cut outside the op)."""
     N, Lin, V, _c = u_prev.shape
     Lout = Lin - dilation * (taps - 1)
     dt, dev = u_prev.dtype, u_prev.device
@@ -332,10 +333,16 @@ def layer_bwd(u_prev: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], 
     P = N * Lout * V
     f32 = dict(device=dev, dtype=torch.float32)
     dx_prev = torch.empty((N, Lin, V, CH), **f32)
-    dx_stats = torch.empty((2, CH), device=dev, dtype=torch.float64)
-    dw_fg, db_fg = torch.empty((taps * CH, 2 * CH), **f32), torch.empty((2 * CH,), **f32)
-    dw_mlp, db_mlp = torch.empty((mlp_in, CH), **f32), torch.empty((CH,), **f32)
-    d_sup = [torch.zeros((V, V), **f32) if (g and has_du) else torch.empty((0,), **f32) for g in needs_grad]
+    # the small accumulated outputs live in ONE zero-filled buffer (one fill kernel instead of six memset nodes)
+    sizes = _layer_bwd_sizes(taps, mlp_in, V, needs_grad, has_du)
+    flat = torch.zeros((sum(sizes),), **f32)
+    parts, off = [], 0
+    for sz in sizes:
+        parts.append(flat[off:off + sz]); off += sz
+    dx_stats = parts[0].view(torch.float64).view(2, CH)
+    dw_fg, db_fg = parts[1].view(taps * CH, 2 * CH), parts[2]
+    dw_mlp, db_mlp = parts[3].view(mlp_in, CH), parts[4]
+    d_sup = [parts[5 + i].view(V, V) if (g and has_du) else torch.empty((0,), **f32) for i, g in enumerate(needs_grad)]
     ws_cat = torch.empty((P, mlp_in) if has_du else (0,), device=dev, dtype=dt)
     ws_dcat = torch.empty((P, mlp_in) if has_du else (0,), device=dev, dtype=dt)
     ws_dfg = torch.empty((P, 2 * CH), **f32)
@@ -347,13 +354,27 @@ def layer_bwd(u_prev: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], 
                         du=_p(du), dz_last=_p(dz_last), dx_prev=_p(dx_prev), dx_stats=_p(dx_stats),
                         dw_fg=_p(dw_fg), db_fg=_p(db_fg), dw_mlp=_p(dw_mlp), db_mlp=_p(db_mlp),
                         ws_cat=_p(ws_cat) if has_du else None, ws_dcat=_p(ws_dcat) if has_du else None,
-                        ws_dfg=_p(ws_dfg))
+                        ws_dfg=_p(ws_dfg), outputs_zeroed=1)
     for i, g in enumerate(needs_grad):
         args.support_needs_grad[i] = int(bool(g) and has_du)
         args.d_supports[i] = d_sup[i].data_ptr() if (g and has_du) else None
     with torch.cuda.device(dev):
         check(lib().gwn_layer_bwd(C.byref(cfg), C.byref(args), _stream()), 'gwn_layer_bwd')
-    return [dx_prev, dx_stats, dw_fg, db_fg, dw_mlp, db_mlp] + d_sup
+    return [dx_prev, flat]
+
+
+def _layer_bwd_sizes(taps: int, mlp_in: int, V: int, needs_grad: Sequence[bool], has_du: bool) -> List[int]:
+    return [2 * 2 * CH, taps * CH * 2 * CH, 2 * CH, mlp_in * CH, CH] + [V * V if (g and has_du) else 0 for g in needs_grad]
+
+
+def _split_layer_bwd(flat: Tensor, taps: int, mlp_in: int, V: int, needs_grad: Sequence[bool], has_du: bool):
+    sizes = _layer_bwd_sizes(taps, mlp_in, V, needs_grad, has_du)
+    parts, off = [], 0
+    for sz in sizes:
+        parts.append(flat[off:off + sz]); off += sz
+    dx_stats = parts[0].view(torch.float64).view(2, CH)
+    d_sup = [parts[5 + i].view(V, V) if sizes[5 + i] else None for i in range(len(needs_grad))]
+    return dx_stats, parts[1].view(taps * CH, 2 * CH), parts[2], parts[3].view(mlp_in, CH), parts[4], d_sup
 
 
 @layer_bwd.register_fake
@@ -362,8 +383,7 @@ def _(u_prev, scale, shift, w_fg, w_mlp, supports, needs_grad, drop_mask, rng, h
     N, Lin, V, _c = u_prev.shape
     mlp_in = CH * (1 + order * len(supports))
     f = lambda *s: u_prev.new_empty(s, dtype=torch.float32)  # noqa: E731
-    return [f(N, Lin, V, CH), u_prev.new_empty((2, CH), dtype=torch.float64), f(taps * CH, 2 * CH), f(2 * CH),
-            f(mlp_in, CH), f(CH)] + [f(V, V) if g and du is not None else f(0) for g in needs_grad]
+    return [f(N, Lin, V, CH), f(sum(_layer_bwd_sizes(taps, mlp_in, V, needs_grad, du is not None)))]
 
 
 class WaveNetLayer(torch.autograd.Function):
@@ -416,8 +436,10 @@ class WaveNetLayer(torch.autograd.Function):
                          dz_last.contiguous() if dz_last is not None else None,
                          m['Lf'], m['taps'], m['dilation'], m['order'], True, m['dropout_p'], m['seed'],
                          m['offset'])
-        dx_prev, dx_stats, dw_fg, db_fg, dw_mlp, db_mlp = outs[:6]
-        d_sup = outs[6:]
+        dx_prev, flat = outs
+        n_sup_b = len(sup) if has_du else 0
+        dx_stats, dw_fg, db_fg, dw_mlp, db_mlp, d_sup = _split_layer_bwd(
+            flat, m['taps'], CH * (1 + m['order'] * n_sup_b), u_prev.shape[2], ctx.sup_needs if has_du else [], has_du)
         if ctx.has_bn:
             du_prev, dgamma, dbeta = bn_bwd(dx_prev, u_prev, dx_stats, ctx.count, gamma, mean, rstd, True)
         else:
