@@ -667,6 +667,10 @@ static int layer_fwd_t(const gwn_layer_cfg* c, const gwn_layer_fwd_args* g, cuda
   if constexpr (std::is_same<T, bf16>::value) tc = tc_mode<T>(c, g->hop_mats) != 0 && g->ws_w != nullptr && c->taps <= 4;
   uint8_t* wsw = reinterpret_cast<uint8_t*>(g->ws_w);
   const long long last_begin = (long long)(c->Lout - c->Lf) * c->V, last_rows = (long long)c->Lf * c->V;
+  bool fused_fwd = false;     // supports on chip: hops + concat + mlp + dropout + residual + statistics as ONE kernel
+  if constexpr (std::is_same<T, bf16>::value)
+    fused_fwd = tc && c->has_gconv && fused_gcn_enabled() && tc_mode<T>(c, g->hop_mats) == 1 && c->order == 2 &&
+                c->n_supports >= 1 && gcn_fused_supported(c->V, 2 * c->n_supports);
   if (tc) {
     if constexpr (std::is_same<T, bf16>::value) {
       // fold the previous layer's BatchNorm affine into the gate weights/bias, build the bf16 UMMA image
@@ -675,6 +679,10 @@ static int layer_fwd_t(const gwn_layer_cfg* c, const gwn_layer_fwd_args* g, cuda
       for (int j = 0; j < c->taps; ++j) wp.w_off[j] = (long long)j * 32 * 64;
       wp.scale = g->scale; wp.shift = g->shift; wp.bias = g->b_fg;
       wp.img = reinterpret_cast<bf16*>(wsw); wp.bias_out = reinterpret_cast<float*>(wsw + 48 * 1024);
+      if (c->has_gconv) {      // same launch: zero the BN statistics and build the fused gcn weight image
+        wp.zero64 = g->stats;
+        if (fused_fwd) { wp.g_w = g->w_mlp; wp.g_nmats = 2 * c->n_supports; wp.g_img = reinterpret_cast<bf16*>(wsw + 64 * 1024); }
+      }
       if (int rc = launch_wprep(wp, st)) return rc;
       PgParams pg{};
       pg.n_chunks = c->taps; pg.rows_per_n_out = RO; pg.P = P; pg.N = 64; pg.w_img = wp.img;
@@ -697,13 +705,11 @@ static int layer_fwd_t(const gwn_layer_cfg* c, const gwn_layer_fwd_args* g, cuda
   if (int rc = launch_pos_gemm<T, 64>(A, g->w_fg, 64, eg, st)) return rc;
   }
   if (!c->has_gconv) return 0;
-  GWN_CUDA(cudaMemsetAsync(g->stats, 0, sizeof(double) * 64, st));
+  if (!tc) GWN_CUDA(cudaMemsetAsync(g->stats, 0, sizeof(double) * 64, st));      // (tc: zeroed by the wprep launch)
   if constexpr (std::is_same<T, bf16>::value) {
     // supports on chip: hops + concat + mlp + dropout + residual + statistics as ONE kernel (gcn_fused.cu)
-    if (tc && fused_gcn_enabled() && tc_mode<T>(c, g->hop_mats) == 1 && c->order == 2 && c->n_supports >= 1 &&
-        gcn_fused_supported(c->V, 2 * c->n_supports)) {
-      bf16* wimg = reinterpret_cast<bf16*>(wsw + 64 * 1024);
-      if (int rc = launch_gcn_wprep(g->w_mlp, 2 * c->n_supports, wimg, st)) return rc;
+    if (fused_fwd) {
+      bf16* wimg = reinterpret_cast<bf16*>(wsw + 64 * 1024);     // built by the gate's wprep launch above
       GcnFwdParams fp{};
       fp.z = cat; fp.u_prev = reinterpret_cast<const bf16*>(g->u_prev); fp.RI = RI; fp.RO = RO;
       fp.crop = (long long)(c->Lin - c->Lout) * c->V; fp.scale = g->scale; fp.shift = g->shift;
@@ -768,7 +774,7 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
   const T* du = reinterpret_cast<const T*>(g->du);
   const unsigned eb = (unsigned)cdiv(P * 8, 256);
   const T* dz = nullptr;
-  bool fused_bwd = false;
+  bool fused_bwd = false, dx_img_ready = false;
   if constexpr (std::is_same<T, bf16>::value) {
     // supports on chip and none of them needs a gradient: the whole diffusion backward (mask, transposed hops, mlp
     // data + weight gradients, gate backward) is ONE kernel (gcn_fused_bwd.cu) that leaves dfg for the conv backward
@@ -782,7 +788,16 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
       bf16* w56 = reinterpret_cast<bf16*>(wsw + 112 * 1024);
       if (!g->outputs_zeroed) GWN_CUDA(cudaMemsetAsync(g->dw_mlp, 0, sizeof(float) * 32 * mlp_in, st));
       if (!g->outputs_zeroed) GWN_CUDA(cudaMemsetAsync(g->db_mlp, 0, sizeof(float) * 32, st));
-      if (int rc = launch_gcn_bwd_wprep(g->w_mlp, 2 * c->n_supports, wt, sa, w56, st)) return rc;
+      {   // one launch: the gcn backward weight images AND the (transposed) gate weight image of the dx GEMM below
+        WPrepParams wp{};
+        wp.W = g->w_fg; wp.ld = 64; wp.transposed = 1; wp.K = 64 * c->taps; wp.N = 32;
+        for (int j = 0; j < c->taps; ++j)
+          for (int h = 0; h < 2; ++h) wp.w_off[2 * j + h] = (long long)j * 32 * 64 + h * 32;
+        wp.img = reinterpret_cast<bf16*>(wsw + 64 * 1024); wp.bias_out = nullptr;
+        wp.g_w = g->w_mlp; wp.g_nmats = 2 * c->n_supports; wp.gb_wt = wt; wp.gb_sa = sa; wp.gb_w56 = w56;
+        if (int rc = launch_wprep(wp, st)) return rc;
+        dx_img_ready = true;
+      }
       GcnBwdParams bp{};
       bp.du = du; bp.a = a; bp.b = b; bp.dz_last = reinterpret_cast<const bf16*>(g->dz_last);
       bp.RO = RO; bp.last_begin = (long long)(c->Lout - c->Lf) * c->V; bp.last_rows = (long long)c->Lf * c->V;
@@ -998,7 +1013,8 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
       for (int j = 0; j < c->taps; ++j)
         for (int h = 0; h < 2; ++h) wp.w_off[2 * j + h] = (long long)j * 32 * 64 + h * 32;
       wp.img = reinterpret_cast<bf16*>(wsw + 64 * 1024); wp.bias_out = nullptr;
-      if (int rc = launch_wprep(wp, st)) return rc;
+      if (!dx_img_ready)
+        if (int rc = launch_wprep(wp, st)) return rc;
       PgParams pg{};
       pg.n_chunks = 2 * c->taps; pg.rows_per_n_out = RI; pg.P = PI; pg.N = 32; pg.w_img = wp.img;
       for (int j = 0; j < c->taps; ++j)

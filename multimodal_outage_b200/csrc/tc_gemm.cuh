@@ -50,6 +50,11 @@ struct WPrepParams {
   const float* bias;            // optional [N]
   bf16* img;                    // out [K/8][N][8]
   float* bias_out;              // out [N] (may be NULL)
+  // piggy-backed jobs (one launch instead of three graph nodes): zero 64 doubles; the fused gcn weight images
+  double* zero64;               // optional
+  const float* g_w; int g_nmats;     // packed mlp weight [32*(1+g_nmats), 32] (NULL: no gcn images)
+  bf16* g_img;                  // forward image  [4][32*(1+H)][8]   (gcn_fused.cu)
+  bf16* gb_wt; int gb_sa; bf16* gb_w56;   // backward images (gcn_fused_bwd.cu); gb_w56 may be NULL
 };
 int launch_wprep(const WPrepParams& w, cudaStream_t st);
 
