@@ -230,6 +230,7 @@ typedef struct {
   void* ws_de1;           /* [P,E] bf16 */
   void* ws_ds1;           /* [P,S] bf16 */
   void* ws_w;
+  int outputs_zeroed;     /* != 0: the caller already zeroed dw_*, db_* */
 } gwn_head_tc_bwd_args;
 long long gwn_head_tc_ws_bytes(int n_layers, int S, int E, int O);
 int gwn_head_fwd_tc(const gwn_head_cfg* cfg, const gwn_head_tc_fwd_args* a, void* stream);

@@ -64,7 +64,8 @@ class HeadTcFwdArgs(C.Structure):
 class HeadTcBwdArgs(C.Structure):
     _fields_ = [(n, vp) for n in ('zcat', 'w_skip', 'w_end1', 'w_end2', 's1', 'e1', 'dout', 'dw_skip', 'db_skip',
                                   'dw_end1', 'db_end1', 'dw_end2', 'db_end2')] + \
-               [('dz_last', vp * MAX_LAYERS)] + [(n, vp) for n in ('ws_do', 'ws_de1', 'ws_ds1', 'ws_w')]
+               [('dz_last', vp * MAX_LAYERS)] + [(n, vp) for n in ('ws_do', 'ws_de1', 'ws_ds1', 'ws_w')] + \
+               [('outputs_zeroed', C.c_int)]
 
 
 # every symbol include/gwn.h declares: name -> (restype, argtypes)

@@ -269,12 +269,14 @@ extern "C" int gwn_head_bwd_tc(const gwn_head_cfg* c, const gwn_head_tc_bwd_args
   jobs.j[2] = CvtJob{a->w_end2, w2, E, Opad, 0, Opad, -1, -1};
   cvt_weights_kernel<<<64, 256, 0, st>>>(jobs);
   GWN_LAUNCHED();
+  if (!a->outputs_zeroed) {
   GWN_CUDA(cudaMemsetAsync(a->dw_skip, 0, sizeof(float) * (size_t)K0 * S, st));
   GWN_CUDA(cudaMemsetAsync(a->db_skip, 0, sizeof(float) * S, st));
   GWN_CUDA(cudaMemsetAsync(a->dw_end1, 0, sizeof(float) * (size_t)S * E, st));
   GWN_CUDA(cudaMemsetAsync(a->db_end1, 0, sizeof(float) * E, st));
   GWN_CUDA(cudaMemsetAsync(a->dw_end2, 0, sizeof(float) * (size_t)E * Opad, st));
   GWN_CUDA(cudaMemsetAsync(a->db_end2, 0, sizeof(float) * Opad, st));
+  }
   bf16* d_o = reinterpret_cast<bf16*>(a->ws_do);
   bf16* de1 = reinterpret_cast<bf16*>(a->ws_de1);
   bf16* ds1 = reinterpret_cast<bf16*>(a->ws_ds1);

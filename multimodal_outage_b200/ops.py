@@ -552,7 +552,8 @@ def _(zcat, w_skip, b_skip, w_end1, b_end1, w_end2, b_end2, out_dim):
 @torch.library.custom_op('gwn::head_bwd_tc', mutates_args=())
 def head_bwd_tc(zcat: Tensor, w_skip: Tensor, w_end1: Tensor, w_end2: Tensor, s1: Tensor, e1: Tensor,
                 dout: Tensor) -> List[Tensor]:
-    """Returns [dw_skip, db_skip, dw_end1, db_end1, dw_end2, db_end2, dz_last_0, ...] (dz_last_i: [N,Lf,V,32] bf16)."""
+    """Returns [flat, dz_last_0, ...]: flat = dw_skip | db_skip | dw_end1 | db_end1 | dw_end2 | db_end2 back to back
+    (`_split_head_bwd`); dz_last_i: [N,Lf,V,32] bf16."""
     N, Lf, V, K0 = zcat.shape
     nl = K0 // CH
     S, E, Opad = w_skip.shape[1], w_end1.shape[1], w_end2.shape[1]
@@ -561,9 +562,12 @@ def head_bwd_tc(zcat: Tensor, w_skip: Tensor, w_end1: Tensor, w_end2: Tensor, s1
     dev = zcat.device
     f32 = dict(device=dev, dtype=torch.float32)
     b16 = dict(device=dev, dtype=torch.bfloat16)
-    dw_skip, db_skip = torch.empty_like(w_skip), torch.empty((S,), **f32)
-    dw_end1, db_end1 = torch.empty_like(w_end1), torch.empty((E,), **f32)
-    dw_end2, db_end2 = torch.empty_like(w_end2), torch.empty((Opad,), **f32)
+    # the six parameter gradients share ONE zero-filled buffer (one fill instead of six memset nodes); cut into views
+    # by `_split_head_bwd` outside the op (custom-op outputs may not alias)
+    sizes = _head_bwd_sizes(K0, S, E, Opad)
+    flat = torch.zeros((sum(sizes),), **f32)
+    offs = [sum(sizes[:i]) for i in range(6)]
+    dw_skip, db_skip, dw_end1, db_end1, dw_end2, db_end2 = (flat[o:o + sz] for o, sz in zip(offs, sizes))
     dz = [torch.empty((N, Lf, V, CH), **b16) for _ in range(nl)]
     ws_do, ws_de1, ws_ds1 = torch.empty((P, Opad), **b16), torch.empty((P, E), **b16), torch.empty((P, S), **b16)
     ws_w = torch.empty((lib().gwn_head_tc_ws_bytes(nl, S, E, O),), device=dev, dtype=torch.uint8)
@@ -571,18 +575,28 @@ def head_bwd_tc(zcat: Tensor, w_skip: Tensor, w_end1: Tensor, w_end2: Tensor, s1
     args = HeadTcBwdArgs(zcat=_p(zcat), w_skip=_p(w_skip), w_end1=_p(w_end1), w_end2=_p(w_end2), s1=_p(s1), e1=_p(e1),
                          dout=_p(dout), dw_skip=_p(dw_skip), db_skip=_p(db_skip), dw_end1=_p(dw_end1),
                          db_end1=_p(db_end1), dw_end2=_p(dw_end2), db_end2=_p(db_end2), dz_last=_ptr_array(dz),
-                         ws_do=_p(ws_do), ws_de1=_p(ws_de1), ws_ds1=_p(ws_ds1), ws_w=_p(ws_w))
+                         ws_do=_p(ws_do), ws_de1=_p(ws_de1), ws_ds1=_p(ws_ds1), ws_w=_p(ws_w), outputs_zeroed=1)
     with torch.cuda.device(dev):
         check(lib().gwn_head_bwd_tc(C.byref(cfg), C.byref(args), _stream()), 'gwn_head_bwd_tc')
-    return [dw_skip, db_skip, dw_end1, db_end1, dw_end2, db_end2] + dz
+    return [flat] + dz
+
+
+def _head_bwd_sizes(K0: int, S: int, E: int, Opad: int) -> List[int]:
+    return [K0 * S, S, S * E, E, E * Opad, Opad]
+
+
+def _split_head_bwd(flat: Tensor, K0: int, S: int, E: int, Opad: int):
+    sizes = _head_bwd_sizes(K0, S, E, Opad)
+    offs = [sum(sizes[:i]) for i in range(6)]
+    p = [flat[o:o + sz] for o, sz in zip(offs, sizes)]
+    return [p[0].view(K0, S), p[1], p[2].view(S, E), p[3], p[4].view(E, Opad), p[5]]
 
 
 @head_bwd_tc.register_fake
 def _(zcat, w_skip, w_end1, w_end2, s1, e1, dout):
     N, Lf, V, K0 = zcat.shape
-    f = lambda t: torch.empty_like(t)  # noqa: E731
-    v = lambda n: zcat.new_empty((n,), dtype=torch.float32)  # noqa: E731
-    return [f(w_skip), v(w_skip.shape[1]), f(w_end1), v(w_end1.shape[1]), f(w_end2), v(w_end2.shape[1])] + \
+    S, E, Opad = w_skip.shape[1], w_end1.shape[1], w_end2.shape[1]
+    return [zcat.new_empty((sum(_head_bwd_sizes(K0, S, E, Opad)),), dtype=torch.float32)] + \
         [zcat.new_empty((N, Lf, V, CH)) for _ in range(K0 // CH)]
 
 
@@ -614,6 +628,8 @@ class SkipHead(torch.autograd.Function):
         w_skip, w_end1, w_end2, s1, e1, *zs = ctx.saved_tensors
         if ctx.tc:
             outs = head_bwd_tc(zs[0], w_skip, w_end1, w_end2, s1, e1, dout.contiguous().float())
+            outs = _split_head_bwd(outs[0], w_skip.shape[0], w_skip.shape[1], w_end1.shape[1], w_end2.shape[1]) + \
+                list(outs[1:])
         else:
             outs = head_bwd(list(zs), w_skip, w_end1, w_end2, s1, e1, dout.contiguous().float())
         return (*outs[:6], None, *outs[6:])
