@@ -160,7 +160,9 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gcn_fwd_kernel(const __grid_con
     for (int kk = (k >= GF_ZST - 2 ? k - (GF_ZST - 2) : 0); kk < k; ++kk) mbar_arrive(&z_full[kk % GF_ZST]);
   } else if (warp == GF_MMA) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp walks the loop (so descriptors live in uniform registers and the MMAs issue back to back); only
+    // the tcgen05 instructions themselves run on one elected lane.
+    {
       const uint32_t idescU = make_idesc_bf16(128, NU, false, false);
       const uint32_t idescH = make_idesc_bf16(128, 32, false, true);
       // descriptor templates (start address added per use; addresses are < 256 KB so no field carry)
@@ -176,17 +178,20 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gcn_fwd_kernel(const __grid_con
         const uint32_t ub = sbase + L.u_off + (uint32_t)us * L.u_stage;
         constexpr uint32_t mat_bytes = (uint32_t)(Kp / 8) * (uint32_t)Kp * 16u, u_slot = 4u * (uint32_t)Kp * 16u;
         const uint64_t ad0 = adm + (uint64_t)(sbase >> 4), bd0 = bdu + (uint64_t)(ub >> 4);
+        if (elect_one()) {
 #pragma unroll
-        for (int m = 0; m < NM; ++m) {
+          for (int m = 0; m < NM; ++m) {
 #pragma unroll
-          for (int ks = 0; ks < KSTEPS; ++ks) {
-            const uint64_t ad = ad0 + (uint64_t)(((uint32_t)m * mat_bytes + (uint32_t)(2 * ks) * (uint32_t)Kp * 16u) >> 4);
-            const uint64_t bd = bd0 + (uint64_t)(((uint32_t)m * u_slot + (uint32_t)ks * 256u) >> 4);
-            umma_bf16(d, ad, bd, idescH, 1u);
+            for (int ks = 0; ks < KSTEPS; ++ks) {
+              const uint64_t ad = ad0 + (uint64_t)(((uint32_t)m * mat_bytes + (uint32_t)(2 * ks) * (uint32_t)Kp * 16u) >> 4);
+              const uint64_t bd = bd0 + (uint64_t)(((uint32_t)m * u_slot + (uint32_t)ks * 256u) >> 4);
+              umma_bf16(d, ad, bd, idescH, 1u);
+            }
           }
+          umma_commit(&us_empty[us]);
+          umma_commit(&ht_full[hb]);
         }
-        umma_commit(&us_empty[us]);
-        umma_commit(&ht_full[hb]);
+        __syncwarp();
       };
       int k = 0;
       for (long long slab = blockIdx.x; slab < p.slabs; slab += gridDim.x, ++k) {
@@ -197,14 +202,17 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gcn_fwd_kernel(const __grid_con
         GF_TRACE(1);
         const uint32_t za = sbase + L.z_off + (uint32_t)zs * L.z_stage;
         const uint32_t wa = sbase + L.w_off;
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          const uint64_t ad = adz + (uint64_t)((za + (uint32_t)(2 * ks) * L.z_piece) >> 4);
-          const uint64_t bd = bdw + (uint64_t)((wa + (uint32_t)(2 * ks) * (uint32_t)NU * 16u) >> 4);
-          umma_bf16(tmem_base + (uint32_t)ub * 256u, ad, bd, idescU, ks == 0 ? 0u : 1u);
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint64_t ad = adz + (uint64_t)((za + (uint32_t)(2 * ks) * L.z_piece) >> 4);
+            const uint64_t bd = bdw + (uint64_t)((wa + (uint32_t)(2 * ks) * (uint32_t)NU * 16u) >> 4);
+            umma_bf16(tmem_base + (uint32_t)ub * 256u, ad, bd, idescU, ks == 0 ? 0u : 1u);
+          }
+          umma_commit(&z_empty[zs]);
+          umma_commit(&ut_full[ub]);
         }
-        umma_commit(&z_empty[zs]);
-        umma_commit(&ut_full[ub]);
+        __syncwarp();
         GF_TRACE(2);
         if (k > 0) issue_hops(k - 1);
         GF_TRACE(3);

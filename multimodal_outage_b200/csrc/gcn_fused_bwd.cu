@@ -140,7 +140,9 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
 
   if (warp == GB_MMA) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp walks the loop (so descriptors live in uniform registers and the MMAs issue back to back); only
+    // the tcgen05 instructions themselves run on one elected lane.
+    {
       const uint32_t idescH = make_idesc_bf16(128, 32, false, true);    // matT (K-major) x dh (MN-major)
       const uint32_t idescZ = make_idesc_bf16(128, 32, false, false);   // cat (K-major) x W^T image (K-major)
       const uint32_t idescW = make_idesc_bf16(128, 32, true, true);     // cat (MN-major) x z (MN-major)
@@ -159,18 +161,21 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
         const uint32_t cat = sbase + L.cat_off + (uint32_t)bb * L.cat_bytes;
         const uint32_t zt = sbase + L.z_off + (uint32_t)bb * L.z_bytes;
         const uint64_t a0 = adm + (uint64_t)(cat >> 4), w0 = bdw + (uint64_t)((sbase + L.w_off) >> 4);
-#pragma unroll
-        for (int ks = 0; ks < 2 * (1 + NM); ++ks)
-          umma_bf16(tmem_base + TZ, a0 + (uint64_t)(((uint32_t)(2 * ks) * (uint32_t)Kp * 16u) >> 4),
-                    w0 + (uint64_t)(((uint32_t)(2 * ks) * 512u) >> 4), idescZ, ks == 0 ? 0u : 1u);
-        umma_commit(dz_full);
         const uint64_t am = bmn + (uint64_t)(cat >> 4), bz = bmn + (uint64_t)(zt >> 4);
+        if (elect_one()) {
 #pragma unroll
-        for (int t = 0; t < 2; ++t)
+          for (int ks = 0; ks < 2 * (1 + NM); ++ks)
+            umma_bf16(tmem_base + TZ, a0 + (uint64_t)(((uint32_t)(2 * ks) * (uint32_t)Kp * 16u) >> 4),
+                      w0 + (uint64_t)(((uint32_t)(2 * ks) * 512u) >> 4), idescZ, ks == 0 ? 0u : 1u);
+          umma_commit(dz_full);
 #pragma unroll
-          for (int ks = 0; ks < KSTEPS; ++ks)
-            umma_bf16(tmem_base + TW + 32u * t, am + (uint64_t)(((uint32_t)(16 * t) * (uint32_t)Kp * 16u + (uint32_t)ks * 256u) >> 4),
-                      bz + (uint64_t)(((uint32_t)ks * 256u) >> 4), idescW, (kk == 0 && ks == 0) ? 0u : 1u);
+          for (int t = 0; t < 2; ++t)
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ++ks)
+              umma_bf16(tmem_base + TW + 32u * t, am + (uint64_t)(((uint32_t)(16 * t) * (uint32_t)Kp * 16u + (uint32_t)ks * 256u) >> 4),
+                        bz + (uint64_t)(((uint32_t)ks * 256u) >> 4), idescW, (kk == 0 && ks == 0) ? 0u : 1u);
+        }
+        __syncwarp();
         if (DA) {
           // dA += T1^T-style products: D[v, w] += sum_c T1[v,c] dh[w,c] + U6[v,c] dU5[w,c]   (all operands K-major)
           GB_TRACE(kk + 1, 5);
@@ -180,16 +185,20 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
           const uint64_t au6 = adm + (uint64_t)((sbase + L.u6_off + (uint32_t)bb * L.slot_bytes) >> 4);
           const uint64_t bdh = adm + (uint64_t)(cat >> 4);
           const uint64_t bd5 = adm + (uint64_t)((cat + (uint32_t)(2 * p.sa + 1) * L.slot_bytes) >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks)
-            umma_bf16(tmem_base + TDA, at1 + (uint64_t)(((uint32_t)(2 * ks) * (uint32_t)Kp * 16u) >> 4),
-                      bdh + (uint64_t)(((uint32_t)(2 * ks) * (uint32_t)Kp * 16u) >> 4), idescA, (kk == 0 && ks == 0) ? 0u : 1u);
+            for (int ks = 0; ks < 2; ++ks)
+              umma_bf16(tmem_base + TDA, at1 + (uint64_t)(((uint32_t)(2 * ks) * (uint32_t)Kp * 16u) >> 4),
+                        bdh + (uint64_t)(((uint32_t)(2 * ks) * (uint32_t)Kp * 16u) >> 4), idescA, (kk == 0 && ks == 0) ? 0u : 1u);
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks)
-            umma_bf16(tmem_base + TDA, au6 + (uint64_t)(((uint32_t)(2 * ks) * (uint32_t)Kp * 16u) >> 4),
-                      bd5 + (uint64_t)(((uint32_t)(2 * ks) * (uint32_t)Kp * 16u) >> 4), idescA, 1u);
+            for (int ks = 0; ks < 2; ++ks)
+              umma_bf16(tmem_base + TDA, au6 + (uint64_t)(((uint32_t)(2 * ks) * (uint32_t)Kp * 16u) >> 4),
+                        bd5 + (uint64_t)(((uint32_t)(2 * ks) * (uint32_t)Kp * 16u) >> 4), idescA, 1u);
+          }
+          __syncwarp();
         }
-        umma_commit(&buf_empty[bb]);
+        if (elect_one()) umma_commit(&buf_empty[bb]);
+        __syncwarp();
       };
       int k = 0;
       for (long long slab = blockIdx.x; slab < p.slabs; slab += gridDim.x, ++k) {
@@ -202,25 +211,31 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
           tc_fence_after();
           const uint64_t az = adm + (uint64_t)((sbase + L.z_off + (uint32_t)bb * L.z_bytes) >> 4);
           const uint64_t bw = b56 + (uint64_t)((sbase + L.w56_off) >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks)
-            umma_bf16(tmem_base + TU5, az + (uint64_t)(((uint32_t)(2 * ks) * (uint32_t)Kp * 16u) >> 4),
-                      bw + (uint64_t)(((uint32_t)(2 * ks) * 1024u) >> 4), idescU, ks == 0 ? 0u : 1u);
-          umma_commit(u56_full);
+            for (int ks = 0; ks < 2; ++ks)
+              umma_bf16(tmem_base + TU5, az + (uint64_t)(((uint32_t)(2 * ks) * (uint32_t)Kp * 16u) >> 4),
+                        bw + (uint64_t)(((uint32_t)(2 * ks) * 1024u) >> 4), idescU, ks == 0 ? 0u : 1u);
+            umma_commit(u56_full);
+          }
+          __syncwarp();
         }
         mbar_wait(ut_empty, (uint32_t)((k & 1) ^ 1));
         GB_TRACE(k, 1);
         tc_fence_after();
         const uint32_t cat = sbase + L.cat_off + (uint32_t)bb * L.cat_bytes;
         const uint64_t a0 = adm + (uint64_t)(sbase >> 4), b0 = bmn + (uint64_t)(cat >> 4);
+        if (elect_one()) {
 #pragma unroll
-        for (int m = 0; m < NM; ++m)
+          for (int m = 0; m < NM; ++m)
 #pragma unroll
-          for (int ks = 0; ks < KSTEPS; ++ks)
-            umma_bf16(tmem_base + 32u * m,
-                      a0 + (uint64_t)(((uint32_t)m * ((uint32_t)(Kp / 8) * (uint32_t)Kp * 16u) + (uint32_t)(2 * ks) * (uint32_t)Kp * 16u) >> 4),
-                      b0 + (uint64_t)(((uint32_t)ks * 256u) >> 4), idescH, ks == 0 ? 0u : 1u);
-        umma_commit(ut_full);
+            for (int ks = 0; ks < KSTEPS; ++ks)
+              umma_bf16(tmem_base + 32u * m,
+                        a0 + (uint64_t)(((uint32_t)m * ((uint32_t)(Kp / 8) * (uint32_t)Kp * 16u) + (uint32_t)(2 * ks) * (uint32_t)Kp * 16u) >> 4),
+                        b0 + (uint64_t)(((uint32_t)ks * 256u) >> 4), idescH, ks == 0 ? 0u : 1u);
+          umma_commit(ut_full);
+        }
+        __syncwarp();
         GB_TRACE(k, 2);
         if (DA) {
           // T1 = U5 + A^T-hop(U6): accumulate the forward hop of the staged U6 onto the U5 columns
@@ -228,18 +243,21 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
           tc_fence_after();
           const uint64_t af = adm + (uint64_t)((sbase + L.fwd_off) >> 4);
           const uint64_t bu = bmn + (uint64_t)((sbase + L.u6_off + (uint32_t)bb * L.slot_bytes) >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < KSTEPS; ++ks)
-            umma_bf16(tmem_base + TU5, af + (uint64_t)(((uint32_t)(2 * ks) * (uint32_t)Kp * 16u) >> 4),
-                      bu + (uint64_t)(((uint32_t)ks * 256u) >> 4), idescH, 1u);
-          umma_commit(t1_full);
+            for (int ks = 0; ks < KSTEPS; ++ks)
+              umma_bf16(tmem_base + TU5, af + (uint64_t)(((uint32_t)(2 * ks) * (uint32_t)Kp * 16u) >> 4),
+                        bu + (uint64_t)(((uint32_t)ks * 256u) >> 4), idescH, 1u);
+            umma_commit(t1_full);
+          }
+          __syncwarp();
         }
         GB_TRACE(k, 3);
         if (k > 0) tail(k - 1);
         GB_TRACE(k, 6);
       }
       if (k > 0) tail(k - 1);
-      umma_commit(w_full);
+      if (elect_one()) umma_commit(w_full);
     }
     __syncwarp();
   } else if (warp == 12 || warp == 13 || warp == 15) {

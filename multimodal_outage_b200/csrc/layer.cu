@@ -123,22 +123,18 @@ __device__ __forceinline__ void store_bf16x16(bf16* dst, const float v[16]) {
 }
 
 struct EpiGateTC {   // N = 64 interleaved (f,g); a chunk of 32 columns = 16 channels
+  // the accumulator already holds f + bias and (g + bias) / 2: the bias rides in the GEMM (has_bias) and the weight
+  // image's g columns are pre-halved (half_odd), so sigmoid(g) = 0.5 tanh(acc) + 0.5
   static constexpr bool kExtra = false;
-  const float* bias;
+  static constexpr int kFast = 2;
   bf16* z; bf16* a; bf16* b; bf16* z_last; long long last_begin, last_rows;
   __device__ __forceinline__ void chunk(long long p, long long n, long long rem, bool valid, int c0, float v[32]) {
     if (!valid) return;
-    float zz[16], aa[16], bb[16], bs[32];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {       // 8 vector loads instead of 32 scalar ones (the LSU queue was the stall)
-      const float4 t = __ldg(reinterpret_cast<const float4*>(bias + c0) + i);
-      bs[4 * i] = t.x; bs[4 * i + 1] = t.y; bs[4 * i + 2] = t.z; bs[4 * i + 3] = t.w;
-    }
+    float zz[16], aa[16], bb[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      const float f = v[2 * i] + bs[2 * i], g = v[2 * i + 1] + bs[2 * i + 1];
-      aa[i] = tanh_fast(f);
-      bb[i] = fmaf(0.5f, tanh_fast(0.5f * g), 0.5f);
+      aa[i] = tanh_fast(v[2 * i]);
+      bb[i] = fmaf(0.5f, tanh_fast(v[2 * i + 1]), 0.5f);
       zz[i] = aa[i] * bb[i];
     }
     const int ch0 = c0 >> 1;
@@ -149,9 +145,9 @@ struct EpiGateTC {   // N = 64 interleaved (f,g); a chunk of 32 columns = 16 cha
   __device__ __forceinline__ void finish() {}
 };
 
-struct EpiMlpTC {    // N = 32: bias + dropout + residual(BN-folded input) -> u, per-channel (sum, sum^2)
+struct EpiMlpTC {    // N = 32: (bias in the GEMM) dropout + residual(BN-folded input) -> u, per-channel (sum, sum^2)
   static constexpr bool kExtra = false;
-  const float* bias;
+  static constexpr int kFast = 0;
   const bf16* u_prev; long long prev_rows_per_n, crop; const float* scale; const float* shift;
   const bf16* mask; float drop_p; uint64_t seed, offset; const uint64_t* rng;
   bf16* u; double* stats;
@@ -173,7 +169,7 @@ struct EpiMlpTC {    // N = 32: bias + dropout + residual(BN-folded input) -> u,
         for (int i = 0; i < 8; ++i) {
           const int c = 8 * j + i;
           float rr = scale ? fmaf(r[i], __ldg(scale + c), __ldg(shift + c)) : r[i];
-          h[c] = (v[c] + __ldg(bias + c)) * m[i] + rr;
+          h[c] = fmaf(v[c], m[i], rr);
         }
       }
       store_bf16x16(u + p * 32, h);
@@ -199,6 +195,7 @@ struct EpiMlpTC {    // N = 32: bias + dropout + residual(BN-folded input) -> u,
 
 struct EpiSlotTC {   // 32-column chunk c0 -> slot c0/32 of a slot-major buffer
   static constexpr bool kExtra = false;
+  static constexpr int kFast = 1;
   bf16* out; long long slot_stride;
   __device__ __forceinline__ void chunk(long long p, long long, long long, bool valid, int c0, float v[32]) {
     if (!valid) return;
@@ -211,49 +208,58 @@ struct EpiSlotTC {   // 32-column chunk c0 -> slot c0/32 of a slot-major buffer
 
 struct EpiGateBwdTC {   // N = 32: dx = acc + du(cropped rows); (sum dx, sum dx*u_prev)
   // du and u_prev rows of the tile arrive by TMA as two extra 64B-swizzled [128 rows][64 B] tiles (the du tile is
-  // zero-filled outside the cropped range), so the epilogue never waits on a global load.
+  // zero-filled outside the cropped range), so the epilogue never waits on a global load.  The 32 columns are
+  // processed as two halves of 16 (keeps the live registers under the 96 the 640-thread CTA allows).
   static constexpr bool kExtra = true;
+  static constexpr int kFast = 4;
   float* dx; double* stats;
-  float s1, s2;
+  float s1[2], s2[2];
   __device__ __forceinline__ void chunk_ex(long long p, long long, long long, bool valid, int, float v[32],
                                            const uint8_t* extra, int r) {
     const int lane = threadIdx.x & 31;
-    float up[32];
-    if (valid) {
-      const int sw = (r >> 1) & 3;                              // 64B swizzle: logical 16-byte chunk c sits at c ^ sw
-      const uint8_t* drow = extra + (size_t)r * 64;
-      const uint8_t* urow = extra + 8192 + (size_t)r * 64;
+    const int sw = (r >> 1) & 3;                                // 64B swizzle: logical 16-byte chunk c sits at c ^ sw
+    const uint8_t* drow = extra + (size_t)r * 64;
+    const uint8_t* urow = extra + 8192 + (size_t)r * 64;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint4 qd = *reinterpret_cast<const uint4*>(drow + ((c ^ sw) << 4));
-        const uint4 qu = *reinterpret_cast<const uint4*>(urow + ((c ^ sw) << 4));
-        const uint32_t wd[4] = {qd.x, qd.y, qd.z, qd.w}, wu[4] = {qu.x, qu.y, qu.z, qu.w};
+    for (int h = 0; h < 2; ++h) {
+      float up[16];
+      float* vh = v + 16 * h;
+      if (valid) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          v[8 * c + 2 * i] += __uint_as_float(wd[i] << 16);
-          v[8 * c + 2 * i + 1] += __uint_as_float(wd[i] & 0xFFFF0000u);
-          up[8 * c + 2 * i] = __uint_as_float(wu[i] << 16);
-          up[8 * c + 2 * i + 1] = __uint_as_float(wu[i] & 0xFFFF0000u);
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = 2 * h + cc;
+          const uint4 qd = *reinterpret_cast<const uint4*>(drow + ((c ^ sw) << 4));
+          const uint4 qu = *reinterpret_cast<const uint4*>(urow + ((c ^ sw) << 4));
+          const uint32_t wd[4] = {qd.x, qd.y, qd.z, qd.w}, wu[4] = {qu.x, qu.y, qu.z, qu.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            vh[8 * cc + 2 * i] += __uint_as_float(wd[i] << 16);
+            vh[8 * cc + 2 * i + 1] += __uint_as_float(wd[i] & 0xFFFF0000u);
+            up[8 * cc + 2 * i] = __uint_as_float(wu[i] << 16);
+            up[8 * cc + 2 * i + 1] = __uint_as_float(wu[i] & 0xFFFF0000u);
+          }
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) store4(dx + p * 32 + 16 * h + 4 * j, vh + 4 * j);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) up[c] *= vh[c];
+      } else {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) { vh[c] = 0.f; up[c] = 0.f; }
       }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) store4(dx + p * 32 + 4 * j, v + 4 * j);
-    } else {
-#pragma unroll
-      for (int c = 0; c < 32; ++c) { v[c] = 0.f; up[c] = 0.f; }
+      s1[h] += warp_column_sums16(vh, lane);      // in place: vh and up are dead afterwards
+      s2[h] += warp_column_sums16(up, lane);
     }
-    float t[32];
-#pragma unroll
-    for (int c = 0; c < 32; ++c) t[c] = v[c];
-    s1 += warp_column_sums(t, lane);
-#pragma unroll
-    for (int c = 0; c < 32; ++c) t[c] = v[c] * up[c];
-    s2 += warp_column_sums(t, lane);
   }
   __device__ __forceinline__ void finish() {
     const int lane = threadIdx.x & 31;
-    atomicAdd(stats + lane, (double)s1);
-    atomicAdd(stats + 32 + lane, (double)s2);
+    if ((lane & 1) == 0) {                         // lanes 2c, 2c+1 both hold column c of each half
+      const int c = lane >> 1;
+      atomicAdd(stats + c, (double)s1[0]);
+      atomicAdd(stats + 16 + c, (double)s1[1]);
+      atomicAdd(stats + 32 + c, (double)s2[0]);
+      atomicAdd(stats + 48 + c, (double)s2[1]);
+    }
   }
 };
 
@@ -678,18 +684,18 @@ static int layer_fwd_t(const gwn_layer_cfg* c, const gwn_layer_fwd_args* g, cuda
       wp.W = g->w_fg; wp.ld = 64; wp.transposed = 0; wp.K = 32 * c->taps; wp.N = 64;
       for (int j = 0; j < c->taps; ++j) wp.w_off[j] = (long long)j * 32 * 64;
       wp.scale = g->scale; wp.shift = g->shift; wp.bias = g->b_fg;
-      wp.img = reinterpret_cast<bf16*>(wsw); wp.bias_out = reinterpret_cast<float*>(wsw + 48 * 1024);
+      wp.img = reinterpret_cast<bf16*>(wsw); wp.bias_out = nullptr; wp.bias_chunk = 1; wp.half_odd = 1;
       if (c->has_gconv) {      // same launch: zero the BN statistics and build the fused gcn weight image
         wp.zero64 = g->stats;
         if (fused_fwd) { wp.g_w = g->w_mlp; wp.g_nmats = 2 * c->n_supports; wp.g_img = reinterpret_cast<bf16*>(wsw + 64 * 1024); }
       }
       if (int rc = launch_wprep(wp, st)) return rc;
       PgParams pg{};
-      pg.n_chunks = c->taps; pg.rows_per_n_out = RO; pg.P = P; pg.N = 64; pg.w_img = wp.img;
+      pg.n_chunks = c->taps; pg.rows_per_n_out = RO; pg.P = P; pg.N = 64; pg.w_img = wp.img; pg.has_bias = 1;
       for (int j = 0; j < c->taps; ++j)
         pg.ch[j] = PgChunk{reinterpret_cast<const bf16*>(g->u_prev), RI, (long long)j * c->dilation * c->V, 32, 0};
       EpiGateTC eg{};
-      eg.bias = wp.bias_out; eg.z = cat;
+      eg.z = cat;
       eg.a = c->training ? reinterpret_cast<bf16*>(g->a) : nullptr;
       eg.b = c->training ? reinterpret_cast<bf16*>(g->b) : nullptr;
       eg.z_last = reinterpret_cast<bf16*>(g->z_last); eg.last_begin = last_begin; eg.last_rows = last_rows;
@@ -736,13 +742,13 @@ static int layer_fwd_t(const gwn_layer_cfg* c, const gwn_layer_fwd_args* g, cuda
       wp.W = g->w_mlp; wp.ld = 32; wp.transposed = 0; wp.K = mlp_in; wp.N = 32;
       for (int q = 0; q < nslots; ++q) wp.w_off[q] = (long long)q * 32 * 32;
       wp.bias = g->b_mlp;
-      wp.img = reinterpret_cast<bf16*>(wsw + 64 * 1024); wp.bias_out = reinterpret_cast<float*>(wsw + 112 * 1024);
+      wp.img = reinterpret_cast<bf16*>(wsw + 64 * 1024); wp.bias_out = nullptr; wp.bias_chunk = 1;
       if (int rc = launch_wprep(wp, st)) return rc;
       PgParams pg{};
-      pg.n_chunks = nslots; pg.rows_per_n_out = RO; pg.P = P; pg.N = 32; pg.w_img = wp.img;
+      pg.n_chunks = nslots; pg.rows_per_n_out = RO; pg.P = P; pg.N = 32; pg.w_img = wp.img; pg.has_bias = 1;
       for (int q = 0; q < nslots; ++q) pg.ch[q] = PgChunk{cat + q * P * 32, RO, 0, 32, 0};
       EpiMlpTC em{};
-      em.bias = wp.bias_out; em.u_prev = reinterpret_cast<const bf16*>(g->u_prev); em.prev_rows_per_n = RI;
+      em.u_prev = reinterpret_cast<const bf16*>(g->u_prev); em.prev_rows_per_n = RI;
       em.crop = (long long)(c->Lin - c->Lout) * c->V; em.scale = g->scale; em.shift = g->shift;
       em.mask = c->training ? reinterpret_cast<const bf16*>(g->drop_mask) : nullptr;
       em.drop_p = c->training ? c->dropout_p : 0.f; em.seed = c->seed; em.offset = c->offset; em.rng = g->rng;
@@ -1021,7 +1027,7 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
         for (int h = 0; h < 2; ++h)
           pg.ch[2 * j + h] = PgChunk{dfg16, RO, -(long long)j * c->dilation * c->V, 64, h * 32};
       EpiGateBwdTC eb2{};
-      eb2.dx = g->dx_prev; eb2.stats = g->dx_stats; eb2.s1 = 0.f; eb2.s2 = 0.f;
+      eb2.dx = g->dx_prev; eb2.stats = g->dx_stats; eb2.s1[0] = eb2.s1[1] = eb2.s2[0] = eb2.s2[1] = 0.f;
       // extra tiles for the epilogue: du shifted by the crop (zero outside), u_prev
       pg.n_extra = 2;
       // (no du for the last layer: a row offset far past the sample makes TMA zero-fill the whole tile)

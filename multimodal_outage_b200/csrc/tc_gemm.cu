@@ -10,9 +10,10 @@ __global__ void wprep_kernel(WPrepParams w) {
     const int q = k >> 5, kk = k & 31;
     float val = w.transposed ? w.W[w.w_off[q] + (long long)n * w.ld + kk] : w.W[w.w_off[q] + (long long)kk * w.ld + n];
     if (w.scale) val *= w.scale[kk];
+    if (w.half_odd && (n & 1)) val *= 0.5f;
     w.img[((long long)(k >> 3) * w.N + n) * 8 + (k & 7)] = __float2bfloat16_rn(val);
   }
-  if (w.bias_out) {
+  if (w.bias_out || w.bias_chunk) {
     for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < w.N; n += gridDim.x * blockDim.x) {
       float b = w.bias ? w.bias[n] : 0.f;
       if (w.shift) {
@@ -23,7 +24,20 @@ __global__ void wprep_kernel(WPrepParams w) {
           b = fmaf(w.shift[kk], val, b);
         }
       }
-      w.bias_out[n] = b;
+      if (w.half_odd && (n & 1)) b *= 0.5f;
+      if (w.bias_out) w.bias_out[n] = b;
+      if (w.bias_chunk) {       // split-precision bias rows of the extra K=16 chunk
+        const bf16 hi = __float2bfloat16_rn(b);
+        const bf16 lo = __float2bfloat16_rn(b - __bfloat162float(hi));
+        bf16* d0 = w.img + ((long long)(w.K >> 3) * w.N + n) * 8;
+        bf16* d1 = w.img + ((long long)((w.K >> 3) + 1) * w.N + n) * 8;
+        const bf16 z = __float2bfloat16_rn(0.f);
+        d0[0] = hi; d0[1] = lo;
+#pragma unroll
+        for (int i = 2; i < 8; ++i) d0[i] = z;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d1[i] = z;
+      }
     }
   }
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;

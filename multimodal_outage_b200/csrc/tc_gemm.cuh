@@ -26,7 +26,9 @@ struct PgParams {
   int n_extra;                  // extra (non-MMA) source tiles ch[n_chunks .. n_chunks+n_extra) brought in by TMA for the epilogue
   long long rows_per_n_out, P;
   int N;                        // output columns (multiple of 16, <= 256)
-  const bf16* w_img;            // [K/8][N][8]
+  const bf16* w_img;            // [K/8 (+2 with has_bias)][N][8]
+  int has_bias;                 // the image carries a bias chunk (K = 16: row 0 = bf16 hi, row 1 = bf16 lo of the fp32 bias):
+                                // one extra MMA per sub-tile against a resident "ones" tile plants it in the accumulator
   int n_tiles;
   // filled by the launcher: TMA tiling.  A tile is 128 consecutive output rows of ONE sample, so that a chunk
   // (temporal tap / concat slot) is one 3-D box {32 ch, 128 rows, 1 sample} whose out-of-range rows TMA zero-fills.
@@ -50,6 +52,8 @@ struct WPrepParams {
   const float* bias;            // optional [N]
   bf16* img;                    // out [K/8][N][8]
   float* bias_out;              // out [N] (may be NULL)
+  int bias_chunk;               // != 0: append the (folded) bias as two K pieces [2][N][8] (k=0: bf16 hi, k=1: bf16 lo)
+  int half_odd;                 // != 0: odd output columns (and their bias) are scaled by 0.5 (sigmoid(g) = 0.5 tanh(g/2) + 0.5)
   // piggy-backed jobs (one launch instead of three graph nodes): zero 64 doubles; the fused gcn weight images
   double* zero64;               // optional
   const float* g_w; int g_nmats;     // packed mlp weight [32*(1+g_nmats), 32] (NULL: no gcn images)

@@ -14,10 +14,14 @@
 
 namespace gwn {
 
-constexpr int PGT_PRODUCERS = 128;   // warps 0-3 (warp 0 lane 0 issues the TMA copies)
-constexpr int PGT_MMA_WARP = 4;
-constexpr int PGT_EPI_WARPS = 12;    // warps 5-16, three per TMEM lane quadrant: they share the (sub-tile, 32-column chunk) items
-constexpr int PGT_THREADS = 32 * (5 + PGT_EPI_WARPS);
+// warps: 0 and 2 = TMA producers (one thread each, on different schedulers; they split a tile's boxes),
+// 1 = MMA issuer, 3 idle, 4-19 = epilogue (four per TMEM lane quadrant = per scheduler)
+constexpr int PGT_PROD_A = 0, PGT_MMA_WARP = 1, PGT_PROD_B = 2;
+constexpr int PGT_EPI_WARP0 = 4;
+constexpr int PGT_EPI_WARPS = 16;
+constexpr int PGT_EPI_RANKS = PGT_EPI_WARPS / 4;
+constexpr int PGT_THREADS = 32 * (PGT_EPI_WARP0 + PGT_EPI_WARPS);
+constexpr uint32_t PGT_ONES_BYTES = 4096;   // resident "ones" A tile of the bias MMA: [2 K pieces][128 rows][16 B]
 
 // lane c of the warp ends up with sum over the 32 lanes of v[c]  (31 shuffles; v is destroyed)
 __device__ __forceinline__ float warp_column_sums(float v[32], int lane) {
@@ -34,129 +38,207 @@ __device__ __forceinline__ float warp_column_sums(float v[32], int lane) {
   return v[0];
 }
 
+// 16 columns: lanes 2c and 2c+1 both end up with the sum over the 32 lanes of v[c]  (16 shuffles; v is destroyed)
+__device__ __forceinline__ float warp_column_sums16(float v[16], int lane) {
+#pragma unroll
+  for (int step = 16; step >= 2; step >>= 1) {
+    const bool up = (lane & step) != 0;
+    const int half = step >> 1;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float keep = up ? v[i + half] : v[i];
+      const float send = up ? v[i] : v[i + half];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 struct PgMaps { CUtensorMap m[PG_TC_MAX_MAPS]; };
-#define PG_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && g < 48 && lane == 0) p.trace[g * 8 + (slot)] = clock64(); } while (0)
+#define PG_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && g < 48) p.trace[g * 8 + (slot)] = clock64(); } while (0)
+
+// (sample, 128-row tile inside the sample) of a CTA's current macro tile, advanced without divisions: a 32-bit
+// division costs a few hundred cycles of latency on the rarely-scheduled producer / per-item epilogue paths
+struct PgWalk {
+  int n, rt, dn, dr, tpn;
+  __device__ __forceinline__ void init(int first_sub, int step_sub, int tiles_per_n) {
+    tpn = tiles_per_n;
+    n = first_sub / tpn; rt = first_sub - n * tpn;
+    dn = step_sub / tpn; dr = step_sub - dn * tpn;
+  }
+  __device__ __forceinline__ void advance() {
+    n += dn; rt += dr;
+    if (rt >= tpn) { rt -= tpn; ++n; }
+  }
+  __device__ __forceinline__ void sub(int t, int& ns, int& r0) const {   // sub-tile t of the macro tile
+    ns = n; int r = rt + t;
+    while (r >= tpn) { r -= tpn; ++ns; }
+    r0 = r * 128;
+  }
+};
 
 // A operand: per chunk one TMA box -> [128 rows][64 B] 64B-swizzled (K-major SW64: 8-row atoms of 512 B, the two
-// K=16 halves of a chunk 32 B apart); B operand: resident no-swizzle weight image; D: two TMEM accumulators.
-template <typename Epi>
+// K=16 halves of a chunk 32 B apart); B operand: resident no-swizzle weight image; D: 2 or 4 TMEM accumulators.
+// NCH > 0: the chunk count is a compile-time constant (the MMA issue loop unrolls to immediates).
+template <typename Epi, int NCH>
 __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __grid_constant__ PgMaps maps,
                                                                       const __grid_constant__ PgParams p, Epi epi,
-                                                                      int stages) {
+                                                                      int stages, int n_acc) {
   using namespace tc;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int N = p.N, K8 = p.n_chunks * 4;                     // 16-byte K pieces per weight row
+  const int N = p.N;
+  const int n_chunks = NCH > 0 ? NCH : p.n_chunks;
+  const int K8 = n_chunks * 4 + (p.has_bias ? 2 : 0);        // 16-byte K pieces per weight row
   const int SUB = p.sub;
-  const int NB = p.n_chunks + p.n_extra;                       // TMA boxes per sub-tile (MMA chunks + epilogue extras)
+  const int NB = n_chunks + p.n_extra;                         // TMA boxes per sub-tile (MMA chunks + epilogue extras)
   const uint32_t a_bytes = (uint32_t)NB * 8192u * (uint32_t)SUB;   // one stage: SUB x NB boxes of 128 x 64 B
   const uint32_t w_bytes = ((uint32_t)K8 * (uint32_t)N * 16u + 1023u) & ~1023u;
   uint8_t* a_s = smem;                                        // stages first (1024-aligned boxes)
   uint8_t* w_s = smem + (size_t)stages * a_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(w_s + w_bytes);
-  uint64_t* full = bars;               // [stages] (<= 4)
-  uint64_t* empty = bars + 4;
-  uint64_t* tfull = bars + 8;          // [2]
-  uint64_t* tempty = bars + 10;        // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint8_t* ones_s = w_s + w_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ones_s + PGT_ONES_BYTES);
+  uint64_t* full = bars;               // [stages] (<= 8)
+  uint64_t* empty = bars + 8;
+  uint64_t* tfull = bars + 16;         // [n_acc] (<= 4)
+  uint64_t* tempty = bars + 20;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  (void)a_s;
 
   if (tid == 0) {
     // a stage is free when the MMAs have read it and (with extras) every epilogue thread is done with it
-    for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], p.n_extra ? 1 + 32 * PGT_EPI_WARPS : 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 32 * PGT_EPI_WARPS); }
+    for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], p.n_extra ? 1 + 32 * PGT_EPI_WARPS : 1); }
+    for (int i = 0; i < n_acc; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 32 * PGT_EPI_WARPS); }
     fence_barrier_init();
   }
   const uint32_t acc_cols = N <= 32 ? 32u : N <= 64 ? 64u : N <= 128 ? 128u : 256u;
   const uint32_t buf_cols = acc_cols * (uint32_t)SUB;          // one accumulator buffer: SUB sub-tiles side by side
-  if (warp == PGT_MMA_WARP) tmem_alloc(tmem_slot, 2 * buf_cols);
+  if (warp == PGT_MMA_WARP) tmem_alloc(tmem_slot, (uint32_t)n_acc * buf_cols);
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.w_img);
     uint4* dst = reinterpret_cast<uint4*>(w_s);
     for (int i = tid; i < K8 * N; i += PGT_THREADS) dst[i] = __ldg(src + i);
+    // ones tile: element (row, k) = 1 for k < 2 (the two bias rows), else 0
+    uint4* od = reinterpret_cast<uint4*>(ones_s);
+    for (int i = tid; i < 256; i += PGT_THREADS) od[i] = i < 128 ? make_uint4(0x3F803F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int acc_mask = n_acc - 1, acc_shift = n_acc == 4 ? 2 : 1;
 
-  if (warp == 0) {
-    // ===================== TMA producer (one thread) =====================
-    if (lane == 0) {
-      int g = 0;
+  if (warp == PGT_PROD_A || warp == PGT_PROD_B) {
+    // ===================== TMA producers (boxes of a macro tile dealt alternately to the two warps; the whole warp
+    // walks the loop so addresses / coordinates stay in uniform registers, one elected lane issues) =====================
+    {
+      const int me = warp == PGT_PROD_A ? 0 : 1;
+      const int boxes = SUB * NB;
+      const uint32_t my_bytes = (uint32_t)((boxes + 1 - me) >> 1) * 8192u;
+      PgWalk w; w.init((int)blockIdx.x * SUB, (int)gridDim.x * SUB, p.tiles_per_n);
+      int g = 0, stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++g) {
-        const int stage = g % stages, phase = (g / stages) & 1;
         mbar_wait(&empty[stage], (uint32_t)(phase ^ 1));
-        PG_TRACE(0);
-        tg::mbar_expect_tx(&full[stage], a_bytes);
-        const uint32_t sa = base + (uint32_t)stage * a_bytes;
-        for (int t = 0; t < SUB; ++t) {
-          // sub-tile st = 128 consecutive rows of ONE sample; past the last sub-tile the sample index is out of range
-          // and TMA zero-fills the box
-          const int st = tile * SUB + t;
-          const int n = st / p.tiles_per_n, r0 = (st - n * p.tiles_per_n) * 128;
-          for (int q = 0; q < NB; ++q)
-            tg::tma_3d(sa + (uint32_t)(t * NB + q) * 8192u, &maps.m[p.map_of[q]], 0, r0 + p.row_off[q], n, &full[stage]);
+        if (me == 0 && lane == 0) PG_TRACE(0);
+        if (elect_one()) {
+          if (my_bytes) tg::mbar_expect_tx(&full[stage], my_bytes); else mbar_arrive(&full[stage]);
+          const uint32_t sa = base + (uint32_t)stage * a_bytes;
+          int i = 0;
+          for (int t = 0; t < SUB; ++t) {
+            // sub-tile = 128 consecutive rows of ONE sample; past the last sub-tile the sample index is out of range
+            // and TMA zero-fills the box
+            int n, r0;
+            w.sub(t, n, r0);
+            for (int q = 0; q < NB; ++q, ++i)
+              if ((i & 1) == me)
+                tg::tma_3d(sa + (uint32_t)i * 8192u, &maps.m[p.map_of[q]], 0, r0 + p.row_off[q], n, &full[stage]);
+          }
         }
-        PG_TRACE(1);
+        __syncwarp();
+        if (me == 0 && lane == 0) PG_TRACE(1);
+        w.advance();
+        if (++stage == stages) { stage = 0; phase ^= 1; }
       }
     }
-    __syncwarp();
   } else if (warp == PGT_MMA_WARP) {
-    if (lane == 0) {
+    // ===================== MMA issuer: the whole warp walks the loop (uniform registers), one elected lane issues =====================
+    {
       const uint32_t idesc = make_idesc_bf16(128, N, false, false);
       const uint32_t w_addr = smem_u32(w_s);
       // descriptor templates: only the 14-bit start-address field changes per MMA (addresses < 256 KB: no carry)
       const uint64_t at = tg::make_desc_sw(0, 16u, 512u, 4u);
       const uint64_t bt = make_smem_desc(w_addr, (uint32_t)N * 16u, 128u);
+      const uint64_t ones_d = make_smem_desc(smem_u32(ones_s), 2048u, 128u);
       const uint32_t bstep = ((uint32_t)N * 32u) >> 4;            // two K pieces of the weight image per K=16 step
-      int g = 0;
+      const uint64_t bias_d = bt + (uint64_t)(2u * bstep) * (uint32_t)n_chunks;
+      const bool has_bias = p.has_bias != 0;
+      int g = 0, stage = 0, sphase = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const int stage = g % stages, acc = g & 1;
-        mbar_wait(&tempty[acc], (uint32_t)(((g >> 1) & 1) ^ 1));
-        PG_TRACE(2);
-        mbar_wait(&full[stage], (uint32_t)((g / stages) & 1));
-        PG_TRACE(3);
+        const int acc = g & acc_mask;
+        mbar_wait(&tempty[acc], (uint32_t)(((g >> acc_shift) & 1) ^ 1));
+        if (lane == 0) PG_TRACE(2);
+        mbar_wait(&full[stage], (uint32_t)sphase);
+        if (lane == 0) PG_TRACE(3);
         tc_fence_after();
-        for (int t = 0; t < SUB; ++t) {
-          uint64_t ad = at + (uint64_t)((base + (uint32_t)stage * a_bytes + (uint32_t)(t * NB) * 8192u) >> 4);
-          uint64_t bd = bt;
-          const uint32_t d = tmem_base + (uint32_t)acc * buf_cols + (uint32_t)t * acc_cols;
+        if (elect_one()) {
+          for (int t = 0; t < SUB; ++t) {
+            uint64_t ad = at + (uint64_t)((base + (uint32_t)stage * a_bytes + (uint32_t)(t * NB) * 8192u) >> 4);
+            uint64_t bd = bt;
+            const uint32_t d = tmem_base + (uint32_t)acc * buf_cols + (uint32_t)t * acc_cols;
+            if (has_bias) umma_bf16(d, ones_d, bias_d, idesc, 0u);
+            if constexpr (NCH > 0) {
+#pragma unroll
+              for (int q = 0; q < NCH; ++q) {
+                umma_bf16(d, ad + (uint64_t)(q * 512), bd + (uint64_t)(2u * q) * bstep, idesc, (q == 0 && !has_bias) ? 0u : 1u);
+                umma_bf16(d, ad + (uint64_t)(q * 512 + 2), bd + (uint64_t)(2u * q + 1u) * bstep, idesc, 1u);
+              }
+            } else {
 #pragma unroll 2
-          for (int q = 0; q < p.n_chunks; ++q) {
-            umma_bf16(d, ad, bd, idesc, q == 0 ? 0u : 1u);
-            umma_bf16(d, ad + 2u, bd + bstep, idesc, 1u);            // second K=16 half of the chunk: +32 B
-            ad += 8192u >> 4;
-            bd += 2u * bstep;
+              for (int q = 0; q < n_chunks; ++q) {
+                umma_bf16(d, ad, bd, idesc, (q == 0 && !has_bias) ? 0u : 1u);
+                umma_bf16(d, ad + 2u, bd + bstep, idesc, 1u);            // second K=16 half of the chunk: +32 B
+                ad += 8192u >> 4;
+                bd += 2u * bstep;
+              }
+            }
           }
+          umma_commit(&empty[stage]);
+          umma_commit(&tfull[acc]);
         }
-        umma_commit(&empty[stage]);
-        umma_commit(&tfull[acc]);
-        PG_TRACE(4);
+        __syncwarp();
+        if (lane == 0) PG_TRACE(4);
         ++g;
+        if (++stage == stages) { stage = 0; sphase ^= 1; }
       }
     }
-    __syncwarp();
-  } else if (warp > PGT_MMA_WARP) {
+  } else if (warp >= PGT_EPI_WARP0) {
     // ===================== epilogue =====================
     const int quad = warp & 3;
-    const int rank = (warp - (PGT_MMA_WARP + 1)) >> 2;          // 0..2: which of the quadrant's three warps
+    const int rank = (warp - PGT_EPI_WARP0) >> 2;               // 0..3: which of the quadrant's four warps
     const int n_c32 = (N + 31) / 32;                            // 32-column chunks per sub-tile
-    int g = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      const int acc = g & 1, stage = g % stages;
-      mbar_wait(&tfull[acc], (uint32_t)((g >> 1) & 1));
-      if (warp == PGT_MMA_WARP + 1) PG_TRACE(5);
+    const int IT = SUB * n_c32;                                 // work items (sub-tile, chunk) per macro tile
+    const bool nc_pow2 = (n_c32 & (n_c32 - 1)) == 0;
+    const int nc_shift = n_c32 >= 8 ? 3 : n_c32 >= 4 ? 2 : n_c32 >= 2 ? 1 : 0;
+    PgWalk w; w.init((int)blockIdx.x * SUB, (int)gridDim.x * SUB, p.tiles_per_n);
+    int g = 0, stage = 0;
+    int first = rank;                                           // items are dealt round-robin ACROSS tiles, so that
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {   // narrow tiles (IT < 4) still use every warp
+      const int acc = g & acc_mask;
+      mbar_wait(&tfull[acc], (uint32_t)((g >> acc_shift) & 1));
+      if (warp == PGT_EPI_WARP0 && lane == 0) PG_TRACE(5);
       tc_fence_after();
-      // work items (sub-tile t, chunk c) dealt round-robin to the quadrant's warps
-      for (int item = rank; item < SUB * n_c32; item += PGT_EPI_WARPS / 4) {
-        const int t = item / n_c32, c0 = (item - t * n_c32) * 32;
-        const int st = tile * SUB + t;
-        const int ns = st / p.tiles_per_n;
-        const int r = (st - ns * p.tiles_per_n) * 128 + quad * 32 + lane;
+      int item = first;
+      for (; item < IT; item += PGT_EPI_RANKS) {
+        int t, ci;
+        if (nc_pow2) { t = item >> nc_shift; ci = item & (n_c32 - 1); } else { t = item / n_c32; ci = item - t * n_c32; }
+        const int c0 = ci * 32;
+        int ns, r0;
+        w.sub(t, ns, r0);
+        const int r = r0 + quad * 32 + lane;
         const bool pv = r < p.rows_out && ns < p.n_samples;
         // (sample, row) of the caller's view: virtual samples (position-wise GEMMs tile the flat position axis)
         long long pp = (long long)ns * p.rows_out + r, n = ns, rem = r;
@@ -164,15 +246,18 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * buf_cols + (uint32_t)t * acc_cols + (uint32_t)c0, v);
         if constexpr (Epi::kExtra)
-          epi.chunk_ex(pp, n, rem, pv, c0, v, smem + (size_t)stage * a_bytes + (size_t)(t * NB + p.n_chunks) * 8192, quad * 32 + lane);
+          epi.chunk_ex(pp, n, rem, pv, c0, v, smem + (size_t)stage * a_bytes + (size_t)(t * NB + n_chunks) * 8192, quad * 32 + lane);
         else
           epi.chunk(pp, n, rem, pv, c0, v);
       }
+      first = item - IT;                                        // where this warp starts in the next tile
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
       if (p.n_extra) mbar_arrive(&empty[stage]);
-      if (warp == PGT_MMA_WARP + 1) PG_TRACE(6);
+      if (warp == PGT_EPI_WARP0 && lane == 0) PG_TRACE(6);
       ++g;
+      w.advance();
+      if (++stage == stages) stage = 0;
     }
     epi.finish();
   }
@@ -180,8 +265,21 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
   __syncthreads();
   if (warp == PGT_MMA_WARP) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * buf_cols);
+    tmem_dealloc(tmem_base, (uint32_t)n_acc * buf_cols);
   }
+}
+
+template <typename Epi, int NCH>
+static int pos_gemm_tc_run(const PgMaps& maps, const PgParams& p, const Epi& epi, int stages, int n_acc, int grid, size_t smem,
+                           cudaStream_t st) {
+  static bool attr_set = false;   // per instantiation
+  if (!attr_set) {
+    GWN_CUDA(cudaFuncSetAttribute(pos_gemm_tc_kernel<Epi, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  pos_gemm_tc_kernel<Epi, NCH><<<grid, PGT_THREADS, smem, st>>>(maps, p, epi, stages, n_acc);
+  GWN_LAUNCHED();
+  return 0;
 }
 
 template <typename Epi>
@@ -200,15 +298,36 @@ int launch_pos_gemm_tc(PgParams& p, const Epi& epi, cudaStream_t st) {
   GWN_REQUIRE(n_real * p.rows_per_n_out == p.P, "pos_gemm_tc: P is not a whole number of samples");
   p.rows_out = flat ? (int)p.P : (int)p.rows_per_n_out;
   p.n_samples = flat ? 1 : (int)n_real;
-  // macro tiles: several 128-row sub-tiles per pipeline step when the accumulators are narrow (the producer / MMA
-  // threads pay ~0.5 us of hand-off latency per step whatever the tile holds)
+  const int sms = tg_sm_count();
   const int acc_c = p.N <= 32 ? 32 : p.N <= 64 ? 64 : p.N <= 128 ? 128 : 256;
-  p.sub = 1;
+  const size_t w_bytes = ((size_t)(p.n_chunks * 4 + (p.has_bias ? 2 : 0)) * p.N * 16 + 1023) & ~(size_t)1023;
+  const size_t fixed = w_bytes + PGT_ONES_BYTES + 1024 + 256;
+  GWN_REQUIRE(fixed + 2 * (size_t)NB * 8192 <= 227 * 1024, "pos_gemm_tc: K=%d does not fit 2 stages in shared memory",
+              32 * p.n_chunks);
   p.tiles_per_n = (int)cdiv(p.rows_out, 128);                     // 128-row sub-tiles per (virtual) sample
   const long long sub_tiles = (long long)p.n_samples * p.tiles_per_n;
-  while (p.sub < 4 && 2 * acc_c * (p.sub * 2) <= 512 && (size_t)NB * 8192 * (p.sub * 2) * 2 <= 150 * 1024 &&
-         cdiv(sub_tiles, p.sub * 2) >= 2 * tg_sm_count())
-    p.sub *= 2;
+  // macro tiles: several 128-row sub-tiles per pipeline step amortise the hand-offs; the choice also looks at the
+  // wave quantisation of the persistent grid (tiles / (ceil(tiles / SMs) * SMs))
+  int subs[3] = {1, 2, 4}, stg_of[3] = {0, 0, 0};
+  double eff_of[3] = {-1, -1, -1}, best_eff = -1;
+  for (int i = 0; i < 3; ++i) {
+    const int sub = subs[i];
+    if (2 * acc_c * sub > 512) continue;
+    const size_t ab = (size_t)NB * 8192 * sub;
+    int stg = (int)((227 * 1024 - fixed) / ab);
+    if (stg > 8) stg = 8;
+    if (stg < (sub == 1 ? 2 : 3)) continue;
+    const long long nt = cdiv(sub_tiles, sub);
+    const long long waves = cdiv(nt, sms);
+    stg_of[i] = stg; eff_of[i] = (double)sub_tiles / (double)(waves * sms * sub);
+    if (eff_of[i] > best_eff) best_eff = eff_of[i];
+  }
+  int pick = 0;
+  for (int i = 0; i < 3; ++i)
+    if (eff_of[i] >= best_eff - 0.02) pick = i;
+  p.sub = subs[pick];
+  const int stages = stg_of[pick];
+  const int n_acc = acc_c * p.sub <= 128 ? 4 : 2;
   p.n_tiles = (int)cdiv(sub_tiles, p.sub);
   PgMaps maps;
   int n_maps = 0;
@@ -236,22 +355,12 @@ int launch_pos_gemm_tc(PgParams& p, const Epi& epi, cudaStream_t st) {
     const char* e = getenv("GWN_PG_TRACE");
     p.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
   }
-  const size_t w_bytes = ((size_t)p.n_chunks * 4 * p.N * 16 + 1023) & ~(size_t)1023;
   const size_t a_bytes = (size_t)NB * 8192 * p.sub;
-  int stages = (int)((220 * 1024 - w_bytes - 1024 - 256) / a_bytes);
-  if (stages > 4) stages = 4;
-  GWN_REQUIRE(stages >= 2, "pos_gemm_tc: K=%d does not fit 2 stages in shared memory", 32 * p.n_chunks);
-  const size_t smem = w_bytes + stages * a_bytes + 1024 + 256;
-  static bool attr_set = false;   // per (Epi) instantiation
-  if (!attr_set) {
-    GWN_CUDA(cudaFuncSetAttribute(pos_gemm_tc_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
-  const int sms = tg_sm_count();
-  int grid = p.n_tiles < sms ? p.n_tiles : sms;
-  pos_gemm_tc_kernel<Epi><<<grid, PGT_THREADS, smem, st>>>(maps, p, epi, stages);
-  GWN_LAUNCHED();
-  return 0;
+  const size_t smem = fixed + stages * a_bytes;
+  const int grid = p.n_tiles < sms ? p.n_tiles : sms;
+  if constexpr (Epi::kFast > 0)
+    if (p.n_chunks == Epi::kFast) return pos_gemm_tc_run<Epi, Epi::kFast>(maps, p, epi, stages, n_acc, grid, smem, st);
+  return pos_gemm_tc_run<Epi, 0>(maps, p, epi, stages, n_acc, grid, smem, st);
 }
 
 }  // namespace gwn

@@ -82,47 +82,58 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int g = 0;
+    // ===================== TMA producer (whole warp walks the loop, one elected lane issues) =====================
+    {
+      int g = 0, stage = 0, phase = 0;
       const uint32_t tx = (uint32_t)p.n_chunks * WG_ATOM + g_bytes;
+      int n = (int)blockIdx.x / p.tiles_per_n, rt = (int)blockIdx.x - n * p.tiles_per_n;
+      const int dn = (int)gridDim.x / p.tiles_per_n, dr = (int)gridDim.x - dn * p.tiles_per_n;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++g) {
-        const int stage = g % WG_STAGES, phase = (g / WG_STAGES) & 1;
-        const int n = tile / p.tiles_per_n, r0 = (tile - n * p.tiles_per_n) * WG_PT;
+        const int r0 = rt * WG_PT;
         mbar_wait(&empty[stage], (uint32_t)(phase ^ 1));
         WG_TRACE(0);
-        tg::mbar_expect_tx(&full[stage], tx);
-        const uint32_t sa = base + (uint32_t)stage * stage_bytes, sg = sa + a_bytes;
-        for (int q = 0; q < p.n_chunks; ++q)
-          tg::tma_3d(sa + (uint32_t)q * WG_ATOM, &maps.a[p.map_of[q]], 0, r0 + p.row_off[q], n, &full[stage]);
-        for (int j = 0; j < N / 32; ++j) tg::tma_3d(sg + (uint32_t)j * WG_ATOM, &maps.g[j], 0, r0, n, &full[stage]);
+        if (elect_one()) {
+          tg::mbar_expect_tx(&full[stage], tx);
+          const uint32_t sa = base + (uint32_t)stage * stage_bytes, sg = sa + a_bytes;
+          for (int q = 0; q < p.n_chunks; ++q)
+            tg::tma_3d(sa + (uint32_t)q * WG_ATOM, &maps.a[p.map_of[q]], 0, r0 + p.row_off[q], n, &full[stage]);
+          for (int j = 0; j < N / 32; ++j) tg::tma_3d(sg + (uint32_t)j * WG_ATOM, &maps.g[j], 0, r0, n, &full[stage]);
+        }
+        __syncwarp();
         WG_TRACE(1);
+        n += dn; rt += dr;
+        if (rt >= p.tiles_per_n) { rt -= p.tiles_per_n; ++n; }
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
       }
     }
     __syncwarp();
   } else if (warp == WG_MMA_WARP) {
-    if (lane == 0) {
+    {
       const uint32_t idesc = make_idesc_bf16(128, N, /*a_mn=*/true, /*b_mn=*/true);
-      int g = 0;
+      // MN-major SW64: LBO = next 32-channel atom, SBO = next 8 positions, K=16 step = 1024 B
+      const uint64_t dt = tg::make_desc_sw(0, WG_ATOM, 512u, 4u);
+      int g = 0, stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const int stage = g % WG_STAGES;
-        mbar_wait(&full[stage], (uint32_t)((g / WG_STAGES) & 1));
+        mbar_wait(&full[stage], (uint32_t)phase);
         WG_TRACE(3);
         tc_fence_after();
         const uint32_t sa = base + (uint32_t)stage * stage_bytes, sg = sa + a_bytes;
-        for (int t = 0; t < mt; ++t)
+        if (elect_one()) {
+          for (int t = 0; t < mt; ++t)
 #pragma unroll
-          for (int ks = 0; ks < WG_PT / 16; ++ks) {
-            // MN-major SW64: LBO = next 32-channel atom, SBO = next 8 positions, K=16 step = 1024 B
-            const uint64_t adesc = tg::make_desc_sw(sa + (uint32_t)t * 4u * WG_ATOM + (uint32_t)ks * 1024u, WG_ATOM, 512u, 4u);
-            const uint64_t bdesc = tg::make_desc_sw(sg + (uint32_t)ks * 1024u, WG_ATOM, 512u, 4u);
-            umma_bf16(tmem_base + (uint32_t)(t * N), adesc, bdesc, idesc, (g == 0 && ks == 0) ? 0u : 1u);
-          }
-        umma_commit(&empty[stage]);
+            for (int ks = 0; ks < WG_PT / 16; ++ks) {
+              const uint64_t adesc = dt + (uint64_t)((sa + (uint32_t)t * 4u * WG_ATOM + (uint32_t)ks * 1024u) >> 4);
+              const uint64_t bdesc = dt + (uint64_t)((sg + (uint32_t)ks * 1024u) >> 4);
+              umma_bf16(tmem_base + (uint32_t)(t * N), adesc, bdesc, idesc, (g == 0 && ks == 0) ? 0u : 1u);
+            }
+          umma_commit(&empty[stage]);
+        }
+        __syncwarp();
         WG_TRACE(4);
         ++g;
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
       }
-      umma_commit(tfull);
+      if (elect_one()) umma_commit(tfull);
     }
     __syncwarp();
   } else if (warp > WG_MMA_WARP) {

@@ -137,30 +137,38 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
   const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
 
+  // producer and MMA warps: the whole warp walks the loops (addresses, coordinates and descriptors stay in uniform
+  // registers, the tcgen05 / TMA instructions issue back to back); only those instructions run on one elected lane
   if (warp == 0) {
-    if (lane == 0) {
-      int it = 0;
+    {
+      int s = 0, ph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int mt = tile % p.m_tiles, rest = tile / p.m_tiles;
         const int nt = rest % p.n_tiles, sp = rest / p.n_tiles;
         const int kb0 = sp * p.kb_per_split;
         const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % ST, ph = (it / ST) & 1;
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[s], (uint32_t)(ph ^ 1));
-          mbar_expect_tx(&full[s], stage_bytes);
-          const uint32_t sa = base + (uint32_t)s * stage_bytes, sb = sa + p.a.tile_bytes;
-          load_operand(p.a, &mapA, sa, mt * TG_BM, p.a_kwrap > 0 ? (kb * TG_BK) % p.a_kwrap : kb * TG_BK, &full[s]);
-          load_operand(p.b, &mapB, sb, nt * p.bn, kb * TG_BK, &full[s]);
+          if (elect_one()) {
+            mbar_expect_tx(&full[s], stage_bytes);
+            const uint32_t sa = base + (uint32_t)s * stage_bytes, sb = sa + p.a.tile_bytes;
+            load_operand(p.a, &mapA, sa, mt * TG_BM, p.a_kwrap > 0 ? (kb * TG_BK) % p.a_kwrap : kb * TG_BK, &full[s]);
+            load_operand(p.b, &mapB, sb, nt * p.bn, kb * TG_BK, &full[s]);
+          }
+          __syncwarp();
+          if (++s == ST) { s = 0; ph ^= 1; }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t idesc = make_idesc_bf16(128, p.bn, p.a.mode == TG_MN_SW128 || p.a.mode == TG_MN_SW64,
                                              p.b.mode == TG_MN_SW128 || p.b.mode == TG_MN_SW64);
-      int it = 0, tcount = 0;
+      // descriptor templates: only the 14-bit start-address field changes per MMA (addresses < 256 KB: no carry)
+      const uint64_t at = make_desc_sw(0, p.a.lbo, p.a.sbo, p.a.layout);
+      const uint64_t bt = make_desc_sw(0, p.b.lbo, p.b.sbo, p.b.layout);
+      int s = 0, ph = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
         const int rest = tile / p.m_tiles;
         const int sp = rest / p.n_tiles;
@@ -170,20 +178,27 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         mbar_wait(&tempty[acc], (uint32_t)(((tcount >> 1) & 1) ^ 1));
         tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)acc * acc_cols;
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % ST, ph = (it / ST) & 1;
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[s], (uint32_t)ph);
           tc_fence_after();
           const uint32_t sa = base + (uint32_t)s * stage_bytes, sb = sa + p.a.tile_bytes;
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < TG_BK / 16; ++ks) {
-            const uint64_t adesc = make_desc_sw(sa + p.a.koff[ks], p.a.lbo, p.a.sbo, p.a.layout);
-            const uint64_t bdesc = make_desc_sw(sb + p.b.koff[ks], p.b.lbo, p.b.sbo, p.b.layout);
-            umma_bf16(d, adesc, bdesc, idesc, (kb == kb0 && ks == 0) ? 0u : 1u);
+            for (int ks = 0; ks < TG_BK / 16; ++ks) {
+              const uint64_t adesc = at + (uint64_t)((sa + p.a.koff[ks]) >> 4);
+              const uint64_t bdesc = bt + (uint64_t)((sb + p.b.koff[ks]) >> 4);
+              umma_bf16(d, adesc, bdesc, idesc, (kb == kb0 && ks == 0) ? 0u : 1u);
+            }
+            umma_commit(&empty[s]);
+            if (kb == kb1 - 1) umma_commit(&tfull[acc]);
           }
-          umma_commit(&empty[s]);
+          __syncwarp();
+          if (++s == ST) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tfull[acc]);
+        if (kb1 <= kb0) {
+          if (elect_one()) umma_commit(&tfull[acc]);
+          __syncwarp();
+        }
       }
     }
     __syncwarp();

@@ -19,5 +19,5 @@ t = trace.cpu().reshape(48, 8)
 t0 = t[0, 0].item()
 names = ['prod_got_empty', 'prod_issued', 'mma_got_tempty', 'mma_got_full', 'mma_issued', 'epi_got_tfull', 'epi_done']
 print('tile ' + ' '.join(f'{n:>15s}' for n in names))
-for k in range(4, 22):
+for k in range(2, 26):
     print(f'{k:4d} ' + ' '.join(f'{(t[k, j].item() - t0) if t[k, j].item() else 0:15d}' for j in range(7)))
