@@ -133,4 +133,45 @@ __device__ __forceinline__ void dropout4(uint64_t seed, uint64_t offset, uint64_
   m[0] = h ? t[4] : t[0]; m[1] = h ? t[5] : t[1]; m[2] = h ? t[6] : t[2]; m[3] = h ? t[7] : t[3];
 }
 
+// ---- end-of-kernel accumulation of a CTA's partial result into a global fp32 array ----
+// Same-address reductions serialise in L2 (~3.5 cycles each): when all CTAs of a persistent grid finish together and
+// walk the same addresses in the same order, every address sees gridDim.x back-to-back reductions and a scalar,
+// row-strided flush of a few thousand values takes 15-50 us.  The partial is therefore staged in shared memory and
+// flushed with coalesced 16-byte vector reductions, each CTA starting at its own rotation of the array.
+__device__ __forceinline__ void red_add_v4(float* dst, const float4& v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+// dst[r * ld + c] += src[r * src_ld + c] for r < rows, c < cols (cols % 4 == 0, src 16-byte aligned, src_ld % 4 == 0).
+// Called by nthr threads with ids t = 0..nthr-1 after the staging writes were made visible (barrier).
+__device__ __forceinline__ void red_flush_2d(float* dst, int ld, const float* src, int src_ld, int rows, int cols, int t,
+                                             int nthr) {
+  const int c4 = cols >> 2, n4 = rows * c4;
+  const int rot = (int)(((long long)blockIdx.x * n4) / gridDim.x);
+  const bool vec = ((reinterpret_cast<unsigned long long>(dst) & 15ull) == 0) && (ld & 3) == 0;
+  for (int i = t; i < n4; i += nthr) {
+    int k = i + rot;
+    if (k >= n4) k -= n4;
+    const int r = k / c4, c = (k - r * c4) << 2;
+    const float4 v = *reinterpret_cast<const float4*>(src + (size_t)r * src_ld + c);
+    float* d = dst + (size_t)r * ld + c;
+    if (vec) red_add_v4(d, v);
+    else { atomicAdd(d, v.x); atomicAdd(d + 1, v.y); atomicAdd(d + 2, v.z); atomicAdd(d + 3, v.w); }
+  }
+}
+// flat variant for arrays whose length is not a multiple of 4 (dst[i] += src[i], i < n)
+__device__ __forceinline__ void red_flush_1d(float* dst, const float* src, int n, int t, int nthr) {
+  const bool vec = (reinterpret_cast<unsigned long long>(dst) & 15ull) == 0;
+  const int n4 = vec ? (n >> 2) : 0;
+  if (n4 > 0) {
+    const int rot = (int)(((long long)blockIdx.x * n4) / gridDim.x);
+    for (int i = t; i < n4; i += nthr) {
+      int k = i + rot;
+      if (k >= n4) k -= n4;
+      red_add_v4(dst + 4 * k, *reinterpret_cast<const float4*>(src + 4 * k));
+    }
+  }
+  for (int i = (n4 << 2) + t; i < n; i += nthr) atomicAdd(dst + i, src[i]);
+}
+
 }  // namespace gwn

@@ -311,22 +311,6 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
     }
     const float s = warp_column_sums(dbs, lane);
     atomicAdd(p.db_mlp + lane, s);
-    if (warp == 15) {
-      // w15 also flushes quadrant 3 of the dW accumulators at the end
-      mbar_wait(w_full, 0u);
-      tc_fence_after();
-#pragma unroll 1
-      for (int t = 0; t < 2; ++t) {
-        const int m = t * 128 + 96 + lane;
-        float vv[32];
-        tmem_ld32(tmem_base + ((uint32_t)96 << 16) + TW + 32u * t, vv);
-        if (m < NU) {
-          float* dst = p.dw_mlp + (size_t)(m >> 5) * 32 * 32 + (m & 31);
-#pragma unroll
-          for (int c = 0; c < 32; ++c) atomicAdd(dst + c * 32, vv[c]);
-        }
-      }
-    }
   } else if ((quad < 2 && wq < 2) || (quad == 2 && wq == 1)) {
     // ===================== stage warps: TMEM(dU_j) -> bf16 -> slots 1..H =====================
     if (quad < nq_stage) {
@@ -452,7 +436,16 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
         }
       }
     }
-    // dW flush: D_W[(j, c'), c] -> dw_mlp[(j*32 + c), c']
+  }
+  // ===================== gradient flush (w8, w9, w10 and w15: one warp per TMEM lane quadrant) =====================
+  // dW: D_W[(j, c'), c] -> dw_mlp[(j*32 + c), c'];  dA: accumulator row = node v, column = node w.  The CTA's partials
+  // are staged in shared memory (every operand buffer is idle once w_full has fired) and flushed with rotated,
+  // coalesced vector reductions (common.cuh: red_flush_1d) - direct scalar atomics from 148 CTAs finishing together
+  // serialise in L2 and cost tens of microseconds per launch.
+  if ((wq == 2 && quad < 3) || warp == 15) {
+    float* stg_w = reinterpret_cast<float*>(smem + L.cat_off);             // [NU][32]
+    float* stg_a = stg_w + 32 * NU;                                        // [V][V]
+    const int et = quad * 32 + lane;
     mbar_wait(w_full, 0u);
     tc_fence_after();
 #pragma unroll 1
@@ -461,12 +454,13 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
       float vv[32];
       tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + TW + 32u * t, vv);
       if (m < NU) {
-        float* dst = p.dw_mlp + (size_t)(m >> 5) * 32 * 32 + (m & 31);
+        float* dst = stg_w + (size_t)(m >> 5) * 32 * 32 + (m & 31);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) atomicAdd(dst + c * 32, vv[c]);
+        for (int c = 0; c < 32; ++c) dst[c * 32] = vv[c];
       }
     }
-    if (DA) {     // dA flush: accumulator row = node v, column = node w
+    if (DA) {
+      const int w = quad * 32 + lane;
 #pragma unroll 1
       for (int c0 = 0; c0 < Kp; c0 += 16) {
         uint32_t r[16];
@@ -481,10 +475,13 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
         if (w < V) {
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (c0 + j < V) atomicAdd(p.dA + (long long)w * V + c0 + j, __uint_as_float(r[j]));
+            if (c0 + j < V) stg_a[w * V + c0 + j] = __uint_as_float(r[j]);
         }
       }
     }
+    asm volatile("bar.sync 2, 128;" ::: "memory");
+    red_flush_1d(p.dw_mlp, stg_w, 32 * NU, et, 128);
+    if (DA) red_flush_1d(p.dA, stg_a, V * V, et, 128);
   }
   tc_fence_before();
   __syncthreads();

@@ -40,6 +40,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#define WG_MARK(i) do { if (p.trace && blockIdx.x == 0 && tid == (i == 2 || i == 3 ? 32 * (WG_MMA_WARP + 1) : 0)) p.trace[47 * 8 + (i)] = clock64(); } while (0)
+  WG_MARK(0);
   const int mrows = 32 * p.n_chunks;                 // real weight rows; row `mrows` is the ones row
   const int mt = (mrows + 1 + 127) / 128;            // M tiles
   const int N = p.N;
@@ -80,6 +82,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  WG_MARK(1);
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp walks the loop, one elected lane issues) =====================
@@ -143,7 +146,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     if (any) {
       mbar_wait(tfull, 0u);
       tc_fence_after();
-      // pass 1: the ones row -> bias gradient (and into smem for the affine correction)
+      WG_MARK(2);
+      // The CTA's partial dW (and db) is staged in shared memory (the TMA stages are free once tfull has fired) and
+      // flushed with rotated, coalesced vector reductions (red_flush_2d): the direct per-row scalar atomics of 148 CTAs
+      // finishing together serialised in L2 and cost ~17 us per launch.
+      float* stg = reinterpret_cast<float*>(smem);           // [mrows][N + 4] fp32, then [N] for db
+      const int sld = N + 4;
+      const int et = tid - 32 * (WG_MMA_WARP + 1);           // 0..127 among the epilogue threads
+      // pass 1: the ones row -> bias gradient (into smem for the affine correction)
       const int ones_t = mrows / 128, ones_r = mrows % 128;
       if (quad == ones_r / 32) {
         for (int c0 = 0; c0 < N; c0 += 32) {
@@ -151,10 +161,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
           tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ones_t * N + c0), v);
           if (lane == ones_r % 32) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              db_s[c0 + j] = v[j];
-              if (p.db) atomicAdd(p.db + c0 + j, v[j]);
-            }
+            for (int j = 0; j < 32; ++j) db_s[c0 + j] = v[j];
           }
         }
       }
@@ -167,16 +174,24 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
           if (m < mrows) {
             float sc = 1.f, sh = 0.f;
             if (p.scale) { sc = __ldg(p.scale + (m & 31)); sh = __ldg(p.shift + (m & 31)); }
-            float* dst = p.dW + (long long)m * p.ldw + c0;
+            float* dst = stg + (size_t)m * sld + c0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(dst + j, fmaf(sc, v[j], sh * db_s[c0 + j]));
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + j) =
+                  make_float4(fmaf(sc, v[j], sh * db_s[c0 + j]), fmaf(sc, v[j + 1], sh * db_s[c0 + j + 1]),
+                              fmaf(sc, v[j + 2], sh * db_s[c0 + j + 2]), fmaf(sc, v[j + 3], sh * db_s[c0 + j + 3]));
           }
         }
       }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      red_flush_2d(p.dW, p.ldw, stg, sld, mrows, N, et, 128);
+      if (p.db) red_flush_1d(p.db, db_s, N, et, 128);
+      WG_MARK(3);
     }
   }
   tc_fence_before();
   __syncthreads();
+  WG_MARK(4);
   if (warp == WG_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
