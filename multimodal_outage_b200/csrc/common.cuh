@@ -69,6 +69,24 @@ __device__ __forceinline__ void store4(bf16* p, const float v[4]) {
   t.y = *reinterpret_cast<uint32_t*>(&b);
   *reinterpret_cast<uint2*>(p) = t;
 }
+// 8 channels: 32 B fp32 (two 16-byte accesses) / one 16-byte access bf16
+__device__ __forceinline__ void load8(const float* p, float v[8]) { load4(p, v); load4(p + 4, v + 4); }
+__device__ __forceinline__ void load8(const bf16* p, float v[8]) {
+  const uint4 t = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
+}
+__device__ __forceinline__ void store8(float* p, const float v[8]) { store4(p, v); store4(p + 4, v + 4); }
+__device__ __forceinline__ void store8(bf16* p, const float v[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
 __device__ __forceinline__ void load2(const float* p, float v[2]) {
   float2 t = *reinterpret_cast<const float2*>(p);
   v[0] = t.x; v[1] = t.y;
@@ -99,13 +117,15 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// ---- Philox4x32-10 (counter-based RNG for the fused dropout mask) ----
+// ---- Philox4x32-7 (counter-based RNG for the fused dropout mask) ----
+// Seven rounds (the minimum Salmon et al. report as passing BigCrush; the mask generator is the largest single item in
+// the SIMT budget of the fused diffusion kernels, and every round is 4 multiplies on a serial chain).
 __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t offset, uint64_t counter) {
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   uint32_t c0 = (uint32_t)counter, c1 = (uint32_t)(counter >> 32);
   uint32_t c2 = (uint32_t)offset, c3 = (uint32_t)(offset >> 32);
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < 7; ++r) {
     uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
     uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
@@ -114,16 +134,31 @@ __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t offset, uint
   }
   return make_uint4(c0, c1, c2, c3);
 }
-// Dropout keep-mask (scaled by 1/(1-p)) for 8 consecutive channels: element e = row*32 + col -> group idx8 = e/8.
-// One Philox call yields eight 16-bit uniforms; an element is dropped when its uniform < round(p * 2^16).
+// Dropout keep-mask for 16 consecutive channels: element e = row*32 + col -> group idx16 = e/16 (= row*2 + col/16).
+// One Philox call yields sixteen 8-bit uniforms; an element is dropped when its uniform < thr = round(p * 256), and
+// kept elements are scaled by 256 / (256 - thr): the mask is exactly unbiased for the drop rate thr/256 it realises
+// (p = 0.3 -> 77/256 = 0.3008).
+__device__ __forceinline__ void dropout16(uint64_t seed, uint64_t offset, uint64_t idx16, float p, float m[16]) {
+  const uint4 r = philox4x32(seed, offset, idx16);
+  uint32_t thr = (uint32_t)(p * 256.0f + 0.5f);
+  thr = thr > 255u ? 255u : thr;
+  const float inv = 256.0f / (256.0f - (float)thr);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m[4 * i] = ((w[i] & 0xFFu) >= thr) ? inv : 0.f;
+    m[4 * i + 1] = (((w[i] >> 8) & 0xFFu) >= thr) ? inv : 0.f;
+    m[4 * i + 2] = (((w[i] >> 16) & 0xFFu) >= thr) ? inv : 0.f;
+    m[4 * i + 3] = ((w[i] >> 24) >= thr) ? inv : 0.f;
+  }
+}
+// the 8 channels of group idx8 = e/8 out of the same stream
 __device__ __forceinline__ void dropout8(uint64_t seed, uint64_t offset, uint64_t idx8, float p, float m[8]) {
-  const uint4 r = philox4x32(seed, offset, idx8);
-  const float inv = 1.0f / (1.0f - p);
-  const uint32_t thr = (uint32_t)(p * 65536.0f + 0.5f);
-  m[0] = ((r.x & 0xFFFFu) >= thr) ? inv : 0.f;  m[1] = ((r.x >> 16) >= thr) ? inv : 0.f;
-  m[2] = ((r.y & 0xFFFFu) >= thr) ? inv : 0.f;  m[3] = ((r.y >> 16) >= thr) ? inv : 0.f;
-  m[4] = ((r.z & 0xFFFFu) >= thr) ? inv : 0.f;  m[5] = ((r.z >> 16) >= thr) ? inv : 0.f;
-  m[6] = ((r.w & 0xFFFFu) >= thr) ? inv : 0.f;  m[7] = ((r.w >> 16) >= thr) ? inv : 0.f;
+  float t[16];
+  dropout16(seed, offset, idx8 >> 1, p, t);
+  const bool h = (idx8 & 1) != 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = h ? t[8 + i] : t[i];
 }
 // the 4 channels [col, col+4) of row `row` (col % 4 == 0) out of the same stream
 __device__ __forceinline__ void dropout4(uint64_t seed, uint64_t offset, uint64_t row, int col, float p, float m[4]) {

@@ -39,7 +39,7 @@ __host__ __device__ inline GfLayout gf_layout(int Kp, int n_mats) {
   L.u_slot = 4u * (uint32_t)Kp * 16u;                          // [4 cg][Kp nodes][16 B]
   L.u_stage = (uint32_t)n_mats * L.u_slot;
   L.bar_off = (L.u_off + GF_UST * L.u_stage + 2048u + 127u) & ~127u;   // 2 KB slack: M=128 operand rows past Kp
-  L.total = L.bar_off + 256u + 384u;                           // barriers + {bias, scale, shift}
+  L.total = L.bar_off + 256u + 640u;                           // barriers + {bias, scale, shift} + statistics scratch
   return L;
 }
 
@@ -77,6 +77,8 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gcn_fwd_kernel(const __grid_con
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#define GF_MARK(i) do { if (p.trace && blockIdx.x == 0 && tid == 0) p.trace[63 * 8 + (i)] = clock64(); } while (0)
+  GF_MARK(0);
   constexpr int Kp = 16 * KSTEPS, nm = NM, NU = 32 * (1 + NM);
   const int V = p.V;
   const GfLayout L = gf_layout(Kp, nm);
@@ -120,6 +122,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gcn_fwd_kernel(const __grid_con
     const uint4* wsrc = reinterpret_cast<const uint4*>(p.w_img);
     uint4* wdst = reinterpret_cast<uint4*>(smem + L.w_off);
     for (int i = tid; i < (int)(L.w_bytes / 16); i += GF_THREADS) wdst[i] = __ldg(wsrc + i);
+    if (tid >= 64 && tid < 128) cst[96 + tid - 64] = 0.f;     // CTA-level (sum, sum^2) scratch
     if (tid < 32) {
       cst[tid] = __ldg(p.bias + tid);
       cst[32 + tid] = p.scale ? __ldg(p.scale + tid) : 1.f;
@@ -133,6 +136,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gcn_fwd_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t sbase = smem_u32(smem);
   const int quad = warp & 3, wq = warp >> 2;      // quadrant and index of this warp inside its quadrant
+  GF_MARK(1);
 
   if (warp == GF_PRODUCER) {
     // ===================== producer =====================
@@ -303,16 +307,25 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gcn_fwd_kernel(const __grid_con
         mbar_arrive(&ht_empty[hb]);
         if (valid) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float m[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f}, r[8];
-            if (p.mask) unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.mask + pp * 32) + j), m);
-            else if (philox) dropout8(sd, of, (uint64_t)(pp * 4 + j), p.drop_p, m);
-            unpack_bf16x8(rr[j], r);
-            const float4 s0 = sc4[2 * j], s1 = sc4[2 * j + 1], t0 = sh4[2 * j], t1 = sh4[2 * j + 1];
-            const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-            const float sh[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+          for (int jj = 0; jj < 2; ++jj) {
+            float m16[16];
+            if (philox) dropout16(sd, of, (uint64_t)(pp * 2 + jj), p.drop_p, m16);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) h[8 * j + i] = fmaf(h[8 * j + i], m[i], fmaf(r[i], sc[i], sh[i]));
+            for (int jh = 0; jh < 2; ++jh) {
+              const int j = 2 * jj + jh;
+              float m[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f}, r[8];
+              if (p.mask) unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.mask + pp * 32) + j), m);
+              else if (philox) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) m[i] = m16[8 * jh + i];
+              }
+              unpack_bf16x8(rr[j], r);
+              const float4 s0 = sc4[2 * j], s1 = sc4[2 * j + 1], t0 = sh4[2 * j], t1 = sh4[2 * j + 1];
+              const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+              const float sh[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) h[8 * j + i] = fmaf(h[8 * j + i], m[i], fmaf(r[i], sc[i], sh[i]));
+            }
           }
           bf16* up = p.u + pp * 32;
 #pragma unroll
@@ -329,12 +342,17 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gcn_fwd_kernel(const __grid_con
       }
       const float s1 = warp_column_sums(sa, lane);
       const float s2 = warp_column_sums(sb, lane);
-      atomicAdd(p.stats + lane, (double)s1);
-      atomicAdd(p.stats + 32 + lane, (double)s2);
+      atomicAdd(cst + 96 + lane, s1);            // CTA-level pre-reduction: one global atomic per statistic per CTA
+      atomicAdd(cst + 128 + lane, s2);
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (warp == 0) {
+    atomicAdd(p.stats + lane, (double)cst[96 + lane]);
+    atomicAdd(p.stats + 32 + lane, (double)cst[128 + lane]);
+  }
+  GF_MARK(2);
   if (warp == GF_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);

@@ -68,6 +68,8 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#define GB_MARK(i) do { if (p.trace && blockIdx.x == 0 && tid == 0) p.trace[63 * 8 + (i)] = clock64(); } while (0)
+  GB_MARK(0);
   constexpr int Kp = 16 * KSTEPS, NU = 32 * (1 + NM);
   const int V = p.V;
   const GbLayout L = gb_layout(Kp, NM, DA);
@@ -135,6 +137,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t sbase = smem_u32(smem);
   const int quad = warp & 3, wq = warp >> 2;
+  GB_MARK(1);
   constexpr uint32_t TZ = 192u, TW = 224u;      // TMEM columns of dz and dW
   constexpr uint32_t TU5 = 288u, TU6 = 320u, TDA = 352u;   // dA: U5 -> T1, U6, dA accumulator (Kp columns)
 
@@ -284,12 +287,17 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
         uint4 qd[4], qa[4], qb[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) { qd[j] = __ldg(s0 + j); qa[j] = __ldg(s1 + j); qb[j] = __ldg(s2 + j); }
+        float m16[16];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float d[8], m[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f}, av[8], bv[8];
           gb_unpack8(qd[j], d); gb_unpack8(qa[j], av); gb_unpack8(qb[j], bv);
           if (p.mask) gb_unpack8(__ldg(reinterpret_cast<const uint4*>(p.mask + pp * 32) + j), m);
-          else if (philox) dropout8(sd, of, (uint64_t)(pp * 4 + j), p.drop_p, m);
+          else if (philox) {
+            if ((j & 1) == 0) dropout16(sd, of, (uint64_t)(pp * 2 + (j >> 1)), p.drop_p, m16);   // one call per 16 channels
+#pragma unroll
+            for (int i = 0; i < 8; ++i) m[i] = m16[8 * (j & 1) + i];
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) { d[i] *= m[i]; dbs[8 * j + i] += d[i]; av[i] *= bv[i]; }
           od[j] = make_uint4(gb_pack(d[0], d[1]), gb_pack(d[2], d[3]), gb_pack(d[4], d[5]), gb_pack(d[6], d[7]));
@@ -485,6 +493,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  GB_MARK(2);
   if (warp == GB_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);

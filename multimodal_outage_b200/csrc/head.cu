@@ -129,69 +129,108 @@ __global__ void __launch_bounds__(256) start_bwd_x_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------ start conv, narrow input
-// Cin <= 8 (config 1-3, 5: in_dim = 2): the contraction is a handful of FMAs per output, so one warp handles one
-// position with lane = output channel; the Cin inputs of a position are uniform (broadcast) loads.
+// Cin <= 8 (config 1-3, 5: in_dim = 2): the contraction is a handful of FMAs per output.  A thread produces 8 output
+// channels of one position (one 16-byte bf16 / two 16-byte fp32 stores): four lanes per position, 8 positions per
+// warp instruction; the Cin inputs of a position are the same address for its four lanes.
 template <typename T, int CIN>
 __global__ void __launch_bounds__(256) start_fwd_small_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                               const float* __restrict__ b, T* __restrict__ u0, int N,
                                                               int V, int Tn, int L0) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float wr[CIN];
+  const int cg = threadIdx.x & 3;                           // channels [8 cg, 8 cg + 8)
+  float wr[8][CIN], bias[8];
 #pragma unroll
-  for (int i = 0; i < CIN; ++i) wr[i] = w[lane * CIN + i];
-  const float bias = b[lane];
+  for (int c = 0; c < 8; ++c) {
+    bias[c] = b[8 * cg + c];
+#pragma unroll
+    for (int i = 0; i < CIN; ++i) wr[c][i] = w[(8 * cg + c) * CIN + i];
+  }
   const int pad = L0 - Tn;
-  const long long P = (long long)N * L0 * V;
-  for (uint32_t p = blockIdx.x * 8u + warp; p < (uint32_t)P; p += gridDim.x * 8u) {     // launcher: P < 2^31
+  const uint32_t P = (uint32_t)((long long)N * L0 * V);     // launcher: P < 2^31
+  const uint32_t stride = gridDim.x * 64u;
+  for (uint32_t p = blockIdx.x * 64u + (threadIdx.x >> 2); p < P; p += stride) {
     const uint32_t r = p / (uint32_t)V;
     const int v = (int)(p - r * (uint32_t)V);
-    const long long n = r / (uint32_t)L0;
-    const int l = (int)(r - (uint32_t)n * (uint32_t)L0);
-    float acc = bias;
-    if (l >= pad) {
-      const float* xr = x + ((n * CIN) * V + v) * (long long)Tn + (l - pad);
+    const uint32_t n = r / (uint32_t)L0;
+    const int l = (int)(r - n * (uint32_t)L0);
+    float acc[8];
 #pragma unroll
-      for (int i = 0; i < CIN; ++i) acc = fmaf(wr[i], __ldg(xr + (long long)i * V * Tn), acc);
+    for (int c = 0; c < 8; ++c) acc[c] = bias[c];
+    if (l >= pad) {
+      const float* xr = x + (((long long)n * CIN) * V + v) * (long long)Tn + (l - pad);
+#pragma unroll
+      for (int i = 0; i < CIN; ++i) {
+        const float xv = __ldg(xr + (long long)i * V * Tn);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = fmaf(wr[c][i], xv, acc[c]);
+      }
     }
-    st1(u0 + (size_t)p * 32 + lane, acc);
+    store8(u0 + (size_t)p * 32 + 8 * cg, acc);
   }
 }
 
-// dw[c][ci] += sum_p du[p][c] x[p][ci], db[c] += sum_p du[p][c]: lane = c, per-lane accumulators, one reduction at the end
+// dw[c][ci] += sum_p du[p][c] x[p][ci], db[c] += sum_p du[p][c].  A thread owns 8 channels (one 16/32-byte load per
+// position) of every fourth-lane-group position: 8 positions per warp instruction instead of one, the index split
+// amortised over 8 channels; per-thread accumulators, one shuffle + shared-memory reduction at the end.
 template <typename T, int CIN>
 __global__ void __launch_bounds__(256) start_bwd_w_small_kernel(const float* __restrict__ x, const T* __restrict__ du,
                                                                 float* __restrict__ dw, float* __restrict__ db, int N,
                                                                 int V, int Tn, int L0) {
-  __shared__ float red[8][32][CIN + 1];
+  constexpr int NA = 8 * (CIN + 1);
+  __shared__ float red[8][4][NA];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cg = lane & 3;                                  // channels [8 cg, 8 cg + 8)
   const int pad = L0 - Tn;
-  const long long P = (long long)N * L0 * V;
-  float acc[CIN], bacc = 0.f;
+  const uint32_t P = (uint32_t)((long long)N * L0 * V);     // launcher: P < 2^31
+  float acc[CIN + 1][8];
 #pragma unroll
-  for (int i = 0; i < CIN; ++i) acc[i] = 0.f;
-  for (uint32_t p = blockIdx.x * 8u + warp; p < (uint32_t)P; p += gridDim.x * 8u) {     // launcher: P < 2^31
+  for (int i = 0; i <= CIN; ++i)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
+  const uint32_t stride = gridDim.x * 64u;
+  for (uint32_t p = blockIdx.x * 64u + (threadIdx.x >> 2); p < P; p += stride) {
     const uint32_t r = p / (uint32_t)V;
     const int v = (int)(p - r * (uint32_t)V);
-    const long long n = r / (uint32_t)L0;
-    const int l = (int)(r - (uint32_t)n * (uint32_t)L0);
-    const float g = ld1(du + (size_t)p * 32 + lane);
-    bacc += g;
-    if (l >= pad) {
-      const float* xr = x + ((n * CIN) * V + v) * (long long)Tn + (l - pad);
+    const uint32_t n = r / (uint32_t)L0;
+    const int l = (int)(r - n * (uint32_t)L0);
+    float g[8];
+    load8(du + (size_t)p * 32 + 8 * cg, g);
 #pragma unroll
-      for (int i = 0; i < CIN; ++i) acc[i] = fmaf(g, __ldg(xr + (long long)i * V * Tn), acc[i]);
+    for (int c = 0; c < 8; ++c) acc[CIN][c] += g[c];
+    if (l >= pad) {
+      const float* xr = x + (((long long)n * CIN) * V + v) * (long long)Tn + (l - pad);
+#pragma unroll
+      for (int i = 0; i < CIN; ++i) {
+        const float xv = __ldg(xr + (long long)i * V * Tn);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[i][c] = fmaf(g[c], xv, acc[i][c]);
+      }
     }
   }
+  // lanes with the same channel group: xor 4, 8, 16
 #pragma unroll
-  for (int i = 0; i < CIN; ++i) red[warp][lane][i] = acc[i];
-  red[warp][lane][CIN] = bacc;
+  for (int i = 0; i <= CIN; ++i)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float t = acc[i][c];
+      t += __shfl_xor_sync(0xffffffffu, t, 4);
+      t += __shfl_xor_sync(0xffffffffu, t, 8);
+      t += __shfl_xor_sync(0xffffffffu, t, 16);
+      acc[i][c] = t;
+    }
+  if (lane < 4) {
+#pragma unroll
+    for (int i = 0; i <= CIN; ++i)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) red[warp][lane][i * 8 + c] = acc[i][c];
+  }
   __syncthreads();
-  for (int i = threadIdx.x; i < 32 * (CIN + 1); i += 256) {
-    const int c = i / (CIN + 1), k = i % (CIN + 1);
+  for (int t = threadIdx.x; t < 4 * NA; t += 256) {
+    const int g4 = t / NA, k = t % NA;                      // channel group, (i, c)
+    const int i = k >> 3, c = 8 * g4 + (k & 7);
     float s = 0.f;
 #pragma unroll
-    for (int wq = 0; wq < 8; ++wq) s += red[wq][c][k];
-    if (k < CIN) atomicAdd(dw + c * CIN + k, s); else atomicAdd(db + c, s);
+    for (int wq = 0; wq < 8; ++wq) s += red[wq][g4][k];
+    if (i < CIN) atomicAdd(dw + c * CIN + i, s); else atomicAdd(db + c, s);
   }
 }
 

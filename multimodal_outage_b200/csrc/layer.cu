@@ -142,7 +142,8 @@ struct EpiGateTC {   // N = 64 interleaved (f,g); a chunk of 32 columns = 16 cha
     if (a) { store_bf16x16(a + p * 32 + ch0, aa); store_bf16x16(b + p * 32 + ch0, bb); }
     if (z_last && rem >= last_begin) store_bf16x16(z_last + (n * last_rows + rem - last_begin) * 32 + ch0, zz);
   }
-  __device__ __forceinline__ void finish() {}
+  __device__ __forceinline__ void finish(float*) {}
+  __device__ __forceinline__ void flush(const float*, int) {}
 };
 
 struct EpiMlpTC {    // N = 32: (bias in the GEMM) dropout + residual(BN-folded input) -> u, per-channel (sum, sum^2)
@@ -159,11 +160,19 @@ struct EpiMlpTC {    // N = 32: (bias in the GEMM) dropout + residual(BN-folded 
       const bf16* rp = u_prev + (n * prev_rows_per_n + rem + crop) * 32;
       uint64_t sd = 0, of = 0;
       if (!mask && drop_p > 0.f) { sd = rng ? __ldg(rng) : seed; of = rng ? offset + __ldg(rng + 1) : offset; }
+      float m32[32];
+      if (!mask && drop_p > 0.f) {
+        dropout16(sd, of, (uint64_t)(p * 2), drop_p, m32);
+        dropout16(sd, of, (uint64_t)(p * 2 + 1), drop_p, m32 + 16);
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float m[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f}, r[8];
         if (mask) { load4(mask + p * 32 + 8 * j, m); load4(mask + p * 32 + 8 * j + 4, m + 4); }
-        else if (drop_p > 0.f) dropout8(sd, of, (uint64_t)(p * 4 + j), drop_p, m);
+        else if (drop_p > 0.f) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) m[i] = m32[8 * j + i];
+        }
         load4(rp + 8 * j, r); load4(rp + 8 * j + 4, r + 4);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -186,10 +195,14 @@ struct EpiMlpTC {    // N = 32: (bias in the GEMM) dropout + residual(BN-folded 
     for (int c = 0; c < 32; ++c) t[c] = h[c] * h[c];
     s2 += warp_column_sums(t, lane);
   }
-  __device__ __forceinline__ void finish() {
+  __device__ __forceinline__ void finish(float* red_s) {
     const int lane = threadIdx.x & 31;
-    atomicAdd(stats + lane, (double)s1);
-    atomicAdd(stats + 32 + lane, (double)s2);
+    atomicAdd(red_s + lane, s1);
+    atomicAdd(red_s + 32 + lane, s2);
+  }
+  __device__ __forceinline__ void flush(const float* red_s, int lane) {
+    atomicAdd(stats + lane, (double)red_s[lane]);
+    atomicAdd(stats + 32 + lane, (double)red_s[32 + lane]);
   }
 };
 
@@ -203,7 +216,8 @@ struct EpiSlotTC {   // 32-column chunk c0 -> slot c0/32 of a slot-major buffer
     store_bf16x16(dst, v);
     store_bf16x16(dst + 16, v + 16);
   }
-  __device__ __forceinline__ void finish() {}
+  __device__ __forceinline__ void finish(float*) {}
+  __device__ __forceinline__ void flush(const float*, int) {}
 };
 
 struct EpiGateBwdTC {   // N = 32: dx = acc + du(cropped rows); (sum dx, sum dx*u_prev)
@@ -251,15 +265,19 @@ struct EpiGateBwdTC {   // N = 32: dx = acc + du(cropped rows); (sum dx, sum dx*
       s2[h] += warp_column_sums16(up, lane);
     }
   }
-  __device__ __forceinline__ void finish() {
+  __device__ __forceinline__ void finish(float* red_s) {
     const int lane = threadIdx.x & 31;
     if ((lane & 1) == 0) {                         // lanes 2c, 2c+1 both hold column c of each half
       const int c = lane >> 1;
-      atomicAdd(stats + c, (double)s1[0]);
-      atomicAdd(stats + 16 + c, (double)s1[1]);
-      atomicAdd(stats + 32 + c, (double)s2[0]);
-      atomicAdd(stats + 48 + c, (double)s2[1]);
+      atomicAdd(red_s + c, s1[0]);
+      atomicAdd(red_s + 16 + c, s1[1]);
+      atomicAdd(red_s + 32 + c, s2[0]);
+      atomicAdd(red_s + 48 + c, s2[1]);
     }
+  }
+  __device__ __forceinline__ void flush(const float* red_s, int lane) {
+    atomicAdd(stats + lane, (double)red_s[lane]);
+    atomicAdd(stats + 32 + lane, (double)red_s[32 + lane]);
   }
 };
 

@@ -4,7 +4,10 @@
 //   __device__ void chunk(long long p, long long n, long long rem, bool valid, int c0, float v[32]);
 //        32 consecutive output columns [c0, c0+32) of row p (valid == p < P); called by every lane so the
 //        functor may use warp collectives (the BN-statistics reduction does).
-//   __device__ void finish();     called once per epilogue warp after its last tile (flush statistics)
+//   __device__ void finish(float* red_s);   called once per epilogue warp after its last tile: add the warp's statistics
+//        into the CTA's 64-float shared scratch (zeroed by the kernel)
+//   __device__ void flush(const float* red_s, int lane);   called by ONE warp after the CTA-wide barrier: one global
+//        atomic per statistic per CTA (per-warp global atomics put 16 x 148 serialised updates on each address)
 #pragma once
 #include <cstdlib>
 
@@ -106,7 +109,9 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
   uint64_t* tfull = bars + 16;         // [n_acc] (<= 4)
   uint64_t* tempty = bars + 20;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  float* red_s = reinterpret_cast<float*>(bars + 32);        // [64] CTA-level statistics scratch
   (void)a_s;
+  if (tid < 64) red_s[tid] = 0.f;
 
   if (tid == 0) {
     // a stage is free when the MMAs have read it and (with extras) every epilogue thread is done with it
@@ -259,10 +264,11 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
       w.advance();
       if (++stage == stages) stage = 0;
     }
-    epi.finish();
+    epi.finish(red_s);
   }
   tc_fence_before();
   __syncthreads();
+  if (warp == 0) epi.flush(red_s, lane);
   if (warp == PGT_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)n_acc * buf_cols);
@@ -301,7 +307,7 @@ int launch_pos_gemm_tc(PgParams& p, const Epi& epi, cudaStream_t st) {
   const int sms = tg_sm_count();
   const int acc_c = p.N <= 32 ? 32 : p.N <= 64 ? 64 : p.N <= 128 ? 128 : 256;
   const size_t w_bytes = ((size_t)(p.n_chunks * 4 + (p.has_bias ? 2 : 0)) * p.N * 16 + 1023) & ~(size_t)1023;
-  const size_t fixed = w_bytes + PGT_ONES_BYTES + 1024 + 256;
+  const size_t fixed = w_bytes + PGT_ONES_BYTES + 1024 + 512;
   GWN_REQUIRE(fixed + 2 * (size_t)NB * 8192 <= 227 * 1024, "pos_gemm_tc: K=%d does not fit 2 stages in shared memory",
               32 * p.n_chunks);
   p.tiles_per_n = (int)cdiv(p.rows_out, 128);                     // 128-row sub-tiles per (virtual) sample

@@ -7,7 +7,8 @@ trace = torch.zeros(64 * 8, device=dev, dtype=torch.int64)
 os.environ['GWN_GCN_TRACE'] = str(trace.data_ptr())
 from multimodal_outage_b200 import ops
 bf = torch.bfloat16
-V, N, Lin, dil = 67, 512, 13, 1
+V, N, dil = 67, 512, 1
+Lin = int(sys.argv[1]) if len(sys.argv) > 1 else 13
 sups = [torch.softmax(torch.randn(V, V, device=dev), dim=1) for _ in range(3)]
 sups[-1].requires_grad_(True)
 mats = ops.hop_mats([s.detach() for s in sups])
@@ -21,7 +22,10 @@ torch.autograd.backward([u, zl], [torch.randn_like(u), torch.randn_like(zl)])
 torch.cuda.synchronize()
 t = trace.cpu().reshape(64, 8)
 t0 = t[0, 0].item()
+print('marks relative to kernel begin: after_prologue, kernel_end, first got_in_full:', [t[63, i].item() - t[63, 0].item() for i in (1, 2)], t0 - t[63, 0].item())
 names = ['got_in_full', 'got_ut_empty', 'hops_issued', 'Y1_issued', 'tail:got_us_full', 'tail:ZW_issued', 'iter_end']
 print('slab ' + ' '.join(f'{n:>17s}' for n in names))
-for k in range(8, 24):
+for k in range(0, 24):
+    if t[k, 0].item() == 0:
+        break
     print(f'{k:4d} ' + ' '.join(f'{(t[k, j].item() - t0) if t[k, j].item() else 0:17d}' for j in range(7)))

@@ -8,7 +8,9 @@ os.environ['GWN_GCN_TRACE'] = str(trace.data_ptr())
 from multimodal_outage_b200 import ops, _lib
 lib = _lib.lib(); bf = torch.bfloat16
 st = lambda: torch.cuda.current_stream().cuda_stream
-V, N, Lin, Lout = 67, 512, 13, 12
+V, N = 67, 512
+Lout = int(sys.argv[1]) if len(sys.argv) > 1 else 12
+Lin = Lout + 1
 sups = [torch.softmax(torch.randn(V, V, device=dev), dim=1) for _ in range(3)]
 mats = ops.hop_mats(sups)
 z = torch.randn(N, Lout, V, 32, device=dev).to(bf); up = torch.randn(N, Lin, V, 32, device=dev).to(bf)
@@ -22,7 +24,10 @@ for it in range(2):
     torch.cuda.synchronize()
 t = trace.cpu().reshape(64, 8)
 t0 = t[0, 1].item()
+print('marks relative to kernel begin: after_prologue, kernel_end, first mma_U_start:', [t[63, i].item() - t[63, 0].item() for i in (1, 2)], t0 - t[63, 0].item())
 names = ['prod_issued', 'mma_U_start', 'mma_U_issued', 'mma_hops_issued', 'stage_start', 'stage_end', 'epi_start', 'epi_end']
 print('slab ' + ' '.join(f'{n:>15s}' for n in names))
 for k in range(0, 42):
+    if t[k, 1].item() == 0:
+        break
     print(f'{k:4d} ' + ' '.join(f'{(t[k, j].item() - t0) if t[k, j].item() else 0:15d}' for j in range(8)))
