@@ -261,6 +261,32 @@ int gwn_dadj_big(const void* x, const void* g, float* dA, long long slabs, int V
 int gwn_gemm_test(const void* A, const void* B, float* C, int M, int N, int K, int a_mode, int b_mode,
                   int lda, int ldb, int bn, int splits, void* stream);
 
+/* ---- parameter re-layout (one launch instead of ~50 stack/permute/copy launches per step) ----
+ * gwn_pack_params gathers the reference-shaped parameters (graph_wavenet.py:150-183: Conv2d weights [out,in,1,k] and
+ * biases, fp32) into one flat fp32 buffer holding the kernels' packed layouts back to back (segment offsets from
+ * gwn_pack_offsets: w_fg [nl][k*32][64] | b_fg [nl][64] | w_mlp [nl][mlp_in][32] | w_skip [nl*32][S] | b_skip [S] |
+ * w_end1 [S][E] | w_end2 [E][Opad] | b_end2 [Opad]).  gwn_unpack_grads scatters the gradients of those packed tensors
+ * (NULL = absent) back into one flat buffer in parameter order (per layer: dWf, dbf, dWg, dbg, dWm, dWs, dbs; then
+ * dW_end1, dW_end2, db_end2).  Pointer tables are passed by value (no device-side table). */
+typedef struct {
+  int n_layers, taps, mlp_in, S, E, O, Opad;
+} gwn_pack_cfg;
+typedef struct {
+  const void* w_filter[GWN_MAX_LAYERS]; const void* b_filter[GWN_MAX_LAYERS];
+  const void* w_gate[GWN_MAX_LAYERS];   const void* b_gate[GWN_MAX_LAYERS];
+  const void* w_mlp[GWN_MAX_LAYERS];    /* gconv.mlp.mlp.weight [32][mlp_in] (or residual_convs weight) */
+  const void* w_skip[GWN_MAX_LAYERS];   const void* b_skip[GWN_MAX_LAYERS];
+  const void* w_end1; const void* w_end2; const void* b_end2;
+} gwn_pack_ptrs;
+typedef struct {
+  const void* w_fg[GWN_MAX_LAYERS]; const void* b_fg[GWN_MAX_LAYERS]; const void* w_mlp[GWN_MAX_LAYERS];
+  const void* w_skip; const void* b_skip; const void* w_end1; const void* w_end2; const void* b_end2;
+} gwn_unpack_ptrs;
+long long gwn_pack_offsets(const gwn_pack_cfg* cfg, long long* off9);   /* returns the total element count */
+int gwn_pack_params(const gwn_pack_cfg* cfg, const gwn_pack_ptrs* ptrs, float* out, void* stream);
+long long gwn_unpack_total(const gwn_pack_cfg* cfg);
+int gwn_unpack_grads(const gwn_pack_cfg* cfg, const gwn_unpack_ptrs* grads, float* out, void* stream);
+
 /* ---- nconv primitive, exposed for unit tests  graph_wavenet.py:60-66 ----
  * y[s,w,c] = sum_v x[s,v,c] * A[v,w] (transpose_a=0) or A[w,v] (transpose_a=1);
  * x,y: [slabs, V, pitch] slots of 32 channels at column offsets xoff/yoff. */

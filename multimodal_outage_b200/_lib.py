@@ -68,6 +68,20 @@ class HeadTcBwdArgs(C.Structure):
                [('outputs_zeroed', C.c_int)]
 
 
+class PackCfg(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ('n_layers', 'taps', 'mlp_in', 'S', 'E', 'O', 'Opad')]
+
+
+class PackPtrs(C.Structure):
+    _fields_ = [(n, vp * MAX_LAYERS) for n in ('w_filter', 'b_filter', 'w_gate', 'b_gate', 'w_mlp', 'w_skip', 'b_skip')] + \
+               [(n, vp) for n in ('w_end1', 'w_end2', 'b_end2')]
+
+
+class UnpackPtrs(C.Structure):
+    _fields_ = [(n, vp * MAX_LAYERS) for n in ('w_fg', 'b_fg', 'w_mlp')] + \
+               [(n, vp) for n in ('w_skip', 'b_skip', 'w_end1', 'w_end2', 'b_end2')]
+
+
 # every symbol include/gwn.h declares: name -> (restype, argtypes)
 _i, _ll, _f, _d = C.c_int, C.c_longlong, C.c_float, C.c_double
 SIGNATURES = {
@@ -101,6 +115,10 @@ SIGNATURES = {
     'gwn_hop_big': (_i, [vp, _i, _i, _i, vp, vp, vp, _ll, _i, vp]),
     'gwn_dadj_big': (_i, [vp, vp, vp, _ll, _i, vp]),
     'gwn_gemm_test': (_i, [vp, vp, vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, vp]),
+    'gwn_pack_offsets': (_ll, [C.POINTER(PackCfg), C.POINTER(_ll)]),
+    'gwn_pack_params': (_i, [C.POINTER(PackCfg), C.POINTER(PackPtrs), vp, vp]),
+    'gwn_unpack_total': (_ll, [C.POINTER(PackCfg)]),
+    'gwn_unpack_grads': (_i, [C.POINTER(PackCfg), C.POINTER(UnpackPtrs), vp, vp]),
     'gwn_node_mix': (_i, [vp, _i, _i, vp, _i, _i, _i, vp, _i, _i, _i, _i, vp]),
     'gwn_comm_unique_id': (_i, [vp]),
     'gwn_comm_init': (_i, [vp, _i, _i]),

@@ -59,71 +59,68 @@ class gcn(nn.Module):
 
 
 class _PackParams(torch.autograd.Function):
-    """Re-lays the reference-shaped parameters into the kernels' packed layouts (and un-packs the
-    gradients): a handful of batched copies per step instead of per-layer glue.
+    """Re-lays the reference-shaped parameters into the kernels' packed layouts (and scatters the gradients back):
+    ONE gather launch forward and ONE scatter launch backward (`gwn_pack_params` / `gwn_unpack_grads`, csrc/pack.cu).
 
     inputs : Wf[nl], bf[nl], Wg[nl], bg[nl], Wm[nl], bm[nl], Ws[nl], bs[nl], W1, b1, W2, b2  (flat list)
     outputs: w_fg[nl] ([k*32, 64]), b_fg[nl] ([64]), w_mlp[nl] ([mlp_in, 32]), w_skip [32*nl, S],
-             b_skip [S], w_end1 [S, E], w_end2 [E, Opad], b_end2 [Opad]
+             b_skip [S], w_end1 [S, E], w_end2 [E, Opad], b_end2 [Opad]   (views of one flat buffer)
     """
 
     @staticmethod
     def forward(ctx, nl, *p):
         Wf, bf, Wg, bg, Wm, bm, Ws, bs = (p[i * nl:(i + 1) * nl] for i in range(8))
         W1, b1, W2, b2 = p[8 * nl:]
-        k = Wf[0].shape[3]
-        wf = torch.stack(Wf)[:, :, :, 0, :]                                    # [nl, o, c, k]
-        wg = torch.stack(Wg)[:, :, :, 0, :]
-        w_fg = torch.stack([wf, wg], dim=2).permute(0, 4, 3, 1, 2).reshape(nl, k * CH, 2 * CH).contiguous()
-        b_fg = torch.stack([torch.stack(bf), torch.stack(bg)], dim=2).reshape(nl, 2 * CH).contiguous()
-        w_mlp = torch.stack(Wm)[:, :, :, 0, 0].transpose(1, 2).contiguous()     # [nl, mlp_in, 32]
-        ws = torch.stack(Ws)[:, :, :, 0, 0]                                     # [nl, S, 32]
-        S = ws.shape[1]
-        w_skip = ws.permute(0, 2, 1).reshape(nl * CH, S).contiguous()
-        b_skip = torch.stack(bs).sum(0)
-        w_end1 = W1[:, :, 0, 0].t().contiguous()                                # [S, E]
+        k, mlp_in, S = Wf[0].shape[3], Wm[0].shape[1], Ws[0].shape[0]
         O, E = W2.shape[0], W2.shape[1]
         Opad = CH * ((O + CH - 1) // CH)
-        w_end2 = W2.new_zeros((E, Opad)); w_end2[:, :O] = W2[:, :, 0, 0].t()
-        b_end2 = b2.new_zeros((Opad,)); b_end2[:O] = b2
-        ctx.dims = (nl, k, S, E, O, Wm[0].shape[1])
+        srcs = [t.detach().contiguous() for t in (*Wf, *bf, *Wg, *bg, *Wm, *Ws, *bs, W1, W2, b2)]
+        flat = ops.pack_params(srcs, nl, k, mlp_in, S, E, O)
+        o = ops.pack_offsets(nl, k, mlp_in, S, E, O)
+        w_fg = flat[o[0]:o[1]].view(nl, k * CH, 2 * CH)
+        b_fg = flat[o[1]:o[2]].view(nl, 2 * CH)
+        w_mlp = flat[o[2]:o[3]].view(nl, mlp_in, CH)
+        w_skip = flat[o[3]:o[4]].view(nl * CH, S)
+        b_skip = flat[o[4]:o[5]]
+        w_end1 = flat[o[5]:o[6]].view(S, E)
+        w_end2 = flat[o[6]:o[7]].view(E, Opad)
+        b_end2 = flat[o[7]:o[8]]
+        ctx.dims = (nl, k, S, E, O, mlp_in)
         ctx.set_materialize_grads(False)
         return (*w_fg.unbind(0), *b_fg.unbind(0), *w_mlp.unbind(0), w_skip, b_skip, w_end1, w_end2, b_end2)
 
     @staticmethod
     def backward(ctx, *g):
         nl, k, S, E, O, mlp_in = ctx.dims
-        g_wfg, g_bfg, g_wmlp = g[:nl], g[nl:2 * nl], g[2 * nl:3 * nl]
-        g_wskip, g_bskip, g_wend1, g_wend2, g_bend2 = g[3 * nl:]
-
-        def unstack(items, fn):
-            """per-layer grads (some None: parameters the block never used) -> per-layer param grads"""
-            live = [i for i, t in enumerate(items) if t is not None]
-            out = [None] * nl
-            if live:
-                res = fn(torch.stack([items[i] for i in live]))
-                for j, i in enumerate(live):
-                    out[i] = tuple(r[j] for r in res)
-            return out
-
-        fg = unstack(g_wfg, lambda t: (
-            t.reshape(-1, k, CH, CH, 2).permute(0, 3, 4, 2, 1)[:, :, 0].unsqueeze(3).contiguous(),   # Wf [o,c,1,k]
-            t.reshape(-1, k, CH, CH, 2).permute(0, 3, 4, 2, 1)[:, :, 1].unsqueeze(3).contiguous()))
-        bfg = unstack(g_bfg, lambda t: (t.reshape(-1, CH, 2)[:, :, 0].contiguous(),
-                                        t.reshape(-1, CH, 2)[:, :, 1].contiguous()))
-        wm = unstack(g_wmlp, lambda t: (t.transpose(1, 2).reshape(-1, CH, mlp_in, 1, 1).contiguous(),))
-        dWf = [x[0] if x else None for x in fg]; dWg = [x[1] if x else None for x in fg]
-        dbf = [x[0] if x else None for x in bfg]; dbg = [x[1] if x else None for x in bfg]
-        dWm = [x[0] if x else None for x in wm]
-        if g_wskip is not None:
-            t = g_wskip.reshape(nl, CH, S).permute(0, 2, 1).reshape(nl, S, CH, 1, 1).contiguous()
-            dWs = list(t.unbind(0))
-        else:
-            dWs = [None] * nl
-        dbs = [g_bskip] * nl if g_bskip is not None else [None] * nl
-        dW1 = g_wend1.t().reshape(E, S, 1, 1).contiguous() if g_wend1 is not None else None
-        dW2 = g_wend2[:, :O].t().reshape(O, E, 1, 1).contiguous() if g_wend2 is not None else None
-        db2 = g_bend2[:O].contiguous() if g_bend2 is not None else None
+        cont = lambda t: None if t is None else t.contiguous()  # noqa: E731
+        g_wfg, g_bfg, g_wmlp = [cont(t) for t in g[:nl]], [cont(t) for t in g[nl:2 * nl]], [cont(t) for t in g[2 * nl:3 * nl]]
+        g_wskip, g_bskip, g_wend1, g_wend2, g_bend2 = (cont(t) for t in g[3 * nl:])
+        if all(t is None for t in (*g_wfg, *g_bfg, *g_wmlp, g_wskip, g_bskip, g_wend1, g_wend2, g_bend2)):
+            return (None,) * (1 + 8 * nl + 4)
+        flat = ops.unpack_grads(g_wfg, g_bfg, g_wmlp, g_wskip, g_bskip, g_wend1, g_wend2, g_bend2, k, mlp_in, S, E, O)
+        nw = CH * CH * k
+        per = 2 * (nw + CH) + CH * mlp_in + CH * S + S
+        dWf, dbf, dWg, dbg, dWm, dWs, dbs = ([None] * nl for _ in range(7))
+        for l in range(nl):
+            b0 = l * per
+            if g_wfg[l] is not None:                       # parameters the block never used keep grad None
+                dWf[l] = flat[b0:b0 + nw].view(CH, CH, 1, k)
+                dWg[l] = flat[b0 + nw + CH:b0 + 2 * nw + CH].view(CH, CH, 1, k)
+            if g_bfg[l] is not None:
+                dbf[l] = flat[b0 + nw:b0 + nw + CH]
+                dbg[l] = flat[b0 + 2 * nw + CH:b0 + 2 * (nw + CH)]
+            b1 = b0 + 2 * (nw + CH)
+            if g_wmlp[l] is not None:
+                dWm[l] = flat[b1:b1 + CH * mlp_in].view(CH, mlp_in, 1, 1)
+            b2 = b1 + CH * mlp_in
+            if g_wskip is not None:
+                dWs[l] = flat[b2:b2 + CH * S].view(S, CH, 1, 1)
+            if g_bskip is not None:
+                dbs[l] = flat[b2 + CH * S:b2 + CH * S + S]
+        t0 = nl * per
+        dW1 = flat[t0:t0 + E * S].view(E, S, 1, 1) if g_wend1 is not None else None
+        dW2 = flat[t0 + E * S:t0 + E * S + O * E].view(O, E, 1, 1) if g_wend2 is not None else None
+        db2 = flat[t0 + E * S + O * E:t0 + E * S + O * E + O] if g_bend2 is not None else None
         # bm, b1 are passed straight to the kernels (no packing) -> no grads through this Function
         return (None, *dWf, *dbf, *dWg, *dbg, *dWm, *([None] * nl), *dWs, *dbs, dW1, None, dW2, db2)
 

@@ -18,7 +18,7 @@ from torch import Tensor
 
 from . import _lib
 from ._lib import (GWN_BF16, GWN_F32, HeadBwdArgs, HeadCfg, HeadFwdArgs, HeadTcBwdArgs, HeadTcFwdArgs, LayerBwdArgs,
-                   LayerCfg, LayerFwdArgs, check, lib)
+                   LayerCfg, LayerFwdArgs, PackCfg, PackPtrs, UnpackPtrs, check, lib)
 
 CH = 32
 
@@ -710,3 +710,82 @@ def hop_tc(mats: Tensor, n_mats: int, mat: int, buf: Tensor, slot_in: int, slot_
     with torch.cuda.device(buf.device):
         check(lib().gwn_hop_tc(_p(mats), n_mats, mat, _p(buf), pitch, slot_in, slot_out, rows // V, V, _stream()),
               'gwn_hop_tc')
+
+
+# =========================================================================== parameter packing
+def _pack_cfg(nl: int, taps: int, mlp_in: int, S: int, E: int, O: int) -> PackCfg:
+    return PackCfg(n_layers=nl, taps=taps, mlp_in=mlp_in, S=S, E=E, O=O, Opad=CH * ((O + CH - 1) // CH))
+
+
+def pack_offsets(nl: int, taps: int, mlp_in: int, S: int, E: int, O: int) -> List[int]:
+    """Element offsets of the 8 packed segments (+ total) inside the buffer `pack_params` returns."""
+    off = (C.c_longlong * 9)()
+    cfg = _pack_cfg(nl, taps, mlp_in, S, E, O)
+    if lib().gwn_pack_offsets(C.byref(cfg), off) < 0:
+        check(-1, 'gwn_pack_offsets')
+    return list(off)
+
+
+@torch.library.custom_op('gwn::pack_params', mutates_args=())
+def pack_params(params: List[Tensor], nl: int, taps: int, mlp_in: int, S: int, E: int, O: int) -> Tensor:
+    """params = Wf[nl], bf[nl], Wg[nl], bg[nl], Wm[nl], Ws[nl], bs[nl], W1, W2, b2 (reference shapes, fp32) ->
+    one flat fp32 buffer with the kernels' layouts (include/gwn.h: gwn_pack_params).  ONE launch."""
+    for t in params:
+        _req(t, torch.float32, 'parameter')
+    cfg = _pack_cfg(nl, taps, mlp_in, S, E, O)
+    ptrs = PackPtrs()
+    for i, name in enumerate(('w_filter', 'b_filter', 'w_gate', 'b_gate', 'w_mlp', 'w_skip', 'b_skip')):
+        arr = getattr(ptrs, name)
+        for l in range(nl):
+            arr[l] = params[i * nl + l].data_ptr()
+    ptrs.w_end1, ptrs.w_end2, ptrs.b_end2 = (params[7 * nl + j].data_ptr() for j in range(3))
+    out = torch.empty((pack_offsets(nl, taps, mlp_in, S, E, O)[8],), device=params[0].device, dtype=torch.float32)
+    with torch.cuda.device(out.device):
+        check(lib().gwn_pack_params(C.byref(cfg), C.byref(ptrs), _p(out), _stream()), 'gwn_pack_params')
+    return out
+
+
+@pack_params.register_fake
+def _(params, nl, taps, mlp_in, S, E, O):
+    Opad = CH * ((O + CH - 1) // CH)
+    n = nl * taps * CH * 2 * CH + nl * 2 * CH + nl * mlp_in * CH + nl * CH * S + S + S * E + E * Opad + Opad
+    return params[0].new_empty((n,))
+
+
+def unpack_total(nl: int, taps: int, mlp_in: int, S: int, E: int, O: int) -> int:
+    return nl * (2 * (CH * CH * taps + CH) + CH * mlp_in + CH * S + S) + E * S + O * E + O
+
+
+@torch.library.custom_op('gwn::unpack_grads', mutates_args=())
+def unpack_grads(g_wfg: List[Optional[Tensor]], g_bfg: List[Optional[Tensor]], g_wmlp: List[Optional[Tensor]],
+                 g_wskip: Optional[Tensor], g_bskip: Optional[Tensor], g_wend1: Optional[Tensor],
+                 g_wend2: Optional[Tensor], g_bend2: Optional[Tensor], taps: int, mlp_in: int, S: int, E: int,
+                 O: int) -> Tensor:
+    """Gradients of the packed tensors (None = absent) -> one flat fp32 buffer in parameter order (gwn_unpack_grads)."""
+    nl = len(g_wfg)
+    cfg = _pack_cfg(nl, taps, mlp_in, S, E, O)
+    ptrs = UnpackPtrs()
+    dev = None
+    for name, lst in (('w_fg', g_wfg), ('b_fg', g_bfg), ('w_mlp', g_wmlp)):
+        arr = getattr(ptrs, name)
+        for l, t in enumerate(lst):
+            if t is not None:
+                _req(t, torch.float32, 'gradient'); dev = t.device
+                arr[l] = t.data_ptr()
+    for name, t in (('w_skip', g_wskip), ('b_skip', g_bskip), ('w_end1', g_wend1), ('w_end2', g_wend2), ('b_end2', g_bend2)):
+        if t is not None:
+            _req(t, torch.float32, 'gradient'); dev = t.device
+            setattr(ptrs, name, t.data_ptr())
+    if dev is None:
+        raise ValueError('unpack_grads: no gradient given')
+    out = torch.empty((unpack_total(nl, taps, mlp_in, S, E, O),), device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        check(lib().gwn_unpack_grads(C.byref(cfg), C.byref(ptrs), _p(out), _stream()), 'gwn_unpack_grads')
+    return out
+
+
+@unpack_grads.register_fake
+def _(g_wfg, g_bfg, g_wmlp, g_wskip, g_bskip, g_wend1, g_wend2, g_bend2, taps, mlp_in, S, E, O):
+    ref = next(t for t in list(g_wfg) + list(g_bfg) + list(g_wmlp) + [g_wskip, g_bskip, g_wend1, g_wend2, g_bend2]
+               if t is not None)
+    return ref.new_empty((unpack_total(len(g_wfg), taps, mlp_in, S, E, O),), dtype=torch.float32)

@@ -37,7 +37,9 @@ def test_struct_layouts_match_the_c_header(tmp_path):
     from multimodal_outage_b200 import _lib
     pairs = {'gwn_layer_cfg': _lib.LayerCfg, 'gwn_layer_fwd_args': _lib.LayerFwdArgs,
              'gwn_layer_bwd_args': _lib.LayerBwdArgs, 'gwn_head_cfg': _lib.HeadCfg,
-             'gwn_head_fwd_args': _lib.HeadFwdArgs, 'gwn_head_bwd_args': _lib.HeadBwdArgs}
+             'gwn_head_fwd_args': _lib.HeadFwdArgs, 'gwn_head_bwd_args': _lib.HeadBwdArgs,
+             'gwn_head_tc_fwd_args': _lib.HeadTcFwdArgs, 'gwn_head_tc_bwd_args': _lib.HeadTcBwdArgs,
+             'gwn_pack_cfg': _lib.PackCfg, 'gwn_pack_ptrs': _lib.PackPtrs, 'gwn_unpack_ptrs': _lib.UnpackPtrs}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "gwn.h"', 'int main(void){']
     for cname, ct in pairs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
@@ -97,45 +99,22 @@ def test_cpu_forward_fails_loudly_no_fallback():
         m(torch.randn(1, 2, 67, 12))
 
 
-def test_param_packing_layouts_and_gradient_unpacking():
-    """_PackParams is pure torch and runs on CPU: check layouts element-wise and that gradients of the
-    packed tensors are routed back to the reference-shaped parameters exactly."""
-    from multimodal_outage_b200 import gwnet
-    torch.manual_seed(0)
+def test_param_packing_segment_arithmetic():
+    """Host side of the parameter packing (csrc/pack.cu): segment offsets of the packed buffer and the size of the
+    flat gradient buffer must match the module's parameter shapes (the gather/scatter kernels themselves are
+    checked element-wise on the GPU: test_gpu_parity.py::test_param_packing_layouts_and_gradient_unpacking)."""
+    from multimodal_outage_b200 import gwnet, ops
     m = gwnet('cpu', in_dim=2, out_dim=12, kernel_size=3, blocks=1, layers=2, skip_channels=64, end_channels=96,
               supports=[torch.eye(67)] * 2)
-    pk = m._packed()
-    Wf, Wg = m.filter_convs[1].weight, m.gate_convs[1].weight
-    w_fg = pk['w_fg'][1]
-    assert w_fg.shape == (3 * 32, 64)
-    for (j, c, o) in [(0, 0, 0), (2, 5, 7), (1, 31, 31)]:
-        assert w_fg[j * 32 + c, 2 * o] == Wf[o, c, 0, j] and w_fg[j * 32 + c, 2 * o + 1] == Wg[o, c, 0, j]
-    assert pk['b_fg'][1][2 * 9] == m.filter_convs[1].bias[9] and pk['b_fg'][1][2 * 9 + 1] == m.gate_convs[1].bias[9]
-    Wm = m.gconv[0].mlp.mlp.weight
-    assert pk['w_mlp'][0].shape == (224, 32) and pk['w_mlp'][0][100, 3] == Wm[3, 100, 0, 0]
-    assert pk['w_skip'].shape == (64, 64) and pk['w_skip'][32 + 4, 17] == m.skip_convs[1].weight[17, 4, 0, 0]
-    assert torch.allclose(pk['b_skip'], m.skip_convs[0].bias + m.skip_convs[1].bias)
-    assert pk['w_end1'].shape == (64, 96) and pk['w_end1'][5, 70] == m.end_conv_1.weight[70, 5, 0, 0]
-    assert pk['w_end2'].shape == (96, 32) and pk['w_end2'][50, 11] == m.end_conv_2.weight[11, 50, 0, 0]
-    assert (pk['w_end2'][:, 12:] == 0).all() and (pk['b_end2'][12:] == 0).all()
-    # gradient routing: loss = sum_k <packed_k, R_k>  =>  dparam = unpack(R)
-    R = {k: ([torch.randn_like(t) for t in v] if isinstance(v, (tuple, list)) else torch.randn_like(v))
-         for k, v in pk.items() if k != 'b_mlp'}
-    loss = sum((t * r).sum() for k in ('w_fg', 'b_fg') for t, r in zip(pk[k], R[k]))
-    loss = loss + (pk['w_mlp'][0] * R['w_mlp'][0]).sum()        # layer 1's mlp unused -> grad must stay None
-    for k in ('w_skip', 'b_skip', 'w_end1', 'w_end2', 'b_end2'):
-        loss = loss + (pk[k] * R[k]).sum()
-    loss.backward()
-    assert m.gconv[1].mlp.mlp.weight.grad is None
-    assert m.filter_convs[1].weight.grad[7, 5, 0, 2] == R['w_fg'][1][2 * 32 + 5, 14]
-    assert m.gate_convs[0].weight.grad[7, 5, 0, 2] == R['w_fg'][0][2 * 32 + 5, 15]
-    assert m.gate_convs[1].bias.grad[3] == R['b_fg'][1][7]
-    assert m.gconv[0].mlp.mlp.weight.grad[3, 100, 0, 0] == R['w_mlp'][0][100, 3]
-    assert m.skip_convs[1].weight.grad[17, 4, 0, 0] == R['w_skip'][36, 17]
-    assert torch.equal(m.skip_convs[0].bias.grad, R['b_skip'])
-    assert m.end_conv_1.weight.grad[70, 5, 0, 0] == R['w_end1'][5, 70]
-    assert m.end_conv_2.weight.grad[11, 50, 0, 0] == R['w_end2'][50, 11]
-    assert torch.equal(m.end_conv_2.bias.grad, R['b_end2'][:12])
+    nl, k, mlp_in, S, E, O = 2, 3, 224, 64, 96, 12
+    off = ops.pack_offsets(nl, k, mlp_in, S, E, O)
+    sizes = [nl * k * 32 * 64, nl * 64, nl * mlp_in * 32, nl * 32 * S, S, S * E, E * 32, 32]
+    assert off[0] == 0 and [off[i + 1] - off[i] for i in range(8)] == sizes
+    assert all(o % 4 == 0 for o in off)                      # every segment starts 16-byte aligned
+    packed = [p for n, p in m.named_parameters()
+              if n.split('.')[0] in ('filter_convs', 'gate_convs', 'skip_convs', 'gconv', 'end_conv_2')
+              and not n.endswith('mlp.mlp.bias')] + [m.end_conv_1.weight]
+    assert ops.unpack_total(nl, k, mlp_in, S, E, O) == sum(p.numel() for p in packed)
 
 
 def test_supports_bit_exact_with_reference_golden():
