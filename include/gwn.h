@@ -109,6 +109,16 @@ typedef struct {
   void* u;                      /* out [N,Lout,V,32] */
   double* stats;                /* out [2,32]: sum, sum of squares (zeroed by callee) */
   void* ws_cat;                 /* workspace [N*Lout*V, 32*(1+order*n_supports)] (dtype) */
+  /* Optional (bf16 tensor-core path only): BatchNorm of the previous layer (graph_wavenet.py:250) folded INSIDE the
+   * gate kernel's prologue - no separate fold / weight-prep launches.  When bn_gamma != NULL, `scale` and `shift`
+   * above are OUTPUTS ([32] each, written by the kernel) together with bn_mean / bn_rstd; with cfg.training the batch
+   * statistics come from bn_stats ([2,32] sum, sum of squares over bn_count elements per channel) and the running
+   * statistics are updated (momentum, unbiased variance); otherwise the running statistics are used. */
+  const double* bn_stats; const float* bn_gamma; const float* bn_beta;
+  float* bn_running_mean; float* bn_running_var;
+  float* bn_mean; float* bn_rstd;
+  double bn_count;
+  float bn_momentum, bn_eps;
 } gwn_layer_fwd_args;
 
 int gwn_layer_fwd(const gwn_layer_cfg* cfg, const gwn_layer_fwd_args* args, void* stream);

@@ -29,7 +29,10 @@ class LayerCfg(C.Structure):
 class LayerFwdArgs(C.Structure):
     _fields_ = [('u_prev', vp), ('scale', vp), ('shift', vp), ('w_fg', vp), ('b_fg', vp), ('w_mlp', vp),
                 ('b_mlp', vp), ('supports', vp * MAX_SUPPORTS), ('drop_mask', vp), ('rng', vp), ('hop_mats', vp), ('ws_w', vp), ('a', vp),
-                ('b', vp), ('z_last', vp), ('u', vp), ('stats', vp), ('ws_cat', vp)]
+                ('b', vp), ('z_last', vp), ('u', vp), ('stats', vp), ('ws_cat', vp),
+                ('bn_stats', vp), ('bn_gamma', vp), ('bn_beta', vp), ('bn_running_mean', vp), ('bn_running_var', vp),
+                ('bn_mean', vp), ('bn_rstd', vp), ('bn_count', C.c_double), ('bn_momentum', C.c_float),
+                ('bn_eps', C.c_float)]
 
 
 class LayerBwdArgs(C.Structure):

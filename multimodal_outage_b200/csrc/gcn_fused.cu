@@ -119,9 +119,30 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gcn_fwd_kernel(const __grid_con
         dst[kc * per_piece + r] = __ldg(src + kc * 128 + r);
       }
     }
-    const uint4* wsrc = reinterpret_cast<const uint4*>(p.w_img);
-    uint4* wdst = reinterpret_cast<uint4*>(smem + L.w_off);
-    for (int i = tid; i < (int)(L.w_bytes / 16); i += GF_THREADS) wdst[i] = __ldg(wsrc + i);
+    if (p.w_src) {       // bf16 UMMA image of the mlp weight built here: (k = c, n = (j, c')) = W[j*32 + c][c']
+      bf16* wimg = reinterpret_cast<bf16*>(smem + L.w_off);
+      constexpr int T4 = 8 * NU, ITS = (T4 + GF_THREADS - 1) / GF_THREADS;      // 16-byte loads, all issued first
+      float4 wv[ITS];
+#pragma unroll
+      for (int it = 0; it < ITS; ++it) {
+        const int i = tid + it * GF_THREADS;
+        wv[it] = i < T4 ? __ldg(reinterpret_cast<const float4*>(p.w_src) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int it = 0; it < ITS; ++it) {
+        const int i = tid + it * GF_THREADS;
+        if (i < T4) {
+          const int co = (i & 7) * 4, c = (i >> 3) & 31, n = (i >> 8) * 32 + co;
+          bf16* d = wimg + ((c >> 3) * NU + n) * 8 + (c & 7);
+          d[0] = __float2bfloat16_rn(wv[it].x); d[8] = __float2bfloat16_rn(wv[it].y);
+          d[16] = __float2bfloat16_rn(wv[it].z); d[24] = __float2bfloat16_rn(wv[it].w);
+        }
+      }
+    } else {
+      const uint4* wsrc = reinterpret_cast<const uint4*>(p.w_img);
+      uint4* wdst = reinterpret_cast<uint4*>(smem + L.w_off);
+      for (int i = tid; i < (int)(L.w_bytes / 16); i += GF_THREADS) wdst[i] = __ldg(wsrc + i);
+    }
     if (tid >= 64 && tid < 128) cst[96 + tid - 64] = 0.f;     // CTA-level (sum, sum^2) scratch
     if (tid < 32) {
       cst[tid] = __ldg(p.bias + tid);

@@ -40,6 +40,7 @@ struct GcnFwdParams {
   bf16* u;                     // out [slabs*V, 32]
   double* stats;               // [2][32], accumulated with atomics (caller zeroes)
   int V, Kp, slabs;
+  const float* w_src;          // optional: packed fp32 mlp weight [32*(1+n_mats)][32]; the kernel builds its bf16 image itself (w_img unused)
   long long* trace;            // optional debug: [64 slabs][8] clock64 timestamps of CTA 0 (NULL = off)
 };
 
@@ -69,6 +70,7 @@ struct GcnBwdParams {
   int mat_src[GF_MAX_MATS];    // image index of the TRANSPOSED hop j+1 (variants 2, 3)
   int n_mats;
   const bf16* wt_img;          // [4*(1+n_mats)][32][8]: (n = c, k = (j, c')) = W_mlp[j*32 + c][c']
+  const float* w_src;          // optional: packed fp32 mlp weight; the kernel builds wt_img / w56_img itself (both unused)
   const bf16* mask;
   float drop_p;
   uint64_t seed, offset;

@@ -115,16 +115,46 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
         dst[kc * Kp + r] = __ldg(src + kc * 128 + r);
       }
     }
-    const uint4* wsrc = reinterpret_cast<const uint4*>(p.wt_img);
-    uint4* wdst = reinterpret_cast<uint4*>(smem + L.w_off);
-    for (int i = tid; i < (int)(L.w_bytes / 16); i += GB_THREADS) wdst[i] = __ldg(wsrc + i);
+    if (p.w_src) {       // bf16 UMMA images of the mlp weight built here (see gcn_bwd_wprep_kernel for the layouts)
+      bf16* wt = reinterpret_cast<bf16*>(smem + L.w_off);
+      bf16* w56 = reinterpret_cast<bf16*>(smem + L.w56_off);
+      constexpr int T4 = 8 * 32 * (1 + NM), ITS = (T4 + GB_THREADS - 1) / GB_THREADS;   // 16-byte loads, all issued first
+      float4 wv[ITS];
+#pragma unroll
+      for (int it = 0; it < ITS; ++it) {
+        const int i = tid + it * GB_THREADS;
+        wv[it] = i < T4 ? __ldg(reinterpret_cast<const float4*>(p.w_src) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int it = 0; it < ITS; ++it) {
+        const int i = tid + it * GB_THREADS;
+        if (i < T4) {
+          const int j = i >> 8, c = (i >> 3) & 31, co = (i & 7) * 4;
+          const float v4[4] = {wv[it].x, wv[it].y, wv[it].z, wv[it].w};
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(v4[0], v4[1]), h1 = __floats2bfloat162_rn(v4[2], v4[3]);
+          uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+          *reinterpret_cast<uint2*>(wt + ((j * 4 + (co >> 3)) * 32 + c) * 8 + (co & 7)) = pk;     // 4 consecutive c'
+          if (DA && (j == 2 * p.sa + 1 || j == 2 * p.sa + 2)) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              w56[((c >> 3) * 64 + (j - (2 * p.sa + 1)) * 32 + co + q) * 8 + (c & 7)] = __float2bfloat16_rn(v4[q]);
+          }
+        }
+      }
+    } else {
+      const uint4* wsrc = reinterpret_cast<const uint4*>(p.wt_img);
+      uint4* wdst = reinterpret_cast<uint4*>(smem + L.w_off);
+      for (int i = tid; i < (int)(L.w_bytes / 16); i += GB_THREADS) wdst[i] = __ldg(wsrc + i);
+    }
     if (DA) {
       const uint4* src = reinterpret_cast<const uint4*>(p.mats) + (size_t)p.mat_fwd * pieces * 128;
       uint4* dst = reinterpret_cast<uint4*>(smem + L.fwd_off);
       for (int i = tid; i < pieces * Kp; i += GB_THREADS) dst[(i / Kp) * Kp + (i % Kp)] = __ldg(src + (i / Kp) * 128 + (i % Kp));
-      const uint4* w5 = reinterpret_cast<const uint4*>(p.w56_img);
-      uint4* d5 = reinterpret_cast<uint4*>(smem + L.w56_off);
-      for (int i = tid; i < 4 * 64; i += GB_THREADS) d5[i] = __ldg(w5 + i);
+      if (!p.w_src) {
+        const uint4* w5 = reinterpret_cast<const uint4*>(p.w56_img);
+        uint4* d5 = reinterpret_cast<uint4*>(smem + L.w56_off);
+        for (int i = tid; i < 4 * 64; i += GB_THREADS) d5[i] = __ldg(w5 + i);
+      }
     }
     // slack past the buffers is read (as ignored accumulator rows) by the M=128 operands: keep it finite
     uint4* sl = reinterpret_cast<uint4*>(smem + L.bar_off - 4096u);
@@ -534,7 +564,7 @@ int launch_gcn_bwd(GcnBwdParams& p, cudaStream_t st) {
               p.n_mats);
   GWN_REQUIRE((long long)p.slabs * p.V < (1ll << 31), "gcn_bwd: too many positions");
   const bool has_da = p.sa >= 0;
-  GWN_REQUIRE(!has_da || (p.dA && p.w56_img && p.sa < p.n_mats / 2), "gcn_bwd: bad support-gradient arguments");
+  GWN_REQUIRE(!has_da || (p.dA && (p.w56_img || p.w_src) && p.sa < p.n_mats / 2), "gcn_bwd: bad support-gradient arguments");
   const GbLayout L = gb_layout(p.Kp, p.n_mats, has_da);
   static int sms = 0;
   if (sms == 0) {

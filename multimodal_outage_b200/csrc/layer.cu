@@ -689,6 +689,7 @@ static int layer_fwd_t(const gwn_layer_cfg* c, const gwn_layer_fwd_args* g, cuda
   }
   bool tc = false;
   if constexpr (std::is_same<T, bf16>::value) tc = tc_mode<T>(c, g->hop_mats) != 0 && g->ws_w != nullptr && c->taps <= 4;
+  GWN_REQUIRE(tc || !g->bn_gamma, "layer_fwd: the in-kernel BatchNorm fold (bn_gamma) needs the bf16 tensor-core path");
   uint8_t* wsw = reinterpret_cast<uint8_t*>(g->ws_w);
   const long long last_begin = (long long)(c->Lout - c->Lf) * c->V, last_rows = (long long)c->Lf * c->V;
   bool fused_fwd = false;     // supports on chip: hops + concat + mlp + dropout + residual + statistics as ONE kernel
@@ -697,19 +698,27 @@ static int layer_fwd_t(const gwn_layer_cfg* c, const gwn_layer_fwd_args* g, cuda
                 c->n_supports >= 1 && gcn_fused_supported(c->V, 2 * c->n_supports);
   if (tc) {
     if constexpr (std::is_same<T, bf16>::value) {
-      // fold the previous layer's BatchNorm affine into the gate weights/bias, build the bf16 UMMA image
-      WPrepParams wp{};
-      wp.W = g->w_fg; wp.ld = 64; wp.transposed = 0; wp.K = 32 * c->taps; wp.N = 64;
-      for (int j = 0; j < c->taps; ++j) wp.w_off[j] = (long long)j * 32 * 64;
-      wp.scale = g->scale; wp.shift = g->shift; wp.bias = g->b_fg;
-      wp.img = reinterpret_cast<bf16*>(wsw); wp.bias_out = nullptr; wp.bias_chunk = 1; wp.half_odd = 1;
-      if (c->has_gconv) {      // same launch: zero the BN statistics and build the fused gcn weight image
-        wp.zero64 = g->stats;
-        if (fused_fwd) { wp.g_w = g->w_mlp; wp.g_nmats = 2 * c->n_supports; wp.g_img = reinterpret_cast<bf16*>(wsw + 64 * 1024); }
-      }
-      if (int rc = launch_wprep(wp, st)) return rc;
+      // The gate kernel builds its own bf16 UMMA weight image in its prologue (tc_gemm.cuh: PgWsrc): the previous
+      // layer's BatchNorm affine is folded into the weights / bias there (from the raw batch statistics when the caller
+      // passes bn_gamma, else from scale / shift computed by gwn_bn_fold), the next statistics buffer is zeroed by
+      // CTA 0 - no weight-prep or fold launch sits between the layer's kernels.
       PgParams pg{};
-      pg.n_chunks = c->taps; pg.rows_per_n_out = RO; pg.P = P; pg.N = 64; pg.w_img = wp.img; pg.has_bias = 1;
+      pg.n_chunks = c->taps; pg.rows_per_n_out = RO; pg.P = P; pg.N = 64; pg.has_bias = 1;
+      PgWsrc& ws = pg.wsrc;
+      ws.W = g->w_fg; ws.ld = 64; ws.transposed = 0; ws.half_odd = 1; ws.bias = g->b_fg;
+      for (int j = 0; j < c->taps; ++j) ws.w_off[j] = j * 32 * 64;
+      if (g->bn_gamma) {
+        GWN_REQUIRE(g->scale && g->shift && g->bn_running_mean && g->bn_running_var && (g->bn_stats || !c->training),
+                    "layer_fwd: fused BatchNorm fold needs scale/shift outputs, running statistics and batch statistics");
+        ws.bn = 1; ws.bn_training = c->training; ws.bn_stats = g->bn_stats; ws.bn_count = g->bn_count;
+        ws.gamma = g->bn_gamma; ws.beta = g->bn_beta; ws.running_mean = g->bn_running_mean;
+        ws.running_var = g->bn_running_var; ws.eps = g->bn_eps; ws.momentum = g->bn_momentum;
+        ws.scale_out = const_cast<float*>(g->scale); ws.shift_out = const_cast<float*>(g->shift);
+        ws.mean_out = g->bn_mean; ws.rstd_out = g->bn_rstd;
+      } else if (g->scale) {          // scale / shift already computed by the caller (gwn_bn_fold)
+        ws.bn = 2; ws.scale_in = g->scale; ws.shift_in = g->shift;
+      }
+      if (c->has_gconv) ws.zero64 = g->stats;
       for (int j = 0; j < c->taps; ++j)
         pg.ch[j] = PgChunk{reinterpret_cast<const bf16*>(g->u_prev), RI, (long long)j * c->dilation * c->V, 32, 0};
       EpiGateTC eg{};
@@ -729,17 +738,16 @@ static int layer_fwd_t(const gwn_layer_cfg* c, const gwn_layer_fwd_args* g, cuda
   if (int rc = launch_pos_gemm<T, 64>(A, g->w_fg, 64, eg, st)) return rc;
   }
   if (!c->has_gconv) return 0;
-  if (!tc) GWN_CUDA(cudaMemsetAsync(g->stats, 0, sizeof(double) * 64, st));      // (tc: zeroed by the wprep launch)
+  if (!tc) GWN_CUDA(cudaMemsetAsync(g->stats, 0, sizeof(double) * 64, st));      // (tc: zeroed by CTA 0 of the gate kernel)
   if constexpr (std::is_same<T, bf16>::value) {
     // supports on chip: hops + concat + mlp + dropout + residual + statistics as ONE kernel (gcn_fused.cu)
     if (fused_fwd) {
-      bf16* wimg = reinterpret_cast<bf16*>(wsw + 64 * 1024);     // built by the gate's wprep launch above
       GcnFwdParams fp{};
       fp.z = cat; fp.u_prev = reinterpret_cast<const bf16*>(g->u_prev); fp.RI = RI; fp.RO = RO;
       fp.crop = (long long)(c->Lin - c->Lout) * c->V; fp.scale = g->scale; fp.shift = g->shift;
       fp.mats = reinterpret_cast<const bf16*>(g->hop_mats); fp.n_mats = 2 * c->n_supports;
       for (int j = 0; j < fp.n_mats; ++j) fp.mat_src[j] = 4 * (j / 2) + (j % 2);      // A_s^T, (A_s^2)^T
-      fp.w_img = wimg; fp.bias = g->b_mlp;
+      fp.w_img = nullptr; fp.w_src = g->w_mlp; fp.bias = g->b_mlp;      // image built in the kernel's prologue
       fp.mask = c->training ? reinterpret_cast<const bf16*>(g->drop_mask) : nullptr;
       fp.drop_p = c->training ? c->dropout_p : 0.f; fp.seed = c->seed; fp.offset = c->offset; fp.rng = g->rng;
       fp.u = reinterpret_cast<bf16*>(g->u); fp.stats = g->stats; fp.V = c->V; fp.slabs = c->N * c->Lout;
@@ -798,7 +806,7 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
   const T* du = reinterpret_cast<const T*>(g->du);
   const unsigned eb = (unsigned)cdiv(P * 8, 256);
   const T* dz = nullptr;
-  bool fused_bwd = false, dx_img_ready = false;
+  bool fused_bwd = false;
   if constexpr (std::is_same<T, bf16>::value) {
     // supports on chip and none of them needs a gradient: the whole diffusion backward (mask, transposed hops, mlp
     // data + weight gradients, gate backward) is ONE kernel (gcn_fused_bwd.cu) that leaves dfg for the conv backward
@@ -807,27 +815,15 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
       if (g->support_needs_grad[s] && g->d_supports[s]) { ++n_dA; sa = s; }
     if (du && n_dA <= 1 && fused_gcn_enabled() && tc_mode<T>(c, g->hop_mats) == 1 && c->order == 2 && c->n_supports >= 1 &&
         g->ws_w != nullptr && gcn_bwd_fused_supported(c->V, 2 * c->n_supports) && wgrad_tc_supported(c->taps, 64)) {
-      uint8_t* wsw = reinterpret_cast<uint8_t*>(g->ws_w);
-      bf16* wt = reinterpret_cast<bf16*>(wsw + 96 * 1024);
-      bf16* w56 = reinterpret_cast<bf16*>(wsw + 112 * 1024);
       if (!g->outputs_zeroed) GWN_CUDA(cudaMemsetAsync(g->dw_mlp, 0, sizeof(float) * 32 * mlp_in, st));
       if (!g->outputs_zeroed) GWN_CUDA(cudaMemsetAsync(g->db_mlp, 0, sizeof(float) * 32, st));
-      {   // one launch: the gcn backward weight images AND the (transposed) gate weight image of the dx GEMM below
-        WPrepParams wp{};
-        wp.W = g->w_fg; wp.ld = 64; wp.transposed = 1; wp.K = 64 * c->taps; wp.N = 32;
-        for (int j = 0; j < c->taps; ++j)
-          for (int h = 0; h < 2; ++h) wp.w_off[2 * j + h] = (long long)j * 32 * 64 + h * 32;
-        wp.img = reinterpret_cast<bf16*>(wsw + 64 * 1024); wp.bias_out = nullptr;
-        wp.g_w = g->w_mlp; wp.g_nmats = 2 * c->n_supports; wp.gb_wt = wt; wp.gb_sa = sa; wp.gb_w56 = w56;
-        if (int rc = launch_wprep(wp, st)) return rc;
-        dx_img_ready = true;
-      }
+      // (weight images: built by the kernels' own prologues - gcn_bwd from w_mlp, the dx GEMM below from w_fg)
       GcnBwdParams bp{};
       bp.du = du; bp.a = a; bp.b = b; bp.dz_last = reinterpret_cast<const bf16*>(g->dz_last);
       bp.RO = RO; bp.last_begin = (long long)(c->Lout - c->Lf) * c->V; bp.last_rows = (long long)c->Lf * c->V;
       bp.mats = reinterpret_cast<const bf16*>(g->hop_mats); bp.n_mats = 2 * c->n_supports;
       for (int j = 0; j < bp.n_mats; ++j) bp.mat_src[j] = 4 * (j / 2) + 2 + (j % 2);     // A_s, A_s^2 (transposed hops)
-      bp.wt_img = wt;
+      bp.wt_img = nullptr; bp.w_src = g->w_mlp;
       const bool drop = c->training && (g->drop_mask != nullptr || c->dropout_p > 0.f);
       bp.mask = drop ? reinterpret_cast<const bf16*>(g->drop_mask) : nullptr;
       bp.drop_p = drop ? c->dropout_p : 0.f; bp.seed = c->seed; bp.offset = c->offset; bp.rng = g->rng;
@@ -837,7 +833,7 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
         const char* e = getenv("GWN_GCN_TRACE");
         bp.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
       }
-      bp.sa = sa; bp.mat_fwd = sa >= 0 ? 4 * sa : 0; bp.w56_img = w56; bp.dA = sa >= 0 ? g->d_supports[sa] : nullptr;
+      bp.sa = sa; bp.mat_fwd = sa >= 0 ? 4 * sa : 0; bp.w56_img = nullptr; bp.dA = sa >= 0 ? g->d_supports[sa] : nullptr;
       if (int rc = launch_gcn_bwd(bp, st)) return rc;
       fused_bwd = true;
     }
@@ -1031,16 +1027,12 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
   ex.u_prev = reinterpret_cast<const T*>(g->u_prev); ex.dx = g->dx_prev;
   if (tc_gate && g->ws_w != nullptr && 2 * c->taps <= PG_TC_MAX_CHUNKS) {
     if constexpr (std::is_same<T, bf16>::value) {
-      uint8_t* wsw = reinterpret_cast<uint8_t*>(g->ws_w);
-      WPrepParams wp{};
-      wp.W = g->w_fg; wp.ld = 64; wp.transposed = 1; wp.K = 64 * c->taps; wp.N = 32;
-      for (int j = 0; j < c->taps; ++j)
-        for (int h = 0; h < 2; ++h) wp.w_off[2 * j + h] = (long long)j * 32 * 64 + h * 32;
-      wp.img = reinterpret_cast<bf16*>(wsw + 64 * 1024); wp.bias_out = nullptr;
-      if (!dx_img_ready)
-        if (int rc = launch_wprep(wp, st)) return rc;
+      // the (transposed) gate weight image of this GEMM is built by the kernel's own prologue (tc_gemm.cuh: PgWsrc)
       PgParams pg{};
-      pg.n_chunks = 2 * c->taps; pg.rows_per_n_out = RI; pg.P = PI; pg.N = 32; pg.w_img = wp.img;
+      pg.n_chunks = 2 * c->taps; pg.rows_per_n_out = RI; pg.P = PI; pg.N = 32;
+      pg.wsrc.W = g->w_fg; pg.wsrc.ld = 64; pg.wsrc.transposed = 1;
+      for (int j = 0; j < c->taps; ++j)
+        for (int h = 0; h < 2; ++h) pg.wsrc.w_off[2 * j + h] = j * 32 * 64 + h * 32;
       for (int j = 0; j < c->taps; ++j)
         for (int h = 0; h < 2; ++h)
           pg.ch[2 * j + h] = PgChunk{dfg16, RO, -(long long)j * c->dilation * c->V, 64, h * 32};
@@ -1092,15 +1084,13 @@ extern "C" int gwn_gcn_fwd(const void* z, const void* u_prev, const float* scale
   GWN_REQUIRE(gcn_fused_supported(V, 2 * n_supports), "gcn_fwd: V=%d with %d supports does not fit on chip", V, n_supports);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   GWN_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 64, st));
-  bf16* wimg = reinterpret_cast<bf16*>(ws_w);
-  if (int rc = launch_gcn_wprep(w_mlp, 2 * n_supports, wimg, st)) return rc;
   GcnFwdParams fp{};
   fp.z = reinterpret_cast<const bf16*>(z); fp.u_prev = reinterpret_cast<const bf16*>(u_prev);
   fp.RI = (long long)Lin * V; fp.RO = (long long)Lout * V; fp.crop = (long long)(Lin - Lout) * V;
   fp.scale = scale; fp.shift = shift;
   fp.mats = reinterpret_cast<const bf16*>(hop_mats); fp.n_mats = 2 * n_supports;
   for (int j = 0; j < fp.n_mats; ++j) fp.mat_src[j] = 4 * (j / 2) + (j % 2);
-  fp.w_img = wimg; fp.bias = b_mlp; fp.mask = nullptr; fp.drop_p = drop_p; fp.seed = seed; fp.offset = offset;
+  fp.w_img = nullptr; fp.w_src = w_mlp; fp.bias = b_mlp; fp.mask = nullptr; fp.drop_p = drop_p; fp.seed = seed; fp.offset = offset;
   fp.rng = nullptr; fp.u = reinterpret_cast<bf16*>(u); fp.stats = stats; fp.V = V; fp.slabs = N * Lout;
   {  // debug timeline: GWN_GCN_TRACE=<device pointer of 64*8 int64> (scripts/gpu_gcn_trace.py)
     const char* e = getenv("GWN_GCN_TRACE");
@@ -1122,19 +1112,15 @@ extern "C" int gwn_gcn_bwd(const void* du, const void* a, const void* b, const v
   const int mlp_in = 32 * (1 + 2 * n_supports);
   GWN_CUDA(cudaMemsetAsync(dw_mlp, 0, sizeof(float) * 32 * mlp_in, st));
   GWN_CUDA(cudaMemsetAsync(db_mlp, 0, sizeof(float) * 32, st));
-  uint8_t* wsw = reinterpret_cast<uint8_t*>(ws_w);
-  bf16* wt = reinterpret_cast<bf16*>(wsw);
-  bf16* w56 = reinterpret_cast<bf16*>(wsw + 16 * 1024);
-  if (int rc = launch_gcn_bwd_wprep(w_mlp, 2 * n_supports, wt, sa, w56, st)) return rc;
   GcnBwdParams bp{};
   bp.du = reinterpret_cast<const bf16*>(du); bp.a = reinterpret_cast<const bf16*>(a); bp.b = reinterpret_cast<const bf16*>(b);
   bp.dz_last = reinterpret_cast<const bf16*>(dz_last);
   bp.RO = (long long)Lout * V; bp.last_begin = (long long)(Lout - Lf) * V; bp.last_rows = (long long)Lf * V;
   bp.mats = reinterpret_cast<const bf16*>(hop_mats); bp.n_mats = 2 * n_supports;
   for (int j = 0; j < bp.n_mats; ++j) bp.mat_src[j] = 4 * (j / 2) + 2 + (j % 2);
-  bp.wt_img = wt; bp.mask = nullptr; bp.drop_p = drop_p; bp.seed = seed; bp.offset = offset; bp.rng = nullptr;
+  bp.wt_img = nullptr; bp.w_src = w_mlp; bp.mask = nullptr; bp.drop_p = drop_p; bp.seed = seed; bp.offset = offset; bp.rng = nullptr;
   bp.dfg = reinterpret_cast<bf16*>(dfg); bp.dw_mlp = dw_mlp; bp.db_mlp = db_mlp; bp.V = V; bp.slabs = N * Lout;
-  bp.sa = sa; bp.mat_fwd = sa >= 0 ? 4 * sa : 0; bp.w56_img = w56; bp.dA = dA; bp.trace = nullptr;
+  bp.sa = sa; bp.mat_fwd = sa >= 0 ? 4 * sa : 0; bp.w56_img = nullptr; bp.dA = dA; bp.trace = nullptr;
   return launch_gcn_bwd(bp, st);
 }
 

@@ -20,8 +20,32 @@ struct PgChunk {
 
 constexpr int PG_TC_MAX_MAPS = 8;
 
+// Weight source for building the bf16 UMMA weight image INSIDE the GEMM kernel's prologue (no separate weight-prep /
+// BatchNorm-fold launches between a layer's kernels): fp32 weights, optional bias, optional fold of the previous
+// layer's BatchNorm (scale into the weights, shift into the bias).  CTA 0 also publishes scale/shift/mean/rstd,
+// updates the running statistics and zeroes the next statistics buffer.
+struct PgWsrc {
+  const float* W;               // NULL: the kernel copies PgParams::w_img instead
+  int w_off[PG_TC_MAX_CHUNKS];  // element offset of chunk q
+  int ld;                       // stride of the non-contiguous index
+  int transposed;               // 0: (k,n) at w_off[q] + kk*ld + n ; 1: w_off[q] + n*ld + kk
+  int half_odd;                 // odd output columns (and their bias) scaled by 0.5
+  const float* bias;            // optional [N]
+  int bn;                       // 1: fold BatchNorm(gamma, beta) of the A operand's channels; 2: fold the given scale_in / shift_in
+  const float* scale_in; const float* shift_in;
+  int bn_training;              // batch statistics from bn_stats (else running statistics)
+  const double* bn_stats;       // [2][32] sum, sum of squares
+  double bn_count;
+  const float* gamma; const float* beta;
+  float* running_mean; float* running_var;
+  float eps, momentum;
+  float* scale_out; float* shift_out; float* mean_out; float* rstd_out;   // [32] each (written by CTA 0)
+  double* zero64;               // optional: 64 doubles zeroed by CTA 0
+};
+
 struct PgParams {
   PgChunk ch[PG_TC_MAX_CHUNKS];
+  PgWsrc wsrc;
   int n_chunks;                 // K = 32 * n_chunks
   int n_extra;                  // extra (non-MMA) source tiles ch[n_chunks .. n_chunks+n_extra) brought in by TMA for the epilogue
   long long rows_per_n_out, P;

@@ -123,14 +123,118 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
   const uint32_t buf_cols = acc_cols * (uint32_t)SUB;          // one accumulator buffer: SUB sub-tiles side by side
   if (warp == PGT_MMA_WARP) tmem_alloc(tmem_slot, (uint32_t)n_acc * buf_cols);
   {
-    const uint4* src = reinterpret_cast<const uint4*>(p.w_img);
-    uint4* dst = reinterpret_cast<uint4*>(w_s);
-    for (int i = tid; i < K8 * N; i += PGT_THREADS) dst[i] = __ldg(src + i);
     // ones tile: element (row, k) = 1 for k < 2 (the two bias rows), else 0
     uint4* od = reinterpret_cast<uint4*>(ones_s);
     for (int i = tid; i < 256; i += PGT_THREADS) od[i] = i < 128 ? make_uint4(0x3F803F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
-    fence_proxy_async();
   }
+  if (p.wsrc.W == nullptr) {
+    const uint4* src = reinterpret_cast<const uint4*>(p.w_img);
+    uint4* dst = reinterpret_cast<uint4*>(w_s);
+    for (int i = tid; i < K8 * N; i += PGT_THREADS) dst[i] = __ldg(src + i);
+  } else {
+    // ---- weight image built here from the fp32 weights (tc_gemm.cuh: PgWsrc) ----
+    const PgWsrc& ws = p.wsrc;
+    float* sc_s = red_s + 64;            // [32] scale | [32] shift
+    const int K = 32 * n_chunks;
+    if (tid < 32) {
+      float sc = 1.f, sh = 0.f;
+      if (ws.bn == 2) {
+        sc = ws.scale_in[tid]; sh = ws.shift_in[tid];
+      } else if (ws.bn) {
+        float mean, var;
+        if (ws.bn_training) {
+          const double m = ws.bn_stats[tid] / ws.bn_count;
+          double v = ws.bn_stats[32 + tid] / ws.bn_count - m * m;
+          if (v < 0) v = 0;
+          mean = (float)m; var = (float)v;
+          if (blockIdx.x == 0) {
+            const double unbiased = ws.bn_count > 1 ? v * (ws.bn_count / (ws.bn_count - 1.0)) : v;
+            ws.running_mean[tid] = (1.f - ws.momentum) * ws.running_mean[tid] + ws.momentum * mean;
+            ws.running_var[tid] = (1.f - ws.momentum) * ws.running_var[tid] + ws.momentum * (float)unbiased;
+          }
+        } else {
+          mean = ws.running_mean[tid]; var = ws.running_var[tid];
+        }
+        const float rstd = rsqrtf(var + ws.eps);
+        sc = ws.gamma[tid] * rstd;
+        sh = ws.beta[tid] - mean * sc;
+        if (blockIdx.x == 0) {
+          ws.scale_out[tid] = sc; ws.shift_out[tid] = sh;
+          if (ws.mean_out) { ws.mean_out[tid] = mean; ws.rstd_out[tid] = rstd; }
+        }
+      }
+      sc_s[tid] = sc; sc_s[32 + tid] = sh;
+    }
+    if (blockIdx.x == 0 && ws.zero64 && tid >= 64 && tid < 128) ws.zero64[tid - 64] = 0.0;
+    if (p.has_bias) {                    // zero the bias chunk (two K pieces)
+      uint4* bz = reinterpret_cast<uint4*>(w_s) + (size_t)(K8 - 2) * N;
+      for (int i = tid; i < 2 * N; i += PGT_THREADS) bz[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    bf16* img = reinterpret_cast<bf16*>(w_s);
+    // 16-byte loads of the fp32 weights (a thread owns 4 consecutive output columns - or, transposed, 4 consecutive
+    // K rows - of one row), all of a thread's loads issued before the first use.  The shift-into-bias partial sums go
+    // through a scratch array in the (still idle) first TMA stage and are added in a FIXED order: every CTA must
+    // build bit-identical images (atomics would make a sample's result depend on which CTA computed it).
+    float* part_s = reinterpret_cast<float*>(a_s);                    // [PGT_THREADS][4]
+    const int N4 = N >> 2, total4 = (K * N) >> 2;
+    constexpr int MAXIT = 4;                                          // K*N <= 4*4*PGT_THREADS elements (launcher checks)
+    float4 wv[MAXIT];
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) {
+      const int i = tid + it * PGT_THREADS;
+      wv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < total4) {
+        if (ws.transposed) { const int k4 = i & 7, r = i >> 3, n = r % N, q = r / N; wv[it] = __ldg(reinterpret_cast<const float4*>(ws.W + ws.w_off[q] + n * ws.ld + 4 * k4)); }
+        else { const int n4 = i % N4, k = i / N4; wv[it] = __ldg(reinterpret_cast<const float4*>(ws.W + ws.w_off[k >> 5] + (k & 31) * ws.ld + 4 * n4)); }
+      }
+    }
+    float part[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) {
+      const int i = tid + it * PGT_THREADS;
+      if (i < total4) {
+        const float raw[4] = {wv[it].x, wv[it].y, wv[it].z, wv[it].w};
+        if (ws.transposed) {
+          const int k4 = i & 7, r = i >> 3, n = r % N, q = r / N, k = q * 32 + 4 * k4;
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(raw[0] * sc_s[4 * k4], raw[1] * sc_s[4 * k4 + 1]);
+          __nv_bfloat162 h1 = __floats2bfloat162_rn(raw[2] * sc_s[4 * k4 + 2], raw[3] * sc_s[4 * k4 + 3]);
+          uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+          *reinterpret_cast<uint2*>(img + ((size_t)(k >> 3) * N + n) * 8 + (k & 7)) = pk;
+        } else {
+          const int n4 = i % N4, k = i / N4, kk = k & 31;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int n = 4 * n4 + j;
+            float val = raw[j] * sc_s[kk];
+            if (ws.half_odd && (n & 1)) val *= 0.5f;
+            img[((size_t)(k >> 3) * N + n) * 8 + (k & 7)] = __float2bfloat16_rn(val);
+            part[j] = fmaf(sc_s[32 + kk], raw[j], part[j]);
+          }
+        }
+      }
+    }
+    if (ws.bn && !ws.transposed) *reinterpret_cast<float4*>(part_s + 4 * tid) = make_float4(part[0], part[1], part[2], part[3]);
+    __syncthreads();
+    if (p.has_bias) {
+      for (int n = tid; n < N; n += PGT_THREADS) {
+        float b = ws.bias ? __ldg(ws.bias + n) : 0.f;
+        if (ws.bn && !ws.transposed) {
+          // threads t with t % N4 == n/4 hold the partials of column n (PGT_THREADS % N4 == 0: launcher checks)
+          float acc = 0.f;
+          for (int t = n >> 2; t < PGT_THREADS; t += N4) acc += part_s[4 * t + (n & 3)];
+          b += acc;
+        }
+        if (ws.half_odd && (n & 1)) b *= 0.5f;
+        const bf16 hi = __float2bfloat16_rn(b);
+        const bf16 lo = __float2bfloat16_rn(b - __bfloat162float(hi));
+        bf16* d0 = img + ((size_t)(K8 - 2) * N + n) * 8;
+        d0[0] = hi; d0[1] = lo;
+      }
+    }
+    __syncthreads();      // part_s lives in the first TMA stage: the producer may only start after the bias is read
+  }
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -307,7 +411,7 @@ int launch_pos_gemm_tc(PgParams& p, const Epi& epi, cudaStream_t st) {
   const int sms = tg_sm_count();
   const int acc_c = p.N <= 32 ? 32 : p.N <= 64 ? 64 : p.N <= 128 ? 128 : 256;
   const size_t w_bytes = ((size_t)(p.n_chunks * 4 + (p.has_bias ? 2 : 0)) * p.N * 16 + 1023) & ~(size_t)1023;
-  const size_t fixed = w_bytes + PGT_ONES_BYTES + 1024 + 512;
+  const size_t fixed = w_bytes + PGT_ONES_BYTES + 1024 + 1024;   // alignment slack + barriers / statistics / fold scratch
   GWN_REQUIRE(fixed + 2 * (size_t)NB * 8192 <= 227 * 1024, "pos_gemm_tc: K=%d does not fit 2 stages in shared memory",
               32 * p.n_chunks);
   p.tiles_per_n = (int)cdiv(p.rows_out, 128);                     // 128-row sub-tiles per (virtual) sample
@@ -363,6 +467,13 @@ int launch_pos_gemm_tc(PgParams& p, const Epi& epi, cudaStream_t st) {
   }
   const size_t a_bytes = (size_t)NB * 8192 * p.sub;
   const size_t smem = fixed + stages * a_bytes;
+  if (p.wsrc.W) {
+    GWN_REQUIRE(32 * p.n_chunks * p.N <= 16 * PGT_THREADS && p.N % 4 == 0 && p.wsrc.ld % 4 == 0,
+                "pos_gemm_tc: weight image %d x %d too large for the in-kernel build", 32 * p.n_chunks, p.N);
+    GWN_REQUIRE(!p.wsrc.bn || (!p.wsrc.transposed && PGT_THREADS % (p.N / 4) == 0 && a_bytes >= 16 * PGT_THREADS),
+                "pos_gemm_tc: BatchNorm fold needs N/4 to divide the CTA size");
+    GWN_REQUIRE((reinterpret_cast<unsigned long long>(p.wsrc.W) & 15ull) == 0, "pos_gemm_tc: weights must be 16-byte aligned");
+  }
   const int grid = p.n_tiles < sms ? p.n_tiles : sms;
   if constexpr (Epi::kFast > 0)
     if (p.n_chunks == Epi::kFast) return pos_gemm_tc_run<Epi, Epi::kFast>(maps, p, epi, stages, n_acc, grid, smem, st);

@@ -263,12 +263,8 @@ def _sup_array(supports: Sequence[Tensor]):
     return arr
 
 
-@torch.library.custom_op('gwn::layer_fwd', mutates_args=())
-def layer_fwd(u_prev: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], w_fg: Tensor, b_fg: Tensor,
-              w_mlp: Optional[Tensor], b_mlp: Optional[Tensor], supports: List[Tensor],
-              drop_mask: Optional[Tensor], rng: Optional[Tensor], hop_mats: Optional[Tensor], Lf: int, taps: int,
-              dilation: int, order: int, training: bool, has_gconv: bool, dropout_p: float, seed: int, offset: int
-              ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+def _layer_fwd_impl(u_prev, scale, shift, w_fg, b_fg, w_mlp, b_mlp, supports, drop_mask, rng, hop_mats, Lf, taps,
+                    dilation, order, training, has_gconv, dropout_p, seed, offset, bn=None):
     _req(u_prev, None, 'u_prev'); _req(w_fg, torch.float32, 'w_fg'); _req(b_fg, torch.float32, 'b_fg')
     for s in supports:
         _req(s, torch.float32, 'support')
@@ -299,9 +295,59 @@ def layer_fwd(u_prev: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], 
                         a=_p(a) if training else None,
                         b=_p(b) if training else None, z_last=_p(z_last), u=_p(u) if has_gconv else None,
                         stats=_p(stats), ws_cat=_p(ws_cat))
+    if bn is not None:
+        bn_stats, count, gamma, beta, rmean, rvar, momentum, eps, mean, rstd = bn
+        for t, nm in ((gamma, 'bn.weight'), (beta, 'bn.bias'), (rmean, 'running_mean'), (rvar, 'running_var')):
+            _req(t, torch.float32, nm)
+        args.bn_stats, args.bn_gamma, args.bn_beta = _p(bn_stats), _p(gamma), _p(beta)
+        args.bn_running_mean, args.bn_running_var = _p(rmean), _p(rvar)
+        args.bn_mean, args.bn_rstd = _p(mean), _p(rstd)
+        args.bn_count, args.bn_momentum, args.bn_eps = float(count), float(momentum), float(eps)
     with torch.cuda.device(dev):
         check(lib().gwn_layer_fwd(C.byref(cfg), C.byref(args), _stream()), 'gwn_layer_fwd')
     return u, stats, z_last, a, b
+
+
+@torch.library.custom_op('gwn::layer_fwd', mutates_args=())
+def layer_fwd(u_prev: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], w_fg: Tensor, b_fg: Tensor,
+              w_mlp: Optional[Tensor], b_mlp: Optional[Tensor], supports: List[Tensor],
+              drop_mask: Optional[Tensor], rng: Optional[Tensor], hop_mats: Optional[Tensor], Lf: int, taps: int,
+              dilation: int, order: int, training: bool, has_gconv: bool, dropout_p: float, seed: int, offset: int
+              ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    return _layer_fwd_impl(u_prev, scale, shift, w_fg, b_fg, w_mlp, b_mlp, supports, drop_mask, rng, hop_mats, Lf, taps,
+                           dilation, order, training, has_gconv, dropout_p, seed, offset)
+
+
+@torch.library.custom_op('gwn::layer_fwd_bn', mutates_args=('rmean', 'rvar'))
+def layer_fwd_bn(u_prev: Tensor, bn_stats: Optional[Tensor], count: float, gamma: Tensor, beta: Tensor, rmean: Tensor,
+                 rvar: Tensor, momentum: float, eps: float, w_fg: Tensor, b_fg: Tensor,
+                 w_mlp: Optional[Tensor], b_mlp: Optional[Tensor], supports: List[Tensor],
+                 drop_mask: Optional[Tensor], rng: Optional[Tensor], hop_mats: Tensor, Lf: int, taps: int,
+                 dilation: int, order: int, training: bool, has_gconv: bool, dropout_p: float, seed: int, offset: int
+                 ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """layer_fwd with the previous layer's BatchNorm (graph_wavenet.py:250) folded inside the gate kernel's prologue
+    (bf16 tensor-core path): batch statistics `bn_stats` [2,32] (training) or the running statistics (eval) ->
+    scale / shift / mean / rstd come back as outputs, the running statistics are updated in place."""
+    f32 = dict(device=u_prev.device, dtype=torch.float32)
+    scale, shift, mean, rstd = (torch.empty((CH,), **f32) for _ in range(4))
+    if training:
+        _req(bn_stats, torch.float64, 'bn_stats')
+    out = _layer_fwd_impl(u_prev, scale, shift, w_fg, b_fg, w_mlp, b_mlp, supports, drop_mask, rng, hop_mats, Lf, taps,
+                          dilation, order, training, has_gconv, dropout_p, seed, offset,
+                          bn=(bn_stats if training else None, count, gamma, beta, rmean, rvar, momentum, eps, mean, rstd))
+    return (*out, scale, shift, mean, rstd)
+
+
+@layer_fwd_bn.register_fake
+def _(u_prev, bn_stats, count, gamma, beta, rmean, rvar, momentum, eps, w_fg, b_fg, w_mlp, b_mlp, supports, drop_mask,
+      rng, hop_mats, Lf, taps, dilation, order, training, has_gconv, dropout_p, seed, offset):
+    N, Lin, V, _c = u_prev.shape
+    Lout = Lin - dilation * (taps - 1)
+    full = (N, Lout, V, CH)
+    v = lambda: u_prev.new_empty((CH,), dtype=torch.float32)  # noqa: E731
+    return (u_prev.new_empty(full if has_gconv else (0,)), u_prev.new_empty((2, CH), dtype=torch.float64),
+            u_prev.new_empty((N, Lf, V, CH)), u_prev.new_empty(full if training else (0,)),
+            u_prev.new_empty(full if training else (0,)), v(), v(), v(), v())
 
 
 @layer_fwd.register_fake
@@ -402,13 +448,21 @@ class WaveNetLayer(torch.autograd.Function):
         has_bn = gamma is not None
         scale = shift = mean = rstd = None
         count = float(u_prev.numel() // CH)
-        if has_bn:
-            scale, shift, mean, rstd = bn_fold(stats_prev if training else None, count, gamma, beta, rmean, rvar,
-                                               m['momentum'], m['eps'], training)
         sup = [s.contiguous() for s in supports]
-        u, stats, z_last, a, b = layer_fwd(u_prev, scale, shift, w_fg, b_fg, w_mlp, b_mlp, sup, drop_mask, rng,
-                                           hop_mats, m['Lf'], m['taps'], m['dilation'], m['order'], training,
-                                           m['has_gconv'], m['dropout_p'], m['seed'], m['offset'])
+        # bf16 tensor-core path: the BatchNorm fold happens inside the gate kernel's prologue (no fold / prep launch)
+        fused_bn = has_bn and u_prev.dtype == torch.bfloat16 and hop_mats is not None and m['taps'] <= 4
+        if fused_bn:
+            u, stats, z_last, a, b, scale, shift, mean, rstd = layer_fwd_bn(
+                u_prev, stats_prev if training else None, count, gamma, beta, rmean, rvar, m['momentum'], m['eps'],
+                w_fg, b_fg, w_mlp, b_mlp, sup, drop_mask, rng, hop_mats, m['Lf'], m['taps'], m['dilation'], m['order'],
+                training, m['has_gconv'], m['dropout_p'], m['seed'], m['offset'])
+        else:
+            if has_bn:
+                scale, shift, mean, rstd = bn_fold(stats_prev if training else None, count, gamma, beta, rmean, rvar,
+                                                   m['momentum'], m['eps'], training)
+            u, stats, z_last, a, b = layer_fwd(u_prev, scale, shift, w_fg, b_fg, w_mlp, b_mlp, sup, drop_mask, rng,
+                                               hop_mats, m['Lf'], m['taps'], m['dilation'], m['order'], training,
+                                               m['has_gconv'], m['dropout_p'], m['seed'], m['offset'])
         ctx.set_materialize_grads(False)      # a dead output (last layer's u) must stay "no gradient"
         ctx.meta = m
         ctx.count = count
