@@ -109,14 +109,27 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gcn_fwd_kernel(const __grid_con
   }
   if (warp == GF_MMA) tmem_alloc(tmem_slot, 512);
   {  // resident operands: support images (rows < Kp of each K piece) and the mlp weight image
-    const int per_piece = Kp;                       // 16-byte rows kept per K piece
-    const int pieces = Kp / 8;
-    for (int m = 0; m < nm; ++m) {
-      const uint4* src = reinterpret_cast<const uint4*>(p.mats) + (size_t)p.mat_src[m] * pieces * 128;
-      uint4* dst = reinterpret_cast<uint4*>(smem + (size_t)m * L.mat_bytes);
-      for (int i = tid; i < pieces * per_piece; i += GF_THREADS) {
-        const int kc = i / per_piece, r = i % per_piece;
-        dst[kc * per_piece + r] = __ldg(src + kc * 128 + r);
+    constexpr int per_piece = Kp;                   // 16-byte rows kept per K piece
+    constexpr int pieces = Kp / 8;
+    {   // all matrices in one flat loop, 4 independent 16-byte loads in flight per thread
+      constexpr int per_mat = pieces * per_piece, total = NM * per_mat;
+      const uint4* src0 = reinterpret_cast<const uint4*>(p.mats);
+      uint4* dst0 = reinterpret_cast<uint4*>(smem);
+      for (int i0 = tid; i0 < total; i0 += 4 * GF_THREADS) {
+        uint4 v[4]; int di[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = i0 + q * GF_THREADS;
+          di[q] = -1;
+          if (i < total) {
+            const int m = i / per_mat, e = i - m * per_mat, kc = e / per_piece, r = e - kc * per_piece;
+            v[q] = __ldg(src0 + (size_t)p.mat_src[m] * pieces * 128 + kc * 128 + r);
+            di[q] = m * (int)(L.mat_bytes / 16) + kc * per_piece + r;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (di[q] >= 0) dst0[di[q]] = v[q];
       }
     }
     if (p.w_src) {       // bf16 UMMA image of the mlp weight built here: (k = c, n = (j, c')) = W[j*32 + c][c']

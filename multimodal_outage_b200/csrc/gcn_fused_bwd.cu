@@ -107,12 +107,25 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
   if (warp == GB_MMA) tmem_alloc(tmem_slot, 512);
   {  // resident operands
     constexpr int pieces = Kp / 8;
-    for (int m = 0; m < NM; ++m) {
-      const uint4* src = reinterpret_cast<const uint4*>(p.mats) + (size_t)p.mat_src[m] * pieces * 128;
-      uint4* dst = reinterpret_cast<uint4*>(smem + (size_t)m * L.mat_bytes);
-      for (int i = tid; i < pieces * Kp; i += GB_THREADS) {
-        const int kc = i / Kp, r = i % Kp;
-        dst[kc * Kp + r] = __ldg(src + kc * 128 + r);
+    {   // all matrices in one flat loop, 4 independent 16-byte loads in flight per thread
+      constexpr int per_mat = pieces * Kp, total = NM * per_mat;
+      const uint4* src0 = reinterpret_cast<const uint4*>(p.mats);
+      uint4* dst0 = reinterpret_cast<uint4*>(smem);
+      for (int i0 = tid; i0 < total; i0 += 4 * GB_THREADS) {
+        uint4 v[4]; int di[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = i0 + q * GB_THREADS;
+          di[q] = -1;
+          if (i < total) {
+            const int m = i / per_mat, e = i - m * per_mat, kc = e / Kp, r = e - kc * Kp;
+            v[q] = __ldg(src0 + (size_t)p.mat_src[m] * pieces * 128 + kc * 128 + r);
+            di[q] = m * (int)(L.mat_bytes / 16) + kc * Kp + r;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (di[q] >= 0) dst0[di[q]] = v[q];
       }
     }
     if (p.w_src) {       // bf16 UMMA images of the mlp weight built here (see gcn_bwd_wprep_kernel for the layouts)
