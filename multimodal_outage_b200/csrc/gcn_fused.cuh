@@ -42,9 +42,14 @@ struct GcnFwdParams {
   int V, Kp, slabs;
   const float* w_src;          // optional: packed fp32 mlp weight [32*(1+n_mats)][32]; the kernel builds its bf16 image itself (w_img unused)
   long long* trace;            // optional debug: [64 slabs][8] clock64 timestamps of CTA 0 (NULL = off)
+  const bf16* mats_t;          // T-form kernel (gcn_fused_t.cu): stacked support image [KT/8][NP][8]; KT, NP filled by the launcher
+  int KT, NP;
 };
 
 int gcn_fused_supported(int V, int n_mats);
+// transposed contraction over groups of four slabs (gcn_fused_t.cu); needs w_src and mats_t
+int gcn_fused_t_supported(int V, int n_mats);
+int launch_gcn_fwd_t(GcnFwdParams& p, cudaStream_t st);
 // builds w_img from the packed fp32 mlp weight [32*(1+n_mats), 32]
 int launch_gcn_wprep(const float* w_mlp, int n_mats, bf16* w_img, cudaStream_t st);
 int launch_gcn_fwd(GcnFwdParams& p, cudaStream_t st);

@@ -611,6 +611,12 @@ static const bf16* big_image(const gwn_layer_cfg* c, const void* hop_mats, int s
   return reinterpret_cast<const bf16*>(hop_mats) + ((long long)s * 2 + which) * c->V * Vp;
 }
 
+static bool gcn_t_enabled() {       // GWN_GCN_T=0 keeps the node-major fused forward (A/B measurements)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GWN_GCN_T"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
 static bool fused_gcn_enabled() {   // GWN_NO_FUSED_GCN=1 keeps the unfused kernels (A/B measurements only)
   static int v = -1;
   if (v < 0) { const char* e = getenv("GWN_NO_FUSED_GCN"); v = (e && e[0] == '1') ? 0 : 1; }
@@ -751,6 +757,11 @@ static int layer_fwd_t(const gwn_layer_cfg* c, const gwn_layer_fwd_args* g, cuda
       fp.mask = c->training ? reinterpret_cast<const bf16*>(g->drop_mask) : nullptr;
       fp.drop_p = c->training ? c->dropout_p : 0.f; fp.seed = c->seed; fp.offset = c->offset; fp.rng = g->rng;
       fp.u = reinterpret_cast<bf16*>(g->u); fp.stats = g->stats; fp.V = c->V; fp.slabs = c->N * c->Lout;
+      if (gcn_t_enabled() && gcn_fused_t_supported(c->V, fp.n_mats)) {      // transposed contraction over groups of 4 slabs
+        const int Kp = ((c->V + 15) / 16) * 16;
+        fp.mats_t = reinterpret_cast<const bf16*>(g->hop_mats) + (size_t)c->n_supports * 4 * (Kp / 8) * 1024;
+        return launch_gcn_fwd_t(fp, st);
+      }
       return launch_gcn_fwd(fp, st);
     }
   }
@@ -1095,6 +1106,11 @@ extern "C" int gwn_gcn_fwd(const void* z, const void* u_prev, const float* scale
   {  // debug timeline: GWN_GCN_TRACE=<device pointer of 64*8 int64> (scripts/gpu_gcn_trace.py)
     const char* e = getenv("GWN_GCN_TRACE");
     fp.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
+  }
+  if (gcn_t_enabled() && gcn_fused_t_supported(V, fp.n_mats)) {
+    const int Kp = ((V + 15) / 16) * 16;
+    fp.mats_t = reinterpret_cast<const bf16*>(hop_mats) + (size_t)n_supports * 4 * (Kp / 8) * 1024;
+    return launch_gcn_fwd_t(fp, st);
   }
   return launch_gcn_fwd(fp, st);
 }

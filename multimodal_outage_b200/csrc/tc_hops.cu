@@ -219,6 +219,33 @@ __global__ void hop_mats_prep_kernel(MatPrep mp, bf16* __restrict__ out) {
   }
 }
 
+// Stacked support image of the transposed ("T-form") fused forward (gcn_fused_t.cu): the B operand of
+//   h^T[(s,c), w] = sum_{j,v} U_j[(s,v), c] * Mt_j[v, w],   k = j*V + v,   Mt_0 = I, Mt_{2s+1} = A_s, Mt_{2s+2} = A_s A_s
+// K-major no-swizzle canonical layout [KT/8][NP][8] bf16 (rows = output node w), zero padded.
+__global__ void hop_mats_t_prep_kernel(MatPrep mp, int KT, int NP, bf16* __restrict__ out) {
+  const int total = KT * NP;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int e = i & 7, w = (i >> 3) % NP, k = (i >> 3) / NP * 8 + e;
+    const int j = k / mp.V, v = k - j * mp.V;
+    float val = 0.f;
+    if (w < mp.V && j <= 2 * mp.n) {
+      if (j == 0) {
+        val = (v == w) ? 1.f : 0.f;
+      } else {
+        const float* A = mp.A[(j - 1) >> 1];
+        if (((j - 1) & 1) == 0) {
+          val = A[(long long)v * mp.V + w];
+        } else {
+          float acc = 0.f;
+          for (int t = 0; t < mp.V; ++t) acc = fmaf(A[(long long)v * mp.V + t], A[(long long)t * mp.V + w], acc);
+          val = acc;
+        }
+      }
+    }
+    out[i] = __float2bfloat16_rn(val);
+  }
+}
+
 static int g_sm_count = 0;
 
 int hops_tc_supported(int V, int n_mats) {
@@ -264,9 +291,12 @@ int launch_hops_tc(HopParams& p, cudaStream_t st) {
 
 using namespace gwn;
 
+static int hop_mats_t_kt(int V, int n_supports) { return (((1 + 2 * n_supports) * V + 15) / 16) * 16; }
+
+// the 4 n images [Kp/8][128][8] followed by the stacked T-form image [KT/8][NP][8]
 extern "C" int gwn_hop_mats_bytes(int V, int n_supports) {
   int Kp = ((V + 15) / 16) * 16;
-  return n_supports * 4 * (Kp / 8) * 2048;
+  return n_supports * 4 * (Kp / 8) * 2048 + hop_mats_t_kt(V, n_supports) * Kp * 2;
 }
 
 extern "C" int gwn_hop_mats_prep(const float* const* supports, int n_supports, int V, void* out, void* stream) {
@@ -278,6 +308,10 @@ extern "C" int gwn_hop_mats_prep(const float* const* supports, int n_supports, i
   long long total = (long long)n_supports * 4 * (mp.Kp / 8) * 1024;
   hop_mats_prep_kernel<<<(unsigned)cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       mp, reinterpret_cast<bf16*>(out));
+  GWN_LAUNCHED();
+  const int KT = hop_mats_t_kt(V, n_supports);
+  hop_mats_t_prep_kernel<<<(unsigned)cdiv((long long)KT * mp.Kp, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      mp, KT, mp.Kp, reinterpret_cast<bf16*>(out) + total);
   GWN_LAUNCHED();
   return 0;
 }

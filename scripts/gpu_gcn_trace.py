@@ -26,6 +26,9 @@ t = trace.cpu().reshape(64, 8)
 t0 = t[0, 1].item()
 print('marks relative to kernel begin: after_prologue, kernel_end, first mma_U_start:', [t[63, i].item() - t[63, 0].item() for i in (1, 2)], t0 - t[63, 0].item())
 names = ['prod_issued', 'mma_U_start', 'mma_U_issued', 'mma_hops_issued', 'stage_start', 'stage_end', 'epi_start', 'epi_end']
+if os.environ.get('GWN_GCN_T', '1') != '0':
+    names = ['mma_grp_start', 'mma_g1_issued', 'mma_got_a_full', 'mma_g2_issued', 'stage_start', 'stage_end', 'epi_got_d', 'epi_end']
+    t0 = t[0, 0].item()
 print('slab ' + ' '.join(f'{n:>15s}' for n in names))
 for k in range(0, 42):
     if t[k, 1].item() == 0:
