@@ -176,7 +176,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '20'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -281,11 +281,11 @@ def kernel_rooflines(peaks, n):
     ms = graph_time([gcn(i) for i in range(R)])
     flops = P * (6 * 2.0 * C32 * V + 2.0 * 224 * 32)
     byts = 3.0 * P * 64
-    roof = {'kernel': 'gcn_fwd_kernel (fused K-hop diffusion + concat + mlp + dropout + residual + BN stats, config-2 '
-                      'layer 0: 6144 slabs of 67 nodes; includes its 2 us weight-image prep + stats memset)',
+    roof = {'kernel': 'gcn_fwd_t_kernel (fused K-hop diffusion + concat + mlp + dropout + residual + BN stats, transposed '
+                      'contraction over groups of 4 slabs; config-2 layer 0: 6144 slabs of 67 nodes; includes the stats memset)',
             'bound': 'hbm', 'achieved': byts / (ms * 1e-3) / 1e9, 'peak': peak_bw, 'unit': 'GB/s',
-            'frac': byts / (ms * 1e-3) / 1e9 / peak_bw, 'traffic': traffic.get('gcn_fwd_kernel', {}).get('bytes'),
-            'traffic_source': traffic.get('gcn_fwd_kernel', {}).get('source'),
+            'frac': byts / (ms * 1e-3) / 1e9 / peak_bw, 'traffic': traffic.get('gcn_fwd_t_kernel', {}).get('bytes'),
+            'traffic_source': traffic.get('gcn_fwd_t_kernel', {}).get('source'),
             'algorithmic_bytes_per_launch': byts, 'algorithmic_flops_per_launch': flops, 'ms_per_launch': ms,
             'tensor_tflops': flops / (ms * 1e-3) / 1e12, 'tensor_frac_of_burst_peak': flops / (ms * 1e-3) / 1e12 / peak_tf,
             'note': 'at V=67 the fused contraction has 209 flop/B, right at the ridge (214): HBM time 12.1 us, tensor '
@@ -310,7 +310,7 @@ def kernel_rooflines(peaks, n):
     byts_b = 5.0 * P * 64
     roof_bwd = {'kernel': 'gcn_bwd_kernel (fused diffusion backward: dropout mask, 6 transposed hops, mlp data + weight '
                           'gradients, adaptive-support gradient, gate backward; config-2 layer 0: 6144 slabs of 67 nodes; '
-                          'includes its weight-image prep + memsets)',
+                          'includes its output memsets)',
                 'bound': 'hbm', 'achieved': byts_b / (ms_b * 1e-3) / 1e9, 'peak': peak_bw, 'unit': 'GB/s',
                 'frac': byts_b / (ms_b * 1e-3) / 1e9 / peak_bw, 'traffic': traffic.get('gcn_bwd_kernel', {}).get('bytes'),
                 'traffic_source': traffic.get('gcn_bwd_kernel', {}).get('source'),
@@ -318,8 +318,9 @@ def kernel_rooflines(peaks, n):
                 'tensor_tflops': flops_b / (ms_b * 1e-3) / 1e12, 'tensor_frac_of_burst_peak': flops_b / (ms_b * 1e-3) / 1e12 / peak_tf,
                 'note': 'algorithmic bytes = read du, a, b + write dfg (5 x 64 B per position); 71 kflop per position -> 222 '
                         'flop/B, at the ridge like the forward: HBM time 20 us, tensor time 21 us.  The kernel is bound by '
-                        'the issue rate of its 65 small-N tcgen05.mma per slab (59 cycles each, smem-operand bound) and by '
-                        'TMEM->smem hand-offs (DESIGN.md section 3, scripts/gpu_gcn_bwd_trace.py)', 'peak_source': src}
+                        'its 65 small-N tcgen05.mma per slab (43 cycles each: the 128-row A operand read from shared '
+                        'memory) and by TMEM->smem hand-offs (DESIGN.md section 3, scripts/gpu_gcn_bwd_trace.py); the '
+                        'transposed form the forward already uses is the planned fix', 'peak_source': src}
     del dus, aas, bbs, dfgs
 
     # ---- gated temporal conv (layer 0, inference form: read r once, write z once)
@@ -334,8 +335,8 @@ def kernel_rooflines(peaks, n):
     ms_gate = graph_time([gate(i) for i in range(R)])
     bytes_alg = (N * 32 * V * L[0] + N * 32 * V * L[1]) * 2.0
     gbs = bytes_alg / (ms_gate * 1e-3) / 1e9
-    gate_roof = {'kernel': 'pos_gemm_tc_kernel<EpiGateTC> (gated dilated conv fwd, config-2 layer 0; includes its weight-'
-                           'image prep launch)', 'bound': 'hbm', 'achieved': gbs, 'peak': peak_bw, 'unit': 'GB/s',
+    gate_roof = {'kernel': 'pos_gemm_tc_kernel<EpiGateTC> (gated dilated conv fwd, config-2 layer 0, eval form: read r once, '
+                           'write z once; weight image built in the prologue)', 'bound': 'hbm', 'achieved': gbs, 'peak': peak_bw, 'unit': 'GB/s',
                  'frac': gbs / peak_bw, 'traffic': None, 'algorithmic_bytes_per_launch': bytes_alg,
                  'ms_per_launch': ms_gate, 'peak_source': src}
 
@@ -564,8 +565,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
-    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')

@@ -237,7 +237,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gcn_fwd_t_kernel(const __grid_c
         tc_fence_after();
         uint8_t* arow = smem + L.a_off + (size_t)(s * 4) * KT * 16 + (size_t)v * 16;
         uint32_t ra[32], rb[32];
-        for (int j = set; j <= NM; j += 4) {
+        const bool warp_has_rows = 128 * t + q * 32 < ns * V;       // (the third tile holds 4V - 256 rows: most warps skip it)
+        for (int j = set; warp_has_rows && j <= NM; j += 4) {
           const int j2 = j + 2;
           tmem_ld32_issue(tmem_base + lane_off + TU + (uint32_t)j * 32u, ra);
           if (j2 <= NM) tmem_ld32_issue(tmem_base + lane_off + TU + (uint32_t)j2 * 32u, rb);
