@@ -700,3 +700,44 @@ def test_param_packing_layouts_and_gradient_unpacking():
     assert m.end_conv_1.weight.grad[70, 5, 0, 0] == R['w_end1'][5, 70]
     assert m.end_conv_2.weight.grad[11, 50, 0, 0] == R['w_end2'][50, 11]
     assert torch.equal(m.end_conv_2.bias.grad, R['b_end2'][:12])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('V,n_sup,N,Lout,Lin', [(67, 3, 3, 3, 4), (67, 3, 1, 13, 13), (20, 3, 5, 2, 3), (64, 2, 2, 3, 3),
+                                                 (68, 3, 2, 2, 4), (33, 1, 3, 3, 3), (5, 3, 7, 1, 2)])
+def test_fused_forward_kernel_shapes_against_torch(V, n_sup, N, Lout, Lin):
+    """The fused diffusion forward (transposed form where it fits) on shapes that exercise its edges: groups of four
+    slabs with a ragged tail, node counts around the 16/32/64 column splits, 1-3 supports.  Reference: the same
+    contraction in fp32 torch on the bf16-rounded inputs (u = mlp(concat hops) + b + residual*scale + shift)."""
+    from multimodal_outage_b200 import _lib, ops
+    lib = _lib.lib()
+    torch.manual_seed(V * 100 + n_sup)
+    dev, bf = 'cuda', torch.bfloat16
+    sups = [torch.softmax(torch.randn(V, V, device=dev), dim=1).contiguous() for _ in range(n_sup)]
+    mats = ops.hop_mats(sups)
+    H = 2 * n_sup
+    z = torch.randn(N, Lout, V, 32, device=dev).to(bf)
+    up = torch.randn(N, Lin, V, 32, device=dev).to(bf)
+    u = torch.zeros(N, Lout, V, 32, device=dev, dtype=bf)
+    w_mlp = (torch.randn(32 * (1 + H), 32, device=dev) / (32 * (1 + H)) ** 0.5).contiguous()
+    b_mlp = torch.randn(32, device=dev)
+    scale, shift = torch.rand(32, device=dev) + 0.5, torch.randn(32, device=dev)
+    ws_w = torch.empty(65536, device=dev, dtype=torch.uint8)
+    stats = torch.zeros(64, device=dev, dtype=torch.float64)
+    _lib.check(lib.gwn_gcn_fwd(z.data_ptr(), up.data_ptr(), scale.data_ptr(), shift.data_ptr(), mats.data_ptr(), n_sup,
+                               w_mlp.data_ptr(), b_mlp.data_ptr(), ws_w.data_ptr(), 0.0, 1, 0, u.data_ptr(), stats.data_ptr(),
+                               N, V, Lin, Lout, torch.cuda.current_stream().cuda_stream), 'gwn_gcn_fwd')
+    torch.cuda.synchronize()
+    zf = z.float()
+    cat = [zf]
+    for A in sups:                                            # y[w] = sum_v x[v] A[v, w], then once more (graph_wavenet.py:87-93)
+        y1 = torch.einsum('nlvc,vw->nlwc', zf, A)
+        cat += [y1, torch.einsum('nlvc,vw->nlwc', y1, A)]
+    h = torch.cat(cat, dim=-1) @ w_mlp + b_mlp
+    ref = h + up.float()[:, Lin - Lout:] * scale + shift
+    assert rel(u.float(), ref) < BF16_TOL, rel(u.float(), ref)
+    cnt = N * Lout * V
+    got_mean = (stats[:32] / cnt).float()
+    assert torch.allclose(got_mean, ref.mean(dim=(0, 1, 2)), atol=3e-2), (got_mean - ref.mean(dim=(0, 1, 2))).abs().max()
+    got_sq = (stats[32:] / cnt).float()
+    assert rel(got_sq, (ref * ref).mean(dim=(0, 1, 2))) < 3e-2
