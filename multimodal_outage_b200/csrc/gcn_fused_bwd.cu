@@ -11,7 +11,7 @@
 //                                               accumulator stays in TMEM for the CTA's whole share of slabs)
 //   epilogue : TMEM(dz) + dz_last -> gate backward with a, b -> dfg (bf16, 128 B per node)
 // TMEM columns: dU [0, 32H), dz [192, 224), dW tiles [224, 256) and [256, 288).
-// Warps (16): q0/q1: stage A (w0,w1), stage B (w4,w5), epilogue (w8,w9); q2: stage w6, epilogue w10; q3: MMA w3.
+// Warps (16): q0/q1: stage A (w0,w1), stage B (w4,w5), epilogue (w8,w9); q2: stage w6,w14, epilogue w10; q3: MMA w3 (stage w7,w11 when Kp > 96).
 // The three prep warps (w12, w13, w15) are not tied to a TMEM lane quadrant; they finish ALL their arithmetic (mask,
 // products, bf16 packing) in registers BEFORE waiting for the buffer, so a freed buffer is refilled in ~100 cycles.
 #include "gcn_fused.cuh"
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
 
   const int nq_stage = (Kp + 31) / 32;
   const int nq_epi = (V + 31) / 32;
-  const int n_stage_warps = 2 * min(nq_stage, 2) + max(0, nq_stage - 2);
+  const int n_stage_warps = 2 * nq_stage;        // two per quadrant that holds node rows
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -362,11 +362,14 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
     }
     const float s = warp_column_sums(dbs, lane);
     atomicAdd(p.db_mlp + lane, s);
-  } else if ((quad < 2 && wq < 2) || (quad == 2 && wq == 1)) {
+  } else if ((quad < 2 && wq < 2) || warp == 6 || warp == 14 || warp == 7 || warp == 11) {
     // ===================== stage warps: TMEM(dU_j) -> bf16 -> slots 1..H =====================
+    // two per quadrant (q0: w0,w4  q1: w1,w5  q2: w6,w14  q3: w7,w11), splitting the hop chunks even / odd: the
+    // TMEM round trips of one warp are serial, so a lone warp doing all H chunks of its quadrant was the last to arrive
     if (quad < nq_stage) {
       const int row = quad * 32 + lane;
-      const int first = (quad < 2) ? 1 + wq : 1, step = (quad < 2) ? 2 : 1;
+      const int sidx = (quad < 2) ? wq : ((warp == 6 || warp == 7) ? 0 : 1);
+      const int first = 1 + sidx, step = 2;
       const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
       int k = 0;
       for (long long slab = blockIdx.x; slab < p.slabs; slab += gridDim.x, ++k) {
@@ -388,7 +391,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
             }
           }
         };
-        const bool does_u6 = DA && (quad >= 2 || wq == 0), does_t1 = DA && (quad >= 2 || wq == 1);
+        const bool does_u6 = DA && sidx == 0, does_t1 = DA && sidx == 1;
         if (does_u6) {       // U6 first: it is ready before the hops of this slab finish
           mbar_wait(u56_full, (uint32_t)(k & 1));
           tc_fence_after();

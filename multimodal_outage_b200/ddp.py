@@ -54,10 +54,17 @@ class BucketedGradAllReduce:
         self.plan = plan_buckets(model)
         self.buckets = []
         self._owner: Dict[torch.nn.Parameter, int] = {}
+        # the buckets are consecutive slices of ONE flat tensor: the overlapped (eager) mode reduces them one by one as they
+        # complete, the CUDA-graph mode reduces the whole tensor with a single collective
+        sizes = [sum(params[n].numel() for n in names) for names in self.plan]
+        dev = params[self.plan[0][0]].device
+        self.flat_all = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        start = 0
         for bi, names in enumerate(self.plan):
             ps = [params[n] for n in names]
-            total = sum(p.numel() for p in ps)
-            flat = torch.zeros(total, dtype=torch.float32, device=ps[0].device)
+            total = sizes[bi]
+            flat = self.flat_all[start:start + total]
+            start += total
             views, off = [], 0
             for p in ps:
                 views.append(flat[off:off + p.numel()].view_as(p))
@@ -111,10 +118,12 @@ class BucketedGradAllReduce:
     def reduce(self):
         """All-reduce (average) the packed buckets in place."""
         if self.world > 1:
-            works = [dist.all_reduce(b['flat'], op=dist.ReduceOp.SUM, group=self.group, async_op=True) for b in self.buckets]
-            for w in works:
-                w.wait()
-            torch._foreach_div_([b['flat'] for b in self.buckets], float(self.world))
+            # one collective over the concatenated buckets; NCCL averages in the reduction itself
+            if dist.get_backend(self.group) == 'nccl':
+                dist.all_reduce(self.flat_all, op=dist.ReduceOp.AVG, group=self.group)
+            else:
+                dist.all_reduce(self.flat_all, op=dist.ReduceOp.SUM, group=self.group)
+                self.flat_all.div_(float(self.world))
 
     def grad_bytes(self) -> int:
         return sum(b['flat'].numel() * 4 for b in self.buckets)
