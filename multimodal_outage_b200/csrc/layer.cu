@@ -126,6 +126,7 @@ struct EpiGateTC {   // N = 64 interleaved (f,g); a chunk of 32 columns = 16 cha
   // the accumulator already holds f + bias and (g + bias) / 2: the bias rides in the GEMM (has_bias) and the weight
   // image's g columns are pre-halved (half_odd), so sigmoid(g) = 0.5 tanh(acc) + 0.5
   static constexpr bool kExtra = false;
+  static constexpr bool kWgrad = false;
   static constexpr int kFast = 2;
   bf16* z; bf16* a; bf16* b; bf16* z_last; long long last_begin, last_rows;
   __device__ __forceinline__ void chunk(long long p, long long n, long long rem, bool valid, int c0, float v[32]) {
@@ -148,6 +149,7 @@ struct EpiGateTC {   // N = 64 interleaved (f,g); a chunk of 32 columns = 16 cha
 
 struct EpiMlpTC {    // N = 32: (bias in the GEMM) dropout + residual(BN-folded input) -> u, per-channel (sum, sum^2)
   static constexpr bool kExtra = false;
+  static constexpr bool kWgrad = false;
   static constexpr int kFast = 0;
   const bf16* u_prev; long long prev_rows_per_n, crop; const float* scale; const float* shift;
   const bf16* mask; float drop_p; uint64_t seed, offset; const uint64_t* rng;
@@ -208,6 +210,7 @@ struct EpiMlpTC {    // N = 32: (bias in the GEMM) dropout + residual(BN-folded 
 
 struct EpiSlotTC {   // 32-column chunk c0 -> slot c0/32 of a slot-major buffer
   static constexpr bool kExtra = false;
+  static constexpr bool kWgrad = false;
   static constexpr int kFast = 1;
   bf16* out; long long slot_stride;
   __device__ __forceinline__ void chunk(long long p, long long, long long, bool valid, int c0, float v[32]) {
@@ -220,14 +223,32 @@ struct EpiSlotTC {   // 32-column chunk c0 -> slot c0/32 of a slot-major buffer
   __device__ __forceinline__ void flush(const float*, int) {}
 };
 
-struct EpiGateBwdTC {   // N = 32: dx = acc + du(cropped rows); (sum dx, sum dx*u_prev)
+template <bool WG>
+struct EpiGateBwdTC {   // N = 32: dx = acc + du(cropped rows); (sum dx, sum dx*u_prev); WG: fused gate weight gradient
   // du and u_prev rows of the tile arrive by TMA as two extra 64B-swizzled [128 rows][64 B] tiles (the du tile is
   // zero-filled outside the cropped range), so the epilogue never waits on a global load.  The 32 columns are
   // processed as two halves of 16 (keeps the live registers under the 96 the 640-thread CTA allows).
   static constexpr bool kExtra = true;
+  static constexpr bool kWgrad = WG;
   static constexpr int kFast = 4;
   float* dx; double* stats;
   float s1[2], s2[2];
+  // fused weight gradient (tc_gemm_impl.cuh): accumulator row c of chunk q = (tap j, half h) -> dw_fg[(j*32 + c), 32h + n],
+  // with the BatchNorm fold of the layer input (dW' = scale[c] dW + shift[c] db[n]); ones row -> db_fg
+  const float* wg_scale; const float* wg_shift; float* dw_fg; float* db_fg;
+  __device__ __forceinline__ void wgrad_row(int q, int c, const float v[32], const float* db_s, float* stg) const {
+    const float sc = wg_scale ? __ldg(wg_scale + c) : 1.f, sh = wg_scale ? __ldg(wg_shift + c) : 0.f;
+    float* dst = stg + (size_t)((q >> 1) * 32 + c) * 64 + 32 * (q & 1);
+#pragma unroll
+    for (int n = 0; n < 32; n += 4)
+      *reinterpret_cast<float4*>(dst + n) =
+          make_float4(fmaf(sc, v[n], sh * db_s[32 * (q & 1) + n]), fmaf(sc, v[n + 1], sh * db_s[32 * (q & 1) + n + 1]),
+                      fmaf(sc, v[n + 2], sh * db_s[32 * (q & 1) + n + 2]), fmaf(sc, v[n + 3], sh * db_s[32 * (q & 1) + n + 3]));
+  }
+  __device__ __forceinline__ void wgrad_flush(const float* stg, const float* db_s, int n_chunks, int t, int nthr) const {
+    red_flush_2d(dw_fg, 64, stg, 64, (n_chunks >> 1) * 32, 64, t, nthr);
+    red_flush_1d(db_fg, db_s, 64, t, nthr);
+  }
   __device__ __forceinline__ void chunk_ex(long long p, long long, long long, bool valid, int, float v[32],
                                            const uint8_t* extra, int r) {
     const int lane = threadIdx.x & 31;
@@ -609,6 +630,12 @@ static int tc_mode(const gwn_layer_cfg* c, const void* hop_mats) {
 static const bf16* big_image(const gwn_layer_cfg* c, const void* hop_mats, int s, int which) {
   const long long Vp = ((c->V + 7) / 8) * 8;
   return reinterpret_cast<const bf16*>(hop_mats) + ((long long)s * 2 + which) * c->V * Vp;
+}
+
+static bool fused_gate_wgrad_enabled() {   // GWN_FUSED_WGRAD=0 keeps the separate weight-gradient launch (A/B measurements)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GWN_FUSED_WGRAD"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
 }
 
 static bool gcn_t_enabled() {       // GWN_GCN_T=0 keeps the node-major fused forward (A/B measurements)
@@ -1008,6 +1035,8 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
     ch.base = g->u_prev; ch.rows_per_n = RI; ch.row_off = (long long)j * c->dilation * c->V;
     ch.pitch = 32; ch.col_off = 0; ch.scale = g->scale; ch.shift = g->shift;
   }
+  // k = 2 taps: the gate weight gradient is fused into the data-gradient GEMM below (same dfg / u_prev tiles)
+  const bool fuse_wg = tc_gate && g->ws_w != nullptr && c->taps == 2 && fused_gate_wgrad_enabled();
   if (tc_gate) {
     if constexpr (std::is_same<T, bf16>::value) {
       if (!g->outputs_zeroed) GWN_CUDA(cudaMemsetAsync(g->dw_fg, 0, sizeof(float) * 64 * 32 * c->taps, st));
@@ -1018,7 +1047,8 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
         w.ch[j] = WgChunk{reinterpret_cast<const bf16*>(g->u_prev), RI, (long long)j * c->dilation * c->V, 32, 0};
       w.G = dfg16; w.g_pitch = 64; w.N = 64; w.dW = g->dw_fg; w.ldw = 64; w.db = g->db_fg;
       w.scale = g->scale; w.shift = g->shift;
-      if (int rc = launch_wgrad_tc(w, st)) return rc;
+      if (!fuse_wg)
+        if (int rc = launch_wgrad_tc(w, st)) return rc;
     }
   } else {
     if (int rc = launch_wgrad<T, float>(A, g->ws_dfg, 64, 0, g->dw_fg, 64, g->db_fg, st)) return rc;
@@ -1047,14 +1077,21 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
       for (int j = 0; j < c->taps; ++j)
         for (int h = 0; h < 2; ++h)
           pg.ch[2 * j + h] = PgChunk{dfg16, RO, -(long long)j * c->dilation * c->V, 64, h * 32};
-      EpiGateBwdTC eb2{};
-      eb2.dx = g->dx_prev; eb2.stats = g->dx_stats; eb2.s1[0] = eb2.s1[1] = eb2.s2[0] = eb2.s2[1] = 0.f;
       // extra tiles for the epilogue: du shifted by the crop (zero outside), u_prev
       pg.n_extra = 2;
       // (no du for the last layer: a row offset far past the sample makes TMA zero-fill the whole tile)
       pg.ch[2 * c->taps] = du ? PgChunk{du, RO, -(long long)(c->Lin - c->Lout) * c->V, 32, 0}
                               : PgChunk{reinterpret_cast<const bf16*>(g->u_prev), RI, (long long)1 << 28, 32, 0};
       pg.ch[2 * c->taps + 1] = PgChunk{reinterpret_cast<const bf16*>(g->u_prev), RI, 0, 32, 0};
+      if (fuse_wg) {
+        EpiGateBwdTC<true> eb2{};
+        eb2.dx = g->dx_prev; eb2.stats = g->dx_stats; eb2.s1[0] = eb2.s1[1] = eb2.s2[0] = eb2.s2[1] = 0.f;
+        eb2.wg_scale = g->scale; eb2.wg_shift = g->shift; eb2.dw_fg = g->dw_fg; eb2.db_fg = g->db_fg;
+        return launch_pos_gemm_tc(pg, eb2, st);
+      }
+      EpiGateBwdTC<false> eb2{};
+      eb2.dx = g->dx_prev; eb2.stats = g->dx_stats; eb2.s1[0] = eb2.s1[1] = eb2.s2[0] = eb2.s2[1] = 0.f;
+      eb2.wg_scale = nullptr; eb2.wg_shift = nullptr; eb2.dw_fg = nullptr; eb2.db_fg = nullptr;
       return launch_pos_gemm_tc(pg, eb2, st);
     }
   }

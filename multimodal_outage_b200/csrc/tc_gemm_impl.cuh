@@ -17,6 +17,12 @@
 
 namespace gwn {
 
+// Optional fused weight gradient (Epi::kWgrad, used by the gate data-gradient GEMM): the tile's chunk boxes (dfg of tap j,
+// half h: [128 rows][32 cols]) and its second "extra" box (u_prev rows of the same tile) are exactly the operands of
+//     dW[(j, c), n] += sum_rows u_prev[row][c] * dfg_j[row][n]              (graph_wavenet.py:222-224 weight gradient)
+// so the MMA warp issues, per chunk, 8 more MMAs (K = 128 rows) with both boxes viewed MN-major (SWIZZLE_64B atoms) into a
+// 128-column accumulator that stays in TMEM for the CTA's whole share; a resident "ones" atom behind the u_prev box adds
+// the bias gradient as accumulator row 32.  The CTA's partial is flushed once at the end (staged, rotated, vectorised).
 // warps: 0 and 2 = TMA producers (one thread each, on different schedulers; they split a tile's boxes),
 // 1 = MMA issuer, 3 idle, 4-19 = epilogue (four per TMEM lane quadrant = per scheduler)
 constexpr int PGT_PROD_A = 0, PGT_MMA_WARP = 1, PGT_PROD_B = 2;
@@ -98,10 +104,12 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
   const int K8 = n_chunks * 4 + (p.has_bias ? 2 : 0);        // 16-byte K pieces per weight row
   const int SUB = p.sub;
   const int NB = n_chunks + p.n_extra;                         // TMA boxes per sub-tile (MMA chunks + epilogue extras)
-  const uint32_t a_bytes = (uint32_t)NB * 8192u * (uint32_t)SUB;   // one stage: SUB x NB boxes of 128 x 64 B
+  // one stage: SUB x NB boxes of 128 x 64 B (+ the resident ones atom of the fused weight gradient, SUB == 1 there)
+  const uint32_t a_bytes = ((uint32_t)NB * (uint32_t)SUB + (Epi::kWgrad ? 1u : 0u)) * 8192u;
   const uint32_t w_bytes = ((uint32_t)K8 * (uint32_t)N * 16u + 1023u) & ~1023u;
   uint8_t* a_s = smem;                                        // stages first (1024-aligned boxes)
-  uint8_t* w_s = smem + (size_t)stages * a_bytes;
+  // (kWgrad: 16 KB of slack after the ring - the M = 128 weight-gradient MMA of the last stage reads two atoms past the ones atom)
+  uint8_t* w_s = smem + (size_t)stages * a_bytes + (Epi::kWgrad ? 16384 : 0);
   uint8_t* ones_s = w_s + w_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ones_s + PGT_ONES_BYTES);
   uint64_t* full = bars;               // [stages] (<= 8)
@@ -109,6 +117,7 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
   uint64_t* tfull = bars + 16;         // [n_acc] (<= 4)
   uint64_t* tempty = bars + 20;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  uint64_t* wfull = bars + 25;         // fused weight gradient: all MMAs of the CTA completed
   float* red_s = reinterpret_cast<float*>(bars + 32);        // [64] CTA-level statistics scratch
   (void)a_s;
   if (tid < 64) red_s[tid] = 0.f;
@@ -117,15 +126,31 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
     // a stage is free when the MMAs have read it and (with extras) every epilogue thread is done with it
     for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], p.n_extra ? 1 + 32 * PGT_EPI_WARPS : 1); }
     for (int i = 0; i < n_acc; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 32 * PGT_EPI_WARPS); }
+    mbar_init(wfull, 1);
     fence_barrier_init();
   }
   const uint32_t acc_cols = N <= 32 ? 32u : N <= 64 ? 64u : N <= 128 ? 128u : 256u;
   const uint32_t buf_cols = acc_cols * (uint32_t)SUB;          // one accumulator buffer: SUB sub-tiles side by side
-  if (warp == PGT_MMA_WARP) tmem_alloc(tmem_slot, (uint32_t)n_acc * buf_cols);
+  const uint32_t tmem_cols = Epi::kWgrad ? 256u : (uint32_t)n_acc * buf_cols;      // (kWgrad: 4 x 32 accumulators + 128 dW columns)
+  if (warp == PGT_MMA_WARP) tmem_alloc(tmem_slot, tmem_cols);
   {
     // ones tile: element (row, k) = 1 for k < 2 (the two bias rows), else 0
     uint4* od = reinterpret_cast<uint4*>(ones_s);
     for (int i = tid; i < 256; i += PGT_THREADS) od[i] = i < 128 ? make_uint4(0x3F803F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  if constexpr (Epi::kWgrad) {
+    // ones atom behind the u_prev box of every stage: element (position k, channel 0) = 1.0; 64B swizzle puts logical
+    // 16-byte chunk 0 of row k at physical chunk ((k >> 1) & 3).  TMA never writes it.
+    for (int st = 0; st < stages; ++st) {
+      uint4* atom = reinterpret_cast<uint4*>(a_s + (size_t)st * a_bytes + (size_t)NB * 8192);
+      for (int i = tid; i < 512; i += PGT_THREADS) atom[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    for (int st = 0; st < stages; ++st) {
+      uint8_t* atom = a_s + (size_t)st * a_bytes + (size_t)NB * 8192;
+      for (int k = tid; k < 128; k += PGT_THREADS)
+        *reinterpret_cast<uint16_t*>(atom + k * 64 + ((k >> 1) & 3) * 16) = 0x3F80u;   // bf16 1.0
+    }
   }
   if (p.wsrc.W == nullptr) {
     const uint4* src = reinterpret_cast<const uint4*>(p.w_img);
@@ -315,13 +340,33 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
               }
             }
           }
-          umma_commit(&empty[stage]);
           umma_commit(&tfull[acc]);
+          if constexpr (Epi::kWgrad) {
+            // dW[(chunk q, c), n] += u_prev^T dfg_q over the tile's 128 rows (both boxes viewed MN-major, SW64 atoms: LBO =
+            // next 32-channel atom, SBO = next 8 positions, K = 16 step = 1024 B); accumulator row 32 = ones row = bias grad
+            const uint32_t sb = base + (uint32_t)stage * a_bytes;
+            const uint64_t wt = tg::make_desc_sw(0, 8192u, 512u, 4u);
+            const uint32_t idw = make_idesc_bf16(128, 32, true, true);
+            const uint64_t au = wt + (uint64_t)((sb + (uint32_t)(NB - 1) * 8192u) >> 4);       // u_prev box, then the ones atom
+#pragma unroll
+            for (int q = 0; q < (NCH > 0 ? NCH : 1); ++q) {
+              const uint64_t bq = wt + (uint64_t)((sb + (uint32_t)q * 8192u) >> 4);
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks)
+                umma_bf16(tmem_base + 128u + 32u * (uint32_t)q, au + (uint64_t)(ks * 64), bq + (uint64_t)(ks * 64), idw,
+                          (g == 0 && ks == 0) ? 0u : 1u);
+            }
+          }
+          umma_commit(&empty[stage]);
         }
         __syncwarp();
         if (lane == 0) PG_TRACE(4);
         ++g;
         if (++stage == stages) { stage = 0; sphase ^= 1; }
+      }
+      if constexpr (Epi::kWgrad) {
+        if (elect_one()) umma_commit(wfull);
+        __syncwarp();
       }
     }
   } else if (warp >= PGT_EPI_WARP0) {
@@ -368,6 +413,28 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
       w.advance();
       if (++stage == stages) stage = 0;
     }
+    if constexpr (Epi::kWgrad) {
+      // ---- flush of the fused weight gradient: quadrant 0 holds rows c = 0..31 of every chunk, lane 0 of quadrant 1 the
+      // ones row (bias gradient).  rank = chunk.  Staged in the (idle) first TMA stage, then one rotated vector flush.
+      asm volatile("bar.sync 4, 512;" ::: "memory");              // every epilogue warp is done with the stages' extra boxes
+      if (quad < 2) {
+        float* stg = reinterpret_cast<float*>(a_s);                 // [n_chunks*16... rows (chunk>>1)*32 + c][64] fp32
+        float* db_s = stg + 4096 * 2;                               // [64] bias gradient (taps <= 4 -> <= 8192 floats above)
+        const int et = (quad * PGT_EPI_RANKS + rank) * 32 + lane;   // 0..255
+        mbar_wait(wfull, 0u);
+        tc_fence_after();
+        float v[32];
+        if (rank < n_chunks) tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + 128u + 32u * (uint32_t)rank, v);
+        if (quad == 1 && rank < 2 && lane == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) db_s[32 * rank + j] = v[j];
+        }
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        if (quad == 0 && rank < n_chunks) epi.wgrad_row(rank, lane, v, db_s, stg);
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        epi.wgrad_flush(stg, db_s, n_chunks, et, 256);
+      }
+    }
     epi.finish(red_s);
   }
   tc_fence_before();
@@ -375,7 +442,7 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
   if (warp == 0) epi.flush(red_s, lane);
   if (warp == PGT_MMA_WARP) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)n_acc * buf_cols);
+    tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -411,9 +478,12 @@ int launch_pos_gemm_tc(PgParams& p, const Epi& epi, cudaStream_t st) {
   const int sms = tg_sm_count();
   const int acc_c = p.N <= 32 ? 32 : p.N <= 64 ? 64 : p.N <= 128 ? 128 : 256;
   const size_t w_bytes = ((size_t)(p.n_chunks * 4 + (p.has_bias ? 2 : 0)) * p.N * 16 + 1023) & ~(size_t)1023;
-  const size_t fixed = w_bytes + PGT_ONES_BYTES + 1024 + 1024;   // alignment slack + barriers / statistics / fold scratch
-  GWN_REQUIRE(fixed + 2 * (size_t)NB * 8192 <= 227 * 1024, "pos_gemm_tc: K=%d does not fit 2 stages in shared memory",
-              32 * p.n_chunks);
+  const size_t fixed = w_bytes + PGT_ONES_BYTES + 1024 + 1024 + (Epi::kWgrad ? 16384 : 0);   // alignment slack + barriers / scratch
+  GWN_REQUIRE(fixed + 2 * (size_t)(NB + (Epi::kWgrad ? 1 : 0)) * 8192 <= 227 * 1024,
+              "pos_gemm_tc: K=%d does not fit 2 stages in shared memory", 32 * p.n_chunks);
+  if (Epi::kWgrad)
+    GWN_REQUIRE(p.n_chunks == Epi::kFast && p.n_extra == 2 && p.N == 32 && p.n_chunks <= 4,
+                "pos_gemm_tc: the fused weight gradient needs %d chunks of 32 columns and the (du, u_prev) extras", Epi::kFast);
   p.tiles_per_n = (int)cdiv(p.rows_out, 128);                     // 128-row sub-tiles per (virtual) sample
   const long long sub_tiles = (long long)p.n_samples * p.tiles_per_n;
   // macro tiles: several 128-row sub-tiles per pipeline step amortise the hand-offs; the choice also looks at the
@@ -422,8 +492,8 @@ int launch_pos_gemm_tc(PgParams& p, const Epi& epi, cudaStream_t st) {
   double eff_of[3] = {-1, -1, -1}, best_eff = -1;
   for (int i = 0; i < 3; ++i) {
     const int sub = subs[i];
-    if (2 * acc_c * sub > 512) continue;
-    const size_t ab = (size_t)NB * 8192 * sub;
+    if (2 * acc_c * sub > 512 || (Epi::kWgrad && sub > 1)) continue;
+    const size_t ab = (size_t)NB * 8192 * sub + (Epi::kWgrad ? 8192 : 0);
     int stg = (int)((227 * 1024 - fixed) / ab);
     if (stg > 8) stg = 8;
     if (stg < (sub == 1 ? 2 : 3)) continue;
@@ -465,7 +535,7 @@ int launch_pos_gemm_tc(PgParams& p, const Epi& epi, cudaStream_t st) {
     const char* e = getenv("GWN_PG_TRACE");
     p.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
   }
-  const size_t a_bytes = (size_t)NB * 8192 * p.sub;
+  const size_t a_bytes = (size_t)NB * 8192 * p.sub + (Epi::kWgrad ? 8192 : 0);
   const size_t smem = fixed + stages * a_bytes;
   if (p.wsrc.W) {
     GWN_REQUIRE(32 * p.n_chunks * p.N <= 16 * PGT_THREADS && p.N % 4 == 0 && p.wsrc.ld % 4 == 0,
