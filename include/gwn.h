@@ -138,7 +138,7 @@ typedef struct {
   const void* du;               /* [N,Lout,V,32] (dtype) or NULL (dead gconv: last layer) */
   const void* dz_last;          /* [N,Lf,V,32] (dtype) or NULL */
   /* outputs */
-  float* dx_prev;               /* [N,Lin,V,32] fp32: grad wrt r = bn_prev(u_prev) */
+  void* dx_prev;                /* [N,Lin,V,32] grad wrt r = bn_prev(u_prev): fp32, or bf16 when dx_prev_bf16 != 0 */
   double* dx_stats;             /* [2,32]: sum dx, sum dx*u_prev (zeroed by callee) */
   float* dw_fg; float* db_fg;   /* [taps*32,64], [64] (overwritten) */
   float* dw_mlp; float* db_mlp; /* packed [mlp_in, 32], [32] (overwritten) */
@@ -148,6 +148,8 @@ typedef struct {
   void* ws_dcat;                /* [P, mlp_in] (dtype): grads of the concat */
   float* ws_dfg;                /* [P, 64] fp32 */
   int outputs_zeroed;           /* != 0: the caller already zeroed dx_stats, dw_*, db_* (one fill instead of six memsets) */
+  int dx_prev_bf16;             /* != 0 (bf16 tensor-core path only): dx_prev is stored as bf16 - it only lives until the
+                                   BatchNorm backward reads it; its statistics are taken from the fp32 accumulator */
 } gwn_layer_bwd_args;
 
 int gwn_layer_bwd(const gwn_layer_cfg* cfg, const gwn_layer_bwd_args* args, void* stream);
@@ -180,7 +182,7 @@ int gwn_bn_fold(const double* stats, double count, const float* gamma, const flo
                 float* scale, float* shift, float* mean, float* rstd, void* stream);
 /* du = BN backward of dx (grad wrt BN output) given u, mean, rstd and dx_stats=(sum dx, sum dx*u).
  * training=0: du = dx*scale.  dgamma,dbeta [32] overwritten.  du has dtype `dtype`. */
-int gwn_bn_bwd(const float* dx, const void* u, int dtype, const double* dx_stats, double count,
+int gwn_bn_bwd(const void* dx, int dx_dtype, const void* u, int dtype, const double* dx_stats, double count,
                const float* gamma, const float* mean, const float* rstd, int training,
                void* du, float* dgamma, float* dbeta, long long rows, void* stream);
 

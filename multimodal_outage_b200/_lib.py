@@ -40,7 +40,8 @@ class LayerBwdArgs(C.Structure):
                 ('supports', vp * MAX_SUPPORTS), ('support_needs_grad', C.c_int * MAX_SUPPORTS),
                 ('drop_mask', vp), ('rng', vp), ('hop_mats', vp), ('ws_w', vp), ('a', vp), ('b', vp), ('du', vp), ('dz_last', vp), ('dx_prev', vp),
                 ('dx_stats', vp), ('dw_fg', vp), ('db_fg', vp), ('dw_mlp', vp), ('db_mlp', vp),
-                ('d_supports', vp * MAX_SUPPORTS), ('ws_cat', vp), ('ws_dcat', vp), ('ws_dfg', vp), ('outputs_zeroed', C.c_int)]
+                ('d_supports', vp * MAX_SUPPORTS), ('ws_cat', vp), ('ws_dcat', vp), ('ws_dfg', vp), ('outputs_zeroed', C.c_int),
+                ('dx_prev_bf16', C.c_int)]
 
 
 class HeadCfg(C.Structure):
@@ -104,7 +105,7 @@ SIGNATURES = {
     'gwn_gcn_fwd': (_i, [vp, vp, vp, vp, vp, _i, vp, vp, vp, _f, C.c_uint64, C.c_uint64, vp, vp, _i, _i, _i, _i, vp]),
     'gwn_gcn_bwd': (_i, [vp, vp, vp, vp, vp, _i, vp, vp, _f, C.c_uint64, C.c_uint64, _i, vp, vp, vp, vp, _i, _i, _i, _i, vp]),
     'gwn_bn_fold': (_i, [vp, _d, vp, vp, vp, vp, _f, _f, _i, vp, vp, vp, vp, vp]),
-    'gwn_bn_bwd': (_i, [vp, vp, _i, vp, _d, vp, vp, vp, _i, vp, vp, vp, _ll, vp]),
+    'gwn_bn_bwd': (_i, [vp, _i, vp, _i, vp, _d, vp, vp, vp, _i, vp, vp, vp, _ll, vp]),
     'gwn_head_fwd': (_i, [C.POINTER(HeadCfg), C.POINTER(HeadFwdArgs), vp]),
     'gwn_head_bwd': (_i, [C.POINTER(HeadCfg), C.POINTER(HeadBwdArgs), vp]),
     'gwn_head_tc_ws_bytes': (_ll, [_i, _i, _i, _i]),

@@ -119,12 +119,12 @@ struct CvtJobs { CvtJob j[3]; int n; };
 __global__ void cvt_weights_kernel(CvtJobs jobs) {
   for (int q = 0; q < jobs.n; ++q) {
     const CvtJob J = jobs.j[q];
-    const long long total = (long long)J.R * J.C;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-      const int r = (int)(i / J.C), c = (int)(i % J.C);
-      const float x = J.src[i];
+    const int total = J.R * J.C;            // (weights: far below 2^31; 32-bit index math - a 64-bit division costs hundreds of cycles)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+      const int r = i / J.C, c = i - r * J.C;
+      const float x = __ldg(J.src + i);
       const bf16 hi = __float2bfloat16_rn(x);
-      const long long o = J.transpose ? (long long)c * J.ld + r : (long long)r * J.ld + c;
+      const int o = J.transpose ? c * J.ld + r : r * J.ld + c;
       J.dst[o] = hi;
       if (J.lo_off >= 0) J.dst[o + J.lo_off] = __float2bfloat16_rn(x - __bfloat162float(hi));
       if (J.hi2_off >= 0) J.dst[o + J.hi2_off] = hi;
@@ -229,7 +229,7 @@ extern "C" int gwn_head_fwd_tc(const gwn_head_cfg* c, const gwn_head_tc_fwd_args
   jobs.j[0] = CvtJob{a->w_skip, wsT, K0, S, 1, 2 * K0p, K0p, -1};
   jobs.j[1] = CvtJob{a->w_end1, w1T, S, E, 1, 3 * S, 2 * S, S};
   jobs.j[2] = CvtJob{a->w_end2, w2T, E, Opad, 1, E, -1, -1};
-  cvt_weights_kernel<<<64, 256, 0, st>>>(jobs);
+  cvt_weights_kernel<<<592, 256, 0, st>>>(jobs);
   GWN_LAUNCHED();
   TgParams p; CUtensorMap ma, mb;
   {   // x1 = zcat.(Ws_hi + Ws_lo): the A operand is read twice (k wraps at K0p)
@@ -273,7 +273,7 @@ extern "C" int gwn_head_bwd_tc(const gwn_head_cfg* c, const gwn_head_tc_bwd_args
   jobs.j[0] = CvtJob{a->w_skip, ws, K0, S, 0, S, -1, -1};
   jobs.j[1] = CvtJob{a->w_end1, w1, S, E, 0, E, -1, -1};
   jobs.j[2] = CvtJob{a->w_end2, w2, E, Opad, 0, Opad, -1, -1};
-  cvt_weights_kernel<<<64, 256, 0, st>>>(jobs);
+  cvt_weights_kernel<<<592, 256, 0, st>>>(jobs);
   GWN_LAUNCHED();
   if (!a->outputs_zeroed) {
   GWN_CUDA(cudaMemsetAsync(a->dw_skip, 0, sizeof(float) * (size_t)K0 * S, st));

@@ -231,7 +231,8 @@ struct EpiGateBwdTC {   // N = 32: dx = acc + du(cropped rows); (sum dx, sum dx*
   static constexpr bool kExtra = true;
   static constexpr bool kWgrad = WG;
   static constexpr int kFast = 4;
-  float* dx; double* stats;
+  float* dx; bf16* dx16;          // exactly one of the two: fp32 or bf16 storage of dx
+  double* stats;
   float s1[2], s2[2];
   // fused weight gradient (tc_gemm_impl.cuh): accumulator row c of chunk q = (tap j, half h) -> dw_fg[(j*32 + c), 32h + n],
   // with the BatchNorm fold of the layer input (dW' = scale[c] dW + shift[c] db[n]); ones row -> db_fg
@@ -274,8 +275,11 @@ struct EpiGateBwdTC {   // N = 32: dx = acc + du(cropped rows); (sum dx, sum dx*
             up[8 * cc + 2 * i + 1] = __uint_as_float(wu[i] & 0xFFFF0000u);
           }
         }
+        if (dx16) store_bf16x16(dx16 + p * 32 + 16 * h, vh);
+        else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) store4(dx + p * 32 + 16 * h + 4 * j, vh + 4 * j);
+          for (int j = 0; j < 4; ++j) store4(dx + p * 32 + 16 * h + 4 * j, vh + 4 * j);
+        }
 #pragma unroll
         for (int c = 0; c < 16; ++c) up[c] *= vh[c];
       } else {
@@ -562,8 +566,8 @@ __global__ void bn_fold_kernel(const double* stats, double count, const float* g
   if (mean_out) { mean_out[c] = mean; rstd_out[c] = rstd; }
 }
 
-template <typename T>
-__global__ void bn_bwd_kernel(const float* __restrict__ dx, const T* __restrict__ u, const double* dx_stats,
+template <typename T, typename DX>
+__global__ void bn_bwd_kernel(const DX* __restrict__ dx, const T* __restrict__ u, const double* dx_stats,
                               double count, const float* gamma, const float* mean, const float* rstd,
                               int training, T* __restrict__ du, float* dgamma, float* dbeta, long long rows) {
   __shared__ float k0[32], k1[32], k2[32];  // du = k0*dx + k1*u + k2
@@ -585,13 +589,13 @@ __global__ void bn_bwd_kernel(const float* __restrict__ dx, const T* __restrict_
   }
   __syncthreads();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * 8) return;
-  long long p = i >> 3; int c = (int)(i & 7) * 4;
-  float g[4], uv[4];
-  load4(dx + p * 32 + c, g); load4(u + p * 32 + c, uv);
+  if (i >= rows * 4) return;
+  long long p = i >> 2; int c = (int)(i & 3) * 8;       // a thread owns 8 channels of a position
+  float g[8], uv[8];
+  load8(dx + p * 32 + c, g); load8(u + p * 32 + c, uv);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) g[j] = k0[c + j] * g[j] + k1[c + j] * uv[j] + k2[c + j];
-  store4(du + p * 32 + c, g);
+  for (int j = 0; j < 8; ++j) g[j] = k0[c + j] * g[j] + k1[c + j] * uv[j] + k2[c + j];
+  store8(du + p * 32 + c, g);
 }
 
 // ------------------------------------------------------------------------------------------ orchestration
@@ -1065,7 +1069,9 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
   if (!g->outputs_zeroed) GWN_CUDA(cudaMemsetAsync(g->dx_stats, 0, sizeof(double) * 64, st));
   EpiGateBwdData<T> ex{};
   ex.stats = g->dx_stats; ex.du = du; ex.du_rows_per_n = RO; ex.crop = (long long)(c->Lin - c->Lout) * c->V;
-  ex.u_prev = reinterpret_cast<const T*>(g->u_prev); ex.dx = g->dx_prev;
+  ex.u_prev = reinterpret_cast<const T*>(g->u_prev); ex.dx = reinterpret_cast<float*>(g->dx_prev);
+  GWN_REQUIRE(!g->dx_prev_bf16 || (tc_gate && g->ws_w != nullptr && 2 * c->taps <= PG_TC_MAX_CHUNKS),
+              "layer_bwd: bf16 dx_prev needs the tensor-core data-gradient GEMM");
   if (tc_gate && g->ws_w != nullptr && 2 * c->taps <= PG_TC_MAX_CHUNKS) {
     if constexpr (std::is_same<T, bf16>::value) {
       // the (transposed) gate weight image of this GEMM is built by the kernel's own prologue (tc_gemm.cuh: PgWsrc)
@@ -1085,12 +1091,16 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
       pg.ch[2 * c->taps + 1] = PgChunk{reinterpret_cast<const bf16*>(g->u_prev), RI, 0, 32, 0};
       if (fuse_wg) {
         EpiGateBwdTC<true> eb2{};
-        eb2.dx = g->dx_prev; eb2.stats = g->dx_stats; eb2.s1[0] = eb2.s1[1] = eb2.s2[0] = eb2.s2[1] = 0.f;
+        eb2.dx = g->dx_prev_bf16 ? nullptr : reinterpret_cast<float*>(g->dx_prev);
+        eb2.dx16 = g->dx_prev_bf16 ? reinterpret_cast<bf16*>(g->dx_prev) : nullptr;
+        eb2.stats = g->dx_stats; eb2.s1[0] = eb2.s1[1] = eb2.s2[0] = eb2.s2[1] = 0.f;
         eb2.wg_scale = g->scale; eb2.wg_shift = g->shift; eb2.dw_fg = g->dw_fg; eb2.db_fg = g->db_fg;
         return launch_pos_gemm_tc(pg, eb2, st);
       }
       EpiGateBwdTC<false> eb2{};
-      eb2.dx = g->dx_prev; eb2.stats = g->dx_stats; eb2.s1[0] = eb2.s1[1] = eb2.s2[0] = eb2.s2[1] = 0.f;
+      eb2.dx = g->dx_prev_bf16 ? nullptr : reinterpret_cast<float*>(g->dx_prev);
+      eb2.dx16 = g->dx_prev_bf16 ? reinterpret_cast<bf16*>(g->dx_prev) : nullptr;
+      eb2.stats = g->dx_stats; eb2.s1[0] = eb2.s1[1] = eb2.s2[0] = eb2.s2[1] = 0.f;
       eb2.wg_scale = nullptr; eb2.wg_shift = nullptr; eb2.dw_fg = nullptr; eb2.db_fg = nullptr;
       return launch_pos_gemm_tc(pg, eb2, st);
     }
@@ -1202,19 +1212,24 @@ extern "C" int gwn_bn_fold(const double* stats, double count, const float* gamma
   return 0;
 }
 
-extern "C" int gwn_bn_bwd(const float* dx, const void* u, int dtype, const double* dx_stats, double count,
+extern "C" int gwn_bn_bwd(const void* dx, int dx_dtype, const void* u, int dtype, const double* dx_stats, double count,
                           const float* gamma, const float* mean, const float* rstd, int training, void* du,
                           float* dgamma, float* dbeta, long long rows, void* stream) {
   GWN_REQUIRE(dx && u && dx_stats && gamma && mean && rstd && du && dgamma && dbeta, "bn_bwd: NULL argument");
+  GWN_REQUIRE((dx_dtype == GWN_F32 || dx_dtype == GWN_BF16) && (dtype == GWN_F32 || dtype == GWN_BF16) &&
+                  !(dx_dtype == GWN_BF16 && dtype == GWN_F32), "bn_bwd: bad dtype combination");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  unsigned blocks = (unsigned)cdiv(rows * 8, 256);
+  unsigned blocks = (unsigned)cdiv(rows * 4, 256);
   if (blocks == 0) blocks = 1;
   if (dtype == GWN_F32)
-    bn_bwd_kernel<float><<<blocks, 256, 0, st>>>(dx, (const float*)u, dx_stats, count, gamma, mean, rstd, training,
-                                                 (float*)du, dgamma, dbeta, rows);
+    bn_bwd_kernel<float, float><<<blocks, 256, 0, st>>>((const float*)dx, (const float*)u, dx_stats, count, gamma, mean, rstd,
+                                                        training, (float*)du, dgamma, dbeta, rows);
+  else if (dx_dtype == GWN_F32)
+    bn_bwd_kernel<bf16, float><<<blocks, 256, 0, st>>>((const float*)dx, (const bf16*)u, dx_stats, count, gamma, mean, rstd,
+                                                       training, (bf16*)du, dgamma, dbeta, rows);
   else
-    bn_bwd_kernel<bf16><<<blocks, 256, 0, st>>>(dx, (const bf16*)u, dx_stats, count, gamma, mean, rstd, training,
-                                                (bf16*)du, dgamma, dbeta, rows);
+    bn_bwd_kernel<bf16, bf16><<<blocks, 256, 0, st>>>((const bf16*)dx, (const bf16*)u, dx_stats, count, gamma, mean, rstd,
+                                                      training, (bf16*)du, dgamma, dbeta, rows);
   GWN_LAUNCHED();
   return 0;
 }

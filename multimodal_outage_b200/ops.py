@@ -232,12 +232,12 @@ def _(stats, count, gamma, beta, running_mean, running_var, momentum, eps, train
 @torch.library.custom_op('gwn::bn_bwd', mutates_args=())
 def bn_bwd(dx: Tensor, u: Tensor, dx_stats: Tensor, count: float, gamma: Tensor, mean: Tensor, rstd: Tensor,
            training: bool) -> Tuple[Tensor, Tensor, Tensor]:
-    _req(dx, torch.float32, 'dx'); _req(u, None, 'u')
+    _req(dx, None, 'dx'); _req(u, None, 'u')
     du = torch.empty_like(u)
     dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(gamma)
     rows = u.numel() // CH
     with torch.cuda.device(u.device):
-        check(lib().gwn_bn_bwd(_p(dx), _p(u), _code(u.dtype), _p(dx_stats), float(count), _p(gamma), _p(mean),
+        check(lib().gwn_bn_bwd(_p(dx), _code(dx.dtype), _p(u), _code(u.dtype), _p(dx_stats), float(count), _p(gamma), _p(mean),
                                _p(rstd), int(training), _p(du), _p(dgamma), _p(dbeta), rows, _stream()),
               'gwn_bn_bwd')
     return du, dgamma, dbeta
@@ -378,7 +378,10 @@ def layer_bwd(u_prev: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], 
     mlp_in = CH * (1 + order * n_sup)
     P = N * Lout * V
     f32 = dict(device=dev, dtype=torch.float32)
-    dx_prev = torch.empty((N, Lin, V, CH), **f32)
+    # bf16 tensor-core path: dx_prev only lives until the BatchNorm backward (or the start conv backward) reads it, so it is
+    # stored in bf16 (its BN statistics come from the fp32 accumulator inside the kernel)
+    dx_bf16 = dt == torch.bfloat16 and hop_mats is not None and taps <= 4
+    dx_prev = torch.empty((N, Lin, V, CH), device=dev, dtype=torch.bfloat16 if dx_bf16 else torch.float32)
     # the small accumulated outputs live in ONE zero-filled buffer (one fill kernel instead of six memset nodes)
     sizes = _layer_bwd_sizes(taps, mlp_in, V, needs_grad, has_du)
     flat = torch.zeros((sum(sizes),), **f32)
@@ -400,7 +403,7 @@ def layer_bwd(u_prev: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], 
                         du=_p(du), dz_last=_p(dz_last), dx_prev=_p(dx_prev), dx_stats=_p(dx_stats),
                         dw_fg=_p(dw_fg), db_fg=_p(db_fg), dw_mlp=_p(dw_mlp), db_mlp=_p(db_mlp),
                         ws_cat=_p(ws_cat) if has_du else None, ws_dcat=_p(ws_dcat) if has_du else None,
-                        ws_dfg=_p(ws_dfg), outputs_zeroed=1)
+                        ws_dfg=_p(ws_dfg), outputs_zeroed=1, dx_prev_bf16=int(dx_bf16))
     for i, g in enumerate(needs_grad):
         args.support_needs_grad[i] = int(bool(g) and has_du)
         args.d_supports[i] = d_sup[i].data_ptr() if (g and has_du) else None
@@ -429,7 +432,9 @@ def _(u_prev, scale, shift, w_fg, w_mlp, supports, needs_grad, drop_mask, rng, h
     N, Lin, V, _c = u_prev.shape
     mlp_in = CH * (1 + order * len(supports))
     f = lambda *s: u_prev.new_empty(s, dtype=torch.float32)  # noqa: E731
-    return [f(N, Lin, V, CH), f(sum(_layer_bwd_sizes(taps, mlp_in, V, needs_grad, du is not None)))]
+    dx_bf16 = u_prev.dtype == torch.bfloat16 and hop_mats is not None and taps <= 4
+    return [u_prev.new_empty((N, Lin, V, CH), dtype=torch.bfloat16 if dx_bf16 else torch.float32),
+            f(sum(_layer_bwd_sizes(taps, mlp_in, V, needs_grad, du is not None)))]
 
 
 class WaveNetLayer(torch.autograd.Function):
