@@ -283,6 +283,10 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
         }
         __syncwarp();
         GB_TRACE(k, 2);
+        // tail of the previous slab BEFORE this slab's T1 hop: its commit frees the concat / z buffers the prep warps
+        // are waiting for, so the next slab's operands are being written while the T1 hop is issued
+        if (k > 0) tail(k - 1);
+        GB_TRACE(k, 3);
         if (DA) {
           // T1 = U5 + A^T-hop(U6): accumulate the forward hop of the staged U6 onto the U5 columns
           mbar_wait(&u6s_full[bb], (uint32_t)((k >> 1) & 1));
@@ -298,8 +302,6 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
           }
           __syncwarp();
         }
-        GB_TRACE(k, 3);
-        if (k > 0) tail(k - 1);
         GB_TRACE(k, 6);
       }
       if (k > 0) tail(k - 1);
