@@ -642,6 +642,12 @@ static bool fused_gate_wgrad_enabled() {   // GWN_FUSED_WGRAD=0 keeps the separa
   return v != 0;
 }
 
+static bool horner_bwd_enabled() {   // GWN_HORNER_BWD=0 keeps the recompute-based backward of the big-graph path (A/B measurements)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GWN_HORNER_BWD"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
 static bool gcn_t_enabled() {       // GWN_GCN_T=0 keeps the node-major fused forward (A/B measurements)
   static int v = -1;
   if (v < 0) { const char* e = getenv("GWN_GCN_T"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -880,8 +886,85 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
       fused_bwd = true;
     }
   }
+  bool horner_done = false;
+  if constexpr (std::is_same<T, bf16>::value) {
+    // ---- big graphs (V > 80): Horner-form backward - no forward recompute ----
+    // dU_0 = dh, dU_{2s+1} = dh A_s^T, dU_{2s+2} = dU_{2s+1} A_s^T (2 transposed hops per support on the 32-channel dh),
+    // dz = sum_j dU_j W_j^T (one position GEMM), dW_j = z^T dU_j (K = positions), and for the support with a gradient:
+    // T1 = z W_{2s+1} + (z W_{2s+2}) A_s,  dA += T1^T dh + (z W_{2s+2})^T dU_{2s+1}.  9 big GEMMs per layer instead of 14
+    // (6 recomputed forward hops + 6 backward hops + 2 support-gradient GEMMs).
+    int n_dA = 0, sa = -1;
+    for (int s = 0; s < c->n_supports; ++s)
+      if (g->support_needs_grad[s] && g->d_supports[s]) { ++n_dA; sa = s; }
+    if (!fused_bwd && du && tc_mode<T>(c, g->hop_mats) == 2 && c->order == 2 && c->n_supports >= 1 && nslots <= 7 && n_dA <= 1 &&
+        g->ws_w != nullptr && horner_bwd_enabled() && wgrad_tc_supported(1, 32)) {
+      const int Vp = ((c->V + 7) / 8) * 8;
+      const long long SS = P * 32;
+      // z = a . b -> cat slot 0;  dh = du . mask -> dcat slot 0
+      zfill_kernel<T><<<eb, 256, 0, st>>>(a, b, cat, 32, P);
+      GWN_LAUNCHED();
+      const bool drop = c->training && (g->drop_mask != nullptr || c->dropout_p > 0.f);
+      if (drop) {
+        drop_bwd_kernel<T><<<eb, 256, 0, st>>>(du, reinterpret_cast<const T*>(g->drop_mask), c->dropout_p, c->seed,
+                                               c->offset, g->rng, dcat, P);
+        GWN_LAUNCHED();
+      } else {
+        GWN_CUDA(cudaMemcpyAsync(dcat, du, sizeof(T) * (size_t)SS, cudaMemcpyDeviceToDevice, st));
+      }
+      // transposed hops
+      for (int s = 0; s < c->n_supports; ++s)
+        for (int k = 1; k <= 2; ++k) {
+          const int slot = 2 * s + k, src = (k == 1) ? 0 : slot - 1;
+          if (int rc = launch_hop_big(big_image(c, g->hop_mats, s, 1), Vp, dcat + src * SS, dcat + slot * SS, nullptr, slabs,
+                                      c->V, st))
+            return rc;
+        }
+      // dW_j = z^T dU_j (j = 0 also gives db = sum dh through the ones row)
+      if (!g->outputs_zeroed) GWN_CUDA(cudaMemsetAsync(g->dw_mlp, 0, sizeof(float) * 32 * mlp_in, st));
+      if (!g->outputs_zeroed) GWN_CUDA(cudaMemsetAsync(g->db_mlp, 0, sizeof(float) * 32, st));
+      for (int j = 0; j < nslots; ++j) {
+        WgParams w{};
+        w.n_chunks = 1; w.rows_per_n_out = RO; w.P = P;
+        w.ch[0] = WgChunk{cat, RO, 0, 32, 0};
+        w.G = dcat + j * SS; w.g_pitch = 32; w.N = 32; w.dW = g->dw_mlp + (size_t)j * 32 * 32; w.ldw = 32;
+        w.db = j == 0 ? g->db_mlp : nullptr;
+        if (int rc = launch_wgrad_tc(w, st)) return rc;
+      }
+      // dz = sum_j dU_j W_j^T -> cat slot 1   (weight image (k = (j, c'), n = c) = W[j*32 + c][c'] built in the kernel)
+      {
+        PgParams pg{};
+        pg.n_chunks = nslots; pg.rows_per_n_out = RO; pg.P = P; pg.N = 32;
+        pg.wsrc.W = g->w_mlp; pg.wsrc.ld = 32; pg.wsrc.transposed = 1;
+        for (int q = 0; q < nslots; ++q) {
+          pg.wsrc.w_off[q] = q * 32 * 32;
+          pg.ch[q] = PgChunk{dcat + q * SS, RO, 0, 32, 0};
+        }
+        EpiSlotTC es{}; es.out = cat + SS; es.slot_stride = SS;
+        if (int rc = launch_pos_gemm_tc(pg, es, st)) return rc;
+      }
+      if (sa >= 0) {
+        // U5 = z W_{2sa+1} -> cat slot 2, U6 = z W_{2sa+2} -> cat slot 3;  T1 = U5 + U6 A_sa -> cat slot 4
+        for (int h = 0; h < 2; ++h) {
+          PgParams pg{};
+          pg.n_chunks = 1; pg.rows_per_n_out = RO; pg.P = P; pg.N = 32;
+          pg.wsrc.W = g->w_mlp + (size_t)(2 * sa + 1 + h) * 32 * 32; pg.wsrc.ld = 32; pg.wsrc.transposed = 0; pg.wsrc.w_off[0] = 0;
+          pg.ch[0] = PgChunk{cat, RO, 0, 32, 0};
+          EpiSlotTC es{}; es.out = cat + (2 + h) * SS; es.slot_stride = SS;
+          if (int rc = launch_pos_gemm_tc(pg, es, st)) return rc;
+        }
+        if (int rc = launch_hop_big(big_image(c, g->hop_mats, sa, 0), Vp, cat + 3 * SS, cat + 4 * SS, cat + 2 * SS, slabs, c->V, st))
+          return rc;
+        if (int rc = launch_dadj_big(cat + 4 * SS, dcat, g->d_supports[sa], slabs, c->V, st)) return rc;
+        if (int rc = launch_dadj_big(cat + 3 * SS, dcat + (2 * sa + 1) * SS, g->d_supports[sa], slabs, c->V, st)) return rc;
+      }
+      dz = cat + SS;
+      horner_done = true;
+    }
+  }
   if (fused_bwd) {
     // dfg is ready: fall through to the conv weight / data gradients
+  } else if (horner_done) {
+    // dz is ready: fall through to the gate backward
   } else if (du) {
     // recompute the concat (z and its hops)
     zfill_kernel<T><<<eb, 256, 0, st>>>(a, b, cat, 32, P);
