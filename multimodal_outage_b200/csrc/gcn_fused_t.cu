@@ -335,16 +335,16 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gcn_fwd_t_kernel(const __grid_c
       mbar_wait(&d_full[b], (uint32_t)((gi >> 1) & 1));
       if (warp == 12) GT_TRACE(6);
       tc_fence_after();
-      // keep-bits of this channel for the slab's rows [q V, q V + V) of the group, aligned to bit 0
-      uint32_t kb[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
+      // keep-bits of this channel for the slab's rows [q V, q V + V) of the group, aligned to bit 0 (three scalars: a
+      // dynamically indexed array would live in local memory)
+      uint32_t kb0 = 0xffffffffu, kb1 = 0xffffffffu, kb2 = 0xffffffffu;
       mbar_wait(m_full, (uint32_t)(gi & 1));
       if (philox) {
         const int r0 = q * V, w0 = r0 >> 5, o = r0 & 31;
         uint32_t w[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) w[k] = (w0 + k < 12) ? kbits[c * 12 + w0 + k] : 0u;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) kb[k] = __funnelshift_r(w[k], w[k + 1], o);
+        kb0 = __funnelshift_r(w[0], w[1], o); kb1 = __funnelshift_r(w[1], w[2], o); kb2 = __funnelshift_r(w[2], w[3], o);
       }
       mbar_arrive(m_free);
       const uint32_t td = tmem_base + lane_off + TD + (uint32_t)b * 128u;
@@ -360,16 +360,30 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gcn_fwd_t_kernel(const __grid_c
             mbar_arrive(&d_empty[b]);
           }
           if (has) {
+            const int nv = V - c0;                // valid nodes of this sub-chunk (may be <= 0 or > 16)
+            const uint32_t kw = (c0 < 32 ? kb0 : c0 < 64 ? kb1 : kb2) >> (c0 & 31);
+            bf16* upk = up + (size_t)c0 * 32;
+            if (mp == nullptr && nv >= 16) {      // common case: a full sub-chunk, no explicit mask - branch free
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              if (c0 + i < V) {
-                float m;
-                if (mp) m = __bfloat162float(mp[(size_t)(c0 + i) * 32]);
-                else m = ((kb[c0 >> 5] >> ((c0 & 31) + i)) & 1u) ? inv : 0.f;
+              for (int i = 0; i < 16; ++i) {
+                const float m = ((kw >> i) & 1u) ? inv : 0.f;
                 const float rv = __uint_as_float(res[16 * k + i] << 16);
                 const float val = fmaf(__uint_as_float(r[i]) + bias, m, fmaf(rv, sc, sh));
-                up[(size_t)(c0 + i) * 32] = __float2bfloat16_rn(val);
+                upk[i * 32] = __float2bfloat16_rn(val);
                 s1 += val; s2 = fmaf(val, val, s2);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                if (i < nv) {
+                  float m;
+                  if (mp) m = __bfloat162float(mp[(size_t)(c0 + i) * 32]);
+                  else m = ((kw >> i) & 1u) ? inv : 0.f;
+                  const float rv = __uint_as_float(res[16 * k + i] << 16);
+                  const float val = fmaf(__uint_as_float(r[i]) + bias, m, fmaf(rv, sc, sh));
+                  upk[i * 32] = __float2bfloat16_rn(val);
+                  s1 += val; s2 = fmaf(val, val, s2);
+                }
               }
             }
           }
