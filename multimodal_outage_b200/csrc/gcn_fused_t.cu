@@ -32,7 +32,7 @@ __host__ __device__ inline GtLayout gt_layout(int KT, int NP, int NU) {
   L.m_off = L.w_off + 4u * (uint32_t)NU * 16u;             // [4][NU][16 B]
   L.s_off = L.m_off + 32u * 12u * 4u;                      // keep-bits [32 ch][12 words]
   L.bar_off = L.s_off + 256u;                              // statistics scratch [64]
-  L.total = L.bar_off + 128u;
+  L.total = L.bar_off + 144u;
   return L;
 }
 
@@ -93,15 +93,17 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gcn_fwd_t_kernel(const __grid_c
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
   uint64_t* z_full = bars;            // [2]
   uint64_t* z_empty = bars + 2;       // [2]
-  uint64_t* u_full = bars + 4;
-  uint64_t* u_empty = bars + 5;
+  uint64_t* ua_full = bars + 4;       // U tile, column half a = chunks 0..3 (TMEM columns [0,128))
+  uint64_t* ua_empty = bars + 5;
   uint64_t* a_full = bars + 6;
   uint64_t* a_empty = bars + 7;
   uint64_t* d_full = bars + 8;        // [2]
   uint64_t* d_empty = bars + 10;      // [2]
   uint64_t* m_free = bars + 12;
   uint64_t* m_full = bars + 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* ub_full = bars + 14;      // U tile, column half b = chunks 4..NM (TMEM columns [128,224)): GEMM 1 of one half
+  uint64_t* ub_empty = bars + 15;     // runs under the staging of the other
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   uint32_t* kbits = reinterpret_cast<uint32_t*>(smem + L.m_off);       // [32 ch][12 words over the group's 384 rows]
   float* sscr = reinterpret_cast<float*>(smem + L.s_off);
 
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gcn_fwd_t_kernel(const __grid_c
       mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 256);
     }
     mbar_init(m_free, 256); mbar_init(m_full, 64);
-    mbar_init(u_full, 1); mbar_init(u_empty, 256);
+    mbar_init(ua_full, 1); mbar_init(ua_empty, 256); mbar_init(ub_full, 1); mbar_init(ub_empty, 256);
     mbar_init(a_full, 256); mbar_init(a_empty, 1);
     fence_barrier_init();
     tg::tma_prefetch_desc(&zmap);
@@ -177,7 +179,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gcn_fwd_t_kernel(const __grid_c
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp walks the loop; one elected lane issues) =====================
-    const uint32_t idesc1 = make_idesc_bf16(128, NU, false, false);
+    constexpr int NA_COLS = NU < 128 ? NU : 128, NB_COLS = NU - NA_COLS;          // GEMM 1 in two column halves
+    const uint32_t idesc1a = make_idesc_bf16(128, NA_COLS, false, false);
+    const uint32_t idesc1b = make_idesc_bf16(128, NB_COLS > 0 ? NB_COLS : 16, false, false);
     const uint32_t idesc2 = make_idesc_bf16(128, NP, true, false);
     const uint64_t az = tg::make_desc_sw(0, 16u, 512u, 4u);                          // z tile: K-major SW64
     const uint64_t bw = make_smem_desc(sbase + L.w_off, (uint32_t)NU * 16u, 128u);   // W image: K-major
@@ -191,16 +195,28 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gcn_fwd_t_kernel(const __grid_c
       for (int t = 0; t < GT_TILES; ++t, ++tt) {
         const int zb = tt & 1;
         mbar_wait(&z_full[zb], (uint32_t)((tt >> 1) & 1));
-        mbar_wait(u_empty, (uint32_t)((tt & 1) ^ 1));
+        const uint64_t ad = az + (uint64_t)((sbase + L.z_off + (uint32_t)zb * 8192u) >> 4);
+        const uint64_t w2 = (uint64_t)(((uint32_t)NU * 32u) >> 4);         // second K = 16 half of the weight image
+        mbar_wait(ua_empty, (uint32_t)((tt & 1) ^ 1));
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t ad = az + (uint64_t)((sbase + L.z_off + (uint32_t)zb * 8192u) >> 4);
-          umma_bf16(tmem_base + TU, ad, bw, idesc1, 0u);
-          umma_bf16(tmem_base + TU, ad + 2u, bw + (uint64_t)(((uint32_t)NU * 32u) >> 4), idesc1, 1u);
-          umma_commit(&z_empty[zb]);
-          umma_commit(u_full);
+          umma_bf16(tmem_base + TU, ad, bw, idesc1a, 0u);
+          umma_bf16(tmem_base + TU, ad + 2u, bw + w2, idesc1a, 1u);
+          if (NB_COLS == 0) umma_commit(&z_empty[zb]);
+          umma_commit(ua_full);
         }
         __syncwarp();
+        if (NB_COLS > 0) {
+          mbar_wait(ub_empty, (uint32_t)((tt & 1) ^ 1));
+          tc_fence_after();
+          if (elect_one()) {
+            umma_bf16(tmem_base + TU + 128u, ad, bw + 128u, idesc1b, 0u);           // weight rows n >= 128: + 128 x 16 B
+            umma_bf16(tmem_base + TU + 128u, ad + 2u, bw + 128u + w2, idesc1b, 1u);
+            umma_commit(&z_empty[zb]);
+            umma_commit(ub_full);
+          }
+          __syncwarp();
+        }
       }
       const int b = gi & 1;
       GT_TRACE(1);
@@ -230,44 +246,37 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gcn_fwd_t_kernel(const __grid_c
         const int rr = 128 * t + q * 32 + lane;              // row inside the group
         const bool valid = rr < ns * V;
         const int s = rr / V, v = rr - s * V;
-        mbar_wait(u_full, (uint32_t)(tt & 1));
-        if (t == 0) {
-          mbar_wait(a_empty, (uint32_t)((gi & 1) ^ 1));      // GEMM 2 of the previous group has read A
-        }
-        tc_fence_after();
         uint8_t* arow = smem + L.a_off + (size_t)(s * 4) * KT * 16 + (size_t)v * 16;
-        uint32_t ra[32], rb[32];
         const bool warp_has_rows = 128 * t + q * 32 < ns * V;       // (the third tile holds 4V - 256 rows: most warps skip it)
-        for (int j = set; warp_has_rows && j <= NM; j += 4) {
-          const int j2 = j + 2;
-          tmem_ld32_issue(tmem_base + lane_off + TU + (uint32_t)j * 32u, ra);
-          if (j2 <= NM) tmem_ld32_issue(tmem_base + lane_off + TU + (uint32_t)j2 * 32u, rb);
-          tmem_ld_wait();
-          if (valid) {
+        auto put = [&](int j, const uint32_t (&r)[32]) {
 #pragma unroll
-            for (int cg = 0; cg < 4; ++cg) {
-              uint4 pk;
-              pk.x = gt_pack(__uint_as_float(ra[8 * cg]), __uint_as_float(ra[8 * cg + 1]));
-              pk.y = gt_pack(__uint_as_float(ra[8 * cg + 2]), __uint_as_float(ra[8 * cg + 3]));
-              pk.z = gt_pack(__uint_as_float(ra[8 * cg + 4]), __uint_as_float(ra[8 * cg + 5]));
-              pk.w = gt_pack(__uint_as_float(ra[8 * cg + 6]), __uint_as_float(ra[8 * cg + 7]));
-              *reinterpret_cast<uint4*>(arow + (size_t)cg * KT * 16 + (size_t)(j * V) * 16) = pk;
-            }
-            if (j2 <= NM) {
-#pragma unroll
-              for (int cg = 0; cg < 4; ++cg) {
-                uint4 pk;
-                pk.x = gt_pack(__uint_as_float(rb[8 * cg]), __uint_as_float(rb[8 * cg + 1]));
-                pk.y = gt_pack(__uint_as_float(rb[8 * cg + 2]), __uint_as_float(rb[8 * cg + 3]));
-                pk.z = gt_pack(__uint_as_float(rb[8 * cg + 4]), __uint_as_float(rb[8 * cg + 5]));
-                pk.w = gt_pack(__uint_as_float(rb[8 * cg + 6]), __uint_as_float(rb[8 * cg + 7]));
-                *reinterpret_cast<uint4*>(arow + (size_t)cg * KT * 16 + (size_t)(j2 * V) * 16) = pk;
-              }
-            }
+          for (int cg = 0; cg < 4; ++cg) {
+            uint4 pk;
+            pk.x = gt_pack(__uint_as_float(r[8 * cg]), __uint_as_float(r[8 * cg + 1]));
+            pk.y = gt_pack(__uint_as_float(r[8 * cg + 2]), __uint_as_float(r[8 * cg + 3]));
+            pk.z = gt_pack(__uint_as_float(r[8 * cg + 4]), __uint_as_float(r[8 * cg + 5]));
+            pk.w = gt_pack(__uint_as_float(r[8 * cg + 6]), __uint_as_float(r[8 * cg + 7]));
+            *reinterpret_cast<uint4*>(arow + (size_t)cg * KT * 16 + (size_t)(j * V) * 16) = pk;
           }
+        };
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (half == 1 && NM < 4) break;                            // (no second column half)
+          const int j = 4 * half + set, j2 = j + 2;                  // this warp's chunks of the half
+          const int jmax = half == 0 ? (NM < 3 ? NM : 3) : NM;
+          mbar_wait(half == 0 ? ua_full : ub_full, (uint32_t)(tt & 1));
+          if (t == 0 && half == 0) mbar_wait(a_empty, (uint32_t)((gi & 1) ^ 1));      // GEMM 2 of the previous group has read A
+          tc_fence_after();
+          uint32_t ra[32], rb[32];
+          const bool l1 = warp_has_rows && j <= jmax, l2 = warp_has_rows && j2 <= jmax;
+          if (l1) tmem_ld32_issue(tmem_base + lane_off + TU + (uint32_t)j * 32u, ra);
+          if (l2) tmem_ld32_issue(tmem_base + lane_off + TU + (uint32_t)j2 * 32u, rb);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(half == 0 ? ua_empty : ub_empty);              // the half is in registers: GEMM 1 may overwrite it
+          if (valid && l1) put(j, ra);
+          if (valid && l2) put(j2, rb);
         }
-        tc_fence_before();
-        mbar_arrive(u_empty);
       }
       fence_proxy_async();
       mbar_arrive(a_full);
