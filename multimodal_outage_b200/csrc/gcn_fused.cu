@@ -393,27 +393,10 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gcn_fwd_kernel(const __grid_con
   }
 }
 
-// w_img[(c>>3)][n = (j, c')][c & 7] = W_mlp[j*32 + c][c']
-__global__ void gcn_wprep_kernel(const float* __restrict__ w, int n_mats, bf16* __restrict__ img) {
-  const int NU = 32 * (1 + n_mats);
-  const int total = 32 * NU;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int c = i / NU, n = i % NU;
-    const int j = n >> 5, co = n & 31;
-    img[((c >> 3) * NU + n) * 8 + (c & 7)] = __float2bfloat16_rn(w[(j * 32 + c) * 32 + co]);
-  }
-}
-
 int gcn_fused_supported(int V, int n_mats) {
   if (V < 1 || V > 80 || (n_mats != 2 && n_mats != 4 && n_mats != 6)) return 0;   // kernel instances: see launch_gcn_fwd
   const int Kp = ((V + 15) / 16) * 16;
   return gf_layout(Kp, n_mats).total <= 227u * 1024u ? 1 : 0;
-}
-
-int launch_gcn_wprep(const float* w_mlp, int n_mats, bf16* w_img, cudaStream_t st) {
-  gcn_wprep_kernel<<<8, 256, 0, st>>>(w_mlp, n_mats, w_img);
-  GWN_LAUNCHED();
-  return 0;
 }
 
 int launch_gcn_fwd(GcnFwdParams& p, cudaStream_t st) {

@@ -50,8 +50,6 @@ int gcn_fused_supported(int V, int n_mats);
 // transposed contraction over groups of four slabs (gcn_fused_t.cu); needs w_src and mats_t
 int gcn_fused_t_supported(int V, int n_mats);
 int launch_gcn_fwd_t(GcnFwdParams& p, cudaStream_t st);
-// builds w_img from the packed fp32 mlp weight [32*(1+n_mats), 32]
-int launch_gcn_wprep(const float* w_mlp, int n_mats, bf16* w_img, cudaStream_t st);
 int launch_gcn_fwd(GcnFwdParams& p, cudaStream_t st);
 
 }  // namespace gwn
@@ -93,7 +91,5 @@ struct GcnBwdParams {
   long long* trace;            // optional debug timeline of CTA 0 (GWN_GCN_TRACE)
 };
 int gcn_bwd_fused_supported(int V, int n_mats);
-// wt_img as above; w56_img (may be NULL) for support sa
-int launch_gcn_bwd_wprep(const float* w_mlp, int n_mats, bf16* wt_img, int sa, bf16* w56_img, cudaStream_t st);
 int launch_gcn_bwd(GcnBwdParams& p, cudaStream_t st);
 }  // namespace gwn

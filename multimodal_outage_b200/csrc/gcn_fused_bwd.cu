@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
           if (di[q] >= 0) dst0[di[q]] = v[q];
       }
     }
-    if (p.w_src) {       // bf16 UMMA images of the mlp weight built here (see gcn_bwd_wprep_kernel for the layouts)
+    if (p.w_src) {       // bf16 UMMA images of the mlp weight built here (layouts: see the comment above gcn_bwd_fused_supported)
       bf16* wt = reinterpret_cast<bf16*>(smem + L.w_off);
       bf16* w56 = reinterpret_cast<bf16*>(smem + L.w56_off);
       constexpr int T4 = 8 * 32 * (1 + NM), ITS = (T4 + GB_THREADS - 1) / GB_THREADS;   // 16-byte loads, all issued first
@@ -548,32 +548,14 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gcn_bwd_kernel(const __grid_con
   }
 }
 
-// wt_img[kc = (j, c'>>3)][n = c][c' & 7] = W_mlp[j*32 + c][c'];  w56[kc = c>>3][n = (h, c')][c & 7] = W_mlp[(2sa+1+h)*32 + c][c']
-__global__ void gcn_bwd_wprep_kernel(const float* __restrict__ w, int n_mats, bf16* __restrict__ img, int sa,
-                                     bf16* __restrict__ w56) {
-  const int total = 32 * 32 * (1 + n_mats);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int j = i / 1024, c = (i / 32) % 32, co = i % 32;
-    const bf16 v = __float2bfloat16_rn(w[i]);
-    img[((j * 4 + (co >> 3)) * 32 + c) * 8 + (co & 7)] = v;
-    if (w56 && sa >= 0 && (j == 2 * sa + 1 || j == 2 * sa + 2)) {
-      const int h = j - (2 * sa + 1);
-      w56[((c >> 3) * 64 + h * 32 + co) * 8 + (c & 7)] = v;
-    }
-  }
-}
-
+// image layouts built in the kernel prologue: wt_img[kc = (j, c'>>3)][n = c][c' & 7] = W_mlp[j*32 + c][c'];
+//   w56[kc = c>>3][n = (h, c')][c & 7] = W_mlp[(2sa+1+h)*32 + c][c']
 int gcn_bwd_fused_supported(int V, int n_mats) {
   if (V < 1 || V > 80 || (n_mats != 2 && n_mats != 4 && n_mats != 6)) return 0;
   const int Kp = ((V + 15) / 16) * 16;
   return gb_layout(Kp, n_mats, true).total <= 227u * 1024u ? 1 : 0;
 }
 
-int launch_gcn_bwd_wprep(const float* w_mlp, int n_mats, bf16* wt_img, int sa, bf16* w56_img, cudaStream_t st) {
-  gcn_bwd_wprep_kernel<<<8, 256, 0, st>>>(w_mlp, n_mats, wt_img, sa, w56_img);
-  GWN_LAUNCHED();
-  return 0;
-}
 
 int launch_gcn_bwd(GcnBwdParams& p, cudaStream_t st) {
   if (p.slabs <= 0) return 0;

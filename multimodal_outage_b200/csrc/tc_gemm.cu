@@ -41,26 +41,6 @@ __global__ void wprep_kernel(WPrepParams w) {
       }
     }
   }
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-  if (w.zero64 && tid < 64) w.zero64[tid] = 0.0;
-  if (w.g_w) {
-    const int NU = 32 * (1 + w.g_nmats);
-    if (w.g_img) {          // (k = c, n = (j, c')) = W[j*32 + c][c']
-      for (int i = tid; i < 32 * NU; i += nth) {
-        const int c = i / NU, n = i % NU;
-        w.g_img[((c >> 3) * NU + n) * 8 + (c & 7)] = __float2bfloat16_rn(w.g_w[((n >> 5) * 32 + c) * 32 + (n & 31)]);
-      }
-    }
-    if (w.gb_wt) {          // (n = c, k = (j, c')) = W[j*32 + c][c'];  w56: (k = c, n = (h, c')) for support gb_sa
-      for (int i = tid; i < 32 * NU; i += nth) {
-        const int j = i / 1024, c = (i / 32) % 32, co = i % 32;
-        const bf16 v = __float2bfloat16_rn(w.g_w[i]);
-        w.gb_wt[((j * 4 + (co >> 3)) * 32 + c) * 8 + (co & 7)] = v;
-        if (w.gb_w56 && w.gb_sa >= 0 && (j == 2 * w.gb_sa + 1 || j == 2 * w.gb_sa + 2))
-          w.gb_w56[((c >> 3) * 64 + (j - (2 * w.gb_sa + 1)) * 32 + co) * 8 + (c & 7)] = v;
-      }
-    }
-  }
 }
 
 int launch_wprep(const WPrepParams& w, cudaStream_t st) {

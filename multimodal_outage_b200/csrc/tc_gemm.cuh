@@ -78,11 +78,6 @@ struct WPrepParams {
   float* bias_out;              // out [N] (may be NULL)
   int bias_chunk;               // != 0: append the (folded) bias as two K pieces [2][N][8] (k=0: bf16 hi, k=1: bf16 lo)
   int half_odd;                 // != 0: odd output columns (and their bias) are scaled by 0.5 (sigmoid(g) = 0.5 tanh(g/2) + 0.5)
-  // piggy-backed jobs (one launch instead of three graph nodes): zero 64 doubles; the fused gcn weight images
-  double* zero64;               // optional
-  const float* g_w; int g_nmats;     // packed mlp weight [32*(1+g_nmats), 32] (NULL: no gcn images)
-  bf16* g_img;                  // forward image  [4][32*(1+H)][8]   (gcn_fused.cu)
-  bf16* gb_wt; int gb_sa; bf16* gb_w56;   // backward images (gcn_fused_bwd.cu); gb_w56 may be NULL
 };
 int launch_wprep(const WPrepParams& w, cudaStream_t st);
 
