@@ -505,6 +505,10 @@ int launch_pos_gemm_tc(PgParams& p, const Epi& epi, cudaStream_t st) {
   int pick = 0;
   for (int i = 0; i < 3; ++i)
     if (eff_of[i] >= best_eff - 0.02) pick = i;
+  {   // GWN_PG_SUB=<1|2|4>: force the macro-tile size (A/B measurements)
+    const char* e = getenv("GWN_PG_SUB");
+    if (e) for (int i = 0; i < 3; ++i) if (subs[i] == atoi(e) && eff_of[i] > 0) pick = i;
+  }
   p.sub = subs[pick];
   const int stages = stg_of[pick];
   const int n_acc = acc_c * p.sub <= 128 ? 4 : 2;
