@@ -464,6 +464,9 @@ def test_bf16_layer_op_fwd_bwd_vs_oracle(with_bn, mask, tensor_cores):
                        mask=mask, seed=4, tensor_cores=True)
         _layer_op_case(torch.bfloat16, BF16_TOL, V=40, N=5, Lin=4, dil=1, taps=2, n_sup=1, with_bn=with_bn,
                        mask=mask, seed=5, tensor_cores=True)
+        # kernel size 3: run-time chunk counts in the position GEMMs, separate (unfused) gate weight-gradient launch
+        _layer_op_case(torch.bfloat16, BF16_TOL, V=67, N=3, Lin=9, dil=2, taps=3, n_sup=3, with_bn=with_bn,
+                       mask=mask, seed=6, tensor_cores=True)
 
 
 @pytest.mark.parametrize('with_bn,mask', [(True, False), (False, True)])
