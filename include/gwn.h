@@ -253,6 +253,11 @@ int gwn_head_bwd_tc(const gwn_head_cfg* cfg, const gwn_head_tc_bwd_args* a, void
  * image 4*s+0 = A_s^T, 4*s+1 = (A_s^2)^T (forward hops), 4*s+2 = A_s, 4*s+3 = A_s^2 (backward hops),
  * bf16, K-major no-swizzle canonical layout, zero padded to [Kp/8][128][8], Kp = 16*ceil(V/16).
  * `supports` is a HOST array of device pointers.  gwn_hop_tc runs one hop (tests / microbench). */
+/* Which image format gwn_layer_fwd / gwn_layer_bwd expect in `hop_mats` for a graph of V nodes with n_supports supports
+ * (order 2): 1 = gwn_hop_mats_prep images (every support resident in shared memory: V <= 80 and the images fit),
+ * 2 = gwn_support_images_prep images (one TMA-tiled GEMM per hop), 0 = bad arguments.  Callers MUST build the images
+ * this function names - it is the same rule the layer entry points apply. */
+int gwn_hop_mode(int V, int n_supports);
 int gwn_hop_mats_bytes(int V, int n_supports);
 int gwn_hop_mats_prep(const float* const* supports, int n_supports, int V, void* out, void* stream);
 int gwn_hop_tc(const void* mats, int n_mats, int mat, void* buf, int pitch, int slot_in, int slot_out,

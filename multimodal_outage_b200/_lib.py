@@ -111,6 +111,7 @@ SIGNATURES = {
     'gwn_head_tc_ws_bytes': (_ll, [_i, _i, _i, _i]),
     'gwn_head_fwd_tc': (_i, [C.POINTER(HeadCfg), C.POINTER(HeadTcFwdArgs), vp]),
     'gwn_head_bwd_tc': (_i, [C.POINTER(HeadCfg), C.POINTER(HeadTcBwdArgs), vp]),
+    'gwn_hop_mode': (_i, [_i, _i]),
     'gwn_hop_mats_bytes': (_i, [_i, _i]),
     'gwn_hop_mats_prep': (_i, [vp, _i, _i, vp, vp]),
     'gwn_hop_tc': (_i, [vp, _i, _i, vp, _i, _i, _i, _i, _i, vp]),

@@ -1,6 +1,7 @@
 // Error reporting, version and device gate of libgwn.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -16,6 +17,15 @@ void set_error(const char* fmt, ...) {
 }
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long* trace_ptr(const char* env_name) {
+#ifdef GWN_TRACE
+  const char* e = getenv(env_name);
+  return e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
+#else
+  (void)env_name;
+  return nullptr;
+#endif
+}
 }  // namespace gwn
 
 extern "C" long long gwn_launch_count(void) { return gwn::g_launches.load(); }

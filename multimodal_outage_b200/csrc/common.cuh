@@ -37,6 +37,11 @@ void count_launch();
 
 typedef __nv_bfloat16 bf16;
 
+// Debug timelines (scripts/gpu_*_trace.py): a device pointer handed over in an environment variable.  Only builds made
+// with -DGWN_TRACE (GWN_TRACE=1 python -m multimodal_outage_b200.build) look at the environment at all: the release
+// library never parses an environment-supplied pointer and pays no getenv per launch.
+long long* trace_ptr(const char* env_name);
+
 static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
 
 // position -> (sample, row in sample) with 32-bit arithmetic: a 64-bit div/mod costs several hundred cycles

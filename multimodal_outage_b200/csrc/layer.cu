@@ -613,12 +613,18 @@ static int check_cfg(const gwn_layer_cfg* c) {
   return 0;
 }
 
+// The ONE rule that picks the image format of `hop_mats` (include/gwn.h): the Python side asks this same function which
+// images to build, so the two sides cannot disagree about what the buffer holds.
+extern "C" int gwn_hop_mode(int V, int n_supports) {
+  if (n_supports < 1 || n_supports > GWN_MAX_SUPPORTS || V < 1) return 0;
+  return (V <= 80 && hops_tc_supported(V, 2 * n_supports) != 0) ? 1 : 2;
+}
+
 // tensor-core path available for this layer?  (bf16 storage, images prepared, supports fit on chip)
 template <typename T>
 static bool use_tc_hops(const gwn_layer_cfg* c, const void* hop_mats) {
   if constexpr (!std::is_same<T, bf16>::value) return false;
-  return hop_mats != nullptr && c->order == 2 && c->n_supports >= 1 &&
-         hops_tc_supported(c->V, 2 * c->n_supports) != 0;
+  return hop_mats != nullptr && c->order == 2 && c->n_supports >= 1 && gwn_hop_mode(c->V, c->n_supports) == 1;
 }
 
 // 0: CUDA-core hops; 1: supports resident on chip (tc_hops.cu); 2: TMA-tiled GEMM per hop (tma_gemm.cu, V > 80).
@@ -628,8 +634,7 @@ static int tc_mode(const gwn_layer_cfg* c, const void* hop_mats) {
   if constexpr (!std::is_same<T, bf16>::value) return 0;
   if (hop_mats == nullptr) return 0;
   if (c->n_supports == 0) return 1;    // no hops at all: the position GEMMs still run on tensor cores
-  if (c->order == 2 && hops_tc_supported(c->V, 2 * c->n_supports)) return 1;
-  return 2;
+  return c->order == 2 ? gwn_hop_mode(c->V, c->n_supports) : 2;
 }
 static const bf16* big_image(const gwn_layer_cfg* c, const void* hop_mats, int s, int which) {
   const long long Vp = ((c->V + 7) / 8) * 8;
@@ -878,8 +883,7 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
       bp.dfg = reinterpret_cast<bf16*>(g->ws_dfg); bp.dw_mlp = g->dw_mlp; bp.db_mlp = g->db_mlp;
       bp.V = c->V; bp.slabs = c->N * c->Lout;
       {
-        const char* e = getenv("GWN_GCN_TRACE");
-        bp.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
+        bp.trace = trace_ptr("GWN_GCN_TRACE");
       }
       bp.sa = sa; bp.mat_fwd = sa >= 0 ? 4 * sa : 0; bp.w56_img = nullptr; bp.dA = sa >= 0 ? g->d_supports[sa] : nullptr;
       if (int rc = launch_gcn_bwd(bp, st)) return rc;
@@ -896,8 +900,10 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
     int n_dA = 0, sa = -1;
     for (int s = 0; s < c->n_supports; ++s)
       if (g->support_needs_grad[s] && g->d_supports[s]) { ++n_dA; sa = s; }
+    // (the support-gradient scratch U5 / U6 / T1 lives in cat slots 2..4: with a single support the concat workspace has
+    //  only 3 slots, so that shape takes the recompute path below)
     if (!fused_bwd && du && tc_mode<T>(c, g->hop_mats) == 2 && c->order == 2 && c->n_supports >= 1 && nslots <= 7 && n_dA <= 1 &&
-        g->ws_w != nullptr && horner_bwd_enabled() && wgrad_tc_supported(1, 32)) {
+        (sa < 0 || nslots >= 5) && g->ws_w != nullptr && horner_bwd_enabled() && wgrad_tc_supported(1, 32)) {
       const int Vp = ((c->V + 7) / 8) * 8;
       const long long SS = P * 32;
       // z = a . b -> cat slot 0;  dh = du . mask -> dcat slot 0
@@ -1234,8 +1240,7 @@ extern "C" int gwn_gcn_fwd(const void* z, const void* u_prev, const float* scale
   fp.w_img = nullptr; fp.w_src = w_mlp; fp.bias = b_mlp; fp.mask = nullptr; fp.drop_p = drop_p; fp.seed = seed; fp.offset = offset;
   fp.rng = nullptr; fp.u = reinterpret_cast<bf16*>(u); fp.stats = stats; fp.V = V; fp.slabs = N * Lout;
   {  // debug timeline: GWN_GCN_TRACE=<device pointer of 64*8 int64> (scripts/gpu_gcn_trace.py)
-    const char* e = getenv("GWN_GCN_TRACE");
-    fp.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
+    fp.trace = trace_ptr("GWN_GCN_TRACE");
   }
   if (gcn_t_enabled() && gcn_fused_t_supported(V, fp.n_mats)) {
     const int Kp = ((V + 15) / 16) * 16;

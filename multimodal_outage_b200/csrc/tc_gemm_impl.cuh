@@ -536,8 +536,7 @@ int launch_pos_gemm_tc(PgParams& p, const Epi& epi, cudaStream_t st) {
   }
   for (int i = n_maps; i < PG_TC_MAX_MAPS; ++i) maps.m[i] = maps.m[0];
   {
-    const char* e = getenv("GWN_PG_TRACE");
-    p.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
+    p.trace = trace_ptr("GWN_PG_TRACE");
   }
   const size_t a_bytes = (size_t)NB * 8192 * p.sub + (Epi::kWgrad ? 8192 : 0);
   const size_t smem = fixed + stages * a_bytes;

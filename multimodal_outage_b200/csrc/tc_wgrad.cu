@@ -332,8 +332,7 @@ int launch_wgrad_tc(WgParams& p, cudaStream_t st) {
   GWN_REQUIRE(wgrad_tc_supported(p.n_chunks, p.N), "wgrad_tc: unsupported shape (chunks=%d, N=%d)", p.n_chunks, p.N);
   GWN_REQUIRE(p.P < (1ll << 31), "wgrad_tc: too many positions");
   {
-    const char* e = getenv("GWN_WG_TRACE");
-    p.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
+    p.trace = trace_ptr("GWN_WG_TRACE");
   }
   bool flat = true;    // every chunk has the output's own row structure: tile the flat position axis
   for (int q = 0; q < p.n_chunks; ++q)

@@ -296,7 +296,8 @@ class gwnet(nn.Module):
             sup_c = [s.detach().contiguous() for s in supports]
             # V <= 80: every support image stays resident in shared memory; larger graphs (the 3,100-node
             # configurations): one TMA-tiled tensor-core GEMM per hop
-            hop_mats = ops.hop_mats(sup_c) if ops.hop_tc_supported(V) else ops.support_images(sup_c)
+            # (ops.hop_mode = the C library's own rule: both sides agree on which images the buffer holds)
+            hop_mats = ops.hop_mats(sup_c) if ops.hop_mode(V, len(sup_c)) == 1 else ops.support_images(sup_c)
 
         u = ops.StartConv.apply(x, self.start_conv.weight, self.start_conv.bias, L[0], dt == torch.bfloat16)
         stats = None

@@ -713,9 +713,18 @@ def _(x, A, transpose_a):
 
 
 # =========================================================================== tcgen05 diffusion hops (V <= 128, bf16)
-def hop_tc_supported(V: int) -> bool:
-    """The tensor-core hop kernel keeps up to 6 support images resident in shared memory: V <= 80 today."""
-    return V <= 80
+def hop_mode(V: int, n_supports: int) -> int:
+    """Image format the layer kernels expect in ``hop_mats`` (include/gwn.h: gwn_hop_mode - the C side applies the same
+    function): 1 = `hop_mats` images (supports resident in shared memory), 2 = `support_images` (TMA-tiled hop GEMMs)."""
+    m = lib().gwn_hop_mode(int(V), int(n_supports))
+    if m not in (1, 2):
+        raise ValueError(f'no tensor-core hop path for V={V}, {n_supports} supports')
+    return m
+
+
+def hop_tc_supported(V: int, n_supports: int = 3) -> bool:
+    """True when every support image stays resident in shared memory (mode 1)."""
+    return hop_mode(V, n_supports) == 1
 
 
 @torch.library.custom_op('gwn::hop_mats', mutates_args=())
