@@ -49,6 +49,13 @@ int gwn_adp_fwd(const float* e1, const float* e2, float* adp, float* adp_t, int 
 /* d_adp [V,V] -> d_e1 [V,R], d_e2 [R,V] (overwritten). ws: V*V floats. */
 int gwn_adp_bwd(const float* e1, const float* e2, const float* adp, const float* d_adp,
                 float* d_e1, float* d_e2, float* ws, int V, int R, void* stream);
+/* The adaptive adjacency as a PAIR [2][V][V] (two identical copies; copy 0 is what the layer kernels read as the
+ * support).  Its gradient comes back from gwn_layer_bwd as (d_supports, d_supports_sq) = (d0, Q), laid out [2][V][V];
+ * gwn_adp_pair_bwd completes it in fp32 (d_adp = d0 + A^T Q + Q A^T, the A*A hop of graph_wavenet.py:91-93 is
+ * linear in Q) and then runs gwn_adp_bwd.  ws: [2][V][V] scratch. */
+int gwn_adp_fwd_pair(const float* e1, const float* e2, float* pair, int V, int R, void* stream);
+int gwn_adp_pair_bwd(const float* e1, const float* e2, const float* adp, const float* d_pair, float* d_e1, float* d_e2,
+                     float* ws, int V, int R, void* stream);
 
 /* ---- start_conv (1x1, Cin->32) + left zero pad + NCHW -> channels-last
  *      graph_wavenet.py:191-196 ---- */
@@ -150,6 +157,12 @@ typedef struct {
   int outputs_zeroed;           /* != 0: the caller already zeroed dx_stats, dw_*, db_* (one fill instead of six memsets) */
   int dx_prev_bf16;             /* != 0 (bf16 tensor-core path only): dx_prev is stored as bf16 - it only lives until the
                                    BatchNorm backward reads it; its statistics are taken from the fp32 accumulator */
+  float* d_supports_sq[GWN_MAX_SUPPORTS];
+                                /* optional [V,V] fp32, ACCUMULATED into (caller zeroes): when non-NULL for a support
+                                   with support_needs_grad, a kernel path MAY leave the gradient that reaches the
+                                   support through its SECOND-order hop A*A in factored form: with Q = d_supports_sq[i]
+                                   the full gradient is d_supports[i] + A^T Q + Q A^T (applied once per step by
+                                   gwn_adp_pair_bwd, in fp32).  Paths that do not use it leave Q = 0. */
 } gwn_layer_bwd_args;
 
 int gwn_layer_bwd(const gwn_layer_cfg* cfg, const gwn_layer_bwd_args* args, void* stream);
@@ -168,6 +181,13 @@ int gwn_gcn_fwd(const void* z, const void* u_prev, const float* scale, const flo
  *   dfg = gate backward of dz (df = dz b (1-a^2), dg = dz a b (1-b), interleaved, bf16 [N*Lout*V, 64]);
  *   sa >= 0: dA[V,V] += gradient wrt support `sa` (the adaptive adjacency).  dw_mlp/db_mlp are overwritten, dA accumulated.
  * ws_w >= 24 KiB scratch.  graph_wavenet.py:76-98 backward + :222-226 backward. */
+/* as gwn_gcn_bwd, through the transposed ("T-form") kernel (csrc/gcn_fused_bwd_t.cu); dQ6 as d_supports_sq above
+ * (required when sa >= 0).  Returns -1 when the shape has no T-form instance (gwn_gcn_bwd_t_supported). */
+int gwn_gcn_bwd_t_supported(int V, int n_supports, int has_da);
+int gwn_gcn_bwd_t(const void* du, const void* a, const void* b, const void* dz_last, const void* hop_mats,
+                  int n_supports, const float* w_mlp, float drop_p, unsigned long long seed, unsigned long long offset,
+                  int sa, void* dfg, float* dw_mlp, float* db_mlp, float* dA, float* dQ6, int N, int V, int Lout, int Lf,
+                  void* stream);
 int gwn_gcn_bwd(const void* du, const void* a, const void* b, const void* dz_last, const void* hop_mats,
                 int n_supports, const float* w_mlp, void* ws_w, float drop_p, unsigned long long seed,
                 unsigned long long offset, int sa, void* dfg, float* dw_mlp, float* db_mlp, float* dA,

@@ -41,7 +41,7 @@ class LayerBwdArgs(C.Structure):
                 ('drop_mask', vp), ('rng', vp), ('hop_mats', vp), ('ws_w', vp), ('a', vp), ('b', vp), ('du', vp), ('dz_last', vp), ('dx_prev', vp),
                 ('dx_stats', vp), ('dw_fg', vp), ('db_fg', vp), ('dw_mlp', vp), ('db_mlp', vp),
                 ('d_supports', vp * MAX_SUPPORTS), ('ws_cat', vp), ('ws_dcat', vp), ('ws_dfg', vp), ('outputs_zeroed', C.c_int),
-                ('dx_prev_bf16', C.c_int)]
+                ('dx_prev_bf16', C.c_int), ('d_supports_sq', vp * MAX_SUPPORTS)]
 
 
 class HeadCfg(C.Structure):
@@ -95,6 +95,8 @@ SIGNATURES = {
     'gwn_check_device': (_i, []),
     'gwn_adp_fwd': (_i, [vp, vp, vp, vp, _i, _i, vp]),
     'gwn_adp_bwd': (_i, [vp, vp, vp, vp, vp, vp, vp, _i, _i, vp]),
+    'gwn_adp_fwd_pair': (_i, [vp, vp, vp, _i, _i, vp]),
+    'gwn_adp_pair_bwd': (_i, [vp, vp, vp, vp, vp, vp, vp, _i, _i, vp]),
     'gwn_start_fwd': (_i, [vp, vp, vp, vp, _i, _i, _i, _i, _i, _i, vp]),
     'gwn_start_bwd': (_i, [vp, vp, vp, _i, vp, vp, vp, _i, _i, _i, _i, _i, vp]),
     'gwn_start_tc_supported': (_i, [_i]),
@@ -103,6 +105,8 @@ SIGNATURES = {
     'gwn_layer_fwd': (_i, [C.POINTER(LayerCfg), C.POINTER(LayerFwdArgs), vp]),
     'gwn_layer_bwd': (_i, [C.POINTER(LayerCfg), C.POINTER(LayerBwdArgs), vp]),
     'gwn_gcn_fwd': (_i, [vp, vp, vp, vp, vp, _i, vp, vp, vp, _f, C.c_uint64, C.c_uint64, vp, vp, _i, _i, _i, _i, vp]),
+    'gwn_gcn_bwd_t_supported': (_i, [_i, _i, _i]),
+    'gwn_gcn_bwd_t': (_i, [vp, vp, vp, vp, vp, _i, vp, _f, C.c_uint64, C.c_uint64, _i, vp, vp, vp, vp, vp, _i, _i, _i, _i, vp]),
     'gwn_gcn_bwd': (_i, [vp, vp, vp, vp, vp, _i, vp, vp, _f, C.c_uint64, C.c_uint64, _i, vp, vp, vp, vp, _i, _i, _i, _i, vp]),
     'gwn_bn_fold': (_i, [vp, _d, vp, vp, vp, vp, _f, _f, _i, vp, vp, vp, vp, vp]),
     'gwn_bn_bwd': (_i, [vp, _i, vp, _i, vp, _d, vp, vp, vp, _i, vp, vp, vp, _ll, vp]),

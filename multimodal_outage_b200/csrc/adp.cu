@@ -9,8 +9,8 @@ namespace gwn {
 constexpr int ADP_MAX_R = 16;
 
 __global__ void __launch_bounds__(256) adp_fwd_kernel(const float* __restrict__ e1, const float* __restrict__ e2,
-                                                      float* __restrict__ adp, float* __restrict__ adp_t, int V,
-                                                      int R) {
+                                                      float* __restrict__ adp, float* __restrict__ adp_t,
+                                                      float* __restrict__ adp2, int V, int R) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= V) return;
@@ -41,6 +41,33 @@ __global__ void __launch_bounds__(256) adp_fwd_kernel(const float* __restrict__ 
     float pv = adp[(long long)row * V + j] * inv;
     adp[(long long)row * V + j] = pv;
     if (adp_t) adp_t[(long long)j * V + row] = pv;
+    if (adp2) adp2[(long long)row * V + j] = pv;
+  }
+}
+
+// Completes a support gradient delivered in factored form (include/gwn.h: d_supports_sq):
+//   out[p, q] = d0[p, q] + sum_w Q[p, w] A[q, w] + sum_v A[v, p] Q[v, q]          (dA = Q5 + Q6 A^T + A^T Q6, fp32)
+// One block per row p; A and Q ([V,V], a few tens of KB) stay in L1/L2.
+__global__ void __launch_bounds__(128) dadj_finish_kernel(const float* __restrict__ A, const float* __restrict__ d0,
+                                                          const float* __restrict__ Q, float* __restrict__ out, int V) {
+  extern __shared__ float sh[];
+  float* qrow = sh;          // Q[p, :]
+  float* acol = sh + V;      // A[:, p]
+  const int p = blockIdx.x;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    qrow[i] = Q[(long long)p * V + i];
+    acol[i] = A[(long long)i * V + p];
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < V; q += blockDim.x) {
+    float acc = d0[(long long)p * V + q];
+    const float* arow = A + (long long)q * V;
+    float t1 = 0.f, t2 = 0.f;
+    for (int w = 0; w < V; ++w) {
+      t1 = fmaf(qrow[w], __ldg(arow + w), t1);
+      t2 = fmaf(acol[w], __ldg(Q + (long long)w * V + q), t2);
+    }
+    out[(long long)p * V + q] = acc + t1 + t2;
   }
 }
 
@@ -120,9 +147,35 @@ using namespace gwn;
 extern "C" int gwn_adp_fwd(const float* e1, const float* e2, float* adp, float* adp_t, int V, int R, void* stream) {
   GWN_REQUIRE(e1 && e2 && adp && V >= 1 && R >= 1 && R <= ADP_MAX_R, "adp_fwd: bad argument (R=%d, max %d)", R,
               ADP_MAX_R);
-  adp_fwd_kernel<<<(unsigned)cdiv(V, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(e1, e2, adp, adp_t, V, R);
+  adp_fwd_kernel<<<(unsigned)cdiv(V, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(e1, e2, adp, adp_t, nullptr, V, R);
   GWN_LAUNCHED();
   return 0;
+}
+
+// The adaptive adjacency as a PAIR [2][V][V] (two identical copies): the layer kernels read copy 0 as the support; the
+// gradient of the pair comes back as (d0, Q) = (first-order part, factored second-order part - gwn.h: d_supports_sq)
+// and gwn_adp_pair_bwd completes it (d_adp = d0 + A^T Q + Q A^T) before the softmax / relu / rank-R backward.
+extern "C" int gwn_adp_fwd_pair(const float* e1, const float* e2, float* pair, int V, int R, void* stream) {
+  GWN_REQUIRE(e1 && e2 && pair && V >= 1 && R >= 1 && R <= ADP_MAX_R, "adp_fwd_pair: bad argument (R=%d, max %d)", R,
+              ADP_MAX_R);
+  adp_fwd_kernel<<<(unsigned)cdiv(V, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(e1, e2, pair, nullptr,
+                                                                                          pair + (long long)V * V, V, R);
+  GWN_LAUNCHED();
+  return 0;
+}
+
+extern "C" int gwn_adp_bwd(const float* e1, const float* e2, const float* adp, const float* d_adp, float* d_e1,
+                           float* d_e2, float* ws, int V, int R, void* stream);
+
+// ws: [2][V][V] scratch
+extern "C" int gwn_adp_pair_bwd(const float* e1, const float* e2, const float* adp, const float* d_pair, float* d_e1,
+                                float* d_e2, float* ws, int V, int R, void* stream) {
+  GWN_REQUIRE(e1 && e2 && adp && d_pair && d_e1 && d_e2 && ws && V >= 1 && R >= 1 && R <= ADP_MAX_R,
+              "adp_pair_bwd: bad argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dadj_finish_kernel<<<V, 128, 2 * V * sizeof(float), st>>>(adp, d_pair, d_pair + (long long)V * V, ws, V);
+  GWN_LAUNCHED();
+  return gwn_adp_bwd(e1, e2, adp, ws, d_e1, d_e2, ws + (long long)V * V, V, R, stream);
 }
 
 extern "C" int gwn_adp_bwd(const float* e1, const float* e2, const float* adp, const float* d_adp, float* d_e1,

@@ -89,7 +89,45 @@ struct GcnBwdParams {
   const bf16* w56_img;         // [4][64][8]: (n = (5|6, c'), k = c) = W_mlp[(2sa+1 | 2sa+2)*32 + c][c']
   float* dA;                   // [V, V] fp32, accumulated with atomics
   long long* trace;            // optional debug timeline of CTA 0 (GWN_GCN_TRACE)
+  // transposed ("T-form") kernel (gcn_fused_bwd_t.cu) only:
+  const bf16* mats_bt;         // stacked TRANSPOSED-hop image (gwn_hop_mats_prep, third region): B operand of GEMM H
+  int debug;                   // experiment switches (GWN_BT_DEBUG), 0 in production
+  float* dQ6;                  // [V, V] fp32, accumulated: Q6 = sum U6[v] . dh[w]; the caller owes dA += A^T Q6 + Q6 A^T
 };
 int gcn_bwd_fused_supported(int V, int n_mats);
 int launch_gcn_bwd(GcnBwdParams& p, cudaStream_t st);
+
+// ---- transposed fused backward: geometry shared by the kernel, its launcher and the image-prep kernel ----
+// A group of four slabs is contracted at once.  GEMM H runs with M = (slab, channel) = 128 on the accumulator rows and
+// N = (hop, node) on the columns, in ITEMS of (node range r of <= 32 nodes) x (hop half h of <= 4 hop slots, slot 0 =
+// identity): item (r, h) owns columns n0(r, h) .. + nh(h) * rs(r) of the stacked image.
+struct BtGeom {
+  int NM, NH, NH0, NH1, NHALF, NPD, NR, RSL, KW, NTOT;
+  __host__ __device__ constexpr BtGeom(int nm, int npd)
+      : NM(nm), NH(1 + nm), NH0(1 + nm < 4 ? 1 + nm : 4), NH1(1 + nm - (1 + nm < 4 ? 1 + nm : 4)),
+        NHALF(1 + nm > 4 ? 2 : 1), NPD(npd), NR((npd + 31) / 32), RSL(npd - 32 * ((npd + 31) / 32 - 1)),
+        KW(((npd + 15) / 16) * 16), NTOT(0) {
+    int n = 0, last = 0;
+    for (int r = 0; r < NR; ++r)
+      for (int h = 0; h < NHALF; ++h) { last = n + ((nh(h) * rs(r) + 15) / 16) * 16; n += nh(h) * rs(r); }
+    NTOT = ((last + 7) / 8) * 8;
+  }
+  __host__ __device__ constexpr int rs(int r) const { return r < NR - 1 ? 32 : RSL; }       // nodes of range r
+  __host__ __device__ constexpr int nh(int h) const { return h == 0 ? NH0 : NH1; }          // hop slots of half h
+  __host__ __device__ constexpr int n0(int r, int h) const {                                // first column of item (r, h)
+    int n = 0;
+    for (int rr = 0; rr < NR; ++rr)
+      for (int hh = 0; hh < NHALF; ++hh) {
+        if (rr == r && hh == h) return n;
+        n += nh(hh) * rs(rr);
+      }
+    return n;
+  }
+  __host__ __device__ constexpr int nmma(int r, int h) const { return ((nh(h) * rs(r) + 15) / 16) * 16; }
+};
+// bytes of the stacked transposed-hop image [KW/8][NTOT][8] bf16 for a graph of V nodes, n_mats = 2 * supports
+int gcn_bwd_t_image_elems(int V, int n_mats);
+int gcn_bwd_t_supported(int V, int n_mats, bool has_da);
+int launch_gcn_bwd_t(GcnBwdParams& p, cudaStream_t st);
+int launch_hop_mats_bt_prep(const float* const* supports, int n_supports, int V, bf16* out, cudaStream_t st);
 }  // namespace gwn

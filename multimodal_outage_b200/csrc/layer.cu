@@ -659,6 +659,19 @@ static bool gcn_t_enabled() {       // GWN_GCN_T=0 keeps the node-major fused fo
   return v != 0;
 }
 
+static bool gcn_bwd_t_enabled() {   // GWN_GCN_BWD_T=0 keeps the node-major fused backward (A/B measurements)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GWN_GCN_BWD_T"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
+// start (in bf16 elements) of the stacked transposed-hop image of the T-form fused backward inside gwn_hop_mats_prep's buffer
+static size_t mats_bt_offset(int V, int n_supports) {
+  const int Kp = ((V + 15) / 16) * 16;
+  const int KT = (((1 + 2 * n_supports) * V + 15) / 16) * 16;
+  return (size_t)n_supports * 4 * (Kp / 8) * 1024 + (size_t)KT * Kp;
+}
+
 static bool fused_gcn_enabled() {   // GWN_NO_FUSED_GCN=1 keeps the unfused kernels (A/B measurements only)
   static int v = -1;
   if (v < 0) { const char* e = getenv("GWN_NO_FUSED_GCN"); v = (e && e[0] == '1') ? 0 : 1; }
@@ -886,7 +899,15 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
         bp.trace = trace_ptr("GWN_GCN_TRACE");
       }
       bp.sa = sa; bp.mat_fwd = sa >= 0 ? 4 * sa : 0; bp.w56_img = nullptr; bp.dA = sa >= 0 ? g->d_supports[sa] : nullptr;
-      if (int rc = launch_gcn_bwd(bp, st)) return rc;
+      // transposed hops over groups of four slabs (gcn_fused_bwd_t.cu) when the shape has an instance and the caller
+      // takes the second-order part of the support gradient in factored form (d_supports_sq)
+      if (gcn_bwd_t_enabled() && gcn_bwd_t_supported(c->V, bp.n_mats, sa >= 0) && (sa < 0 || g->d_supports_sq[sa])) {
+        bp.mats_bt = reinterpret_cast<const bf16*>(g->hop_mats) + mats_bt_offset(c->V, c->n_supports);
+        bp.dQ6 = sa >= 0 ? g->d_supports_sq[sa] : nullptr;
+        if (int rc = launch_gcn_bwd_t(bp, st)) return rc;
+      } else {
+        if (int rc = launch_gcn_bwd(bp, st)) return rc;
+      }
       fused_bwd = true;
     }
   }
@@ -1273,6 +1294,36 @@ extern "C" int gwn_gcn_bwd(const void* du, const void* a, const void* b, const v
   bp.dfg = reinterpret_cast<bf16*>(dfg); bp.dw_mlp = dw_mlp; bp.db_mlp = db_mlp; bp.V = V; bp.slabs = N * Lout;
   bp.sa = sa; bp.mat_fwd = sa >= 0 ? 4 * sa : 0; bp.w56_img = nullptr; bp.dA = dA; bp.trace = nullptr;
   return launch_gcn_bwd(bp, st);
+}
+
+extern "C" int gwn_gcn_bwd_t_supported(int V, int n_supports, int has_da) {
+  return gcn_bwd_t_supported(V, 2 * n_supports, has_da != 0);
+}
+
+extern "C" int gwn_gcn_bwd_t(const void* du, const void* a, const void* b, const void* dz_last, const void* hop_mats,
+                             int n_supports, const float* w_mlp, float drop_p, unsigned long long seed,
+                             unsigned long long offset, int sa, void* dfg, float* dw_mlp, float* db_mlp, float* dA,
+                             float* dQ6, int N, int V, int Lout, int Lf, void* stream) {
+  GWN_REQUIRE(du && a && b && hop_mats && w_mlp && dfg && dw_mlp && db_mlp && n_supports >= 1 && Lf >= 1 && Lf <= Lout,
+              "gcn_bwd_t: bad argument");
+  GWN_REQUIRE(sa < n_supports && (sa < 0 || (dA != nullptr && dQ6 != nullptr)), "gcn_bwd_t: bad support-gradient argument");
+  GWN_REQUIRE(gcn_bwd_t_supported(V, 2 * n_supports, sa >= 0), "gcn_bwd_t: no T-form instance for V=%d with %d supports", V,
+              n_supports);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int mlp_in = 32 * (1 + 2 * n_supports);
+  GWN_CUDA(cudaMemsetAsync(dw_mlp, 0, sizeof(float) * 32 * mlp_in, st));
+  GWN_CUDA(cudaMemsetAsync(db_mlp, 0, sizeof(float) * 32, st));
+  GcnBwdParams bp{};
+  bp.du = reinterpret_cast<const bf16*>(du); bp.a = reinterpret_cast<const bf16*>(a); bp.b = reinterpret_cast<const bf16*>(b);
+  bp.dz_last = reinterpret_cast<const bf16*>(dz_last);
+  bp.RO = (long long)Lout * V; bp.last_begin = (long long)(Lout - Lf) * V; bp.last_rows = (long long)Lf * V;
+  bp.mats = reinterpret_cast<const bf16*>(hop_mats); bp.n_mats = 2 * n_supports;
+  bp.mats_bt = bp.mats + mats_bt_offset(V, n_supports);
+  bp.w_src = w_mlp; bp.mask = nullptr; bp.drop_p = drop_p; bp.seed = seed; bp.offset = offset; bp.rng = nullptr;
+  bp.dfg = reinterpret_cast<bf16*>(dfg); bp.dw_mlp = dw_mlp; bp.db_mlp = db_mlp; bp.V = V; bp.slabs = N * Lout;
+  bp.sa = sa; bp.dA = dA; bp.dQ6 = dQ6; bp.trace = trace_ptr("GWN_GCN_TRACE");
+  { const char* e = getenv("GWN_BT_DEBUG"); bp.debug = e ? atoi(e) : 0; }
+  return launch_gcn_bwd_t(bp, st);
 }
 
 extern "C" int gwn_node_mix(const void* x, int x_pitch, int x_off, void* y, int y_pitch, int y_off, int accumulate,

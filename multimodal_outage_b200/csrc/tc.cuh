@@ -48,6 +48,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
   __trap();  // pipeline protocol bug: fail loudly instead of hanging the GPU
 }
+// Event-driven wait: try_wait with a suspend-time hint parks the thread until the phase completes (or the hint
+// expires) instead of returning after ~30 cycles.  A kernel with ~20 warps parked on barriers otherwise spends more
+// than half of its issue slots in poll loops (ncu: 63 % of the executed instructions of the T-form fused backward),
+// starving the few warps that have work.
+__device__ __forceinline__ uint32_t mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait_park(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
+  for (uint32_t i = 0; i < (1u << 16); ++i) {
+    if (mbar_try_wait_hint(bar, parity, 20000u)) return;
+  }
+  __trap();  // pipeline protocol bug: fail loudly instead of hanging the GPU
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }

@@ -16,6 +16,7 @@
 // Persistent: grid = min(tiles, SMs); each CTA walks tiles of 8 slabs.
 #include "tc.cuh"
 #include "tc_hops.cuh"
+#include "gcn_fused.cuh"
 #include "tma_gemm.cuh"
 
 namespace gwn {
@@ -293,10 +294,12 @@ using namespace gwn;
 
 static int hop_mats_t_kt(int V, int n_supports) { return (((1 + 2 * n_supports) * V + 15) / 16) * 16; }
 
-// the 4 n images [Kp/8][128][8] followed by the stacked T-form image [KT/8][NP][8]
+// the 4 n images [Kp/8][128][8], the stacked T-form image [KT/8][NP][8] of the fused forward, and the stacked
+// transposed-hop image of the T-form fused backward (gcn_fused_bwd_t.cu: BtGeom)
 extern "C" int gwn_hop_mats_bytes(int V, int n_supports) {
   int Kp = ((V + 15) / 16) * 16;
-  return n_supports * 4 * (Kp / 8) * 2048 + hop_mats_t_kt(V, n_supports) * Kp * 2;
+  return n_supports * 4 * (Kp / 8) * 2048 + hop_mats_t_kt(V, n_supports) * Kp * 2 +
+         gcn_bwd_t_image_elems(V, 2 * n_supports) * 2;
 }
 
 extern "C" int gwn_hop_mats_prep(const float* const* supports, int n_supports, int V, void* out, void* stream) {
@@ -313,7 +316,8 @@ extern "C" int gwn_hop_mats_prep(const float* const* supports, int n_supports, i
   hop_mats_t_prep_kernel<<<(unsigned)cdiv((long long)KT * mp.Kp, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       mp, KT, mp.Kp, reinterpret_cast<bf16*>(out) + total);
   GWN_LAUNCHED();
-  return 0;
+  return launch_hop_mats_bt_prep(supports, n_supports, V, reinterpret_cast<bf16*>(out) + total + (long long)KT * mp.Kp,
+                                 reinterpret_cast<cudaStream_t>(stream));
 }
 
 // Test/bench entry: one tensor-core hop  y[slot_out] = Mop[mat] * x[slot_in]  over a pitched bf16 buffer.

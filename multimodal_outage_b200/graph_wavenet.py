@@ -271,7 +271,11 @@ class gwnet(nn.Module):
         if self.gcn_bool:
             supports = list(self.supports)
             if self.addaptadj:                               # graph_wavenet.py:201-203
-                supports = supports + [ops.AdaptiveAdjacency.apply(self.nodevec1, self.nodevec2)]
+                # bf16 path with the supports resident on chip: the adjacency travels as a pair [2,V,V] so the fused
+                # backward can return its gradient in factored form (ops.AdaptiveAdjacency)
+                pair = (dt == torch.bfloat16 and self.use_tensor_cores and training and
+                        ops.hop_mode(V, len(supports) + 1) == 1)
+                supports = supports + [ops.AdaptiveAdjacency.apply(self.nodevec1, self.nodevec2, pair)]
 
         p_drop = float(self.dropout) if (training and self.gcn_bool) else 0.0
         rng = None
@@ -293,7 +297,7 @@ class gwnet(nn.Module):
         # images of (A, A^2, A^T, (A^2)^T) are built once per forward and shared by all layers
         hop_mats = None
         if dt == torch.bfloat16 and supports and self.use_tensor_cores:
-            sup_c = [s.detach().contiguous() for s in supports]
+            sup_c = [(s[0] if s.dim() == 3 else s).detach().contiguous() for s in supports]
             # V <= 80: every support image stays resident in shared memory; larger graphs (the 3,100-node
             # configurations): one TMA-tiled tensor-core GEMM per hop
             # (ops.hop_mode = the C library's own rule: both sides agree on which images the buffer holds)

@@ -83,20 +83,62 @@ def _(e1, e2, adp, d_adp):
     return torch.empty_like(e1), torch.empty_like(e2)
 
 
+@torch.library.custom_op('gwn::adp_fwd_pair', mutates_args=())
+def adp_fwd_pair(e1: Tensor, e2: Tensor) -> Tensor:
+    """The adaptive adjacency as a pair [2,V,V] of identical copies (include/gwn.h: gwn_adp_fwd_pair)."""
+    _req(e1, torch.float32, 'nodevec1'); _req(e2, torch.float32, 'nodevec2')
+    V, R = e1.shape
+    pair = torch.empty((2, V, V), device=e1.device, dtype=torch.float32)
+    with torch.cuda.device(e1.device):
+        check(lib().gwn_adp_fwd_pair(_p(e1), _p(e2), _p(pair), V, R, _stream()), 'gwn_adp_fwd_pair')
+    return pair
+
+
+@adp_fwd_pair.register_fake
+def _(e1, e2):
+    return e1.new_empty((2, e1.shape[0], e1.shape[0]))
+
+
+@torch.library.custom_op('gwn::adp_pair_bwd', mutates_args=())
+def adp_pair_bwd(e1: Tensor, e2: Tensor, pair: Tensor, d_pair: Tensor) -> Tuple[Tensor, Tensor]:
+    """d_pair = (d0, Q) -> d_adp = d0 + A^T Q + Q A^T (fp32) -> softmax / relu / rank-R backward."""
+    _req(d_pair, torch.float32, 'd_pair')
+    V, R = e1.shape
+    de1, de2 = torch.empty_like(e1), torch.empty_like(e2)
+    ws = torch.empty((2, V, V), device=e1.device, dtype=torch.float32)
+    with torch.cuda.device(e1.device):
+        check(lib().gwn_adp_pair_bwd(_p(e1), _p(e2), _p(pair), _p(d_pair), _p(de1), _p(de2), _p(ws), V, R, _stream()),
+              'gwn_adp_pair_bwd')
+    return de1, de2
+
+
+@adp_pair_bwd.register_fake
+def _(e1, e2, pair, d_pair):
+    return torch.empty_like(e1), torch.empty_like(e2)
+
+
 class AdaptiveAdjacency(torch.autograd.Function):
-    """softmax(relu(E1 @ E2), dim=1), warp-per-row fused forward and backward."""
+    """softmax(relu(E1 @ E2), dim=1), warp-per-row fused forward and backward.
+
+    ``pair=True`` returns ``[2,V,V]`` (two identical copies).  A layer that receives the pair as a support may return
+    the gradient in factored form ``(d0, Q)`` - the part reaching the adjacency through its A*A hop
+    (graph_wavenet.py:91-93) is linear in Q = sum (z W_{A^2})[v] . dh[w] - and the backward here completes it once
+    per step in fp32: ``d_adp = d0 + A^T Q + Q A^T`` (csrc/gcn_fused_bwd_t.cu)."""
 
     @staticmethod
-    def forward(ctx, e1, e2):
+    def forward(ctx, e1, e2, pair=False):
         e1c, e2c = e1.contiguous(), e2.contiguous()
-        adp = adp_fwd(e1c, e2c)
+        ctx.pair = bool(pair)
+        adp = adp_fwd_pair(e1c, e2c) if ctx.pair else adp_fwd(e1c, e2c)
         ctx.save_for_backward(e1c, e2c, adp)
         return adp
 
     @staticmethod
     def backward(ctx, d_adp):
         e1, e2, adp = ctx.saved_tensors
-        return adp_bwd(e1, e2, adp, d_adp.contiguous())
+        if ctx.pair:
+            return (*adp_pair_bwd(e1, e2, adp, d_adp.contiguous()), None)
+        return (*adp_bwd(e1, e2, adp, d_adp.contiguous()), None)
 
 
 # =========================================================================== start conv (:191-196)
@@ -383,7 +425,8 @@ def layer_bwd(u_prev: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], 
     dx_bf16 = dt == torch.bfloat16 and hop_mats is not None and taps <= 4
     dx_prev = torch.empty((N, Lin, V, CH), device=dev, dtype=torch.bfloat16 if dx_bf16 else torch.float32)
     # the small accumulated outputs live in ONE zero-filled buffer (one fill kernel instead of six memset nodes)
-    sizes = _layer_bwd_sizes(taps, mlp_in, V, needs_grad, has_du)
+    pairs = [s.dim() == 3 for s in supports]         # [2,V,V] supports take their gradient in factored form (d0, Q)
+    sizes = _layer_bwd_sizes(taps, mlp_in, V, needs_grad, has_du, pairs)
     flat = torch.zeros((sum(sizes),), **f32)
     parts, off = [], 0
     for sz in sizes:
@@ -391,7 +434,7 @@ def layer_bwd(u_prev: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], 
     dx_stats = parts[0].view(torch.float64).view(2, CH)
     dw_fg, db_fg = parts[1].view(taps * CH, 2 * CH), parts[2]
     dw_mlp, db_mlp = parts[3].view(mlp_in, CH), parts[4]
-    d_sup = [parts[5 + i].view(V, V) if (g and has_du) else torch.empty((0,), **f32) for i, g in enumerate(needs_grad)]
+    d_sup = [parts[5 + i] if (g and has_du) else torch.empty((0,), **f32) for i, g in enumerate(needs_grad)]
     ws_cat = torch.empty((P, mlp_in) if has_du else (0,), device=dev, dtype=dt)
     ws_dcat = torch.empty((P, mlp_in) if has_du else (0,), device=dev, dtype=dt)
     ws_dfg = torch.empty((P, 2 * CH), **f32)
@@ -407,22 +450,29 @@ def layer_bwd(u_prev: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], 
     for i, g in enumerate(needs_grad):
         args.support_needs_grad[i] = int(bool(g) and has_du)
         args.d_supports[i] = d_sup[i].data_ptr() if (g and has_du) else None
+        args.d_supports_sq[i] = d_sup[i][V * V:].data_ptr() if (g and has_du and pairs[i]) else None
     with torch.cuda.device(dev):
         check(lib().gwn_layer_bwd(C.byref(cfg), C.byref(args), _stream()), 'gwn_layer_bwd')
     return [dx_prev, flat]
 
 
-def _layer_bwd_sizes(taps: int, mlp_in: int, V: int, needs_grad: Sequence[bool], has_du: bool) -> List[int]:
-    return [2 * 2 * CH, taps * CH * 2 * CH, 2 * CH, mlp_in * CH, CH] + [V * V if (g and has_du) else 0 for g in needs_grad]
+def _layer_bwd_sizes(taps: int, mlp_in: int, V: int, needs_grad: Sequence[bool], has_du: bool,
+                     pairs: Optional[Sequence[bool]] = None) -> List[int]:
+    pairs = pairs if pairs is not None else [False] * len(needs_grad)
+    return [2 * 2 * CH, taps * CH * 2 * CH, 2 * CH, mlp_in * CH, CH] + \
+        [(2 if pr else 1) * V * V if (g and has_du) else 0 for g, pr in zip(needs_grad, pairs)]
 
 
-def _split_layer_bwd(flat: Tensor, taps: int, mlp_in: int, V: int, needs_grad: Sequence[bool], has_du: bool):
-    sizes = _layer_bwd_sizes(taps, mlp_in, V, needs_grad, has_du)
+def _split_layer_bwd(flat: Tensor, taps: int, mlp_in: int, V: int, needs_grad: Sequence[bool], has_du: bool,
+                     pairs: Optional[Sequence[bool]] = None):
+    pairs = pairs if pairs is not None else [False] * len(needs_grad)
+    sizes = _layer_bwd_sizes(taps, mlp_in, V, needs_grad, has_du, pairs)
     parts, off = [], 0
     for sz in sizes:
         parts.append(flat[off:off + sz]); off += sz
     dx_stats = parts[0].view(torch.float64).view(2, CH)
-    d_sup = [parts[5 + i].view(V, V) if sizes[5 + i] else None for i in range(len(needs_grad))]
+    d_sup = [(parts[5 + i].view(2, V, V) if pairs[i] else parts[5 + i].view(V, V)) if sizes[5 + i] else None
+             for i in range(len(needs_grad))]
     return dx_stats, parts[1].view(taps * CH, 2 * CH), parts[2], parts[3].view(mlp_in, CH), parts[4], d_sup
 
 
@@ -434,7 +484,7 @@ def _(u_prev, scale, shift, w_fg, w_mlp, supports, needs_grad, drop_mask, rng, h
     f = lambda *s: u_prev.new_empty(s, dtype=torch.float32)  # noqa: E731
     dx_bf16 = u_prev.dtype == torch.bfloat16 and hop_mats is not None and taps <= 4
     return [u_prev.new_empty((N, Lin, V, CH), dtype=torch.bfloat16 if dx_bf16 else torch.float32),
-            f(sum(_layer_bwd_sizes(taps, mlp_in, V, needs_grad, du is not None)))]
+            f(sum(_layer_bwd_sizes(taps, mlp_in, V, needs_grad, du is not None, [s.dim() == 3 for s in supports])))]
 
 
 class WaveNetLayer(torch.autograd.Function):
@@ -498,7 +548,8 @@ class WaveNetLayer(torch.autograd.Function):
         dx_prev, flat = outs
         n_sup_b = len(sup) if has_du else 0
         dx_stats, dw_fg, db_fg, dw_mlp, db_mlp, d_sup = _split_layer_bwd(
-            flat, m['taps'], CH * (1 + m['order'] * n_sup_b), u_prev.shape[2], ctx.sup_needs if has_du else [], has_du)
+            flat, m['taps'], CH * (1 + m['order'] * n_sup_b), u_prev.shape[2], ctx.sup_needs if has_du else [], has_du,
+            [s.dim() == 3 for s in sup] if has_du else [])
         if ctx.has_bn:
             du_prev, dgamma, dbeta = bn_bwd(dx_prev, u_prev, dx_stats, ctx.count, gamma, mean, rstd, True)
         else:
@@ -744,8 +795,7 @@ def hop_mats(supports: List[Tensor]) -> Tensor:
 @hop_mats.register_fake
 def _(supports):
     V = supports[0].shape[0]
-    Kp = 16 * ((V + 15) // 16)
-    return supports[0].new_empty((len(supports) * 4 * (Kp // 8) * 1024,), dtype=torch.bfloat16)
+    return supports[0].new_empty((lib().gwn_hop_mats_bytes(V, len(supports)) // 2,), dtype=torch.bfloat16)
 
 
 @torch.library.custom_op('gwn::support_images', mutates_args=())

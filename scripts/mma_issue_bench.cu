@@ -43,11 +43,11 @@ __global__ void __launch_bounds__(128, 1) k(int n_mma, int N, long long* out, in
     long long t2 = clock64();
     out[0] = t1 - t0; out[1] = t2 - t0;
     stop = 1;
-  } else if (warp > 0 && side) {
+  } else if (warp > 0 && (side % 10)) {
     // side traffic: side=1 TMEM loads (x32) of this warp's quadrant; side=2 shared-memory 16-byte stores
     float acc = 0.f; int cnt = 0;
     while (!stop) {
-      if (side == 1) {
+      if (side % 10 == 1) {
         float v[32];
         tmem_ld32(tb + ((uint32_t)(warp * 32) << 16) + 256u, v);
         acc += v[lane];
@@ -66,9 +66,9 @@ int main() {
   long long* d; cudaMalloc(&d, 16);
   cudaFuncSetAttribute(k<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
   cudaFuncSetAttribute(k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-  for (int side : {0, 10})
+  for (int side : {0, 1, 2, 10, 11, 12})
   for (int mode = 0; mode < 1; ++mode)
-    for (int N : {32, 64, 128, 256}) {
+    for (int N : {32, 80, 128, 256}) {
       const int n = 3000;
       for (int rep = 0; rep < 2; ++rep) {
         if (mode == 0) k<0><<<1, 128, 128 * 1024>>>(n, N, d, side); else k<1><<<1, 128, 128 * 1024>>>(n, N, d, side);

@@ -690,3 +690,116 @@ def test_fused_forward_kernel_shapes_against_torch(V, n_sup, N, Lout, Lin):
     assert torch.allclose(got_mean, ref.mean(dim=(0, 1, 2)), atol=3e-2), (got_mean - ref.mean(dim=(0, 1, 2))).abs().max()
     got_sq = (stats[32:] / cnt).float()
     assert rel(got_sq, (ref * ref).mean(dim=(0, 1, 2))) < 3e-2
+
+
+def _gcn_bwd_reference(du, a, b, dz_last, sups, w_mlp, sa, Lf):
+    """fp64 restatement of the fused diffusion backward (graph_wavenet.py:76-98 backward + gate backward :222-226) on
+    the bf16-rounded inputs; the support gradient comes from autograd of h = sum_j Mt_j-hop(z W_j)."""
+    dd = torch.float64
+    dh = du.double().cpu()
+    af, bfl = a.double().cpu(), b.double().cpu()
+    z = (a.float() * b.float()).to(torch.bfloat16).double().cpu()
+    W = w_mlp.double().cpu()
+    A = [s.double().cpu().clone() for s in sups]
+    if sa >= 0:
+        A[sa].requires_grad_(True)
+    mts = []
+    for s in A:
+        mts += [s, s @ s]
+    dU = [dh] + [torch.einsum('vw,nlwc->nlvc', m.detach(), dh) for m in mts]
+    dz = sum(dU[j] @ W[32 * j:32 * j + 32].T for j in range(len(dU)))
+    dW = torch.cat([torch.einsum('nlvc,nlvd->cd', z, dU[j]) for j in range(len(dU))], dim=0)
+    db = dh.sum(dim=(0, 1, 2))
+    if dz_last is not None:
+        dz[:, -Lf:] += dz_last.double().cpu()
+    df = dz * bfl * (1 - af * af)
+    dg = dz * af * bfl * (1 - bfl)
+    dfg = torch.stack([df, dg], dim=-1).flatten(-2)
+    dA = None
+    if sa >= 0:
+        h = sum(torch.einsum('vw,nlvc->nlwc', m, z @ W[32 * (j + 1):32 * (j + 2)]) for j, m in enumerate(mts))
+        (h * dh).sum().backward()
+        dA = A[sa].grad
+    return dfg, dW, db, dA
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('V,n_sup,N,Lout,Lf,sa', [(67, 3, 3, 3, 1, 2), (67, 3, 2, 13, 13, 2), (67, 3, 5, 1, 1, -1),
+                                                  (67, 2, 3, 2, 1, -1), (67, 1, 2, 3, 2, 0), (72, 3, 2, 2, 1, 2),
+                                                  (65, 3, 1, 5, 2, 1), (64, 3, 2, 3, 1, 2), (40, 3, 3, 2, 1, 2),
+                                                  (33, 2, 3, 3, 1, 1), (20, 3, 5, 2, 2, 2), (5, 3, 7, 1, 1, 2),
+                                                  (32, 3, 2, 2, 1, 0)])
+def test_transposed_fused_diffusion_backward_kernel(V, n_sup, N, Lout, Lf, sa):
+    """The T-form fused diffusion backward (csrc/gcn_fused_bwd_t.cu) through its C-ABI entry on shapes that exercise its
+    edges: ragged last group of four slabs, node ranges of 32 / 8 / 24 nodes, 1-3 supports, with and without the
+    adaptive-support gradient (delivered factored: dA = d0 + A^T Q + Q A^T), with and without tail rows (dz_last)."""
+    from multimodal_outage_b200 import _lib, ops
+    lib = _lib.lib()
+    if not lib.gwn_gcn_bwd_t_supported(V, n_sup, int(sa >= 0)):
+        pytest.skip('no T-form instance for this shape (the node-major kernel runs instead)')
+    torch.manual_seed(V * 1000 + n_sup * 10 + N)
+    dev, bf = 'cuda', torch.bfloat16
+    sups = [torch.softmax(torch.randn(V, V, device=dev), dim=1).contiguous() for _ in range(n_sup)]
+    mats = ops.hop_mats(sups)
+    H = 2 * n_sup
+    du = torch.randn(N, Lout, V, 32, device=dev).to(bf)
+    a = torch.tanh(torch.randn(N, Lout, V, 32, device=dev)).to(bf)
+    b = torch.sigmoid(torch.randn(N, Lout, V, 32, device=dev)).to(bf)
+    dz_last = torch.randn(N, Lf, V, 32, device=dev).to(bf)
+    w_mlp = (torch.randn(32 * (1 + H), 32, device=dev) / (32 * (1 + H)) ** 0.5).contiguous()
+    dfg = torch.zeros(N, Lout, V, 64, device=dev, dtype=bf)
+    dw = torch.empty(32 * (1 + H), 32, device=dev)
+    db = torch.empty(32, device=dev)
+    dA = torch.zeros(V, V, device=dev)
+    dQ = torch.zeros(V, V, device=dev)
+    _lib.check(lib.gwn_gcn_bwd_t(du.data_ptr(), a.data_ptr(), b.data_ptr(), dz_last.data_ptr(), mats.data_ptr(), n_sup,
+                                 w_mlp.data_ptr(), 0.0, 1, 0, sa, dfg.data_ptr(), dw.data_ptr(), db.data_ptr(),
+                                 dA.data_ptr() if sa >= 0 else None, dQ.data_ptr() if sa >= 0 else None, N, V, Lout, Lf,
+                                 torch.cuda.current_stream().cuda_stream), 'gwn_gcn_bwd_t')
+    torch.cuda.synchronize()
+    r_dfg, r_dw, r_db, r_dA = _gcn_bwd_reference(du, a, b, dz_last, sups, w_mlp, sa, Lf)
+    assert rel(dfg.float(), r_dfg) < BF16_TOL, rel(dfg.float(), r_dfg)
+    assert rel(dw, r_dw) < BF16_TOL, rel(dw, r_dw)
+    assert rel(db, r_db) < 1e-2, rel(db, r_db)
+    if sa >= 0:
+        A = sups[sa].double().cpu()
+        full = dA.double().cpu() + A.T @ dQ.double().cpu() + dQ.double().cpu() @ A.T
+        assert rel(full, r_dA) < BF16_TOL, rel(full, r_dA)
+
+
+@pytest.mark.gpu
+def test_transposed_fused_backward_draws_the_same_dropout_mask_as_the_node_major_kernel():
+    """Same Philox stream in both fused backward kernels: with dropout on, dfg / dW / db agree to accumulation-order
+    noise, and the factored support gradient completes to the node-major kernel's dA."""
+    from multimodal_outage_b200 import _lib, ops
+    lib = _lib.lib()
+    V, n_sup, N, Lout, Lf, sa = 67, 3, 6, 3, 1, 2
+    torch.manual_seed(5)
+    dev, bf = 'cuda', torch.bfloat16
+    sups = [torch.softmax(torch.randn(V, V, device=dev), dim=1).contiguous() for _ in range(n_sup)]
+    mats = ops.hop_mats(sups)
+    du = torch.randn(N, Lout, V, 32, device=dev).to(bf)
+    a = torch.tanh(torch.randn(N, Lout, V, 32, device=dev)).to(bf)
+    b = torch.sigmoid(torch.randn(N, Lout, V, 32, device=dev)).to(bf)
+    dz_last = torch.randn(N, Lf, V, 32, device=dev).to(bf)
+    w_mlp = (torch.randn(32 * 7, 32, device=dev) / 15.0).contiguous()
+    ws_w = torch.empty(131072, device=dev, dtype=torch.uint8)
+    st = torch.cuda.current_stream().cuda_stream
+    out = []
+    for t_form in (False, True):
+        dfg = torch.zeros(N, Lout, V, 64, device=dev, dtype=bf)
+        dw, db = torch.empty(32 * 7, 32, device=dev), torch.empty(32, device=dev)
+        dA, dQ = torch.zeros(V, V, device=dev), torch.zeros(V, V, device=dev)
+        if t_form:
+            _lib.check(lib.gwn_gcn_bwd_t(du.data_ptr(), a.data_ptr(), b.data_ptr(), dz_last.data_ptr(), mats.data_ptr(),
+                                         n_sup, w_mlp.data_ptr(), 0.3, 1234, 7, sa, dfg.data_ptr(), dw.data_ptr(),
+                                         db.data_ptr(), dA.data_ptr(), dQ.data_ptr(), N, V, Lout, Lf, st), 'gwn_gcn_bwd_t')
+        else:
+            _lib.check(lib.gwn_gcn_bwd(du.data_ptr(), a.data_ptr(), b.data_ptr(), dz_last.data_ptr(), mats.data_ptr(),
+                                       n_sup, w_mlp.data_ptr(), ws_w.data_ptr(), 0.3, 1234, 7, sa, dfg.data_ptr(),
+                                       dw.data_ptr(), db.data_ptr(), dA.data_ptr(), N, V, Lout, Lf, st), 'gwn_gcn_bwd')
+        torch.cuda.synchronize()
+        A = sups[sa]
+        out.append((dfg.float(), dw, db, dA + A.T @ dQ + dQ @ A.T))
+    for x, y, tol in zip(out[1], out[0], (1e-2, 1e-2, 5e-3, 1e-2)):
+        assert rel(x, y) < tol, rel(x, y)
