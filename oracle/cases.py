@@ -67,3 +67,32 @@ def case_inputs(name: str):
     if c.get('literal'):
         return rng.standard_normal((cfg.num_nodes, c['horizon'], cfg.in_dim)).astype(np.float32), rng
     return rng.standard_normal((c['n'], cfg.in_dim, cfg.num_nodes, c['t_in'])).astype(np.float32), rng
+
+
+def synthetic_module_state(state_shapes, seed: int):
+    """Deterministic (numpy PCG64) values for an arbitrary module ``state_dict`` given as an ordered list of
+    ``(key, shape, dtype_str)``: fan-in scaled weights, BatchNorm scales near 1, positive running variances, zero
+    counters.  Shared by tests/golden/make_golden_unet.py (which fills the REFERENCE classes with it) and the tests
+    (which fill this repo's modules with it), so no weights need to be stored."""
+    import torch
+    rng = np.random.default_rng(seed)
+    out = {}
+    for key, shape, dtype in state_shapes:
+        shape = tuple(int(s) for s in shape)
+        if key.endswith('num_batches_tracked'):
+            out[key] = torch.zeros((), dtype=torch.int64)
+            continue
+        v = rng.standard_normal(shape if shape else (1,)).astype(np.float32).reshape(shape)
+        if key.endswith('running_var'):
+            v = np.abs(v) + 0.5
+        elif key.endswith('running_mean'):
+            v = 0.1 * v
+        elif len(shape) == 1 and key.endswith('weight'):          # BatchNorm scale
+            v = 1.0 + 0.1 * v
+        elif len(shape) == 1:                                      # biases
+            v = 0.1 * v
+        else:
+            fan_in = int(np.prod(shape[1:]))
+            v = v / np.sqrt(max(fan_in, 1))
+        out[key] = torch.tensor(v)
+    return out
