@@ -248,7 +248,7 @@ def kernel_rooflines(peaks, n):
     peak_tf_sus = peaks.get('bf16_tflops_sustained', 1400.0)
     src = 'MEASURED_PEAKS.json' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
     try:
-        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')))
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
     except Exception:
         traffic = {}
     V, C32 = 67, 32
@@ -299,28 +299,30 @@ def kernel_rooflines(peaks, n):
     dzl = torch.randn(N, 1, V, C32, device=dev).to(bf)
     dw_m, db_m, dA_m = torch.zeros(224, 32, device=dev), torch.zeros(32, device=dev), torch.zeros(V, V, device=dev)
 
+    dQ_m = torch.zeros(V, V, device=dev)
+
     def gcnb(i):
         def f():
-            _lib.check(lib.gwn_gcn_bwd(dus[i].data_ptr(), aas[i].data_ptr(), bbs[i].data_ptr(), dzl.data_ptr(), mats.data_ptr(),
-                                       3, w_mlp.data_ptr(), ws_w.data_ptr(), 0.3, 42, i, 2, dfgs[i].data_ptr(), dw_m.data_ptr(),
-                                       db_m.data_ptr(), dA_m.data_ptr(), N, V, L[1], 1, st()), 'gwn_gcn_bwd')
+            _lib.check(lib.gwn_gcn_bwd_t(dus[i].data_ptr(), aas[i].data_ptr(), bbs[i].data_ptr(), dzl.data_ptr(), mats.data_ptr(),
+                                         3, w_mlp.data_ptr(), 0.3, 42, i, 2, dfgs[i].data_ptr(), dw_m.data_ptr(),
+                                         db_m.data_ptr(), dA_m.data_ptr(), dQ_m.data_ptr(), N, V, L[1], 1, st()), 'gwn_gcn_bwd_t')
         return f
     ms_b = graph_time([gcnb(i) for i in range(R)])
-    flops_b = P * (6 * 2.0 * C32 * V + 2 * 2.0 * 224 * 32 + 2.0 * 32 * 64 + 2.0 * C32 * V + 2 * 2.0 * C32 * V)
+    flops_b = P * (6 * 2.0 * C32 * V + 2 * 2.0 * 224 * 32 + 2.0 * 32 * 64 + 2 * 2.0 * C32 * V)
     byts_b = 5.0 * P * 64
-    roof_bwd = {'kernel': 'gcn_bwd_kernel (fused diffusion backward: dropout mask, 6 transposed hops, mlp data + weight '
-                          'gradients, adaptive-support gradient, gate backward; config-2 layer 0: 6144 slabs of 67 nodes; '
-                          'includes its output memsets)',
+    roof_bwd = {'kernel': 'gcn_bwd_t_kernel (fused diffusion backward, transposed hops over groups of 4 slabs: dropout mask, 6 '
+                          'transposed hops, mlp data + weight gradients, factored adaptive-support gradient, gate backward; '
+                          'config-2 layer 0: 6144 slabs of 67 nodes)',
                 'bound': 'hbm', 'achieved': byts_b / (ms_b * 1e-3) / 1e9, 'peak': peak_bw, 'unit': 'GB/s',
-                'frac': byts_b / (ms_b * 1e-3) / 1e9 / peak_bw, 'traffic': traffic.get('gcn_bwd_kernel', {}).get('bytes'),
-                'traffic_source': traffic.get('gcn_bwd_kernel', {}).get('source'),
+                'frac': byts_b / (ms_b * 1e-3) / 1e9 / peak_bw, 'traffic': traffic.get('gcn_bwd_t_kernel', {}).get('bytes'),
+                'traffic_source': traffic.get('gcn_bwd_t_kernel', {}).get('source'),
                 'algorithmic_bytes_per_launch': byts_b, 'algorithmic_flops_per_launch': flops_b, 'ms_per_launch': ms_b,
                 'tensor_tflops': flops_b / (ms_b * 1e-3) / 1e12, 'tensor_frac_of_burst_peak': flops_b / (ms_b * 1e-3) / 1e12 / peak_tf,
-                'note': 'algorithmic bytes = read du, a, b + write dfg (5 x 64 B per position); 71 kflop per position -> 222 '
-                        'flop/B, at the ridge like the forward: HBM time 20 us, tensor time 21 us.  The kernel is bound by '
-                        'its 65 small-N tcgen05.mma per slab (43 cycles each: the 128-row A operand read from shared '
-                        'memory) and by TMEM->smem hand-offs (DESIGN.md section 3, scripts/gpu_gcn_bwd_trace.py); the '
-                        'transposed form the forward already uses is the planned fix', 'peak_source': src}
+                'note': 'algorithmic bytes = read du, a, b + write dfg (5 x 64 B per position); ~70 kflop per position -> 220 '
+                        'flop/B, at the ridge like the forward: HBM time 20 us, tensor time 21 us.  The kernel is bound by the '
+                        'shared-memory / L1 data path (DESIGN.md section 3): ~870 KB of operand reads and staging writes per '
+                        'group of four slabs for 86 KB of HBM traffic - the N = 32 weight GEMMs re-read a 4 KB A tile per '
+                        '1 KB of B', 'peak_source': src}
     del dus, aas, bbs, dfgs
 
     # ---- gated temporal conv (layer 0, inference form: read r once, write z once)

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libgwn.so')
+LIB_PATH = os.environ.get('GWN_LIB') or os.path.join(HERE, 'libgwn.so')     # GWN_LIB: a debug build (libgwn_trace.so)
 
 GWN_F32, GWN_BF16 = 0, 1
 MAX_SUPPORTS, MAX_TAPS, MAX_LAYERS = 4, 8, 32

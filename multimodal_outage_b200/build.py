@@ -17,8 +17,18 @@ STAMP = os.path.join(HERE, 'libgwn.so.stamp')
 SOURCES = ['api.cu', 'adp.cu', 'layer.cu', 'head.cu', 'comm.cu', 'tc_hops.cu', 'tc_wgrad.cu', 'tc_gemm.cu', 'tma_gemm.cu', 'head_tc.cu', 'gcn_fused.cu', 'gcn_fused_bwd.cu', 'gcn_fused_bwd_t.cu', 'start_tc.cu', 'pack.cu', 'gcn_fused_t.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr', '-Xptxas', '-v']
-if os.environ.get('GWN_TRACE') == '1':       # debug build: clock64 timeline hooks read GWN_*_TRACE (scripts/gpu_*_trace.py)
+TRACE = os.environ.get('GWN_TRACE') == '1'    # debug build: clock64 timeline hooks read GWN_*_TRACE (scripts/gpu_*_trace.py)
+if TRACE:                                     # goes to its own library (libgwn_trace.so, loaded with GWN_LIB=...) beside the product
     NVCC_FLAGS.append('-DGWN_TRACE')
+    LIB = os.path.join(HERE, 'libgwn_trace.so')
+    STAMP = LIB + '.stamp'
+
+
+VARIANT = os.environ.get('GWN_VARIANT')        # experiment builds: GWN_VARIANT=name GWN_DEFINES="-DX=1 ..." -> libgwn_<name>.so
+if VARIANT:
+    NVCC_FLAGS += os.environ.get('GWN_DEFINES', '').split()
+    LIB = os.path.join(HERE, f'libgwn_{VARIANT}.so')
+    STAMP = LIB + '.stamp'
 
 
 def _fingerprint() -> str:
@@ -39,9 +49,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, 'build'), exist_ok=True)
+    bdir = os.path.join(HERE, 'build', VARIANT or ('trace' if TRACE else ''))
+    os.makedirs(bdir, exist_ok=True)
     for src in SOURCES:
-        obj = os.path.join(HERE, 'build', src.replace('.cu', '.o'))
+        obj = os.path.join(bdir, src.replace('.cu', '.o'))
         objs.append(obj)
         cmd = [nvcc, *NVCC_FLAGS, '-c', os.path.join(CSRC, src), '-o', obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -55,7 +66,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f'link failed:\n{r.stdout}')
-    with open(os.path.join(HERE, 'build', 'ptxas.log'), 'w') as f:
+    with open(os.path.join(bdir, 'ptxas.log'), 'w') as f:
         f.write('\n'.join(log))
     with open(STAMP, 'w') as f:
         f.write(fp)

@@ -13,8 +13,8 @@ for r in rows[hi + 1:]:
         v /= 1000
     seq.append((r[ki], v))
 idx = [i for i, s in enumerate(seq) if 'start_fwd' in s[0]]
-a = idx[0]
-b = idx[1] if len(idx) > 1 else len(seq)
+# the last complete step in the capture (the first ones carry one-time optimizer-state fills)
+a, b = (idx[-2], idx[-1]) if len(idx) > 1 else (idx[0], len(seq))
 step = seq[a:b]
 tot = sum(s[1] for s in step)
 print(f'one step: {len(step)} launches, {tot:.0f} us of (cold-cache, serialised) kernel time')
