@@ -193,6 +193,12 @@ int gwn_gcn_bwd(const void* du, const void* a, const void* b, const void* dz_las
                 unsigned long long offset, int sa, void* dfg, float* dw_mlp, float* db_mlp, float* dA,
                 int N, int V, int Lout, int Lf, void* stream);
 
+/* The fused dropout stream on its own (graph_wavenet.py:97, F.dropout(h, p, training)): out = x * mask over `rows` rows of
+ * 32 bf16 channels, mask = the Philox4x32-7 keep-mask {seed, offset, element} every fused kernel draws (0 or
+ * 256 / (256 - round(256 p))).  Used by the statistical tests of the stream; the layer kernels apply it in their epilogues. */
+int gwn_dropout_apply(const void* x, void* out, long long rows, float p, unsigned long long seed,
+                      unsigned long long offset, void* stream);
+
 /* ---- BatchNorm2d(32) folded to an affine  graph_wavenet.py:167,250 ----
  * training: mean/var from stats (count = N*L*V), scale = gamma*rstd, shift = beta - mean*scale,
  *           running <- (1-m)*running + m*(mean, unbiased var); saves mean,rstd.

@@ -108,6 +108,7 @@ SIGNATURES = {
     'gwn_gcn_bwd_t_supported': (_i, [_i, _i, _i]),
     'gwn_gcn_bwd_t': (_i, [vp, vp, vp, vp, vp, _i, vp, _f, C.c_uint64, C.c_uint64, _i, vp, vp, vp, vp, vp, _i, _i, _i, _i, vp]),
     'gwn_gcn_bwd': (_i, [vp, vp, vp, vp, vp, _i, vp, vp, _f, C.c_uint64, C.c_uint64, _i, vp, vp, vp, vp, _i, _i, _i, _i, vp]),
+    'gwn_dropout_apply': (_i, [vp, vp, _ll, _f, C.c_uint64, C.c_uint64, vp]),
     'gwn_bn_fold': (_i, [vp, _d, vp, vp, vp, vp, _f, _f, _i, vp, vp, vp, vp, vp]),
     'gwn_bn_bwd': (_i, [vp, _i, vp, _i, vp, _d, vp, vp, vp, _i, vp, vp, vp, _ll, vp]),
     'gwn_head_fwd': (_i, [C.POINTER(HeadCfg), C.POINTER(HeadFwdArgs), vp]),

@@ -1296,6 +1296,16 @@ extern "C" int gwn_gcn_bwd(const void* du, const void* a, const void* b, const v
   return launch_gcn_bwd(bp, st);
 }
 
+extern "C" int gwn_dropout_apply(const void* x, void* out, long long rows, float p, unsigned long long seed,
+                                 unsigned long long offset, void* stream) {
+  GWN_REQUIRE(x && out && rows >= 0 && p >= 0.f && p < 1.f, "dropout_apply: bad argument");
+  if (rows == 0) return 0;
+  drop_bwd_kernel<bf16><<<(unsigned)cdiv(rows * 8, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const bf16*>(x), nullptr, p, seed, offset, nullptr, reinterpret_cast<bf16*>(out), rows);
+  GWN_LAUNCHED();
+  return 0;
+}
+
 extern "C" int gwn_gcn_bwd_t_supported(int V, int n_supports, int has_da) {
   return gcn_bwd_t_supported(V, 2 * n_supports, has_da != 0);
 }

@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
     bf16* img = reinterpret_cast<bf16*>(w_s);
     // 16-byte loads of the fp32 weights (a thread owns 4 consecutive output columns - or, transposed, 4 consecutive
     // K rows - of one row), all of a thread's loads issued before the first use.  The shift-into-bias partial sums go
-    // through a scratch array in the (still idle) first TMA stage and are added in a FIXED order: every CTA must
+    // through a scratch array in the (still idle, contiguous) TMA stages and are added in a FIXED order: every CTA must
     // build bit-identical images (atomics would make a sample's result depend on which CTA computed it).
     float* part_s = reinterpret_cast<float*>(a_s);                    // [PGT_THREADS][4]
     const int N4 = N >> 2, total4 = (K * N) >> 2;
@@ -543,7 +543,7 @@ int launch_pos_gemm_tc(PgParams& p, const Epi& epi, cudaStream_t st) {
   if (p.wsrc.W) {
     GWN_REQUIRE(32 * p.n_chunks * p.N <= 16 * PGT_THREADS && p.N % 4 == 0 && p.wsrc.ld % 4 == 0,
                 "pos_gemm_tc: weight image %d x %d too large for the in-kernel build", 32 * p.n_chunks, p.N);
-    GWN_REQUIRE(!p.wsrc.bn || (!p.wsrc.transposed && PGT_THREADS % (p.N / 4) == 0 && a_bytes >= 16 * PGT_THREADS),
+    GWN_REQUIRE(!p.wsrc.bn || (!p.wsrc.transposed && PGT_THREADS % (p.N / 4) == 0 && stages * a_bytes >= 16 * PGT_THREADS),
                 "pos_gemm_tc: BatchNorm fold needs N/4 to divide the CTA size");
     GWN_REQUIRE((reinterpret_cast<unsigned long long>(p.wsrc.W) & 15ull) == 0, "pos_gemm_tc: weights must be 16-byte aligned");
   }

@@ -715,6 +715,11 @@ def head_tc_supported(P: int, S: int, E: int) -> bool:
     return S % 64 == 0 and E % 64 == 0 and P < 2 ** 31
 
 
+# parity-test hook: a dict here receives the saved head activations of the next bf16 forward ('s1': [P, hi | lo] of
+# relu(skip), 'e1': relu(end_conv_1)) - the ReLU decisions the backward will use (tests/gpu_helpers.captured_head_masks)
+HEAD_CAPTURE: Optional[dict] = None
+
+
 class SkipHead(torch.autograd.Function):
     """relu(sum_i Ws_i z_i[..., -Lf:] + sum_i bs_i) -> relu(end_conv_1) -> end_conv_2, NCHW out."""
 
@@ -727,6 +732,8 @@ class SkipHead(torch.autograd.Function):
             zcat = torch.cat(z_last, dim=-1)
             out, s1, e1 = head_fwd_tc(zcat, w_skip, b_skip, w_end1, b_end1, w_end2, b_end2, out_dim)
             ctx.save_for_backward(w_skip, w_end1, w_end2, s1, e1, zcat)
+            if HEAD_CAPTURE is not None:
+                HEAD_CAPTURE.update(s1=s1.detach().clone(), e1=e1.detach().clone())
             return out
         zs = [z.contiguous() for z in z_last]
         out, s1, e1 = head_fwd(zs, w_skip, b_skip, w_end1, b_end1, w_end2, b_end2, out_dim)

@@ -30,7 +30,7 @@ def rel(a, b):
 
 
 def oracle_run(cfg, sd, x_np, sup_np, target_np=None, literal=False, horizon=None, dtype=torch.float64,
-               dropout_masks=None, training=True, storage=None):
+               dropout_masks=None, training=True, storage=None, head_masks=None):
     """Runs the CPU oracle (fp64 by default); returns out, loss, grads dict, trace."""
     sdo = {}
     for k, v in sd.items():
@@ -43,10 +43,10 @@ def oracle_run(cfg, sd, x_np, sup_np, target_np=None, literal=False, horizon=Non
     tr = ForwardTrace()
     if literal:
         out = gwnet_forward_literal(sdo, x, sup, cfg, horizon, training=training, trace=tr,
-                                    dropout_masks=dropout_masks, storage=storage)
+                                    dropout_masks=dropout_masks, storage=storage, head_masks=head_masks)
     else:
         out = gwnet_forward(sdo, x, sup, cfg, training=training, trace=tr, dropout_masks=dropout_masks,
-                            storage=storage)
+                            storage=storage, head_masks=head_masks)
     loss = None
     grads = {}
     if target_np is not None and training:
@@ -81,3 +81,13 @@ def compare_grads(model, grads, tol, report=None):
         if not err <= tol:
             bad.append((k, err))
     return bad
+
+
+def captured_head_masks(cap, n, v, lf):
+    """ReLU decisions of the CUDA head (ops.HEAD_CAPTURE after a bf16 forward) as oracle-layout 0/1 masks
+    ([N,S,V,Lf], [N,E,V,Lf]).  s1 is saved as [P, hi | lo] of relu(skip), e1 as relu(end_conv_1)."""
+    s1, e1 = cap['s1'].float(), cap['e1'].float()
+    S = s1.shape[1] // 2
+    m1 = ((s1[:, :S] != 0) | (s1[:, S:] != 0)).view(n, lf, v, S).permute(0, 3, 2, 1).double().cpu()
+    m2 = (e1 != 0).view(n, lf, v, -1).permute(0, 3, 2, 1).double().cpu()
+    return m1, m2

@@ -13,7 +13,7 @@ from oracle.cases import GOLDEN_CASES, GOLDEN_DIR, case_inputs, case_supports
 from oracle.graph_oracle import double_transition, synthetic_directed_graph, synthetic_knn_graph
 from oracle.gwnet_oracle import (GWNetConfig, adaptive_adjacency, adaptive_adjacency_backward, layer_lengths,
                                  node_mix)
-from gpu_helpers import build_model, compare_grads, load_synth, oracle_run, rel
+from gpu_helpers import build_model, captured_head_masks, compare_grads, load_synth, oracle_run, rel
 
 pytestmark = pytest.mark.gpu
 FP32_TOL = 1e-4
@@ -82,44 +82,56 @@ def _oracle_case(cfg, sup, n, t_in, seed, dtype, tol, masks=False, autocast=Fals
         dm_g = [torch.tensor(d, device='cuda') for d in dm_np]
     bf16 = autocast or dtype == torch.bfloat16
     out_o, loss_o, grads, tr = oracle_run(cfg, sd, x_np, sup, y_np, dropout_masks=dm_o)
-    if bf16:
-        # Gradients of a ReLU network are discontinuous in the activations: the ~2^-9 noise of ANY bf16
-        # evaluation flips ~0.3% of the head's relu masks, which moves per-tensor gradient L2 by
-        # ~sqrt(0.003) = 5% against an exact oracle (the reference's own bf16-autocast run differs from
-        # its fp32 run by 7.5e-2..1.2e-1).  Activations and loss are checked against
-        # the exact oracle; gradients against the oracle evaluated with the SAME 16-bit storage points
-        # (oracle `storage=`), where the 2e-2 bar is meaningful.  See DESIGN.md "bf16 parity".
-        out_s, loss_s, grads_s, tr_s = oracle_run(cfg, sd, x_np, sup, y_np, dropout_masks=dm_o,
-                                                  storage=torch.bfloat16)
     x = torch.tensor(x_np, device='cuda', requires_grad=True)
     m.train()
-    if autocast:
-        with torch.autocast('cuda', dtype=torch.bfloat16):
+    from multimodal_outage_b200 import ops
+    ops.HEAD_CAPTURE = {} if bf16 else None
+    try:
+        if autocast:
+            with torch.autocast('cuda', dtype=torch.bfloat16):
+                out = m(x, dropout_masks=dm_g)
+        else:
+            m.compute_dtype = dtype
             out = m(x, dropout_masks=dm_g)
-    else:
-        m.compute_dtype = dtype
-        out = m(x, dropout_masks=dm_g)
+    finally:
+        cap, ops.HEAD_CAPTURE = ops.HEAD_CAPTURE, None
     assert out.dtype == torch.float32
     assert rel(out, out_o) < tol, rel(out, out_o)
     loss = torch.nn.functional.mse_loss(out, torch.tensor(y_np, device='cuda'))
     assert abs(loss.item() - loss_o.item()) < tol * abs(loss_o.item())
     loss.backward()
     if bf16:
-        # Gradients of a ReLU network are discontinuous in its activations: 2^-9 activation noise flips
-        # ~0.3% of the head's relu masks and moves per-tensor gradient L2 by ~sqrt(0.003) ~ 5% (error
-        # scales with sqrt(eps), DESIGN.md "bf16 parity"; the reference's own bf16-autocast run is
-        # 7.5e-2..1.2e-1 away from its fp32 run).  So at whole-model scope the bar is:
-        # the CUDA path is as close to the exact oracle as the bf16-storage oracle is.  The 2e-2 bar on
-        # gradients is enforced per op, on identical inputs, in test_bf16_layer_op_fwd_bwd_vs_oracle.
-        worst_k, worst_s = 0.0, 0.0
-        gx, gxs = grads.pop('__x__'), grads_s.pop('__x__')
-        pairs = [(x.grad, gx, gxs)] + [(p.grad, grads[k], grads_s[k]) for k, p in m.named_parameters()
-                                        if grads.get(k) is not None and not (k.endswith('bias') and 'gconv' in k)]
-        for g_k, g_e, g_s in pairs:
-            worst_k = max(worst_k, rel(g_k, g_e)); worst_s = max(worst_s, rel(g_s, g_e))
-        print(f'bf16 whole-model: out vs exact {rel(out, out_o):.2e}; worst grad tensor vs exact: '
-              f'CUDA {worst_k:.2e}, bf16-storage oracle {worst_s:.2e}')
-        assert worst_k <= 2.0 * worst_s + tol and worst_k < 0.15
+        # Output and loss: 2e-2 against the exact fp64 oracle (above).  Gradients: a ReLU network is piecewise linear in
+        # its activations, and ANY 16-bit evaluation flips ~0.15 % of the head's ReLU decisions (measured:
+        # profiles/r2_bf16_grad_parity.json), which alone moves per-tensor gradient L2 by 4-10 % at these batch sizes -
+        # the bf16-storage oracle shows the same figures, and so does the reference's own autocast run (7.5e-2 .. 1.2e-1,
+        # SURVEY App. C.4).  Two FIXED bars:
+        #  (1) with the head's ReLU decisions pinned to the ones the CUDA run took (the masks its backward used), every
+        #      gradient tensor is within the north-star 2e-2 of the exact fp64 oracle - everything that is smooth is held
+        #      to the stated tolerance;
+        #  (2) unpinned, every gradient tensor is within 0.12 of the exact oracle (the reference's own bf16-vs-fp32 spread).
+        m1, m2 = captured_head_masks(cap, n, cfg.num_nodes, L[-1])
+        _, _, grads_p, _ = oracle_run(cfg, sd, x_np, sup, y_np, dropout_masks=dm_o, head_masks=(m1, m2))
+        flips = float(((tr.skip.detach() > 0).double() != m1).double().mean())
+        worst_p, worst_e, worst_name = 0.0, 0.0, ''
+        names = ['__x__'] + [k for k, p in m.named_parameters()
+                             if grads.get(k) is not None and not (k.endswith('bias') and 'gconv' in k)]
+        for k in names:
+            g_k = x.grad if k == '__x__' else dict(m.named_parameters())[k].grad
+            e_p, e_e = rel(g_k, grads_p[k]), rel(g_k, grads[k])
+            if k.endswith('bias') and k != '__x__' and not k.startswith('bn.'):
+                # conv biases feeding a training-mode BatchNorm have an analytically zero gradient (noise / noise)
+                wk = k[:-4] + 'weight'
+                scale = float(grads_p[wk].norm()) if grads_p.get(wk) is not None else 0.0
+                if float(grads_p[k].norm()) < 1e-6 * max(scale, 1e-30):
+                    continue
+            if e_p > worst_p:
+                worst_p, worst_name = e_p, k
+            worst_e = max(worst_e, e_e)
+        print(f'bf16 whole-model: out {rel(out, out_o):.2e}; {100 * flips:.2f}% head ReLU decisions flipped; worst gradient '
+              f'tensor vs exact fp64: {worst_e:.2e} unpinned, {worst_p:.2e} with the head decisions pinned ({worst_name})')
+        assert worst_p < BF16_TOL, (worst_name, worst_p)
+        assert worst_e < 0.12, worst_e
         return m, []
     assert rel(x.grad, grads.pop('__x__')) < tol
     rep = []
@@ -803,3 +815,127 @@ def test_transposed_fused_backward_draws_the_same_dropout_mask_as_the_node_major
         out.append((dfg.float(), dw, db, dA + A.T @ dQ + dQ @ A.T))
     for x, y, tol in zip(out[1], out[0], (1e-2, 1e-2, 5e-3, 1e-2)):
         assert rel(x, y) < tol, rel(x, y)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# bf16 tensor-core path at the shapes the benchmarked / reference configurations use beyond dilation 1-2 and k = 2
+@pytest.mark.parametrize('dil,Lin', [(4, 7), (8, 11)])
+def test_bf16_layer_op_config5_dilations(dil, Lin):
+    """Config 5's layers run dilations 4 and 8 (4x4 layers): every output and gradient of the layer op within 2e-2 of
+    the fp64 oracle on the tensor-core path - supports resident on chip (V=67, with and without the adaptive-support
+    gradient = both fused backward kernels) and the TMA-tiled big-graph path (V=150)."""
+    for kw in (dict(V=67, N=3, adp_grad=True, seed=31), dict(V=67, N=2, adp_grad=False, seed=32),
+               dict(V=150, N=2, adp_grad=True, seed=33)):
+        errs = _layer_op_case(torch.bfloat16, BF16_TOL, Lin=Lin, dil=dil, taps=2, n_sup=3, with_bn=True, mask=True,
+                              tensor_cores=True, **kw)
+        print(f'bf16 layer op, dilation {dil}:', kw, {k: f'{v:.1e}' for k, v in errs.items()})
+
+
+@pytest.mark.parametrize('V,n_sup', [(67, 2), (67, 3), (150, 2)])
+def test_bf16_layer_op_kernel_size_1(V, n_sup):
+    """kernel_size = 1 is the reference's literal default (graph_wavenet.py:101): the gated conv is a plain 1x1 pair (one
+    chunk, Lout = Lin), nothing is cropped from the residual.  Tensor-core path, 2e-2 on everything."""
+    for with_bn, mask in ((True, False), (False, True)):
+        errs = _layer_op_case(torch.bfloat16, BF16_TOL, V=V, N=3, Lin=3, dil=1, taps=1, n_sup=n_sup, with_bn=with_bn,
+                              mask=mask, seed=41, tensor_cores=True)
+        print(f'bf16 layer op, kernel size 1, V={V}:', {k: f'{v:.1e}' for k, v in errs.items()})
+
+
+def test_literal_reference_call_in_bf16():
+    """The literal `[67, h, 320]` call of Modified_UNET.forward (unet.py:224-226; kernel_size 1, supports [I] + adaptive,
+    batch 1) under bf16: output and loss within 2e-2 of what the REFERENCE's own classes produced in fp32
+    (tests/golden/literal.npz); gradients against the exact oracle, fixed bars as in `_oracle_case`."""
+    from multimodal_outage_b200 import ops
+    c = GOLDEN_CASES['literal']
+    cfg, g = c['cfg'], _golden('literal')
+    sup = case_supports(c['supports'])
+    m = build_model(cfg, sup, horizon=c['horizon'])
+    sd = load_synth(m, cfg, c['seed'])
+    x_np, _ = case_inputs('literal')
+    x = torch.tensor(x_np, device='cuda', requires_grad=True)
+    assert x.dim() == 3
+    m.train()
+    m.compute_dtype = torch.bfloat16
+    ops.HEAD_CAPTURE = {}
+    try:
+        out = m(x)
+    finally:
+        cap, ops.HEAD_CAPTURE = ops.HEAD_CAPTURE, None
+    assert tuple(out.shape) == g['out_train'].shape and out.dtype == torch.float32
+    assert rel(out, g['out_train']) < BF16_TOL, rel(out, g['out_train'])
+    loss = torch.nn.functional.mse_loss(out, torch.tensor(g['target'], device='cuda'))
+    assert abs(loss.item() - float(g['loss'])) < BF16_TOL * abs(float(g['loss']))
+    loss.backward()
+    h = c['horizon']
+    m1, m2 = captured_head_masks(cap, 1, 67, h)
+    _, _, grads_p, _ = oracle_run(cfg, sd, x_np, sup, g['target'], literal=True, horizon=h, head_masks=(m1, m2))
+    worst = {}
+    for k, p in [('__x__', x)] + list(m.named_parameters()):
+        gr = grads_p.get(k)
+        if gr is None or p.grad is None or (k.endswith('bias') and 'gconv' in k):
+            continue
+        worst[k] = rel(p.grad, gr.reshape(p.grad.shape))
+    bad = {k: v for k, v in worst.items() if not v < BF16_TOL}
+    print('literal bf16: worst gradient (head decisions pinned)', max(worst.values()), 'x.grad vs reference fp32',
+          rel(x.grad, g['x_grad']))
+    assert not bad, bad
+    assert rel(x.grad, g['x_grad']) < 0.12
+    m.eval()
+    with torch.no_grad():
+        assert rel(m(x.detach()), g['out_eval']) < BF16_TOL
+
+
+def test_hop_and_support_gradient_at_3100_nodes():
+    """The 3,100-node configurations (BASELINE configs 3 and 5) run `gwn_hop_big` / `gwn_dadj_big` at V = 3100: one hop
+    through each operand image (A and A^T) and the support gradient against fp64 einsums, at the real graph size
+    (ragged: 3100 = 24 x 128 + 28) and a slab count that is not a multiple of the 8-slab box."""
+    from multimodal_outage_b200 import ops, _lib
+    lib = _lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    torch.manual_seed(2)
+    V, slabs = 3100, 11
+    A = torch.softmax(torch.randn(V, V, device='cuda') * 3, dim=1)
+    img = ops.support_images([A])
+    x = torch.randn(slabs, V, 32, device='cuda').to(torch.bfloat16)
+    g = torch.randn(slabs, V, 32, device='cuda').to(torch.bfloat16)
+    y = torch.empty_like(x)
+    Ab = A.to(torch.bfloat16).double()
+    for which in range(2):
+        ref = torch.einsum('vw,svc->swc' if which == 0 else 'wv,svc->swc', Ab, x.double())
+        _lib.check(lib.gwn_hop_big(img.data_ptr(), 1, 0, which, x.data_ptr(), y.data_ptr(), None, slabs, V, st), 'hop')
+        assert rel(y, ref) < 4e-3, (which, rel(y, ref))                 # bf16 output rounding only
+        _lib.check(lib.gwn_hop_big(img.data_ptr(), 1, 0, which, x.data_ptr(), y.data_ptr(), g.data_ptr(), slabs, V, st), 'hop')
+        assert rel(y, ref + g.double()) < 4e-3
+    dA = torch.zeros(V, V, device='cuda')
+    _lib.check(lib.gwn_dadj_big(x.data_ptr(), g.data_ptr(), dA.data_ptr(), slabs, V, st), 'dadj')
+    ref = torch.einsum('svc,swc->vw', x.double(), g.double())
+    assert rel(dA, ref) < 1e-5, rel(dA, ref)
+
+
+def test_fused_dropout_statistics():
+    """The in-kernel Philox stream (7 rounds, one byte per element): realised drop rate, per-channel and per-node
+    uniformity and lag-1 independence over 1.1e7 draws, at the benchmark's p = 0.3 (realised as 77/256)."""
+    from multimodal_outage_b200 import ops, _lib
+    lib = _lib.lib()
+    N, L, V = 512, 10, 67
+    n = N * L * V * 32
+    ones = torch.ones(N, L, V, 32, device='cuda', dtype=torch.bfloat16)
+    out = torch.empty_like(ones)
+    _lib.check(lib.gwn_dropout_apply(ones.data_ptr(), out.data_ptr(), n // 32, 0.3, 12345, 7,
+                                     torch.cuda.current_stream().cuda_stream), 'gwn_dropout_apply')
+    keep = (out != 0)
+    p_real = 77 / 256
+    rate = 1.0 - keep.double().mean().item()
+    sigma = (p_real * (1 - p_real) / n) ** 0.5
+    assert abs(rate - p_real) < 5 * sigma, (rate, p_real, sigma)
+    kept_val = out[keep].float()
+    assert torch.allclose(kept_val, torch.full_like(kept_val, 256 / (256 - 77)), rtol=4e-3)    # unbiased for the realised rate
+    per_c = 1.0 - keep.double().mean(dim=(0, 1, 2))
+    per_v = 1.0 - keep.double().mean(dim=(0, 1, 3))
+    assert (per_c - p_real).abs().max().item() < 5 * (p_real * (1 - p_real) / (n / 32)) ** 0.5
+    assert (per_v - p_real).abs().max().item() < 5 * (p_real * (1 - p_real) / (n / V)) ** 0.5
+    k = keep.double().flatten()
+    for lag in (1, 16, 32, 32 * V):                     # neighbouring channel, next Philox call, next node, next time step
+        a, b = k[:-lag] - (1 - p_real), k[lag:] - (1 - p_real)
+        corr = (a * b).mean().item() / (p_real * (1 - p_real))
+        assert abs(corr) < 5 / (n - lag) ** 0.5, (lag, corr)

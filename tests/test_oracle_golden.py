@@ -158,3 +158,41 @@ def test_closed_form_backwards_fp64():
     dx, da = node_mix_backward(x.detach(), a.detach(), gy)
     assert rel_err(dx, x.grad) < 1e-12 and rel_err(da, a.grad) < 1e-12
     assert torch.allclose(node_mix(x, a), torch.einsum('ncvl,vw->ncwl', x, a))
+
+
+def test_oracle_pinned_head_decisions_and_selective_storage():
+    """The two checker options the bf16 GPU tests rely on: (1) replacing the head's ReLUs by masks taken from the same
+    evaluation changes nothing (output and every gradient identical); (2) `STORAGE_EXCLUDE` removes exactly the named
+    rounding points (excluding all of them gives back the exact evaluation)."""
+    import oracle.gwnet_oracle as go
+    cfg = GWNetConfig(num_nodes=67, in_dim=2, out_dim=12, kernel_size=2, blocks=1, layers=2, skip_channels=64,
+                      end_channels=64, dropout=0.0)
+    sup = [torch.tensor(s).double() for s in case_supports('dir')]
+    sd0 = synthetic_state_dict(cfg, 3)
+    rng = np.random.default_rng(4)
+    x_np = rng.standard_normal((2, 2, 67, 5))
+
+    def run(**kw):
+        sd = {k: (v.double().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v) for k, v in sd0.items()}
+        tr = go.ForwardTrace()
+        out = go.gwnet_forward(sd, torch.tensor(x_np), sup, cfg, training=True, trace=tr, **kw)
+        out.square().mean().backward()
+        return out.detach(), {k: v.grad for k, v in sd.items() if v.is_floating_point() and v.requires_grad and v.grad is not None}, tr, sd
+
+    out, g, tr, sd = run()
+    m1 = (tr.skip.detach() > 0).double()
+    e1 = go.pointwise(torch.relu(tr.skip.detach()), sd['end_conv_1.weight'].detach(), sd['end_conv_1.bias'].detach())
+    out_p, g_p, _, _ = run(head_masks=(m1, (e1 > 0).double()))
+    assert torch.equal(out, out_p)
+    for k in g:
+        assert torch.allclose(g[k], g_p[k], rtol=1e-12, atol=1e-15), k
+    out_s, g_s, _, _ = run(storage=torch.bfloat16)
+    assert (out_s - out).norm() / out.norm() > 1e-4                   # rounding is visible ...
+    go.STORAGE_EXCLUDE = {'u', 'z', 'hops', 'gate_saved'}
+    try:
+        out_x, g_x, _, _ = run(storage=torch.bfloat16)
+    finally:
+        go.STORAGE_EXCLUDE = set()
+    assert torch.equal(out_x, out)                                    # ... and gone with every point excluded
+    for k in g:
+        assert torch.allclose(g[k], g_x[k], rtol=1e-12, atol=1e-15), k
