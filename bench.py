@@ -35,7 +35,7 @@ CONFIGS = {
     # BASELINE.json configs[1]: the configuration the metric is quoted on at N=1 (default)
     'c2': dict(name='config2: gwnet V=67 fwd/bwd+adaptive supports, k=2, 4x2 layers, in_dim=2, T=12, out=12',
                V=67, in_dim=2, out_dim=12, T=12, kernel_size=2, blocks=4, layers=2, batch_per_gpu=512,
-               dropout=0.3, cpu_sample_batch=64),
+               dropout=0.3, cpu_sample_batch=512),
     # configs[2]: 3,100-node graph, K=2 diffusion, 8 layers, batch 64 per GPU (weak scaling)
     'c3': dict(name='config3: gwnet V=3100 synthetic kNN county graph, fwd/bwd+adaptive supports, k=2, 4x2 layers, '
                     'in_dim=2, T=12, out=12', V=3100, in_dim=2, out_dim=12, T=12, kernel_size=2, blocks=4, layers=2,
@@ -43,14 +43,14 @@ CONFIGS = {
     # configs[3]: 67 nodes, in_dim = 256 UNet features + 64 date2vec, batch 256
     'c4': dict(name='config4: gwnet V=67, in_dim=320 (UNet features + date2vec), k=2, 4x2 layers, T=12, out=12',
                V=67, in_dim=320, out_dim=12, T=12, kernel_size=2, blocks=4, layers=2, batch_per_gpu=256,
-               dropout=0.3, cpu_sample_batch=32),
+               dropout=0.3, cpu_sample_batch=256),
     # configs[4]: long horizon, 3,100 nodes, T=48, 4x4 layers (dilations 1,2,4,8), batch 32 per GPU
     'c5': dict(name='config5: gwnet V=3100, T=48, 4x4 layers (dilation <= 8, rf 61), k=2, in_dim=2, out=12',
                V=3100, in_dim=2, out_dim=12, T=48, kernel_size=2, blocks=4, layers=4, batch_per_gpu=32,
                dropout=0.3, cpu_sample_batch=1),
 }
 WORKLOAD = dict(CONFIGS['c2'])
-CPU_SAMPLE_BATCH = 64
+CPU_SAMPLE_BATCH = 512
 
 
 def select_config(key):
@@ -144,19 +144,30 @@ def cpu_reference_steps(steps, warmup, batch):
 
 
 def run_reference(args):
+    """The reference's CPU implementation of the path on all host cores (kind "port": the golden-pinned oracle in its
+    ATen-call form - the reference is Python-only and cannot travel to the GPU box).  Each step is the FULL step of the
+    configuration when the requested run fits in a few minutes (config 2: 512 samples, ~2 s/step), otherwise a bounded
+    sample of the batch."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    sps, sec = cpu_reference_steps(args.steps, args.warmup, CPU_SAMPLE_BATCH)
+    batch = CPU_SAMPLE_BATCH
+    _, sec1 = cpu_reference_steps(1, 1, batch)
+    while batch > 1 and sec1 * (args.steps + args.warmup) > 240.0:      # keep the whole run within a few minutes
+        batch = max(1, batch // 2)
+        _, sec1 = cpu_reference_steps(1, 0, batch)
+    sps, sec = cpu_reference_steps(args.steps, args.warmup, batch)
     cores = torch.get_num_threads()
+    full = batch == WORKLOAD['batch_per_gpu']
     line = {
         'impl': 'reference', 'metric': 'gwnet train samples/sec', 'value': sps, 'unit': 'samples/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD['name'], 'batch_per_gpu': WORKLOAD['batch_per_gpu'],
+        'config': {'workload': WORKLOAD['name'], 'batch_per_gpu': WORKLOAD['batch_per_gpu'], 'global_batch': WORKLOAD['batch_per_gpu'],
+                   'dropout': WORKLOAD['dropout'], 'optimizer': 'Adam(lr=1e-3)', 'parallelism': 'cpu', 'cuda_graph': False,
                    'note': 'reference CPU path = oracle port in ATen-call form (reference is Python-only)'},
         'cpu_baseline': {'value': sps, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
-                         'sample': f'batch {CPU_SAMPLE_BATCH} of the {WORKLOAD["batch_per_gpu"]}-sample step, '
+                         'sample': ('the full ' if full else f'batch {batch} of the ') + f'{WORKLOAD["batch_per_gpu"]}-sample step, '
                                    'fwd+MSE+bwd+Adam, fp32, dropout 0.3'},
         'e2e': {'value': sps, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
@@ -325,22 +336,31 @@ def kernel_rooflines(peaks, n):
                         '1 KB of B', 'peak_source': src}
     del dus, aas, bbs, dfgs
 
-    # ---- gated temporal conv (layer 0, inference form: read r once, write z once)
+    # ---- gated temporal conv at layer 0, in the form the training step runs (reads r once, writes z and the saved
+    #      tanh / sigmoid halves a, b) and in the inference form of SURVEY 8d (read r once, write z once)
     w_fg = torch.randn(2 * 32, 64, device=dev) / 8
     b_fg = torch.zeros(64, device=dev)
 
-    def gate(i):
+    def gate(i, training):
         def f():
-            ops.layer_fwd(ups[i], None, None, w_fg, b_fg, None, None, [], None, None, mats, 1, 2, 1, 2, False, False,
+            ops.layer_fwd(ups[i], None, None, w_fg, b_fg, None, None, [], None, None, mats, 1, 2, 1, 2, training, False,
                           0.0, 0, 0)
         return f
-    ms_gate = graph_time([gate(i) for i in range(R)])
-    bytes_alg = (N * 32 * V * L[0] + N * 32 * V * L[1]) * 2.0
+    ms_gate = graph_time([gate(i, True) for i in range(R)])
+    ms_gate_eval = graph_time([gate(i, False) for i in range(R)])
+    bytes_in, bytes_out = N * 32 * V * L[0] * 2.0, N * 32 * V * L[1] * 2.0
+    bytes_alg = bytes_in + 3 * bytes_out
     gbs = bytes_alg / (ms_gate * 1e-3) / 1e9
-    gate_roof = {'kernel': 'pos_gemm_tc_kernel<EpiGateTC> (gated dilated conv fwd, config-2 layer 0, eval form: read r once, '
-                           'write z once; weight image built in the prologue)', 'bound': 'hbm', 'achieved': gbs, 'peak': peak_bw, 'unit': 'GB/s',
-                 'frac': gbs / peak_bw, 'traffic': None, 'algorithmic_bytes_per_launch': bytes_alg,
-                 'ms_per_launch': ms_gate, 'peak_source': src}
+    gbs_eval = (bytes_in + bytes_out) / (ms_gate_eval * 1e-3) / 1e9
+    tr_g = traffic.get('pos_gemm_tc_kernel_gate_fwd_training', {})
+    gate_roof = {'kernel': 'pos_gemm_tc_kernel<EpiGateTC> (gated dilated conv fwd, config-2 layer 0, TRAINING form - the one the '
+                           'step runs: read r once, write z, a = tanh(f), b = sigmoid(g); weight image built in the prologue)',
+                 'bound': 'hbm', 'achieved': gbs, 'peak': peak_bw, 'unit': 'GB/s', 'frac': gbs / peak_bw,
+                 'traffic': tr_g.get('bytes'), 'traffic_source': tr_g.get('source'),
+                 'algorithmic_bytes_per_launch': bytes_alg, 'ms_per_launch': ms_gate,
+                 'eval_form': {'achieved': gbs_eval, 'frac': gbs_eval / peak_bw, 'ms_per_launch': ms_gate_eval,
+                               'algorithmic_bytes_per_launch': bytes_in + bytes_out},
+                 'peak_source': src}
 
     # ---- diffusion hop GEMM at the 3,100-node shape (config 3 layer 0: 64 x 12 slabs)
     del zs, ups, us
@@ -367,10 +387,220 @@ def kernel_rooflines(peaks, n):
     return roof_bwd, roof, gate_roof, big_roof
 
 
+class Trainer:
+    """One data-parallel replica of the training step of the selected WORKLOAD (forward + MSELoss + backward + gradient
+    exchange at N > 1 + Adam), resident-input and end-to-end (pinned host -> device) step functions."""
+
+    def __init__(self, dev, world, rank, dtype=torch.bfloat16, use_graph=True, dropout_mode='fused', comm_capture=True,
+                 n_batches=4):
+        import torch.distributed as dist
+        from multimodal_outage_b200 import gwnet, _lib
+        from multimodal_outage_b200.ddp import BucketedGradAllReduce
+        self.dist, self.world, self.dev = dist, world, dev
+        w = WORKLOAD
+        n = self.n = w['batch_per_gpu']
+        torch.manual_seed(42)
+        model = self.model = gwnet(dev, num_nodes=w['V'], dropout=w['dropout'], supports=[torch.tensor(s) for s in fl_supports()],
+                                   in_dim=w['in_dim'], out_dim=w['out_dim'], kernel_size=w['kernel_size'], blocks=w['blocks'],
+                                   layers=w['layers'])
+        assert model.layer_lengths(w['T']) == layer_lengths()
+        model.compute_dtype = dtype
+        model.dropout_mode = dropout_mode
+        model.train()
+        opt = self.opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True, fused=True)
+        loss_fn = torch.nn.MSELoss()
+        sync = self.sync = BucketedGradAllReduce(model) if world > 1 else None
+
+        # distinct batches rotated through the timed loop (inputs differ every step; working set >> L2)
+        R = self.R = n_batches
+        g = torch.Generator().manual_seed(42 + rank)
+        self.xs_host = [torch.randn(n, w['in_dim'], w['V'], w['T'], generator=g).pin_memory() for _ in range(R)]
+        self.ys_host = [torch.randn(n, w['out_dim'], w['V'], 1, generator=g).pin_memory() for _ in range(R)]
+        self.xs = [t.to(dev) for t in self.xs_host]
+        self.ys = [t.to(dev) for t in self.ys_host]
+        self.x_static, self.y_static = torch.empty_like(self.xs[0]), torch.empty_like(self.ys[0])
+        self.loss_static = torch.zeros((), device=dev)
+        self.h2d_bytes = self.xs_host[0].numel() * 4 + self.ys_host[0].numel() * 4
+
+        def fwd_bwd(x, y):
+            opt.zero_grad(set_to_none=True)
+            loss = loss_fn(model(x), y)
+            loss.backward()
+            return loss
+
+        def step_eager(x, y):
+            # backward launches bucket 0's all-reduce (head + skip gradients) from its gradient hooks as soon as the head's
+            # backward is done - it runs on NCCL's stream under the backward of the layers - and bucket 1's at the end
+            loss = fwd_bwd(x, y)
+            if sync is not None:
+                sync.finish()
+            opt.step()
+            return loss
+        self.step_eager = step_eager
+
+        for _ in range(3):                                        # eager warm-up (allocator, rng state, Adam state)
+            step_eager(self.xs[0], self.ys[0])
+        torch.cuda.synchronize()
+        c0 = _lib.lib().gwn_launch_count()
+        step_eager(self.xs[0], self.ys[0])
+        torch.cuda.synchronize()
+        self.launches_per_step = _lib.lib().gwn_launch_count() - c0
+
+        # CUDA graph.  N = 1: the whole step.  N > 1: the whole step INCLUDING the two NCCL all-reduces (forked onto
+        # NCCL's stream by the gradient hooks, joined before Adam) - one graph launch per step, bucket 0 overlapped with
+        # the layers' backward.  If the collective cannot be captured on this stack, fall back to: graph = forward +
+        # backward + packing, then the exchange (one collective) and Adam issued eagerly after each replay.
+        self.graph = None
+        self.comm = 'none (1 GPU)' if world == 1 else 'eager: 2 overlapped all-reduces launched from gradient hooks'
+        self._post_replay = None
+        if use_graph:
+            modes = ['captured'] if world == 1 else ((['captured'] if comm_capture else []) + ['split'])
+            for mode in modes:
+                try:
+                    self._capture(mode, fwd_bwd, step_eager)
+                    if world > 1:
+                        self.comm = ('captured in the step graph: bucket 0 all-reduce overlaps the layer backward, bucket 1 + '
+                                     'fused Adam at the end' if mode == 'captured' else
+                                     'graph = fwd + bwd + pack; ONE all-reduce + fused Adam eagerly after the replay')
+                    break
+                except Exception as e:                            # noqa: BLE001
+                    if mode == modes[-1]:
+                        raise
+                    print(f'[bench] capturing the collective failed ({type(e).__name__}: {e}); using the split scheme',
+                          file=sys.stderr, flush=True)
+                    torch.cuda.synchronize()
+                    self.graph = None
+
+        # end-to-end input pipeline: the pinned-host -> device copy of step i+1's batch runs on a copy stream while step i
+        # computes (two staging buffers); every step still pays its own H2D copy inside the timed region and reads its
+        # loss back to the host
+        self.copy_stream = torch.cuda.Stream()
+        self.x_stage = [torch.empty_like(self.x_static) for _ in range(2)]
+        self.y_stage = [torch.empty_like(self.y_static) for _ in range(2)]
+        self.staged_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        self.staged_for = [None, None]
+
+    def _capture(self, mode, fwd_bwd, step_eager):
+        sync, opt = self.sync, self.opt
+        if mode == 'split':
+            sync.remove()                                         # hooks off: gradients are packed explicitly
+            sync.overlap = False
+
+            def captured(x, y):
+                loss = fwd_bwd(x, y)
+                sync.pack()
+                return loss
+
+            def post():
+                sync.reduce()
+                opt.step()
+            self._post_replay = post
+        else:
+            captured = step_eager
+        graph = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self.x_static.copy_(self.xs[0]); self.y_static.copy_(self.ys[0])
+            captured(self.x_static, self.y_static)
+            if self._post_replay:
+                self._post_replay()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(graph):
+            self.loss_static.copy_(captured(self.x_static, self.y_static).detach())
+        self.graph = graph
+
+    def _replay(self):
+        self.graph.replay()
+        if self._post_replay:
+            self._post_replay()
+
+    def step_resident(self, i):
+        R = self.R
+        if self.graph is not None:
+            self.x_static.copy_(self.xs[i % R]); self.y_static.copy_(self.ys[i % R])
+            self._replay()
+            return self.loss_static
+        return self.step_eager(self.xs[i % R], self.ys[i % R])
+
+    def _prefetch(self, i):
+        b = i % 2
+        # (the previous reader of this staging buffer finished two steps ago: every step ends with a host read of its loss)
+        with torch.cuda.stream(self.copy_stream):
+            self.x_stage[b].copy_(self.xs_host[i % self.R], non_blocking=True)
+            self.y_stage[b].copy_(self.ys_host[i % self.R], non_blocking=True)
+            self.staged_ev[b].record(self.copy_stream)
+        self.staged_for[b] = i
+
+    def step_e2e(self, i):
+        # host (pinned) -> device copy of this step's inputs, the step, device -> host read of the loss
+        b = i % 2
+        if self.staged_for[b] != i:
+            self._prefetch(i)
+        torch.cuda.current_stream().wait_event(self.staged_ev[b])
+        if self.graph is not None:
+            self.x_static.copy_(self.x_stage[b]); self.y_static.copy_(self.y_stage[b])
+            self._replay()
+            self._prefetch(i + 1)
+            return float(self.loss_static.item())
+        loss = self.step_eager(self.x_stage[b], self.y_stage[b])
+        self._prefetch(i + 1)
+        return float(loss.item())
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, step_fn, K, W):
+        """W untimed steps, then exactly K steps between barrier + synchronize, CUDA events; max over ranks (ms)."""
+        for i in range(W):
+            step_fn(i)
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            step_fn(W + i)
+        e1.record()
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.dev)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def close(self):
+        self.graph = None
+        self._post_replay = None
+        if self.sync is not None:
+            self.sync.remove()
+        torch.cuda.synchronize()
+
+
+def side_run(key, dev, world, rank, steps, warmup, **kw):
+    """A short run of another configuration / mode in the same process (samples/s over all ranks)."""
+    prev = dict(WORKLOAD)
+    select_config(key)
+    try:
+        t = Trainer(dev, world, rank, n_batches=2, **kw)
+        ms = t.timed(t.step_resident, steps, warmup) / steps
+        rec = {'workload': WORKLOAD['name'], 'batch_per_gpu': t.n, 'samples_per_s': world * t.n / (ms * 1e-3), 'ms_per_step': ms,
+               'steps': steps, 'warmup': warmup, 'cuda_graph': t.graph is not None, 'dtype': 'f32' if kw.get('dtype') == torch.float32 else 'bf16',
+               'dropout_mode': kw.get('dropout_mode', 'fused')}
+        t.close()
+        del t
+        torch.cuda.empty_cache()
+        return rec
+    finally:
+        WORKLOAD.clear(); WORKLOAD.update(prev)
+        global CPU_SAMPLE_BATCH
+        CPU_SAMPLE_BATCH = WORKLOAD['cpu_sample_batch']
+
+
 def run_ours(args):
     import torch.distributed as dist
-    from multimodal_outage_b200 import gwnet, _lib
-    from multimodal_outage_b200.ddp import BucketedGradAllReduce
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -381,150 +611,30 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     dev = torch.device('cuda', local)
     w = WORKLOAD
-    n = w['batch_per_gpu']
-    torch.manual_seed(42)
-    model = gwnet(dev, num_nodes=w['V'], dropout=w['dropout'], supports=[torch.tensor(s) for s in fl_supports()],
-                  in_dim=w['in_dim'], out_dim=w['out_dim'], kernel_size=w['kernel_size'], blocks=w['blocks'],
-                  layers=w['layers'])
-    assert model.layer_lengths(w['T']) == layer_lengths()
-    model.compute_dtype = torch.bfloat16
-    model.train()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True, fused=True)
-    loss_fn = torch.nn.MSELoss()
-    sync = BucketedGradAllReduce(model) if world > 1 else None
-
-    # distinct batches rotated through the timed loop (inputs differ every step; working set >> L2)
-    R = 4
-    g = torch.Generator().manual_seed(42 + rank)
-    xs_host = [torch.randn(n, w['in_dim'], w['V'], w['T'], generator=g).pin_memory() for _ in range(R)]
-    ys_host = [torch.randn(n, w['out_dim'], w['V'], 1, generator=g).pin_memory() for _ in range(R)]
-    xs = [t.to(dev) for t in xs_host]
-    ys = [t.to(dev) for t in ys_host]
-    x_static, y_static = torch.empty_like(xs[0]), torch.empty_like(ys[0])
-    loss_static = torch.zeros((), device=dev)
-
-    def fwd_bwd(x, y):
-        opt.zero_grad(set_to_none=True)
-        loss = loss_fn(model(x), y)
-        loss.backward()
-        return loss
-
-    def step_eager(x, y):
-        loss = fwd_bwd(x, y)
-        if sync is not None:
-            sync.finish()
-        opt.step()
-        return loss
-
-    # CUDA graph: N=1 captures the whole step (fwd + loss + bwd + Adam).  N>1 captures fwd + loss + bwd + the
-    # device-side packing of gradients into the flat buckets; the ONE NCCL exchange and the fused Adam step are
-    # issued eagerly after each replay (a handful of launches), so no collective lives inside a captured graph.
-    use_graph = not args.no_graph
-    graph = None
-    launches_per_step = None
-    for _ in range(3):                                        # eager warm-up (allocator, rng state, Adam state)
-        step_eager(xs[0], ys[0])
-    torch.cuda.synchronize()
-    c0 = _lib.lib().gwn_launch_count()
-    step_eager(xs[0], ys[0])
-    torch.cuda.synchronize()
-    launches_per_step = _lib.lib().gwn_launch_count() - c0
-    if use_graph:
-        if sync is not None:
-            sync.remove()                                     # hooks off: gradients are packed explicitly
-            sync.overlap = False
-
-        def captured(x, y):
-            if sync is None:
-                return step_eager(x, y)
-            loss = fwd_bwd(x, y)
-            sync.pack()
-            return loss
-        graph = torch.cuda.CUDAGraph()
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            x_static.copy_(xs[0]); y_static.copy_(ys[0])
-            captured(x_static, y_static)
-        torch.cuda.current_stream().wait_stream(s)
-        torch.cuda.synchronize()
-        with torch.cuda.graph(graph):
-            loss_static.copy_(captured(x_static, y_static).detach())
-
-    def replay():
-        graph.replay()
-        if sync is not None:
-            sync.reduce()
-            opt.step()
-
-    def step_resident(i):
-        if graph is not None:
-            x_static.copy_(xs[i % R]); y_static.copy_(ys[i % R])
-            replay()
-            return loss_static
-        return step_eager(xs[i % R], ys[i % R])
-
-    # end-to-end input pipeline: the pinned-host -> device copy of step i+1's batch runs on a copy stream while step i
-    # computes (two staging buffers); every step still pays its own H2D copy inside the timed region and reads its
-    # loss back to the host
-    copy_stream = torch.cuda.Stream()
-    x_stage = [torch.empty_like(x_static) for _ in range(2)]
-    y_stage = [torch.empty_like(y_static) for _ in range(2)]
-    staged_ev = [torch.cuda.Event(), torch.cuda.Event()]
-    staged_for = [None, None]
-
-    def prefetch(i):
-        b = i % 2
-        # (the previous reader of this staging buffer finished two steps ago: every step ends with a host read of its loss)
-        with torch.cuda.stream(copy_stream):
-            x_stage[b].copy_(xs_host[i % R], non_blocking=True); y_stage[b].copy_(ys_host[i % R], non_blocking=True)
-            staged_ev[b].record(copy_stream)
-        staged_for[b] = i
-
-    def step_e2e(i):
-        # host (pinned) -> device copy of this step's inputs, the step, device -> host read of the loss
-        b = i % 2
-        if staged_for[b] != i:
-            prefetch(i)
-        torch.cuda.current_stream().wait_event(staged_ev[b])
-        if graph is not None:
-            x_static.copy_(x_stage[b]); y_static.copy_(y_stage[b])
-            replay()
-            prefetch(i + 1)
-            return float(loss_static.item())
-        loss = step_eager(x_stage[b], y_stage[b])
-        prefetch(i + 1)
-        return float(loss.item())
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(step_fn, K, W):
-        for i in range(W):
-            step_fn(i)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(K):
-            step_fn(W + i)
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+    tr = Trainer(dev, world, rank, use_graph=not args.no_graph, comm_capture=not args.no_comm_capture)
+    n = tr.n
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_total = timed(step_resident, args.steps, max(args.warmup, 3))
+    ms_total = tr.timed(tr.step_resident, args.steps, max(args.warmup, 3))
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e = timed(step_e2e, args.steps, 3)
-    final_loss = float(step_resident(0).item())
+    ms_e2e = tr.timed(tr.step_e2e, args.steps, 3)
+    final_loss = float(tr.step_resident(0).item())
+    launches_per_step, graph_on, comm, h2d = tr.launches_per_step, tr.graph is not None, tr.comm, tr.h2d_bytes
+    tr.close()
+    del tr
+    torch.cuda.empty_cache()
+
+    # side records (every rank takes part: they are data-parallel runs too): the 3,100-node configurations BASELINE.json
+    # quotes at 1/2/4/8 GPUs, the reference's exact dropout draws, and the fp32 parity mode
+    extra = {}
+    if not args.no_extra and args.config == 'c2':
+        extra['config3'] = side_run('c3', dev, world, rank, 4, 3, use_graph=False)
+        extra['config5'] = side_run('c5', dev, world, rank, 2, 2, use_graph=False)
+        if world == 1:
+            extra['config2_dropout_mode_torch'] = side_run('c2', dev, world, rank, 20, 5, dropout_mode='torch')
+            extra['config2_fp32'] = side_run('c2', dev, world, rank, 10, 3, dtype=torch.float32)
 
     if rank == 0:
         peaks = {}
@@ -537,19 +647,19 @@ def run_ours(args):
             sps_cpu, sec_cpu = cpu_reference_steps(3, 1, CPU_SAMPLE_BATCH)
             cpu = {'value': sps_cpu, 'unit': 'samples/s', 'cores': torch.get_num_threads(), 'kind': 'port',
                    'sample': f'batch {CPU_SAMPLE_BATCH} of the {n}-sample step (fwd+MSE+bwd+Adam, fp32, dropout 0.3), '
-                             f'{sec_cpu:.2f} s/step, oracle port in ATen-call form'}
+                             f'{sec_cpu:.2f} s/step, 3 steps, oracle port in ATen-call form'}
         ms_step = ms_total / args.steps
         value = world * n / (ms_step * 1e-3)
         e2e_value = world * n / (ms_e2e / args.steps * 1e-3)
-        h2d = xs_host[0].numel() * 4 + ys_host[0].numel() * 4
         work = algorithmic_work(n)
         line = {
             'metric': 'gwnet train samples/sec', 'value': value, 'unit': 'samples/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
             'config': {'workload': w['name'], 'batch_per_gpu': n, 'global_batch': world * n, 'dropout': w['dropout'],
-                       'optimizer': 'Adam(lr=1e-3)', 'parallelism': f'dp{world}', 'cuda_graph': bool(graph),
-                       'l2': f'{R} distinct input batches rotated; per-step working set (activations+workspaces, '
+                       'optimizer': 'Adam(lr=1e-3)', 'parallelism': f'dp{world}', 'cuda_graph': graph_on,
+                       'gradient_exchange': comm,
+                       'l2': '4 distinct input batches rotated; per-step working set (activations+workspaces, '
                              '>1 GB) exceeds the 126 MB L2; kernel microbenchmarks use buffers > L2'},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4},
@@ -559,6 +669,7 @@ def run_ours(args):
             'final_loss': final_loss,
             'algorithmic_gflop_per_step_diffusion_fwd': (work['hop_fwd_flops'] + work['mlp_fwd_flops']) / 1e9,
         }
+        line.update(extra)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -574,6 +685,8 @@ def main():
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))
     ap.add_argument('--no-roofline', action='store_true')
+    ap.add_argument('--no-extra', action='store_true', help='skip the config3 / config5 / dropout-mode / fp32 side records')
+    ap.add_argument('--no-comm-capture', action='store_true', help='N > 1: keep the collective out of the CUDA graph (A/B)')
     args = ap.parse_args()
     select_config(args.config)
     if args.impl == 'reference':

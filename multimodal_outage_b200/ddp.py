@@ -1,6 +1,8 @@
 """Batch data-parallel training for the gwnet block: static flat gradient buckets all-reduced
 (averaged) over torch.distributed (NCCL over NVLink/NVSwitch on B200; gloo in the CPU tests),
 launched from post-accumulate-grad hooks so the first bucket's exchange overlaps the rest of backward.
+The whole sequence - hooks, the two collectives on NCCL's stream, the waits, a fused Adam step - is
+capturable in ONE CUDA graph together with forward and backward (bench.py at N > 1 does that).
 
 The reference has no distributed code at all; this adds the one strategy the path
 needs: identical replicas, batch sharded by rank, ONE exchange per step.  BatchNorm
@@ -8,7 +10,8 @@ statistics stay per replica, exactly as plain nn.BatchNorm2d does in the referen
 
 Bucket plan (static, identical on every rank):
   bucket 0  end_conv_2, end_conv_1, skip_convs.*   - their grads are complete at the very start of
-            backward (the head runs first), ~2/3 of all gradient bytes
+            backward (the head runs first and its packed gradients are scattered by their own autograd
+            node right after it, graph_wavenet._PackHead), ~2/3 of all gradient bytes
   bucket 1  everything else that receives a gradient (layers in reverse, start_conv, nodevec1/2)
 Parameters that never receive a gradient (residual_convs.* when gcn_bool, the last layer's
 bn/gconv - graph_wavenet.py:245,250-252) are left out on every rank.
@@ -50,6 +53,8 @@ class BucketedGradAllReduce:
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.overlap = overlap
+        # NCCL averages inside the reduction; gloo (CPU tests) sums and the result is divided afterwards
+        self._avg_in_collective = dist.is_initialized() and dist.get_backend(process_group) == 'nccl'
         params: Dict[str, torch.nn.Parameter] = dict(model.named_parameters())
         self.plan = plan_buckets(model)
         self.buckets = []
@@ -86,7 +91,8 @@ class BucketedGradAllReduce:
         torch._foreach_copy_(b['views'], grads)
         b['launched'] = True
         if self.world > 1:
-            b['work'] = dist.all_reduce(b['flat'], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            op = dist.ReduceOp.AVG if self._avg_in_collective else dist.ReduceOp.SUM
+            b['work'] = dist.all_reduce(b['flat'], op=op, group=self.group, async_op=True)
 
     def finish(self):
         """Wait for the exchanges, average, and point .grad at the bucket views."""
@@ -97,7 +103,7 @@ class BucketedGradAllReduce:
             if b['work'] is not None:
                 b['work'].wait()
                 b['work'] = None
-            if self.world > 1:
+            if self.world > 1 and not self._avg_in_collective:
                 b['flat'].div_(self.world)
             for p, v in zip(b['params'], b['views']):
                 p.grad = v

@@ -58,71 +58,112 @@ class gcn(nn.Module):
         self.order = order
 
 
-class _PackParams(torch.autograd.Function):
-    """Re-lays the reference-shaped parameters into the kernels' packed layouts (and scatters the gradients back):
-    ONE gather launch forward and ONE scatter launch backward (`gwn_pack_params` / `gwn_unpack_grads`, csrc/pack.cu).
-
-    inputs : Wf[nl], bf[nl], Wg[nl], bg[nl], Wm[nl], bm[nl], Ws[nl], bs[nl], W1, b1, W2, b2  (flat list)
-    outputs: w_fg[nl] ([k*32, 64]), b_fg[nl] ([64]), w_mlp[nl] ([mlp_in, 32]), w_skip [32*nl, S],
-             b_skip [S], w_end1 [S, E], w_end2 [E, Opad], b_end2 [Opad]   (views of one flat buffer)
-    """
-
-    @staticmethod
-    def forward(ctx, nl, *p):
-        Wf, bf, Wg, bg, Wm, bm, Ws, bs = (p[i * nl:(i + 1) * nl] for i in range(8))
-        W1, b1, W2, b2 = p[8 * nl:]
-        k, mlp_in, S = Wf[0].shape[3], Wm[0].shape[1], Ws[0].shape[0]
-        O, E = W2.shape[0], W2.shape[1]
-        Opad = CH * ((O + CH - 1) // CH)
+def _pack_all(nl, p):
+    """One gather launch: reference-shaped parameters -> the kernels' packed layouts (`gwn_pack_params`, csrc/pack.cu).
+    p = Wf[nl], bf[nl], Wg[nl], bg[nl], Wm[nl], bm[nl], Ws[nl], bs[nl], W1, b1, W2, b2 (flat list).  Returns the views
+    (w_fg [nl, k*32, 64], b_fg [nl, 64], w_mlp [nl, mlp_in, 32], w_skip [32*nl, S], b_skip [S], w_end1 [S, E],
+    w_end2 [E, Opad], b_end2 [Opad]) of one flat buffer, and the dims."""
+    Wf, bf, Wg, bg, Wm, bm, Ws, bs = (p[i * nl:(i + 1) * nl] for i in range(8))
+    W1, b1, W2, b2 = p[8 * nl:]
+    k, mlp_in, S = Wf[0].shape[3], Wm[0].shape[1], Ws[0].shape[0]
+    O, E = W2.shape[0], W2.shape[1]
+    Opad = CH * ((O + CH - 1) // CH)
+    with torch.no_grad():
         srcs = [t.detach().contiguous() for t in (*Wf, *bf, *Wg, *bg, *Wm, *Ws, *bs, W1, W2, b2)]
         flat = ops.pack_params(srcs, nl, k, mlp_in, S, E, O)
-        o = ops.pack_offsets(nl, k, mlp_in, S, E, O)
-        w_fg = flat[o[0]:o[1]].view(nl, k * CH, 2 * CH)
-        b_fg = flat[o[1]:o[2]].view(nl, 2 * CH)
-        w_mlp = flat[o[2]:o[3]].view(nl, mlp_in, CH)
-        w_skip = flat[o[3]:o[4]].view(nl * CH, S)
-        b_skip = flat[o[4]:o[5]]
-        w_end1 = flat[o[5]:o[6]].view(S, E)
-        w_end2 = flat[o[6]:o[7]].view(E, Opad)
-        b_end2 = flat[o[7]:o[8]]
-        ctx.dims = (nl, k, S, E, O, mlp_in)
+    o = ops.pack_offsets(nl, k, mlp_in, S, E, O)
+    views = (flat[o[0]:o[1]].view(nl, k * CH, 2 * CH), flat[o[1]:o[2]].view(nl, 2 * CH), flat[o[2]:o[3]].view(nl, mlp_in, CH),
+             flat[o[3]:o[4]].view(nl * CH, S), flat[o[4]:o[5]], flat[o[5]:o[6]].view(S, E), flat[o[6]:o[7]].view(E, Opad),
+             flat[o[7]:o[8]])
+    return views, (nl, k, S, E, O, mlp_in)
+
+
+def _unpacked_views(flat, dims):
+    """Parameter-shaped views of the flat buffer `gwn_unpack_grads` writes (parameter order, csrc/pack.cu)."""
+    nl, k, S, E, O, mlp_in = dims
+    nw = CH * CH * k
+    per = 2 * (nw + CH) + CH * mlp_in + CH * S + S
+    dWf, dbf, dWg, dbg, dWm, dWs, dbs = ([None] * nl for _ in range(7))
+    for l in range(nl):
+        b0 = l * per
+        dWf[l] = flat[b0:b0 + nw].view(CH, CH, 1, k)
+        dbf[l] = flat[b0 + nw:b0 + nw + CH]
+        dWg[l] = flat[b0 + nw + CH:b0 + 2 * nw + CH].view(CH, CH, 1, k)
+        dbg[l] = flat[b0 + 2 * nw + CH:b0 + 2 * (nw + CH)]
+        b1 = b0 + 2 * (nw + CH)
+        dWm[l] = flat[b1:b1 + CH * mlp_in].view(CH, mlp_in, 1, 1)
+        b2 = b1 + CH * mlp_in
+        dWs[l] = flat[b2:b2 + CH * S].view(S, CH, 1, 1)
+        dbs[l] = flat[b2 + CH * S:b2 + CH * S + S]
+    t0 = nl * per
+    dW1 = flat[t0:t0 + E * S].view(E, S, 1, 1)
+    dW2 = flat[t0 + E * S:t0 + E * S + O * E].view(O, E, 1, 1)
+    db2 = flat[t0 + E * S + O * E:t0 + E * S + O * E + O]
+    return dWf, dbf, dWg, dbg, dWm, dWs, dbs, dW1, dW2, db2
+
+
+class _PackLayers(torch.autograd.Function):
+    """Autograd edge from the per-layer parameters (filter / gate convs, gcn mlp weight) to their packed views; backward
+    scatters the packed gradients back with ONE launch (`gwn_unpack_grads`).  The packing itself happened in `_pack_all`.
+
+    inputs : dims, w_fg [nl,..], b_fg [nl,..], w_mlp [nl,..] (packed views), Wf[nl], bf[nl], Wg[nl], bg[nl], Wm[nl]
+    outputs: w_fg[nl], b_fg[nl], w_mlp[nl]"""
+
+    @staticmethod
+    def forward(ctx, dims, w_fg, b_fg, w_mlp, *p):
+        ctx.dims = dims
         ctx.set_materialize_grads(False)
-        return (*w_fg.unbind(0), *b_fg.unbind(0), *w_mlp.unbind(0), w_skip, b_skip, w_end1, w_end2, b_end2)
+        return (*w_fg.unbind(0), *b_fg.unbind(0), *w_mlp.unbind(0))
 
     @staticmethod
     def backward(ctx, *g):
         nl, k, S, E, O, mlp_in = ctx.dims
         cont = lambda t: None if t is None else t.contiguous()  # noqa: E731
         g_wfg, g_bfg, g_wmlp = [cont(t) for t in g[:nl]], [cont(t) for t in g[nl:2 * nl]], [cont(t) for t in g[2 * nl:3 * nl]]
-        g_wskip, g_bskip, g_wend1, g_wend2, g_bend2 = (cont(t) for t in g[3 * nl:])
-        if all(t is None for t in (*g_wfg, *g_bfg, *g_wmlp, g_wskip, g_bskip, g_wend1, g_wend2, g_bend2)):
-            return (None,) * (1 + 8 * nl + 4)
-        flat = ops.unpack_grads(g_wfg, g_bfg, g_wmlp, g_wskip, g_bskip, g_wend1, g_wend2, g_bend2, k, mlp_in, S, E, O)
-        nw = CH * CH * k
-        per = 2 * (nw + CH) + CH * mlp_in + CH * S + S
-        dWf, dbf, dWg, dbg, dWm, dWs, dbs = ([None] * nl for _ in range(7))
-        for l in range(nl):
-            b0 = l * per
-            if g_wfg[l] is not None:                       # parameters the block never used keep grad None
-                dWf[l] = flat[b0:b0 + nw].view(CH, CH, 1, k)
-                dWg[l] = flat[b0 + nw + CH:b0 + 2 * nw + CH].view(CH, CH, 1, k)
-            if g_bfg[l] is not None:
-                dbf[l] = flat[b0 + nw:b0 + nw + CH]
-                dbg[l] = flat[b0 + 2 * nw + CH:b0 + 2 * (nw + CH)]
-            b1 = b0 + 2 * (nw + CH)
-            if g_wmlp[l] is not None:
-                dWm[l] = flat[b1:b1 + CH * mlp_in].view(CH, mlp_in, 1, 1)
-            b2 = b1 + CH * mlp_in
-            if g_wskip is not None:
-                dWs[l] = flat[b2:b2 + CH * S].view(S, CH, 1, 1)
-            if g_bskip is not None:
-                dbs[l] = flat[b2 + CH * S:b2 + CH * S + S]
-        t0 = nl * per
-        dW1 = flat[t0:t0 + E * S].view(E, S, 1, 1) if g_wend1 is not None else None
-        dW2 = flat[t0 + E * S:t0 + E * S + O * E].view(O, E, 1, 1) if g_wend2 is not None else None
-        db2 = flat[t0 + E * S + O * E:t0 + E * S + O * E + O] if g_bend2 is not None else None
-        # bm, b1 are passed straight to the kernels (no packing) -> no grads through this Function
-        return (None, *dWf, *dbf, *dWg, *dbg, *dWm, *([None] * nl), *dWs, *dbs, dW1, None, dW2, db2)
+        if all(t is None for t in (*g_wfg, *g_bfg, *g_wmlp)):
+            return (None,) * (4 + 5 * nl)
+        flat = ops.unpack_grads(g_wfg, g_bfg, g_wmlp, None, None, None, None, None, k, mlp_in, S, E, O)
+        dWf, dbf, dWg, dbg, dWm, _dWs, _dbs, _dW1, _dW2, _db2 = _unpacked_views(flat, ctx.dims)
+        for l in range(nl):                                    # parameters the block never used keep grad None
+            if g_wfg[l] is None:
+                dWf[l] = dWg[l] = None
+            if g_bfg[l] is None:
+                dbf[l] = dbg[l] = None
+            if g_wmlp[l] is None:
+                dWm[l] = None
+        return (None, None, None, None, *dWf, *dbf, *dWg, *dbg, *dWm)
+
+
+class _PackHead(torch.autograd.Function):
+    """Same for the head's parameters (skip convs, end_conv_1 weight, end_conv_2).  Applied right before the head in
+    forward, so that in backward it runs right AFTER the head (autograd runs the youngest ready node first): the head's
+    parameter gradients - two thirds of all gradient bytes - are final at the very start of backward and their
+    data-parallel exchange (ddp.BucketedGradAllReduce, bucket 0) overlaps the backward of every layer.
+
+    inputs : dims, w_skip, b_skip, w_end1, w_end2, b_end2 (packed views), Ws[nl], bs[nl], W1, W2, b2
+    outputs: w_skip, b_skip, w_end1, w_end2, b_end2"""
+
+    @staticmethod
+    def forward(ctx, dims, w_skip, b_skip, w_end1, w_end2, b_end2, *p):
+        ctx.dims = dims
+        ctx.set_materialize_grads(False)
+        return tuple(t.view_as(t) for t in (w_skip, b_skip, w_end1, w_end2, b_end2))
+
+    @staticmethod
+    def backward(ctx, *g):
+        nl, k, S, E, O, mlp_in = ctx.dims
+        g_wskip, g_bskip, g_wend1, g_wend2, g_bend2 = (None if t is None else t.contiguous() for t in g)
+        if all(t is None for t in (g_wskip, g_bskip, g_wend1, g_wend2, g_bend2)):
+            return (None,) * (6 + 2 * nl + 3)
+        none = [None] * nl
+        flat = ops.unpack_grads(none, none, none, g_wskip, g_bskip, g_wend1, g_wend2, g_bend2, k, mlp_in, S, E, O)
+        _a, _b, _c, _d, _e, dWs, dbs, dW1, dW2, db2 = _unpacked_views(flat, ctx.dims)
+        if g_wskip is None:
+            dWs = none
+        if g_bskip is None:
+            dbs = none
+        return (None, None, None, None, None, None, *dWs, *dbs, dW1 if g_wend1 is not None else None,
+                dW2 if g_wend2 is not None else None, db2 if g_bend2 is not None else None)
 
 
 class gwnet(nn.Module):
@@ -228,17 +269,22 @@ class gwnet(nn.Module):
         return L
 
     def _packed(self):
+        """Packs every parameter with one launch; returns the layer views (autograd-connected) and a closure that
+        connects the head's views - to be called right before the head (see _PackHead)."""
         nl = self.blocks * self.layers
         mlps = [g.mlp.mlp for g in self.gconv] if self.gcn_bool else list(self.residual_convs)
-        flat = ([c.weight for c in self.filter_convs] + [c.bias for c in self.filter_convs] +
-                [c.weight for c in self.gate_convs] + [c.bias for c in self.gate_convs] +
-                [m.weight for m in mlps] + [m.bias for m in mlps] +
-                [c.weight for c in self.skip_convs] + [c.bias for c in self.skip_convs] +
-                [self.end_conv_1.weight, self.end_conv_1.bias, self.end_conv_2.weight, self.end_conv_2.bias])
-        out = _PackParams.apply(nl, *flat)
-        return dict(w_fg=out[:nl], b_fg=out[nl:2 * nl], w_mlp=out[2 * nl:3 * nl], b_mlp=[m.bias for m in mlps],
-                    w_skip=out[3 * nl], b_skip=out[3 * nl + 1], w_end1=out[3 * nl + 2], w_end2=out[3 * nl + 3],
-                    b_end2=out[3 * nl + 4])
+        Wf, bf = [c.weight for c in self.filter_convs], [c.bias for c in self.filter_convs]
+        Wg, bg = [c.weight for c in self.gate_convs], [c.bias for c in self.gate_convs]
+        Wm, bm = [m.weight for m in mlps], [m.bias for m in mlps]
+        Ws, bs = [c.weight for c in self.skip_convs], [c.bias for c in self.skip_convs]
+        head = [self.end_conv_1.weight, self.end_conv_1.bias, self.end_conv_2.weight, self.end_conv_2.bias]
+        (w_fg, b_fg, w_mlp, w_skip, b_skip, w_end1, w_end2, b_end2), dims = _pack_all(nl, Wf + bf + Wg + bg + Wm + bm + Ws + bs + head)
+        out = _PackLayers.apply(dims, w_fg, b_fg, w_mlp, *Wf, *bf, *Wg, *bg, *Wm)
+
+        def head_views():
+            h = _PackHead.apply(dims, w_skip, b_skip, w_end1, w_end2, b_end2, *Ws, *bs, head[0], head[2], head[3])
+            return dict(w_skip=h[0], b_skip=h[1], w_end1=h[2], w_end2=h[3], b_end2=h[4])
+        return dict(w_fg=out[:nl], b_fg=out[nl:2 * nl], w_mlp=out[2 * nl:3 * nl], b_mlp=bm, head=head_views)
 
     # ------------------------------------------------------------------ forward
     def forward(self, input: torch.Tensor, dropout_masks: Optional[Sequence[Optional[torch.Tensor]]] = None):
@@ -330,5 +376,6 @@ class gwnet(nn.Module):
                 ops.bn_fold(stats, float(N * L[nl] * V), bl.weight, bl.bias, bl.running_mean, bl.running_var,
                             0.1 if bl.momentum is None else bl.momentum, bl.eps, True)
                 torch._foreach_add_([b.num_batches_tracked for b in self.bn], 1)
-        return ops.SkipHead.apply(pk['w_skip'], pk['b_skip'], pk['w_end1'], self.end_conv_1.bias, pk['w_end2'],
-                                  pk['b_end2'], self.out_dim, *z_last)
+        hk = pk['head']()
+        return ops.SkipHead.apply(hk['w_skip'], hk['b_skip'], hk['w_end1'], self.end_conv_1.bias, hk['w_end2'],
+                                  hk['b_end2'], self.out_dim, *z_last)

@@ -9,7 +9,7 @@ timeout 600 python bench.py > gpurun_out/bench_$tag.log 2>&1; rc=$?; echo "bench
 tail -n 3 gpurun_out/bench_$tag.log
 if [ $rc -eq 0 ]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches_$tag.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu --no-roofline > gpurun_out/ncu_$tag.log 2>&1; echo "ncu rc=$?"
+    python bench.py --steps 2 --warmup 1 --no-cpu --no-roofline --no-extra > gpurun_out/ncu_$tag.log 2>&1; echo "ncu rc=$?"
   python scripts/launch_summary.py gpurun_out/launches_$tag.csv 40 > gpurun_out/launch_summary_$tag.md 2>&1
   cat gpurun_out/launch_summary_$tag.md
 fi
