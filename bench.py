@@ -391,7 +391,7 @@ class Trainer:
     """One data-parallel replica of the training step of the selected WORKLOAD (forward + MSELoss + backward + gradient
     exchange at N > 1 + Adam), resident-input and end-to-end (pinned host -> device) step functions."""
 
-    def __init__(self, dev, world, rank, dtype=torch.bfloat16, use_graph=True, dropout_mode='fused', comm_capture=True,
+    def __init__(self, dev, world, rank, dtype=torch.bfloat16, use_graph=True, dropout_mode='fused', comm='fused',
                  n_batches=4):
         import torch.distributed as dist
         from multimodal_outage_b200 import gwnet, _lib
@@ -407,9 +407,17 @@ class Trainer:
         model.compute_dtype = dtype
         model.dropout_mode = dropout_mode
         model.train()
-        opt = self.opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True, fused=True)
+        # comm == 'fused' (default): Adam over one flat buffer in ONE launch, and at N > 1 the gradient all-reduce happens
+        # inside that launch over NVSwitch peer memory (multimodal_outage_b200/flat_adam.py, csrc/peer.cu).  The other
+        # values keep torch.optim.Adam (fused multi-tensor) with an NCCL exchange (--comm single|overlap|eager, A/B).
+        if comm == 'fused':
+            from multimodal_outage_b200.flat_adam import FlatAdam
+            opt = self.opt = FlatAdam(model, lr=1e-3)
+            sync = self.sync = None
+        else:
+            opt = self.opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True, fused=True)
+            sync = self.sync = BucketedGradAllReduce(model) if world > 1 else None
         loss_fn = torch.nn.MSELoss()
-        sync = self.sync = BucketedGradAllReduce(model) if world > 1 else None
 
         # distinct batches rotated through the timed loop (inputs differ every step; working set >> L2)
         R = self.R = n_batches
@@ -446,27 +454,37 @@ class Trainer:
         torch.cuda.synchronize()
         self.launches_per_step = _lib.lib().gwn_launch_count() - c0
 
-        # CUDA graph.  N = 1: the whole step.  N > 1: the whole step INCLUDING the two NCCL all-reduces (forked onto
-        # NCCL's stream by the gradient hooks, joined before Adam) - one graph launch per step, bucket 0 overlapped with
-        # the layers' backward.  If the collective cannot be captured on this stack, fall back to: graph = forward +
-        # backward + packing, then the exchange (one collective) and Adam issued eagerly after each replay.
+        # CUDA graph.  N = 1: the whole step.  N > 1, three ways to place the gradient exchange (--comm):
+        #   single   (default) the whole step in ONE graph: forward, backward, gradient packing, ONE NCCL all-reduce over the
+        #            flat gradient tensor (1.2 MB, averaged in the collective), fused Adam - one graph launch per step;
+        #   overlap  the whole step in one graph with the two bucket all-reduces launched from the gradient hooks (bucket 0
+        #            forked onto NCCL's stream under the layers' backward).  Measured slower at this step size: the NCCL
+        #            kernel takes SMs away from persistent one-CTA-per-SM kernels, whose last CTAs then run as a second wave;
+        #   eager    graph = forward + backward + packing; the collective and Adam issued eagerly after each replay.
+        # If the collective cannot be captured on this stack the next scheme in the list is used (reported in `config`).
         self.graph = None
         self.comm = 'none (1 GPU)' if world == 1 else 'eager: 2 overlapped all-reduces launched from gradient hooks'
+        if comm == 'fused':
+            self.comm = ('Adam over one flat buffer, one launch (gwn_adam_flat)' if world == 1 else
+                         'one-shot all-reduce over NVSwitch peer memory fused into the Adam kernel (gwn_allreduce_adam, one launch '
+                         'per rank, no NCCL on the step path)') + ('; whole step in one CUDA graph' if use_graph else '')
         self._post_replay = None
+        desc = {'single': 'whole step in one CUDA graph: fwd + bwd + pack + ONE all-reduce (flat 1.2 MB, NCCL AVG) + fused Adam',
+                'overlap': 'whole step in one CUDA graph: bucket 0 all-reduce forked under the layer backward, bucket 1 + fused Adam at the end',
+                'eager': 'graph = fwd + bwd + pack; ONE all-reduce + fused Adam issued eagerly after the replay'}
         if use_graph:
-            modes = ['captured'] if world == 1 else ((['captured'] if comm_capture else []) + ['split'])
+            order = {'single': ['single', 'eager'], 'overlap': ['overlap', 'single', 'eager'], 'eager': ['eager'], 'fused': []}[comm]
+            modes = ['whole'] if (world == 1 or comm == 'fused') else order
             for mode in modes:
                 try:
                     self._capture(mode, fwd_bwd, step_eager)
-                    if world > 1:
-                        self.comm = ('captured in the step graph: bucket 0 all-reduce overlaps the layer backward, bucket 1 + '
-                                     'fused Adam at the end' if mode == 'captured' else
-                                     'graph = fwd + bwd + pack; ONE all-reduce + fused Adam eagerly after the replay')
+                    if world > 1 and comm != 'fused':
+                        self.comm = desc[mode]
                     break
                 except Exception as e:                            # noqa: BLE001
                     if mode == modes[-1]:
                         raise
-                    print(f'[bench] capturing the collective failed ({type(e).__name__}: {e}); using the split scheme',
+                    print(f'[bench] capturing the collective ({mode}) failed ({type(e).__name__}: {e}); trying the next scheme',
                           file=sys.stderr, flush=True)
                     torch.cuda.synchronize()
                     self.graph = None
@@ -482,20 +500,24 @@ class Trainer:
 
     def _capture(self, mode, fwd_bwd, step_eager):
         sync, opt = self.sync, self.opt
-        if mode == 'split':
+        self._post_replay = None
+        if mode in ('single', 'eager'):
             sync.remove()                                         # hooks off: gradients are packed explicitly
             sync.overlap = False
-
-            def captured(x, y):
-                loss = fwd_bwd(x, y)
-                sync.pack()
-                return loss
 
             def post():
                 sync.reduce()
                 opt.step()
-            self._post_replay = post
-        else:
+
+            def captured(x, y):
+                loss = fwd_bwd(x, y)
+                sync.pack()
+                if mode == 'single':
+                    post()
+                return loss
+            if mode == 'eager':
+                self._post_replay = post
+        else:                                                     # 'whole' (1 GPU) or 'overlap'
             captured = step_eager
         graph = torch.cuda.CUDAGraph()
         s = torch.cuda.Stream()
@@ -577,6 +599,8 @@ class Trainer:
         if self.sync is not None:
             self.sync.remove()
         torch.cuda.synchronize()
+        if hasattr(self.opt, 'close'):
+            self.opt.close()
 
 
 def side_run(key, dev, world, rank, steps, warmup, **kw):
@@ -611,7 +635,7 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     dev = torch.device('cuda', local)
     w = WORKLOAD
-    tr = Trainer(dev, world, rank, use_graph=not args.no_graph, comm_capture=not args.no_comm_capture)
+    tr = Trainer(dev, world, rank, use_graph=not args.no_graph, comm=args.comm)
     n = tr.n
 
     sampler = ClockSampler(local)
@@ -630,11 +654,11 @@ def run_ours(args):
     # quotes at 1/2/4/8 GPUs, the reference's exact dropout draws, and the fp32 parity mode
     extra = {}
     if not args.no_extra and args.config == 'c2':
-        extra['config3'] = side_run('c3', dev, world, rank, 4, 3, use_graph=False)
-        extra['config5'] = side_run('c5', dev, world, rank, 2, 2, use_graph=False)
+        extra['config3'] = side_run('c3', dev, world, rank, 4, 3, comm=args.comm)
+        extra['config5'] = side_run('c5', dev, world, rank, 2, 2, comm=args.comm)
         if world == 1:
-            extra['config2_dropout_mode_torch'] = side_run('c2', dev, world, rank, 20, 5, dropout_mode='torch')
-            extra['config2_fp32'] = side_run('c2', dev, world, rank, 10, 3, dtype=torch.float32)
+            extra['config2_dropout_mode_torch'] = side_run('c2', dev, world, rank, 20, 5, dropout_mode='torch', comm=args.comm)
+            extra['config2_fp32'] = side_run('c2', dev, world, rank, 10, 3, dtype=torch.float32, comm=args.comm)
 
     if rank == 0:
         peaks = {}
@@ -657,7 +681,8 @@ def run_ours(args):
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
             'config': {'workload': w['name'], 'batch_per_gpu': n, 'global_batch': world * n, 'dropout': w['dropout'],
-                       'optimizer': 'Adam(lr=1e-3)', 'parallelism': f'dp{world}', 'cuda_graph': graph_on,
+                       'optimizer': 'Adam(lr=1e-3)' + (' [FlatAdam: same update rule, one launch]' if args.comm == 'fused' else ' [torch.optim.Adam, fused]'),
+                       'parallelism': f'dp{world}', 'cuda_graph': graph_on,
                        'gradient_exchange': comm,
                        'l2': '4 distinct input batches rotated; per-step working set (activations+workspaces, '
                              '>1 GB) exceeds the 126 MB L2; kernel microbenchmarks use buffers > L2'},
@@ -686,7 +711,9 @@ def main():
     ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))
     ap.add_argument('--no-roofline', action='store_true')
     ap.add_argument('--no-extra', action='store_true', help='skip the config3 / config5 / dropout-mode / fp32 side records')
-    ap.add_argument('--no-comm-capture', action='store_true', help='N > 1: keep the collective out of the CUDA graph (A/B)')
+    ap.add_argument('--comm', default='fused', choices=['fused', 'single', 'overlap', 'eager'],
+                    help='optimizer + gradient exchange (see Trainer): fused = FlatAdam with the all-reduce inside the Adam '
+                         'kernel (default); the others = torch.optim.Adam with an NCCL all-reduce placed three ways (A/B)')
     args = ap.parse_args()
     select_config(args.config)
     if args.impl == 'reference':

@@ -336,11 +336,28 @@ int gwn_unpack_grads(const gwn_pack_cfg* cfg, const gwn_unpack_ptrs* grads, floa
 int gwn_node_mix(const void* x, int x_pitch, int x_off, void* y, int y_pitch, int y_off, int accumulate,
                  const float* A, int transpose_a, int slabs, int V, int dtype, void* stream);
 
-/* ---- data-parallel gradient all-reduce over NCCL (absent in the reference) ---- */
-int gwn_comm_unique_id(void* out128);                       /* host buffer, 128 bytes */
-int gwn_comm_init(const void* id128, int rank, int world);  /* host */
-int gwn_comm_allreduce_avg(float* buf, long long count, void* stream);
-int gwn_comm_destroy(void);
+/* ---- optimizer step, and the data-parallel gradient exchange fused with it (csrc/peer.cu) ----
+ * Replaces, for the train step of lit.py:29-43,59-61 (torch.optim.Adam(lr=1e-3), amsgrad off, no weight decay):
+ *   1 GPU : `optimizer.step()` over ~110 small tensors (three multi-tensor launches) -> gwn_adam_flat, ONE launch over
+ *           the flat fp32 parameter / gradient / moment buffers;
+ *   N GPUs: gradient all-reduce (the reference has no distributed code) + `optimizer.step()` ->
+ *           gwn_allreduce_adam, ONE launch per rank: one-shot all-reduce (average) over NVLink / NVSwitch peer memory
+ *           fused with the Adam update.
+ * Exchange block = gwn_peer_header_bytes() of flags followed by the flat gradient; allocate with gwn_peer_alloc (cudaMalloc,
+ * zeroed), export with gwn_peer_export (64-byte CUDA IPC handle, host buffer), map the peers' blocks with gwn_peer_open.
+ * `state` = 2 x uint64 on the device, zero-initialised: [completed steps, CTA counter]; the step count advances on the
+ * device, so CUDA-graph replays work.  `blocks[r]` = exchange block of rank r as mapped in THIS process (blocks[rank] = own).
+ * Every rank must launch once per step; a rank that never arrives makes the others trap (bounded polls), never hang. */
+long long gwn_peer_header_bytes(void);
+int gwn_peer_alloc(long long grad_bytes, void** block);
+int gwn_peer_free(void* block);
+int gwn_peer_export(const void* block, void* handle64);
+int gwn_peer_open(const void* handle64, void** mapped_block);
+int gwn_peer_close(void* mapped_block);
+int gwn_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                  void* state, void* stream);
+int gwn_allreduce_adam(float* p, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                       void* state, const void* const* blocks, int rank, int world, void* stream);
 
 #ifdef __cplusplus
 }

@@ -130,10 +130,14 @@ SIGNATURES = {
     'gwn_unpack_total': (_ll, [C.POINTER(PackCfg)]),
     'gwn_unpack_grads': (_i, [C.POINTER(PackCfg), C.POINTER(UnpackPtrs), vp, vp]),
     'gwn_node_mix': (_i, [vp, _i, _i, vp, _i, _i, _i, vp, _i, _i, _i, _i, vp]),
-    'gwn_comm_unique_id': (_i, [vp]),
-    'gwn_comm_init': (_i, [vp, _i, _i]),
-    'gwn_comm_allreduce_avg': (_i, [vp, _ll, vp]),
-    'gwn_comm_destroy': (_i, []),
+    'gwn_peer_header_bytes': (_ll, []),
+    'gwn_peer_alloc': (_i, [_ll, C.POINTER(vp)]),
+    'gwn_peer_free': (_i, [vp]),
+    'gwn_peer_export': (_i, [vp, vp]),
+    'gwn_peer_open': (_i, [vp, C.POINTER(vp)]),
+    'gwn_peer_close': (_i, [vp]),
+    'gwn_adam_flat': (_i, [vp, vp, vp, vp, _ll, _f, _f, _f, _f, vp, vp]),
+    'gwn_allreduce_adam': (_i, [vp, vp, vp, _ll, _f, _f, _f, _f, vp, C.POINTER(vp), _i, _i, vp]),
 }
 
 _lib = None

@@ -622,14 +622,16 @@ def test_bf16_head_on_tensor_cores_fwd_bwd_vs_oracle(nl, S, E, Lf):
 
 @pytest.mark.gpu
 def test_param_packing_layouts_and_gradient_unpacking():
-    """_PackParams = one gather launch / one scatter launch (csrc/pack.cu): check layouts element-wise and that
-    gradients of the packed tensors are routed back to the reference-shaped parameters exactly."""
+    """Parameter packing = one gather launch; gradient scatter = one launch per autograd node (_PackLayers, _PackHead;
+    csrc/pack.cu): check layouts element-wise and that gradients of the packed tensors are routed back to the
+    reference-shaped parameters exactly."""
     from multimodal_outage_b200 import gwnet
     torch.manual_seed(0)
     m = gwnet('cuda', in_dim=2, out_dim=12, kernel_size=3, blocks=1, layers=2, skip_channels=64, end_channels=96,
               supports=[torch.eye(67)] * 2)
     m.skip_convs[0].bias.data.normal_(); m.skip_convs[1].bias.data.normal_()
     pk = m._packed()
+    pk.update(pk.pop('head')())
     Wf, Wg = m.filter_convs[1].weight, m.gate_convs[1].weight
     w_fg = pk['w_fg'][1]
     assert w_fg.shape == (3 * 32, 64)
