@@ -206,7 +206,7 @@ class gwnet(nn.Module):
             supports = [torch.eye(num_nodes, dtype=torch.float32)]
         self.supports_len = 0 if supports is None else len(supports)
         self.supports: List[torch.Tensor] = [] if supports is None else \
-            [torch.as_tensor(s, dtype=torch.float32).to(device) for s in supports]
+            [torch.as_tensor(s, dtype=torch.float32).to(device).contiguous() for s in supports]
 
         if gcn_bool and addaptadj:
             if aptinit is None:
@@ -249,7 +249,7 @@ class gwnet(nn.Module):
     # let .to()/.cuda() move them with the module
     def _apply(self, fn, *args, **kwargs):
         super()._apply(fn, *args, **kwargs)
-        self.supports = [fn(s) for s in self.supports]
+        self.supports = [fn(s).contiguous() for s in self.supports]
         if self._rng_state is not None:
             self._rng_state = fn(self._rng_state)
         return self
@@ -350,6 +350,22 @@ class gwnet(nn.Module):
             hop_mats = ops.hop_mats(sup_c) if ops.hop_mode(V, len(sup_c)) == 1 else ops.support_images(sup_c)
 
         u = ops.StartConv.apply(x, self.start_conv.weight, self.start_conv.bias, L[0], dt == torch.bfloat16)
+        # per-step gradient workspace (bf16 tensor-core path): ONE zero-filled buffer whose slices receive every layer's
+        # small accumulated gradients (BN-backward statistics, dW, db) and ONE accumulator for the adaptive support's
+        # gradient that all layers add into - instead of a fill per layer and an autograd add per layer
+        grad_ws = None
+        if (training and torch.is_grad_enabled() and hop_mats is not None and dt == torch.bfloat16 and self.gcn_bool and
+                self.kernel_size <= 4 and sum(bool(s.requires_grad) for s in supports) <= 1):
+            mlp_in = CH * (1 + 2 * len(supports))
+            per = sum(ops._layer_bwd_sizes(self.kernel_size, mlp_in, V, [], True))
+            per = (per + 3) // 4 * 4
+            acc_n = sum(s.numel() for s in supports if s.requires_grad)
+            ws = torch.zeros(nl * per + acc_n, device=x.device, dtype=torch.float32)
+            d_acc = None
+            for s in supports:
+                if s.requires_grad:
+                    d_acc = ws[nl * per:].view(s.shape)
+            grad_ws = [dict(flat=ws[i * per:(i + 1) * per], d_acc=d_acc, first=(i == 0)) for i in range(nl)]
         stats = None
         z_last = []
         for i in range(nl):
@@ -362,6 +378,8 @@ class gwnet(nn.Module):
                         dropout_p=p_drop if masks[i] is None else 1.0, seed=0, offset=i)
             if masks[i] is not None:
                 meta['dropout_p'] = p_drop
+            if grad_ws is not None:
+                meta['grad_ws'] = grad_ws[i]
             u, stats, zl = ops.WaveNetLayer.apply(
                 u, stats,
                 None if bn_prev is None else bn_prev.weight, None if bn_prev is None else bn_prev.bias,

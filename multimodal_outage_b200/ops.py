@@ -403,15 +403,10 @@ def _(u_prev, scale, shift, w_fg, b_fg, w_mlp, b_mlp, supports, drop_mask, rng, 
             u_prev.new_empty(full if training else (0,)))
 
 
-@torch.library.custom_op('gwn::layer_bwd', mutates_args=())
-def layer_bwd(u_prev: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], w_fg: Tensor,
-              w_mlp: Optional[Tensor], supports: List[Tensor], needs_grad: List[bool],
-              drop_mask: Optional[Tensor], rng: Optional[Tensor], hop_mats: Optional[Tensor], a: Tensor, b: Tensor,
-              du: Optional[Tensor], dz_last: Optional[Tensor], Lf: int, taps: int, dilation: int, order: int, training: bool,
-              dropout_p: float, seed: int, offset: int) -> List[Tensor]:
-    """Returns [dx_prev, flat]: flat is ONE zero-initialised fp32 buffer holding, back to back, dx_stats (64 fp64),
-    dw_fg, db_fg, dw_mlp, db_mlp and d_support_i for the supports whose needs_grad is True - see
-    `_split_layer_bwd` (custom-op outputs may not alias, so the views are cut outside the op)."""
+def _layer_bwd_impl(u_prev, scale, shift, w_fg, w_mlp, supports, needs_grad, drop_mask, rng, hop_mats, a, b, du, dz_last,
+                    Lf, taps, dilation, order, training, dropout_p, seed, offset, flat_ws=None, d_acc=None):
+    """flat_ws / d_acc: optional caller-owned, already zeroed accumulation buffers (the model hands every layer a slice
+    of ONE per-step buffer and ONE shared support-gradient accumulator: no per-layer fill, no per-layer add)."""
     N, Lin, V, _c = u_prev.shape
     Lout = Lin - dilation * (taps - 1)
     dt, dev = u_prev.dtype, u_prev.device
@@ -426,15 +421,24 @@ def layer_bwd(u_prev: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], 
     dx_prev = torch.empty((N, Lin, V, CH), device=dev, dtype=torch.bfloat16 if dx_bf16 else torch.float32)
     # the small accumulated outputs live in ONE zero-filled buffer (one fill kernel instead of six memset nodes)
     pairs = [s.dim() == 3 for s in supports]         # [2,V,V] supports take their gradient in factored form (d0, Q)
-    sizes = _layer_bwd_sizes(taps, mlp_in, V, needs_grad, has_du, pairs)
-    flat = torch.zeros((sum(sizes),), **f32)
+    if flat_ws is None:
+        sizes = _layer_bwd_sizes(taps, mlp_in, V, needs_grad, has_du, pairs)
+        flat = torch.zeros((sum(sizes),), **f32)
+    else:                                            # the support gradient goes to the shared accumulator
+        sizes = _layer_bwd_sizes(taps, mlp_in, V, [False] * len(needs_grad), has_du, pairs)
+        flat = flat_ws
+        if flat.numel() < sum(sizes) or flat.dtype != torch.float32:
+            raise ValueError('layer_bwd: gradient workspace too small')
     parts, off = [], 0
     for sz in sizes:
         parts.append(flat[off:off + sz]); off += sz
     dx_stats = parts[0].view(torch.float64).view(2, CH)
     dw_fg, db_fg = parts[1].view(taps * CH, 2 * CH), parts[2]
     dw_mlp, db_mlp = parts[3].view(mlp_in, CH), parts[4]
-    d_sup = [parts[5 + i] if (g and has_du) else torch.empty((0,), **f32) for i, g in enumerate(needs_grad)]
+    if flat_ws is None:
+        d_sup = [parts[5 + i] if (g and has_du) else torch.empty((0,), **f32) for i, g in enumerate(needs_grad)]
+    else:
+        d_sup = [d_acc.reshape(-1) if (g and has_du) else torch.empty((0,), **f32) for g in needs_grad]
     ws_cat = torch.empty((P, mlp_in) if has_du else (0,), device=dev, dtype=dt)
     ws_dcat = torch.empty((P, mlp_in) if has_du else (0,), device=dev, dtype=dt)
     ws_dfg = torch.empty((P, 2 * CH), **f32)
@@ -454,6 +458,43 @@ def layer_bwd(u_prev: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], 
     with torch.cuda.device(dev):
         check(lib().gwn_layer_bwd(C.byref(cfg), C.byref(args), _stream()), 'gwn_layer_bwd')
     return [dx_prev, flat]
+
+
+@torch.library.custom_op('gwn::layer_bwd', mutates_args=())
+def layer_bwd(u_prev: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], w_fg: Tensor,
+              w_mlp: Optional[Tensor], supports: List[Tensor], needs_grad: List[bool],
+              drop_mask: Optional[Tensor], rng: Optional[Tensor], hop_mats: Optional[Tensor], a: Tensor, b: Tensor,
+              du: Optional[Tensor], dz_last: Optional[Tensor], Lf: int, taps: int, dilation: int, order: int, training: bool,
+              dropout_p: float, seed: int, offset: int) -> List[Tensor]:
+    """Returns [dx_prev, flat]: flat is ONE zero-initialised fp32 buffer holding, back to back, dx_stats (64 fp64),
+    dw_fg, db_fg, dw_mlp, db_mlp and d_support_i for the supports whose needs_grad is True - see
+    `_split_layer_bwd` (custom-op outputs may not alias, so the views are cut outside the op)."""
+    return _layer_bwd_impl(u_prev, scale, shift, w_fg, w_mlp, supports, needs_grad, drop_mask, rng, hop_mats, a, b, du,
+                           dz_last, Lf, taps, dilation, order, training, dropout_p, seed, offset)
+
+
+@torch.library.custom_op('gwn::layer_bwd_ws', mutates_args=('flat_ws', 'd_acc'))
+def layer_bwd_ws(flat_ws: Tensor, d_acc: Optional[Tensor], u_prev: Tensor, scale: Optional[Tensor], shift: Optional[Tensor],
+                 w_fg: Tensor, w_mlp: Optional[Tensor], supports: List[Tensor], needs_grad: List[bool],
+                 drop_mask: Optional[Tensor], rng: Optional[Tensor], hop_mats: Optional[Tensor], a: Tensor, b: Tensor,
+                 du: Optional[Tensor], dz_last: Optional[Tensor], Lf: int, taps: int, dilation: int, order: int,
+                 training: bool, dropout_p: float, seed: int, offset: int) -> Tensor:
+    """layer_bwd accumulating into caller-owned zeroed buffers: `flat_ws` (this layer's slice of the per-step gradient
+    workspace: dx_stats, dw_fg, db_fg, dw_mlp, db_mlp) and `d_acc` (the ONE support-gradient accumulator every layer of
+    the step adds into; at most one support may need a gradient).  Returns dx_prev."""
+    if sum(bool(g) for g in needs_grad) > (1 if d_acc is not None else 0):
+        raise ValueError('layer_bwd_ws: one shared accumulator serves one support gradient')
+    return _layer_bwd_impl(u_prev, scale, shift, w_fg, w_mlp, supports, needs_grad, drop_mask, rng, hop_mats, a, b, du,
+                           dz_last, Lf, taps, dilation, order, training, dropout_p, seed, offset, flat_ws=flat_ws,
+                           d_acc=d_acc)[0]
+
+
+@layer_bwd_ws.register_fake
+def _(flat_ws, d_acc, u_prev, scale, shift, w_fg, w_mlp, supports, needs_grad, drop_mask, rng, hop_mats, a, b, du, dz_last,
+      Lf, taps, dilation, order, training, dropout_p, seed, offset):
+    N, Lin, V, _c = u_prev.shape
+    dx_bf16 = u_prev.dtype == torch.bfloat16 and hop_mats is not None and taps <= 4
+    return u_prev.new_empty((N, Lin, V, CH), dtype=torch.bfloat16 if dx_bf16 else torch.float32)
 
 
 def _layer_bwd_sizes(taps: int, mlp_in: int, V: int, needs_grad: Sequence[bool], has_du: bool,
@@ -539,17 +580,28 @@ class WaveNetLayer(torch.autograd.Function):
         if du is not None and du.numel() == 0:
             du = None
         has_du = du is not None and m['has_gconv']
-        outs = layer_bwd(u_prev, scale, shift, w_fg, w_mlp if has_du else None, sup if has_du else [],
-                         ctx.sup_needs if has_du else [], drop_mask, rng, hop_mats, a, b,
-                         du.contiguous() if has_du else None,
-                         dz_last.contiguous() if dz_last is not None else None,
-                         m['Lf'], m['taps'], m['dilation'], m['order'], True, m['dropout_p'], m['seed'],
-                         m['offset'])
-        dx_prev, flat = outs
+        gw = m.get('grad_ws')
         n_sup_b = len(sup) if has_du else 0
-        dx_stats, dw_fg, db_fg, dw_mlp, db_mlp, d_sup = _split_layer_bwd(
-            flat, m['taps'], CH * (1 + m['order'] * n_sup_b), u_prev.shape[2], ctx.sup_needs if has_du else [], has_du,
-            [s.dim() == 3 for s in sup] if has_du else [])
+        needs = ctx.sup_needs if has_du else []
+        args = (u_prev, scale, shift, w_fg, w_mlp if has_du else None, sup if has_du else [], needs, drop_mask, rng,
+                hop_mats, a, b, du.contiguous() if has_du else None,
+                dz_last.contiguous() if dz_last is not None else None,
+                m['Lf'], m['taps'], m['dilation'], m['order'], True, m['dropout_p'], m['seed'], m['offset'])
+        if gw is not None and sum(needs) <= 1:
+            # per-step gradient workspace (graph_wavenet._forward_nchw): this layer's zeroed slice + the shared
+            # support-gradient accumulator; the accumulated support gradient is handed to autograd by layer 0 only
+            # (its backward runs last: every other layer's contribution is already in)
+            flat = gw['flat']
+            dx_prev = layer_bwd_ws(flat, gw['d_acc'] if any(needs) else None, *args)
+            dx_stats, dw_fg, db_fg, dw_mlp, db_mlp, _none = _split_layer_bwd(
+                flat, m['taps'], CH * (1 + m['order'] * n_sup_b), u_prev.shape[2], [False] * len(needs), has_du,
+                [s.dim() == 3 for s in sup] if has_du else [])
+            d_sup = [gw['d_acc'] if (g and gw['first']) else None for g in needs]
+        else:
+            dx_prev, flat = layer_bwd(*args)
+            dx_stats, dw_fg, db_fg, dw_mlp, db_mlp, d_sup = _split_layer_bwd(
+                flat, m['taps'], CH * (1 + m['order'] * n_sup_b), u_prev.shape[2], needs, has_du,
+                [s.dim() == 3 for s in sup] if has_du else [])
         if ctx.has_bn:
             du_prev, dgamma, dbeta = bn_bwd(dx_prev, u_prev, dx_stats, ctx.count, gamma, mean, rstd, True)
         else:

@@ -12,7 +12,8 @@ model = gwnet(dev, num_nodes=w['V'], dropout=w['dropout'], supports=[torch.tenso
               in_dim=w['in_dim'], out_dim=w['out_dim'], kernel_size=w['kernel_size'], blocks=w['blocks'], layers=w['layers'])
 model.compute_dtype = torch.bfloat16
 model.train()
-opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True, fused=True)
+from multimodal_outage_b200.flat_adam import FlatAdam
+opt = FlatAdam(model, lr=1e-3)
 n = w['batch_per_gpu']
 x = torch.randn(n, w['in_dim'], w['V'], w['T'], device=dev); y = torch.randn(n, w['out_dim'], w['V'], 1, device=dev)
 def step():
