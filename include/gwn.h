@@ -348,6 +348,9 @@ int gwn_node_mix(const void* x, int x_pitch, int x_off, void* y, int y_pitch, in
  * `state` = 2 x uint64 on the device, zero-initialised: [completed steps, CTA counter]; the step count advances on the
  * device, so CUDA-graph replays work.  `blocks[r]` = exchange block of rank r as mapped in THIS process (blocks[rank] = own).
  * Every rank must launch once per step; a rank that never arrives makes the others trap (bounded polls), never hang. */
+/* srcs[k] (device pointers, NULL = zeros) of counts[k] fp32 elements each -> `out` back to back: one launch (pointer table
+ * by value, n <= 160).  The gradient packing step in front of gwn_adam_flat / gwn_allreduce_adam. */
+int gwn_gather_flat(const void* const* srcs, const long long* counts, int n, float* out, void* stream);
 long long gwn_peer_header_bytes(void);
 int gwn_peer_alloc(long long grad_bytes, void** block);
 int gwn_peer_free(void* block);

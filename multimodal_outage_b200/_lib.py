@@ -130,6 +130,7 @@ SIGNATURES = {
     'gwn_unpack_total': (_ll, [C.POINTER(PackCfg)]),
     'gwn_unpack_grads': (_i, [C.POINTER(PackCfg), C.POINTER(UnpackPtrs), vp, vp]),
     'gwn_node_mix': (_i, [vp, _i, _i, vp, _i, _i, _i, vp, _i, _i, _i, _i, vp]),
+    'gwn_gather_flat': (_i, [C.POINTER(vp), C.POINTER(_ll), _i, vp, vp]),
     'gwn_peer_header_bytes': (_ll, []),
     'gwn_peer_alloc': (_i, [_ll, C.POINTER(vp)]),
     'gwn_peer_free': (_i, [vp]),

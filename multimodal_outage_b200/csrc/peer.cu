@@ -152,9 +152,51 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_flat_kernel(float* __restri
   }
 }
 
+// ---- gather of the per-parameter gradients into the flat gradient: ONE launch, pointer table passed by value
+constexpr int GATHER_MAX = 160;
+struct GatherTable {
+  const float* src[GATHER_MAX];
+  int off[GATHER_MAX + 1];       // element offsets in the flat buffer (prefix sums), off[n] = total
+  int n;
+};
+__global__ void __launch_bounds__(256) gather_flat_kernel(const __grid_constant__ GatherTable t, float* __restrict__ out) {
+  // element-parallel over the whole flat buffer (tensors range from 32 to 131072 elements: a per-tensor split would
+  // leave most CTAs idle); the owning tensor of an element is found by bisection in the offset table (constant bank)
+  const int total = t.off[t.n];
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+    int lo = 0, hi = t.n;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (i >= t.off[mid]) lo = mid; else hi = mid;
+    }
+    const float* s = t.src[lo];
+    const int j = i - t.off[lo];
+    if (s == nullptr) out[i] = 0.f;
+    else if (s + j != out + i) out[i] = __ldg(s + j);      // (src == dst: the gradient is already in place)
+  }
+}
+
 }  // namespace gwn
 
 using namespace gwn;
+
+extern "C" int gwn_gather_flat(const void* const* srcs, const long long* counts, int n, float* out, void* stream) {
+  GWN_REQUIRE(srcs && counts && out && n >= 1 && n <= GATHER_MAX, "gather_flat: 1..%d tensors", GATHER_MAX);
+  GatherTable t{};
+  long long off = 0;
+  for (int k = 0; k < n; ++k) {
+    GWN_REQUIRE(counts[k] >= 0 && off + counts[k] < (1ll << 31), "gather_flat: sizes out of range");
+    t.src[k] = reinterpret_cast<const float*>(srcs[k]);
+    t.off[k] = (int)off;
+    off += counts[k];
+  }
+  t.off[n] = (int)off;
+  t.n = n;
+  const long long blocks = cdiv(off, 256 * 4);
+  gather_flat_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks > 592 ? 592 : blocks), 256, 0, (cudaStream_t)stream>>>(t, out);
+  GWN_LAUNCHED();
+  return 0;
+}
 
 extern "C" long long gwn_peer_header_bytes(void) { return PEER_HDR; }
 

@@ -71,6 +71,7 @@ class FlatAdam:
                 p.data = self.flat_p[off:off + k].view_as(p)
                 self._g_views.append(self.flat_g[off:off + k].view_as(p))
                 off += k
+        self._counts = (C.c_longlong * len(self.params))(*[p.numel() for p in self.params])
         self._mapped: List[Optional[int]] = [None] * self.world
         self._blocks = None
         if self.world > 1:
@@ -99,10 +100,28 @@ class FlatAdam:
 
     # ------------------------------------------------------------------ step
     def pack_grads(self):
-        """Gathers this step's per-parameter gradients into the flat gradient of the exchange block (one multi-tensor
-        copy) and points ``.grad`` at the flat views."""
-        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
-        torch._foreach_copy_(self._g_views, grads)
+        """Gathers this step's per-parameter gradients into the flat gradient of the exchange block (one launch:
+        `gwn_gather_flat`, pointer table by value) and points ``.grad`` at the flat views."""
+        n = len(self.params)
+        if n <= 160:                                  # one launch, pointer table by value (csrc/peer.cu)
+            srcs = (C.c_void_p * n)()
+            for i, (p, v) in enumerate(zip(self.params, self._g_views)):
+                g = p.grad
+                if g is not None and g.data_ptr() == v.data_ptr():
+                    srcs[i] = v.data_ptr()                          # already in place: the kernel skips src == dst
+                elif g is None:
+                    srcs[i] = None
+                else:
+                    if g.dtype != torch.float32 or not g.is_contiguous():
+                        g = g.float().contiguous()
+                        p.grad = g                                  # keep it alive until the launch has been enqueued
+                    srcs[i] = g.data_ptr()
+            with torch.cuda.device(self.device):
+                check(lib().gwn_gather_flat(srcs, self._counts, n, self.flat_g.data_ptr(),
+                                            torch.cuda.current_stream(self.device).cuda_stream), 'gwn_gather_flat')
+        else:
+            grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
+            torch._foreach_copy_(self._g_views, grads)
         for p, v in zip(self.params, self._g_views):
             p.grad = v
 
