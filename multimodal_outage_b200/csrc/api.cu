@@ -17,6 +17,11 @@ void set_error(const char* fmt, ...) {
 }
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GWN_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
 long long* trace_ptr(const char* env_name) {
 #ifdef GWN_TRACE
   const char* e = getenv(env_name);

@@ -37,6 +37,27 @@ void count_launch();
 
 typedef __nv_bfloat16 bf16;
 
+// ---- programmatic dependent launch (PDL): a kernel launched with launch_pdl() may start while its predecessor in the
+// stream is still draining - its CTAs become resident as the predecessor's CTAs exit and run their prologue (barrier /
+// TMEM set-up, resident weight and support images: data that is constant within a step).  pdl_wait() blocks until the
+// predecessor has completed and its memory is visible: it must precede every access to data an earlier kernel of the
+// step produces or still reads.  pdl_trigger() (placed AFTER the kernel's own pdl_wait: at most two kernels overlap)
+// allows the successor's launch.  Both are no-ops for normal launches.  GWN_PDL=0 turns the launch attribute off (A/B).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // Debug timelines (scripts/gpu_*_trace.py): a device pointer handed over in an environment variable.  Only builds made
 // with -DGWN_TRACE (GWN_TRACE=1 python -m multimodal_outage_b200.build) look at the environment at all: the release
 // library never parses an environment-supplied pointer and pays no getenv per launch.

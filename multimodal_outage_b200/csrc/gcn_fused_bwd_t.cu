@@ -226,6 +226,10 @@ __global__ void __launch_bounds__(BT_THREADS, 1) gcn_bwd_t_kernel(const __grid_c
     if (tid < 32) dbs[tid] = 0.f;
     fence_proxy_async();
   }
+  // everything above read step-constant data only (support image, mlp weights) and wrote shared memory: it may run while
+  // the previous kernel of the stream drains.  du / a / b / dz_last and every output are touched after this point.
+  pdl_wait();
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -836,8 +840,8 @@ int launch_gcn_bwd_t(GcnBwdParams& p, cudaStream_t st) {
       attr = true;                                                                                                      \
     }                                                                                                                   \
     constexpr BtGeom G_(NM_, NPD_);                                                                                     \
-    if (has_da) gcn_bwd_t_kernel<NM_, NPD_, true><<<grid, BT_THREADS, bt_layout(G_, true).total, st>>>(p);              \
-    else gcn_bwd_t_kernel<NM_, NPD_, false><<<grid, BT_THREADS, bt_layout(G_, false).total, st>>>(p);                   \
+    if (has_da) GWN_CUDA(launch_pdl(gcn_bwd_t_kernel<NM_, NPD_, true>, dim3(grid), dim3(BT_THREADS), bt_layout(G_, true).total, st, p)); \
+    else GWN_CUDA(launch_pdl(gcn_bwd_t_kernel<NM_, NPD_, false>, dim3(grid), dim3(BT_THREADS), bt_layout(G_, false).total, st, p));  \
     GWN_LAUNCHED();                                                                                                     \
     return 0;                                                                                                           \
   }

@@ -154,6 +154,10 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gcn_fwd_t_kernel(const __grid_c
     if (tid < 64) sscr[tid] = 0.f;
     fence_proxy_async();
   }
+  // the prologue read step-constant data only (support image, mlp weights): under a programmatic launch it runs while the
+  // gate kernel that produces z / scale / shift drains; those, the residual and all outputs come after this point
+  pdl_wait();
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -445,7 +449,7 @@ int launch_gcn_fwd_t(GcnFwdParams& p, cudaStream_t st) {
       GWN_CUDA(cudaFuncSetAttribute(gcn_fwd_t_kernel<NM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
       attr = true;                                                                                                    \
     }                                                                                                                 \
-    gcn_fwd_t_kernel<NM_><<<grid, GT_THREADS, L.total, st>>>(zmap, p);                                                \
+    GWN_CUDA(launch_pdl(gcn_fwd_t_kernel<NM_>, dim3(grid), dim3(GT_THREADS), L.total, st, zmap, p));                  \
     GWN_LAUNCHED();                                                                                                   \
     return 0;                                                                                                         \
   }

@@ -571,6 +571,8 @@ __global__ void bn_bwd_kernel(const DX* __restrict__ dx, const T* __restrict__ u
                               double count, const float* gamma, const float* mean, const float* rstd,
                               int training, T* __restrict__ du, float* dgamma, float* dbeta, long long rows) {
   __shared__ float k0[32], k1[32], k2[32];  // du = k0*dx + k1*u + k2
+  pdl_wait();         // (programmatic launch: only the launch latency overlaps - dx_stats come from the predecessor)
+  pdl_trigger();
   if (threadIdx.x < 32) {
     int c = threadIdx.x;
     double sdx = dx_stats[c], sdxu = dx_stats[32 + c];
@@ -1371,14 +1373,14 @@ extern "C" int gwn_bn_bwd(const void* dx, int dx_dtype, const void* u, int dtype
   unsigned blocks = (unsigned)cdiv(rows * 4, 256);
   if (blocks == 0) blocks = 1;
   if (dtype == GWN_F32)
-    bn_bwd_kernel<float, float><<<blocks, 256, 0, st>>>((const float*)dx, (const float*)u, dx_stats, count, gamma, mean, rstd,
-                                                        training, (float*)du, dgamma, dbeta, rows);
+    GWN_CUDA(launch_pdl(bn_bwd_kernel<float, float>, dim3(blocks), dim3(256), 0, st, (const float*)dx, (const float*)u, dx_stats, count, gamma, mean, rstd,
+                                                        training, (float*)du, dgamma, dbeta, rows));
   else if (dx_dtype == GWN_F32)
-    bn_bwd_kernel<bf16, float><<<blocks, 256, 0, st>>>((const float*)dx, (const bf16*)u, dx_stats, count, gamma, mean, rstd,
-                                                       training, (bf16*)du, dgamma, dbeta, rows);
+    GWN_CUDA(launch_pdl(bn_bwd_kernel<bf16, float>, dim3(blocks), dim3(256), 0, st, (const float*)dx, (const bf16*)u, dx_stats, count, gamma, mean, rstd,
+                                                       training, (bf16*)du, dgamma, dbeta, rows));
   else
-    bn_bwd_kernel<bf16, bf16><<<blocks, 256, 0, st>>>((const bf16*)dx, (const bf16*)u, dx_stats, count, gamma, mean, rstd,
-                                                      training, (bf16*)du, dgamma, dbeta, rows);
+    GWN_CUDA(launch_pdl(bn_bwd_kernel<bf16, bf16>, dim3(blocks), dim3(256), 0, st, (const bf16*)dx, (const bf16*)u, dx_stats, count, gamma, mean, rstd,
+                                                      training, (bf16*)du, dgamma, dbeta, rows));
   GWN_LAUNCHED();
   return 0;
 }

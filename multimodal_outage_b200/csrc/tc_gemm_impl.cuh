@@ -152,6 +152,11 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
         *reinterpret_cast<uint16_t*>(atom + k * 64 + ((k >> 1) & 3) * 16) = 0x3F80u;   // bf16 1.0
     }
   }
+  // Programmatic launch: barrier / TMEM / ones-atom set-up above overlapped the predecessor's tail.  The weight image below
+  // is step-constant too UNLESS it folds the batch statistics the predecessor just produced (wsrc.bn == 1, training) or is
+  // a prepared image (w_img): only then the wait comes first; otherwise it follows the image build.
+  const bool pdl_early = p.wsrc.W == nullptr || p.wsrc.bn == 1;
+  if (pdl_early) { pdl_wait(); pdl_trigger(); }
   if (p.wsrc.W == nullptr) {
     const uint4* src = reinterpret_cast<const uint4*>(p.w_img);
     uint4* dst = reinterpret_cast<uint4*>(w_s);
@@ -190,7 +195,6 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
       }
       sc_s[tid] = sc; sc_s[32 + tid] = sh;
     }
-    if (blockIdx.x == 0 && ws.zero64 && tid >= 64 && tid < 128) ws.zero64[tid - 64] = 0.0;
     if (p.has_bias) {                    // zero the bias chunk (two K pieces)
       uint4* bz = reinterpret_cast<uint4*>(w_s) + (size_t)(K8 - 2) * N;
       for (int i = tid; i < 2 * N; i += PGT_THREADS) bz[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -259,6 +263,9 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
     }
     __syncthreads();      // part_s lives in the first TMA stage: the producer may only start after the bias is read
   }
+  if (!pdl_early) { pdl_wait(); pdl_trigger(); }
+  // (global writes only after the wait: the zeroed statistics buffer is memory an earlier kernel may still be using)
+  if (p.wsrc.W != nullptr && blockIdx.x == 0 && p.wsrc.zero64 && tid >= 64 && tid < 128) p.wsrc.zero64[tid - 64] = 0.0;
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -454,7 +461,7 @@ static int pos_gemm_tc_run(const PgMaps& maps, const PgParams& p, const Epi& epi
     GWN_CUDA(cudaFuncSetAttribute(pos_gemm_tc_kernel<Epi, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  pos_gemm_tc_kernel<Epi, NCH><<<grid, PGT_THREADS, smem, st>>>(maps, p, epi, stages, n_acc);
+  GWN_CUDA(launch_pdl(pos_gemm_tc_kernel<Epi, NCH>, dim3(grid), dim3(PGT_THREADS), smem, st, maps, p, epi, stages, n_acc));
   GWN_LAUNCHED();
   return 0;
 }

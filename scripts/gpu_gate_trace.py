@@ -13,11 +13,11 @@ mats = ops.hop_mats(sups)
 u_prev = torch.randn(N, Lin, V, 32, device=dev).to(bf)
 w_fg = torch.randn(64, 64, device=dev) / 8; b_fg = torch.zeros(64, device=dev)
 for _ in range(2):
-    ops.layer_fwd(u_prev, None, None, w_fg, b_fg, None, None, [], None, None, mats, 1, 2, 1, 2, False, False, 0.0, 0, 0)
+    ops.layer_fwd(u_prev, None, None, w_fg, b_fg, None, None, [], None, None, mats, 1, 2, 1, 2, os.environ.get("GATE_TRAIN", "1") == "1", False, 0.0, 0, 0)
 torch.cuda.synchronize()
 t = trace.cpu().reshape(48, 8)
 t0 = t[0, 0].item()
 names = ['prod_got_empty', 'prod_issued', 'mma_got_tempty', 'mma_got_full', 'mma_issued', 'epi_got_tfull', 'epi_done']
 print('tile ' + ' '.join(f'{n:>15s}' for n in names))
-for k in range(2, 26):
+for k in range(2, 34):
     print(f'{k:4d} ' + ' '.join(f'{(t[k, j].item() - t0) if t[k, j].item() else 0:15d}' for j in range(7)))
