@@ -11,6 +11,8 @@ constexpr int ADP_MAX_R = 16;
 __global__ void __launch_bounds__(256) adp_fwd_kernel(const float* __restrict__ e1, const float* __restrict__ e2,
                                                       float* __restrict__ adp, float* __restrict__ adp_t,
                                                       float* __restrict__ adp2, int V, int R) {
+  pdl_wait();      // programmatic launch: the launch latency overlaps the predecessor (common.cuh)
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= V) return;
@@ -50,6 +52,8 @@ __global__ void __launch_bounds__(256) adp_fwd_kernel(const float* __restrict__ 
 // One block per row p; A and Q ([V,V], a few tens of KB) stay in L1/L2.
 __global__ void __launch_bounds__(128) dadj_finish_kernel(const float* __restrict__ A, const float* __restrict__ d0,
                                                           const float* __restrict__ Q, float* __restrict__ out, int V) {
+  pdl_wait();      // programmatic launch: the launch latency overlaps the predecessor (common.cuh)
+  pdl_trigger();
   extern __shared__ float sh[];
   float* qrow = sh;          // Q[p, :]
   float* acol = sh + V;      // A[:, p]
@@ -78,6 +82,8 @@ __global__ void __launch_bounds__(256) adp_bwd_rows_kernel(const float* __restri
                                                            const float* __restrict__ dadp,
                                                            float* __restrict__ de1, float* __restrict__ dm, int V,
                                                            int R) {
+  pdl_wait();      // programmatic launch: the launch latency overlaps the predecessor (common.cuh)
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= V) return;
@@ -111,6 +117,8 @@ __global__ void __launch_bounds__(256) adp_bwd_cols_kernel(const float* __restri
                                                            const float* __restrict__ dm,
                                                            float* __restrict__ de2, int V, int R,
                                                            int rows_per_split) {
+  pdl_wait();      // programmatic launch: the launch latency overlaps the predecessor (common.cuh)
+  pdl_trigger();
   __shared__ float es[64][ADP_MAX_R];
   const int j = blockIdx.x * 256 + threadIdx.x;
   const int ib = blockIdx.y * rows_per_split, ie = min(V, ib + rows_per_split);
@@ -147,7 +155,7 @@ using namespace gwn;
 extern "C" int gwn_adp_fwd(const float* e1, const float* e2, float* adp, float* adp_t, int V, int R, void* stream) {
   GWN_REQUIRE(e1 && e2 && adp && V >= 1 && R >= 1 && R <= ADP_MAX_R, "adp_fwd: bad argument (R=%d, max %d)", R,
               ADP_MAX_R);
-  adp_fwd_kernel<<<(unsigned)cdiv(V, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(e1, e2, adp, adp_t, nullptr, V, R);
+  GWN_CUDA(launch_pdl(adp_fwd_kernel, dim3((unsigned)cdiv(V, 8)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), e1, e2, adp, adp_t, nullptr, V, R));
   GWN_LAUNCHED();
   return 0;
 }
@@ -158,8 +166,8 @@ extern "C" int gwn_adp_fwd(const float* e1, const float* e2, float* adp, float* 
 extern "C" int gwn_adp_fwd_pair(const float* e1, const float* e2, float* pair, int V, int R, void* stream) {
   GWN_REQUIRE(e1 && e2 && pair && V >= 1 && R >= 1 && R <= ADP_MAX_R, "adp_fwd_pair: bad argument (R=%d, max %d)", R,
               ADP_MAX_R);
-  adp_fwd_kernel<<<(unsigned)cdiv(V, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(e1, e2, pair, nullptr,
-                                                                                          pair + (long long)V * V, V, R);
+  GWN_CUDA(launch_pdl(adp_fwd_kernel, dim3((unsigned)cdiv(V, 8)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), e1, e2, pair, nullptr,
+                                                                                          pair + (long long)V * V, V, R));
   GWN_LAUNCHED();
   return 0;
 }
@@ -173,7 +181,7 @@ extern "C" int gwn_adp_pair_bwd(const float* e1, const float* e2, const float* a
   GWN_REQUIRE(e1 && e2 && adp && d_pair && d_e1 && d_e2 && ws && V >= 1 && R >= 1 && R <= ADP_MAX_R,
               "adp_pair_bwd: bad argument");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  dadj_finish_kernel<<<V, 128, 2 * V * sizeof(float), st>>>(adp, d_pair, d_pair + (long long)V * V, ws, V);
+  GWN_CUDA(launch_pdl(dadj_finish_kernel, dim3(V), dim3(128), 2 * V * sizeof(float), st, adp, d_pair, d_pair + (long long)V * V, ws, V));
   GWN_LAUNCHED();
   return gwn_adp_bwd(e1, e2, adp, ws, d_e1, d_e2, ws + (long long)V * V, V, R, stream);
 }
@@ -183,7 +191,7 @@ extern "C" int gwn_adp_bwd(const float* e1, const float* e2, const float* adp, c
   GWN_REQUIRE(e1 && e2 && adp && d_adp && d_e1 && d_e2 && ws && V >= 1 && R >= 1 && R <= ADP_MAX_R,
               "adp_bwd: bad argument");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  adp_bwd_rows_kernel<<<(unsigned)cdiv(V, 8), 256, 0, st>>>(e1, e2, adp, d_adp, d_e1, ws, V, R);
+  GWN_CUDA(launch_pdl(adp_bwd_rows_kernel, dim3((unsigned)cdiv(V, 8)), dim3(256), 0, st, e1, e2, adp, d_adp, d_e1, ws, V, R));
   GWN_LAUNCHED();
   GWN_CUDA(cudaMemsetAsync(d_e2, 0, sizeof(float) * (size_t)R * V, st));
   int col_tiles = (int)cdiv(V, 256);
@@ -192,7 +200,7 @@ extern "C" int gwn_adp_bwd(const float* e1, const float* e2, const float* adp, c
   per = (int)cdiv(per, 64) * 64;
   splits = (int)cdiv(V, per);
   dim3 grid(col_tiles, splits);
-  adp_bwd_cols_kernel<<<grid, 256, 0, st>>>(e1, ws, d_e2, V, R, per);
+  GWN_CUDA(launch_pdl(adp_bwd_cols_kernel, dim3(grid), dim3(256), 0, st, e1, ws, d_e2, V, R, per));
   GWN_LAUNCHED();
   return 0;
 }

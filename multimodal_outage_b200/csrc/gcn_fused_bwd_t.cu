@@ -773,6 +773,8 @@ int gcn_bwd_t_supported(int V, int n_mats, bool has_da) {
 //   element (k = w, n = column of item (r, h), slot j_l, node v_l) = Mt_j[v, w],  j = 4h + j_l, v = 32 r + v_l
 __global__ void hop_mats_bt_prep_kernel(const float* A0, const float* A1, const float* A2, const float* A3, int n_sup, int V,
                                         BtGeom G, bf16* __restrict__ out) {
+  pdl_wait();      // programmatic launch: the launch latency overlaps the predecessor (common.cuh)
+  pdl_trigger();
   const float* As[4] = {A0, A1, A2, A3};
   const int total = (G.KW / 8) * G.NTOT * 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -810,7 +812,7 @@ int launch_hop_mats_bt_prep(const float* const* supports, int n_supports, int V,
   const int total = (G.KW / 8) * G.NTOT * 8;
   const float* A[4] = {nullptr, nullptr, nullptr, nullptr};
   for (int i = 0; i < n_supports && i < 4; ++i) A[i] = supports[i];
-  hop_mats_bt_prep_kernel<<<(unsigned)cdiv(total, 256), 256, 0, st>>>(A[0], A[1], A[2], A[3], n_supports, V, G, out);
+  GWN_CUDA(launch_pdl(hop_mats_bt_prep_kernel, dim3((unsigned)cdiv(total, 256)), dim3(256), 0, st, A[0], A[1], A[2], A[3], n_supports, V, G, out));
   GWN_LAUNCHED();
   return 0;
 }

@@ -136,6 +136,8 @@ template <typename T, int CIN>
 __global__ void __launch_bounds__(256) start_fwd_small_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                               const float* __restrict__ b, T* __restrict__ u0, int N,
                                                               int V, int Tn, int L0) {
+  pdl_wait();      // programmatic launch: the launch latency overlaps the predecessor (common.cuh)
+  pdl_trigger();
   const int cg = threadIdx.x & 3;                           // channels [8 cg, 8 cg + 8)
   float wr[8][CIN], bias[8];
 #pragma unroll
@@ -175,6 +177,8 @@ template <typename T, int CIN>
 __global__ void __launch_bounds__(256) start_bwd_w_small_kernel(const float* __restrict__ x, const T* __restrict__ du,
                                                                 float* __restrict__ dw, float* __restrict__ db, int N,
                                                                 int V, int Tn, int L0) {
+  pdl_wait();      // programmatic launch: the launch latency overlaps the predecessor (common.cuh)
+  pdl_trigger();
   constexpr int NA = 8 * (CIN + 1);
   __shared__ float red[8][4][NA];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -390,8 +394,8 @@ extern "C" int gwn_start_fwd(const float* x, const float* w, const float* b, voi
   if ((Cin == 2 || Cin == 1 || Cin == 4) && (long long)N * L0 * V < (1ll << 31)) {   // narrow inputs: warp-per-position kernel (64-bit index math only, no smem)
     const unsigned nb = 148 * 8;
 #define GWN_SF(CI)                                                                                                   \
-  if (dtype == GWN_F32) start_fwd_small_kernel<float, CI><<<nb, 256, 0, st>>>(x, w, b, (float*)u0, N, V, T, L0);      \
-  else if (dtype == GWN_BF16) start_fwd_small_kernel<bf16, CI><<<nb, 256, 0, st>>>(x, w, b, (bf16*)u0, N, V, T, L0);  \
+  if (dtype == GWN_F32) GWN_CUDA(launch_pdl(start_fwd_small_kernel<float, CI>, dim3(nb), dim3(256), 0, st, x, w, b, (float*)u0, N, V, T, L0));      \
+  else if (dtype == GWN_BF16) GWN_CUDA(launch_pdl(start_fwd_small_kernel<bf16, CI>, dim3(nb), dim3(256), 0, st, x, w, b, (bf16*)u0, N, V, T, L0));  \
   else GWN_REQUIRE(false, "bad dtype %d", dtype);
     if (Cin == 1) { GWN_SF(1) } else if (Cin == 2) { GWN_SF(2) } else { GWN_SF(4) }
 #undef GWN_SF
@@ -418,8 +422,8 @@ extern "C" int gwn_start_bwd(const float* x, const float* w, const void* du0, in
   if ((Cin == 2 || Cin == 1 || Cin == 4) && P < (1ll << 31)) {
     const unsigned nb = 148 * 4;
 #define GWN_SB(CI)                                                                                                       \
-  if (dtype == GWN_F32) start_bwd_w_small_kernel<float, CI><<<nb, 256, 0, st>>>(x, (const float*)du0, dw, db, N, V, T, L0); \
-  else start_bwd_w_small_kernel<bf16, CI><<<nb, 256, 0, st>>>(x, (const bf16*)du0, dw, db, N, V, T, L0);
+  if (dtype == GWN_F32) GWN_CUDA(launch_pdl(start_bwd_w_small_kernel<float, CI>, dim3(nb), dim3(256), 0, st, x, (const float*)du0, dw, db, N, V, T, L0)); \
+  else GWN_CUDA(launch_pdl(start_bwd_w_small_kernel<bf16, CI>, dim3(nb), dim3(256), 0, st, x, (const bf16*)du0, dw, db, N, V, T, L0));
     if (Cin == 1) { GWN_SB(1) } else if (Cin == 2) { GWN_SB(2) } else { GWN_SB(4) }
 #undef GWN_SB
     GWN_LAUNCHED();

@@ -117,6 +117,8 @@ struct EpiAtomicF32 {      // dW[m][n] += acc (split-K partial)
 struct CvtJob { const float* src; bf16* dst; int R, C, transpose, ld, lo_off, hi2_off; };
 struct CvtJobs { CvtJob j[3]; int n; };
 __global__ void cvt_weights_kernel(CvtJobs jobs) {
+  pdl_wait();      // programmatic launch: the launch latency overlaps the predecessor (common.cuh)
+  pdl_trigger();
   for (int q = 0; q < jobs.n; ++q) {
     const CvtJob J = jobs.j[q];
     const int total = J.R * J.C;            // (weights: far below 2^31; 32-bit index math - a 64-bit division costs hundreds of cycles)
@@ -136,6 +138,8 @@ __global__ void cvt_weights_kernel(CvtJobs jobs) {
 __global__ void __launch_bounds__(256) dout_to_cl_kernel(const float* __restrict__ src, bf16* __restrict__ dst,
                                                          float* __restrict__ db, long long P, int O, int V, int Lf,
                                                          int Opad) {
+  pdl_wait();      // programmatic launch: the launch latency overlaps the predecessor (common.cuh)
+  pdl_trigger();
   __shared__ float red[8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int groups = Opad / 32;
@@ -229,7 +233,7 @@ extern "C" int gwn_head_fwd_tc(const gwn_head_cfg* c, const gwn_head_tc_fwd_args
   jobs.j[0] = CvtJob{a->w_skip, wsT, K0, S, 1, 2 * K0p, K0p, -1};
   jobs.j[1] = CvtJob{a->w_end1, w1T, S, E, 1, 3 * S, 2 * S, S};
   jobs.j[2] = CvtJob{a->w_end2, w2T, E, Opad, 1, E, -1, -1};
-  cvt_weights_kernel<<<592, 256, 0, st>>>(jobs);
+  GWN_CUDA(launch_pdl(cvt_weights_kernel, dim3(592), dim3(256), 0, st, jobs));
   GWN_LAUNCHED();
   TgParams p; CUtensorMap ma, mb;
   {   // x1 = zcat.(Ws_hi + Ws_lo): the A operand is read twice (k wraps at K0p)
@@ -273,7 +277,7 @@ extern "C" int gwn_head_bwd_tc(const gwn_head_cfg* c, const gwn_head_tc_bwd_args
   jobs.j[0] = CvtJob{a->w_skip, ws, K0, S, 0, S, -1, -1};
   jobs.j[1] = CvtJob{a->w_end1, w1, S, E, 0, E, -1, -1};
   jobs.j[2] = CvtJob{a->w_end2, w2, E, Opad, 0, Opad, -1, -1};
-  cvt_weights_kernel<<<592, 256, 0, st>>>(jobs);
+  GWN_CUDA(launch_pdl(cvt_weights_kernel, dim3(592), dim3(256), 0, st, jobs));
   GWN_LAUNCHED();
   if (!a->outputs_zeroed) {
   GWN_CUDA(cudaMemsetAsync(a->dw_skip, 0, sizeof(float) * (size_t)K0 * S, st));
@@ -294,7 +298,7 @@ extern "C" int gwn_head_bwd_tc(const gwn_head_cfg* c, const gwn_head_tc_bwd_args
     long long blocks = cdiv(items, 8 * 16);
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
-    dout_to_cl_kernel<<<(unsigned)blocks, 256, 0, st>>>(a->dout, d_o, a->db_end2, P, c->O, c->V, c->Lf, Opad);
+    GWN_CUDA(launch_pdl(dout_to_cl_kernel, dim3((unsigned)blocks), dim3(256), 0, st, a->dout, d_o, a->db_end2, P, c->O, c->V, c->Lf, Opad));
     GWN_LAUNCHED();
   }
   // end_conv_2

@@ -33,6 +33,8 @@ __host__ __device__ inline PackSeg pack_segments(const gwn_pack_cfg& c) {
 
 __global__ void __launch_bounds__(256) pack_params_kernel(const __grid_constant__ gwn_pack_cfg c,
                                                           const __grid_constant__ gwn_pack_ptrs p, float* __restrict__ out) {
+  pdl_wait();      // programmatic launch: the launch latency overlaps the predecessor (common.cuh)
+  pdl_trigger();
   const PackSeg s = pack_segments(c);
   const int k = c.taps, mi = c.mlp_in, S = c.S, E = c.E, Op = c.Opad, O = c.O;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < s.off[8]; i += (long long)gridDim.x * blockDim.x) {
@@ -82,6 +84,8 @@ __global__ void __launch_bounds__(256) pack_params_kernel(const __grid_constant_
 //   then dW1 [E][S] | dW2 [O][E] | db2 [O]
 __global__ void __launch_bounds__(256) unpack_grads_kernel(const __grid_constant__ gwn_pack_cfg c,
                                                            const __grid_constant__ gwn_unpack_ptrs g, float* __restrict__ out) {
+  pdl_wait();      // programmatic launch: the launch latency overlaps the predecessor (common.cuh)
+  pdl_trigger();
   const int k = c.taps, mi = c.mlp_in, S = c.S, E = c.E, Op = c.Opad, O = c.O;
   const long long per_layer = 2ll * (32 * 32 * k + 32) + 32ll * mi + 32ll * S + S;
   const long long total = per_layer * c.n_layers + (long long)E * S + (long long)O * E + O;
@@ -164,7 +168,7 @@ extern "C" int gwn_pack_params(const gwn_pack_cfg* cfg, const gwn_pack_ptrs* ptr
   if (int rc = gwn_check_device()) return rc;
   const long long total = pack_segments(*cfg).off[8];
   const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-  pack_params_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*cfg, *ptrs, out);
+  GWN_CUDA(launch_pdl(pack_params_kernel, dim3(blocks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), *cfg, *ptrs, out));
   GWN_LAUNCHED();
   return 0;
 }
@@ -181,7 +185,7 @@ extern "C" int gwn_unpack_grads(const gwn_pack_cfg* cfg, const gwn_unpack_ptrs* 
   if (int rc = gwn_check_device()) return rc;
   const long long total = gwn_unpack_total(cfg);
   const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-  unpack_grads_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*cfg, *grads, out);
+  GWN_CUDA(launch_pdl(unpack_grads_kernel, dim3(blocks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), *cfg, *grads, out));
   GWN_LAUNCHED();
   return 0;
 }

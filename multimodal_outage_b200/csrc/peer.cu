@@ -56,6 +56,8 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_flat_kernel(float* __restri
                                                                  float lr, float b1, float b2, float eps,
                                                                  unsigned long long* __restrict__ state, PeerTable pt,
                                                                  int rank, int world) {
+  pdl_wait();      // programmatic launch: the launch latency overlaps the predecessor (common.cuh)
+  pdl_trigger();
   __shared__ unsigned long long s_step;
   __shared__ int s_last;
   __shared__ float s_coef[2];
@@ -160,6 +162,8 @@ struct GatherTable {
   int n;
 };
 __global__ void __launch_bounds__(256) gather_flat_kernel(const __grid_constant__ GatherTable t, float* __restrict__ out) {
+  pdl_wait();      // programmatic launch: the launch latency overlaps the predecessor (common.cuh)
+  pdl_trigger();
   // element-parallel over the whole flat buffer (tensors range from 32 to 131072 elements: a per-tensor split would
   // leave most CTAs idle); the owning tensor of an element is found by bisection in the offset table (constant bank)
   const int total = t.off[t.n];
@@ -193,7 +197,7 @@ extern "C" int gwn_gather_flat(const void* const* srcs, const long long* counts,
   t.off[n] = (int)off;
   t.n = n;
   const long long blocks = cdiv(off, 256 * 4);
-  gather_flat_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks > 592 ? 592 : blocks), 256, 0, (cudaStream_t)stream>>>(t, out);
+  GWN_CUDA(launch_pdl(gather_flat_kernel, dim3((unsigned)(blocks < 1 ? 1 : blocks > 592 ? 592 : blocks)), dim3(256), 0, (cudaStream_t)stream, t, out));
   GWN_LAUNCHED();
   return 0;
 }
@@ -249,8 +253,8 @@ extern "C" int gwn_adam_flat(float* p, const float* g, float* m, float* v, long 
   const int grid = adam_grid(n);
   GWN_REQUIRE(cdiv(n, 4) <= (long long)grid * ADAM_THREADS * ADAM_MAXIT, "adam_flat: %lld parameters exceed one launch", n);
   PeerTable pt{};
-  adam_flat_kernel<false><<<grid, ADAM_THREADS, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, b1, b2, eps,
-                                                                          reinterpret_cast<unsigned long long*>(state), pt, 0, 1);
+  GWN_CUDA(launch_pdl(adam_flat_kernel<false>, dim3(grid), dim3(ADAM_THREADS), 0, (cudaStream_t)stream, p, g, m, v, n, lr, b1, b2, eps,
+                                                                          reinterpret_cast<unsigned long long*>(state), pt, 0, 1));
   GWN_LAUNCHED();
   return 0;
 }
@@ -267,9 +271,9 @@ extern "C" int gwn_allreduce_adam(float* p, float* m, float* v, long long n, flo
     pt.flags[r] = reinterpret_cast<unsigned long long*>(const_cast<void*>(blocks[r]));
     pt.grads[r] = reinterpret_cast<const float*>(reinterpret_cast<const char*>(blocks[r]) + PEER_HDR);
   }
-  adam_flat_kernel<true><<<grid, ADAM_THREADS, 0, (cudaStream_t)stream>>>(p, pt.grads[rank], m, v, n, lr, b1, b2, eps,
+  GWN_CUDA(launch_pdl(adam_flat_kernel<true>, dim3(grid), dim3(ADAM_THREADS), 0, (cudaStream_t)stream, p, pt.grads[rank], m, v, n, lr, b1, b2, eps,
                                                                          reinterpret_cast<unsigned long long*>(state), pt, rank,
-                                                                         world);
+                                                                         world));
   GWN_LAUNCHED();
   return 0;
 }

@@ -194,6 +194,8 @@ struct MatPrep {
   int n, V, Kp;
 };
 __global__ void hop_mats_prep_kernel(MatPrep mp, bf16* __restrict__ out) {
+  pdl_wait();      // programmatic launch: the launch latency overlaps the predecessor (common.cuh)
+  pdl_trigger();
   // matrix index m = 4*s + variant; variant: 0 = A^T, 1 = (A^2)^T (forward), 2 = A, 3 = A^2 (backward)
   const int per_mat = (mp.Kp / 8) * 128 * 8;
   const long long total = (long long)mp.n * 4 * per_mat;
@@ -224,6 +226,8 @@ __global__ void hop_mats_prep_kernel(MatPrep mp, bf16* __restrict__ out) {
 //   h^T[(s,c), w] = sum_{j,v} U_j[(s,v), c] * Mt_j[v, w],   k = j*V + v,   Mt_0 = I, Mt_{2s+1} = A_s, Mt_{2s+2} = A_s A_s
 // K-major no-swizzle canonical layout [KT/8][NP][8] bf16 (rows = output node w), zero padded.
 __global__ void hop_mats_t_prep_kernel(MatPrep mp, int KT, int NP, bf16* __restrict__ out) {
+  pdl_wait();      // programmatic launch: the launch latency overlaps the predecessor (common.cuh)
+  pdl_trigger();
   const int total = KT * NP;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int e = i & 7, w = (i >> 3) % NP, k = (i >> 3) / NP * 8 + e;
@@ -309,12 +313,12 @@ extern "C" int gwn_hop_mats_prep(const float* const* supports, int n_supports, i
   for (int i = 0; i < n_supports; ++i) mp.A[i] = supports[i];
   mp.n = n_supports; mp.V = V; mp.Kp = ((V + 15) / 16) * 16;
   long long total = (long long)n_supports * 4 * (mp.Kp / 8) * 1024;
-  hop_mats_prep_kernel<<<(unsigned)cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      mp, reinterpret_cast<bf16*>(out));
+  GWN_CUDA(launch_pdl(hop_mats_prep_kernel, dim3((unsigned)cdiv(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
+      mp, reinterpret_cast<bf16*>(out)));
   GWN_LAUNCHED();
   const int KT = hop_mats_t_kt(V, n_supports);
-  hop_mats_t_prep_kernel<<<(unsigned)cdiv((long long)KT * mp.Kp, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      mp, KT, mp.Kp, reinterpret_cast<bf16*>(out) + total);
+  GWN_CUDA(launch_pdl(hop_mats_t_prep_kernel, dim3((unsigned)cdiv((long long)KT * mp.Kp, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
+      mp, KT, mp.Kp, reinterpret_cast<bf16*>(out) + total));
   GWN_LAUNCHED();
   return launch_hop_mats_bt_prep(supports, n_supports, V, reinterpret_cast<bf16*>(out) + total + (long long)KT * mp.Kp,
                                  reinterpret_cast<cudaStream_t>(stream));

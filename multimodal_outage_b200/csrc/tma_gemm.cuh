@@ -131,6 +131,8 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   }
   const uint32_t acc_cols = p.bn <= 32 ? 32u : p.bn <= 64 ? 64u : p.bn <= 128 ? 128u : 256u;
   if (warp == 1) tmem_alloc(tmem_slot, 2 * acc_cols);
+  pdl_wait();      // programmatic launch: barrier / TMEM set-up above overlapped the predecessor's tail (common.cuh)
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -283,7 +285,7 @@ int launch_tma_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, TgParams& 
   const int sms = tg_sm_count();
   const long long tiles = (long long)p.m_tiles * p.n_tiles * p.splits;
   const int grid = (int)(tiles < sms ? tiles : sms);
-  tma_gemm_kernel<Epi><<<grid, TG_THREADS, smem, st>>>(mapA, mapB, p, epi);
+  GWN_CUDA(launch_pdl(tma_gemm_kernel<Epi>, dim3(grid), dim3(TG_THREADS), smem, st, mapA, mapB, p, epi));
   GWN_LAUNCHED();
   return 0;
 }
