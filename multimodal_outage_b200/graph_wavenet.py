@@ -167,6 +167,8 @@ class _PackHead(torch.autograd.Function):
 
 
 class gwnet(nn.Module):
+    _instances = 0          # numbers the modules of a process (fused dropout stream key)
+
     def __init__(self, device, num_nodes=67, dropout=0.3, supports=_DEFAULT, gcn_bool=True, addaptadj=True,
                  aptinit=None, in_dim=256, out_dim=255, horizon=1, residual_channels=32, dilation_channels=32,
                  skip_channels=256, end_channels=512, kernel_size=1, blocks=4, layers=2):
@@ -242,6 +244,8 @@ class gwnet(nn.Module):
         self.end_conv_2 = nn.Conv2d(end_channels, out_dim, (1, 1), bias=True)
         self.receptive_field = receptive_field
         self._rng_state: Optional[torch.Tensor] = None
+        self._instance = gwnet._instances
+        gwnet._instances += 1
         self._calls = 0
         self.to(device)
 
@@ -334,8 +338,13 @@ class gwnet(nn.Module):
                          .permute(0, 3, 2, 1).contiguous().to(dt) for i in range(nl)]
             else:
                 if self._rng_state is None or self._rng_state.device != x.device:
-                    self._rng_state = torch.tensor([torch.initial_seed() & (2 ** 62 - 1), 0], dtype=torch.int64,
-                                                   device=x.device)
+                    # key of the fused dropout stream: torch's seed mixed with the data-parallel rank (every rank draws
+                    # its own masks for its own shard) and a per-instance number (two gwnet modules in one process do not
+                    # share a stream).  Not a registered buffer: the reference's state_dict has no such entry.
+                    rank = torch.distributed.get_rank() if (torch.distributed.is_available() and
+                                                            torch.distributed.is_initialized()) else 0
+                    seed = (torch.initial_seed() + 0x9E3779B97F4A7C15 * (rank + 1) + 0xD1B54A32D192ED03 * self._instance)
+                    self._rng_state = torch.tensor([seed & (2 ** 62 - 1), 0], dtype=torch.int64, device=x.device)
                 rng = self._rng_state.clone()                # this step's {seed, offset}
                 self._rng_state[1] += nl                     # graph-safe: advances on every replay
 
