@@ -941,3 +941,22 @@ def test_fused_dropout_statistics():
         a, b = k[:-lag] - (1 - p_real), k[lag:] - (1 - p_real)
         corr = (a * b).mean().item() / (p_real * (1 - p_real))
         assert abs(corr) < 5 / (n - lag) ** 0.5, (lag, corr)
+
+
+def test_bf16_config2_full_batch_training_parity():
+    """BASELINE config 2 exactly as benchmarked - 67-county graph, fwd/bwd/adaptive supports, k = 2, 4x2 layers, batch 512,
+    training mode with dropout masks p = 0.3 (explicit, so the fp64 oracle applies the same masks) - through the same
+    fixed bars as every whole-model bf16 case: output / loss 2e-2, every gradient 2e-2 with the head's ReLU decisions
+    pinned, 0.12 unpinned."""
+    cfg = GWNetConfig(num_nodes=67, in_dim=2, out_dim=12, kernel_size=2, dropout=0.3)
+    sup = double_transition(np.load(os.path.join(GOLDEN_DIR, 'adj_mx_fl.npy')).astype(np.float32))
+    _oracle_case(cfg, sup, n=512, t_in=12, seed=12, dtype=torch.bfloat16, tol=BF16_TOL, masks=True)
+
+
+def test_bf16_layer_op_at_3100_nodes():
+    """One layer of the 3,100-node configurations (BASELINE configs 3 and 5) at the REAL graph size: TMA-tiled hop GEMMs,
+    the Horner-form backward and the support gradient `gwn_dadj_big`, every output and gradient within 2e-2 of the fp64
+    oracle (one sample, three time steps - the oracle's 3100 x 3100 products stay in the seconds)."""
+    errs = _layer_op_case(torch.bfloat16, BF16_TOL, V=3100, N=1, Lin=3, dil=1, taps=2, n_sup=3, with_bn=True, mask=True,
+                          seed=51, tensor_cores=True)
+    print('bf16 layer op at V=3100:', {k: f'{v:.1e}' for k, v in errs.items()})
