@@ -96,6 +96,17 @@ typedef struct {
   uint64_t seed, offset;        /* Philox key/offset for the fused dropout mask */
 } gwn_layer_cfg;
 
+/* Optional SPARSE form of a fixed support.  County adjacency graphs have a handful of neighbours per node and asym_adj
+ * (utils.py:152-158) keeps that pattern, so at V = 3100 a dense V x V hop multiplies 99.7 % exact zeros.  With width > 0 the
+ * bf16 big-graph path (V > 80) applies the support with a gather kernel over ELL rows instead of a dense tensor-core GEMM:
+ * the same sums with the zero terms skipped (values in fp32).  The adaptive adjacency (a dense softmax) stays a GEMM. */
+typedef struct {
+  const int* idx[2];            /* [V][width] int32, -1 pads.  which = 0: neighbours v of column w (y[w] = sum_v A[v,w] x[v], the
+                                   forward hop); which = 1: neighbours v of row w (y[w] = sum_v A[w,v] x[v], its transpose) */
+  const float* val[2];          /* [V][width] fp32 */
+  int width;                    /* 0 = dense */
+} gwn_ell;
+
 typedef struct {
   const void* u_prev;           /* [N,Lin,V,32] */
   const float* scale;           /* [32] or NULL */
@@ -126,6 +137,7 @@ typedef struct {
   float* bn_mean; float* bn_rstd;
   double bn_count;
   float bn_momentum, bn_eps;
+  const gwn_ell* ell;           /* optional HOST array [GWN_MAX_SUPPORTS] (see gwn_ell), NULL = all supports dense */
 } gwn_layer_fwd_args;
 
 int gwn_layer_fwd(const gwn_layer_cfg* cfg, const gwn_layer_fwd_args* args, void* stream);
@@ -163,6 +175,7 @@ typedef struct {
                                    support through its SECOND-order hop A*A in factored form: with Q = d_supports_sq[i]
                                    the full gradient is d_supports[i] + A^T Q + Q A^T (applied once per step by
                                    gwn_adp_pair_bwd, in fp32).  Paths that do not use it leave Q = 0. */
+  const gwn_ell* ell;           /* optional HOST array [GWN_MAX_SUPPORTS] (see gwn_ell), NULL = all supports dense */
 } gwn_layer_bwd_args;
 
 int gwn_layer_bwd(const gwn_layer_cfg* cfg, const gwn_layer_bwd_args* args, void* stream);
@@ -198,6 +211,11 @@ int gwn_gcn_bwd(const void* du, const void* a, const void* b, const void* dz_las
  * 256 / (256 - round(256 p))).  Used by the statistical tests of the stream; the layer kernels apply it in their epilogues. */
 int gwn_dropout_apply(const void* x, void* out, long long rows, float p, unsigned long long seed,
                       unsigned long long offset, void* stream);
+
+/* One sparse hop on its own (tests / microbenchmarks): y[s,w,:] = sum_k val[w][k] x[s, idx[w][k], :] (+ add), bf16 slabs of
+ * V rows x 32 channels. */
+int gwn_hop_ell(const int* idx, const float* val, int width, const void* x, void* y, const void* add, long long slabs,
+                int V, void* stream);
 
 /* ---- BatchNorm2d(32) folded to an affine  graph_wavenet.py:167,250 ----
  * training: mean/var from stats (count = N*L*V), scale = gamma*rstd, shift = beta - mean*scale,

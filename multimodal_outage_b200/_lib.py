@@ -26,13 +26,17 @@ class LayerCfg(C.Structure):
                [('dropout_p', C.c_float), ('seed', C.c_uint64), ('offset', C.c_uint64)]
 
 
+class Ell(C.Structure):
+    _fields_ = [('idx', vp * 2), ('val', vp * 2), ('width', C.c_int)]
+
+
 class LayerFwdArgs(C.Structure):
     _fields_ = [('u_prev', vp), ('scale', vp), ('shift', vp), ('w_fg', vp), ('b_fg', vp), ('w_mlp', vp),
                 ('b_mlp', vp), ('supports', vp * MAX_SUPPORTS), ('drop_mask', vp), ('rng', vp), ('hop_mats', vp), ('ws_w', vp), ('a', vp),
                 ('b', vp), ('z_last', vp), ('u', vp), ('stats', vp), ('ws_cat', vp),
                 ('bn_stats', vp), ('bn_gamma', vp), ('bn_beta', vp), ('bn_running_mean', vp), ('bn_running_var', vp),
                 ('bn_mean', vp), ('bn_rstd', vp), ('bn_count', C.c_double), ('bn_momentum', C.c_float),
-                ('bn_eps', C.c_float)]
+                ('bn_eps', C.c_float), ('ell', C.POINTER(Ell))]
 
 
 class LayerBwdArgs(C.Structure):
@@ -41,7 +45,7 @@ class LayerBwdArgs(C.Structure):
                 ('drop_mask', vp), ('rng', vp), ('hop_mats', vp), ('ws_w', vp), ('a', vp), ('b', vp), ('du', vp), ('dz_last', vp), ('dx_prev', vp),
                 ('dx_stats', vp), ('dw_fg', vp), ('db_fg', vp), ('dw_mlp', vp), ('db_mlp', vp),
                 ('d_supports', vp * MAX_SUPPORTS), ('ws_cat', vp), ('ws_dcat', vp), ('ws_dfg', vp), ('outputs_zeroed', C.c_int),
-                ('dx_prev_bf16', C.c_int), ('d_supports_sq', vp * MAX_SUPPORTS)]
+                ('dx_prev_bf16', C.c_int), ('d_supports_sq', vp * MAX_SUPPORTS), ('ell', C.POINTER(Ell))]
 
 
 class HeadCfg(C.Structure):
@@ -124,6 +128,7 @@ SIGNATURES = {
     'gwn_support_images_prep': (_i, [vp, _i, _i, vp, vp]),
     'gwn_hop_big': (_i, [vp, _i, _i, _i, vp, vp, vp, _ll, _i, vp]),
     'gwn_dadj_big': (_i, [vp, vp, vp, _ll, _i, vp]),
+    'gwn_hop_ell': (_i, [vp, vp, _i, vp, vp, vp, _ll, _i, vp]),
     'gwn_gemm_test': (_i, [vp, vp, vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, vp]),
     'gwn_pack_offsets': (_ll, [C.POINTER(PackCfg), C.POINTER(_ll)]),
     'gwn_pack_params': (_i, [C.POINTER(PackCfg), C.POINTER(PackPtrs), vp, vp]),

@@ -643,6 +643,15 @@ static const bf16* big_image(const gwn_layer_cfg* c, const void* hop_mats, int s
   return reinterpret_cast<const bf16*>(hop_mats) + ((long long)s * 2 + which) * c->V * Vp;
 }
 
+// one hop of support s at V > 80: the sparse gather when the caller supplied ELL rows for it, else the dense tensor-core GEMM
+static int hop_any(const gwn_layer_cfg* c, const void* hop_mats, const gwn_ell* ell, int s, int which, const bf16* X, bf16* Y,
+                   const bf16* add, long long slabs, cudaStream_t st) {
+  if (ell && ell[s].width > 0 && ell[s].idx[which] && ell[s].val[which])
+    return launch_hop_ell(ell[s].idx[which], ell[s].val[which], ell[s].width, X, Y, add, slabs, c->V, st);
+  const int Vp = ((c->V + 7) / 8) * 8;
+  return launch_hop_big(big_image(c, hop_mats, s, which), Vp, X, Y, add, slabs, c->V, st);
+}
+
 static bool fused_gate_wgrad_enabled() {   // GWN_FUSED_WGRAD=0 keeps the separate weight-gradient launch (A/B measurements)
   static int v = -1;
   if (v < 0) { const char* e = getenv("GWN_FUSED_WGRAD"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -707,20 +716,17 @@ static int hops_forward_tc(const gwn_layer_cfg* c, bf16* cat, const void* hop_ma
 
 template <typename T>
 static int hops_forward(const gwn_layer_cfg* c, T* cat, const float* const* supports,
-                        const void* hop_mats, cudaStream_t st) {
+                        const void* hop_mats, const gwn_ell* ell, cudaStream_t st) {
   const long long slabs = (long long)c->N * c->Lout;
   const long long SS = slabs * c->V * 32;   // slot stride
   if constexpr (std::is_same<T, bf16>::value) {
     const int mode = tc_mode<T>(c, hop_mats);
     if (mode == 1 && c->n_supports > 0) return hops_forward_tc(c, cat, hop_mats, st);
     if (mode == 2) {
-      const int Vp = ((c->V + 7) / 8) * 8;
       for (int s = 0; s < c->n_supports; ++s)
         for (int k = 1; k <= c->order; ++k) {
           const int slot = 1 + s * c->order + (k - 1), src = (k == 1) ? 0 : slot - 1;
-          if (int rc = launch_hop_big(big_image(c, hop_mats, s, 0), Vp, cat + src * SS, cat + slot * SS, nullptr, slabs,
-                                      c->V, st))
-            return rc;
+          if (int rc = hop_any(c, hop_mats, ell, s, 0, cat + src * SS, cat + slot * SS, nullptr, slabs, st)) return rc;
         }
       return 0;
     }
@@ -823,7 +829,7 @@ static int layer_fwd_t(const gwn_layer_cfg* c, const gwn_layer_fwd_args* g, cuda
     }
   }
   // diffusion hops into the concat slots, then mlp + dropout + residual + stats
-  if (int rc = hops_forward<T>(c, cat, g->supports, g->hop_mats, st)) return rc;
+  if (int rc = hops_forward<T>(c, cat, g->supports, g->hop_mats, g->ell, st)) return rc;
   GemmA M{};
   M.n_chunks = nslots; M.rows_per_n_out = RO; M.P = P;
   for (int q = 0; q < nslots; ++q) {
@@ -944,9 +950,7 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
       for (int s = 0; s < c->n_supports; ++s)
         for (int k = 1; k <= 2; ++k) {
           const int slot = 2 * s + k, src = (k == 1) ? 0 : slot - 1;
-          if (int rc = launch_hop_big(big_image(c, g->hop_mats, s, 1), Vp, dcat + src * SS, dcat + slot * SS, nullptr, slabs,
-                                      c->V, st))
-            return rc;
+          if (int rc = hop_any(c, g->hop_mats, g->ell, s, 1, dcat + src * SS, dcat + slot * SS, nullptr, slabs, st)) return rc;
         }
       // dW_j = z^T dU_j (j = 0 also gives db = sum dh through the ones row)
       if (!g->outputs_zeroed) GWN_CUDA(cudaMemsetAsync(g->dw_mlp, 0, sizeof(float) * 32 * mlp_in, st));
@@ -998,7 +1002,7 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
     // recompute the concat (z and its hops)
     zfill_kernel<T><<<eb, 256, 0, st>>>(a, b, cat, 32, P);
     GWN_LAUNCHED();
-    if (int rc = hops_forward<T>(c, cat, g->supports, g->hop_mats, st)) return rc;
+    if (int rc = hops_forward<T>(c, cat, g->supports, g->hop_mats, g->ell, st)) return rc;
     // dh = du * mask
     const T* dh = du;
     const bool drop = c->training && (g->drop_mask != nullptr || c->dropout_p > 0.f);
@@ -1068,8 +1072,8 @@ static int layer_bwd_t(const gwn_layer_cfg* c, const gwn_layer_bwd_args* g, cuda
             if (g->support_needs_grad[s] && g->d_supports[s])
               if (int rc = launch_dadj_big(cat + src * P * 32, dcat + slot * P * 32, g->d_supports[s], slabs, c->V, st))
                 return rc;
-            if (int rc = launch_hop_big(big_image(c, g->hop_mats, s, 1), Vp, dcat + slot * P * 32, dcat + src * P * 32,
-                                        dcat + src * P * 32, slabs, c->V, st))
+            if (int rc = hop_any(c, g->hop_mats, g->ell, s, 1, dcat + slot * P * 32, dcat + src * P * 32, dcat + src * P * 32,
+                                 slabs, st))
               return rc;
           }
         tc_done = true;

@@ -243,6 +243,7 @@ class gwnet(nn.Module):
         self.end_conv_1 = nn.Conv2d(skip_channels, end_channels, (1, 1), bias=True)
         self.end_conv_2 = nn.Conv2d(end_channels, out_dim, (1, 1), bias=True)
         self.receptive_field = receptive_field
+        self._sparse_checked = False
         self._rng_state: Optional[torch.Tensor] = None
         self._instance = gwnet._instances
         gwnet._instances += 1
@@ -254,6 +255,7 @@ class gwnet(nn.Module):
     def _apply(self, fn, *args, **kwargs):
         super()._apply(fn, *args, **kwargs)
         self.supports = [fn(s).contiguous() for s in self.supports]
+        self._sparse_checked = False
         if self._rng_state is not None:
             self._rng_state = fn(self._rng_state)
         return self
@@ -320,6 +322,12 @@ class gwnet(nn.Module):
         supports: List[torch.Tensor] = []
         if self.gcn_bool:
             supports = list(self.supports)
+            if not self._sparse_checked and V > 80:
+                # big graphs: fixed supports with few neighbours per node are applied as sparse gathers (ops.register_sparse_support)
+                for s_ in supports:
+                    if s_.is_cuda:
+                        ops.register_sparse_support(s_)
+                self._sparse_checked = True
             if self.addaptadj:                               # graph_wavenet.py:201-203
                 # bf16 path with the supports resident on chip: the adjacency travels as a pair [2,V,V] so the fused
                 # backward can return its gradient in factored form (ops.AdaptiveAdjacency)

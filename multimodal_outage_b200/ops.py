@@ -290,6 +290,54 @@ def _(dx, u, dx_stats, count, gamma, mean, rstd, training):
     return torch.empty_like(u), torch.empty_like(gamma), torch.empty_like(gamma)
 
 
+# =========================================================================== sparse fixed supports (V > 80)
+# County adjacency graphs have a handful of neighbours per node, and asym_adj keeps that pattern: at V = 3100 a dense hop
+# multiplies 99.7 % exact zeros.  A support registered here is applied by the big-graph bf16 path with a gather kernel over
+# ELL rows (include/gwn.h: gwn_ell) - same sums, zero terms skipped.  Keyed by the support tensor's storage; an entry is
+# used only while that very tensor is alive and unmodified.
+_ELL_REGISTRY: dict = {}
+ELL_MAX_WIDTH = 32
+
+
+def register_sparse_support(A: Tensor, max_width: int = ELL_MAX_WIDTH) -> bool:
+    """Builds ELL rows (both hop directions) of a fixed [V,V] fp32 CUDA support and registers them.  Returns False (and
+    registers nothing) when some row or column has more than `max_width` non-zeros - the support then stays dense."""
+    import weakref
+    _req(A, torch.float32, 'support')
+    V = A.shape[0]
+    nz = A != 0
+    width = int(max(nz.sum(dim=0).max().item(), nz.sum(dim=1).max().item(), 1))
+    if width > max_width:
+        _ELL_REGISTRY.pop(A.data_ptr(), None)
+        return False
+    def rows(M):                # M[w, v] != 0 -> neighbours v of output row w, padded with -1
+        order = torch.argsort((M == 0).to(torch.int8), dim=1, stable=True)[:, :width]       # non-zeros first, ascending v
+        vals = torch.gather(M, 1, order)
+        idx = torch.where(vals != 0, order, torch.full_like(order, -1)).to(torch.int32).contiguous()
+        return idx, vals.contiguous()
+    idx0, val0 = rows(A.t().contiguous())      # which = 0: y[w] = sum_v A[v, w] x[v]
+    idx1, val1 = rows(A)                       # which = 1: y[w] = sum_v A[w, v] x[v]
+    _ELL_REGISTRY[A.data_ptr()] = dict(ref=weakref.ref(A), version=A._version, idx=(idx0, idx1), val=(val0, val1), width=width)
+    return True
+
+
+def _ell_array(supports: Sequence[Tensor]):
+    """ctypes `gwn_ell[MAX_SUPPORTS]` for the registered supports among `supports` (None when there is none)."""
+    arr, keep = None, []
+    for i, s in enumerate(supports):
+        e = _ELL_REGISTRY.get(s.data_ptr())
+        r = e['ref']() if e is not None else None
+        if r is None or r.data_ptr() != s.data_ptr() or r.shape != s.shape or e['version'] != s._version:
+            continue
+        if arr is None:
+            arr = (_lib.Ell * _lib.MAX_SUPPORTS)()
+        arr[i].idx[0], arr[i].idx[1] = e['idx'][0].data_ptr(), e['idx'][1].data_ptr()
+        arr[i].val[0], arr[i].val[1] = e['val'][0].data_ptr(), e['val'][1].data_ptr()
+        arr[i].width = e['width']
+        keep.append(e)
+    return arr, keep
+
+
 # =========================================================================== one layer (:206-250)
 def _layer_cfg(N, V, Lin, Lout, Lf, taps, dilation, n_sup, order, dtype, training, has_gconv, dropout_p, seed,
                offset) -> LayerCfg:
@@ -337,6 +385,9 @@ def _layer_fwd_impl(u_prev, scale, shift, w_fg, b_fg, w_mlp, b_mlp, supports, dr
                         a=_p(a) if training else None,
                         b=_p(b) if training else None, z_last=_p(z_last), u=_p(u) if has_gconv else None,
                         stats=_p(stats), ws_cat=_p(ws_cat))
+    ell, _ell_keep = _ell_array(supports) if (has_gconv and hop_mats is not None and dt == torch.bfloat16) else (None, None)
+    if ell is not None:
+        args.ell = ell
     if bn is not None:
         bn_stats, count, gamma, beta, rmean, rvar, momentum, eps, mean, rstd = bn
         for t, nm in ((gamma, 'bn.weight'), (beta, 'bn.bias'), (rmean, 'running_mean'), (rvar, 'running_var')):
@@ -451,6 +502,9 @@ def _layer_bwd_impl(u_prev, scale, shift, w_fg, w_mlp, supports, needs_grad, dro
                         dw_fg=_p(dw_fg), db_fg=_p(db_fg), dw_mlp=_p(dw_mlp), db_mlp=_p(db_mlp),
                         ws_cat=_p(ws_cat) if has_du else None, ws_dcat=_p(ws_dcat) if has_du else None,
                         ws_dfg=_p(ws_dfg), outputs_zeroed=1, dx_prev_bf16=int(dx_bf16))
+    ell, _ell_keep = _ell_array(supports) if (has_du and hop_mats is not None and dt == torch.bfloat16) else (None, None)
+    if ell is not None:
+        args.ell = ell
     for i, g in enumerate(needs_grad):
         args.support_needs_grad[i] = int(bool(g) and has_du)
         args.d_supports[i] = d_sup[i].data_ptr() if (g and has_du) else None

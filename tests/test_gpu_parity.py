@@ -326,7 +326,7 @@ def test_non_b200_or_cpu_input_raises():
 
 
 def _layer_op_case(dtype, tol, V=67, N=6, Lin=9, dil=2, taps=2, n_sup=3, with_bn=True, mask=False, seed=0,
-                   tensor_cores=False, adp_grad=True):
+                   tensor_cores=False, adp_grad=True, sparse=False):
     """ops.WaveNetLayer (bn-fold + gate + hops + mlp + dropout + residual, fwd AND bwd) against the
     oracle's single-layer restatement on IDENTICAL inputs (no ReLU anywhere -> bf16 error stays at
     rounding level, so the 2e-2 / 1e-4 bars apply to every gradient)."""
@@ -343,6 +343,10 @@ def _layer_op_case(dtype, tol, V=67, N=6, Lin=9, dil=2, taps=2, n_sup=3, with_bn
     mlp_in = 32 * (1 + 2 * n_sup)
     wm, bm = rn(32, mlp_in, 1, 1) / mlp_in ** 0.5, 0.1 * rn(32)
     sups = [torch.softmax(rn(V, V), dim=1) for _ in range(n_sup)]
+    if sparse:      # fixed supports as the configurations have them: transition matrices of a kNN graph (a few non-zeros per row)
+        tr = double_transition(synthetic_knn_graph(V))
+        for i in range(min(n_sup - 1, 2)):
+            sups[i] = torch.tensor(np.asarray(tr[i]), dtype=torch.float64)
     du = rn(N, 32, V, Lout).to(dtype).double()
     dzl = rn(N, 32, V, Lf).to(dtype).double()
     keep = 0.7
@@ -373,6 +377,9 @@ def _layer_op_case(dtype, tol, V=67, N=6, Lin=9, dil=2, taps=2, n_sup=3, with_bn
     wfg_k, bfg_k = f32(w_fg).contiguous().requires_grad_(True), f32(b_fg).requires_grad_(True)
     wm_k, bm_k = f32(wm[:, :, 0, 0].t()).contiguous().requires_grad_(True), f32(bm).requires_grad_(True)
     sup_k = [f32(a) for a in sups]
+    if sparse:
+        assert all(ops.register_sparse_support(a) for a in sup_k[:min(n_sup - 1, 2)])
+        assert not ops.register_sparse_support(sup_k[-1])          # the dense (softmax) support stays a GEMM
     sup_k[-1].requires_grad_(adp_grad)
     meta = dict(training=True, momentum=0.1, eps=1e-5, Lf=Lf, taps=taps, dilation=dil, order=2, has_gconv=True,
                 dropout_p=0.3 if mask else 0.0, seed=0, offset=0)
@@ -960,3 +967,46 @@ def test_bf16_layer_op_at_3100_nodes():
     errs = _layer_op_case(torch.bfloat16, BF16_TOL, V=3100, N=1, Lin=3, dil=1, taps=2, n_sup=3, with_bn=True, mask=True,
                           seed=51, tensor_cores=True)
     print('bf16 layer op at V=3100:', {k: f'{v:.1e}' for k, v in errs.items()})
+
+
+def test_sparse_support_hop_matches_the_dense_hop():
+    """`gwn_hop_ell` (ELL gather) against an fp64 einsum and against the dense tensor-core hop, both directions, with and
+    without the add-in (in place), on the transition matrices of a 3,100-node kNN graph (<= 20 non-zeros per row)."""
+    from multimodal_outage_b200 import ops, _lib
+    lib = _lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    torch.manual_seed(3)
+    V, slabs = 3100, 7
+    A = torch.tensor(np.asarray(double_transition(synthetic_knn_graph(V))[0]), dtype=torch.float32, device='cuda').contiguous()
+    assert ops.register_sparse_support(A)
+    e = ops._ELL_REGISTRY[A.data_ptr()]
+    assert e['width'] <= ops.ELL_MAX_WIDTH and int((A != 0).sum(dim=1).max()) <= e['width']
+    x = torch.randn(slabs, V, 32, device='cuda').to(torch.bfloat16)
+    add = torch.randn(slabs, V, 32, device='cuda').to(torch.bfloat16)
+    img = ops.support_images([A])
+    for which in range(2):
+        ref = torch.einsum('vw,svc->swc' if which == 0 else 'wv,svc->swc', A.double(), x.double())
+        y = torch.empty_like(x)
+        _lib.check(lib.gwn_hop_ell(e['idx'][which].data_ptr(), e['val'][which].data_ptr(), e['width'], x.data_ptr(), y.data_ptr(),
+                                   None, slabs, V, st), 'hop_ell')
+        assert rel(y, ref) < 4e-3, (which, rel(y, ref))                      # bf16 output rounding only
+        yd = torch.empty_like(x)
+        _lib.check(lib.gwn_hop_big(img.data_ptr(), 1, 0, which, x.data_ptr(), yd.data_ptr(), None, slabs, V, st), 'hop')
+        assert rel(y, yd) < 8e-3
+        y2 = add.clone()                                                      # y += A x, in place
+        _lib.check(lib.gwn_hop_ell(e['idx'][which].data_ptr(), e['val'][which].data_ptr(), e['width'], x.data_ptr(), y2.data_ptr(),
+                                   y2.data_ptr(), slabs, V, st), 'hop_ell')
+        assert rel(y2, ref + add.double()) < 4e-3
+    # a modified support is no longer served from the registry
+    A.mul_(1.0)
+    assert ops._ell_array([A])[0] is None
+
+
+@pytest.mark.parametrize('V,N', [(150, 3), (333, 2)])
+def test_bf16_layer_op_big_graph_sparse_fixed_supports(V, N):
+    """The big-graph layer op with its two fixed supports applied as sparse gathers (forward hops, Horner backward,
+    recompute backward share `hop_any`) and the adaptive one as a dense GEMM: everything within 2e-2 of the fp64 oracle."""
+    for with_bn, mask in ((True, False), (False, True)):
+        errs = _layer_op_case(torch.bfloat16, BF16_TOL, V=V, N=N, Lin=5, dil=1, taps=2, n_sup=3, with_bn=with_bn, mask=mask,
+                              seed=61, tensor_cores=True, sparse=True)
+        print(f'bf16 big-graph layer op, sparse fixed supports, V={V}:', {k: f'{v:.1e}' for k, v in errs.items()})

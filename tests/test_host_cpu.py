@@ -35,7 +35,7 @@ def test_struct_layouts_match_the_c_header(tmp_path):
     """sizeof/offsetof of every ABI struct, as gcc sees include/gwn.h, equals the ctypes mirror."""
     import subprocess
     from multimodal_outage_b200 import _lib
-    pairs = {'gwn_layer_cfg': _lib.LayerCfg, 'gwn_layer_fwd_args': _lib.LayerFwdArgs,
+    pairs = {'gwn_layer_cfg': _lib.LayerCfg, 'gwn_ell': _lib.Ell, 'gwn_layer_fwd_args': _lib.LayerFwdArgs,
              'gwn_layer_bwd_args': _lib.LayerBwdArgs, 'gwn_head_cfg': _lib.HeadCfg,
              'gwn_head_fwd_args': _lib.HeadFwdArgs, 'gwn_head_bwd_args': _lib.HeadBwdArgs,
              'gwn_head_tc_fwd_args': _lib.HeadTcFwdArgs, 'gwn_head_tc_bwd_args': _lib.HeadTcBwdArgs,
