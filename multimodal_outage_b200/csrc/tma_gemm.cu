@@ -239,10 +239,87 @@ __global__ void __launch_bounds__(256) hop_ell_kernel(const int* __restrict__ id
   *(reinterpret_cast<uint4*>(Y + (base + w) * 32) + pc) = o;
 }
 
+// The same hop with the slab staged in shared memory (V x 64 B <= 220 KB: every 3,100-node slab is 198 KB): one CTA per
+// slab reads x[s] once, coalesced, and the ~8 gathers per output row hit shared memory instead of L2 (the global version
+// moves 8x the slab through the L2 -> SM path and is bound by it).  Persistent over slabs.
+__global__ void __launch_bounds__(1024) hop_ell_smem_kernel(const int* __restrict__ idx, const float* __restrict__ val, int W,
+                                                            const bf16* __restrict__ X, bf16* Y, const bf16* add, int V,
+                                                            int slabs) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ uint4 xs[];                    // [V][4] pieces of 8 channels
+  const int tid = threadIdx.x, pc = tid & 3;
+  for (int s = blockIdx.x; s < slabs; s += gridDim.x) {
+    const long long base = (long long)s * V;
+    const uint4* src = reinterpret_cast<const uint4*>(X + base * 32);
+    for (int i = tid; i < V * 4; i += 1024) xs[i] = __ldg(src + i);
+    __syncthreads();
+    for (int w = tid >> 2; w < V; w += 256) {
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      if (add) {
+        const uint4 q = *(reinterpret_cast<const uint4*>(add + (base + w) * 32) + pc);
+        const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { acc[2 * i] = __uint_as_float(u[i] << 16); acc[2 * i + 1] = __uint_as_float(u[i] & 0xFFFF0000u); }
+      }
+      const int* ir = idx + (long long)w * W;
+      const float* vr = val + (long long)w * W;
+      for (int k0 = 0; k0 < W; k0 += 4) {
+        int v[4]; float a[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool in = k0 + j < W;
+          v[j] = in ? __ldg(ir + k0 + j) : -1;
+          a[j] = in ? __ldg(vr + k0 + j) : 0.f;
+        }
+        if (v[0] < 0) break;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 q = v[j] >= 0 ? xs[v[j] * 4 + pc] : make_uint4(0u, 0u, 0u, 0u);
+          const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            acc[2 * i] = fmaf(a[j], __uint_as_float(u[i] << 16), acc[2 * i]);
+            acc[2 * i + 1] = fmaf(a[j], __uint_as_float(u[i] & 0xFFFF0000u), acc[2 * i + 1]);
+          }
+        }
+      }
+      uint4 o;
+      uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1]);
+        ow[i] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      *(reinterpret_cast<uint4*>(Y + (base + w) * 32) + pc) = o;
+    }
+    __syncthreads();                               // the slab buffer is reused by the next slab of this CTA
+  }
+}
+
 int launch_hop_ell(const int* idx, const float* val, int W, const bf16* X, bf16* Y, const bf16* add, long long slabs, int V,
                    cudaStream_t st) {
   if (slabs <= 0) return 0;
   GWN_REQUIRE(idx && val && W >= 1 && X && Y && X != Y, "hop_ell: bad argument");
+  const size_t slab_bytes = (size_t)V * 64;
+  if (slab_bytes <= 220 * 1024 && slabs < (1ll << 31)) {       // the slab fits in shared memory
+    static bool attr = false;
+    static int sms = 148;
+    if (!attr) {
+      GWN_CUDA(cudaFuncSetAttribute(hop_ell_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      int dev = 0;
+      GWN_CUDA(cudaGetDevice(&dev));
+      GWN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      attr = true;
+    }
+    const int per_sm = slab_bytes <= 100 * 1024 ? 2 : 1;
+    const long long grid = slabs < (long long)sms * per_sm ? slabs : (long long)sms * per_sm;
+    GWN_CUDA(launch_pdl(hop_ell_smem_kernel, dim3((unsigned)grid), dim3(1024), slab_bytes, st, idx, val, W, X, Y, add, V, (int)slabs));
+    GWN_LAUNCHED();
+    return 0;
+  }
   GWN_REQUIRE(slabs <= 65535, "hop_ell: too many slabs (%lld)", slabs);
   GWN_CUDA(launch_pdl(hop_ell_kernel, dim3((unsigned)cdiv(V, 64), (unsigned)slabs), dim3(256), 0, st, idx, val, W, X, Y, add, V));
   GWN_LAUNCHED();
