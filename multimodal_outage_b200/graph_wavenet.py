@@ -192,6 +192,7 @@ class gwnet(nn.Module):
         self.compute_dtype: Optional[torch.dtype] = None    # None: follow autocast, else fp32
         self.use_tensor_cores = True                        # bf16 hops on tcgen05 when the supports fit on chip
         self.dropout_mode = 'fused'                         # 'fused' (in-kernel Philox) | 'torch' (F.dropout mask)
+        self.sparse_supports = True                         # V > 80: fixed supports with few non-zeros per row run as sparse gathers
 
         # registration order below mirrors graph_wavenet.py:110-183 so state_dict keys (and a seeded
         # default init) line up with the reference
@@ -322,7 +323,7 @@ class gwnet(nn.Module):
         supports: List[torch.Tensor] = []
         if self.gcn_bool:
             supports = list(self.supports)
-            if not self._sparse_checked and V > 80:
+            if not self._sparse_checked and V > 80 and self.sparse_supports:
                 # big graphs: fixed supports with few neighbours per node are applied as sparse gathers (ops.register_sparse_support)
                 for s_ in supports:
                     if s_.is_cuda:
