@@ -7,13 +7,17 @@ Workload (N=1 and per rank at N>1, weak scaling): BASELINE config 2 - Graph Wave
 county graph, forward/backward transition supports + adaptive adjacency, k=2, 4x2 layers, in_dim 2,
 T=12 -> 12-step forecast, batch 512 per GPU, bf16 activations, dropout 0.3 (reference default).
 A "step" is forward + MSELoss + backward + gradient all-reduce (N>1) + Adam(lr=1e-3) step
-(lit.py:24,29-43,59-61).  Synthetic N(0,1) inputs/targets, seed 42, default (reference-style) random init under seed 42.
+(lit.py:24,29-43,59-61), the whole of it one CUDA graph per rank; by default the optimizer is FlatAdam (the same update
+rule in one launch, with the all-reduce fused into it over NVSwitch peer memory at N>1; --comm selects the NCCL variants).
+Synthetic N(0,1) inputs/targets, seed 42, default (reference-style) random init under seed 42.
 
 `--impl reference` times the reference's CPU implementation of the same path - the oracle port in
 its ATen-call form (the reference is Python-only and cannot travel to the GPU box) - on
-all host cores, on a bounded sample of the same workload.
+all host cores, at the full step of the workload (a bounded sample only if the run would not fit in minutes).
 
-Prints ONE JSON line (rank 0).
+Prints ONE JSON line (rank 0): metric / value / e2e / clocks / gpu_launches, `roofline` (dominant kernel) and three more
+kernel rooflines, `cpu_baseline`, and side records `config3`, `config5` (the 3,100-node configurations, every rank takes
+part), `config2_dropout_mode_torch`, `config2_fp32`.
 """
 from __future__ import annotations
 
