@@ -75,6 +75,58 @@ __global__ void __launch_bounds__(128) dadj_finish_kernel(const float* __restric
   }
 }
 
+// Small graphs (V <= 96): the same completion with A and Q staged in shared memory by every CTA (coalesced, 2 x 36 KB at
+// V = 96) - the per-element loop above walks A row-wise per thread (a different line per thread and iteration).
+// CTA = 8 output rows p, thread = (row p, column q) pairs strided over the CTA.
+__global__ void __launch_bounds__(256) dadj_finish_small_kernel(const float* __restrict__ A, const float* __restrict__ d0,
+                                                                const float* __restrict__ Q, float* __restrict__ out, int V) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ float sh[];
+  float* As = sh;            // [V][V]
+  float* Qs = sh + V * V;    // [V][V]
+  for (int i = threadIdx.x; i < V * V; i += 256) { As[i] = __ldg(A + i); Qs[i] = __ldg(Q + i); }
+  __syncthreads();
+  const int p0 = blockIdx.x * 8;
+  for (int o = threadIdx.x; o < 8 * V; o += 256) {
+    const int p = p0 + o / V, q = o % V;
+    if (p >= V) break;
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll 4
+    for (int w = 0; w < V; ++w) {
+      t1 = fmaf(Qs[p * V + w], As[q * V + w], t1);      // broadcast x stride-V (conflict-free for odd V; 2-way at worst)
+      t2 = fmaf(As[w * V + p], Qs[w * V + q], t2);      // broadcast x consecutive
+    }
+    out[(long long)p * V + q] = __ldg(d0 + (long long)p * V + q) + t1 + t2;
+  }
+}
+
+// dE2[r, j] = sum_i E1[i, r] dM[i, j] for small graphs: CTA = rank index r, thread = column j, eight independent loads in
+// flight per thread; plain stores (no memset node, no atomics)
+__global__ void __launch_bounds__(128) adp_bwd_cols_small_kernel(const float* __restrict__ e1, const float* __restrict__ dm,
+                                                                 float* __restrict__ de2, int V, int R) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float ecol[128];
+  const int r = blockIdx.x, j = threadIdx.x;
+  for (int i = threadIdx.x; i < V; i += 128) ecol[i] = __ldg(e1 + (long long)i * R + r);
+  __syncthreads();
+  if (j >= V) return;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  int i = 0;
+  for (; i + 8 <= V; i += 8) {
+    float g[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g[k] = __ldg(dm + (long long)(i + k) * V + j);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = fmaf(ecol[i + k], g[k], acc[k]);
+  }
+  for (; i < V; ++i) acc[0] = fmaf(ecol[i], __ldg(dm + (long long)i * V + j), acc[0]);
+  de2[(long long)r * V + j] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+}
+
 // one warp per row: dM row -> ws, dE1 row
 __global__ void __launch_bounds__(256) adp_bwd_rows_kernel(const float* __restrict__ e1,
                                                            const float* __restrict__ e2,
@@ -181,7 +233,17 @@ extern "C" int gwn_adp_pair_bwd(const float* e1, const float* e2, const float* a
   GWN_REQUIRE(e1 && e2 && adp && d_pair && d_e1 && d_e2 && ws && V >= 1 && R >= 1 && R <= ADP_MAX_R,
               "adp_pair_bwd: bad argument");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  GWN_CUDA(launch_pdl(dadj_finish_kernel, dim3(V), dim3(128), 2 * V * sizeof(float), st, adp, d_pair, d_pair + (long long)V * V, ws, V));
+  if (V <= 96) {
+    static bool attr = false;
+    if (!attr) {
+      GWN_CUDA(cudaFuncSetAttribute(dadj_finish_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+      attr = true;
+    }
+    GWN_CUDA(launch_pdl(dadj_finish_small_kernel, dim3((unsigned)cdiv(V, 8)), dim3(256), 2 * (size_t)V * V * sizeof(float), st, adp, d_pair,
+                        d_pair + (long long)V * V, ws, V));
+  } else {
+    GWN_CUDA(launch_pdl(dadj_finish_kernel, dim3(V), dim3(128), 2 * V * sizeof(float), st, adp, d_pair, d_pair + (long long)V * V, ws, V));
+  }
   GWN_LAUNCHED();
   return gwn_adp_bwd(e1, e2, adp, ws, d_e1, d_e2, ws + (long long)V * V, V, R, stream);
 }
@@ -193,6 +255,11 @@ extern "C" int gwn_adp_bwd(const float* e1, const float* e2, const float* adp, c
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   GWN_CUDA(launch_pdl(adp_bwd_rows_kernel, dim3((unsigned)cdiv(V, 8)), dim3(256), 0, st, e1, e2, adp, d_adp, d_e1, ws, V, R));
   GWN_LAUNCHED();
+  if (V <= 128) {
+    GWN_CUDA(launch_pdl(adp_bwd_cols_small_kernel, dim3(R), dim3(128), 0, st, e1, ws, d_e2, V, R));
+    GWN_LAUNCHED();
+    return 0;
+  }
   GWN_CUDA(cudaMemsetAsync(d_e2, 0, sizeof(float) * (size_t)R * V, st));
   int col_tiles = (int)cdiv(V, 256);
   int splits = (int)cdiv(148 * 2, col_tiles);

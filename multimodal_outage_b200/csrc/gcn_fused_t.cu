@@ -110,11 +110,13 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gcn_fwd_t_kernel(const __grid_c
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&z_full[i], 1); mbar_init(&z_empty[i], 1);
-      mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 256);
+      mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 8);
     }
-    mbar_init(m_free, 256); mbar_init(m_full, 64);
-    mbar_init(ua_full, 1); mbar_init(ua_empty, 256); mbar_init(ub_full, 1); mbar_init(ub_empty, 256);
-    mbar_init(a_full, 256); mbar_init(a_empty, 1);
+    // consumer -> producer hand-offs count ONE arrival per warp (lane 0 after __syncwarp): per-thread arrivals put
+    // ~2,400 serialised updates of the barrier words on the shared-memory pipe per group
+    mbar_init(m_free, 8); mbar_init(m_full, 2);
+    mbar_init(ua_full, 1); mbar_init(ua_empty, 8); mbar_init(ub_full, 1); mbar_init(ub_empty, 8);
+    mbar_init(a_full, 8); mbar_init(a_empty, 1);
     fence_barrier_init();
     tg::tma_prefetch_desc(&zmap);
   }
@@ -268,8 +270,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gcn_fwd_t_kernel(const __grid_c
           if (half == 1 && NM < 4) break;                            // (no second column half)
           const int j = 4 * half + set, j2 = j + 2;                  // this warp's chunks of the half
           const int jmax = half == 0 ? (NM < 3 ? NM : 3) : NM;
-          mbar_wait(half == 0 ? ua_full : ub_full, (uint32_t)(tt & 1));
-          if (t == 0 && half == 0) mbar_wait(a_empty, (uint32_t)((gi & 1) ^ 1));      // GEMM 2 of the previous group has read A
+          mbar_wait_lazy2(half == 0 ? ua_full : ub_full, (uint32_t)(tt & 1));
+          if (t == 0 && half == 0) mbar_wait_lazy2(a_empty, (uint32_t)((gi & 1) ^ 1));      // GEMM 2 of the previous group has read A
           tc_fence_after();
           uint32_t ra[32], rb[32];
           const bool l1 = warp_has_rows && j <= jmax, l2 = warp_has_rows && j2 <= jmax;
@@ -277,13 +279,15 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gcn_fwd_t_kernel(const __grid_c
           if (l2) tmem_ld32_issue(tmem_base + lane_off + TU + (uint32_t)j2 * 32u, rb);
           tmem_ld_wait();
           tc_fence_before();
-          mbar_arrive(half == 0 ? ua_empty : ub_empty);              // the half is in registers: GEMM 1 may overwrite it
+          __syncwarp();
+          if (lane == 0) mbar_arrive(half == 0 ? ua_empty : ub_empty);   // the half is in registers: GEMM 1 may overwrite it
           if (valid && l1) put(j, ra);
           if (valid && l2) put(j2, rb);
         }
       }
       fence_proxy_async();
-      mbar_arrive(a_full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full);
       if (warp == 8) GT_TRACE(5);
     }
   } else if (warp == 2 || warp == 3) {
@@ -298,7 +302,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gcn_fwd_t_kernel(const __grid_c
     int gi = 0;
     for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++gi) {
       const int ns = min(4, p.slabs - 4 * g);
-      mbar_wait(m_free, (uint32_t)((gi & 1) ^ 1));           // the epilogue of the previous group has read its bits
+      mbar_wait_lazy(m_free, (uint32_t)((gi & 1) ^ 1));           // the epilogue of the previous group has read its bits
       if (philox) {
         for (int wi = warp - 2; wi < 12; wi += 2) {
           const int rr = 32 * wi + lane;
@@ -310,7 +314,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gcn_fwd_t_kernel(const __grid_c
           kbits[lane * 12 + wi] = warp_bit_transpose(keep, lane);
         }
       }
-      mbar_arrive(m_full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(m_full);
     }
   } else if (warp >= 12) {
     // ===================== epilogue: lane = channel c of slab q of the group =====================
@@ -345,13 +350,13 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gcn_fwd_t_kernel(const __grid_c
 #pragma unroll
       for (int i = 0; i < 48; ++i)
         if (has && cb + i < V && (e == 1 || i < 32)) res[i] = __ldg(reinterpret_cast<const uint16_t*>(rp) + (size_t)(cb + i) * 32);
-      mbar_wait(&d_full[b], (uint32_t)((gi >> 1) & 1));
+      mbar_wait_lazy(&d_full[b], (uint32_t)((gi >> 1) & 1));
       if (warp == 12) GT_TRACE(6);
       tc_fence_after();
       // keep-bits of this channel for the slab's rows [q V, q V + V) of the group, aligned to bit 0 (three scalars: a
       // dynamically indexed array would live in local memory)
       uint32_t kb0 = 0xffffffffu, kb1 = 0xffffffffu, kb2 = 0xffffffffu;
-      mbar_wait(m_full, (uint32_t)(gi & 1));
+      mbar_wait_lazy(m_full, (uint32_t)(gi & 1));
       if (philox) {
         const int r0 = q * V, w0 = r0 >> 5, o = r0 & 31;
         uint32_t w[4];
@@ -359,7 +364,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gcn_fwd_t_kernel(const __grid_c
         for (int k = 0; k < 4; ++k) w[k] = (w0 + k < 12) ? kbits[c * 12 + w0 + k] : 0u;
         kb0 = __funnelshift_r(w[0], w[1], o); kb1 = __funnelshift_r(w[1], w[2], o); kb2 = __funnelshift_r(w[2], w[3], o);
       }
-      mbar_arrive(m_free);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(m_free);
       const uint32_t td = tmem_base + lane_off + TD + (uint32_t)b * 128u;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
@@ -370,7 +376,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gcn_fwd_t_kernel(const __grid_c
           tmem_ld_wait();
           if (c0 + 16 >= c_end) {                 // this warp's last read: the accumulator may be overwritten
             tc_fence_before();
-            mbar_arrive(&d_empty[b]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&d_empty[b]);
           }
           if (has) {
             const int nv = V - c0;                // valid nodes of this sub-chunk (may be <= 0 or > 16)
@@ -404,7 +411,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gcn_fwd_t_kernel(const __grid_c
       }
       if (cb >= c_end) {                          // (V <= 32: set 1 has no columns but still takes part in the hand-offs)
         tc_fence_before();
-        mbar_arrive(&d_empty[b]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&d_empty[b]);
       }
       if (warp == 12) GT_TRACE(7);
     }

@@ -143,6 +143,43 @@ struct EpiGateTC {   // N = 64 interleaved (f,g); a chunk of 32 columns = 16 cha
     if (a) { store_bf16x16(a + p * 32 + ch0, aa); store_bf16x16(b + p * 32 + ch0, bb); }
     if (z_last && rem >= last_begin) store_bf16x16(z_last + (n * last_rows + rem - last_begin) * 32 + ch0, zz);
   }
+  // staged form (tc_gemm_impl.cuh, kTmaOut): the thread's 16 channels of z (a, b) go to 16-byte pieces 2*ci, 2*ci + 1 of its
+  // row in the 64B-swizzled [128][64 B] tiles (piece ^ ((row >> 1) & 3): a quarter warp's stores hit 8 distinct bank groups)
+  static constexpr int kTmaOut = 3;
+  int staged;                                                   // host switch (GWN_GATE_TMA_STORE=0: direct stores)
+  int n_out() const { return (staged && a) ? 3 : 0; }           // (one output: the direct stores are faster, 18.9 vs 22.2 us)
+  bf16* out_ptr(int i) const { return i == 0 ? z : i == 1 ? a : b; }
+  __device__ __forceinline__ void chunk_st(long long p, long long n, long long rem, bool valid, int c0, float v[32], uint8_t* slot_s,
+                                           int trow, uint64_t* sempty, uint32_t parity) {
+    uint32_t zw[8], aw[8], bw[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float a0 = tanh_fast(v[4 * i]), a1 = tanh_fast(v[4 * i + 2]);
+      const float b0 = fmaf(0.5f, tanh_fast(v[4 * i + 1]), 0.5f), b1 = fmaf(0.5f, tanh_fast(v[4 * i + 3]), 0.5f);
+      __nv_bfloat162 h = __floats2bfloat162_rn(a0 * b0, a1 * b1);
+      zw[i] = *reinterpret_cast<uint32_t*>(&h);
+      h = __floats2bfloat162_rn(a0, a1); aw[i] = *reinterpret_cast<uint32_t*>(&h);
+      h = __floats2bfloat162_rn(b0, b1); bw[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    tc::mbar_wait_lazy(sempty, parity);                              // the slot's previous tile has been read by its bulk stores
+    const uint32_t sw = ((uint32_t)trow >> 1) & 3u, cc = (uint32_t)(c0 >> 5) * 2u;
+    uint8_t* row = slot_s + (size_t)trow * 64;
+    uint8_t* p0 = row + ((cc ^ sw) << 4);
+    uint8_t* p1 = row + (((cc + 1u) ^ sw) << 4);
+    *reinterpret_cast<uint4*>(p0) = make_uint4(zw[0], zw[1], zw[2], zw[3]);
+    *reinterpret_cast<uint4*>(p1) = make_uint4(zw[4], zw[5], zw[6], zw[7]);
+    if (a) {
+      *reinterpret_cast<uint4*>(p0 + 8192) = make_uint4(aw[0], aw[1], aw[2], aw[3]);
+      *reinterpret_cast<uint4*>(p1 + 8192) = make_uint4(aw[4], aw[5], aw[6], aw[7]);
+      *reinterpret_cast<uint4*>(p0 + 16384) = make_uint4(bw[0], bw[1], bw[2], bw[3]);
+      *reinterpret_cast<uint4*>(p1 + 16384) = make_uint4(bw[4], bw[5], bw[6], bw[7]);
+    }
+    if (z_last && valid && rem >= last_begin) {
+      uint4* zl = reinterpret_cast<uint4*>(z_last + (n * last_rows + rem - last_begin) * 32 + (c0 >> 1));
+      zl[0] = make_uint4(zw[0], zw[1], zw[2], zw[3]);
+      zl[1] = make_uint4(zw[4], zw[5], zw[6], zw[7]);
+    }
+  }
   __device__ __forceinline__ void finish(float*) {}
   __device__ __forceinline__ void flush(const float*, int) {}
 };
@@ -664,6 +701,12 @@ static bool horner_bwd_enabled() {   // GWN_HORNER_BWD=0 keeps the recompute-bas
   return v != 0;
 }
 
+static bool gate_tma_store_enabled() {   // GWN_GATE_TMA_STORE=0: the gated conv writes z, a, b with per-thread stores (A/B measurements)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GWN_GATE_TMA_STORE"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
 static bool gcn_t_enabled() {       // GWN_GCN_T=0 keeps the node-major fused forward (A/B measurements)
   static int v = -1;
   if (v < 0) { const char* e = getenv("GWN_GCN_T"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -795,6 +838,7 @@ static int layer_fwd_t(const gwn_layer_cfg* c, const gwn_layer_fwd_args* g, cuda
       eg.a = c->training ? reinterpret_cast<bf16*>(g->a) : nullptr;
       eg.b = c->training ? reinterpret_cast<bf16*>(g->b) : nullptr;
       eg.z_last = reinterpret_cast<bf16*>(g->z_last); eg.last_begin = last_begin; eg.last_rows = last_rows;
+      eg.staged = gate_tma_store_enabled() ? 1 : 0;
       if (int rc = launch_pos_gemm_tc(pg, eg, st)) return rc;
     }
   } else {

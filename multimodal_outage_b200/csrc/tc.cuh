@@ -72,6 +72,18 @@ __device__ __forceinline__ void mbar_wait_park(uint64_t* bar, uint32_t parity) {
   }
   __trap();  // pipeline protocol bug: fail loudly instead of hanging the GPU
 }
+// Waits of the many-warp roles (epilogue / staging / store warps): parked, so that their polls do not take issue slots from
+// the single producer / MMA-issuing warps that share their scheduler.  GWN_PARK: 0 = every wait spins, 1 = epilogue-type
+// waits park (default), 2 = the TMEM -> shared-memory stage warps park too (A/B builds).
+#ifndef GWN_PARK
+#define GWN_PARK 1
+#endif
+__device__ __forceinline__ void mbar_wait_lazy(uint64_t* bar, uint32_t parity) {
+  if (GWN_PARK >= 1) mbar_wait_park(bar, parity); else mbar_wait(bar, parity);
+}
+__device__ __forceinline__ void mbar_wait_lazy2(uint64_t* bar, uint32_t parity) {
+  if (GWN_PARK >= 2) mbar_wait_park(bar, parity); else mbar_wait(bar, parity);
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }

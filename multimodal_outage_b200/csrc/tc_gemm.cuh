@@ -59,6 +59,7 @@ struct PgParams {
   int tiles_per_n, n_samples;
   int sub;                      // 128-row sub-tiles per pipeline step (macro tile = 128*sub rows): amortises hand-offs
   int rows_out;                 // output rows per (virtual) sample
+  int n_out;                    // staged outputs (Epi::kTmaOut epilogues): bulk tensor stores from shared memory; 0 = direct stores
   int map_of[PG_TC_MAX_CHUNKS]; // chunk -> tensor map
   int row_off[PG_TC_MAX_CHUNKS];
   long long* trace;             // optional debug timeline of CTA 0 (GWN_PG_TRACE)

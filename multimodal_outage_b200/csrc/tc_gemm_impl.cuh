@@ -10,6 +10,7 @@
 //        atomic per statistic per CTA (per-warp global atomics put 16 x 148 serialised updates on each address)
 #pragma once
 #include <cstdlib>
+#include <type_traits>
 
 #include "tc.cuh"
 #include "tc_gemm.cuh"
@@ -64,6 +65,28 @@ __device__ __forceinline__ float warp_column_sums16(float v[16], int lane) {
 }
 
 struct PgMaps { CUtensorMap m[PG_TC_MAX_MAPS]; };
+
+// Optional staged outputs (Epi::kTmaOut = K > 0, used by the gated conv): the epilogue threads write their bf16 output rows
+// into 64B-swizzled [128 rows][64 B] shared-memory tiles (conflict-free 16-byte stores) and the otherwise idle warp 3
+// sends each tile to global memory with ONE bulk tensor store per output (rows past the sample's end are clipped by the
+// tensor map) - instead of 32-row x 16-byte scattered st.global per warp instruction.  Two staging slots.
+//   host:   int n_out() const;  bf16* out_ptr(int i) const;          (outputs actually written by this launch, <= K)
+//   device: void chunk_st(p, n, rem, valid, c0, v, slot_smem, tile_row, sempty_bar, parity);   tile i of output o lives at
+//           slot_smem + o * 8192; the functor waits for (sempty_bar, parity) before its first shared-memory store
+template <typename E, typename = void> struct epi_tma_out { static constexpr int value = 0; };
+template <typename E> struct epi_tma_out<E, std::void_t<decltype(E::kTmaOut)>> { static constexpr int value = E::kTmaOut; };
+constexpr int PGT_STORE_WARP = 3;
+constexpr int PGT_OUT_SLOTS = 2;
+constexpr int PGT_OUT_MAP0 = PG_TC_MAX_MAPS - 3;       // output maps live in the last three PgMaps entries
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 #define PG_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && g < 48) p.trace[g * 8 + (slot)] = clock64(); } while (0)
 
 // (sample, 128-row tile inside the sample) of a CTA's current macro tile, advanced without divisions: a 32-bit
@@ -109,7 +132,11 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
   const uint32_t w_bytes = ((uint32_t)K8 * (uint32_t)N * 16u + 1023u) & ~1023u;
   uint8_t* a_s = smem;                                        // stages first (1024-aligned boxes)
   // (kWgrad: 16 KB of slack after the ring - the M = 128 weight-gradient MMA of the last stage reads two atoms past the ones atom)
-  uint8_t* w_s = smem + (size_t)stages * a_bytes + (Epi::kWgrad ? 16384 : 0);
+  constexpr int KOUT = epi_tma_out<Epi>::value;
+  const int n_out = KOUT > 0 ? p.n_out : 0;                   // staged outputs of this launch (0: direct stores)
+  constexpr uint32_t out_slot_bytes = (uint32_t)KOUT * 8192u;
+  uint8_t* out_s = smem + (size_t)stages * a_bytes + (Epi::kWgrad ? 16384 : 0);      // [slots][KOUT][128 rows][64 B]
+  uint8_t* w_s = out_s + (size_t)PGT_OUT_SLOTS * out_slot_bytes;
   uint8_t* ones_s = w_s + w_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ones_s + PGT_ONES_BYTES);
   uint64_t* full = bars;               // [stages] (<= 8)
@@ -118,15 +145,23 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
   uint64_t* tempty = bars + 20;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
   uint64_t* wfull = bars + 25;         // fused weight gradient: all MMAs of the CTA completed
+  uint64_t* sfull = bars + 26;         // [2] staged outputs: every epilogue warp of the tile has written its rows
+  uint64_t* sempty = bars + 28;        // [2] the bulk stores of the slot have read it
   float* red_s = reinterpret_cast<float*>(bars + 32);        // [64] CTA-level statistics scratch
   (void)a_s;
   if (tid < 64) red_s[tid] = 0.f;
+  // epilogue warps that take part in one macro tile: its SUB x ceil(N/32) items go to consecutive ranks of every lane
+  // quadrant, so min(items, ranks) warps per quadrant have work; the others skip the tile (no wait, no arrival)
+  const int epi_items = SUB * ((N + 31) / 32);
+  const uint32_t epi_arrivals = 4u * (uint32_t)(epi_items < PGT_EPI_RANKS ? epi_items : PGT_EPI_RANKS);
 
   if (tid == 0) {
-    // a stage is free when the MMAs have read it and (with extras) every epilogue thread is done with it
-    for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], p.n_extra ? 1 + 32 * PGT_EPI_WARPS : 1); }
-    for (int i = 0; i < n_acc; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 32 * PGT_EPI_WARPS); }
+    // a stage is free when the MMAs have read it and (with extras) every epilogue warp with work in the tile is done with it
+    // (ONE arrival per warp: 512 per-thread arrivals per tile serialise on the barrier word)
+    for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], p.n_extra ? 1 + epi_arrivals : 1); }
+    for (int i = 0; i < n_acc; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], epi_arrivals); }
     mbar_init(wfull, 1);
+    for (int i = 0; i < PGT_OUT_SLOTS; ++i) { mbar_init(&sfull[i], epi_arrivals); mbar_init(&sempty[i], 1); }
     fence_barrier_init();
   }
   const uint32_t acc_cols = N <= 32 ? 32u : N <= 64 ? 64u : N <= 128 ? 128u : 256u;
@@ -156,6 +191,23 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
   // is step-constant too UNLESS it folds the batch statistics the predecessor just produced (wsrc.bn == 1, training) or is
   // a prepared image (w_img): only then the wait comes first; otherwise it follows the image build.
   const bool pdl_early = p.wsrc.W == nullptr || p.wsrc.bn == 1;
+  // 16-byte loads of the fp32 weights (a thread owns 4 consecutive output columns - or, transposed, 4 consecutive K rows -
+  // of one row), all issued BEFORE the wait: the parameters are step-constant even when the fold is not
+  constexpr int MAXIT = 4;                                            // K*N <= 4*4*PGT_THREADS elements (launcher checks)
+  float4 wv[MAXIT];
+  if (p.wsrc.W != nullptr) {
+    const PgWsrc& ws = p.wsrc;
+    const int N4 = N >> 2, total4 = (32 * n_chunks * N) >> 2;
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) {
+      const int i = tid + it * PGT_THREADS;
+      wv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < total4) {
+        if (ws.transposed) { const int k4 = i & 7, r = i >> 3, n = r % N, q = r / N; wv[it] = __ldg(reinterpret_cast<const float4*>(ws.W + ws.w_off[q] + n * ws.ld + 4 * k4)); }
+        else { const int n4 = i % N4, k = i / N4; wv[it] = __ldg(reinterpret_cast<const float4*>(ws.W + ws.w_off[k >> 5] + (k & 31) * ws.ld + 4 * n4)); }
+      }
+    }
+  }
   if (pdl_early) { pdl_wait(); pdl_trigger(); }
   if (p.wsrc.W == nullptr) {
     const uint4* src = reinterpret_cast<const uint4*>(p.w_img);
@@ -201,23 +253,11 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
     }
     __syncthreads();
     bf16* img = reinterpret_cast<bf16*>(w_s);
-    // 16-byte loads of the fp32 weights (a thread owns 4 consecutive output columns - or, transposed, 4 consecutive
-    // K rows - of one row), all of a thread's loads issued before the first use.  The shift-into-bias partial sums go
-    // through a scratch array in the (still idle, contiguous) TMA stages and are added in a FIXED order: every CTA must
-    // build bit-identical images (atomics would make a sample's result depend on which CTA computed it).
+    // The shift-into-bias partial sums go through a scratch array in the (still idle, contiguous) TMA stages and are added
+    // in a FIXED order: every CTA must build bit-identical images (atomics would make a sample's result depend on which
+    // CTA computed it).
     float* part_s = reinterpret_cast<float*>(a_s);                    // [PGT_THREADS][4]
     const int N4 = N >> 2, total4 = (K * N) >> 2;
-    constexpr int MAXIT = 4;                                          // K*N <= 4*4*PGT_THREADS elements (launcher checks)
-    float4 wv[MAXIT];
-#pragma unroll
-    for (int it = 0; it < MAXIT; ++it) {
-      const int i = tid + it * PGT_THREADS;
-      wv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (i < total4) {
-        if (ws.transposed) { const int k4 = i & 7, r = i >> 3, n = r % N, q = r / N; wv[it] = __ldg(reinterpret_cast<const float4*>(ws.W + ws.w_off[q] + n * ws.ld + 4 * k4)); }
-        else { const int n4 = i % N4, k = i / N4; wv[it] = __ldg(reinterpret_cast<const float4*>(ws.W + ws.w_off[k >> 5] + (k & 31) * ws.ld + 4 * n4)); }
-      }
-    }
     float part[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int it = 0; it < MAXIT; ++it) {
@@ -376,6 +416,32 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
         __syncwarp();
       }
     }
+  } else if (warp == PGT_STORE_WARP) {
+    // ===================== store warp: staged output tiles -> global memory, one bulk tensor store per output =====================
+    if constexpr (KOUT > 0) {
+      if (n_out > 0) {
+        PgWalk w; w.init((int)blockIdx.x, (int)gridDim.x, p.tiles_per_n);      // (staged outputs: SUB == 1)
+        const uint32_t so = smem_u32(out_s);
+        int g = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++g) {
+          const int slot = g & 1;
+          mbar_wait_lazy(&sfull[slot], (uint32_t)((g >> 1) & 1));
+          if (lane == 0) {                                      // (bulk groups belong to the issuing thread: always lane 0)
+            int ns, r0;
+            w.sub(0, ns, r0);
+            for (int o = 0; o < n_out; ++o)
+              tma_store_3d(&maps.m[PGT_OUT_MAP0 + o], so + (uint32_t)slot * out_slot_bytes + (uint32_t)o * 8192u, 0, r0, ns);
+            bulk_commit();
+            bulk_wait_read0();
+            mbar_arrive(&sempty[slot]);
+          }
+          __syncwarp();
+          w.advance();
+        }
+        if (lane == 0) bulk_wait0();
+        __syncwarp();
+      }
+    }
   } else if (warp >= PGT_EPI_WARP0) {
     // ===================== epilogue =====================
     const int quad = warp & 3;
@@ -388,34 +454,50 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
     int g = 0, stage = 0;
     int first = rank;                                           // items are dealt round-robin ACROSS tiles, so that
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {   // narrow tiles (IT < 4) still use every warp
-      const int acc = g & acc_mask;
-      mbar_wait(&tfull[acc], (uint32_t)((g >> acc_shift) & 1));
-      if (warp == PGT_EPI_WARP0 && lane == 0) PG_TRACE(5);
-      tc_fence_after();
-      int item = first;
-      for (; item < IT; item += PGT_EPI_RANKS) {
-        int t, ci;
-        if (nc_pow2) { t = item >> nc_shift; ci = item & (n_c32 - 1); } else { t = item / n_c32; ci = item - t * n_c32; }
-        const int c0 = ci * 32;
-        int ns, r0;
-        w.sub(t, ns, r0);
-        const int r = r0 + quad * 32 + lane;
-        const bool pv = r < p.rows_out && ns < p.n_samples;
-        // (sample, row) of the caller's view: virtual samples (position-wise GEMMs tile the flat position axis)
-        long long pp = (long long)ns * p.rows_out + r, n = ns, rem = r;
-        if (p.rows_out != (int)p.rows_per_n_out && pv) split_pos(pp, p.rows_per_n_out, n, rem);
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * buf_cols + (uint32_t)t * acc_cols + (uint32_t)c0, v);
-        if constexpr (Epi::kExtra)
-          epi.chunk_ex(pp, n, rem, pv, c0, v, smem + (size_t)stage * a_bytes + (size_t)(t * NB + n_chunks) * 8192, quad * 32 + lane);
-        else
-          epi.chunk(pp, n, rem, pv, c0, v);
+      if (first < IT) {                                         // this warp has work in the tile
+        const int acc = g & acc_mask;
+        mbar_wait_lazy(&tfull[acc], (uint32_t)((g >> acc_shift) & 1));
+        if (warp == PGT_EPI_WARP0 && lane == 0) PG_TRACE(5);
+        tc_fence_after();
+        int item = first;
+        for (; item < IT; item += PGT_EPI_RANKS) {
+          int t, ci;
+          if (nc_pow2) { t = item >> nc_shift; ci = item & (n_c32 - 1); } else { t = item / n_c32; ci = item - t * n_c32; }
+          const int c0 = ci * 32;
+          int ns, r0;
+          w.sub(t, ns, r0);
+          const int r = r0 + quad * 32 + lane;
+          const bool pv = r < p.rows_out && ns < p.n_samples;
+          // (sample, row) of the caller's view: virtual samples (position-wise GEMMs tile the flat position axis)
+          long long pp = (long long)ns * p.rows_out + r, n = ns, rem = r;
+          if (p.rows_out != (int)p.rows_per_n_out && pv) split_pos(pp, p.rows_per_n_out, n, rem);
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * buf_cols + (uint32_t)t * acc_cols + (uint32_t)c0, v);
+          if constexpr (Epi::kExtra) {
+            epi.chunk_ex(pp, n, rem, pv, c0, v, smem + (size_t)stage * a_bytes + (size_t)(t * NB + n_chunks) * 8192, quad * 32 + lane);
+          } else if constexpr (KOUT > 0) {
+            if (n_out > 0)
+              epi.chunk_st(pp, n, rem, pv, c0, v, out_s + (size_t)(g & 1) * out_slot_bytes, quad * 32 + lane, &sempty[g & 1],
+                           (uint32_t)(((g >> 1) & 1) ^ 1));
+            else
+              epi.chunk(pp, n, rem, pv, c0, v);
+          } else {
+            epi.chunk(pp, n, rem, pv, c0, v);
+          }
+        }
+        first = item - IT;                                      // where this warp starts in the next tile
+        tc_fence_before();
+        if constexpr (KOUT > 0) { if (n_out > 0) fence_proxy_async(); }     // staged rows -> visible to the bulk store
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&tempty[acc]);
+          if (p.n_extra) mbar_arrive(&empty[stage]);
+          if constexpr (KOUT > 0) { if (n_out > 0) mbar_arrive(&sfull[g & 1]); }
+        }
+        if (warp == PGT_EPI_WARP0 && lane == 0) PG_TRACE(6);
+      } else {
+        first -= IT;
       }
-      first = item - IT;                                        // where this warp starts in the next tile
-      tc_fence_before();
-      mbar_arrive(&tempty[acc]);
-      if (p.n_extra) mbar_arrive(&empty[stage]);
-      if (warp == PGT_EPI_WARP0 && lane == 0) PG_TRACE(6);
       ++g;
       w.advance();
       if (++stage == stages) stage = 0;
@@ -485,7 +567,12 @@ int launch_pos_gemm_tc(PgParams& p, const Epi& epi, cudaStream_t st) {
   const int sms = tg_sm_count();
   const int acc_c = p.N <= 32 ? 32 : p.N <= 64 ? 64 : p.N <= 128 ? 128 : 256;
   const size_t w_bytes = ((size_t)(p.n_chunks * 4 + (p.has_bias ? 2 : 0)) * p.N * 16 + 1023) & ~(size_t)1023;
-  const size_t fixed = w_bytes + PGT_ONES_BYTES + 1024 + 1024 + (Epi::kWgrad ? 16384 : 0);   // alignment slack + barriers / scratch
+  constexpr int KOUT = epi_tma_out<Epi>::value;
+  int n_out = 0;
+  if constexpr (KOUT > 0) n_out = epi.n_out();
+  p.n_out = n_out;
+  const size_t fixed = w_bytes + PGT_ONES_BYTES + 1024 + 1024 + (Epi::kWgrad ? 16384 : 0) +   // alignment slack + barriers / scratch
+                       (size_t)PGT_OUT_SLOTS * KOUT * 8192;
   GWN_REQUIRE(fixed + 2 * (size_t)(NB + (Epi::kWgrad ? 1 : 0)) * 8192 <= 227 * 1024,
               "pos_gemm_tc: K=%d does not fit 2 stages in shared memory", 32 * p.n_chunks);
   if (Epi::kWgrad)
@@ -499,7 +586,7 @@ int launch_pos_gemm_tc(PgParams& p, const Epi& epi, cudaStream_t st) {
   double eff_of[3] = {-1, -1, -1}, best_eff = -1;
   for (int i = 0; i < 3; ++i) {
     const int sub = subs[i];
-    if (2 * acc_c * sub > 512 || (Epi::kWgrad && sub > 1)) continue;
+    if (2 * acc_c * sub > 512 || ((Epi::kWgrad || n_out > 0) && sub > 1)) continue;
     const size_t ab = (size_t)NB * 8192 * sub + (Epi::kWgrad ? 8192 : 0);
     int stg = (int)((227 * 1024 - fixed) / ab);
     if (stg > 8) stg = 8;
@@ -542,6 +629,12 @@ int launch_pos_gemm_tc(PgParams& p, const Epi& epi, cudaStream_t st) {
     p.row_off[q] = (int)c.row_off;
   }
   for (int i = n_maps; i < PG_TC_MAX_MAPS; ++i) maps.m[i] = maps.m[0];
+  if constexpr (KOUT > 0) {
+    GWN_REQUIRE(n_out <= KOUT && KOUT <= 3 && n_maps <= PGT_OUT_MAP0 && p.N == 64, "pos_gemm_tc: staged outputs need <= %d input maps", PGT_OUT_MAP0);
+    for (int o = 0; o < n_out; ++o)
+      if (int rc = tg_map_rows3d(&maps.m[PGT_OUT_MAP0 + o], epi.out_ptr(o), (uint64_t)p.rows_out, (uint64_t)p.n_samples, 32, 128))
+        return rc;
+  }
   {
     p.trace = trace_ptr("GWN_PG_TRACE");
   }

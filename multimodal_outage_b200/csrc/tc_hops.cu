@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(TH_THREADS, 1) hops_tc_kernel(const __grid_con
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 32 * TH_EPI_WARPS);
+      mbar_init(&tempty[i], TH_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -176,7 +176,8 @@ __global__ void __launch_bounds__(TH_THREADS, 1) hops_tc_kernel(const __grid_con
           }
         }
         tc_fence_before();
-        mbar_arrive(&tempty[st.acc]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[st.acc]);    // one arrival per warp
       }
     }
   }

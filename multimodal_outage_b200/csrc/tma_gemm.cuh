@@ -124,7 +124,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
   if (tid == 0) {
     for (int i = 0; i < ST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 32 * TG_EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], TG_EPI_WARPS); }
     fence_barrier_init();
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
@@ -232,7 +232,8 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty[acc]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);    // one arrival per warp
     }
   }
   tc_fence_before();
