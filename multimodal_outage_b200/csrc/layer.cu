@@ -274,14 +274,16 @@ struct EpiGateBwdTC {   // N = 32: dx = acc + du(cropped rows); (sum dx, sum dx*
   // fused weight gradient (tc_gemm_impl.cuh): accumulator row c of chunk q = (tap j, half h) -> dw_fg[(j*32 + c), 32h + n],
   // with the BatchNorm fold of the layer input (dW' = scale[c] dW + shift[c] db[n]); ones row -> db_fg
   const float* wg_scale; const float* wg_shift; float* dw_fg; float* db_fg;
-  __device__ __forceinline__ void wgrad_row(int q, int c, const float v[32], const float* db_s, float* stg) const {
-    const float sc = wg_scale ? __ldg(wg_scale + c) : 1.f, sh = wg_scale ? __ldg(wg_shift + c) : 0.f;
-    float* dst = stg + (size_t)((q >> 1) * 32 + c) * 64 + 32 * (q & 1);
+  // row (chunk q = (tap j, half h), column n) of the transposed accumulator: v[c] = sum u_prev[.][c] dfg_q[.][n], db = sum dfg_q[.][n]
+  // over the same rows (so the fold's shift term pairs with exactly the partial sum this CTA holds)
+  __device__ __forceinline__ void wgrad_row_t(int q, int n, const float v[32], float db, float* db_s, float* stg) const {
+    float* dst = stg + (size_t)((q >> 1) * 32) * 64 + 32 * (q & 1) + n;
 #pragma unroll
-    for (int n = 0; n < 32; n += 4)
-      *reinterpret_cast<float4*>(dst + n) =
-          make_float4(fmaf(sc, v[n], sh * db_s[32 * (q & 1) + n]), fmaf(sc, v[n + 1], sh * db_s[32 * (q & 1) + n + 1]),
-                      fmaf(sc, v[n + 2], sh * db_s[32 * (q & 1) + n + 2]), fmaf(sc, v[n + 3], sh * db_s[32 * (q & 1) + n + 3]));
+    for (int c = 0; c < 32; ++c) {
+      const float sc = wg_scale ? __ldg(wg_scale + c) : 1.f, sh = wg_scale ? __ldg(wg_shift + c) : 0.f;
+      dst[(size_t)c * 64] = fmaf(sc, v[c], sh * db);
+    }
+    if (q < 2) db_s[32 * q + n] = db;                           // tap 0 sees every output position once: the bias gradient
   }
   __device__ __forceinline__ void wgrad_flush(const float* stg, const float* db_s, int n_chunks, int t, int nthr) const {
     red_flush_2d(dw_fg, 64, stg, 64, (n_chunks >> 1) * 32, 64, t, nthr);

@@ -87,7 +87,11 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t sr
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-#define PG_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && g < 48) p.trace[g * 8 + (slot)] = clock64(); } while (0)
+#ifdef GWN_TRACE     // clock64 timeline of CTA 0, 16 slots per tile (scripts/gpu_gate_trace.py); compiled out of release builds
+#define PG_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && g < 48) p.trace[g * 16 + (slot)] = clock64(); } while (0)
+#else
+#define PG_TRACE(slot) do { } while (0)
+#endif
 
 // (sample, 128-row tile inside the sample) of a CTA's current macro tile, advanced without divisions: a 32-bit
 // division costs a few hundred cycles of latency on the rarely-scheduled producer / per-item epilogue paths
@@ -209,6 +213,49 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
     }
   }
   if (pdl_early) { pdl_wait(); pdl_trigger(); }
+  // ===================== TMA producers (warps PROD_A / PROD_B; boxes of a macro tile dealt alternately to the two warps; the
+  // whole warp walks the loop so addresses / coordinates stay in uniform registers, one elected lane issues).  A resumable
+  // routine: the gated conv's prologue calls it for the first ring of stages BEFORE the weight image is built (the loads'
+  // HBM round trip then runs under the BatchNorm fold), the role dispatch below for the rest. =====================
+  const bool is_prod = warp == PGT_PROD_A || warp == PGT_PROD_B;
+  PgWalk pw;
+  int p_g = 0, p_stage = 0, p_phase = 0, p_tile = (int)blockIdx.x;
+  if (is_prod) pw.init((int)blockIdx.x * SUB, (int)gridDim.x * SUB, p.tiles_per_n);
+  auto produce = [&](int max_tiles) {
+    const int me = warp == PGT_PROD_A ? 0 : 1;
+    const int boxes = SUB * NB;
+    const uint32_t my_bytes = (uint32_t)((boxes + 1 - me) >> 1) * 8192u;
+    for (; p_tile < p.n_tiles && max_tiles > 0; p_tile += gridDim.x, ++p_g, --max_tiles) {
+      const int g = p_g, stage = p_stage;
+      (void)g;
+      mbar_wait(&empty[stage], (uint32_t)(p_phase ^ 1));
+      if (me == 0 && lane == 0) PG_TRACE(0);
+      if (elect_one()) {
+        if (my_bytes) tg::mbar_expect_tx(&full[stage], my_bytes); else mbar_arrive(&full[stage]);
+        const uint32_t sa = base + (uint32_t)stage * a_bytes;
+        int i = 0;
+        for (int t = 0; t < SUB; ++t) {
+          // sub-tile = 128 consecutive rows of ONE sample; past the last sub-tile the sample index is out of range
+          // and TMA zero-fills the box
+          int n, r0;
+          pw.sub(t, n, r0);
+          for (int q = 0; q < NB; ++q, ++i)
+            if ((i & 1) == me)
+              tg::tma_3d(sa + (uint32_t)i * 8192u, &maps.m[p.map_of[q]], 0, r0 + p.row_off[q], n, &full[stage]);
+        }
+      }
+      __syncwarp();
+      if (me == 0 && lane == 0) PG_TRACE(1);
+      pw.advance();
+      if (++p_stage == stages) { p_stage = 0; p_phase ^= 1; }
+    }
+  };
+  // head start (staged-output epilogues only: their staging slots hold the fold's scratch, so the TMA stages are free)
+  const bool head_start = KOUT > 0 && pdl_early && p.wsrc.W != nullptr;
+  if (head_start) {
+    __syncthreads();                                             // barriers initialised
+    if (is_prod) produce(stages);
+  }
   if (p.wsrc.W == nullptr) {
     const uint4* src = reinterpret_cast<const uint4*>(p.w_img);
     uint4* dst = reinterpret_cast<uint4*>(w_s);
@@ -256,7 +303,7 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
     // The shift-into-bias partial sums go through a scratch array in the (still idle, contiguous) TMA stages and are added
     // in a FIXED order: every CTA must build bit-identical images (atomics would make a sample's result depend on which
     // CTA computed it).
-    float* part_s = reinterpret_cast<float*>(a_s);                    // [PGT_THREADS][4]
+    float* part_s = reinterpret_cast<float*>(head_start ? out_s : a_s);      // [PGT_THREADS][4]
     const int N4 = N >> 2, total4 = (K * N) >> 2;
     float part[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -313,38 +360,8 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
   const uint32_t tmem_base = *tmem_slot;
   const int acc_mask = n_acc - 1, acc_shift = n_acc == 4 ? 2 : 1;
 
-  if (warp == PGT_PROD_A || warp == PGT_PROD_B) {
-    // ===================== TMA producers (boxes of a macro tile dealt alternately to the two warps; the whole warp
-    // walks the loop so addresses / coordinates stay in uniform registers, one elected lane issues) =====================
-    {
-      const int me = warp == PGT_PROD_A ? 0 : 1;
-      const int boxes = SUB * NB;
-      const uint32_t my_bytes = (uint32_t)((boxes + 1 - me) >> 1) * 8192u;
-      PgWalk w; w.init((int)blockIdx.x * SUB, (int)gridDim.x * SUB, p.tiles_per_n);
-      int g = 0, stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++g) {
-        mbar_wait(&empty[stage], (uint32_t)(phase ^ 1));
-        if (me == 0 && lane == 0) PG_TRACE(0);
-        if (elect_one()) {
-          if (my_bytes) tg::mbar_expect_tx(&full[stage], my_bytes); else mbar_arrive(&full[stage]);
-          const uint32_t sa = base + (uint32_t)stage * a_bytes;
-          int i = 0;
-          for (int t = 0; t < SUB; ++t) {
-            // sub-tile = 128 consecutive rows of ONE sample; past the last sub-tile the sample index is out of range
-            // and TMA zero-fills the box
-            int n, r0;
-            w.sub(t, n, r0);
-            for (int q = 0; q < NB; ++q, ++i)
-              if ((i & 1) == me)
-                tg::tma_3d(sa + (uint32_t)i * 8192u, &maps.m[p.map_of[q]], 0, r0 + p.row_off[q], n, &full[stage]);
-          }
-        }
-        __syncwarp();
-        if (me == 0 && lane == 0) PG_TRACE(1);
-        w.advance();
-        if (++stage == stages) { stage = 0; phase ^= 1; }
-      }
-    }
+  if (is_prod) {
+    produce(0x7fffffff);                                       // (the tiles not requested by the prologue's head start)
   } else if (warp == PGT_MMA_WARP) {
     // ===================== MMA issuer: the whole warp walks the loop (uniform registers), one elected lane issues =====================
     {
@@ -389,20 +406,20 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
           }
           umma_commit(&tfull[acc]);
           if constexpr (Epi::kWgrad) {
-            // dW[(chunk q, c), n] += u_prev^T dfg_q over the tile's 128 rows (both boxes viewed MN-major, SW64 atoms: LBO =
-            // next 32-channel atom, SBO = next 8 positions, K = 16 step = 1024 B); accumulator row 32 = ones row = bias grad
+            // dWt[(chunk q, n), c] += dfg_q^T u_prev over the tile's 128 rows - ONE chain of 8 MMAs (K = 16 rows each) for all four
+            // chunks: A = the tile's four chunk boxes viewed MN-major (M = 4 x 32 dfg columns: SW64 atoms, LBO = next box, SBO =
+            // next 8 rows, K step = 1024 B), B = the u_prev box and the ones atom behind it (N = 48: 32 channels, the ones
+            // column = bias gradient, 15 zero columns).  The earlier orientation (M = channels padded to 128, N = 32 dfg
+            // columns, one chain per chunk) issued 32 MMAs whose 4 KB A read (45 cycles each) made the MMA warp the
+            // bottleneck of the kernel: 1,780 of 2,250 cycles per tile.
             const uint32_t sb = base + (uint32_t)stage * a_bytes;
             const uint64_t wt = tg::make_desc_sw(0, 8192u, 512u, 4u);
-            const uint32_t idw = make_idesc_bf16(128, 32, true, true);
-            const uint64_t au = wt + (uint64_t)((sb + (uint32_t)(NB - 1) * 8192u) >> 4);       // u_prev box, then the ones atom
+            const uint32_t idw = make_idesc_bf16(128, 48, true, true);
+            const uint64_t aw = wt + (uint64_t)(sb >> 4);                                       // chunk boxes 0..3
+            const uint64_t bw = wt + (uint64_t)((sb + (uint32_t)(NB - 1) * 8192u) >> 4);       // u_prev box, then the ones atom
 #pragma unroll
-            for (int q = 0; q < (NCH > 0 ? NCH : 1); ++q) {
-              const uint64_t bq = wt + (uint64_t)((sb + (uint32_t)q * 8192u) >> 4);
-#pragma unroll
-              for (int ks = 0; ks < 8; ++ks)
-                umma_bf16(tmem_base + 128u + 32u * (uint32_t)q, au + (uint64_t)(ks * 64), bq + (uint64_t)(ks * 64), idw,
-                          (g == 0 && ks == 0) ? 0u : 1u);
-            }
+            for (int ks = 0; ks < 8; ++ks)
+              umma_bf16(tmem_base + 128u, aw + (uint64_t)(ks * 64), bw + (uint64_t)(ks * 64), idw, (g == 0 && ks == 0) ? 0u : 1u);
           }
           umma_commit(&empty[stage]);
         }
@@ -426,6 +443,7 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++g) {
           const int slot = g & 1;
           mbar_wait_lazy(&sfull[slot], (uint32_t)((g >> 1) & 1));
+          if (lane == 0) PG_TRACE(8);
           if (lane == 0) {                                      // (bulk groups belong to the issuing thread: always lane 0)
             int ns, r0;
             w.sub(0, ns, r0);
@@ -434,6 +452,7 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
             bulk_commit();
             bulk_wait_read0();
             mbar_arrive(&sempty[slot]);
+            PG_TRACE(9);
           }
           __syncwarp();
           w.advance();
@@ -456,8 +475,10 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {   // narrow tiles (IT < 4) still use every warp
       if (first < IT) {                                         // this warp has work in the tile
         const int acc = g & acc_mask;
+        const bool tr = quad == 0 && first == 0 && lane == 0;      // (trace builds: the warp that takes the tile's first item)
+        (void)tr;
         mbar_wait_lazy(&tfull[acc], (uint32_t)((g >> acc_shift) & 1));
-        if (warp == PGT_EPI_WARP0 && lane == 0) PG_TRACE(5);
+        if (tr) PG_TRACE(5);
         tc_fence_after();
         int item = first;
         for (; item < IT; item += PGT_EPI_RANKS) {
@@ -473,6 +494,7 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
           if (p.rows_out != (int)p.rows_per_n_out && pv) split_pos(pp, p.rows_per_n_out, n, rem);
           float v[32];
           tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * buf_cols + (uint32_t)t * acc_cols + (uint32_t)c0, v);
+          if (tr && item == 0) PG_TRACE(7);
           if constexpr (Epi::kExtra) {
             epi.chunk_ex(pp, n, rem, pv, c0, v, smem + (size_t)stage * a_bytes + (size_t)(t * NB + n_chunks) * 8192, quad * 32 + lane);
           } else if constexpr (KOUT > 0) {
@@ -486,6 +508,7 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
           }
         }
         first = item - IT;                                      // where this warp starts in the next tile
+        if (tr) PG_TRACE(10);
         tc_fence_before();
         if constexpr (KOUT > 0) { if (n_out > 0) fence_proxy_async(); }     // staged rows -> visible to the bulk store
         __syncwarp();
@@ -494,7 +517,7 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
           if (p.n_extra) mbar_arrive(&empty[stage]);
           if constexpr (KOUT > 0) { if (n_out > 0) mbar_arrive(&sfull[g & 1]); }
         }
-        if (warp == PGT_EPI_WARP0 && lane == 0) PG_TRACE(6);
+        if (tr) PG_TRACE(6);
       } else {
         first -= IT;
       }
@@ -503,26 +526,24 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
       if (++stage == stages) stage = 0;
     }
     if constexpr (Epi::kWgrad) {
-      // ---- flush of the fused weight gradient: quadrant 0 holds rows c = 0..31 of every chunk, lane 0 of quadrant 1 the
-      // ones row (bias gradient).  rank = chunk.  Staged in the (idle) first TMA stage, then one rotated vector flush.
+      // ---- flush of the fused weight gradient: lane n of quadrant q holds row (chunk q, column n): 32 channels and the ones
+      // column (bias gradient).  One warp per quadrant stages it (BatchNorm fold applied) in the idle first TMA stage, then
+      // every epilogue thread takes part in one rotated vector flush.
       asm volatile("bar.sync 4, 512;" ::: "memory");              // every epilogue warp is done with the stages' extra boxes
-      if (quad < 2) {
-        float* stg = reinterpret_cast<float*>(a_s);                 // [n_chunks*16... rows (chunk>>1)*32 + c][64] fp32
-        float* db_s = stg + 4096 * 2;                               // [64] bias gradient (taps <= 4 -> <= 8192 floats above)
-        const int et = (quad * PGT_EPI_RANKS + rank) * 32 + lane;   // 0..255
+      float* stg = reinterpret_cast<float*>(a_s);                   // [(tap j) * 32 + c][64] fp32
+      float* db_s = stg + 4096 * 2;                                 // [64] bias gradient (taps <= 4 -> <= 8192 floats above)
+      if (rank == 0) {
         mbar_wait(wfull, 0u);
         tc_fence_after();
-        float v[32];
-        if (rank < n_chunks) tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + 128u + 32u * (uint32_t)rank, v);
-        if (quad == 1 && rank < 2 && lane == 0) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) db_s[32 * rank + j] = v[j];
-        }
-        asm volatile("bar.sync 3, 256;" ::: "memory");
-        if (quad == 0 && rank < n_chunks) epi.wgrad_row(rank, lane, v, db_s, stg);
-        asm volatile("bar.sync 3, 256;" ::: "memory");
-        epi.wgrad_flush(stg, db_s, n_chunks, et, 256);
+        float v[32], o[32];
+        const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + 128u;
+        tmem_ld32(ta + 32u, o);                                   // (columns 32..47 are live; 48..63 allocated, unused)
+        const float db = o[0];
+        tmem_ld32(ta, v);
+        epi.wgrad_row_t(quad, lane, v, db, db_s, stg);
       }
+      asm volatile("bar.sync 4, 512;" ::: "memory");
+      epi.wgrad_flush(stg, db_s, n_chunks, (warp - PGT_EPI_WARP0) * 32 + lane, 32 * PGT_EPI_WARPS);
     }
     epi.finish(red_s);
   }

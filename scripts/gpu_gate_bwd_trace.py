@@ -4,7 +4,7 @@ import os, sys
 sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), '..')))
 import torch
 dev = 'cuda'
-trace = torch.zeros(48 * 8, device=dev, dtype=torch.int64)
+trace = torch.zeros(48 * 16, device=dev, dtype=torch.int64)
 os.environ['GWN_PG_TRACE'] = str(trace.data_ptr())
 from multimodal_outage_b200 import ops
 bf = torch.bfloat16
@@ -23,11 +23,11 @@ for it in range(2):
     trace.zero_()
     torch.autograd.backward([u, zl], [torch.randn_like(u), torch.randn_like(zl)])
     torch.cuda.synchronize()
-t = trace.cpu().reshape(48, 8)
+t = trace.cpu().reshape(48, 16)
 t0 = t[0, 0].item()
-names = ['prod_got_empty', 'prod_issued', 'mma_got_tempty', 'mma_got_full', 'mma_issued', 'epi_got_tfull', 'epi_done']
-print('tile ' + ' '.join(f'{n:>15s}' for n in names))
+names = ['prod_got_empty', 'prod_issued', 'mma_got_tempty', 'mma_got_full', 'mma_issued', 'epi_got_tfull', 'epi_done', 'epi_ldtm', '-', '-', 'epi_computed']
+print('tile ' + ' '.join(f'{n:>14s}' for n in names))
 for k in range(0, 30):
     if t[k, 0].item() == 0:
         break
-    print(f'{k:4d} ' + ' '.join(f'{(t[k, j].item() - t0) if t[k, j].item() else 0:15d}' for j in range(7)))
+    print(f'{k:4d} ' + ' '.join(f'{(t[k, j].item() - t0) if t[k, j].item() else 0:14d}' for j in range(11)))

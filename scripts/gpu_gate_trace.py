@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), '..')))
 import torch
 dev = 'cuda'
-trace = torch.zeros(48 * 8, device=dev, dtype=torch.int64)
+trace = torch.zeros(48 * 16, device=dev, dtype=torch.int64)
 os.environ['GWN_PG_TRACE'] = str(trace.data_ptr())
 from multimodal_outage_b200 import ops
 bf = torch.bfloat16
@@ -15,9 +15,9 @@ w_fg = torch.randn(64, 64, device=dev) / 8; b_fg = torch.zeros(64, device=dev)
 for _ in range(2):
     ops.layer_fwd(u_prev, None, None, w_fg, b_fg, None, None, [], None, None, mats, 1, 2, 1, 2, os.environ.get("GATE_TRAIN", "1") == "1", False, 0.0, 0, 0)
 torch.cuda.synchronize()
-t = trace.cpu().reshape(48, 8)
+t = trace.cpu().reshape(48, 16)
 t0 = t[0, 0].item()
-names = ['prod_got_empty', 'prod_issued', 'mma_got_tempty', 'mma_got_full', 'mma_issued', 'epi_got_tfull', 'epi_done']
-print('tile ' + ' '.join(f'{n:>15s}' for n in names))
+names = ['prod_got_empty', 'prod_issued', 'mma_got_tempty', 'mma_got_full', 'mma_issued', 'epi_got_tfull', 'epi_done', 'epi_ldtm', 'st_got_sfull', 'st_released', 'epi_computed']
+print('tile ' + ' '.join(f'{n:>14s}' for n in names))
 for k in range(2, 34):
-    print(f'{k:4d} ' + ' '.join(f'{(t[k, j].item() - t0) if t[k, j].item() else 0:15d}' for j in range(7)))
+    print(f'{k:4d} ' + ' '.join(f'{(t[k, j].item() - t0) if t[k, j].item() else 0:14d}' for j in range(11)))
