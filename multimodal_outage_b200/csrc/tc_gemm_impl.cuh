@@ -132,14 +132,15 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
   const int SUB = p.sub;
   const int NB = n_chunks + p.n_extra;                         // TMA boxes per sub-tile (MMA chunks + epilogue extras)
   // one stage: SUB x NB boxes of 128 x 64 B (+ the resident ones atom of the fused weight gradient, SUB == 1 there)
-  const uint32_t a_bytes = ((uint32_t)NB * (uint32_t)SUB + (Epi::kWgrad ? 1u : 0u)) * 8192u;
+  const uint32_t a_bytes = (uint32_t)NB * (uint32_t)SUB * 8192u;
   const uint32_t w_bytes = ((uint32_t)K8 * (uint32_t)N * 16u + 1023u) & ~1023u;
   uint8_t* a_s = smem;                                        // stages first (1024-aligned boxes)
-  // (kWgrad: 16 KB of slack after the ring - the M = 128 weight-gradient MMA of the last stage reads two atoms past the ones atom)
+  // (kWgrad: ONE 8 KB "ones" atom behind the ring, shared by every stage - the B descriptor's leading byte offset reaches it)
   constexpr int KOUT = epi_tma_out<Epi>::value;
   const int n_out = KOUT > 0 ? p.n_out : 0;                   // staged outputs of this launch (0: direct stores)
   constexpr uint32_t out_slot_bytes = (uint32_t)KOUT * 8192u;
-  uint8_t* out_s = smem + (size_t)stages * a_bytes + (Epi::kWgrad ? 16384 : 0);      // [slots][KOUT][128 rows][64 B]
+  uint8_t* wones_s = smem + (size_t)stages * a_bytes;
+  uint8_t* out_s = wones_s + (Epi::kWgrad ? 8192 : 0);           // [slots][KOUT][128 rows][64 B]
   uint8_t* w_s = out_s + (size_t)PGT_OUT_SLOTS * out_slot_bytes;
   uint8_t* ones_s = w_s + w_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ones_s + PGT_ONES_BYTES);
@@ -178,18 +179,15 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
     for (int i = tid; i < 256; i += PGT_THREADS) od[i] = i < 128 ? make_uint4(0x3F803F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
   }
   if constexpr (Epi::kWgrad) {
-    // ones atom behind the u_prev box of every stage: element (position k, channel 0) = 1.0; 64B swizzle puts logical
-    // 16-byte chunk 0 of row k at physical chunk ((k >> 1) & 3).  TMA never writes it.
-    for (int st = 0; st < stages; ++st) {
-      uint4* atom = reinterpret_cast<uint4*>(a_s + (size_t)st * a_bytes + (size_t)NB * 8192);
+    // ones atom: element (position k, channel 0) = 1.0; 64B swizzle puts logical 16-byte chunk 0 of row k at physical
+    // chunk ((k >> 1) & 3).
+    {
+      uint4* atom = reinterpret_cast<uint4*>(wones_s);
       for (int i = tid; i < 512; i += PGT_THREADS) atom[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
-    for (int st = 0; st < stages; ++st) {
-      uint8_t* atom = a_s + (size_t)st * a_bytes + (size_t)NB * 8192;
-      for (int k = tid; k < 128; k += PGT_THREADS)
-        *reinterpret_cast<uint16_t*>(atom + k * 64 + ((k >> 1) & 3) * 16) = 0x3F80u;   // bf16 1.0
-    }
+    for (int k = tid; k < 128; k += PGT_THREADS)
+      *reinterpret_cast<uint16_t*>(wones_s + k * 64 + ((k >> 1) & 3) * 16) = 0x3F80u;   // bf16 1.0
   }
   // Programmatic launch: barrier / TMEM / ones-atom set-up above overlapped the predecessor's tail.  The weight image below
   // is step-constant too UNLESS it folds the batch statistics the predecessor just produced (wsrc.bn == 1, training) or is
@@ -416,7 +414,8 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
             const uint64_t wt = tg::make_desc_sw(0, 8192u, 512u, 4u);
             const uint32_t idw = make_idesc_bf16(128, 48, true, true);
             const uint64_t aw = wt + (uint64_t)(sb >> 4);                                       // chunk boxes 0..3
-            const uint64_t bw = wt + (uint64_t)((sb + (uint32_t)(NB - 1) * 8192u) >> 4);       // u_prev box, then the ones atom
+            const uint32_t ub = sb + (uint32_t)(NB - 1) * 8192u;                               // u_prev box; next MN atom = the ones atom
+            const uint64_t bw = tg::make_desc_sw(ub, smem_u32(wones_s) - ub, 512u, 4u);
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)
               umma_bf16(tmem_base + 128u, aw + (uint64_t)(ks * 64), bw + (uint64_t)(ks * 64), idw, (g == 0 && ks == 0) ? 0u : 1u);
@@ -592,9 +591,9 @@ int launch_pos_gemm_tc(PgParams& p, const Epi& epi, cudaStream_t st) {
   int n_out = 0;
   if constexpr (KOUT > 0) n_out = epi.n_out();
   p.n_out = n_out;
-  const size_t fixed = w_bytes + PGT_ONES_BYTES + 1024 + 1024 + (Epi::kWgrad ? 16384 : 0) +   // alignment slack + barriers / scratch
+  const size_t fixed = w_bytes + PGT_ONES_BYTES + 1024 + 1024 + (Epi::kWgrad ? 8192 : 0) +    // alignment slack + barriers / scratch
                        (size_t)PGT_OUT_SLOTS * KOUT * 8192;
-  GWN_REQUIRE(fixed + 2 * (size_t)(NB + (Epi::kWgrad ? 1 : 0)) * 8192 <= 227 * 1024,
+  GWN_REQUIRE(fixed + 2 * (size_t)NB * 8192 <= 227 * 1024,
               "pos_gemm_tc: K=%d does not fit 2 stages in shared memory", 32 * p.n_chunks);
   if (Epi::kWgrad)
     GWN_REQUIRE(p.n_chunks == Epi::kFast && p.n_extra == 2 && p.N == 32 && p.n_chunks <= 4,
@@ -608,7 +607,7 @@ int launch_pos_gemm_tc(PgParams& p, const Epi& epi, cudaStream_t st) {
   for (int i = 0; i < 3; ++i) {
     const int sub = subs[i];
     if (2 * acc_c * sub > 512 || ((Epi::kWgrad || n_out > 0) && sub > 1)) continue;
-    const size_t ab = (size_t)NB * 8192 * sub + (Epi::kWgrad ? 8192 : 0);
+    const size_t ab = (size_t)NB * 8192 * sub;
     int stg = (int)((227 * 1024 - fixed) / ab);
     if (stg > 8) stg = 8;
     if (stg < (sub == 1 ? 2 : 3)) continue;
@@ -659,7 +658,7 @@ int launch_pos_gemm_tc(PgParams& p, const Epi& epi, cudaStream_t st) {
   {
     p.trace = trace_ptr("GWN_PG_TRACE");
   }
-  const size_t a_bytes = (size_t)NB * 8192 * p.sub + (Epi::kWgrad ? 8192 : 0);
+  const size_t a_bytes = (size_t)NB * 8192 * p.sub;
   const size_t smem = fixed + stages * a_bytes;
   if (p.wsrc.W) {
     GWN_REQUIRE(32 * p.n_chunks * p.N <= 16 * PGT_THREADS && p.N % 4 == 0 && p.wsrc.ld % 4 == 0,
