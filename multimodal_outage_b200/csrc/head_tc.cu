@@ -44,6 +44,22 @@ struct EpiBiasReluBf16 {   // out[m][n] = relu(acc + bias[n]) (bf16); split: als
       for (int j = 0; j < 32; ++j) v[j] -= __bfloat162float(__float2bfloat16_rn(v[j]));
       store_bf16x32(out + (long long)m * ldo + N + n0, v);
     }
+  }  // coalesced form (tma_gemm.cuh: kWarpScratch)
+  static constexpr bool kWarpScratch = true;
+  __device__ __forceinline__ void chunk_ws(int m0, int M, bool, int n0, float v[32], uint8_t* scr, int lane) const {
+    if (n0 >= N) return;
+    const int rows = M - m0 < 32 ? M - m0 : 32;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + __ldg(bias + n0 + j), 0.f);
+    uint4 q[4];
+    tg::pack_bf16x32(v, q);
+    tg::ws_store_rows64(scr, q, out + (long long)m0 * ldo + n0, ldo, rows, lane);
+    if (split) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] -= __bfloat162float(__float2bfloat16_rn(v[j]));
+      tg::pack_bf16x32(v, q);
+      tg::ws_store_rows64(scr, q, out + (long long)m0 * ldo + N + n0, ldo, rows, lane);
+    }
   }
 };
 
@@ -82,6 +98,31 @@ struct EpiMaskColsum {     // out = acc . [mask > 0] (bf16); colsum[n] += sum_m 
     const int lane = threadIdx.x & 31;
     const float s = warp_column_sums(v, lane);
     atomicAdd(colsum + n0 + lane, s);
+  }  static constexpr bool kWarpScratch = true;
+  __device__ __forceinline__ void chunk_ws(int m0, int M, bool m_ok, int n0, float v[32], uint8_t* scr, int lane) const {
+    if (n0 >= N) return;
+    const int rows = M - m0 < 32 ? M - m0 : 32;
+    uint4 mq[4];
+    tg::ws_load_rows64(scr, mq, mask + (long long)m0 * ldm + n0, ldm, rows, lane);
+    if (m_ok) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t w[4] = {mq[j].x, mq[j].y, mq[j].z, mq[j].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {      // bf16 > 0  <=>  its 16 bits, read as a signed integer, are > 0
+          if ((int16_t)(w[i] & 0xFFFFu) <= 0) v[8 * j + 2 * i] = 0.f;
+          if ((int16_t)(w[i] >> 16) <= 0) v[8 * j + 2 * i + 1] = 0.f;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    }
+    uint4 q[4];
+    tg::pack_bf16x32(v, q);
+    tg::ws_store_rows64(scr, q, out + (long long)m0 * ld + n0, ld, rows, lane);
+    const float s = warp_column_sums(v, lane);
+    atomicAdd(colsum + n0 + lane, s);
   }
 };
 
@@ -90,6 +131,13 @@ struct EpiGroupBf16 {      // column group n0/32 -> its own [P,32] bf16 tensor
   __device__ __forceinline__ void chunk(int m, bool m_ok, int n0, float v[32]) const {
     if (!m_ok || n0 >= N) return;
     store_bf16x32(outs[n0 >> 5] + (long long)m * 32, v);
+  }  static constexpr bool kWarpScratch = true;
+  __device__ __forceinline__ void chunk_ws(int m0, int M, bool, int n0, float v[32], uint8_t* scr, int lane) const {
+    if (n0 >= N) return;
+    const int rows = M - m0 < 32 ? M - m0 : 32;
+    uint4 q[4];
+    tg::pack_bf16x32(v, q);
+    tg::ws_store_rows64(scr, q, outs[n0 >> 5] + (long long)m0 * 32, 32, rows, lane);
   }
 };
 

@@ -20,6 +20,7 @@
 //   MN-major SW64 : ((4,n),(8,k)):((1,LBO),(4,SBO))     -> LBO = next slab, SBO = 512 B
 //   K-major  SW64 : ((8,m),(T,2)):((4T,SBO),(1,T))      -> SBO = 512 B, K=16 step = +32 B, next slab = +rows*64 B
 #pragma once
+#include <type_traits>
 #include <cuda.h>
 
 #include "tc.cuh"
@@ -29,8 +30,16 @@ namespace gwn {
 enum { TG_K_SW128 = 0, TG_MN_SW128 = 1, TG_MN_SW64 = 2, TG_K_SW64 = 3 };
 
 constexpr int TG_BM = 128, TG_BK = 64;
-constexpr int TG_EPI_WARPS = 4;
-constexpr int TG_THREADS = 32 * (2 + TG_EPI_WARPS);   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+// Epilogue warps: TG_EPI_WARPS / 4 "ranks" per TMEM lane quadrant, the tile's 64-column pairs dealt round-robin to the
+// ranks.  With one rank, an epilogue that loads from global memory (relu masks of the head's data gradients) exposes one
+// HBM round trip per 32-column chunk: 34 us for a K = 32 GEMM whose traffic takes 11.  (GWN_TG_EPI_WARPS: A/B builds.)
+#ifndef GWN_TG_EPI_WARPS
+#define GWN_TG_EPI_WARPS 16
+#endif
+constexpr int TG_EPI_WARPS = GWN_TG_EPI_WARPS;
+constexpr int TG_EPI_RANKS = TG_EPI_WARPS / 4;
+static_assert(TG_EPI_WARPS % 4 == 0 && TG_EPI_WARPS >= 4 && TG_EPI_WARPS <= 16, "epilogue warps come in groups of four (TMEM lane quadrants)");
+constexpr int TG_THREADS = 32 * (2 + TG_EPI_WARPS);   // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 
 struct TgOperand {
   int mode;
@@ -97,7 +106,56 @@ __device__ __forceinline__ void load_operand(const TgOperand& o, const CUtensorM
     tma_3d(dst, map, 0, mn0, k0 >> 5, bar);
   }
 }
+// ---- warp-private staging of a 32-row x 64-byte chunk (one row per lane <-> four lanes per row) ----
+// The accumulator layout gives a thread one ROW, so a per-thread 16-byte global access touches 32 different rows per warp
+// instruction: 32 LSU wavefronts for 512 bytes.  Through a 2 KB swizzled scratch (conflict-free in both directions) the warp
+// instead moves 8 rows x 64 contiguous bytes per instruction - a quarter of the wavefronts.
+constexpr int TG_WS_BYTES = 2048;
+__device__ __forceinline__ uint32_t ws_off(int r, int c) { return (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4)); }
+// q[c] = 16-byte piece c of this lane's row  ->  global rows g0 + r * ld (elements), rows [0, rows_valid)
+__device__ __forceinline__ void ws_store_rows64(uint8_t* scr, const uint4 q[4], bf16* g0, long long ld, int rows_valid, int lane) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(scr + ws_off(lane, c)) = q[c];
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = 8 * i + (lane >> 2), c = lane & 3;
+    const uint4 x = *reinterpret_cast<const uint4*>(scr + ws_off(r, c));
+    if (r < rows_valid) *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(g0 + (long long)r * ld) + c * 16) = x;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void ws_load_rows64(uint8_t* scr, uint4 q[4], const bf16* g0, long long ld, int rows_valid, int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = 8 * i + (lane >> 2), c = lane & 3;
+    uint4 x = make_uint4(0u, 0u, 0u, 0u);
+    if (r < rows_valid) x = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(g0 + (long long)r * ld) + c * 16));
+    *reinterpret_cast<uint4*>(scr + ws_off(r, c)) = x;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < 4; ++c) q[c] = *reinterpret_cast<const uint4*>(scr + ws_off(lane, c));
+  __syncwarp();
+}
+__device__ __forceinline__ void pack_bf16x32(const float v[32], uint4 q[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
+    __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+    __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+    q[j].x = *reinterpret_cast<uint32_t*>(&h0); q[j].y = *reinterpret_cast<uint32_t*>(&h1);
+    q[j].z = *reinterpret_cast<uint32_t*>(&h2); q[j].w = *reinterpret_cast<uint32_t*>(&h3);
+  }
+}
 }  // namespace tg
+
+// Epilogue functors with `static constexpr bool kWarpScratch = true` are called as
+//   void chunk_ws(int m0, int M, bool m_ok, int n0, float v[32], uint8_t* scratch, int lane);
+// m0 = row of the warp's lane 0, scratch = the warp's private TG_WS_BYTES of shared memory (tg::ws_* helpers).
+template <typename E, typename = void> struct epi_warp_scratch { static constexpr bool value = false; };
+template <typename E> struct epi_warp_scratch<E, std::void_t<decltype(E::kWarpScratch)>> { static constexpr bool value = E::kWarpScratch; };
 
 // Epilogue functor contract (one thread = one accumulator row):
 //   void chunk(int m, bool m_ok, int n0, float v[32]);   32 consecutive columns [n0, n0+32) of row m
@@ -205,7 +263,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     }
     __syncwarp();
   } else {
-    const int quad = warp & 3;
+    const int quad = warp & 3, rank = (warp - 2) >> 2;
     int tcount = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const int mt = tile % p.m_tiles, rest = tile / p.m_tiles;
@@ -216,19 +274,31 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       const int m = mt * TG_BM + quad * 32 + lane;
       const bool m_ok = m < p.M;
       const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * acc_cols;
-      for (int c0 = 0; c0 < p.bn; c0 += 64) {
-        uint32_t r[2][32];
-        tmem_ld32_issue(t0 + (uint32_t)c0, r[0]);
-        if (c0 + 32 < p.bn) tmem_ld32_issue(t0 + (uint32_t)c0 + 32u, r[1]);
-        tmem_ld_wait();
-        float v[32];
+      if constexpr (TG_EPI_RANKS > 1) {
+        // several ranks per quadrant: one 32-column chunk at a time (the other ranks' chunks hide this one's latencies)
+        for (int c0 = 32 * rank; c0 < p.bn; c0 += 32 * TG_EPI_RANKS) {
+          float v[32];
+          tmem_ld32(t0 + (uint32_t)c0, v);
+          if constexpr (epi_warp_scratch<Epi>::value)
+            epi.chunk_ws(m - lane, p.M, m_ok, nt * p.bn + c0, v, smem + (size_t)ST * stage_bytes + 256 + (size_t)(warp - 2) * TG_WS_BYTES, lane);
+          else
+            epi.chunk(m, m_ok, nt * p.bn + c0, v);
+        }
+      } else {
+        for (int c0 = 0; c0 < p.bn; c0 += 64) {
+          uint32_t r[2][32];
+          tmem_ld32_issue(t0 + (uint32_t)c0, r[0]);
+          if (c0 + 32 < p.bn) tmem_ld32_issue(t0 + (uint32_t)c0 + 32u, r[1]);
+          tmem_ld_wait();
+          float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[0][j]);
-        epi.chunk(m, m_ok, nt * p.bn + c0, v);
-        if (c0 + 32 < p.bn) {
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[0][j]);
+          epi.chunk(m, m_ok, nt * p.bn + c0, v);
+          if (c0 + 32 < p.bn) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[1][j]);
-          epi.chunk(m, m_ok, nt * p.bn + c0 + 32, v);
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[1][j]);
+            epi.chunk(m, m_ok, nt * p.bn + c0 + 32, v);
+          }
         }
       }
       tc_fence_before();
@@ -273,11 +343,14 @@ int launch_tma_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, TgParams& 
   p.kb_per_split = (int)cdiv(p.k_blocks, p.splits);
   p.splits = (int)cdiv(p.k_blocks, p.kb_per_split);
   const size_t stage = (size_t)p.a.tile_bytes + p.b.tile_bytes;
-  int stages = (int)((size_t)(224 * 1024 - 1024 - 256) / stage);
+  constexpr bool kWS = epi_warp_scratch<Epi>::value;
+  static_assert(!kWS || TG_EPI_RANKS > 1, "warp-scratch epilogues use the one-chunk-at-a-time epilogue loop");
+  const size_t ws_bytes = kWS ? (size_t)TG_EPI_WARPS * tg::TG_WS_BYTES : 0;
+  int stages = (int)((size_t)((kWS ? 227 : 224) * 1024 - 1024 - 256 - ws_bytes) / stage);
   if (stages > 6) stages = 6;
   GWN_REQUIRE(stages >= 2, "tma_gemm: tile does not fit 2 stages");
   p.stages = stages;
-  const size_t smem = stages * stage + 1024 + 256;
+  const size_t smem = stages * stage + 1024 + 256 + ws_bytes;
   static bool attr_set = false;
   if (!attr_set) {
     GWN_CUDA(cudaFuncSetAttribute(tma_gemm_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
