@@ -32,7 +32,7 @@ __host__ __device__ inline GtLayout gt_layout(int KT, int NP, int NU) {
   L.m_off = L.w_off + 4u * (uint32_t)NU * 16u;             // [4][NU][16 B]
   L.s_off = L.m_off + 32u * 12u * 4u;                      // keep-bits [32 ch][12 words]
   L.bar_off = L.s_off + 256u;                              // statistics scratch [64]
-  L.total = L.bar_off + 144u;
+  L.total = L.bar_off + 160u;
   return L;
 }
 
@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gcn_fwd_t_kernel(const __grid_c
   uint64_t* ub_full = bars + 14;      // U tile, column half b = chunks 4..NM (TMEM columns [128,224)): GEMM 1 of one half
   uint64_t* ub_empty = bars + 15;     // runs under the staging of the other
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* a_half = bars + 17;       // chunks 0..3 of the whole group are staged: GEMM 2 may start on K rows [0, 256)
   uint32_t* kbits = reinterpret_cast<uint32_t*>(smem + L.m_off);       // [32 ch][12 words over the group's 384 rows]
   float* sscr = reinterpret_cast<float*>(smem + L.s_off);
 
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gcn_fwd_t_kernel(const __grid_c
     // ~2,400 serialised updates of the barrier words on the shared-memory pipe per group
     mbar_init(m_free, 8); mbar_init(m_full, 2);
     mbar_init(ua_full, 1); mbar_init(ua_empty, 8); mbar_init(ub_full, 1); mbar_init(ub_empty, 8);
-    mbar_init(a_full, 8); mbar_init(a_empty, 1);
+    mbar_init(a_full, 8); mbar_init(a_empty, 1); mbar_init(a_half, 8);
     fence_barrier_init();
     tg::tma_prefetch_desc(&zmap);
   }
@@ -226,13 +227,26 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gcn_fwd_t_kernel(const __grid_c
       }
       const int b = gi & 1;
       GT_TRACE(1);
+      // GEMM 2 in two K parts: rows k = j V + v < 256 belong to chunks j <= 3, whose staging (column half a) ends one hand-off
+      // before the group's last one - the first 16 K steps run under the staging of the last tile's column half b
+      const int ks_half = (NB_COLS > 0 && 4 * V >= 256 && ksteps > 16) ? 16 : 0;
+      const uint32_t d = tmem_base + TD + (uint32_t)b * 128u;
+      if (ks_half > 0) {
+        mbar_wait(a_half, (uint32_t)(gi & 1));
+        mbar_wait(&d_empty[b], (uint32_t)(((gi >> 1) & 1) ^ 1));
+        tc_fence_after();
+        if (elect_one()) {
+          for (int ks = 0; ks < ks_half; ++ks)
+            umma_bf16(d, au + (uint64_t)(16 * ks), bm + (uint64_t)ks * bstep, idesc2, ks == 0 ? 0u : 1u);
+        }
+        __syncwarp();
+      }
       mbar_wait(a_full, (uint32_t)(gi & 1));
       GT_TRACE(2);
-      mbar_wait(&d_empty[b], (uint32_t)(((gi >> 1) & 1) ^ 1));
+      if (ks_half == 0) mbar_wait(&d_empty[b], (uint32_t)(((gi >> 1) & 1) ^ 1));
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t d = tmem_base + TD + (uint32_t)b * 128u;
-        for (int ks = 0; ks < ksteps; ++ks)
+        for (int ks = ks_half; ks < ksteps; ++ks)
           umma_bf16(d, au + (uint64_t)(16 * ks), bm + (uint64_t)ks * bstep, idesc2, ks == 0 ? 0u : 1u);
         umma_commit(a_empty);
         umma_commit(&d_full[b]);
@@ -283,6 +297,11 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gcn_fwd_t_kernel(const __grid_c
           if (lane == 0) mbar_arrive(half == 0 ? ua_empty : ub_empty);   // the half is in registers: GEMM 1 may overwrite it
           if (valid && l1) put(j, ra);
           if (valid && l2) put(j2, rb);
+          if (half == 0 && t == GT_TILES - 1) {                      // column half a of the whole group is in shared memory
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_half);
+          }
         }
       }
       fence_proxy_async();

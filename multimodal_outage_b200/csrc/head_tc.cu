@@ -239,11 +239,11 @@ static int wgrad_gemm(const bf16* A, int lda, int M, const bf16* B, int ldb, int
   const int bn = N >= 256 ? 256 : (N >= 128 ? 128 : 64);
   p.M = M; p.N = N; p.K = (int)P; p.bn = bn;
   const long long tiles = cdiv(M, 128) * cdiv(N, bn);
-  // split-K over positions: enough CTAs to fill the GPU, but >= 16 K blocks per split so the fp32 atomic tail
-  // (128 x bn atomics per CTA) stays small next to the streaming
+  // split-K over positions: enough CTAs to fill the GPU, but >= 8 K blocks per split so the fp32 atomic tail
+  // (128 x bn vector reductions per CTA) stays small next to the streaming (16 left the skip GEMM on 64 CTAs)
   long long splits = cdiv(tg_sm_count(), tiles);
   const long long kb = cdiv(P, TG_BK);
-  if (splits > kb / 16) splits = kb / 16;
+  if (splits > kb / 8) splits = kb / 8;
   if (splits < 1) splits = 1;
   p.splits = (int)splits;
   tg_operand(p.a, TG_MN_SW128, 128);
