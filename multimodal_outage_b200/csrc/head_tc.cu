@@ -167,16 +167,32 @@ struct CvtJobs { CvtJob j[3]; int n; };
 __global__ void cvt_weights_kernel(CvtJobs jobs) {
   pdl_wait();      // programmatic launch: the launch latency overlaps the predecessor (common.cuh)
   pdl_trigger();
-  for (int q = 0; q < jobs.n; ++q) {
-    const CvtJob J = jobs.j[q];
-    const int total = J.R * J.C;            // (weights: far below 2^31; 32-bit index math - a 64-bit division costs hundreds of cycles)
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+  // one flat index space over the jobs: every thread has its (few) loads in flight at once - with one job after the other a
+  // thread paid an L2 round trip per job (8.7 us for 213k elements)
+  const int t0 = jobs.j[0].R * jobs.j[0].C;   // (weights: far below 2^31; 32-bit index math - a 64-bit division costs hundreds of cycles)
+  const int t1 = t0 + (jobs.n > 1 ? jobs.j[1].R * jobs.j[1].C : 0);
+  const int t2 = t1 + (jobs.n > 2 ? jobs.j[2].R * jobs.j[2].C : 0);
+  constexpr int U = 2;
+  const int stride = gridDim.x * blockDim.x;
+  for (int e0 = blockIdx.x * blockDim.x + threadIdx.x; e0 < t2; e0 += U * stride) {
+    float x[U]; int q[U], idx[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int e = e0 + u * stride;
+      q[u] = e < t0 ? 0 : (e < t1 ? 1 : 2);
+      idx[u] = e - (q[u] == 0 ? 0 : (q[u] == 1 ? t0 : t1));
+      x[u] = e < t2 ? __ldg(jobs.j[q[u]].src + idx[u]) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (e0 + u * stride >= t2) break;
+      const CvtJob& J = jobs.j[q[u]];
+      const int i = idx[u];
       const int r = i / J.C, c = i - r * J.C;
-      const float x = __ldg(J.src + i);
-      const bf16 hi = __float2bfloat16_rn(x);
+      const bf16 hi = __float2bfloat16_rn(x[u]);
       const int o = J.transpose ? c * J.ld + r : r * J.ld + c;
       J.dst[o] = hi;
-      if (J.lo_off >= 0) J.dst[o + J.lo_off] = __float2bfloat16_rn(x - __bfloat162float(hi));
+      if (J.lo_off >= 0) J.dst[o + J.lo_off] = __float2bfloat16_rn(x[u] - __bfloat162float(hi));
       if (J.hi2_off >= 0) J.dst[o + J.hi2_off] = hi;
     }
   }
@@ -343,7 +359,7 @@ extern "C" int gwn_head_bwd_tc(const gwn_head_cfg* c, const gwn_head_tc_bwd_args
   const bf16* zcat = reinterpret_cast<const bf16*>(a->zcat);
   {
     long long items = P * (Opad / 32);
-    long long blocks = cdiv(items, 8 * 16);
+    long long blocks = cdiv(items, 8 * 4);       // (every item is one dependent gather: 16 per warp took 10 us for 1.6 MB)
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
     GWN_CUDA(launch_pdl(dout_to_cl_kernel, dim3((unsigned)blocks), dim3(256), 0, st, a->dout, d_o, a->db_end2, P, c->O, c->V, c->Lf, Opad));

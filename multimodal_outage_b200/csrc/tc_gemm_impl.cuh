@@ -88,9 +88,11 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 #ifdef GWN_TRACE     // clock64 timeline of CTA 0, 16 slots per tile (scripts/gpu_gate_trace.py); compiled out of release builds
-#define PG_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && g < 48) p.trace[g * 16 + (slot)] = clock64(); } while (0)
+#define PG_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && g < 47) p.trace[g * 16 + (slot)] = clock64(); } while (0)
+#define PG_MARK(k) do { if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[47 * 16 + (k)] = clock64(); } while (0)   // kernel phases
 #else
 #define PG_TRACE(slot) do { } while (0)
+#define PG_MARK(k) do { } while (0)
 #endif
 
 // (sample, 128-row tile inside the sample) of a CTA's current macro tile, advanced without divisions: a 32-bit
@@ -126,6 +128,7 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  PG_MARK(0);
   const int N = p.N;
   const int n_chunks = NCH > 0 ? NCH : p.n_chunks;
   const int K8 = n_chunks * 4 + (p.has_bias ? 2 : 0);        // 16-byte K pieces per weight row
@@ -210,7 +213,9 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
       }
     }
   }
+  PG_MARK(1);
   if (pdl_early) { pdl_wait(); pdl_trigger(); }
+  PG_MARK(2);
   // ===================== TMA producers (warps PROD_A / PROD_B; boxes of a macro tile dealt alternately to the two warps; the
   // whole warp walks the loop so addresses / coordinates stay in uniform registers, one elected lane issues).  A resumable
   // routine: the gated conv's prologue calls it for the first ring of stages BEFORE the weight image is built (the loads'
@@ -355,6 +360,7 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  PG_MARK(3);
   const uint32_t tmem_base = *tmem_slot;
   const int acc_mask = n_acc - 1, acc_shift = n_acc == 4 ? 2 : 1;
 
@@ -548,6 +554,7 @@ __global__ void __launch_bounds__(PGT_THREADS, 1) pos_gemm_tc_kernel(const __gri
   }
   tc_fence_before();
   __syncthreads();
+  PG_MARK(4);
   if (warp == 0) epi.flush(red_s, lane);
   if (warp == PGT_MMA_WARP) {
     tc_fence_after();

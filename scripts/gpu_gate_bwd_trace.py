@@ -31,3 +31,7 @@ for k in range(0, 30):
     if t[k, 0].item() == 0:
         break
     print(f'{k:4d} ' + ' '.join(f'{(t[k, j].item() - t0) if t[k, j].item() else 0:14d}' for j in range(11)))
+
+m = t[47]
+print('kernel phases (cycles from entry): prologue set-up', m[1].item() - m[0].item(), ' pdl wait', m[2].item() - m[1].item(), ' image build', m[3].item() - m[2].item(),
+      ' first producer event', t0 - m[0].item(), ' all tiles done', m[4].item() - m[0].item())

@@ -19,5 +19,9 @@ t = trace.cpu().reshape(48, 16)
 t0 = t[0, 0].item()
 names = ['prod_got_empty', 'prod_issued', 'mma_got_tempty', 'mma_got_full', 'mma_issued', 'epi_got_tfull', 'epi_done', 'epi_ldtm', 'st_got_sfull', 'st_released', 'epi_computed']
 print('tile ' + ' '.join(f'{n:>14s}' for n in names))
-for k in range(2, 34):
+for k in range(0, 34):
     print(f'{k:4d} ' + ' '.join(f'{(t[k, j].item() - t0) if t[k, j].item() else 0:14d}' for j in range(11)))
+
+m = t[47]
+print('kernel phases (cycles from entry): prologue set-up', m[1].item() - m[0].item(), ' pdl wait', m[2].item() - m[1].item(), ' image build', m[3].item() - m[2].item(),
+      ' first producer event', t0 - m[0].item(), ' all tiles done', m[4].item() - m[0].item())

@@ -27,3 +27,10 @@ t0 = min(e.time_range.start for e in ev); t1 = max(e.time_range.end for e in ev)
 print(f'{key}: {R} replays: kernel time sum {tot/R:.0f} us/step, span {(t1-t0)/R:.0f} us/step, {len(ev)/R:.0f} device activities/step')
 for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
     print(f'{t/R:9.1f} us {c/R:6.1f}x  {k}')
+
+if os.environ.get('PER_INSTANCE'):        # durations of every launch of the main kernel families, in launch order (one replay)
+    fams = ['gcn_bwd_t', 'gcn_fwd_t', 'EpiGateBwdTC', 'EpiGateTC', 'bn_bwd']
+    ev1 = sorted(ev, key=lambda e: e.time_range.start)
+    n1 = len(ev1) // R
+    for f in fams:
+        print(f, ' '.join(f'{e.device_time:.1f}' for e in ev1[:n1] if f in e.name))
