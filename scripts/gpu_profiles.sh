@@ -15,6 +15,7 @@ cap() { timeout 400 ncu --set full --clock-control none --import-source on -k re
         ncu -i $out/$3.ncu-rep --page details --csv > $out/$3_details.csv 2>/dev/null; rm -f $out/$3.ncu-rep; }
 cap "gcn_bwd_t_kernel" 20 gcn_bwd_t_L0
 cap "gcn_fwd_t_kernel" 16 gcn_fwd_t_L0
-cap "EpiGateTC" 16 gate_fwd_L0
-cap "EpiGateBwdTC" 23 gate_bwd_L0
+# (-k matches the base name: 16 pos_gemm_tc launches per step - 8 gate forwards, then 8 gate data gradients, layer 0 last)
+cap "pos_gemm_tc_kernel" 32 gate_fwd_L0
+cap "pos_gemm_tc_kernel" 47 gate_bwd_L0
 ls -la $out

@@ -1,5 +1,5 @@
 cd "$(dirname "$0")/.."
-out=gpurun_out/prof_r2g
+out=gpurun_out/prof_${1:-r2g}
 mkdir -p $out
 B="python bench.py --steps 2 --warmup 1 --no-cpu --no-roofline --no-extra"
 cap() { timeout 400 ncu --set full --clock-control none --import-source on -k regex:"$1" -s $2 -c 1 -o $out/$3 $B > $out/ncu_$3.log 2>&1; \
