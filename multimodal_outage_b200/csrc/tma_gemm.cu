@@ -179,6 +179,53 @@ int launch_hop_big(const bf16* img, int Vp, const bf16* X, bf16* Y, const bf16* 
 }
 
 // ------------------------------------------------------------------------------------------ sparse hop (ELL rows)
+// acc[0..7] += a * (the eight bf16 channels of q), fp32 throughout.  Packed fp32 FMA (fma.rn.f32x2: FFMA2 on sm_100, two
+// IEEE fp32 fused multiply-adds per instruction, the same results as two FFMAs) - the sparse hop is instruction-issue bound and
+// per channel pair this is shift + mask + one FFMA2 instead of shift + mask + two FFMAs.
+__device__ __forceinline__ void ell_fma8(uint64_t acc[4], float a, const uint4& q) {
+  const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+  uint64_t a2;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(a2) : "f"(a));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint64_t b2;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b2) : "r"(u[i] << 16), "r"(u[i] & 0xFFFF0000u));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[i]) : "l"(a2), "l"(b2));
+  }
+}
+__device__ __forceinline__ void ell_acc_init(uint64_t acc[4], const uint4& q) {   // acc = the eight bf16 channels of q
+  const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) asm("mov.b64 %0, {%1, %2};" : "=l"(acc[i]) : "r"(u[i] << 16), "r"(u[i] & 0xFFFF0000u));
+}
+__device__ __forceinline__ uint4 ell_acc_pack(const uint64_t acc[4]) {             // eight fp32 sums -> eight bf16 (rn)
+  uint4 o;
+  uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[i]));
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    ow[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return o;
+}
+// the four (index, value) pairs k0..k0+3 of an ELL row: one 16-byte load each when the row pitch allows it
+__device__ __forceinline__ void ell_row4(const int* ir, const float* vr, int k0, int W, bool vec, int v[4], float a[4]) {
+  if (vec) {
+    const int4 vi = __ldg(reinterpret_cast<const int4*>(ir + k0));
+    const float4 va = __ldg(reinterpret_cast<const float4*>(vr + k0));
+    v[0] = vi.x; v[1] = vi.y; v[2] = vi.z; v[3] = vi.w;
+    a[0] = va.x; a[1] = va.y; a[2] = va.z; a[3] = va.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool in = k0 + j < W;
+      v[j] = in ? __ldg(ir + k0 + j) : -1;
+      a[j] = in ? __ldg(vr + k0 + j) : 0.f;
+    }
+  }
+}
 // y[s, w, :] = sum_k val[w][k] * x[s, idx[w][k], :] (+ add[s, w, :]); thread = (row w, 8-channel piece), 64 rows per CTA,
 // blockIdx.y = slab.  The index / value rows are shared by every slab (L1 / L2 hits); x rows are 64-byte gathers that stay
 // in L2 (a slab of 3,100 nodes is 198 KB).  HBM traffic: x once, y once - a dense V x V GEMM at 0.3 % density does 300x the
@@ -249,51 +296,26 @@ __global__ void __launch_bounds__(1024) hop_ell_smem_kernel(const int* __restric
   pdl_trigger();
   extern __shared__ uint4 xs[];                    // [V][4] pieces of 8 channels
   const int tid = threadIdx.x, pc = tid & 3;
+  const bool vec = (W & 3) == 0 && ((reinterpret_cast<uintptr_t>(idx) | reinterpret_cast<uintptr_t>(val)) & 15) == 0;
   for (int s = blockIdx.x; s < slabs; s += gridDim.x) {
     const long long base = (long long)s * V;
     const uint4* src = reinterpret_cast<const uint4*>(X + base * 32);
     for (int i = tid; i < V * 4; i += 1024) xs[i] = __ldg(src + i);
     __syncthreads();
     for (int w = tid >> 2; w < V; w += 256) {
-      float acc[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-      if (add) {
-        const uint4 q = *(reinterpret_cast<const uint4*>(add + (base + w) * 32) + pc);
-        const uint32_t u[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { acc[2 * i] = __uint_as_float(u[i] << 16); acc[2 * i + 1] = __uint_as_float(u[i] & 0xFFFF0000u); }
-      }
+      uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
+      if (add) ell_acc_init(acc, *(reinterpret_cast<const uint4*>(add + (base + w) * 32) + pc));
       const int* ir = idx + (long long)w * W;
       const float* vr = val + (long long)w * W;
       for (int k0 = 0; k0 < W; k0 += 4) {
         int v[4]; float a[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const bool in = k0 + j < W;
-          v[j] = in ? __ldg(ir + k0 + j) : -1;
-          a[j] = in ? __ldg(vr + k0 + j) : 0.f;
-        }
+        ell_row4(ir, vr, k0, W, vec, v, a);
         if (v[0] < 0) break;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint4 q = v[j] >= 0 ? xs[v[j] * 4 + pc] : make_uint4(0u, 0u, 0u, 0u);
-          const uint32_t u[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            acc[2 * i] = fmaf(a[j], __uint_as_float(u[i] << 16), acc[2 * i]);
-            acc[2 * i + 1] = fmaf(a[j], __uint_as_float(u[i] & 0xFFFF0000u), acc[2 * i + 1]);
-          }
-        }
+        for (int j = 0; j < 4; ++j)      // pads inside a chunk: nothing is loaded, zeros are added
+          ell_fma8(acc, a[j], v[j] >= 0 ? xs[v[j] * 4 + pc] : make_uint4(0u, 0u, 0u, 0u));
       }
-      uint4 o;
-      uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        __nv_bfloat162 h = __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1]);
-        ow[i] = *reinterpret_cast<uint32_t*>(&h);
-      }
-      *(reinterpret_cast<uint4*>(Y + (base + w) * 32) + pc) = o;
+      *(reinterpret_cast<uint4*>(Y + (base + w) * 32) + pc) = ell_acc_pack(acc);
     }
     __syncthreads();                               // the slab buffer is reused by the next slab of this CTA
   }
@@ -327,16 +349,56 @@ int launch_hop_ell(const int* idx, const float* val, int W, const bf16* X, bf16*
 }
 
 // dA[v, w] += sum_{s,c} X[s,v,c] * G[s,w,c]   (nconv gradient wrt the support; adaptive adjacency only)
+//
+// Split-K: at V = 3100 the output is 25 x 13 = 325 tiles of 128 x 256 - 2.2 rounds of work for 148 persistent CTAs that take
+// 3 (each tile contracts over every slab: ~100 us).  With the slab range cut into `splits` parts the CTAs walk
+// 325 * splits smaller tiles (5 parts: 10.98 rounds of a fifth each) and add their partial sums with 16-byte vector
+// reductions; tiles of one part run together, so the CTAs still share operand boxes through L2.
 struct EpiAccF32 {
-  float* C; int ldc, N;
+  float* C; int ldc, N, atomic;
   __device__ __forceinline__ void chunk(int m, bool m_ok, int n0, float v[32]) const {
     if (!m_ok) return;
     float* dst = C + (long long)m * ldc + n0;
+    if (atomic) {
+      if (n0 + 32 <= N && (ldc & 3) == 0 && (reinterpret_cast<unsigned long long>(C) & 15ull) == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) red_add_v4(dst + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+        return;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < N) atomicAdd(dst + j, v[j]);
+      return;
+    }
 #pragma unroll
     for (int j = 0; j < 32; ++j)
       if (n0 + j < N) dst[j] += v[j];
   }
 };
+
+// Number of K parts that minimises the persistent grid's makespan, from a cost model fitted to B200 timings at V = 3100
+// (scripts/gpu_big_graph_bench.py): a CTA's share is ceil(tiles * s / sms) tiles of k_blocks / s K blocks at ~0.52 us each
+// plus ~5 us per tile (accumulator hand-off and the reductions' L2 traffic); the single-part form pays ~30 us per tile for its
+// row-per-thread read-modify-write epilogue instead.  768 slabs: 663 -> 508 us, 192 slabs: 287 -> 159 us.
+// GWN_DADJ_SPLITS overrides (A/B runs; 1 = the deterministic single-part form).
+static int dadj_splits(long long tiles, int k_blocks, int sms) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("GWN_DADJ_SPLITS");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced > 0) return forced;
+  if (tiles % sms == 0 || k_blocks < 32) return 1;    // nothing to balance / too little work per tile to cut
+  int best = 1;
+  double best_cost = 1e30;
+  for (int s = 1; s <= 8; ++s) {
+    if (s > 1 && k_blocks / s < 16) break;            // keep >= 16 K blocks (64 MMAs) per tile
+    const long long rounds = (tiles * s + sms - 1) / sms;
+    const double cost = (double)rounds * (0.52 * k_blocks / s + (s == 1 ? 30.0 : 5.0));
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
+  }
+  return best;
+}
 
 int launch_dadj_big(const bf16* X, const bf16* G, float* dA, long long slabs, int V, cudaStream_t st) {
   if (slabs <= 0) return 0;
@@ -346,10 +408,11 @@ int launch_dadj_big(const bf16* X, const bf16* G, float* dA, long long slabs, in
   if (int rc = tg_map_slabs(&mb, G, (uint64_t)V, (uint64_t)slabs, (uint32_t)bn, 2)) return rc;
   TgParams p{};
   GWN_REQUIRE(slabs * 32 < (1ll << 31), "dadj_big: too many slabs");
-  p.M = V; p.N = V; p.K = (int)(slabs * 32); p.bn = bn; p.splits = 1;
+  p.M = V; p.N = V; p.K = (int)(slabs * 32); p.bn = bn;
+  p.splits = dadj_splits(cdiv(V, TG_BM) * cdiv(V, bn), (int)cdiv(p.K, TG_BK), tg_sm_count());
   tg_operand(p.a, TG_K_SW64, 128);
   tg_operand(p.b, TG_K_SW64, bn);
-  EpiAccF32 e{dA, V, V};
+  EpiAccF32 e{dA, V, V, p.splits > 1 ? 1 : 0};
   return launch_tma_gemm(ma, mb, p, e, st);
 }
 

@@ -310,14 +310,16 @@ def register_sparse_support(A: Tensor, max_width: int = ELL_MAX_WIDTH) -> bool:
     if width > max_width:
         _ELL_REGISTRY.pop(A.data_ptr(), None)
         return False
+    # (row pitch rounded up to four entries: the hop kernel then reads a row's indices / values 16 bytes at a time)
+    pitch = min(V, (width + 3) // 4 * 4)
     def rows(M):                # M[w, v] != 0 -> neighbours v of output row w, padded with -1
-        order = torch.argsort((M == 0).to(torch.int8), dim=1, stable=True)[:, :width]       # non-zeros first, ascending v
+        order = torch.argsort((M == 0).to(torch.int8), dim=1, stable=True)[:, :pitch]       # non-zeros first, ascending v
         vals = torch.gather(M, 1, order)
         idx = torch.where(vals != 0, order, torch.full_like(order, -1)).to(torch.int32).contiguous()
         return idx, vals.contiguous()
     idx0, val0 = rows(A.t().contiguous())      # which = 0: y[w] = sum_v A[v, w] x[v]
     idx1, val1 = rows(A)                       # which = 1: y[w] = sum_v A[w, v] x[v]
-    _ELL_REGISTRY[A.data_ptr()] = dict(ref=weakref.ref(A), version=A._version, idx=(idx0, idx1), val=(val0, val1), width=width)
+    _ELL_REGISTRY[A.data_ptr()] = dict(ref=weakref.ref(A), version=A._version, idx=(idx0, idx1), val=(val0, val1), width=pitch)
     return True
 
 
