@@ -10,6 +10,7 @@
 #include <mutex>
 
 #include "tma_gemm.cuh"
+#include "tma_gemm2.cuh"
 #include "tma_hops.cuh"
 
 namespace gwn {
@@ -118,6 +119,15 @@ int tg_sm_count() {
   return sms;
 }
 
+bool tg2_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("GWN_TG2");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
 // ------------------------------------------------------------------------------------------ epilogues
 struct EpiHopBig {   // accumulator row = node w, column = (slab, channel)
   bf16* out; const bf16* add; int V; long long slabs;
@@ -173,8 +183,13 @@ int launch_hop_big(const bf16* img, int Vp, const bf16* X, bf16* Y, const bf16* 
   p.M = V; p.K = V; p.N = (int)(slabs * 32); p.bn = bn; p.splits = 1;
   GWN_REQUIRE(slabs * 32 < (1ll << 31), "hop_big: too many slabs");
   tg_operand(p.a, TG_K_SW128, 128);
-  tg_operand(p.b, TG_MN_SW64, bn);
   EpiHopBig e{Y, add, V, slabs};
+  if (bn == 256 && V > 128 && tg2_enabled()) {        // CTA pairs: 256 nodes x 8 slabs per tile, 4 slabs staged per CTA
+    if (int rc = tg_map_slabs(&mb, X, (uint64_t)V, (uint64_t)slabs, 64, 4)) return rc;
+    tg_operand(p.b, TG_MN_SW64, 128);
+    return launch_tma_gemm2(ma, mb, p, e, st);
+  }
+  tg_operand(p.b, TG_MN_SW64, bn);
   return launch_tma_gemm(ma, mb, p, e, st);
 }
 
@@ -381,7 +396,7 @@ struct EpiAccF32 {
 // plus ~5 us per tile (accumulator hand-off and the reductions' L2 traffic); the single-part form pays ~30 us per tile for its
 // row-per-thread read-modify-write epilogue instead.  768 slabs: 663 -> 508 us, 192 slabs: 287 -> 159 us.
 // GWN_DADJ_SPLITS overrides (A/B runs; 1 = the deterministic single-part form).
-static int dadj_splits(long long tiles, int k_blocks, int sms) {
+static int dadj_splits(long long tiles, int k_blocks, int sms, double us_per_kb = 0.52) {
   static int forced = -1;
   if (forced < 0) {
     const char* e = getenv("GWN_DADJ_SPLITS");
@@ -394,7 +409,7 @@ static int dadj_splits(long long tiles, int k_blocks, int sms) {
   for (int s = 1; s <= 8; ++s) {
     if (s > 1 && k_blocks / s < 16) break;            // keep >= 16 K blocks (64 MMAs) per tile
     const long long rounds = (tiles * s + sms - 1) / sms;
-    const double cost = (double)rounds * (0.52 * k_blocks / s + (s == 1 ? 30.0 : 5.0));
+    const double cost = (double)rounds * (us_per_kb * k_blocks / s + (s == 1 ? 30.0 : 5.0));
     if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
   }
   return best;
@@ -409,8 +424,15 @@ int launch_dadj_big(const bf16* X, const bf16* G, float* dA, long long slabs, in
   TgParams p{};
   GWN_REQUIRE(slabs * 32 < (1ll << 31), "dadj_big: too many slabs");
   p.M = V; p.N = V; p.K = (int)(slabs * 32); p.bn = bn;
-  p.splits = dadj_splits(cdiv(V, TG_BM) * cdiv(V, bn), (int)cdiv(p.K, TG_BK), tg_sm_count());
   tg_operand(p.a, TG_K_SW64, 128);
+  if (bn == 256 && tg2_enabled()) {                     // CTA pairs: 256 x 256 tiles, each CTA stages 128 rows of X and of G
+    if (int rc = tg_map_slabs(&mb, G, (uint64_t)V, (uint64_t)slabs, 128, 2)) return rc;
+    p.splits = dadj_splits(cdiv(V, 2 * TG_BM) * cdiv(V, bn), (int)cdiv(p.K, TG_BK), tg_sm_count() / 2, 0.75);
+    tg_operand(p.b, TG_K_SW64, 128);
+    EpiAccF32 e{dA, V, V, p.splits > 1 ? 1 : 0};
+    return launch_tma_gemm2(ma, mb, p, e, st);
+  }
+  p.splits = dadj_splits(cdiv(V, TG_BM) * cdiv(V, bn), (int)cdiv(p.K, TG_BK), tg_sm_count());
   tg_operand(p.b, TG_K_SW64, bn);
   EpiAccF32 e{dA, V, V, p.splits > 1 ? 1 : 0};
   return launch_tma_gemm(ma, mb, p, e, st);

@@ -46,6 +46,21 @@ for L in (12, 7, 3):
     fl = 2.0 * V * V * slabs * 32
     print(f'dadj_big slabs={slabs}: {us:8.1f} us  {fl / us * 1e-6:7.1f} TFLOP/s')
 
+# dense hop (adaptive support): y = Aop x over `slabs` slabs
+Ad = torch.softmax(torch.randn(V, V, device='cuda'), dim=1).contiguous()
+img = ops.support_images([Ad])
+for L in (12, 7, 3):
+    slabs = 64 * L
+    x = torch.randn(slabs, V, 32, device='cuda').to(torch.bfloat16)
+    y = torch.empty_like(x)
+    for which in range(2):
+        f = lambda: _lib.check(lib.gwn_hop_big(img.data_ptr(), 1, 0, which, x.data_ptr(), y.data_ptr(), None, slabs, V, st()), 'hop')  # noqa: E731
+        us = timed(f)
+        if L == 3:
+            ref = torch.einsum('vw,svc->swc' if which == 0 else 'wv,svc->swc', Ad.to(torch.bfloat16).float(), x.float())
+            print(f'  hop check which={which}: rel {rel(y, ref):.2e}')
+        print(f'hop_big slabs={slabs} which={which}: {us:8.1f} us  {2.0 * V * V * slabs * 32 / us * 1e-6:7.1f} TFLOP/s')
+
 A = torch.tensor(np.asarray(double_transition(synthetic_knn_graph(V))[0]), dtype=torch.float32, device='cuda').contiguous()
 assert ops.register_sparse_support(A)
 e = ops._ELL_REGISTRY[A.data_ptr()]
