@@ -921,6 +921,30 @@ def test_hop_and_support_gradient_at_3100_nodes():
     assert rel(dA, ref) < 1e-5, rel(dA, ref)
 
 
+@pytest.mark.parametrize('V,slabs', [(400, 80), (3100, 100)])
+def test_support_gradient_split_k_on_cta_pairs(V, slabs):
+    """`gwn_dadj_big` at slab counts where the launcher cuts the contraction into several parts (split-K over the slab
+    range, partial sums added with vector reductions) on the two-SM kernel: accumulates INTO dA, within 1e-5 of the fp64
+    einsum; and the two-SM hop at a slab count that is not a multiple of its 8-slab tile."""
+    from multimodal_outage_b200 import ops, _lib
+    lib = _lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    torch.manual_seed(4)
+    x = torch.randn(slabs, V, 32, device='cuda').to(torch.bfloat16)
+    g = torch.randn(slabs, V, 32, device='cuda').to(torch.bfloat16)
+    dA = torch.full((V, V), 0.5, device='cuda')
+    for _ in range(2):                                                       # two accumulating calls
+        _lib.check(lib.gwn_dadj_big(x.data_ptr(), g.data_ptr(), dA.data_ptr(), slabs, V, st), 'dadj')
+    ref = 0.5 + 2.0 * torch.einsum('svc,swc->vw', x.double(), g.double())
+    assert rel(dA, ref) < 1e-5, (V, slabs, rel(dA, ref))
+    A = torch.softmax(torch.randn(V, V, device='cuda') * 2, dim=1)
+    img = ops.support_images([A])
+    y = torch.empty_like(x)
+    refh = torch.einsum('vw,svc->swc', A.to(torch.bfloat16).double(), x.double())
+    _lib.check(lib.gwn_hop_big(img.data_ptr(), 1, 0, 0, x.data_ptr(), y.data_ptr(), None, slabs, V, st), 'hop')
+    assert rel(y, refh) < 4e-3, (V, slabs, rel(y, refh))
+
+
 def test_fused_dropout_statistics():
     """The in-kernel Philox stream (7 rounds, one byte per element): realised drop rate, per-channel and per-node
     uniformity and lag-1 independence over 1.1e7 draws, at the benchmark's p = 0.3 (realised as 77/256)."""
