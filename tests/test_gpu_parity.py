@@ -525,6 +525,16 @@ def test_bf16_whole_model_big_graph_310_nodes():
     _oracle_case(cfg, sup, n=2, t_in=12, seed=16, dtype=torch.bfloat16, tol=BF16_TOL)
 
 
+def test_bf16_whole_model_config3_structure_at_3100_nodes():
+    """BASELINE config 3's model (4 x 2 layers, fwd / bwd transition matrices of a 3,100-node kNN graph + adaptive support,
+    dropout masks) at the REAL graph size, forward + backward against the fp64 oracle: sparse fixed-support hops, the
+    two-SM hop GEMM (layers with >= 8 slabs) and the single-SM one (the short layers), Horner backward, support gradient.
+    Two samples keep the oracle's 3100 x 3100 products in the seconds."""
+    cfg = GWNetConfig(num_nodes=3100, in_dim=2, out_dim=12, kernel_size=2, blocks=4, layers=2, dropout=0.3)
+    sup = double_transition(synthetic_knn_graph(3100))
+    _oracle_case(cfg, sup, n=2, t_in=12, seed=17, dtype=torch.bfloat16, tol=BF16_TOL, masks=True)
+
+
 def test_tc_hop_kernel_every_image_variant():
     """gwn_hop_tc (tcgen05) against an fp64 einsum for A^T, (A^2)^T, A, A^2 images, ragged slab counts."""
     from multimodal_outage_b200 import ops
