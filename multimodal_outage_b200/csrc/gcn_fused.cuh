@@ -129,5 +129,4 @@ struct BtGeom {
 int gcn_bwd_t_image_elems(int V, int n_mats);
 int gcn_bwd_t_supported(int V, int n_mats, bool has_da);
 int launch_gcn_bwd_t(GcnBwdParams& p, cudaStream_t st);
-int launch_hop_mats_bt_prep(const float* const* supports, int n_supports, int V, bf16* out, cudaStream_t st);
 }  // namespace gwn

@@ -769,54 +769,6 @@ int gcn_bwd_t_supported(int V, int n_mats, bool has_da) {
   return bt_layout(G, has_da).total <= 227u * 1024u ? 1 : 0;
 }
 
-// Stacked transposed-hop image: B operand of GEMM H, K-major no-swizzle canonical layout [KW/8][NTOT][8] bf16:
-//   element (k = w, n = column of item (r, h), slot j_l, node v_l) = Mt_j[v, w],  j = 4h + j_l, v = 32 r + v_l
-__global__ void hop_mats_bt_prep_kernel(const float* A0, const float* A1, const float* A2, const float* A3, int n_sup, int V,
-                                        BtGeom G, bf16* __restrict__ out) {
-  pdl_wait();      // programmatic launch: the launch latency overlaps the predecessor (common.cuh)
-  pdl_trigger();
-  const float* As[4] = {A0, A1, A2, A3};
-  const int total = (G.KW / 8) * G.NTOT * 8;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int e = i & 7, n = (i >> 3) % G.NTOT, w = (i >> 3) / G.NTOT * 8 + e;
-    // decode n -> (r, h, j_l, v_l)
-    int r = -1, h = 0, jl = 0, vl = 0, n0 = 0;
-    for (int rr = 0; rr < G.NR && r < 0; ++rr)
-      for (int hh = 0; hh < G.NHALF; ++hh) {
-        const int cnt = G.nh(hh) * G.rs(rr);
-        if (n < n0 + cnt) { r = rr; h = hh; jl = (n - n0) / G.rs(rr); vl = (n - n0) - jl * G.rs(rr); break; }
-        n0 += cnt;
-      }
-    float val = 0.f;
-    if (r >= 0) {
-      const int j = 4 * h + jl, v = 32 * r + vl;
-      if (v < V && w < V && j <= 2 * n_sup) {
-        if (j == 0) val = (v == w) ? 1.f : 0.f;
-        else {
-          const float* A = As[(j - 1) >> 1];
-          if (((j - 1) & 1) == 0) val = A[(long long)v * V + w];
-          else {
-            float acc = 0.f;
-            for (int t = 0; t < V; ++t) acc = fmaf(A[(long long)v * V + t], A[(long long)t * V + w], acc);
-            val = acc;
-          }
-        }
-      }
-    }
-    out[i] = __float2bfloat16_rn(val);
-  }
-}
-
-int launch_hop_mats_bt_prep(const float* const* supports, int n_supports, int V, bf16* out, cudaStream_t st) {
-  const BtGeom G(2 * n_supports, bt_npd(V));
-  const int total = (G.KW / 8) * G.NTOT * 8;
-  const float* A[4] = {nullptr, nullptr, nullptr, nullptr};
-  for (int i = 0; i < n_supports && i < 4; ++i) A[i] = supports[i];
-  GWN_CUDA(launch_pdl(hop_mats_bt_prep_kernel, dim3((unsigned)cdiv(total, 256)), dim3(256), 0, st, A[0], A[1], A[2], A[3], n_supports, V, G, out));
-  GWN_LAUNCHED();
-  return 0;
-}
-
 int launch_gcn_bwd_t(GcnBwdParams& p, cudaStream_t st) {
   if (p.slabs <= 0) return 0;
   const bool has_da = p.sa >= 0;

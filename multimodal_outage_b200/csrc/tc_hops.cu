@@ -15,6 +15,7 @@
 // (two warps per TMEM lane quadrant, each draining 4 of the 8 slabs of an accumulator, loads issued in pairs).
 // Persistent: grid = min(tiles, SMs); each CTA walks tiles of 8 slabs.
 #include "tc.cuh"
+#include "hop_prep.cuh"
 #include "tc_hops.cuh"
 #include "gcn_fused.cuh"
 #include "tma_gemm.cuh"
@@ -189,67 +190,18 @@ __global__ void __launch_bounds__(TH_THREADS, 1) hops_tc_kernel(const __grid_con
   }
 }
 
-// image[m][kc][r][e] = Mop[r][kc*8+e] in bf16; Mop = X or X^T, X = A or A*A (fp32 product), zero padded.
-struct MatPrep {
-  const float* A[GWN_MAX_SUPPORTS];
-  int n, V, Kp;
-};
-__global__ void hop_mats_prep_kernel(MatPrep mp, bf16* __restrict__ out) {
+// ONE launch for the three support images (hop_prep.cuh): blocks [0, nb0) build the per-support images, [nb0, nb0 + nb1)
+// the stacked forward image, the rest the stacked transposed-hop image of the fused backward (nb2 == 0: no such kernel
+// instance for this shape).
+__global__ void __launch_bounds__(256) hop_mats_all_prep_kernel(MatPrep mp, int KT, BtGeom G, bf16* __restrict__ out0,
+                                                                bf16* __restrict__ out1, bf16* __restrict__ out2, int nb0, int nb1,
+                                                                int nb2) {
   pdl_wait();      // programmatic launch: the launch latency overlaps the predecessor (common.cuh)
   pdl_trigger();
-  // matrix index m = 4*s + variant; variant: 0 = A^T, 1 = (A^2)^T (forward), 2 = A, 3 = A^2 (backward)
-  const int per_mat = (mp.Kp / 8) * 128 * 8;
-  const long long total = (long long)mp.n * 4 * per_mat;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    int m = (int)(i / per_mat), rem = (int)(i % per_mat);
-    int kc = rem / 1024, r = (rem / 8) % 128, e = rem % 8;
-    int k = kc * 8 + e;
-    int s = m / 4, variant = m % 4;
-    float val = 0.f;
-    if (r < mp.V && k < mp.V) {
-      const float* A = mp.A[s];
-      const bool transpose = variant < 2, square = variant & 1;
-      int row = transpose ? k : r, col = transpose ? r : k;  // X[row][col]
-      if (!square) {
-        val = A[(long long)row * mp.V + col];
-      } else {
-        float acc = 0.f;
-        for (int t = 0; t < mp.V; ++t) acc = fmaf(A[(long long)row * mp.V + t], A[(long long)t * mp.V + col], acc);
-        val = acc;
-      }
-    }
-    out[i] = __float2bfloat16_rn(val);
-  }
-}
-
-// Stacked support image of the transposed ("T-form") fused forward (gcn_fused_t.cu): the B operand of
-//   h^T[(s,c), w] = sum_{j,v} U_j[(s,v), c] * Mt_j[v, w],   k = j*V + v,   Mt_0 = I, Mt_{2s+1} = A_s, Mt_{2s+2} = A_s A_s
-// K-major no-swizzle canonical layout [KT/8][NP][8] bf16 (rows = output node w), zero padded.
-__global__ void hop_mats_t_prep_kernel(MatPrep mp, int KT, int NP, bf16* __restrict__ out) {
-  pdl_wait();      // programmatic launch: the launch latency overlaps the predecessor (common.cuh)
-  pdl_trigger();
-  const int total = KT * NP;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int e = i & 7, w = (i >> 3) % NP, k = (i >> 3) / NP * 8 + e;
-    const int j = k / mp.V, v = k - j * mp.V;
-    float val = 0.f;
-    if (w < mp.V && j <= 2 * mp.n) {
-      if (j == 0) {
-        val = (v == w) ? 1.f : 0.f;
-      } else {
-        const float* A = mp.A[(j - 1) >> 1];
-        if (((j - 1) & 1) == 0) {
-          val = A[(long long)v * mp.V + w];
-        } else {
-          float acc = 0.f;
-          for (int t = 0; t < mp.V; ++t) acc = fmaf(A[(long long)v * mp.V + t], A[(long long)t * mp.V + w], acc);
-          val = acc;
-        }
-      }
-    }
-    out[i] = __float2bfloat16_rn(val);
-  }
+  const int b = (int)blockIdx.x;
+  if (b < nb0) hop_mats_prep_body(mp, out0, (long long)b * 256 + threadIdx.x, (long long)nb0 * 256);
+  else if (b < nb0 + nb1) hop_mats_t_prep_body(mp, KT, mp.Kp, out1, (long long)(b - nb0) * 256 + threadIdx.x, (long long)nb1 * 256);
+  else hop_mats_bt_prep_body(mp, G, out2, (long long)(b - nb0 - nb1) * 256 + threadIdx.x, (long long)nb2 * 256);
 }
 
 static int g_sm_count = 0;
@@ -313,16 +265,16 @@ extern "C" int gwn_hop_mats_prep(const float* const* supports, int n_supports, i
   MatPrep mp{};
   for (int i = 0; i < n_supports; ++i) mp.A[i] = supports[i];
   mp.n = n_supports; mp.V = V; mp.Kp = ((V + 15) / 16) * 16;
-  long long total = (long long)n_supports * 4 * (mp.Kp / 8) * 1024;
-  GWN_CUDA(launch_pdl(hop_mats_prep_kernel, dim3((unsigned)cdiv(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
-      mp, reinterpret_cast<bf16*>(out)));
-  GWN_LAUNCHED();
+  const long long total = (long long)n_supports * 4 * (mp.Kp / 8) * 1024;
   const int KT = hop_mats_t_kt(V, n_supports);
-  GWN_CUDA(launch_pdl(hop_mats_t_prep_kernel, dim3((unsigned)cdiv((long long)KT * mp.Kp, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
-      mp, KT, mp.Kp, reinterpret_cast<bf16*>(out) + total));
+  const BtGeom G(2 * n_supports, ((V + 7) / 8) * 8);
+  const int nb0 = (int)cdiv(total, 256), nb1 = (int)cdiv((long long)KT * mp.Kp, 256);
+  const int nb2 = (int)cdiv((long long)(G.KW / 8) * G.NTOT * 8, 256);
+  bf16* o = reinterpret_cast<bf16*>(out);
+  GWN_CUDA(launch_pdl(hop_mats_all_prep_kernel, dim3((unsigned)(nb0 + nb1 + nb2)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+                      mp, KT, G, o, o + total, o + total + (long long)KT * mp.Kp, nb0, nb1, nb2));
   GWN_LAUNCHED();
-  return launch_hop_mats_bt_prep(supports, n_supports, V, reinterpret_cast<bf16*>(out) + total + (long long)KT * mp.Kp,
-                                 reinterpret_cast<cudaStream_t>(stream));
+  return 0;
 }
 
 // Test/bench entry: one tensor-core hop  y[slot_out] = Mop[mat] * x[slot_in]  over a pitched bf16 buffer.
