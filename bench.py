@@ -422,7 +422,10 @@ class Trainer:
         else:
             opt = self.opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True, fused=True)
             sync = self.sync = BucketedGradAllReduce(model) if world > 1 else None
-        loss_fn = torch.nn.MSELoss()
+        # the training step's nn.MSELoss() (lit.py:24) as LitGWNet applies it: one forward and one backward launch
+        # (GWN_STOCK_LOSS=1: torch.nn.MSELoss, for A/B)
+        from multimodal_outage_b200 import ops as _ops
+        loss_fn = torch.nn.MSELoss() if os.environ.get('GWN_STOCK_LOSS') == '1' else _ops.mse_loss
 
         # distinct batches rotated through the timed loop (inputs differ every step; working set >> L2)
         R = self.R = n_batches

@@ -322,6 +322,13 @@ int gwn_dadj_big(const void* x, const void* g, float* dA, long long slabs, int V
 int gwn_gemm_test(const void* A, const void* B, float* C, int M, int N, int K, int a_mode, int b_mode,
                   int lda, int ldb, int bn, int splits, void* stream);
 
+/* ---- training loss: nn.MSELoss() of the reference's step (lit.py:24, applied at lit.py:41 and :50), fp32 ----
+ * gwn_mse_loss_fwd: loss[0] = mean((a - b)^2) over n elements, ONE launch (a cluster of eight CTAs, partial sums added in
+ * a fixed order through distributed shared memory: deterministic, no workspace, nothing to zero).
+ * gwn_mse_loss_bwd: d_a[i] = (a[i] - b[i]) * 2 * grad_loss[0] / n (every element written; grad_loss on the device). */
+int gwn_mse_loss_fwd(const float* a, const float* b, long long n, float* loss, void* stream);
+int gwn_mse_loss_bwd(const float* a, const float* b, const float* grad_loss, long long n, float* d_a, void* stream);
+
 /* ---- parameter re-layout (one launch instead of ~50 stack/permute/copy launches per step) ----
  * gwn_pack_params gathers the reference-shaped parameters (graph_wavenet.py:150-183: Conv2d weights [out,in,1,k] and
  * biases, fp32) into one flat fp32 buffer holding the kernels' packed layouts back to back (segment offsets from

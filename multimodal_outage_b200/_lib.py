@@ -129,6 +129,8 @@ SIGNATURES = {
     'gwn_hop_big': (_i, [vp, _i, _i, _i, vp, vp, vp, _ll, _i, vp]),
     'gwn_dadj_big': (_i, [vp, vp, vp, _ll, _i, vp]),
     'gwn_hop_ell': (_i, [vp, vp, _i, vp, vp, vp, _ll, _i, vp]),
+    'gwn_mse_loss_fwd': (_i, [vp, vp, _ll, vp, vp]),
+    'gwn_mse_loss_bwd': (_i, [vp, vp, vp, _ll, vp, vp]),
     'gwn_gemm_test': (_i, [vp, vp, vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, vp]),
     'gwn_pack_offsets': (_ll, [C.POINTER(PackCfg), C.POINTER(_ll)]),
     'gwn_pack_params': (_i, [C.POINTER(PackCfg), C.POINTER(PackPtrs), vp, vp]),

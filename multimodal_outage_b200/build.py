@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libgwn.so')
 STAMP = os.path.join(HERE, 'libgwn.so.stamp')
-SOURCES = ['api.cu', 'adp.cu', 'layer.cu', 'head.cu', 'peer.cu', 'tc_hops.cu', 'tc_wgrad.cu', 'tc_gemm.cu', 'tma_gemm.cu', 'head_tc.cu', 'gcn_fused.cu', 'gcn_fused_bwd.cu', 'gcn_fused_bwd_t.cu', 'start_tc.cu', 'pack.cu', 'gcn_fused_t.cu']
+SOURCES = ['api.cu', 'adp.cu', 'layer.cu', 'head.cu', 'peer.cu', 'tc_hops.cu', 'tc_wgrad.cu', 'tc_gemm.cu', 'tma_gemm.cu', 'head_tc.cu', 'gcn_fused.cu', 'gcn_fused_bwd.cu', 'gcn_fused_bwd_t.cu', 'start_tc.cu', 'pack.cu', 'gcn_fused_t.cu', 'loss.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr', '-Xptxas', '-v']
 TRACE = os.environ.get('GWN_TRACE') == '1'    # debug build: clock64 timeline hooks read GWN_*_TRACE (scripts/gpu_*_trace.py)

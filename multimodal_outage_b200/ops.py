@@ -860,6 +860,58 @@ class SkipHead(torch.autograd.Function):
         return (*outs[:6], None, *outs[6:])
 
 
+# =========================================================================== training loss (lit.py:24)
+@torch.library.custom_op('gwn::mse_loss_fwd', mutates_args=())
+def mse_loss_fwd(a: Tensor, b: Tensor) -> Tensor:
+    """mean((a - b)^2) of two fp32 CUDA tensors of the same shape as a 0-dim tensor, one launch."""
+    _req(a, torch.float32, 'input'); _req(b, torch.float32, 'target')
+    loss = torch.empty((), device=a.device, dtype=torch.float32)
+    with torch.cuda.device(a.device):
+        check(lib().gwn_mse_loss_fwd(_p(a), _p(b), a.numel(), _p(loss), _stream()), 'gwn_mse_loss_fwd')
+    return loss
+
+
+@mse_loss_fwd.register_fake
+def _(a, b):
+    return a.new_empty(())
+
+
+@torch.library.custom_op('gwn::mse_loss_bwd', mutates_args=())
+def mse_loss_bwd(a: Tensor, b: Tensor, grad_loss: Tensor) -> Tensor:
+    _req(a, torch.float32, 'input'); _req(b, torch.float32, 'target'); _req(grad_loss, torch.float32, 'grad_loss')
+    da = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        check(lib().gwn_mse_loss_bwd(_p(a), _p(b), _p(grad_loss), a.numel(), _p(da), _stream()), 'gwn_mse_loss_bwd')
+    return da
+
+
+@mse_loss_bwd.register_fake
+def _(a, b, grad_loss):
+    return torch.empty_like(a)
+
+
+class _MSELoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.save_for_backward(a, b)
+        return mse_loss_fwd(a, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        return mse_loss_bwd(a, b, g.contiguous()), None
+
+
+def mse_loss(input: Tensor, target: Tensor) -> Tensor:
+    """``nn.MSELoss()(input, target)`` (lit.py:24; reduction 'mean', gradient for `input` only) in one forward and one
+    backward launch for fp32 CUDA tensors; anything else (other dtypes, a target that needs a gradient, shapes that would
+    broadcast) goes to ``torch.nn.functional.mse_loss`` unchanged."""
+    if (input.is_cuda and target.is_cuda and input.dtype == torch.float32 and target.dtype == torch.float32 and
+            input.shape == target.shape and not target.requires_grad and 0 < input.numel() < 2 ** 31):
+        return _MSELoss.apply(input.contiguous(), target.contiguous())
+    return torch.nn.functional.mse_loss(input, target)
+
+
 # =========================================================================== nconv primitive (:60-66)
 @torch.library.custom_op('gwn::node_mix', mutates_args=())
 def node_mix(x: Tensor, A: Tensor, transpose_a: bool) -> Tensor:

@@ -1044,3 +1044,42 @@ def test_bf16_layer_op_big_graph_sparse_fixed_supports(V, N):
         errs = _layer_op_case(torch.bfloat16, BF16_TOL, V=V, N=N, Lin=5, dil=1, taps=2, n_sup=3, with_bn=with_bn, mask=mask,
                               seed=61, tensor_cores=True, sparse=True)
         print(f'bf16 big-graph layer op, sparse fixed supports, V={V}:', {k: f'{v:.1e}' for k, v in errs.items()})
+
+
+@pytest.mark.parametrize('shape', [(512, 12, 67, 1), (3, 5, 7), (4099,), (1,)])
+def test_fused_mse_loss_matches_torch(shape):
+    """`ops.mse_loss` (nn.MSELoss of the training step, lit.py:24: one cluster launch forward, one launch backward) against
+    torch.nn.functional.mse_loss: value and gradient to fp32 rounding, incl. sizes that are not multiples of four, an
+    unaligned view, a non-unit upstream gradient, and CUDA-graph replay (no workspace to re-zero)."""
+    from multimodal_outage_b200 import ops
+    torch.manual_seed(5)
+    a = torch.randn(*shape, device='cuda', requires_grad=True)
+    b = torch.randn(*shape, device='cuda')
+    l0 = torch.nn.functional.mse_loss(a, b)
+    (g0,) = torch.autograd.grad(l0 * 3.0, a)
+    l1 = ops.mse_loss(a, b)
+    (g1,) = torch.autograd.grad(l1 * 3.0, a)
+    assert abs(l1.item() - l0.item()) <= 2e-6 * abs(l0.item()) + 1e-12, (l1.item(), l0.item())
+    assert rel(g1, g0) < 1e-6
+    if len(shape) == 1 and shape[0] > 8:                       # 4-byte aligned views: the scalar path
+        av, bv = a.detach()[1:], b[1:]
+        assert abs(ops.mse_loss(av.contiguous(), bv.contiguous()).item() - torch.nn.functional.mse_loss(av, bv).item()) < 1e-5
+        from multimodal_outage_b200 import _lib
+        out = torch.empty((), device='cuda')
+        _lib.check(_lib.lib().gwn_mse_loss_fwd(av.data_ptr(), bv.data_ptr(), av.numel(), out.data_ptr(),
+                                               torch.cuda.current_stream().cuda_stream), 'mse')
+        assert abs(out.item() - torch.nn.functional.mse_loss(av, bv).item()) < 1e-5
+    if shape == (512, 12, 67, 1):
+        ad = a.detach()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            ops.mse_loss(ad, b)
+        torch.cuda.current_stream().wait_stream(s)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            lg = ops.mse_loss(ad, b)
+        for _ in range(3):
+            ad.add_(0.25)
+            graph.replay()
+            assert abs(lg.item() - torch.nn.functional.mse_loss(ad, b).item()) < 1e-5
