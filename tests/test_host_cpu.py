@@ -142,3 +142,23 @@ def test_module_moves_supports_and_accepts_literal_input_shape():
     assert m.supports[0].device.type == 'cpu'
     m2 = m.to(torch.float32)
     assert m2 is m and len(m.supports) == 1
+
+
+def test_training_loss_dispatch_on_cpu_tensors():
+    """`ops.mse_loss` (LitGWNet.loss_fn; nn.MSELoss of lit.py:24) only takes its CUDA path for same-shape fp32 CUDA tensors;
+    everything else is torch's own functional - bit-identical on CPU, broadcasting and double precision included."""
+    import torch
+    from multimodal_outage_b200 import ops
+    from multimodal_outage_b200.lit import LitGWNet
+    torch.manual_seed(0)
+    a = torch.randn(4, 3, 5, requires_grad=True)
+    b = torch.randn(4, 3, 5)
+    l0 = torch.nn.functional.mse_loss(a, b)
+    l1 = ops.mse_loss(a, b)
+    assert torch.equal(l0, l1)
+    (g0,) = torch.autograd.grad(l0, a)
+    (g1,) = torch.autograd.grad(l1, a)
+    assert torch.equal(g0, g1)
+    assert torch.equal(ops.mse_loss(a.double(), b.double()), torch.nn.functional.mse_loss(a.double(), b.double()))
+    lit = LitGWNet(torch.nn.Linear(2, 2))
+    assert torch.equal(lit.loss_fn(a, b), l0)
